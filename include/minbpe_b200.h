@@ -1,0 +1,192 @@
+/* minbpe_b200.h -- C ABI of the B200-native BPE engine (libminbpe_b200.so).
+ *
+ * Drop-in boundary for the train and encode hot paths of justinhj/minbpe-cc. The reference is a
+ * header-only C++ library with no FFI of its own; the seams this ABI sits behind are:
+ *   1. PairCount<Token>          code/include/PairCount.h:27-47   (both conflict-resolution implementations)
+ *   2. Tokenizer public methods  code/include/Tokenizer.h:489 train, :653 encode, :725 decode, :754 load, :875 save
+ *   3. on-disk formats           .model Tokenizer.h:881-891, .vocab :905-917, .enc examples/minbpe-cc.cpp:58-89
+ *
+ * Conventions: plain pointers and sizes, caller-owned buffers, int status (0 = ok, negative = error, see
+ * MBPE_E_*), nothing throws across the boundary, no torch types. Every compute entry point runs on a B200
+ * through hand-written sm_100a kernels; there is NO CPU fallback: without a CUDA device the compute calls
+ * return MBPE_E_NO_DEVICE.
+ *
+ * "stream" arguments are a cudaStream_t passed as void* (NULL = the legacy default stream), so a caller
+ * can time the kernels with its own events on its own stream.
+ */
+#ifndef MINBPE_B200_H
+#define MINBPE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MBPE_OK 0
+#define MBPE_E_INVALID (-1)    /* bad argument (null pointer, vocab_size < 256, token >= 256 inside a chunk, ...) */
+#define MBPE_E_NO_DEVICE (-2)  /* no usable CUDA device / extension built without kernels */
+#define MBPE_E_CUDA (-3)       /* a CUDA call failed; mbpe_last_error() has the text */
+#define MBPE_E_CAPACITY (-4)   /* caller buffer too small; required size is reported through the out parameter */
+#define MBPE_E_IO (-5)         /* file could not be opened / parsed */
+#define MBPE_E_REGEX (-6)      /* PCRE2 compile or match error */
+#define MBPE_E_EMPTY (-7)      /* nothing to do where the reference would assert/abort */
+
+/* Tokenizer::CONFLICT_RESOLUTION (Tokenizer.h:54-57) */
+#define MBPE_MODE_FIRST 0
+#define MBPE_MODE_LEXICAL 1
+
+/* how the merge loop is driven on the device (results are identical) */
+#define MBPE_ENGINE_STEPWISE 0   /* every phase of every merge is its own full-grid kernel launch */
+#define MBPE_ENGINE_PERSISTENT 1 /* one resident CTA runs small merges back to back; big merges, table growth and
+                                    candidate rebuilds go to full-grid kernels */
+
+const char *mbpe_version(void);
+const char *mbpe_last_error(void); /* thread-local text of the last error */
+int mbpe_device_count(void);       /* number of CUDA devices visible (0 on a CPU-only box) */
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 1. PairCount seam  (PairCount.h:27-47; PairCountInsertOrder :101-181, PairCountLexicalOrder :227-279)
+ *    Device-resident pair table + arg-max with both tie-breaks. Batched: one call = n create_or_modify_pair
+ *    calls applied in array order (insertion order = array order, PairCount.h:149).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct mbpe_paircount mbpe_paircount;
+int mbpe_paircount_create(int mode, int device, mbpe_paircount **out);
+void mbpe_paircount_destroy(mbpe_paircount *pc);
+/* create_or_modify_pair x n (PairCount.h:141 / :249) */
+int mbpe_paircount_add(mbpe_paircount *pc, const uint32_t *a, const uint32_t *b, const int32_t *delta, uint64_t n);
+/* get_top_pair_count (PairCount.h:159 / :262): *found = 0 when the table is empty */
+int mbpe_paircount_top(mbpe_paircount *pc, uint32_t *a, uint32_t *b, int32_t *count, int *found);
+/* get_pair (PairCount.h:123 / :239) */
+int mbpe_paircount_get(mbpe_paircount *pc, uint32_t a, uint32_t b, int32_t *count, int *found);
+/* get_count (PairCount.h:114 / :235) */
+int mbpe_paircount_size(mbpe_paircount *pc, uint64_t *n_pairs);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 2. Train merge loop  (Tokenizer.h:551-589: create_lists, calculate_freqs, loop of get_top_pair_count +
+ *    merge_chunks [+ recount in FIRST mode])
+ *
+ *    Input is the chunk list after pre-tokenisation: tokens = every chunk's bytes widened to u32 and
+ *    concatenated, chunk_off = n_chunks+1 offsets into tokens, chunk_weight = multiplicity of each chunk
+ *    (NULL = all 1). Chunks may be deduplicated provided unique chunks are in first-appearance order
+ *    (exact in both modes). Tokens inside chunks longer than one token must be < 256.
+ *
+ *    Output: merges_out[2*i], merges_out[2*i+1] = pair merged into id 256+i; counts_out (optional) = that
+ *    pair's count when chosen (the "had C occurrences" figure, Tokenizer.h:576); *n_merges_out <=
+ *    vocab_size-256 (FIRST stops early when no pair is left, Tokenizer.h:586-588; LEXICAL repeats the
+ *    smallest zero-count pair).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct mbpe_trainer mbpe_trainer;
+
+typedef struct mbpe_train_stats {
+    double gpu_ms;           /* CUDA-event time of the whole merge loop incl. index build */
+    double build_ms;         /* of which: initial histogram + occurrence index build */
+    uint64_t n_positions;    /* tokens uploaded */
+    uint64_t n_pairs;        /* distinct pairs ever inserted */
+    uint64_t table_slots;    /* final pair-table capacity */
+    uint64_t n_launches;     /* kernels launched by the run */
+    uint64_t n_big_merges;   /* merges done by full-grid kernels (persistent engine) */
+    uint64_t n_rebuilds;     /* candidate-list rebuilds */
+    uint64_t n_grows;        /* pair-table rehashes */
+    uint64_t rescan_bytes;   /* sum over merges of 12*T_m + 16*P_m: SURVEY 8(d) full-rescan algorithmic volume */
+} mbpe_train_stats;
+
+/* uploads the corpus to `device` (H2D) and keeps a pristine copy so run() can be repeated */
+int mbpe_trainer_create(const uint32_t *tokens, uint64_t n_tokens, const uint64_t *chunk_off, uint64_t n_chunks,
+                        const uint32_t *chunk_weight, int device, mbpe_trainer **out);
+/* runs the whole merge loop from the resident pristine copy; only the merge list crosses back (D2H) */
+int mbpe_trainer_run(mbpe_trainer *t, uint32_t vocab_size, int mode, int engine, void *stream, uint32_t *merges_out,
+                     int32_t *counts_out, uint32_t *n_merges_out, mbpe_train_stats *stats /* optional */);
+void mbpe_trainer_destroy(mbpe_trainer *t);
+
+/* one-shot with host buffers: create + run + destroy on device 0 */
+int mbpe_train(const uint32_t *tokens, uint64_t n_tokens, const uint64_t *chunk_off, uint64_t n_chunks,
+               const uint32_t *chunk_weight, uint32_t vocab_size, int mode, uint32_t *merges_out, int32_t *counts_out,
+               uint32_t *n_merges_out);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 3. Encode merge scan + decode  (Tokenizer.h:325-377 internal_internal_encode / internal_encode, :714-717
+ *    flatten; :725-751 decode; lookup table built as load() does, :833-837, later duplicate pairs overwrite)
+ *
+ *    Encode semantics are the reference's: per chunk, scan left to right replacing ANY known pair, repeat
+ *    until a pass merges nothing -- not rank-ordered BPE.
+ *    Chunks are byte ranges of `bytes`: chunk c = [chunk_off[c], chunk_off[c+1]).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct mbpe_encoder mbpe_encoder;
+int mbpe_encoder_create(const uint32_t *merges, uint32_t n_merges, int device, mbpe_encoder **out);
+void mbpe_encoder_destroy(mbpe_encoder *e);
+/* special tokens for decode (Tokenizer.h:733-736): ids + concatenated byte strings, off has n+1 entries */
+int mbpe_encoder_set_specials(mbpe_encoder *e, const uint32_t *ids, const uint8_t *bytes, const uint64_t *off,
+                              uint32_t n);
+
+/* host buffers in, host buffers out (H2D + kernels + D2H). out_tokens must hold n_bytes entries in the worst
+ * case; *n_out receives the count. out_off (optional) receives n_chunks+1 token offsets. */
+int mbpe_encode(mbpe_encoder *e, const uint8_t *bytes, uint64_t n_bytes, const uint64_t *chunk_off,
+                uint64_t n_chunks, uint32_t *out_tokens, uint64_t out_cap, uint64_t *n_out, uint64_t *out_off);
+/* everything already resident on the encoder's device (d_* are device pointers); *d_n_out is a device u64.
+ * d_chunk_off32 holds n_chunks+1 u32 offsets (a batch is < 4 GiB). */
+int mbpe_encode_device(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t n_bytes, const uint32_t *d_chunk_off32,
+                       uint64_t n_chunks, uint32_t *d_out_tokens, uint64_t out_cap, uint64_t *d_n_out,
+                       void *stream);
+/* bytes of device scratch mbpe_encode_device needs for a batch of that shape (kept inside the handle) */
+int mbpe_encode_reserve(mbpe_encoder *e, uint64_t n_bytes, uint64_t n_chunks);
+
+/* ids -> bytes. Call with out == NULL to size. Invalid ids are skipped (Tokenizer.h:739-742). */
+int mbpe_decode(mbpe_encoder *e, const uint32_t *ids, uint64_t n_ids, uint8_t *out, uint64_t out_cap,
+                uint64_t *n_out);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 4. Tokenizer mirror (host C++23 front end over 2. and 3.): same method set, argument meaning and error
+ *    behaviour as MinBpeCC::Tokenizer::Tokenizer. Regex pre-tokenisation (PCRE2), chunk dedup, special-token
+ *    splitting and file formats run on the host; the merge loop / merge scan / gather run on the GPU.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct mbpe_tokenizer mbpe_tokenizer;
+const char *mbpe_gpt2_split_pattern(void); /* Tokenizer.h:59 */
+const char *mbpe_gpt4_split_pattern(void); /* Tokenizer.h:60 */
+
+/* Tokenizer(pattern) (Tokenizer.h:391); pattern "" = no regex (encoder "basic") */
+int mbpe_tokenizer_create(const char *pattern, int device, mbpe_tokenizer **out);
+void mbpe_tokenizer_destroy(mbpe_tokenizer *t);
+/* set_special_tokens_from_file (Tokenizer.h:476): the file CONTENTS, "token id" per line */
+int mbpe_tokenizer_set_special_tokens(mbpe_tokenizer *t, const char *contents, uint64_t len);
+/* train (Tokenizer.h:489) */
+int mbpe_tokenizer_train(mbpe_tokenizer *t, const uint8_t *text, uint64_t len, int vocab_size, int mode, int verbose);
+/* save (Tokenizer.h:875): writes path and, if write_vocab, path + ".vocab" */
+int mbpe_tokenizer_save(mbpe_tokenizer *t, const char *path, int write_vocab);
+/* load (Tokenizer.h:754) */
+int mbpe_tokenizer_load(mbpe_tokenizer *t, const char *path, int verbose);
+/* encode (Tokenizer.h:653). Call with out == NULL to get the count. */
+int mbpe_tokenizer_encode(mbpe_tokenizer *t, const uint8_t *text, uint64_t len, uint32_t *out, uint64_t out_cap,
+                          uint64_t *n_out);
+/* decode (Tokenizer.h:725). Call with out == NULL to get the size. */
+int mbpe_tokenizer_decode(mbpe_tokenizer *t, const uint32_t *ids, uint64_t n, uint8_t *out, uint64_t out_cap,
+                          uint64_t *n_out);
+/* introspection used by the parity tests */
+int mbpe_tokenizer_get_merges(mbpe_tokenizer *t, uint32_t *merges_out, uint32_t cap_pairs, uint32_t *n_merges);
+int mbpe_tokenizer_last_train_stats(mbpe_tokenizer *t, mbpe_train_stats *stats, double *split_s, double *dedup_s,
+                                    uint64_t *n_chunks, uint64_t *n_unique);
+void mbpe_tokenizer_set_engine(mbpe_tokenizer *t, int engine);
+void mbpe_tokenizer_set_threads(mbpe_tokenizer *t, int n_threads); /* host pre-tokenisation threads, 0 = all */
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 5. Host-only pieces exposed for CPU-side tests (no GPU needed)
+ * ---------------------------------------------------------------------------------------------------------- */
+/* regex pre-tokenisation (Tokenizer.h:500-544), multi-threaded with regex-safe cut points; writes chunk
+ * [start,end) pairs. Call with starts == NULL to count. */
+int mbpe_split(const char *pattern, const uint8_t *text, uint64_t len, int n_threads, uint64_t *starts,
+               uint64_t *ends, uint64_t cap, uint64_t *n_chunks);
+/* chunk dedup in first-appearance order + byte->token widening (Tokenizer.h:85-100). Sizing: n_unique <=
+ * n_chunks, n_tokens <= sum of lengths. */
+int mbpe_dedup(const uint8_t *text, const uint64_t *starts, const uint64_t *ends, uint64_t n_chunks,
+               uint32_t *tokens_out, uint64_t *n_tokens, uint64_t *off_out, uint32_t *weight_out, uint64_t *n_unique);
+/* .model / .vocab writer given a merge list (Tokenizer.h:875-926) */
+int mbpe_write_model(const char *path, const char *pattern, const char *special_contents, uint64_t special_len,
+                     const uint32_t *merges, uint32_t n_merges, int write_vocab);
+/* deterministic synthetic Zipfian UTF-8 corpus (SURVEY 8(d) input 3): fills out[0..n) */
+int mbpe_synth_corpus(uint64_t seed, uint8_t *out, uint64_t n, int n_threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

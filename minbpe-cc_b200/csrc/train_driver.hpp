@@ -1,0 +1,213 @@
+// train_driver.hpp -- host-side orchestration of the train merge loop (Tokenizer.h:551-589), written once
+// against a small backend interface. The product backend (train_cuda.cu) launches the phases as sm_100a
+// kernels; tests/emu/ has a sequential host backend used ONLY by the CPU unit tests to check the phase
+// logic and this orchestration against the oracle. There is no CPU execution path in the product library.
+//
+// Backend interface:
+//   void *alloc(size_t bytes);  void release(void *p);
+//   void upload(void *dst, const void *src, size_t n);  void download(void *dst, const void *src, size_t n);  // sync
+//   template <class F> void par(const F &f, uint64_t n_items);   // f(tid, nth) over enough threads for n_items
+//   template <class F> void one(const F &f);                     // f() on one thread
+//   void init_count(const Ctx &c);                                // calculate_freqs: fill the pair table
+//   void persistent(const Ctx &c);                                // persistent_program until status != ST_RUN
+//   uint64_t launches() const;
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#include "train_phases.cuh"
+
+namespace mbpe {
+
+struct TrainConfig {
+    uint32_t vocab_size;
+    int mode;            // 0 first, 1 lexical
+    int engine;          // 0 stepwise, 1 persistent
+    uint32_t big_limit;  // persistent CTA yields merges with longer segments to the grid
+    uint32_t cand_want;  // candidate list target size at a rebuild
+    uint32_t init_slots; // initial pair-table capacity (power of two), 0 = sized for 65536 byte pairs
+};
+
+struct TrainOutcome {
+    uint32_t n_merges;   // merges recorded on the device before stop
+    int32_t final_status;
+    uint64_t min_key_ever;
+    uint64_t n_pairs, table_slots, n_big, n_rebuilds, n_grows, rescan_bytes;
+};
+
+inline uint32_t next_pow2_u32(uint64_t v) {
+    uint32_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+template <class BE>
+class TrainLoop {
+  public:
+    TrainLoop(BE &be) : be_(be) { memset(&c_, 0, sizeof c_); }
+    ~TrainLoop() { free_all(); }
+
+    // d_tokens/d_off/d_weight: resident inputs (weight may be null). h_merges: 2*(vocab-256), h_counts: vocab-256.
+    int run(const uint32_t *d_tokens, const uint64_t *d_off, const uint32_t *d_weight, uint64_t n_tokens,
+            uint64_t n_chunks, const TrainConfig &cfg, uint32_t *h_merges, int32_t *h_counts, TrainOutcome *out) {
+        const uint32_t n_target = cfg.vocab_size - 256;
+        memset(out, 0, sizeof *out);
+        if (n_target == 0) return 0;
+        c_.n_pos = (uint32_t)n_tokens;
+        const uint64_t np = n_tokens ? n_tokens : 1;
+        c_.node = (Node *)be_.alloc(np * sizeof(Node));
+        c_.arena_cap = (uint32_t)(3 * np + 16);
+        c_.occ = (uint32_t *)be_.alloc((uint64_t)c_.arena_cap * 4);
+        c_.hit = (uint32_t *)be_.alloc((np + 16) * 4);
+        c_.rec_slot = (uint32_t *)be_.alloc((np + 16) * 4);
+        c_.rec_pos = (uint32_t *)be_.alloc((np + 16) * 4);
+        c_.newp = (uint32_t *)be_.alloc((np + 16) * 4);
+        c_.ctl = (Ctl *)be_.alloc(sizeof(Ctl));
+        c_.merges_out = (uint32_t *)be_.alloc((uint64_t)n_target * 8);
+        c_.counts_out = (int32_t *)be_.alloc((uint64_t)n_target * 4);
+        // initial pairs are byte pairs (tokens < 256 inside multi-token chunks): at most 65536 distinct
+        uint64_t init_pairs = n_tokens < 65536 ? n_tokens : 65536;
+        alloc_table(cfg.init_slots ? next_pow2_u32(cfg.init_slots) : next_pow2_u32(4 * init_pairs + 1024));
+
+        Ctl h;
+        memset(&h, 0, sizeof h);
+        h.n_target = n_target;
+        h.mode = cfg.mode;
+        h.status = ST_NEED_REBUILD;
+        h.cmax = CMAX_NONE;
+        h.best_tie = ~0ull;
+        h.theta = 1;
+        h.big_limit = cfg.big_limit;
+        h.min_key_ever = ~0ull;
+        h.live_tokens = n_tokens;
+        be_.upload(c_.ctl, &h, sizeof h);
+
+        be_.par(PhInitNodes{c_, d_tokens, d_off, d_weight, n_chunks}, n_tokens);
+        be_.init_count(c_);
+        be_.par(PhInitAlloc{c_}, (uint64_t)c_.cap_mask + 1);
+        be_.par(PhInitFill{c_}, n_tokens);
+
+        for (;;) {
+            be_.download(&h, c_.ctl, sizeof h);
+            if (h.status == ST_DONE || h.status == ST_EXHAUSTED) break;
+            switch (h.status) {
+            case ST_NEED_REBUILD:
+                rebuild(cfg);
+                break;
+            case ST_NEED_GROW:
+                grow(h);
+                rebuild(cfg);
+                break;
+            case ST_BIG_MERGE:
+                be_.one(PhTakeBig{c_});
+                apply_grid(h.seg_len);
+                select_grid(1, h.n_cand);
+                out->n_big++;
+                break;
+            case ST_RUN:
+                if (cfg.engine == 1) {
+                    be_.persistent(c_);
+                } else if (!h.selected) {
+                    select_grid(0, h.n_cand);
+                } else {
+                    apply_grid(h.seg_len);
+                    select_grid(0, h.n_cand);
+                }
+                break;
+            default:
+                return -1;
+            }
+        }
+        out->n_merges = h.step;
+        out->final_status = h.status;
+        out->min_key_ever = h.min_key_ever;
+        out->n_pairs = h.n_pairs;
+        out->table_slots = (uint64_t)c_.cap_mask + 1;
+        out->n_rebuilds = n_rebuilds_;
+        out->n_grows = n_grows_;
+        out->rescan_bytes = h.rescan_bytes;
+        if (h.step) {
+            be_.download(h_merges, c_.merges_out, (uint64_t)h.step * 8);
+            if (h_counts) be_.download(h_counts, c_.counts_out, (uint64_t)h.step * 4);
+        }
+        free_all();
+        return 0;
+    }
+
+  private:
+    void alloc_table(uint32_t cap) {
+        c_.slot = (Slot *)be_.alloc((uint64_t)cap * sizeof(Slot));
+        c_.cap_mask = cap - 1;
+        c_.cand_cap = cap / 2 + 64;
+        c_.cand = (uint32_t *)be_.alloc((uint64_t)c_.cand_cap * 4);
+        c_.fix = (uint32_t *)be_.alloc((uint64_t)c_.cand_cap * 4);
+        be_.par(PhClearSlots{c_.slot, cap}, cap);
+    }
+    void select_grid(int persistent, uint32_t n_cand) {
+        be_.par(PhSelMax{c_}, n_cand);
+        be_.par(PhSelTie{c_}, n_cand);
+        be_.one(PhSelCheck{c_});
+        be_.par(PhSelFixScan{c_}, n_cand);
+        be_.par(PhSelFixTie{c_}, n_cand);
+        be_.par(PhSelPick{c_}, n_cand);
+        be_.one(PhSelCommit{c_, persistent});
+    }
+    void apply_grid(uint32_t seg_len) {
+        be_.par(PhHits{c_}, seg_len);
+        be_.par(PhMutate{c_}, seg_len);
+        be_.par(PhSegAlloc{c_}, 2ull * seg_len);
+        be_.par(PhSegFill{c_}, 2ull * seg_len);
+        be_.one(PhFin{c_});
+    }
+    void rebuild(const TrainConfig &cfg) {
+        uint64_t cap = (uint64_t)c_.cap_mask + 1;
+        be_.one(PhRebuildReset{c_});
+        be_.par(PhRebuildHist{c_}, cap);
+        be_.one(PhRebuildTheta{c_, cfg.cand_want});
+        be_.par(PhRebuildCollect{c_}, cap);
+        be_.one(PhSelReset{c_});
+        n_rebuilds_++;
+    }
+    void grow(const Ctl &h) {
+        Slot *old = c_.slot;
+        uint32_t old_cap = c_.cap_mask + 1;
+        uint64_t need = (uint64_t)h.n_pairs + 2ull * h.seg_len + 64; // same bound as phase_sel_commit
+        uint64_t cap = (uint64_t)old_cap * 4;
+        while (need * 2 > cap) cap *= 2;
+        be_.release(c_.cand);
+        be_.release(c_.fix);
+        alloc_table((uint32_t)cap);
+        be_.par(PhRehash{c_, old, old_cap}, old_cap);
+        be_.release(old);
+        n_grows_++;
+    }
+    void free_all() {
+        void *ps[] = {c_.node, c_.occ, c_.hit, c_.rec_slot, c_.rec_pos, c_.newp, c_.ctl,
+                      c_.merges_out, c_.counts_out, c_.slot, c_.cand, c_.fix};
+        for (void *p : ps)
+            if (p) be_.release(p);
+        memset(&c_, 0, sizeof c_);
+    }
+
+    BE &be_;
+    Ctx c_;
+    uint64_t n_rebuilds_ = 0, n_grows_ = 0;
+};
+
+// Host epilogue shared by every caller: turn the device outcome into the reference's observable merge list.
+//  FIRST:   stop where the table ran empty (Tokenizer.h:586-588).
+//  LEXICAL: entries are never erased, so once the best count is 0 the smallest pair ever inserted is
+//           returned for every remaining id; no pair ever inserted => loop breaks at once.
+inline uint32_t finish_merges(const TrainOutcome &o, uint32_t vocab_size, int mode, uint32_t *merges, int32_t *counts) {
+    uint32_t n_target = vocab_size - 256, n = o.n_merges;
+    if (mode == 1 && n < n_target && o.min_key_ever != ~0ull) {
+        for (; n < n_target; n++) {
+            merges[2 * n] = (uint32_t)(o.min_key_ever >> 32);
+            merges[2 * n + 1] = (uint32_t)o.min_key_ever;
+            if (counts) counts[n] = 0;
+        }
+    }
+    return n;
+}
+
+} // namespace mbpe

@@ -1,0 +1,791 @@
+// train_phases.cuh -- the BPE train merge loop as barrier-separated phases.
+//
+// Replaces (file:line under /root/reference/code/include):
+//   PairCount<T> + both implementations          PairCount.h:27-47, :101-181, :227-279   -> pair table (Slot[])
+//   calculate_freqs                              Tokenizer.h:127-146                     -> initial histogram (train_kernels.cu)
+//   get_top_pair_count + comparators             PairCount.h:66-74, :159, :195-207, :262 -> sel_* phases
+//   merge / merge_incremental / merge_chunks     Tokenizer.h:162-320                     -> hits / mutate / seg_* phases
+//   train driver loop                            Tokenizer.h:557-589                     -> one "step" = sel .. fin
+//
+// Design (B200-first, not a translation):
+//   * The deduplicated corpus lives in HBM as one 16-byte Node per token position {tok, nxt, prv, weight};
+//     positions never move, merged-away tokens are unlinked (no compaction, no rescans).
+//   * The pair table is open-addressed, one 32-byte Slot per pair (one DRAM sector per probe hit).
+//   * Every adjacent-pair occurrence of a pair (p, q) comes into existence in the merge step that creates
+//     max(p, q) (or is in the initial text), and after that the set only shrinks. So each pair owns ONE
+//     contiguous segment of an occurrence arena, written once; stale entries are filtered on use.
+//   * arg-max runs over a small candidate list (all pairs with count >= theta). The best count never
+//     increases and new pairs never exceed it, so the list stays complete until its best falls below theta;
+//     then a full-grid scan rebuilds it with a lower theta.
+//   * first-occurrence tie-break: Slot.first = min live position of the pair (flat position order ==
+//     (first-appearance rank of the chunk, offset in chunk) order == insertion order of the reference's fresh
+//     recount). It is invalidated when that occurrence dies and recomputed from the pair's segment
+//     only when the pair ties for the best count.
+//
+// Each phase is a function of (ctx, tid, nth): thread `tid` of `nth` handles items tid, tid+nth, ...
+// Phases only communicate through memory + atomics, and a barrier separates consecutive phases. The same
+// code is driven three ways:  full-grid kernels (one launch per phase), one persistent CTA with
+// __syncthreads() between phases, and -- in tests only -- a sequential host loop.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define MB_HD __host__ __device__ __forceinline__
+#else
+#define MB_HD inline
+#endif
+
+namespace mbpe {
+
+constexpr uint32_t NIL = 0xFFFFFFFFu;      // no neighbour
+constexpr uint32_t DEAD = 0xFFFFFFFFu;     // Node.tok of an unlinked position
+constexpr uint64_t EMPTY_KEY = ~0ull;      // free slot
+constexpr uint32_t NO_FIRST = 0xFFFFFFFFu; // Slot.first unknown
+constexpr int32_t CMAX_NONE = INT32_MIN;
+
+enum Status : int32_t {
+    ST_RUN = 0,          // keep going
+    ST_DONE = 1,         // n_target merges done
+    ST_EXHAUSTED = 2,    // best count <= 0: FIRST stops (Tokenizer.h:586-588), LEXICAL replays
+    ST_NEED_REBUILD = 3, // candidate list no longer holds the best pair
+    ST_NEED_GROW = 4,    // pair table too full for the next step
+    ST_BIG_MERGE = 5,    // selected pair has more occurrences than one CTA should walk
+};
+
+struct Node {
+    uint32_t tok, nxt, prv, wt;
+};
+static_assert(sizeof(Node) == 16, "Node is one 16-byte vector load");
+
+struct Slot {
+    uint64_t key;   // (a << 32) | b; numeric order == lexicographic pair order
+    int32_t cnt;    // weighted count (PairCount.h:57 'int count')
+    uint32_t len;   // occurrences recorded at creation (segment length)
+    uint32_t first; // min live position, or NO_FIRST
+    uint32_t seg;   // segment start in the arena
+    uint32_t fill;  // segment fill cursor
+    uint32_t pad;
+};
+static_assert(sizeof(Slot) == 32, "Slot is one 32-byte sector");
+
+struct Ctl {
+    // loop state
+    uint32_t step;     // merges recorded so far
+    uint32_t n_target; // vocab_size - 256
+    int32_t mode;      // MBPE_MODE_*
+    int32_t status;
+    // selection
+    int32_t cmax;
+    uint32_t n_fix;
+    uint64_t best_tie;
+    uint32_t best_slot;
+    uint32_t a, b, new_id;
+    uint32_t seg, seg_len;
+    int32_t theta;
+    uint32_t n_live; // candidates still >= theta, counted by sel_max
+    // per-step lists
+    uint32_t n_hit, n_rec, n_newp;
+    uint32_t n_cand;
+    uint32_t selected; // 1 between sel_commit and fin: (a, b, seg...) of the current step are valid
+    // table / arena
+    uint32_t n_pairs;
+    uint32_t arena_cursor;
+    uint32_t big_limit; // segment length above which the persistent CTA yields
+    uint32_t pad0;
+    uint64_t min_key_ever;
+    // rebuild scratch
+    int32_t gmax;
+    uint32_t n_positive;
+    uint32_t hist[32]; // pairs per floor(log2(count))
+    // accounting (SURVEY 8(d) rescan-volume figure)
+    uint64_t live_tokens;
+    uint64_t rescan_bytes;
+    uint64_t n_small_steps;
+};
+
+struct Ctx {
+    Node *node;
+    uint32_t n_pos;
+    Slot *slot;
+    uint32_t cap_mask; // slots - 1
+    uint32_t *occ;     // occurrence arena
+    uint32_t arena_cap;
+    uint32_t *hit;      // positions of this step's merges
+    uint32_t *rec_slot; // this step's new-occurrence records
+    uint32_t *rec_pos;
+    uint32_t *newp;     // slots created this step
+    uint32_t *cand;     // candidate slot list (capacity cand_cap = slots / 2 >= number of pairs)
+    uint32_t *fix;      // FIRST mode: tied candidates whose first position must be recomputed (cand_cap)
+    uint32_t cand_cap;
+    Ctl *ctl;
+    uint32_t *merges_out; // device copy, 2 * n_target
+    int32_t *counts_out;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// atomics: CUDA intrinsics on the device; plain sequential updates under the host test driver
+// ---------------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+#define MB_ON_DEVICE 1
+#else
+#define MB_ON_DEVICE 0
+#endif
+
+MB_HD uint32_t a_add(uint32_t *p, uint32_t v) {
+#if MB_ON_DEVICE
+    return atomicAdd(p, v);
+#else
+    uint32_t o = *p;
+    *p = o + v;
+    return o;
+#endif
+}
+MB_HD int32_t a_add(int32_t *p, int32_t v) {
+#if MB_ON_DEVICE
+    return atomicAdd(p, v);
+#else
+    int32_t o = *p;
+    *p = o + v;
+    return o;
+#endif
+}
+MB_HD uint64_t a_add(uint64_t *p, uint64_t v) {
+#if MB_ON_DEVICE
+    return (uint64_t)atomicAdd((unsigned long long *)p, (unsigned long long)v);
+#else
+    uint64_t o = *p;
+    *p = o + v;
+    return o;
+#endif
+}
+MB_HD void a_min(uint32_t *p, uint32_t v) {
+#if MB_ON_DEVICE
+    atomicMin(p, v);
+#else
+    if (v < *p) *p = v;
+#endif
+}
+MB_HD void a_min(uint64_t *p, uint64_t v) {
+#if MB_ON_DEVICE
+    atomicMin((unsigned long long *)p, (unsigned long long)v);
+#else
+    if (v < *p) *p = v;
+#endif
+}
+MB_HD void a_max(int32_t *p, int32_t v) {
+#if MB_ON_DEVICE
+    atomicMax(p, v);
+#else
+    if (v > *p) *p = v;
+#endif
+}
+MB_HD uint64_t a_cas(uint64_t *p, uint64_t expect, uint64_t v) {
+#if MB_ON_DEVICE
+    return (uint64_t)atomicCAS((unsigned long long *)p, (unsigned long long)expect, (unsigned long long)v);
+#else
+    uint64_t o = *p;
+    if (o == expect) *p = v;
+    return o;
+#endif
+}
+// loads of words that other threads update with atomics in an earlier phase: go to L2, not a stale L1 line
+template <class T>
+MB_HD T ld_l2(const T *p) {
+#if MB_ON_DEVICE
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+MB_HD Node ld_node(const Node *p) {
+#if MB_ON_DEVICE
+    uint4 v = __ldcg(reinterpret_cast<const uint4 *>(p));
+    Node n;
+    n.tok = v.x;
+    n.nxt = v.y;
+    n.prv = v.z;
+    n.wt = v.w;
+    return n;
+#else
+    return *p;
+#endif
+}
+
+MB_HD uint64_t pair_key(uint32_t a, uint32_t b) { return ((uint64_t)a << 32) | b; }
+MB_HD uint32_t hash_key(uint64_t k) {
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdULL;
+    k ^= k >> 29;
+    k *= 0xc4ceb9fe1a85ec53ULL;
+    k ^= k >> 32;
+    return (uint32_t)k;
+}
+
+// find an existing key (exact counts guarantee presence for every decrement)
+MB_HD uint32_t slot_find(const Ctx &c, uint64_t key) {
+    uint32_t s = hash_key(key) & c.cap_mask;
+    for (;;) {
+        uint64_t k = ld_l2(&c.slot[s].key);
+        if (k == key) return s;
+        if (k == EMPTY_KEY) return NIL;
+        s = (s + 1) & c.cap_mask;
+    }
+}
+// find or claim. *created is set for the claiming thread only
+MB_HD uint32_t slot_upsert(const Ctx &c, uint64_t key, bool *created) {
+    uint32_t s = hash_key(key) & c.cap_mask;
+    *created = false;
+    for (;;) {
+        uint64_t k = ld_l2(&c.slot[s].key);
+        if (k == key) return s;
+        if (k == EMPTY_KEY) {
+            uint64_t old = a_cas(&c.slot[s].key, EMPTY_KEY, key);
+            if (old == EMPTY_KEY) {
+                *created = true;
+                return s;
+            }
+            if (old == key) return s;
+        }
+        s = (s + 1) & c.cap_mask;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// count updates
+// ---------------------------------------------------------------------------------------------------------
+#define MB_G(field) ld_l2(&g->field) /* Ctl words are updated by atomics / other threads: always read at L2 */
+
+// -(p,q) x w for the occurrence whose first token sits at position pairpos
+MB_HD void pair_dec(const Ctx &c, int32_t mode, uint32_t p, uint32_t q, uint32_t w, uint32_t pairpos) {
+    uint32_t s = slot_find(c, pair_key(p, q));
+    if (s == NIL) return; // reference: decrement only if present (Tokenizer.h:250-256); always present
+    a_add(&c.slot[s].cnt, -(int32_t)w);
+    if (mode == 0 && ld_l2(&c.slot[s].first) == pairpos) c.slot[s].first = NO_FIRST;
+}
+// +(p,q) x w for a new occurrence at pairpos; q or p is this step's new id, so the pair is born in this step
+MB_HD void pair_inc(const Ctx &c, int32_t mode, uint32_t p, uint32_t q, uint32_t w, uint32_t pairpos) {
+    bool created;
+    uint64_t key = pair_key(p, q);
+    uint32_t s = slot_upsert(c, key, &created);
+    if (created) {
+        c.newp[a_add(&c.ctl->n_newp, 1u)] = s;
+        a_add(&c.ctl->n_pairs, 1u);
+        a_min(&c.ctl->min_key_ever, key);
+    }
+    // cnt (low word) += w and len (high word) += 1 in one 64-bit atomic: both only grow during the birth step
+    a_add(reinterpret_cast<uint64_t *>(&c.slot[s].cnt), ((uint64_t)1 << 32) | (uint64_t)w);
+    if (mode == 0) a_min(&c.slot[s].first, pairpos);
+    uint32_t r = a_add(&c.ctl->n_rec, 1u);
+    c.rec_slot[r] = s;
+    c.rec_pos[r] = pairpos;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// selection: get_top_pair_count. Every sel_* phase is a no-op unless status == ST_RUN and nothing is selected
+// yet, so a driver may enqueue them without looking at the status first.
+// ---------------------------------------------------------------------------------------------------------
+MB_HD bool selecting(const Ctl *g) { return MB_G(status) == ST_RUN && MB_G(selected) == 0; }
+
+// sel_max: best count among candidates (+ how many are still >= theta)
+MB_HD void phase_sel_max(const Ctx &c, uint32_t tid, uint32_t nth) {
+    Ctl *g = c.ctl;
+    if (!selecting(g)) return;
+    uint32_t n = MB_G(n_cand);
+    int32_t theta = MB_G(theta), best = CMAX_NONE;
+    uint32_t live = 0;
+    for (uint32_t i = tid; i < n; i += nth) {
+        int32_t v = ld_l2(&c.slot[ld_l2(&c.cand[i])].cnt);
+        if (v > best) best = v;
+        live += (v >= theta);
+    }
+    if (best != CMAX_NONE) a_max(&g->cmax, best);
+    if (live) a_add(&g->n_live, live);
+}
+// sel_tie: among candidates holding the best count, the smallest tie-break key. FIRST-mode pairs whose first
+// position is unknown go to the fix list instead.
+MB_HD void phase_sel_tie(const Ctx &c, uint32_t tid, uint32_t nth) {
+    Ctl *g = c.ctl;
+    if (!selecting(g)) return;
+    int32_t cmax = MB_G(cmax);
+    if (cmax == CMAX_NONE || cmax < MB_G(theta)) return; // sel_check turns this into ST_NEED_REBUILD
+    uint32_t n = MB_G(n_cand);
+    int32_t mode = MB_G(mode);
+    for (uint32_t i = tid; i < n; i += nth) {
+        uint32_t s = ld_l2(&c.cand[i]);
+        if (ld_l2(&c.slot[s].cnt) != cmax) continue;
+        if (mode == 1) {
+            a_min(&g->best_tie, ld_l2(&c.slot[s].key)); // PairCount.h:195-207
+        } else {
+            uint32_t f = ld_l2(&c.slot[s].first);
+            if (f == NO_FIRST)
+                c.fix[a_add(&g->n_fix, 1u)] = s;
+            else
+                a_min(&g->best_tie, (uint64_t)f); // PairCount.h:66-74 via SURVEY H1
+        }
+    }
+}
+// sel_check (one thread, after sel_tie): candidate list exhausted?
+MB_HD void phase_sel_check(const Ctx &c) {
+    Ctl *g = c.ctl;
+    if (!selecting(g)) return;
+    int32_t cmax = MB_G(cmax);
+    if (cmax == CMAX_NONE || cmax < MB_G(theta)) g->status = ST_NEED_REBUILD;
+}
+// sel_fix_scan: recompute Slot.first of every pair on the fix list from its segment (live occurrences only).
+// Short segments: one thread per pair. Long segments: all threads stride over the segment together.
+MB_HD void fix_scan_range(const Ctx &c, uint32_t s, uint32_t k0, uint32_t stride) {
+    uint64_t key = ld_l2(&c.slot[s].key);
+    uint32_t p = (uint32_t)(key >> 32), q = (uint32_t)key;
+    uint32_t seg = ld_l2(&c.slot[s].seg), len = ld_l2(&c.slot[s].len);
+    uint32_t best = NO_FIRST;
+    for (uint32_t k = k0; k < len; k += stride) {
+        uint32_t pos = ld_l2(&c.occ[seg + k]);
+        if (pos >= best) continue;
+        Node n0 = ld_node(&c.node[pos]);
+        if (n0.tok != p || n0.nxt == NIL) continue;
+        if (ld_l2(&c.node[n0.nxt].tok) != q) continue;
+        best = pos;
+    }
+    if (best != NO_FIRST) a_min(&c.slot[s].first, best);
+}
+constexpr uint32_t FIX_SOLO_LEN = 128;
+MB_HD void phase_sel_fix_scan(const Ctx &c, uint32_t tid, uint32_t nth) {
+    Ctl *g = c.ctl;
+    if (!selecting(g)) return;
+    uint32_t nf = MB_G(n_fix);
+    for (uint32_t f = tid; f < nf; f += nth) {
+        uint32_t s = ld_l2(&c.fix[f]);
+        if (ld_l2(&c.slot[s].len) <= FIX_SOLO_LEN) fix_scan_range(c, s, 0, 1);
+    }
+    for (uint32_t f = 0; f < nf; f++) {
+        uint32_t s = ld_l2(&c.fix[f]);
+        if (ld_l2(&c.slot[s].len) > FIX_SOLO_LEN) fix_scan_range(c, s, tid, nth);
+    }
+}
+MB_HD void phase_sel_fix_tie(const Ctx &c, uint32_t tid, uint32_t nth) {
+    Ctl *g = c.ctl;
+    if (!selecting(g)) return;
+    uint32_t nf = MB_G(n_fix);
+    for (uint32_t f = tid; f < nf; f += nth) a_min(&g->best_tie, (uint64_t)ld_l2(&c.slot[ld_l2(&c.fix[f])].first));
+}
+// sel_pick: the unique candidate matching (cmax, best_tie)
+MB_HD void phase_sel_pick(const Ctx &c, uint32_t tid, uint32_t nth) {
+    Ctl *g = c.ctl;
+    if (!selecting(g)) return;
+    uint32_t n = MB_G(n_cand);
+    int32_t cmax = MB_G(cmax), mode = MB_G(mode);
+    uint64_t tie = MB_G(best_tie);
+    for (uint32_t i = tid; i < n; i += nth) {
+        uint32_t s = ld_l2(&c.cand[i]);
+        if (ld_l2(&c.slot[s].cnt) != cmax) continue;
+        uint64_t t = mode == 1 ? ld_l2(&c.slot[s].key) : (uint64_t)ld_l2(&c.slot[s].first);
+        if (t == tie) g->best_slot = s;
+    }
+}
+// sel_commit (one thread): record the merge (Tokenizer.h:578) and decide how the step is executed.
+// persistent != 0: called from the resident CTA, which hands segments longer than big_limit to the grid.
+MB_HD void phase_sel_commit(const Ctx &c, int persistent) {
+    Ctl *g = c.ctl;
+    if (!selecting(g)) return;
+    uint32_t s = MB_G(best_slot);
+    uint64_t key = ld_l2(&c.slot[s].key);
+    uint32_t step = MB_G(step), seg_len = ld_l2(&c.slot[s].len);
+    g->seg_len = seg_len;
+    // every occurrence can create two pairs; keep the load factor under 1/2 after the step
+    uint64_t need = (uint64_t)MB_G(n_pairs) + 2ull * seg_len + 64;
+    if (need * 2 > (uint64_t)c.cap_mask + 1) {
+        g->status = ST_NEED_GROW; // slots move: the step is re-selected after the rehash
+        return;
+    }
+    g->a = (uint32_t)(key >> 32);
+    g->b = (uint32_t)key;
+    g->new_id = 256 + step;
+    g->seg = ld_l2(&c.slot[s].seg);
+    g->seg_len = seg_len;
+    c.merges_out[2 * step] = (uint32_t)(key >> 32);
+    c.merges_out[2 * step + 1] = (uint32_t)key;
+    c.counts_out[step] = MB_G(cmax);
+    g->selected = 1;
+    if (persistent && seg_len > MB_G(big_limit)) g->status = ST_BIG_MERGE;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// hits: find the live occurrences of (a, b), decide the count deltas from the OLD neighbourhood (read-only on
+// the corpus), and record what to rewrite. Net effect == merge_incremental's (Tokenizer.h:239-280): exact
+// counts of the rewritten text; -(a,b) itself is folded into "count(a,b) := 0" in phase_fin.
+// ---------------------------------------------------------------------------------------------------------
+MB_HD void phase_hits(const Ctx &c, uint32_t tid, uint32_t nth) {
+    Ctl *g = c.ctl;
+    const uint32_t a = MB_G(a), b = MB_G(b), id = MB_G(new_id), seg = MB_G(seg), len = MB_G(seg_len);
+    const int32_t mode = MB_G(mode);
+    for (uint32_t k = tid; k < len; k += nth) {
+        uint32_t pos = ld_l2(&c.occ[seg + k]);
+        Node p = ld_node(&c.node[pos]);
+        if (p.tok != a || p.nxt == NIL) continue; // stale record
+        uint32_t j = p.nxt;
+        Node q = ld_node(&c.node[j]);
+        if (q.tok != b) continue;
+        const uint32_t w = p.wt;
+        if (a != b) {
+            c.hit[a_add(&g->n_hit, 1u)] = pos;
+            if (p.prv != NIL) {
+                Node x = ld_node(&c.node[p.prv]);
+                // x is the tail of another occurrence ("abab"): that occurrence's right side covers this gap
+                bool tail = (x.tok == b && x.prv != NIL && ld_l2(&c.node[x.prv].tok) == a);
+                if (!tail) {
+                    pair_dec(c, mode, x.tok, a, w, p.prv);
+                    pair_inc(c, mode, x.tok, id, w, p.prv);
+                }
+            }
+            if (q.nxt != NIL) {
+                Node y = ld_node(&c.node[q.nxt]);
+                bool head = (y.tok == a && y.nxt != NIL && ld_l2(&c.node[y.nxt].tok) == b);
+                pair_dec(c, mode, b, y.tok, w, j);
+                pair_inc(c, mode, id, head ? id : y.tok, w, pos);
+            }
+        } else {
+            // a == b: left-to-right non-overlapping rule (Tokenizer.h:176-191). Only the start of a run of a's
+            // acts; it walks its run and merges the 1st, 3rd, 5th... pair.
+            if (p.prv != NIL) {
+                uint32_t xt = ld_l2(&c.node[p.prv].tok);
+                if (xt == a) continue;
+                pair_dec(c, mode, xt, a, w, p.prv);
+                pair_inc(c, mode, xt, id, w, p.prv);
+            }
+            uint32_t cur = pos, second = j;
+            for (;;) {
+                c.hit[a_add(&g->n_hit, 1u)] = cur;
+                uint32_t r = ld_l2(&c.node[second].nxt);
+                if (r == NIL) break;
+                Node nr = ld_node(&c.node[r]);
+                if (nr.tok != a) { // run ended right after this pair
+                    pair_dec(c, mode, a, nr.tok, w, second);
+                    pair_inc(c, mode, id, nr.tok, w, cur);
+                    break;
+                }
+                bool head = (nr.nxt != NIL && ld_l2(&c.node[nr.nxt].tok) == a);
+                pair_inc(c, mode, id, head ? id : a, w, cur);
+                if (!head) break; // one trailing a stays; its right-hand pair is untouched
+                cur = r;
+                second = nr.nxt;
+            }
+        }
+    }
+}
+
+// mutate: rewrite the corpus (merge, Tokenizer.h:182-183). Field-wise stores only: different threads own
+// different fields of a shared neighbour node.
+MB_HD void phase_mutate(const Ctx &c, uint32_t tid, uint32_t nth) {
+    Ctl *g = c.ctl;
+    const uint32_t id = MB_G(new_id), n = MB_G(n_hit);
+    for (uint32_t h = tid; h < n; h += nth) {
+        uint32_t pos = ld_l2(&c.hit[h]);
+        uint32_t j = ld_l2(&c.node[pos].nxt);
+        uint32_t y = ld_l2(&c.node[j].nxt);
+        c.node[pos].tok = id;
+        c.node[pos].nxt = y;
+        c.node[j].tok = DEAD;
+        if (y != NIL) c.node[y].prv = pos;
+    }
+}
+
+// seg_alloc: give every pair born in this step its arena segment; join the candidate list if it qualifies
+MB_HD void phase_seg_alloc(const Ctx &c, uint32_t tid, uint32_t nth) {
+    Ctl *g = c.ctl;
+    uint32_t n = MB_G(n_newp);
+    int32_t theta = MB_G(theta);
+    for (uint32_t i = tid; i < n; i += nth) {
+        uint32_t s = ld_l2(&c.newp[i]);
+        c.slot[s].seg = a_add(&g->arena_cursor, ld_l2(&c.slot[s].len));
+        if (ld_l2(&c.slot[s].cnt) >= theta) {
+            uint32_t k = a_add(&g->n_cand, 1u);
+            if (k < c.cand_cap) c.cand[k] = s; // cannot overflow: cand_cap >= number of pairs
+        }
+    }
+}
+// seg_fill: scatter this step's occurrence records into their pair's segment
+MB_HD void phase_seg_fill(const Ctx &c, uint32_t tid, uint32_t nth) {
+    Ctl *g = c.ctl;
+    uint32_t n = MB_G(n_rec);
+    for (uint32_t r = tid; r < n; r += nth) {
+        uint32_t s = ld_l2(&c.rec_slot[r]);
+        uint32_t k = a_add(&c.slot[s].fill, 1u);
+        c.occ[ld_l2(&c.slot[s].seg) + k] = ld_l2(&c.rec_pos[r]);
+    }
+}
+// fin (one thread): close the step
+MB_HD void phase_fin(const Ctx &c) {
+    Ctl *g = c.ctl;
+    uint64_t live = MB_G(live_tokens);
+    uint32_t n_hit = MB_G(n_hit), n_cand = MB_G(n_cand), step = MB_G(step) + 1;
+    // B_train(m) = 4 T_m + 4 T_m + 4 T_{m+1} + 16 P_m
+    g->rescan_bytes = MB_G(rescan_bytes) + 8ull * live + 4ull * (live - n_hit) + 16ull * MB_G(n_pairs);
+    g->live_tokens = live - n_hit;
+    c.slot[MB_G(best_slot)].cnt = 0; // every occurrence of (a,b) was merged or destroyed
+    g->step = step;
+    g->selected = 0;
+    g->n_hit = 0;
+    g->n_rec = 0;
+    g->n_newp = 0;
+    g->cmax = CMAX_NONE;
+    g->best_tie = ~0ull;
+    g->n_fix = 0;
+    int32_t st = (step >= MB_G(n_target)) ? ST_DONE : ST_RUN;
+    // list is mostly dead weight: rebuild (full-grid scan) before the next selection
+    if (st == ST_RUN && n_cand > 2 * MB_G(n_live) + 4096) st = ST_NEED_REBUILD;
+    g->n_live = 0;
+    g->status = st;
+}
+// reset of the selection scratch when a step is (re-)selected after a rebuild / grow
+MB_HD void phase_sel_reset(const Ctx &c) {
+    Ctl *g = c.ctl;
+    g->cmax = CMAX_NONE;
+    g->best_tie = ~0ull;
+    g->n_fix = 0;
+    g->n_live = 0;
+    g->selected = 0;
+    if (MB_G(status) != ST_EXHAUSTED) g->status = ST_RUN;
+}
+// a big merge taken over by the grid: same step, status back to RUN
+MB_HD void phase_take_big(const Ctx &c) {
+    Ctl *g = c.ctl;
+    if (MB_G(status) == ST_BIG_MERGE) g->status = ST_RUN;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// candidate rebuild (full scans of the table)
+// ---------------------------------------------------------------------------------------------------------
+MB_HD void phase_rebuild_reset(const Ctx &c) {
+    Ctl *g = c.ctl;
+    g->gmax = 0;
+    g->n_positive = 0;
+    for (int i = 0; i < 32; i++) g->hist[i] = 0;
+}
+MB_HD void phase_rebuild_hist(const Ctx &c, uint32_t tid, uint32_t nth) {
+    Ctl *g = c.ctl;
+    uint32_t cap = c.cap_mask + 1;
+    for (uint32_t s = tid; s < cap; s += nth) {
+        if (ld_l2(&c.slot[s].key) == EMPTY_KEY) continue;
+        int32_t v = ld_l2(&c.slot[s].cnt);
+        if (v <= 0) continue;
+        a_max(&g->gmax, v);
+        a_add(&g->n_positive, 1u);
+        uint32_t bkt = 0;
+        for (uint32_t t = (uint32_t)v; t > 1; t >>= 1) bkt++;
+        a_add(&g->hist[bkt], 1u);
+    }
+}
+// one thread: theta = largest power of two with at least `want` pairs at or above it (or 1)
+MB_HD void phase_rebuild_theta(const Ctx &c, uint32_t want) {
+    Ctl *g = c.ctl;
+    g->n_cand = 0;
+    if (MB_G(gmax) <= 0) {
+        g->status = ST_EXHAUSTED;
+        return;
+    }
+    uint32_t acc = 0;
+    int32_t theta = 1;
+    for (int bkt = 31; bkt >= 0; bkt--) {
+        acc += MB_G(hist[bkt]);
+        if (acc >= want) {
+            theta = (int32_t)(1u << bkt);
+            break;
+        }
+    }
+    g->theta = theta;
+}
+MB_HD void phase_rebuild_collect(const Ctx &c, uint32_t tid, uint32_t nth) {
+    Ctl *g = c.ctl;
+    if (MB_G(status) == ST_EXHAUSTED) return;
+    uint32_t cap = c.cap_mask + 1;
+    int32_t theta = MB_G(theta);
+    for (uint32_t s = tid; s < cap; s += nth) {
+        if (ld_l2(&c.slot[s].key) == EMPTY_KEY) continue;
+        if (ld_l2(&c.slot[s].cnt) >= theta) c.cand[a_add(&g->n_cand, 1u)] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// table growth: re-insert every slot of `old` into the (larger, cleared) table of c
+// ---------------------------------------------------------------------------------------------------------
+MB_HD void phase_rehash(const Ctx &c, const Slot *old, uint32_t old_cap, uint32_t tid, uint32_t nth) {
+    for (uint32_t s = tid; s < old_cap; s += nth) {
+        Slot v = old[s];
+        if (v.key == EMPTY_KEY) continue;
+        bool created;
+        uint32_t d = slot_upsert(c, v.key, &created);
+        c.slot[d].cnt = v.cnt;
+        c.slot[d].len = v.len;
+        c.slot[d].first = v.first;
+        c.slot[d].seg = v.seg;
+        c.slot[d].fill = v.fill;
+    }
+}
+MB_HD void phase_clear_slots(Slot *slot, uint32_t cap, uint32_t tid, uint32_t nth) {
+    for (uint32_t s = tid; s < cap; s += nth) {
+        Slot v;
+        v.key = EMPTY_KEY;
+        v.cnt = 0;
+        v.len = 0;
+        v.first = NO_FIRST;
+        v.seg = 0;
+        v.fill = 0;
+        v.pad = 0;
+        slot[s] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// initial build: calculate_freqs (Tokenizer.h:127-146) + occurrence index
+// ---------------------------------------------------------------------------------------------------------
+// nodes from the flattened chunk list: chunk c = positions [off[c], off[c+1])
+MB_HD uint64_t chunk_of(const uint64_t *off, uint64_t n_chunks, uint64_t i) {
+    uint64_t lo = 0, hi = n_chunks; // largest c with off[c] <= i (empty chunks share an offset: take the last)
+    while (hi - lo > 1) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (off[mid] <= i)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+MB_HD void phase_init_nodes(const Ctx &c, const uint32_t *tokens, const uint64_t *off, const uint32_t *weight,
+                            uint64_t n_chunks, uint32_t tid, uint32_t nth) {
+    for (uint32_t i = tid; i < c.n_pos; i += nth) {
+        uint64_t ch = chunk_of(off, n_chunks, i);
+        Node n;
+        n.tok = tokens[i];
+        n.prv = (i == off[ch]) ? NIL : i - 1;
+        n.nxt = (i + 1 == off[ch + 1]) ? NIL : i + 1;
+        n.wt = weight ? weight[ch] : 1u;
+        c.node[i] = n;
+    }
+}
+// count of one pair: w = summed weight, n_occ = occurrences, first = smallest position (the CUDA build
+// pre-aggregates these per CTA in shared memory before touching the table in HBM)
+MB_HD void count_one(const Ctx &c, uint64_t key, uint32_t w, uint32_t n_occ, uint32_t first) {
+    bool created;
+    uint32_t s = slot_upsert(c, key, &created);
+    if (created) {
+        a_add(&c.ctl->n_pairs, 1u);
+        a_min(&c.ctl->min_key_ever, key);
+    }
+    a_add(reinterpret_cast<uint64_t *>(&c.slot[s].cnt), ((uint64_t)n_occ << 32) | (uint64_t)w);
+    a_min(&c.slot[s].first, first);
+}
+MB_HD void phase_init_count(const Ctx &c, uint32_t tid, uint32_t nth) {
+    for (uint32_t i = tid; i < c.n_pos; i += nth) {
+        Node n = c.node[i];
+        if (n.nxt == NIL) continue;
+        count_one(c, pair_key(n.tok, c.node[n.nxt].tok), n.wt, 1u, i);
+    }
+}
+MB_HD void phase_init_alloc(const Ctx &c, uint32_t tid, uint32_t nth) {
+    uint32_t cap = c.cap_mask + 1;
+    for (uint32_t s = tid; s < cap; s += nth) {
+        if (c.slot[s].key == EMPTY_KEY) continue;
+        c.slot[s].seg = a_add(&c.ctl->arena_cursor, c.slot[s].len);
+    }
+}
+MB_HD void phase_init_fill(const Ctx &c, uint32_t tid, uint32_t nth) {
+    for (uint32_t i = tid; i < c.n_pos; i += nth) {
+        Node n = c.node[i];
+        if (n.nxt == NIL) continue;
+        uint32_t s = slot_find(c, pair_key(n.tok, c.node[n.nxt].tok));
+        uint32_t k = a_add(&c.slot[s].fill, 1u);
+        c.occ[c.slot[s].seg + k] = i;
+    }
+}
+
+} // namespace mbpe
+
+// ---------------------------------------------------------------------------------------------------------
+// phase functors: what a backend launches (kernel names in ncu read k_par<mbpe::PhHits> etc.)
+// ---------------------------------------------------------------------------------------------------------
+namespace mbpe {
+#define MB_PHASE_PAR(NAME, CALL)                                                \
+    struct NAME {                                                               \
+        Ctx c;                                                                  \
+        MB_HD void operator()(uint32_t tid, uint32_t nth) const { CALL; }       \
+    };
+#define MB_PHASE_ONE(NAME, CALL)                 \
+    struct NAME {                                \
+        Ctx c;                                   \
+        MB_HD void operator()() const { CALL; }  \
+    };
+MB_PHASE_PAR(PhSelMax, phase_sel_max(c, tid, nth))
+MB_PHASE_PAR(PhSelTie, phase_sel_tie(c, tid, nth))
+MB_PHASE_ONE(PhSelCheck, phase_sel_check(c))
+MB_PHASE_PAR(PhSelFixScan, phase_sel_fix_scan(c, tid, nth))
+MB_PHASE_PAR(PhSelFixTie, phase_sel_fix_tie(c, tid, nth))
+MB_PHASE_PAR(PhSelPick, phase_sel_pick(c, tid, nth))
+MB_PHASE_PAR(PhHits, phase_hits(c, tid, nth))
+MB_PHASE_PAR(PhMutate, phase_mutate(c, tid, nth))
+MB_PHASE_PAR(PhSegAlloc, phase_seg_alloc(c, tid, nth))
+MB_PHASE_PAR(PhSegFill, phase_seg_fill(c, tid, nth))
+MB_PHASE_ONE(PhFin, phase_fin(c))
+MB_PHASE_ONE(PhSelReset, phase_sel_reset(c))
+MB_PHASE_ONE(PhTakeBig, phase_take_big(c))
+MB_PHASE_ONE(PhRebuildReset, phase_rebuild_reset(c))
+MB_PHASE_PAR(PhRebuildHist, phase_rebuild_hist(c, tid, nth))
+MB_PHASE_PAR(PhRebuildCollect, phase_rebuild_collect(c, tid, nth))
+MB_PHASE_PAR(PhInitCount, phase_init_count(c, tid, nth))
+MB_PHASE_PAR(PhInitAlloc, phase_init_alloc(c, tid, nth))
+MB_PHASE_PAR(PhInitFill, phase_init_fill(c, tid, nth))
+struct PhSelCommit {
+    Ctx c;
+    int persistent;
+    MB_HD void operator()() const { phase_sel_commit(c, persistent); }
+};
+struct PhRebuildTheta {
+    Ctx c;
+    uint32_t want;
+    MB_HD void operator()() const { phase_rebuild_theta(c, want); }
+};
+struct PhRehash {
+    Ctx c;
+    const Slot *old;
+    uint32_t old_cap;
+    MB_HD void operator()(uint32_t tid, uint32_t nth) const { phase_rehash(c, old, old_cap, tid, nth); }
+};
+struct PhClearSlots {
+    Slot *slot;
+    uint32_t cap;
+    MB_HD void operator()(uint32_t tid, uint32_t nth) const { phase_clear_slots(slot, cap, tid, nth); }
+};
+struct PhInitNodes {
+    Ctx c;
+    const uint32_t *tokens;
+    const uint64_t *off;
+    const uint32_t *weight;
+    uint64_t n_chunks;
+    MB_HD void operator()(uint32_t tid, uint32_t nth) const { phase_init_nodes(c, tokens, off, weight, n_chunks, tid, nth); }
+};
+
+// The resident program: steps back to back until something needs the grid (status != ST_RUN).
+// Exec supplies the barrier: on the device  par(f) = f(threadIdx.x, blockDim.x); __syncthreads();
+// under the host test driver it is a sequential loop over tid.
+template <class Exec>
+MB_HD void persistent_program(const Ctx &c, Exec &ex) {
+    for (;;) {
+        if (ex.load(&c.ctl->status) != ST_RUN) return;
+        if (ex.load(&c.ctl->selected) == 0) {
+            ex.par(PhSelMax{c});
+            ex.par(PhSelTie{c});
+            ex.one(PhSelCheck{c});
+            if (ex.load(&c.ctl->n_fix) != 0) {
+                ex.par(PhSelFixScan{c});
+                ex.par(PhSelFixTie{c});
+            }
+            ex.par(PhSelPick{c});
+            ex.one(PhSelCommit{c, 1});
+            if (ex.load(&c.ctl->status) != ST_RUN) return;
+        }
+        ex.par(PhHits{c});
+        ex.par2(PhMutate{c}, PhSegAlloc{c}); // disjoint data: corpus nodes vs. new slots
+        ex.par(PhSegFill{c});
+        ex.one(PhFin{c});
+    }
+}
+} // namespace mbpe
