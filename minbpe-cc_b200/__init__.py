@@ -1,0 +1,365 @@
+"""ctypes binding of libminbpe_b200.so (include/minbpe_b200.h) for the tests and bench.py.
+
+The directory name has a hyphen (it mirrors the reference's name), so import it with
+`importlib` -- see `load_package()` in tests/conftest.py / __graft_entry__.py -- as module `minbpe_cc_b200`.
+
+This is plumbing only: every compute entry point is a C-ABI call into hand-written sm_100a kernels. There is no
+Python or CPU implementation behind it; a missing library or a missing GPU raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libminbpe_b200.so")
+CLI_PATH = os.path.join(HERE, "bin", "minbpe-cc")
+
+MODE = {"first": 0, "lexical": 1}
+ENGINE = {"stepwise": 0, "persistent": 1}
+
+EXPORTS = [
+    "mbpe_version", "mbpe_last_error", "mbpe_device_count",
+    "mbpe_paircount_create", "mbpe_paircount_destroy", "mbpe_paircount_add", "mbpe_paircount_top",
+    "mbpe_paircount_get", "mbpe_paircount_size",
+    "mbpe_trainer_create", "mbpe_trainer_run", "mbpe_trainer_destroy", "mbpe_train",
+    "mbpe_encoder_create", "mbpe_encoder_destroy", "mbpe_encoder_set_specials", "mbpe_encode", "mbpe_encode_device",
+    "mbpe_encode_reserve", "mbpe_decode",
+    "mbpe_gpt2_split_pattern", "mbpe_gpt4_split_pattern", "mbpe_tokenizer_create", "mbpe_tokenizer_destroy",
+    "mbpe_tokenizer_set_special_tokens", "mbpe_tokenizer_train", "mbpe_tokenizer_save", "mbpe_tokenizer_load",
+    "mbpe_tokenizer_encode", "mbpe_tokenizer_decode", "mbpe_tokenizer_get_merges",
+    "mbpe_tokenizer_last_train_stats", "mbpe_tokenizer_set_engine", "mbpe_tokenizer_set_threads",
+    "mbpe_split", "mbpe_dedup", "mbpe_write_model", "mbpe_synth_corpus",
+]
+
+
+class MbpeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"mbpe error {code}: {msg}")
+        self.code = code
+
+
+class TrainStats(C.Structure):
+    _fields_ = [("gpu_ms", C.c_double), ("build_ms", C.c_double), ("n_positions", C.c_uint64),
+                ("n_pairs", C.c_uint64), ("table_slots", C.c_uint64), ("n_launches", C.c_uint64),
+                ("n_big_merges", C.c_uint64), ("n_rebuilds", C.c_uint64), ("n_grows", C.c_uint64),
+                ("rescan_bytes", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_lib = None
+
+
+def lib():
+    """Load the library or raise: there is no fallback implementation."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python minbpe-cc_b200/build.py` (nvcc, sm_100a)")
+        L = C.CDLL(LIB_PATH)
+        L.mbpe_version.restype = C.c_char_p
+        L.mbpe_last_error.restype = C.c_char_p
+        L.mbpe_gpt2_split_pattern.restype = C.c_char_p
+        L.mbpe_gpt4_split_pattern.restype = C.c_char_p
+        L.mbpe_tokenizer_destroy.restype = None
+        L.mbpe_trainer_destroy.restype = None
+        L.mbpe_encoder_destroy.restype = None
+        L.mbpe_paircount_destroy.restype = None
+        L.mbpe_tokenizer_set_engine.restype = None
+        L.mbpe_tokenizer_set_threads.restype = None
+        _lib = L
+    return _lib
+
+
+def _ck(rc):
+    if rc != 0:
+        raise MbpeError(rc, lib().mbpe_last_error().decode(errors="replace"))
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _u8(b):
+    return np.frombuffer(b, dtype=np.uint8) if len(b) else np.zeros(1, np.uint8)
+
+
+def device_count():
+    return lib().mbpe_device_count()
+
+
+def patterns():
+    L = lib()
+    return {"basic": "", "gpt2": L.mbpe_gpt2_split_pattern().decode(), "gpt4": L.mbpe_gpt4_split_pattern().decode()}
+
+
+# ---- 1. PairCount seam ----------------------------------------------------------------------------------
+class PairCount:
+    """PairCount<T> (PairCount.h:27-47) on the device."""
+
+    def __init__(self, mode, device=0):
+        self.h = C.c_void_p()
+        _ck(lib().mbpe_paircount_create(MODE[mode], device, C.byref(self.h)))
+
+    def create_or_modify_pair(self, a, b, freq):
+        self.add([(a, b, freq)])
+
+    def add(self, ops):
+        arr = np.asarray(ops, np.int64).reshape(-1, 3)
+        a = np.ascontiguousarray(arr[:, 0], np.uint32)
+        b = np.ascontiguousarray(arr[:, 1], np.uint32)
+        d = np.ascontiguousarray(arr[:, 2], np.int32)
+        _ck(lib().mbpe_paircount_add(self.h, _p(a, C.c_uint32), _p(b, C.c_uint32), _p(d, C.c_int32), C.c_uint64(len(a))))
+
+    def get_top_pair_count(self):
+        a, b, c, f = C.c_uint32(), C.c_uint32(), C.c_int32(), C.c_int()
+        _ck(lib().mbpe_paircount_top(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(f)))
+        return (a.value, b.value) if f.value else None
+
+    def get_pair(self, pair):
+        c, f = C.c_int32(), C.c_int()
+        _ck(lib().mbpe_paircount_get(self.h, C.c_uint32(pair[0]), C.c_uint32(pair[1]), C.byref(c), C.byref(f)))
+        return c.value if f.value else None
+
+    def get_count(self):
+        n = C.c_uint64()
+        _ck(lib().mbpe_paircount_size(self.h, C.byref(n)))
+        return n.value
+
+    def close(self):
+        if self.h:
+            lib().mbpe_paircount_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- 2. train merge loop --------------------------------------------------------------------------------
+class Trainer:
+    """Resident deduplicated corpus + repeatable merge loop (Tokenizer.h:551-589)."""
+
+    def __init__(self, tokens, off, weight=None, device=0):
+        self.tokens = np.ascontiguousarray(tokens, np.uint32)
+        self.off = np.ascontiguousarray(off, np.uint64)
+        self.weight = None if weight is None else np.ascontiguousarray(weight, np.uint32)
+        self.h = C.c_void_p()
+        tok = self.tokens if len(self.tokens) else np.zeros(1, np.uint32)
+        _ck(lib().mbpe_trainer_create(_p(tok, C.c_uint32), C.c_uint64(len(self.tokens)), _p(self.off, C.c_uint64),
+                                      C.c_uint64(len(self.off) - 1),
+                                      None if self.weight is None else _p(self.weight, C.c_uint32), device,
+                                      C.byref(self.h)))
+
+    def run(self, vocab_size, mode, engine="persistent", stream=None):
+        n = max(vocab_size - 256, 1)
+        merges = np.zeros((n, 2), np.uint32)
+        counts = np.zeros(n, np.int32)
+        nm = C.c_uint32()
+        st = TrainStats()
+        _ck(lib().mbpe_trainer_run(self.h, C.c_uint32(vocab_size), MODE[mode] if isinstance(mode, str) else mode,
+                                   ENGINE[engine] if isinstance(engine, str) else engine,
+                                   C.c_void_p(stream or 0), _p(merges, C.c_uint32), _p(counts, C.c_int32),
+                                   C.byref(nm), C.byref(st)))
+        return merges[:nm.value].copy(), counts[:nm.value].copy(), st.as_dict()
+
+    def close(self):
+        if self.h:
+            lib().mbpe_trainer_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def train(tokens, off, weight, vocab_size, mode, engine="persistent", device=0):
+    t = Trainer(tokens, off, weight, device)
+    try:
+        return t.run(vocab_size, mode, engine)
+    finally:
+        t.close()
+
+
+# ---- 3. encode / decode ---------------------------------------------------------------------------------
+class Encoder:
+    def __init__(self, merges, device=0):
+        m = np.ascontiguousarray(merges, np.uint32).reshape(-1, 2)
+        self.n_merges = len(m)
+        self.h = C.c_void_p()
+        mm = m if len(m) else np.zeros((1, 2), np.uint32)
+        _ck(lib().mbpe_encoder_create(_p(mm, C.c_uint32), C.c_uint32(len(m)), device, C.byref(self.h)))
+
+    def set_specials(self, specials):
+        """specials: dict id -> bytes"""
+        ids = np.asarray(list(specials.keys()) or [0], np.uint32)
+        blob = b"".join(specials.values())
+        off = np.zeros(len(specials) + 1, np.uint64)
+        if specials:
+            off[1:] = np.cumsum([len(v) for v in specials.values()])
+        _ck(lib().mbpe_encoder_set_specials(self.h, _p(ids, C.c_uint32), _p(_u8(blob), C.c_uint8), _p(off, C.c_uint64),
+                                            C.c_uint32(len(specials))))
+
+    def encode(self, data: bytes, chunk_off, want_off=False):
+        off = np.ascontiguousarray(chunk_off, np.uint64)
+        out = np.zeros(max(len(data), 1), np.uint32)
+        out_off = np.zeros(len(off), np.uint64) if want_off else None
+        n = C.c_uint64()
+        _ck(lib().mbpe_encode(self.h, _p(_u8(data), C.c_uint8), C.c_uint64(len(data)), _p(off, C.c_uint64),
+                              C.c_uint64(len(off) - 1), _p(out, C.c_uint32), C.c_uint64(len(out)), C.byref(n),
+                              None if out_off is None else _p(out_off, C.c_uint64)))
+        return (out[:n.value].copy(), out_off) if want_off else out[:n.value].copy()
+
+    def encode_device(self, d_bytes, n_bytes, d_off32, n_chunks, d_out, out_cap, d_n_out, stream=None):
+        """All pointers are device addresses (ints)."""
+        _ck(lib().mbpe_encode_device(self.h, C.c_void_p(d_bytes), C.c_uint64(n_bytes), C.c_void_p(d_off32),
+                                     C.c_uint64(n_chunks), C.c_void_p(d_out), C.c_uint64(out_cap), C.c_void_p(d_n_out),
+                                     C.c_void_p(stream or 0)))
+
+    def reserve(self, n_bytes, n_chunks):
+        _ck(lib().mbpe_encode_reserve(self.h, C.c_uint64(n_bytes), C.c_uint64(n_chunks)))
+
+    def decode(self, ids):
+        ids = np.ascontiguousarray(ids, np.uint32)
+        src = ids if len(ids) else np.zeros(1, np.uint32)
+        n = C.c_uint64()
+        _ck(lib().mbpe_decode(self.h, _p(src, C.c_uint32), C.c_uint64(len(ids)), None, C.c_uint64(0), C.byref(n)))
+        out = np.zeros(max(n.value, 1), np.uint8)
+        if n.value:
+            _ck(lib().mbpe_decode(self.h, _p(src, C.c_uint32), C.c_uint64(len(ids)), _p(out, C.c_uint8),
+                                  C.c_uint64(n.value), C.byref(n)))
+        return out[:n.value].tobytes()
+
+    def close(self):
+        if self.h:
+            lib().mbpe_encoder_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- 4. Tokenizer mirror --------------------------------------------------------------------------------
+class Tokenizer:
+    """MinBpeCC::Tokenizer::Tokenizer (Tokenizer.h:379-927), same method names and argument meaning."""
+
+    FIRST, LEXICAL = 0, 1
+
+    def __init__(self, pattern="", device=0):
+        self.h = C.c_void_p()
+        _ck(lib().mbpe_tokenizer_create(pattern.encode(), device, C.byref(self.h)))
+
+    def set_special_tokens_from_file(self, contents):
+        b = contents if isinstance(contents, bytes) else contents.encode()
+        _ck(lib().mbpe_tokenizer_set_special_tokens(self.h, b, C.c_uint64(len(b))))
+
+    def train(self, text: bytes, vocab_size, conflict_resolution, verbose=False):
+        mode = MODE[conflict_resolution] if isinstance(conflict_resolution, str) else conflict_resolution
+        _ck(lib().mbpe_tokenizer_train(self.h, _p(_u8(text), C.c_uint8), C.c_uint64(len(text)), int(vocab_size), mode,
+                                       int(verbose)))
+
+    def save(self, path, write_vocab=False):
+        _ck(lib().mbpe_tokenizer_save(self.h, str(path).encode(), int(write_vocab)))
+
+    def load(self, path, verbose=False):
+        _ck(lib().mbpe_tokenizer_load(self.h, str(path).encode(), int(verbose)))
+
+    def encode(self, text: bytes, verbose=False):
+        n = C.c_uint64()
+        out = np.zeros(max(len(text), 1), np.uint32)
+        _ck(lib().mbpe_tokenizer_encode(self.h, _p(_u8(text), C.c_uint8), C.c_uint64(len(text)), _p(out, C.c_uint32),
+                                        C.c_uint64(len(out)), C.byref(n)))
+        return out[:n.value].copy()
+
+    def decode(self, ids, verbose=False):
+        ids = np.ascontiguousarray(ids, np.uint32)
+        src = ids if len(ids) else np.zeros(1, np.uint32)
+        n = C.c_uint64()
+        _ck(lib().mbpe_tokenizer_decode(self.h, _p(src, C.c_uint32), C.c_uint64(len(ids)), None, C.c_uint64(0),
+                                        C.byref(n)))
+        out = np.zeros(max(n.value, 1), np.uint8)
+        _ck(lib().mbpe_tokenizer_decode(self.h, _p(src, C.c_uint32), C.c_uint64(len(ids)), _p(out, C.c_uint8),
+                                        C.c_uint64(len(out)), C.byref(n)))
+        return out[:n.value].tobytes()
+
+    def merges(self):
+        n = C.c_uint32()
+        _ck(lib().mbpe_tokenizer_get_merges(self.h, None, 0, C.byref(n)))
+        m = np.zeros((max(n.value, 1), 2), np.uint32)
+        _ck(lib().mbpe_tokenizer_get_merges(self.h, _p(m, C.c_uint32), C.c_uint32(len(m)), C.byref(n)))
+        return m[:n.value].copy()
+
+    def last_train_stats(self):
+        st = TrainStats()
+        split, dedup, nc, nu = C.c_double(), C.c_double(), C.c_uint64(), C.c_uint64()
+        _ck(lib().mbpe_tokenizer_last_train_stats(self.h, C.byref(st), C.byref(split), C.byref(dedup), C.byref(nc),
+                                                  C.byref(nu)))
+        d = st.as_dict()
+        d.update(split_s=split.value, dedup_s=dedup.value, n_chunks=nc.value, n_unique=nu.value)
+        return d
+
+    def set_engine(self, engine):
+        lib().mbpe_tokenizer_set_engine(self.h, ENGINE[engine] if isinstance(engine, str) else engine)
+
+    def set_threads(self, n):
+        lib().mbpe_tokenizer_set_threads(self.h, int(n))
+
+    def close(self):
+        if self.h:
+            lib().mbpe_tokenizer_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- 5. host-only helpers -------------------------------------------------------------------------------
+def split(pattern: str, text: bytes, n_threads=0):
+    n = C.c_uint64()
+    buf = _u8(text)
+    _ck(lib().mbpe_split(pattern.encode(), _p(buf, C.c_uint8), C.c_uint64(len(text)), n_threads, None, None,
+                         C.c_uint64(0), C.byref(n)))
+    s = np.zeros(max(n.value, 1), np.uint64)
+    e = np.zeros(max(n.value, 1), np.uint64)
+    _ck(lib().mbpe_split(pattern.encode(), _p(buf, C.c_uint8), C.c_uint64(len(text)), n_threads, _p(s, C.c_uint64),
+                         _p(e, C.c_uint64), C.c_uint64(len(s)), C.byref(n)))
+    return s[:n.value], e[:n.value]
+
+
+def dedup(text: bytes, starts, ends):
+    starts = np.ascontiguousarray(starts, np.uint64)
+    ends = np.ascontiguousarray(ends, np.uint64)
+    total = int((ends - starts).sum())
+    tokens = np.zeros(max(total, 1), np.uint32)
+    off = np.zeros(len(starts) + 1, np.uint64)
+    w = np.zeros(max(len(starts), 1), np.uint32)
+    nt, nu = C.c_uint64(), C.c_uint64()
+    _ck(lib().mbpe_dedup(_p(_u8(text), C.c_uint8), _p(starts, C.c_uint64), _p(ends, C.c_uint64),
+                         C.c_uint64(len(starts)), _p(tokens, C.c_uint32), C.byref(nt), _p(off, C.c_uint64),
+                         _p(w, C.c_uint32), C.byref(nu)))
+    return tokens[:nt.value].copy(), off[:nu.value + 1].copy(), w[:nu.value].copy()
+
+
+def write_model(path, pattern, special_contents, merges, write_vocab=False):
+    m = np.ascontiguousarray(merges, np.uint32).reshape(-1, 2)
+    sp = special_contents or b""
+    _ck(lib().mbpe_write_model(str(path).encode(), pattern.encode(), sp, C.c_uint64(len(sp)), _p(m, C.c_uint32),
+                               C.c_uint32(len(m)), int(write_vocab)))
+
+
+def synth_corpus(seed, n_bytes, n_threads=0):
+    out = np.zeros(n_bytes, np.uint8)
+    _ck(lib().mbpe_synth_corpus(C.c_uint64(seed), _p(out, C.c_uint8), C.c_uint64(n_bytes), n_threads))
+    return out

@@ -1,0 +1,595 @@
+// train_cuda.cu -- sm_100a backend of the train merge loop + the PairCount seam.
+//
+// Kernels (names as they appear in ncu):
+//   k_init_count            calculate_freqs (Tokenizer.h:127-146): weighted adjacent-pair histogram. 128-bit node
+//                           loads, per-CTA shared-memory open-addressed pre-aggregation, then one 64-bit atomic per
+//                           distinct pair per CTA into the HBM pair table.
+//   k_par<Ph*> / k_one<Ph*> one barrier-separated phase of train_phases.cuh over the whole grid / one thread
+//   k_persistent            persistent_program(): one resident 1024-thread CTA runs merge steps back to back
+//                           (selection, hits, mutate, segment build) with __syncthreads() as the phase barrier
+//   k_pc_*                  PairCount seam (PairCount.h:27-47): batched upsert, block-then-grid arg-max, lookup
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "train_driver.hpp"
+
+namespace mbpe {
+
+// ---------------------------------------------------------------------------------------------------------
+// generic phase launchers
+// ---------------------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(256) k_par(const F f) {
+    f(blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+template <class F>
+__global__ void __launch_bounds__(32) k_one(const F f) {
+    if (threadIdx.x == 0) f();
+}
+
+struct DevExec {
+    template <class F>
+    __device__ __forceinline__ void par(const F &f) {
+        f(threadIdx.x, blockDim.x);
+        __syncthreads();
+    }
+    template <class F, class G>
+    __device__ __forceinline__ void par2(const F &f, const G &g) {
+        f(threadIdx.x, blockDim.x);
+        g(threadIdx.x, blockDim.x);
+        __syncthreads();
+    }
+    template <class F>
+    __device__ __forceinline__ void one(const F &f) {
+        if (threadIdx.x == 0) f();
+        __syncthreads();
+    }
+    template <class T>
+    __device__ __forceinline__ T load(const T *p) {
+        return __ldcg(p);
+    }
+};
+
+constexpr int PERSISTENT_THREADS = 1024;
+__global__ void __launch_bounds__(PERSISTENT_THREADS, 1) k_persistent(const Ctx c) {
+    DevExec ex;
+    persistent_program(c, ex);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_init_count: K1, the weighted adjacent-pair histogram
+// ---------------------------------------------------------------------------------------------------------
+constexpr int IC_THREADS = 256;
+constexpr int IC_SLOTS = 4096; // shared-memory table: 4096 * (8 + 4 + 4 + 4) B = 80 KB
+constexpr int IC_ITEMS = 16;   // positions per thread per tile
+struct IcSmem {
+    unsigned long long key[IC_SLOTS];
+    uint32_t w[IC_SLOTS];
+    uint32_t n[IC_SLOTS];
+    uint32_t first[IC_SLOTS];
+    uint32_t used;
+};
+
+__device__ __forceinline__ void ic_flush(const Ctx &c, IcSmem *sm) {
+    __syncthreads();
+    for (int s = threadIdx.x; s < IC_SLOTS; s += blockDim.x) {
+        unsigned long long k = sm->key[s];
+        if (k != EMPTY_KEY) {
+            count_one(c, k, sm->w[s], sm->n[s], sm->first[s]);
+            sm->key[s] = EMPTY_KEY;
+            sm->w[s] = 0;
+            sm->n[s] = 0;
+            sm->first[s] = NO_FIRST;
+        }
+    }
+    if (threadIdx.x == 0) sm->used = 0;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(IC_THREADS) k_init_count(const Ctx c) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    IcSmem *sm = reinterpret_cast<IcSmem *>(smem_raw);
+    for (int s = threadIdx.x; s < IC_SLOTS; s += blockDim.x) {
+        sm->key[s] = EMPTY_KEY;
+        sm->w[s] = 0;
+        sm->n[s] = 0;
+        sm->first[s] = NO_FIRST;
+    }
+    if (threadIdx.x == 0) sm->used = 0;
+    __syncthreads();
+
+    const uint32_t tile = IC_THREADS * IC_ITEMS;
+    const uint4 *nodes = reinterpret_cast<const uint4 *>(c.node);
+    for (uint64_t base = (uint64_t)blockIdx.x * tile; base < c.n_pos; base += (uint64_t)gridDim.x * tile) {
+#pragma unroll 4
+        for (int it = 0; it < IC_ITEMS; it++) {
+            uint64_t i = base + (uint64_t)it * IC_THREADS + threadIdx.x; // coalesced 16-byte loads
+            if (i >= c.n_pos) break;
+            uint4 nd = __ldg(&nodes[i]); // {tok, nxt, prv, wt}
+            if (nd.y == NIL) continue;
+            uint32_t tok2 = __ldg(&nodes[nd.y]).x; // the neighbour: same or next 128-byte line
+            unsigned long long key = pair_key(nd.x, tok2);
+            uint32_t s = hash_key(key) & (IC_SLOTS - 1);
+            bool done = false;
+            for (int probe = 0; probe < 16; probe++) {
+                unsigned long long k = sm->key[s];
+                if (k == EMPTY_KEY) {
+                    k = atomicCAS(&sm->key[s], EMPTY_KEY, key);
+                    if (k == EMPTY_KEY) {
+                        atomicAdd(&sm->used, 1u);
+                        k = key;
+                    }
+                }
+                if (k == key) {
+                    atomicAdd(&sm->w[s], nd.w);
+                    atomicAdd(&sm->n[s], 1u);
+                    atomicMin(&sm->first[s], (uint32_t)i);
+                    done = true;
+                    break;
+                }
+                s = (s + 1) & (IC_SLOTS - 1);
+            }
+            if (!done) count_one(c, key, nd.w, 1u, (uint32_t)i); // crowded neighbourhood: straight to HBM
+        }
+        __syncthreads();
+        if (sm->used > IC_SLOTS / 2) ic_flush(c, sm); // block-uniform: read after the barrier
+    }
+    ic_flush(c, sm);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// CUDA backend for TrainLoop
+// ---------------------------------------------------------------------------------------------------------
+struct CudaBE {
+    cudaStream_t stream = nullptr;
+    int sms = 148;
+    uint64_t n_launch = 0;
+    cudaError_t err = cudaSuccess;
+    const char *err_what = "";
+    Ctl *pinned = nullptr; // staging for the per-iteration control read
+
+    void note(cudaError_t e, const char *what) {
+        if (e != cudaSuccess && err == cudaSuccess) {
+            err = e;
+            err_what = what;
+        }
+    }
+    void *alloc(size_t n) {
+        void *p = nullptr;
+        if (err == cudaSuccess) note(cudaMallocAsync(&p, n ? n : 1, stream), "cudaMallocAsync");
+        return p;
+    }
+    void release(void *p) {
+        if (p) note(cudaFreeAsync(p, stream), "cudaFreeAsync");
+    }
+    void upload(void *d, const void *s, size_t n) {
+        if (err != cudaSuccess) return;
+        note(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, stream), "H2D");
+        note(cudaStreamSynchronize(stream), "sync");
+    }
+    void download(void *d, const void *s, size_t n) {
+        if (err != cudaSuccess) { // make the driver loop terminate
+            if (n == sizeof(Ctl)) reinterpret_cast<Ctl *>(d)->status = ST_DONE;
+            return;
+        }
+        if (n == sizeof(Ctl) && pinned) {
+            note(cudaMemcpyAsync(pinned, s, n, cudaMemcpyDeviceToHost, stream), "D2H ctl");
+            note(cudaStreamSynchronize(stream), "sync");
+            memcpy(d, pinned, n);
+        } else {
+            note(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, stream), "D2H");
+            note(cudaStreamSynchronize(stream), "sync");
+        }
+        if (err != cudaSuccess && n == sizeof(Ctl)) reinterpret_cast<Ctl *>(d)->status = ST_DONE;
+    }
+    unsigned grid_for(uint64_t n_items) const {
+        uint64_t blocks = (n_items + 255) / 256;
+        uint64_t cap = (uint64_t)sms * 8; // 8 resident 256-thread CTAs per SM
+        return (unsigned)std::max<uint64_t>(1, std::min(blocks, cap));
+    }
+    template <class F>
+    void par(const F &f, uint64_t n_items) {
+        if (err != cudaSuccess) return;
+        k_par<F><<<grid_for(n_items), 256, 0, stream>>>(f);
+        n_launch++;
+        note(cudaGetLastError(), "k_par launch");
+    }
+    template <class F>
+    void one(const F &f) {
+        if (err != cudaSuccess) return;
+        k_one<F><<<1, 32, 0, stream>>>(f);
+        n_launch++;
+        note(cudaGetLastError(), "k_one launch");
+    }
+    void init_count(const Ctx &c) {
+        if (err != cudaSuccess) return;
+        static bool attr_set = false;
+        if (!attr_set) {
+            note(cudaFuncSetAttribute(k_init_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IcSmem)),
+                 "smem attr");
+            attr_set = true;
+        }
+        uint64_t tiles = ((uint64_t)c.n_pos + IC_THREADS * IC_ITEMS - 1) / (IC_THREADS * IC_ITEMS);
+        unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)sms * 2));
+        k_init_count<<<grid, IC_THREADS, sizeof(IcSmem), stream>>>(c);
+        n_launch++;
+        note(cudaGetLastError(), "k_init_count launch");
+    }
+    void persistent(const Ctx &c) {
+        if (err != cudaSuccess) return;
+        k_persistent<<<1, PERSISTENT_THREADS, 0, stream>>>(c);
+        n_launch++;
+        note(cudaGetLastError(), "k_persistent launch");
+    }
+    uint64_t launches() const { return n_launch; }
+};
+
+} // namespace mbpe
+
+using namespace mbpe;
+
+// ---------------------------------------------------------------------------------------------------------
+// C ABI: trainer
+// ---------------------------------------------------------------------------------------------------------
+struct mbpe_trainer {
+    int device = 0;
+    uint32_t *d_tokens = nullptr;
+    uint64_t *d_off = nullptr;
+    uint32_t *d_weight = nullptr;
+    uint64_t n_tokens = 0, n_chunks = 0;
+    Ctl *pinned_ctl = nullptr;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+};
+
+extern "C" int mbpe_trainer_create(const uint32_t *tokens, uint64_t n_tokens, const uint64_t *chunk_off,
+                                   uint64_t n_chunks, const uint32_t *chunk_weight, int device, mbpe_trainer **out) {
+    if (!out || (!tokens && n_tokens) || !chunk_off) return set_error(MBPE_E_INVALID, "null argument");
+    *out = nullptr;
+    if (n_tokens >= (1ull << 30)) return set_error(MBPE_E_INVALID, "n_tokens must be < 2^30 per trainer");
+    if (chunk_off[0] != 0 || chunk_off[n_chunks] != n_tokens)
+        return set_error(MBPE_E_INVALID, "chunk_off must start at 0 and end at n_tokens");
+    for (uint64_t c = 0; c < n_chunks; c++) {
+        if (chunk_off[c + 1] < chunk_off[c]) return set_error(MBPE_E_INVALID, "chunk_off not monotonic");
+        if (chunk_off[c + 1] - chunk_off[c] >= 2)
+            for (uint64_t i = chunk_off[c]; i < chunk_off[c + 1]; i++)
+                if (tokens[i] >= 256)
+                    return set_error(MBPE_E_INVALID, "token >= 256 inside a multi-token chunk (new ids would collide)");
+    }
+    int rc = use_device(device);
+    if (rc) return rc;
+    mbpe_trainer *t = new mbpe_trainer();
+    t->device = device;
+    t->n_tokens = n_tokens;
+    t->n_chunks = n_chunks;
+    MB_CUDA(cudaMalloc(&t->d_tokens, std::max<uint64_t>(n_tokens, 1) * 4));
+    MB_CUDA(cudaMalloc(&t->d_off, (n_chunks + 1) * 8));
+    MB_CUDA(cudaMemcpy(t->d_tokens, tokens, n_tokens * 4, cudaMemcpyHostToDevice));
+    MB_CUDA(cudaMemcpy(t->d_off, chunk_off, (n_chunks + 1) * 8, cudaMemcpyHostToDevice));
+    if (chunk_weight) {
+        MB_CUDA(cudaMalloc(&t->d_weight, std::max<uint64_t>(n_chunks, 1) * 4));
+        MB_CUDA(cudaMemcpy(t->d_weight, chunk_weight, n_chunks * 4, cudaMemcpyHostToDevice));
+    }
+    MB_CUDA(cudaMallocHost(&t->pinned_ctl, sizeof(Ctl)));
+    for (auto &e : t->ev) MB_CUDA(cudaEventCreate(&e));
+    // keep freed blocks in the stream-ordered pool so repeated runs do not go back to the driver
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    *out = t;
+    return MBPE_OK;
+}
+
+extern "C" void mbpe_trainer_destroy(mbpe_trainer *t) {
+    if (!t) return;
+    cudaSetDevice(t->device);
+    cudaFree(t->d_tokens);
+    cudaFree(t->d_off);
+    cudaFree(t->d_weight);
+    cudaFreeHost(t->pinned_ctl);
+    for (auto &e : t->ev)
+        if (e) cudaEventDestroy(e);
+    delete t;
+}
+
+static uint32_t env_u32(const char *name, uint32_t dflt) {
+    const char *v = getenv(name);
+    return v && *v ? (uint32_t)strtoul(v, nullptr, 10) : dflt;
+}
+
+extern "C" int mbpe_trainer_run(mbpe_trainer *t, uint32_t vocab_size, int mode, int engine, void *stream,
+                                uint32_t *merges_out, int32_t *counts_out, uint32_t *n_merges_out,
+                                mbpe_train_stats *stats) {
+    if (!t || !merges_out || !n_merges_out) return set_error(MBPE_E_INVALID, "null argument");
+    if (vocab_size < 256) return set_error(MBPE_E_INVALID, "vocab_size must be >= 256 (Tokenizer.h:492)");
+    if (mode != MBPE_MODE_FIRST && mode != MBPE_MODE_LEXICAL) return set_error(MBPE_E_INVALID, "bad mode");
+    if (engine != MBPE_ENGINE_STEPWISE && engine != MBPE_ENGINE_PERSISTENT) return set_error(MBPE_E_INVALID, "bad engine");
+    int rc = use_device(t->device);
+    if (rc) return rc;
+    CudaBE be;
+    be.stream = (cudaStream_t)stream;
+    be.sms = sm_count(t->device);
+    be.pinned = t->pinned_ctl;
+    TrainConfig cfg{vocab_size, mode, engine, env_u32("MBPE_BIG_LIMIT", 16384), env_u32("MBPE_CAND_WANT", 1024),
+                    env_u32("MBPE_INIT_SLOTS", 0)};
+    TrainOutcome o;
+    *n_merges_out = 0;
+    MB_CUDA(cudaEventRecord(t->ev[0], be.stream));
+    int drc;
+    {
+        TrainLoop<CudaBE> loop(be);
+        drc = loop.run(t->d_tokens, t->d_off, t->d_weight, t->n_tokens, t->n_chunks, cfg, merges_out, counts_out, &o);
+    }
+    MB_CUDA(cudaEventRecord(t->ev[1], be.stream));
+    MB_CUDA(cudaStreamSynchronize(be.stream));
+    if (be.err != cudaSuccess) return cuda_fail(be.err, be.err_what, __FILE__, __LINE__);
+    if (drc) return set_error(MBPE_E_CUDA, "train loop reached an unknown state");
+    *n_merges_out = finish_merges(o, vocab_size, mode, merges_out, counts_out);
+    if (stats) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, t->ev[0], t->ev[1]);
+        memset(stats, 0, sizeof *stats);
+        stats->gpu_ms = ms;
+        stats->n_positions = t->n_tokens;
+        stats->n_pairs = o.n_pairs;
+        stats->table_slots = o.table_slots;
+        stats->n_launches = be.launches();
+        stats->n_big_merges = o.n_big;
+        stats->n_rebuilds = o.n_rebuilds;
+        stats->n_grows = o.n_grows;
+        stats->rescan_bytes = o.rescan_bytes;
+    }
+    return MBPE_OK;
+}
+
+extern "C" int mbpe_train(const uint32_t *tokens, uint64_t n_tokens, const uint64_t *chunk_off, uint64_t n_chunks,
+                          const uint32_t *chunk_weight, uint32_t vocab_size, int mode, uint32_t *merges_out,
+                          int32_t *counts_out, uint32_t *n_merges_out) {
+    mbpe_trainer *t = nullptr;
+    int rc = mbpe_trainer_create(tokens, n_tokens, chunk_off, n_chunks, chunk_weight, 0, &t);
+    if (rc) return rc;
+    rc = mbpe_trainer_run(t, vocab_size, mode, MBPE_ENGINE_PERSISTENT, nullptr, merges_out, counts_out, n_merges_out,
+                          nullptr);
+    mbpe_trainer_destroy(t);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// C ABI: PairCount seam (PairCount.h:27-47). Slot.first doubles as insert_order (index of the first add that
+// named the pair == next_insert++ order, PairCount.h:149).
+// ---------------------------------------------------------------------------------------------------------
+namespace mbpe {
+
+struct PcBest {
+    int32_t cnt;
+    uint32_t valid;
+    uint64_t tie;
+    uint64_t key;
+};
+__device__ __forceinline__ bool pc_better(const PcBest &x, const PcBest &y) { // x ranks before y
+    if (!x.valid) return false;
+    if (!y.valid) return true;
+    if (x.cnt != y.cnt) return x.cnt > y.cnt;
+    return x.tie < y.tie;
+}
+__device__ __forceinline__ PcBest pc_shfl_down(const PcBest &v, int d) {
+    PcBest r;
+    r.cnt = __shfl_down_sync(0xffffffffu, v.cnt, d);
+    r.valid = __shfl_down_sync(0xffffffffu, v.valid, d);
+    r.tie = __shfl_down_sync(0xffffffffu, v.tie, d);
+    r.key = __shfl_down_sync(0xffffffffu, v.key, d);
+    return r;
+}
+
+__global__ void k_pc_add(Slot *slot, uint32_t cap_mask, const uint32_t *a, const uint32_t *b, const int32_t *delta,
+                         uint64_t n, uint32_t order_base, uint32_t *n_pairs) {
+    Ctx c{};
+    c.slot = slot;
+    c.cap_mask = cap_mask;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        bool created;
+        uint32_t s = slot_upsert(c, pair_key(a[i], b[i]), &created);
+        if (created) atomicAdd(n_pairs, 1u);
+        atomicAdd(&slot[s].cnt, delta[i]);
+        atomicMin(&slot[s].first, order_base + (uint32_t)i);
+    }
+}
+
+// block-then-grid arg-max over the table: thread -> warp shuffle -> block shared memory -> per-block result;
+// the last block to finish reduces the per-block results (threadfence + ticket).
+__global__ void __launch_bounds__(256) k_pc_top(const Slot *slot, uint32_t cap, int mode, PcBest *block_best,
+                                                unsigned *ticket, PcBest *result) {
+    __shared__ PcBest sh[8];
+    __shared__ bool last;
+    PcBest best{0, 0, 0, 0};
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += gridDim.x * blockDim.x) {
+        uint64_t key = slot[s].key;
+        if (key == EMPTY_KEY) continue;
+        PcBest v{slot[s].cnt, 1u, mode == MBPE_MODE_LEXICAL ? key : (uint64_t)slot[s].first, key};
+        if (pc_better(v, best)) best = v;
+    }
+    auto block_reduce = [&](PcBest v) {
+        for (int d = 16; d > 0; d >>= 1) {
+            PcBest o = pc_shfl_down(v, d);
+            if (pc_better(o, v)) v = o;
+        }
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            v = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : PcBest{0, 0, 0, 0};
+            for (int d = 4; d > 0; d >>= 1) {
+                PcBest o = pc_shfl_down(v, d);
+                if (pc_better(o, v)) v = o;
+            }
+        }
+        return v;
+    };
+    best = block_reduce(best);
+    if (threadIdx.x == 0) {
+        block_best[blockIdx.x] = best;
+        __threadfence();
+        last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        PcBest v{0, 0, 0, 0};
+        for (uint32_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+            PcBest o = block_best[i];
+            if (pc_better(o, v)) v = o;
+        }
+        __syncthreads();
+        v = block_reduce(v);
+        if (threadIdx.x == 0) {
+            *result = v;
+            *ticket = 0;
+        }
+    }
+}
+
+__global__ void k_pc_get(const Slot *slot, uint32_t cap_mask, uint64_t key, int32_t *out /* cnt, found */) {
+    Ctx c{};
+    c.slot = const_cast<Slot *>(slot);
+    c.cap_mask = cap_mask;
+    uint32_t s = slot_find(c, key);
+    out[0] = s == NIL ? 0 : slot[s].cnt;
+    out[1] = s != NIL;
+}
+
+} // namespace mbpe
+
+struct mbpe_paircount {
+    int device = 0, mode = 0;
+    Slot *slot = nullptr;
+    uint32_t cap = 0;
+    uint32_t *d_n_pairs = nullptr;
+    uint64_t n_added = 0;
+    PcBest *d_block_best = nullptr, *d_result = nullptr;
+    unsigned *d_ticket = nullptr;
+    int32_t *d_get = nullptr;
+    int sms = 148;
+};
+
+static int pc_alloc_table(mbpe_paircount *pc, uint32_t cap) {
+    MB_CUDA(cudaMalloc(&pc->slot, (uint64_t)cap * sizeof(Slot)));
+    pc->cap = cap;
+    k_par<PhClearSlots><<<std::min<uint32_t>((cap + 255) / 256, pc->sms * 8), 256>>>(PhClearSlots{pc->slot, cap});
+    MB_CUDA(cudaGetLastError());
+    return MBPE_OK;
+}
+
+extern "C" int mbpe_paircount_create(int mode, int device, mbpe_paircount **out) {
+    if (!out) return set_error(MBPE_E_INVALID, "null argument");
+    *out = nullptr;
+    if (mode != MBPE_MODE_FIRST && mode != MBPE_MODE_LEXICAL) return set_error(MBPE_E_INVALID, "bad mode");
+    int rc = use_device(device);
+    if (rc) return rc;
+    mbpe_paircount *pc = new mbpe_paircount();
+    pc->device = device;
+    pc->mode = mode;
+    pc->sms = sm_count(device);
+    if ((rc = pc_alloc_table(pc, 1024))) return rc;
+    MB_CUDA(cudaMalloc(&pc->d_n_pairs, 4));
+    MB_CUDA(cudaMemset(pc->d_n_pairs, 0, 4));
+    MB_CUDA(cudaMalloc(&pc->d_block_best, sizeof(PcBest) * pc->sms * 8));
+    MB_CUDA(cudaMalloc(&pc->d_result, sizeof(PcBest)));
+    MB_CUDA(cudaMalloc(&pc->d_ticket, 4));
+    MB_CUDA(cudaMemset(pc->d_ticket, 0, 4));
+    MB_CUDA(cudaMalloc(&pc->d_get, 8));
+    *out = pc;
+    return MBPE_OK;
+}
+
+extern "C" void mbpe_paircount_destroy(mbpe_paircount *pc) {
+    if (!pc) return;
+    cudaSetDevice(pc->device);
+    cudaFree(pc->slot);
+    cudaFree(pc->d_n_pairs);
+    cudaFree(pc->d_block_best);
+    cudaFree(pc->d_result);
+    cudaFree(pc->d_ticket);
+    cudaFree(pc->d_get);
+    delete pc;
+}
+
+extern "C" int mbpe_paircount_size(mbpe_paircount *pc, uint64_t *n_pairs) {
+    if (!pc || !n_pairs) return set_error(MBPE_E_INVALID, "null argument");
+    int rc = use_device(pc->device);
+    if (rc) return rc;
+    uint32_t v = 0;
+    MB_CUDA(cudaMemcpy(&v, pc->d_n_pairs, 4, cudaMemcpyDeviceToHost));
+    *n_pairs = v;
+    return MBPE_OK;
+}
+
+extern "C" int mbpe_paircount_add(mbpe_paircount *pc, const uint32_t *a, const uint32_t *b, const int32_t *delta,
+                                  uint64_t n) {
+    if (!pc || (n && (!a || !b || !delta))) return set_error(MBPE_E_INVALID, "null argument");
+    if (n == 0) return MBPE_OK;
+    if (pc->n_added + n >= 0xFFFFFFFFull) return set_error(MBPE_E_INVALID, "insert_order space exhausted");
+    int rc = use_device(pc->device);
+    if (rc) return rc;
+    uint64_t cur = 0;
+    if ((rc = mbpe_paircount_size(pc, &cur))) return rc;
+    if ((cur + n) * 2 > pc->cap) { // keep load <= 1/2 even if every record names a new pair
+        Slot *old = pc->slot;
+        uint32_t old_cap = pc->cap, cap = pc->cap;
+        while ((cur + n) * 2 > cap) cap *= 2;
+        if ((rc = pc_alloc_table(pc, cap))) return rc;
+        Ctx c{};
+        c.slot = pc->slot;
+        c.cap_mask = cap - 1;
+        k_par<PhRehash><<<std::min<uint32_t>((old_cap + 255) / 256, pc->sms * 8), 256>>>(PhRehash{c, old, old_cap});
+        MB_CUDA(cudaGetLastError());
+        MB_CUDA(cudaDeviceSynchronize());
+        MB_CUDA(cudaFree(old));
+    }
+    uint32_t *da, *db;
+    int32_t *dd;
+    MB_CUDA(cudaMalloc(&da, n * 4));
+    MB_CUDA(cudaMalloc(&db, n * 4));
+    MB_CUDA(cudaMalloc(&dd, n * 4));
+    MB_CUDA(cudaMemcpy(da, a, n * 4, cudaMemcpyHostToDevice));
+    MB_CUDA(cudaMemcpy(db, b, n * 4, cudaMemcpyHostToDevice));
+    MB_CUDA(cudaMemcpy(dd, delta, n * 4, cudaMemcpyHostToDevice));
+    unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)pc->sms * 8);
+    k_pc_add<<<grid, 256>>>(pc->slot, pc->cap - 1, da, db, dd, n, (uint32_t)pc->n_added, pc->d_n_pairs);
+    MB_CUDA(cudaGetLastError());
+    MB_CUDA(cudaDeviceSynchronize());
+    pc->n_added += n;
+    cudaFree(da);
+    cudaFree(db);
+    cudaFree(dd);
+    return MBPE_OK;
+}
+
+extern "C" int mbpe_paircount_top(mbpe_paircount *pc, uint32_t *a, uint32_t *b, int32_t *count, int *found) {
+    if (!pc || !a || !b || !count || !found) return set_error(MBPE_E_INVALID, "null argument");
+    int rc = use_device(pc->device);
+    if (rc) return rc;
+    unsigned grid = std::min<uint32_t>((pc->cap + 255) / 256, pc->sms * 8);
+    k_pc_top<<<grid, 256>>>(pc->slot, pc->cap, pc->mode, pc->d_block_best, pc->d_ticket, pc->d_result);
+    MB_CUDA(cudaGetLastError());
+    PcBest r;
+    MB_CUDA(cudaMemcpy(&r, pc->d_result, sizeof r, cudaMemcpyDeviceToHost));
+    *found = r.valid != 0;
+    *a = (uint32_t)(r.key >> 32);
+    *b = (uint32_t)r.key;
+    *count = r.cnt;
+    return MBPE_OK;
+}
+
+extern "C" int mbpe_paircount_get(mbpe_paircount *pc, uint32_t a, uint32_t b, int32_t *count, int *found) {
+    if (!pc || !count || !found) return set_error(MBPE_E_INVALID, "null argument");
+    int rc = use_device(pc->device);
+    if (rc) return rc;
+    k_pc_get<<<1, 1>>>(pc->slot, pc->cap - 1, pair_key(a, b), pc->d_get);
+    MB_CUDA(cudaGetLastError());
+    int32_t r[2];
+    MB_CUDA(cudaMemcpy(r, pc->d_get, 8, cudaMemcpyDeviceToHost));
+    *count = r[0];
+    *found = r[1];
+    return MBPE_OK;
+}

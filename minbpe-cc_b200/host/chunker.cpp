@@ -1,0 +1,439 @@
+// chunker.cpp -- regex pre-tokenisation (PCRE2), chunk dedup and the synthetic corpus generator. Host side.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <thread>
+
+#include "bpe_host.hpp"
+
+namespace mbpe::host {
+
+const char *const kGpt2Pattern = "'(?:[sdmt]|ll|ve|re)| ?\\p{L}+| ?\\p{N}+| ?[^\\s\\p{L}\\p{N}]+|\\s+(?!\\S)|\\s+";
+const char *const kGpt4Pattern =
+    "'(?i:[sdmt]|ll|ve|re)|[^\\r\\n\\p{L}\\p{N}]?+\\p{L}+|\\p{N}{1,3}| ?[^\\s\\p{L}\\p{N}]++[\\r\\n]*|\\s*[\\r\\n]|\\s+(?!\\S)|\\s+";
+
+int hardware_threads() {
+    unsigned n = std::thread::hardware_concurrency();
+    return n ? (int)n : 1;
+}
+
+Regex::~Regex() {
+    if (code_) pcre2_code_free_8(code_);
+}
+
+int Regex::compile(const std::string &pattern, std::string *err) {
+    if (code_) {
+        pcre2_code_free_8(code_);
+        code_ = nullptr;
+    }
+    if (pattern.empty()) return MBPE_OK; // encoder "basic": no regex (Tokenizer.h:400)
+    uint32_t options = MBPE_PCRE2_UTF | MBPE_PCRE2_UCP;                            // Tokenizer.h:407
+    if (pattern.find("(?i:") != std::string::npos) options |= MBPE_PCRE2_CASELESS; // Tokenizer.h:413-415
+    int errcode = 0;
+    size_t erroff = 0;
+    code_ = pcre2_compile_8(reinterpret_cast<const uint8_t *>(pattern.data()), pattern.size(), options, &errcode,
+                            &erroff, nullptr);
+    if (!code_) {
+        uint8_t buf[256];
+        pcre2_get_error_message_8(errcode, buf, sizeof buf);
+        if (err) *err = std::string("PCRE2 pattern compilation failed: ") + reinterpret_cast<char *>(buf);
+        return MBPE_E_REGEX;
+    }
+    pcre2_jit_compile_8(code_, MBPE_PCRE2_JIT_COMPLETE); // failure just means the interpreter runs
+    return MBPE_OK;
+}
+
+// Matches over text[0, len) starting at `begin`, stopping at the first match that starts at or after `stop`.
+// The subject is always the WHOLE text so that look-aheads at the end of a segment see the real next byte.
+template <class Emit>
+static int match_loop(const Regex &re, const uint8_t *text, uint64_t len, uint64_t begin, uint64_t stop,
+                      std::string *err, Emit emit) {
+    pcre2_match_data_8 *md = pcre2_match_data_create_from_pattern_8(re.code(), nullptr);
+    if (!md) {
+        if (err) *err = "PCRE2 match data creation failed.";
+        return MBPE_E_REGEX;
+    }
+    size_t offset = begin;
+    int rc_out = MBPE_OK;
+    while (offset < stop || (begin == stop && offset == begin)) {
+        int rc = pcre2_match_8(re.code(), text, len, offset, MBPE_PCRE2_NO_UTF_CHECK, md, nullptr);
+        if (rc < 0) {
+            if (rc != MBPE_PCRE2_ERROR_NOMATCH) {
+                uint8_t buf[256];
+                pcre2_get_error_message_8(rc, buf, sizeof buf);
+                if (err) *err = std::string("PCRE2 match error: ") + reinterpret_cast<char *>(buf);
+                rc_out = MBPE_E_REGEX;
+            }
+            break;
+        }
+        const size_t *ov = pcre2_get_ovector_pointer_8(md);
+        size_t s = ov[0], e = ov[1];
+        if (s == e) { // empty match: step one byte (Tokenizer.h:529-533)
+            if (offset >= len) break;
+            offset++;
+            continue;
+        }
+        if (s >= stop) break; // belongs to the next segment
+        emit((uint64_t)s, (uint64_t)e);
+        offset = e;
+    }
+    pcre2_match_data_free_8(md);
+    return rc_out;
+}
+
+int split_range(const Regex &re, const uint8_t *text, uint64_t len, uint64_t begin, uint64_t stop,
+                std::vector<Span> &out, std::string *err) {
+    if (re.empty()) { // whole text is one chunk (Tokenizer.h:541-544)
+        out.push_back(Span{0, len});
+        return MBPE_OK;
+    }
+    return match_loop(re, text, len, begin, stop, err, [&](uint64_t s, uint64_t e) { out.push_back(Span{s, e}); });
+}
+
+// cut points p (0 < p < len) where no match of the GPT-2/GPT-4 patterns can span p: text[p-1] == '\n' and
+// text[p] is a printable non-space ASCII byte (a byte >= 0x80 could start a multi-byte Unicode space).
+static std::vector<uint64_t> safe_cuts(const uint8_t *text, uint64_t len, int parts) {
+    std::vector<uint64_t> cuts{0};
+    for (int k = 1; k < parts; k++) {
+        uint64_t p = std::max<uint64_t>(len / parts * k, cuts.back() + 1);
+        while (p < len && !(text[p - 1] == '\n' && text[p] >= 0x21 && text[p] <= 0x7E)) p++;
+        if (p >= len) break;
+        cuts.push_back(p);
+    }
+    cuts.push_back(len);
+    return cuts;
+}
+
+static bool builtin_pattern(const std::string &p) { return p == kGpt2Pattern || p == kGpt4Pattern; }
+
+int split_parallel(const Regex &re, const std::string &pattern, const uint8_t *text, uint64_t len, int n_threads,
+                   std::vector<Span> &out, std::string *err) {
+    if (n_threads <= 0) n_threads = hardware_threads();
+    if (re.empty() || !builtin_pattern(pattern) || n_threads == 1 || len < (1u << 16))
+        return split_range(re, text, len, 0, len, out, err);
+    std::vector<uint64_t> cuts = safe_cuts(text, len, n_threads * 4);
+    const size_t n_seg = cuts.size() - 1;
+    std::vector<std::vector<Span>> parts(n_seg);
+    std::vector<int> rcs(n_seg, MBPE_OK);
+    std::vector<std::string> errs(n_seg);
+    std::atomic<size_t> next{0};
+    auto work = [&]() {
+        for (size_t s; (s = next.fetch_add(1)) < n_seg;)
+            rcs[s] = split_range(re, text, len, cuts[s], cuts[s + 1], parts[s], &errs[s]);
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; t++) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+    size_t total = out.size();
+    for (size_t s = 0; s < n_seg; s++) {
+        if (rcs[s] != MBPE_OK) {
+            if (err) *err = errs[s];
+            return rcs[s];
+        }
+        total += parts[s].size();
+    }
+    out.reserve(total);
+    for (auto &p : parts) out.insert(out.end(), p.begin(), p.end());
+    return MBPE_OK;
+}
+
+bool marker_token(std::string_view chunk, Token *id) {
+    if (chunk.empty() || chunk[0] != '\0') return false;
+    try {
+        int v = std::stoi(std::string(chunk.substr(1))); // Tokenizer.h:88
+        *id = static_cast<Token>(v);
+        return true;
+    } catch (...) {
+        return false; // falls back to plain bytes (Tokenizer.h:90-92)
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// dedup: unique chunk -> count, first-appearance order
+// ---------------------------------------------------------------------------------------------------------
+static inline uint64_t hash_bytes(const uint8_t *p, uint64_t n) {
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ (n * 0xff51afd7ed558ccdULL);
+    while (n >= 8) {
+        uint64_t w;
+        memcpy(&w, p, 8);
+        h = (h ^ w) * 0xc4ceb9fe1a85ec53ULL;
+        h ^= h >> 29;
+        p += 8;
+        n -= 8;
+    }
+    uint64_t w = 0;
+    memcpy(&w, p, n);
+    h = (h ^ w) * 0xff51afd7ed558ccdULL;
+    h ^= h >> 32;
+    return h;
+}
+
+struct UniqueSet {
+    struct Item {
+        uint64_t hash, start;
+        uint32_t len, count;
+    };
+    std::vector<Item> items;      // first-appearance order
+    std::vector<uint32_t> slots;  // index + 1, 0 = empty
+    uint64_t mask = 0;
+
+    void init(uint64_t cap) {
+        uint64_t c = 1024;
+        while (c < cap) c <<= 1;
+        slots.assign(c, 0);
+        mask = c - 1;
+    }
+    void grow() {
+        std::vector<uint32_t> ns((mask + 1) * 2, 0);
+        uint64_t m = ns.size() - 1;
+        for (uint32_t i = 0; i < items.size(); i++) {
+            uint64_t h = items[i].hash & m;
+            while (ns[h]) h = (h + 1) & m;
+            ns[h] = i + 1;
+        }
+        slots.swap(ns);
+        mask = m;
+    }
+    void add(const uint8_t *text, uint64_t hash, uint64_t start, uint32_t len, uint32_t count) {
+        uint64_t h = hash & mask;
+        while (slots[h]) {
+            Item &it = items[slots[h] - 1];
+            if (it.hash == hash && it.len == len && memcmp(text + it.start, text + start, len) == 0) {
+                it.count += count;
+                return;
+            }
+            h = (h + 1) & mask;
+        }
+        items.push_back(Item{hash, start, len, count});
+        slots[h] = (uint32_t)items.size();
+        if (items.size() * 2 > mask) grow();
+    }
+};
+
+void dedup_chunks(const uint8_t *text, const std::vector<Span> &chunks, int n_threads, Corpus &out) {
+    if (n_threads <= 0) n_threads = hardware_threads();
+    const uint64_t n = chunks.size();
+    if (n < (1u << 16)) n_threads = 1;
+    std::vector<UniqueSet> local(n_threads);
+    auto work = [&](int t) {
+        uint64_t k0 = n * t / n_threads, k1 = n * (t + 1) / n_threads;
+        local[t].init(1 << 16);
+        for (uint64_t k = k0; k < k1; k++) {
+            uint64_t s = chunks[k].start, l = chunks[k].end - s;
+            local[t].add(text, hash_bytes(text + s, l), s, (uint32_t)l, 1);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto &t : th) t.join();
+    // merge in thread (= text) order: global first-appearance order is preserved
+    UniqueSet *g = &local[0];
+    for (int t = 1; t < n_threads; t++)
+        for (const auto &it : local[t].items) g->add(text, it.hash, it.start, it.len, it.count);
+
+    out.n_chunks = n;
+    out.off.clear();
+    out.weight.clear();
+    out.tokens.clear();
+    uint64_t total = 0;
+    for (const auto &it : g->items) total += it.len;
+    out.tokens.reserve(total);
+    out.off.reserve(g->items.size() + 1);
+    out.weight.reserve(g->items.size());
+    out.off.push_back(0);
+    for (const auto &it : g->items) {
+        Token id;
+        std::string_view sv(reinterpret_cast<const char *>(text + it.start), it.len);
+        if (it.len && text[it.start] == 0 && marker_token(sv, &id))
+            out.tokens.push_back(id);
+        else
+            for (uint32_t i = 0; i < it.len; i++) out.tokens.push_back(text[it.start + i]);
+        out.off.push_back(out.tokens.size());
+        out.weight.push_back(it.count);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// synthetic Zipfian UTF-8 corpus (SURVEY 8(d) input 3). Deterministic in (seed, n): the text is generated in
+// independent 1 MiB blocks, each seeded by (seed, block index), so any number of threads gives the same bytes.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct SplitMix {
+    uint64_t s;
+    uint64_t next() {
+        uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    }
+    double unit() { return (next() >> 11) * (1.0 / 9007199254740992.0); }
+    uint32_t below(uint32_t n) { return (uint32_t)(((next() >> 32) * (uint64_t)n) >> 32); }
+};
+
+constexpr uint32_t kWords = 1u << 20;
+constexpr double kZipfS = 1.07;
+
+struct WordList {
+    std::vector<uint32_t> off;
+    std::vector<uint8_t> bytes;
+    std::vector<double> prob;   // alias table
+    std::vector<uint32_t> alias;
+};
+
+// cumulative English-like letter frequencies (per 1000) for a..z
+const uint16_t kLetterCum[26] = {82, 97, 125, 168, 295, 317, 337, 398, 468, 470, 478, 518, 542,
+                                 609, 684, 703, 704, 764, 827, 918, 946, 956, 980, 982, 1000, 1001};
+char letter(SplitMix &r) {
+    uint32_t v = r.below(1001);
+    for (int i = 0; i < 26; i++)
+        if (v < kLetterCum[i]) return (char)('a' + i);
+    return 'e';
+}
+void put_utf8(std::vector<uint8_t> &b, uint32_t cp) {
+    if (cp < 0x80)
+        b.push_back((uint8_t)cp);
+    else if (cp < 0x800) {
+        b.push_back(0xC0 | (cp >> 6));
+        b.push_back(0x80 | (cp & 63));
+    } else if (cp < 0x10000) {
+        b.push_back(0xE0 | (cp >> 12));
+        b.push_back(0x80 | ((cp >> 6) & 63));
+        b.push_back(0x80 | (cp & 63));
+    } else {
+        b.push_back(0xF0 | (cp >> 18));
+        b.push_back(0x80 | ((cp >> 12) & 63));
+        b.push_back(0x80 | ((cp >> 6) & 63));
+        b.push_back(0x80 | (cp & 63));
+    }
+}
+uint32_t poisson4(SplitMix &r) { // Knuth, lambda = 4
+    const double L = std::exp(-4.0);
+    uint32_t k = 0;
+    double p = 1.0;
+    do {
+        k++;
+        p *= r.unit();
+    } while (p > L);
+    return k - 1;
+}
+
+// the word list ("language") is fixed; the corpus seed only drives which words are drawn, so a model trained
+// on one synthetic corpus is meaningful on another
+constexpr uint64_t kLanguageSeed = 0x5EED0000ull;
+
+const WordList &word_list() {
+    static WordList wl;
+    static bool built = false;
+    static std::mutex *mu = new std::mutex();
+    std::lock_guard<std::mutex> lock(*mu);
+    if (built) return wl;
+    const uint64_t seed = kLanguageSeed;
+    wl.off.reserve(kWords + 1);
+    wl.off.push_back(0);
+    for (uint32_t i = 0; i < kWords; i++) {
+        SplitMix r{seed ^ (0xA5A5A5A5ull + (uint64_t)i * 0x9E3779B97F4A7C15ull)};
+        uint32_t len = std::min<uint32_t>(1 + poisson4(r), 16);
+        double kind = r.unit();
+        if (kind < 0.92) { // lowercase
+            for (uint32_t k = 0; k < len; k++) wl.bytes.push_back((uint8_t)letter(r));
+        } else if (kind < 0.95) { // Capitalised
+            for (uint32_t k = 0; k < len; k++) {
+                char c = letter(r);
+                wl.bytes.push_back((uint8_t)(k == 0 ? c - 32 : c));
+            }
+        } else { // letters from other scripts: Latin-1 supplement, Cyrillic, CJK, emoji
+            uint32_t script = r.below(4);
+            for (uint32_t k = 0; k < len; k++) {
+                uint32_t cp;
+                switch (script) {
+                case 0: cp = (k & 1) ? 0xE0 + r.below(23) : (uint32_t)letter(r); break; // àáâ... mixed with ASCII
+                case 1: cp = 0x430 + r.below(32); break;                                 // а..я
+                case 2: cp = 0x4E00 + r.below(2048); break;                              // CJK ideographs
+                default: cp = 0x1F600 + r.below(64); break;                              // emoji
+                }
+                put_utf8(wl.bytes, cp);
+                if (script >= 2 && k >= 3) break; // keep CJK / emoji words short
+            }
+        }
+        wl.off.push_back((uint32_t)wl.bytes.size());
+    }
+    // Zipf(s) over ranks 1..kWords, Walker alias table
+    std::vector<double> w(kWords);
+    double sum = 0;
+    for (uint32_t i = 0; i < kWords; i++) sum += (w[i] = std::pow((double)(i + 1), -kZipfS));
+    wl.prob.assign(kWords, 0.0);
+    wl.alias.assign(kWords, 0);
+    std::vector<uint32_t> small, large;
+    for (uint32_t i = 0; i < kWords; i++) {
+        w[i] = w[i] / sum * kWords;
+        (w[i] < 1.0 ? small : large).push_back(i);
+    }
+    while (!small.empty() && !large.empty()) {
+        uint32_t s = small.back(), l = large.back();
+        small.pop_back();
+        wl.prob[s] = w[s];
+        wl.alias[s] = l;
+        w[l] = (w[l] + w[s]) - 1.0;
+        if (w[l] < 1.0) {
+            large.pop_back();
+            small.push_back(l);
+        }
+    }
+    for (uint32_t i : large) wl.prob[i] = 1.0;
+    for (uint32_t i : small) wl.prob[i] = 1.0;
+    built = true;
+    return wl;
+}
+
+void fill_block(const WordList &wl, uint64_t seed, uint64_t block, uint8_t *out, uint64_t n) {
+    SplitMix r{seed * 0xD6E8FEB86659FD93ull + block * 0x9E3779B97F4A7C15ull + 1};
+    uint64_t o = 0;
+    uint8_t tmp[80];
+    while (o < n) {
+        uint32_t wlen;
+        const uint8_t *wp;
+        if (r.unit() < 0.03) { // 1-6 digit number
+            wlen = 1 + r.below(6);
+            for (uint32_t k = 0; k < wlen; k++) tmp[k] = (uint8_t)('0' + r.below(10));
+            wp = tmp;
+        } else {
+            uint32_t i = r.below(kWords);
+            if (r.unit() >= wl.prob[i]) i = wl.alias[i];
+            wp = wl.bytes.data() + wl.off[i];
+            wlen = wl.off[i + 1] - wl.off[i];
+        }
+        double sep = r.unit();
+        const char *sp = sep < 0.82 ? " " : sep < 0.87 ? ", " : sep < 0.92 ? ". " : sep < 0.98 ? "\n" : "\n\n";
+        uint32_t slen = (uint32_t)strlen(sp);
+        if (o + wlen + slen > n) { // tail of the block: pad with spaces, end the block on a newline
+            while (o + 1 < n) out[o++] = ' ';
+            out[o++] = '\n';
+            break;
+        }
+        memcpy(out + o, wp, wlen);
+        o += wlen;
+        memcpy(out + o, sp, slen);
+        o += slen;
+    }
+}
+} // namespace
+
+void synth_corpus(uint64_t seed, uint8_t *out, uint64_t n, int n_threads) {
+    if (n_threads <= 0) n_threads = hardware_threads();
+    const WordList &wl = word_list();
+    const uint64_t B = 1ull << 20, n_blocks = (n + B - 1) / B;
+    std::atomic<uint64_t> next{0};
+    auto work = [&]() {
+        for (uint64_t b; (b = next.fetch_add(1)) < n_blocks;) fill_block(wl, seed, b, out + b * B, std::min(B, n - b * B));
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads && (uint64_t)t < n_blocks; t++) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+}
+
+} // namespace mbpe::host

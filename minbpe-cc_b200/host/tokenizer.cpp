@@ -1,0 +1,562 @@
+// tokenizer.cpp -- host mirror of MinBpeCC::Tokenizer::Tokenizer (Tokenizer.h:379-927) over the GPU engine,
+// and the tokenizer / host-only part of the C ABI.
+#include <chrono>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+
+#include "bpe_host.hpp"
+
+namespace mbpe::host {
+
+static double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+Tokenizer::Tokenizer(const std::string &pattern, int device) : pattern_(pattern), device_(device) {
+    if (regex_.compile(pattern_, &error_) != MBPE_OK) throw std::runtime_error(error_); // Tokenizer.h:427-431
+    rebuild_vocab();
+}
+
+Tokenizer::~Tokenizer() {
+    if (encoder_) mbpe_encoder_destroy(encoder_);
+}
+
+void Tokenizer::set_special_tokens_from_file(const std::string &contents) {
+    special_tokens_.clear();
+    special_reverse_.clear();
+    std::istringstream iss(contents);
+    std::string key;
+    Token value;
+    while (iss >> key >> value) { // "token id" per line (Tokenizer.h:482-485)
+        special_tokens_[key] = value;
+        special_reverse_[value] = key;
+    }
+    encoder_stale_ = true;
+}
+
+void Tokenizer::rebuild_vocab() { // Tokenizer.h:103-111 + :844-861
+    vocab_.clear();
+    vocab_.reserve(256 + merges_.size());
+    for (int i = 0; i < 256; i++) vocab_.push_back(std::string(1, static_cast<char>(i)));
+    for (const auto &[a, b] : merges_) vocab_.push_back(vocab_[a] + vocab_[b]);
+}
+
+static std::string printable(const std::string &bytes) { // Tokenizer.h:569-575
+    std::string s;
+    for (unsigned char c : bytes) s += (c >= 32 && c < 127) ? static_cast<char>(c) : ' ';
+    return s;
+}
+
+int Tokenizer::train(std::string_view text, int vocab_size, CONFLICT_RESOLUTION mode, bool verbose) {
+    if (vocab_size < 256) { // assert in the reference (Tokenizer.h:492)
+        error_ = "vocab_size must be >= 256";
+        return MBPE_E_INVALID;
+    }
+    merges_.clear();
+    rebuild_vocab();
+    encoder_stale_ = true;
+    if (regex_.empty() && text.empty()) { // the reference dereferences an empty list here
+        error_ = "empty training text";
+        return MBPE_E_EMPTY;
+    }
+    const uint8_t *bytes = reinterpret_cast<const uint8_t *>(text.data());
+    double t0 = now_s();
+    std::vector<Span> spans;
+    int rc = split_parallel(regex_, pattern_, bytes, text.size(), n_threads_, spans, &error_);
+    if (rc) return rc;
+    double t1 = now_s();
+    if (verbose) std::cout << "Split input text into " << spans.size() << " chunks\n"; // Tokenizer.h:547
+    Corpus corpus;
+    dedup_chunks(bytes, spans, n_threads_, corpus);
+    std::vector<Span>().swap(spans);
+    double t2 = now_s();
+    last_split_s = t1 - t0;
+    last_dedup_s = t2 - t1;
+    last_n_chunks = corpus.n_chunks;
+    last_n_unique = corpus.weight.size();
+
+    const uint32_t n_target = static_cast<uint32_t>(vocab_size - 256);
+    std::vector<uint32_t> m(2ull * std::max<uint32_t>(n_target, 1));
+    std::vector<int32_t> counts(std::max<uint32_t>(n_target, 1));
+    uint32_t n_merges = 0;
+    mbpe_trainer *tr = nullptr;
+    rc = mbpe_trainer_create(corpus.tokens.data(), corpus.tokens.size(), corpus.off.data(), corpus.weight.size(),
+                             corpus.weight.data(), device_, &tr);
+    if (rc) {
+        error_ = mbpe_last_error();
+        return rc;
+    }
+    rc = mbpe_trainer_run(tr, static_cast<uint32_t>(vocab_size), mode, engine_, nullptr, m.data(), counts.data(),
+                          &n_merges, &last_stats);
+    mbpe_trainer_destroy(tr);
+    if (rc) {
+        error_ = mbpe_last_error();
+        return rc;
+    }
+    merges_.reserve(n_merges);
+    for (uint32_t i = 0; i < n_merges; i++) {
+        Token a = m[2 * i], b = m[2 * i + 1];
+        vocab_.push_back(vocab_[a] + vocab_[b]); // Tokenizer.h:562-564
+        if (verbose) // Tokenizer.h:576
+            std::cout << "merge " << i + 1 << "/" << n_target << ": (" << a << ", " << b << ") -> " << 256 + i << " (b'"
+                      << printable(vocab_.back()) << "') had " << counts[i] << " occurrences\n";
+        merges_.emplace_back(a, b);
+    }
+    if (verbose) // Tokenizer.h:591-597 prints the per-copy length; the GPU path keeps unique chunks only
+        std::cout << "Length of training text " << text.length() << ". Unique chunks " << last_n_unique << " of "
+                  << last_n_chunks << ", " << last_stats.n_positions << " resident tokens.\n";
+    return MBPE_OK;
+}
+
+std::vector<std::string> Tokenizer::split_on_special(std::string_view text) {
+    std::vector<std::string> result;
+    if (special_tokens_.empty()) {
+        result.emplace_back(text);
+        return result;
+    }
+    size_t pos = 0, last = 0;
+    while (pos < text.size()) {
+        size_t found_pos = std::string::npos, found_len = 0;
+        Token found_id = 0;
+        for (const auto &kv : special_tokens_) { // earliest occurrence wins; ties go to map order (Tokenizer.h:618-626)
+            size_t p = text.find(kv.first, pos);
+            if (p != std::string::npos && (found_pos == std::string::npos || p < found_pos)) {
+                found_pos = p;
+                found_len = kv.first.size();
+                found_id = kv.second;
+            }
+        }
+        if (found_pos == std::string::npos) break;
+        if (found_pos > last) result.emplace_back(text.substr(last, found_pos - last));
+        std::string marker(1, '\0');
+        marker += std::to_string(found_id);
+        result.push_back(std::move(marker));
+        pos = found_pos + found_len;
+        last = pos;
+    }
+    if (last < text.size()) result.emplace_back(text.substr(last));
+    if (result.empty()) result.emplace_back(text);
+    return result;
+}
+
+int Tokenizer::ensure_encoder() {
+    if (encoder_ && !encoder_stale_) return MBPE_OK;
+    if (encoder_) {
+        mbpe_encoder_destroy(encoder_);
+        encoder_ = nullptr;
+    }
+    std::vector<uint32_t> m;
+    m.reserve(2 * merges_.size());
+    for (const auto &[a, b] : merges_) {
+        m.push_back(a);
+        m.push_back(b);
+    }
+    int rc = mbpe_encoder_create(m.data(), static_cast<uint32_t>(merges_.size()), device_, &encoder_);
+    if (rc) {
+        error_ = mbpe_last_error();
+        return rc;
+    }
+    std::vector<uint32_t> ids;
+    std::vector<uint8_t> bytes;
+    std::vector<uint64_t> off{0};
+    for (const auto &kv : special_reverse_) {
+        ids.push_back(kv.first);
+        bytes.insert(bytes.end(), kv.second.begin(), kv.second.end());
+        off.push_back(bytes.size());
+    }
+    if (!ids.empty()) {
+        rc = mbpe_encoder_set_specials(encoder_, ids.data(), bytes.data(), off.data(), static_cast<uint32_t>(ids.size()));
+        if (rc) {
+            error_ = mbpe_last_error();
+            return rc;
+        }
+    }
+    encoder_stale_ = false;
+    return MBPE_OK;
+}
+
+int Tokenizer::encode(std::string_view text, bool verbose, std::vector<Token> &out) {
+    out.clear();
+    int rc = ensure_encoder();
+    if (rc) return rc;
+    std::vector<std::string> parts;
+    bool single = special_tokens_.empty();
+    if (!single) parts = split_on_special(text);
+    const size_t n_parts = single ? 1 : parts.size();
+    if (verbose) std::cout << "Splitting input text into " << n_parts << " parts\n";
+
+    // chunk list over one byte arena; ready-made ids (special markers) are spliced in afterwards
+    std::vector<uint8_t> arena_copy;
+    const uint8_t *arena = nullptr;
+    std::vector<uint64_t> off{0};
+    std::vector<std::pair<uint64_t, Token>> ready; // (index of the chunk this id precedes, id)
+    std::vector<Span> spans;
+    auto add_chunk = [&](std::string_view chunk) {
+        Token id;
+        if (!chunk.empty() && chunk[0] == '\0' && marker_token(chunk, &id)) {
+            ready.emplace_back(off.size() - 1, id);
+            return;
+        }
+        arena_copy.insert(arena_copy.end(), chunk.begin(), chunk.end());
+        off.push_back(arena_copy.size());
+    };
+    if (single && !regex_.empty()) {
+        const uint8_t *bytes = reinterpret_cast<const uint8_t *>(text.data());
+        rc = split_parallel(regex_, pattern_, bytes, text.size(), n_threads_, spans, &error_);
+        if (rc) return rc;
+        bool contiguous = !spans.empty() && spans.front().start == 0 && spans.back().end == text.size();
+        for (size_t i = 0; contiguous && i < spans.size(); i++) {
+            if (i && spans[i].start != spans[i - 1].end) contiguous = false;
+            if (bytes[spans[i].start] == 0) contiguous = false; // possible ready-made id: take the general path
+        }
+        if (contiguous) { // the usual case: the text itself is the arena, no copy
+            arena = bytes;
+            off.resize(spans.size() + 1);
+            for (size_t i = 0; i < spans.size(); i++) off[i + 1] = spans[i].end;
+        } else {
+            for (const auto &s : spans) add_chunk(text.substr(s.start, s.end - s.start));
+        }
+    } else {
+        for (size_t p = 0; p < n_parts; p++) {
+            std::string_view part = single ? text : std::string_view(parts[p]);
+            bool special = !part.empty() && part[0] == '\0';
+            if (special || regex_.empty()) { // one chunk (Tokenizer.h:667-671, :706-709)
+                add_chunk(part);
+                continue;
+            }
+            spans.clear();
+            rc = split_parallel(regex_, pattern_, reinterpret_cast<const uint8_t *>(part.data()), part.size(), n_threads_,
+                                spans, &error_);
+            if (rc) return rc;
+            for (const auto &s : spans) add_chunk(part.substr(s.start, s.end - s.start));
+        }
+    }
+    if (!arena) arena = arena_copy.data();
+    const uint64_t n_chunks = off.size() - 1, n_bytes = off.back();
+    std::vector<Token> ids(std::max<uint64_t>(n_bytes, 1));
+    std::vector<uint64_t> out_off;
+    if (!ready.empty()) out_off.resize(n_chunks + 1);
+    uint64_t n_ids = 0;
+    rc = mbpe_encode(encoder_, arena, n_bytes, off.data(), n_chunks, ids.data(), ids.size(), &n_ids,
+                     ready.empty() ? nullptr : out_off.data());
+    if (rc) {
+        error_ = mbpe_last_error();
+        return rc;
+    }
+    if (ready.empty()) {
+        ids.resize(n_ids);
+        out.swap(ids);
+    } else {
+        out.reserve(n_ids + ready.size());
+        uint64_t done = 0;
+        for (const auto &[before_chunk, id] : ready) {
+            uint64_t upto = out_off[before_chunk];
+            out.insert(out.end(), ids.begin() + done, ids.begin() + upto);
+            done = upto;
+            out.push_back(id);
+        }
+        out.insert(out.end(), ids.begin() + done, ids.begin() + n_ids);
+    }
+    if (verbose) std::cout << "Encoded input text (length " << text.length() << ") to " << out.size() << " tokens\n";
+    return MBPE_OK;
+}
+
+int Tokenizer::decode(const std::vector<Token> &tokens, bool verbose, std::string &out) {
+    out.clear();
+    if (verbose) std::cout << "Decoding " << tokens.size() << " tokens\n";
+    int rc = ensure_encoder();
+    if (rc) return rc;
+    for (Token t : tokens) // same diagnostics as the reference (Tokenizer.h:739-742)
+        if (t >= vocab_.size() && special_reverse_.find(t) == special_reverse_.end())
+            std::cerr << "Warning: Attempted to decode invalid token ID: " << t << "\n";
+    uint64_t n = 0;
+    rc = mbpe_decode(encoder_, tokens.data(), tokens.size(), nullptr, 0, &n);
+    if (rc) {
+        error_ = mbpe_last_error();
+        return rc;
+    }
+    out.resize(n);
+    if (n) {
+        rc = mbpe_decode(encoder_, tokens.data(), tokens.size(), reinterpret_cast<uint8_t *>(out.data()), n, &n);
+        if (rc) {
+            error_ = mbpe_last_error();
+            return rc;
+        }
+    }
+    return MBPE_OK;
+}
+
+int Tokenizer::load(const std::string &path, bool verbose) {
+    std::ifstream in(path, std::ios::in);
+    if (!in.is_open()) {
+        std::cerr << "Failed to open file for loading: " << path << "\n";
+        error_ = "cannot open " + path;
+        return MBPE_E_IO;
+    }
+    std::string version;
+    std::getline(in, version);
+    if (version != "minbpe v1") {
+        std::cerr << "Unexpected version: " << version << "\n";
+        error_ = "unexpected version line";
+        return MBPE_E_IO;
+    }
+    merges_.clear();
+    std::getline(in, pattern_);
+    if (regex_.compile(pattern_, &error_) != MBPE_OK) {
+        std::cerr << "PCRE2 compilation failed on load: " << error_ << "\n";
+        return MBPE_E_REGEX;
+    }
+    int num_special = 0;
+    in >> num_special;
+    for (int i = 0; i < num_special; i++) { // existing specials are kept, as in the reference
+        std::string token;
+        Token id;
+        in >> token >> id;
+        special_tokens_[token] = id;
+        special_reverse_[id] = token;
+        if (verbose) std::cout << "Loaded special token: " << token << " with ID " << id << "\n";
+    }
+    Token a, b;
+    while (in >> a >> b) {
+        if (a >= 256 + merges_.size() || b >= 256 + merges_.size()) { // the reference would index past vocab
+            error_ = "merge line names an id that does not exist yet";
+            return MBPE_E_IO;
+        }
+        merges_.emplace_back(a, b);
+    }
+    if (verbose) std::cout << "Read input model from " << path << "\n";
+    rebuild_vocab();
+    if (verbose)
+        std::cout << "Loaded vocab with " << merges_.size() << " merges, vocab size is " << vocab_.size() << "\n";
+    encoder_stale_ = true;
+    return MBPE_OK;
+}
+
+int write_model_files(const std::string &path, const std::string &pattern,
+                      const std::unordered_map<std::string, Token> &specials,
+                      const std::vector<std::pair<Token, Token>> &merges, const std::vector<std::string> *vocab,
+                      std::string *err) {
+    std::ofstream out(path, std::ios::out);
+    if (!out.is_open()) {
+        std::cerr << "Unable to open file for saving: " << path << std::endl;
+        if (err) *err = "cannot open " + path;
+        return MBPE_E_IO;
+    }
+    std::cout << "Writing model...\n";
+    out << "minbpe v1" << '\n' << pattern << '\n' << specials.size() << '\n';
+    for (const auto &st : specials) out << st.first << ' ' << st.second << '\n'; // map iteration order
+    for (const auto &[a, b] : merges) out << a << ' ' << b << "\n";
+    out.close();
+    if (vocab) {
+        const std::string vpath = path + ".vocab"; // appended, not an extension swap (Tokenizer.h:896)
+        std::ofstream vf(vpath, std::ios::out);
+        if (!vf.is_open()) {
+            std::cerr << "Failed to open .vocab file for writing: " << vpath << std::endl;
+            if (err) *err = "cannot open " + vpath;
+            return MBPE_E_IO;
+        }
+        Token id = 0;
+        for (const auto &v : *vocab) { // Tokenizer.h:905-917
+            vf << std::setw(6) << std::left << id << ": \"";
+            for (unsigned char c : v) {
+                if (c >= 32 && c <= 126)
+                    vf << static_cast<char>(c);
+                else
+                    vf << "\xEF\xBF\xBD";
+            }
+            vf << "\"\n";
+            id++;
+        }
+    }
+    std::cout << "Complete.\n";
+    return MBPE_OK;
+}
+
+int Tokenizer::save(const std::string &path, bool write_vocab) {
+    if (merges_.empty()) { // assert in the reference (Tokenizer.h:876)
+        error_ = "no merges to save";
+        return MBPE_E_EMPTY;
+    }
+    return write_model_files(path, pattern_, special_tokens_, merges_, write_vocab ? &vocab_ : nullptr, &error_);
+}
+
+} // namespace mbpe::host
+
+// ---------------------------------------------------------------------------------------------------------
+// C ABI: tokenizer mirror + host-only helpers
+// ---------------------------------------------------------------------------------------------------------
+using namespace mbpe::host;
+
+namespace mbpe {
+std::string &last_error_ref();
+}
+static int fail(int code, const std::string &msg) {
+    mbpe::last_error_ref() = msg;
+    return code;
+}
+
+struct mbpe_tokenizer {
+    Tokenizer tk;
+    mbpe_tokenizer(const char *p, int device) : tk(p ? p : "", device) {}
+};
+
+extern "C" const char *mbpe_gpt2_split_pattern(void) { return kGpt2Pattern; }
+extern "C" const char *mbpe_gpt4_split_pattern(void) { return kGpt4Pattern; }
+
+extern "C" int mbpe_tokenizer_create(const char *pattern, int device, mbpe_tokenizer **out) {
+    if (!out) return fail(MBPE_E_INVALID, "null argument");
+    *out = nullptr;
+    try {
+        *out = new mbpe_tokenizer(pattern, device);
+    } catch (const std::exception &e) {
+        return fail(MBPE_E_REGEX, e.what());
+    }
+    return MBPE_OK;
+}
+extern "C" void mbpe_tokenizer_destroy(mbpe_tokenizer *t) { delete t; }
+extern "C" int mbpe_tokenizer_set_special_tokens(mbpe_tokenizer *t, const char *contents, uint64_t len) {
+    if (!t || (!contents && len)) return fail(MBPE_E_INVALID, "null argument");
+    t->tk.set_special_tokens_from_file(std::string(contents ? contents : "", len));
+    return MBPE_OK;
+}
+extern "C" int mbpe_tokenizer_train(mbpe_tokenizer *t, const uint8_t *text, uint64_t len, int vocab_size, int mode,
+                                    int verbose) {
+    if (!t || (!text && len)) return fail(MBPE_E_INVALID, "null argument");
+    if (mode != MBPE_MODE_FIRST && mode != MBPE_MODE_LEXICAL) return fail(MBPE_E_INVALID, "bad mode");
+    int rc = t->tk.train(std::string_view(reinterpret_cast<const char *>(text), len), vocab_size,
+                         static_cast<Tokenizer::CONFLICT_RESOLUTION>(mode), verbose != 0);
+    return rc ? fail(rc, t->tk.error()) : MBPE_OK;
+}
+extern "C" int mbpe_tokenizer_save(mbpe_tokenizer *t, const char *path, int write_vocab) {
+    if (!t || !path) return fail(MBPE_E_INVALID, "null argument");
+    int rc = t->tk.save(path, write_vocab != 0);
+    return rc ? fail(rc, t->tk.error()) : MBPE_OK;
+}
+extern "C" int mbpe_tokenizer_load(mbpe_tokenizer *t, const char *path, int verbose) {
+    if (!t || !path) return fail(MBPE_E_INVALID, "null argument");
+    int rc = t->tk.load(path, verbose != 0);
+    return rc ? fail(rc, t->tk.error()) : MBPE_OK;
+}
+extern "C" int mbpe_tokenizer_encode(mbpe_tokenizer *t, const uint8_t *text, uint64_t len, uint32_t *out,
+                                     uint64_t out_cap, uint64_t *n_out) {
+    if (!t || !n_out || (!text && len)) return fail(MBPE_E_INVALID, "null argument");
+    std::vector<Token> ids;
+    int rc = t->tk.encode(std::string_view(reinterpret_cast<const char *>(text), len), false, ids);
+    if (rc) return fail(rc, t->tk.error());
+    *n_out = ids.size();
+    if (!out) return MBPE_OK;
+    if (ids.size() > out_cap) return fail(MBPE_E_CAPACITY, "out too small; *n_out holds the needed count");
+    memcpy(out, ids.data(), ids.size() * sizeof(Token));
+    return MBPE_OK;
+}
+extern "C" int mbpe_tokenizer_decode(mbpe_tokenizer *t, const uint32_t *ids, uint64_t n, uint8_t *out,
+                                     uint64_t out_cap, uint64_t *n_out) {
+    if (!t || !n_out || (!ids && n)) return fail(MBPE_E_INVALID, "null argument");
+    std::string s;
+    int rc = t->tk.decode(std::vector<Token>(ids, ids + n), false, s);
+    if (rc) return fail(rc, t->tk.error());
+    *n_out = s.size();
+    if (!out) return MBPE_OK;
+    if (s.size() > out_cap) return fail(MBPE_E_CAPACITY, "out too small; *n_out holds the needed size");
+    memcpy(out, s.data(), s.size());
+    return MBPE_OK;
+}
+extern "C" int mbpe_tokenizer_get_merges(mbpe_tokenizer *t, uint32_t *merges_out, uint32_t cap_pairs,
+                                         uint32_t *n_merges) {
+    if (!t || !n_merges) return fail(MBPE_E_INVALID, "null argument");
+    const auto &m = t->tk.merges();
+    *n_merges = static_cast<uint32_t>(m.size());
+    if (!merges_out) return MBPE_OK;
+    if (m.size() > cap_pairs) return fail(MBPE_E_CAPACITY, "merges_out too small");
+    for (size_t i = 0; i < m.size(); i++) {
+        merges_out[2 * i] = m[i].first;
+        merges_out[2 * i + 1] = m[i].second;
+    }
+    return MBPE_OK;
+}
+extern "C" int mbpe_tokenizer_last_train_stats(mbpe_tokenizer *t, mbpe_train_stats *stats, double *split_s,
+                                               double *dedup_s, uint64_t *n_chunks, uint64_t *n_unique) {
+    if (!t) return fail(MBPE_E_INVALID, "null argument");
+    if (stats) *stats = t->tk.last_stats;
+    if (split_s) *split_s = t->tk.last_split_s;
+    if (dedup_s) *dedup_s = t->tk.last_dedup_s;
+    if (n_chunks) *n_chunks = t->tk.last_n_chunks;
+    if (n_unique) *n_unique = t->tk.last_n_unique;
+    return MBPE_OK;
+}
+extern "C" void mbpe_tokenizer_set_engine(mbpe_tokenizer *t, int engine) {
+    if (t) t->tk.set_engine(engine);
+}
+extern "C" void mbpe_tokenizer_set_threads(mbpe_tokenizer *t, int n_threads) {
+    if (t) t->tk.set_threads(n_threads);
+}
+
+extern "C" int mbpe_split(const char *pattern, const uint8_t *text, uint64_t len, int n_threads, uint64_t *starts,
+                          uint64_t *ends, uint64_t cap, uint64_t *n_chunks) {
+    if (!pattern || !n_chunks || (!text && len)) return fail(MBPE_E_INVALID, "null argument");
+    Regex re;
+    std::string err;
+    int rc = re.compile(pattern, &err);
+    if (rc) return fail(rc, err);
+    std::vector<Span> spans;
+    rc = split_parallel(re, pattern, text, len, n_threads, spans, &err);
+    if (rc) return fail(rc, err);
+    *n_chunks = spans.size();
+    if (!starts || !ends) return MBPE_OK;
+    if (spans.size() > cap) return fail(MBPE_E_CAPACITY, "starts/ends too small");
+    for (size_t i = 0; i < spans.size(); i++) {
+        starts[i] = spans[i].start;
+        ends[i] = spans[i].end;
+    }
+    return MBPE_OK;
+}
+
+extern "C" int mbpe_dedup(const uint8_t *text, const uint64_t *starts, const uint64_t *ends, uint64_t n_chunks,
+                          uint32_t *tokens_out, uint64_t *n_tokens, uint64_t *off_out, uint32_t *weight_out,
+                          uint64_t *n_unique) {
+    if (!n_tokens || !n_unique || (n_chunks && (!text || !starts || !ends))) return fail(MBPE_E_INVALID, "null argument");
+    std::vector<Span> spans(n_chunks);
+    for (uint64_t i = 0; i < n_chunks; i++) spans[i] = Span{starts[i], ends[i]};
+    Corpus c;
+    dedup_chunks(text, spans, 0, c);
+    *n_tokens = c.tokens.size();
+    *n_unique = c.weight.size();
+    if (tokens_out) memcpy(tokens_out, c.tokens.data(), c.tokens.size() * 4);
+    if (off_out) memcpy(off_out, c.off.data(), c.off.size() * 8);
+    if (weight_out) memcpy(weight_out, c.weight.data(), c.weight.size() * 4);
+    return MBPE_OK;
+}
+
+extern "C" int mbpe_write_model(const char *path, const char *pattern, const char *special_contents,
+                                uint64_t special_len, const uint32_t *merges, uint32_t n_merges, int write_vocab) {
+    if (!path || !pattern || (n_merges && !merges)) return fail(MBPE_E_INVALID, "null argument");
+    if (n_merges == 0) return fail(MBPE_E_EMPTY, "no merges to save");
+    std::unordered_map<std::string, Token> specials; // filled exactly as set_special_tokens_from_file does
+    if (special_contents && special_len) {
+        std::istringstream iss(std::string(special_contents, special_len));
+        std::string key;
+        Token value;
+        while (iss >> key >> value) specials[key] = value;
+    }
+    std::vector<std::pair<Token, Token>> m;
+    std::vector<std::string> vocab;
+    for (int i = 0; i < 256; i++) vocab.push_back(std::string(1, static_cast<char>(i)));
+    for (uint32_t i = 0; i < n_merges; i++) {
+        Token a = merges[2 * i], b = merges[2 * i + 1];
+        if (a >= vocab.size() || b >= vocab.size()) return fail(MBPE_E_INVALID, "merge names an id that does not exist yet");
+        m.emplace_back(a, b);
+        vocab.push_back(vocab[a] + vocab[b]);
+    }
+    std::string err;
+    int rc = write_model_files(path, pattern, specials, m, write_vocab ? &vocab : nullptr, &err);
+    return rc ? fail(rc, err) : MBPE_OK;
+}
+
+extern "C" int mbpe_synth_corpus(uint64_t seed, uint8_t *out, uint64_t n, int n_threads) {
+    if (!out && n) return fail(MBPE_E_INVALID, "null argument");
+    synth_corpus(seed, out, n, n_threads);
+    return MBPE_OK;
+}

