@@ -262,6 +262,14 @@ void dedup_chunks(const uint8_t *text, const std::vector<Span> &chunks, int n_th
 // independent 1 MiB blocks, each seeded by (seed, block index), so any number of threads gives the same bytes.
 // ---------------------------------------------------------------------------------------------------------
 namespace {
+inline uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+// independent stream per (seed, index): the state is a hash, not an offset into one shared sequence
+inline uint64_t stream_seed(uint64_t seed, uint64_t index) { return mix64(mix64(seed) ^ mix64(index * 2 + 1)); }
+
 struct SplitMix {
     uint64_t s;
     uint64_t next() {
@@ -335,7 +343,7 @@ const WordList &word_list() {
     wl.off.reserve(kWords + 1);
     wl.off.push_back(0);
     for (uint32_t i = 0; i < kWords; i++) {
-        SplitMix r{seed ^ (0xA5A5A5A5ull + (uint64_t)i * 0x9E3779B97F4A7C15ull)};
+        SplitMix r{stream_seed(seed, i)};
         uint32_t len = std::min<uint32_t>(1 + poisson4(r), 16);
         double kind = r.unit();
         if (kind < 0.92) { // lowercase
@@ -390,7 +398,7 @@ const WordList &word_list() {
 }
 
 void fill_block(const WordList &wl, uint64_t seed, uint64_t block, uint8_t *out, uint64_t n) {
-    SplitMix r{seed * 0xD6E8FEB86659FD93ull + block * 0x9E3779B97F4A7C15ull + 1};
+    SplitMix r{stream_seed(seed ^ 0xB10C5EEDull, block)};
     uint64_t o = 0;
     uint8_t tmp[80];
     while (o < n) {

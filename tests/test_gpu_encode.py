@@ -1,0 +1,126 @@
+"""GPU: parity of the encode merge scan and the decode gather (through the C ABI) with the reference."""
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_data
+
+pytestmark = pytest.mark.gpu
+
+
+def _cases():
+    man = json.load(open(os.path.join(GOLDEN, "manifest.json")))
+    return sorted(k for k, e in man["encode"].items() if e["rc"] == 0)
+
+
+@pytest.mark.parametrize("name", _cases())
+def test_tokenizer_encode_matches_reference_stream(pkg, manifest, name):
+    e = manifest["encode"][name]
+    tk = pkg.Tokenizer(pkg.patterns()["gpt4"])  # replaced by the pattern stored in the model
+    tk.load(os.path.join(GOLDEN, "models", e["model"] + ".model"))
+    text = golden_data(e["input"])
+    ids = tk.encode(text)
+    assert len(ids) == e["n_tokens"]
+    assert hashlib.sha256(ids.tobytes()).hexdigest() == e["enc_sha256"]
+    assert tk.decode(ids) == text  # endtoend-test.sh round trip
+
+
+def test_expected_ids_of_special_token_sample(pkg):
+    tk = pkg.Tokenizer("")
+    tk.load(os.path.join(GOLDEN, "models", "ts512_gpt4_first_special.model"))
+    ids = tk.encode(golden_data("specialtokensample.txt"))
+    assert ids.tolist() == [84, 104, 355, 32, 355, 306, 288, 101, 261, 101, 120, 116, 434, 287, 349, 262, 116, 97, 259,
+                            115, 32, 100258, 261, 119, 111, 306, 112, 310, 478, 108, 32, 100257, 348, 107, 290, 115, 46]
+
+
+def test_chunk_level_encode_vs_oracle_incl_offsets(pkg, oracle):
+    _, _, merges = oracle.read_model(os.path.join(GOLDEN, "models", "shk4096_gpt4_lexical_special.model"))
+    text = golden_data("shakespeare.txt")
+    s, e = oracle.split(text, oracle.GPT4_SPLIT_PATTERN)
+    off = np.concatenate([s, e[-1:]])
+    enc = pkg.Encoder(merges)
+    ids, out_off = enc.encode(text, off, want_off=True)
+    oids, ooff = oracle.encode_chunks(merges, text, s, e)
+    assert np.array_equal(ids, oids) and np.array_equal(out_off, ooff)
+
+
+def test_ragged_empty_and_long_chunks(pkg, oracle):
+    _, _, merges = oracle.read_model(os.path.join(GOLDEN, "models", "ts512_gpt4_lexical.model"))
+    enc = pkg.Encoder(merges)
+    assert len(enc.encode(b"", [0])) == 0
+    text = golden_data("taylorswift.txt")[:50000]
+    rng = np.random.default_rng(9)
+    cuts = np.unique(np.concatenate([[0, len(text)], rng.integers(0, len(text), 3000),
+                                     np.arange(1000, 1200)]))  # 1-byte chunks, mixed with chunks > 64 bytes
+    cuts = np.sort(np.concatenate([cuts, cuts[5:15]]))            # and a few empty chunks
+    ids, out_off = enc.encode(text, cuts, want_off=True)
+    oids, ooff = oracle.encode_chunks(merges, text, cuts[:-1], cuts[1:])
+    assert np.array_equal(ids, oids) and np.array_equal(out_off, ooff)
+    # one chunk = whole text (encoder "basic")
+    ids = enc.encode(text, [0, len(text)])
+    oids, _ = oracle.encode_chunks(merges, text, [0], [len(text)])
+    assert np.array_equal(ids, oids)
+
+
+def test_duplicate_merge_lines_overwrite(pkg, oracle):
+    """SURVEY F4/Tokenizer.h:835: a pair listed twice maps to the LATER id."""
+    _, _, merges = oracle.read_model(os.path.join(GOLDEN, "models", "str_exhaust_basic_lexical.model"))
+    assert len(merges) == 44
+    enc = pkg.Encoder(merges)
+    text = b"abcdebce abab"
+    ids = enc.encode(text, [0, len(text)])
+    oids, _ = oracle.encode_chunks(merges, text, [0], [len(text)])
+    assert np.array_equal(ids, oids) and 299 in ids.tolist()
+    assert enc.decode(ids) == text
+
+
+def test_decode_invalid_ids_and_special_override(pkg, oracle):
+    merges = np.asarray([[97, 98], [256, 99]], np.uint32)
+    enc = pkg.Encoder(merges)
+    ids = [97, 256, 999999, 257, 98, 258]
+    assert enc.decode(ids) == oracle.decode(merges, ids, {}) == b"aababcb"
+    sp = {256: b"<S>", 100257: b"<|endoftext|>", 65: b"<A>"}
+    enc.set_specials(sp)
+    ids = [65, 256, 100257, 257, 5000]
+    assert enc.decode(ids) == oracle.decode(merges, ids, sp) == b"<A><S><|endoftext|>abc"
+    assert enc.decode([]) == b""
+
+
+def test_large_synthetic_roundtrip_and_oracle_slice(pkg, oracle):
+    """Size-independent property at a bench-like size: decode(encode(x)) == x; plus an oracle diff on a slice."""
+    text = pkg.synth_corpus(0x5EED0002, 64 << 20).tobytes()
+    tk = pkg.Tokenizer(pkg.patterns()["gpt4"])
+    tk.train(text[: 8 << 20], 256 + 2000, "lexical")
+    ids = tk.encode(text)
+    assert tk.decode(ids) == text
+    merges = tk.merges()
+    cut = text.rfind(b"\nq", 0, 4 << 20) + 1 or (4 << 20)
+    s, e = oracle.split(text[:cut], oracle.GPT4_SPLIT_PATTERN)
+    oids, _ = oracle.encode_chunks(merges, text[:cut], s, e)
+    assert np.array_equal(ids[:len(oids)], oids)
+
+
+def test_cli_end_to_end(pkg, manifest, tmp_path):
+    """endtoend-test.sh, both scenarios, through the flag-compatible CLI; models must equal the goldens."""
+    cli, data = pkg.CLI_PATH, os.path.join(GOLDEN, "data")
+    run = lambda *a: subprocess.run([cli, *a], check=True, capture_output=True)
+    m1 = str(tmp_path / "basic-model")
+    run("--train", "--input", f"{data}/shakespeare.txt", "--model-path", m1, "--vocab-size", "512", "--encoder", "basic",
+        "--conflict-resolution", "lexical")
+    assert hashlib.sha256(open(m1, "rb").read()).hexdigest() == manifest["train"]["shk512_basic_lexical"]["model_sha256"]
+    run("--encode", "--input", f"{data}/sample.txt", "--model-path", m1, "--output", str(tmp_path / "s.enc"))
+    assert (hashlib.sha256((tmp_path / "s.enc").read_bytes()).hexdigest()
+            == manifest["encode"]["sample__shk512_basic_lexical"]["enc_sha256"])
+    run("--decode", "--input", str(tmp_path / "s.enc"), "--model-path", m1, "--output", str(tmp_path / "s.txt"))
+    assert (tmp_path / "s.txt").read_bytes() == golden_data("sample.txt")
+    m2 = str(tmp_path / "gpt4-model")
+    run("-t", "-i", f"{data}/taylorswift.txt", "-s", f"{data}/special1.txt", "-m", m2, "--vocab-size=512",
+        "--encoder", "gpt4", "-c", "first")
+    assert hashlib.sha256(open(m2, "rb").read()).hexdigest() == manifest["train"]["ts512_gpt4_first_special"]["model_sha256"]
+    run("-e", "-i", f"{data}/specialtokensample.txt", "-m", m2, "-o", str(tmp_path / "t.enc"))
+    run("-d", "-i", str(tmp_path / "t.enc"), "-m", m2, "-o", str(tmp_path / "t.txt"))
+    assert (tmp_path / "t.txt").read_bytes() == golden_data("specialtokensample.txt")
