@@ -180,6 +180,11 @@ int mbpe_split(const char *pattern, const uint8_t *text, uint64_t len, int n_thr
  * n_chunks, n_tokens <= sum of lengths. */
 int mbpe_dedup(const uint8_t *text, const uint64_t *starts, const uint64_t *ends, uint64_t n_chunks,
                uint32_t *tokens_out, uint64_t *n_tokens, uint64_t *off_out, uint32_t *weight_out, uint64_t *n_unique);
+/* the train front end in one call: regex split + dedup fused and multi-threaded (the chunk list is never
+ * materialised). Call with tokens_out == NULL to size (the result is kept for the following call). */
+int mbpe_split_dedup(const char *pattern, const uint8_t *text, uint64_t len, int n_threads, uint32_t *tokens_out,
+                     uint64_t tokens_cap, uint64_t *n_tokens, uint64_t *off_out, uint32_t *weight_out,
+                     uint64_t unique_cap, uint64_t *n_unique, uint64_t *n_chunks);
 /* .model / .vocab writer given a merge list (Tokenizer.h:875-926) */
 int mbpe_write_model(const char *path, const char *pattern, const char *special_contents, uint64_t special_len,
                      const uint32_t *merges, uint32_t n_merges, int write_vocab);

@@ -29,7 +29,7 @@ EXPORTS = [
     "mbpe_tokenizer_set_special_tokens", "mbpe_tokenizer_train", "mbpe_tokenizer_save", "mbpe_tokenizer_load",
     "mbpe_tokenizer_encode", "mbpe_tokenizer_decode", "mbpe_tokenizer_get_merges",
     "mbpe_tokenizer_last_train_stats", "mbpe_tokenizer_set_engine", "mbpe_tokenizer_set_threads",
-    "mbpe_split", "mbpe_dedup", "mbpe_write_model", "mbpe_synth_corpus",
+    "mbpe_split", "mbpe_dedup", "mbpe_split_dedup", "mbpe_write_model", "mbpe_synth_corpus",
 ]
 
 
@@ -329,13 +329,12 @@ class Tokenizer:
 def split(pattern: str, text: bytes, n_threads=0):
     n = C.c_uint64()
     buf = _u8(text)
-    _ck(lib().mbpe_split(pattern.encode(), _p(buf, C.c_uint8), C.c_uint64(len(text)), n_threads, None, None,
-                         C.c_uint64(0), C.byref(n)))
-    s = np.zeros(max(n.value, 1), np.uint64)
-    e = np.zeros(max(n.value, 1), np.uint64)
+    cap = len(text) + 1  # a chunk is at least one byte; untouched pages of the zeroed arrays cost nothing
+    s = np.zeros(cap, np.uint64)
+    e = np.zeros(cap, np.uint64)
     _ck(lib().mbpe_split(pattern.encode(), _p(buf, C.c_uint8), C.c_uint64(len(text)), n_threads, _p(s, C.c_uint64),
-                         _p(e, C.c_uint64), C.c_uint64(len(s)), C.byref(n)))
-    return s[:n.value], e[:n.value]
+                         _p(e, C.c_uint64), C.c_uint64(cap), C.byref(n)))
+    return s[:n.value].copy(), e[:n.value].copy()
 
 
 def dedup(text: bytes, starts, ends):
@@ -350,6 +349,21 @@ def dedup(text: bytes, starts, ends):
                          C.c_uint64(len(starts)), _p(tokens, C.c_uint32), C.byref(nt), _p(off, C.c_uint64),
                          _p(w, C.c_uint32), C.byref(nu)))
     return tokens[:nt.value].copy(), off[:nu.value + 1].copy(), w[:nu.value].copy()
+
+
+def split_dedup(pattern: str, text: bytes, n_threads=0):
+    """regex split + dedup fused (the train front end). Returns (tokens, off, weight, n_chunks)."""
+    buf = _u8(text)
+    nt, nu, nc = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    args = (pattern.encode(), _p(buf, C.c_uint8), C.c_uint64(len(text)), n_threads)
+    _ck(lib().mbpe_split_dedup(*args, None, C.c_uint64(0), C.byref(nt), None, None, C.c_uint64(0), C.byref(nu),
+                               C.byref(nc)))
+    tokens = np.zeros(max(nt.value, 1), np.uint32)
+    off = np.zeros(nu.value + 1, np.uint64)
+    w = np.zeros(max(nu.value, 1), np.uint32)
+    _ck(lib().mbpe_split_dedup(*args, _p(tokens, C.c_uint32), C.c_uint64(len(tokens)), C.byref(nt), _p(off, C.c_uint64),
+                               _p(w, C.c_uint32), C.c_uint64(len(w)), C.byref(nu), C.byref(nc)))
+    return tokens[:nt.value], off, w[:nu.value], nc.value
 
 
 def write_model(path, pattern, special_contents, merges, write_vocab=False):

@@ -127,6 +127,7 @@ __global__ void k_encode_long(EncTable tab, const uint8_t *bytes, const uint32_t
 struct EncArgs {
     EncTable tab;
     const uint8_t *bytes;
+    uint64_t n_bytes_total; // bytes readable from `bytes` (vector loads never cross it)
     const uint32_t *off;
     uint64_t n_chunks;
     uint32_t *out;
@@ -141,35 +142,113 @@ struct EncArgs {
     uint32_t *overflow;          // set when out_cap is too small
 };
 
-__global__ void __launch_bounds__(ENC_THREADS) k_encode_tiles(const EncArgs a) {
+// A tile = ET_CHUNKS consecutive chunks. Its text is staged into shared memory with coalesced 16-byte loads,
+// one u32 token slot per byte; each thread owns ET_CPT consecutive chunks (a private, contiguous slot range) and
+// runs the passes in place. Per pass the pair lookups of up to 8 positions are issued together (independent
+// read-only loads in flight), then resolved left to right.
+constexpr int ET_CPT = 4;
+constexpr int ET_CHUNKS = ENC_THREADS * ET_CPT;
+constexpr int ET_CAP = 10240; // staged bytes per tile; a tile with more text takes the unstaged path
+constexpr uint32_t ENC_NONE = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t enc_lookup_id(const EncTable &t, uint32_t a, uint32_t b) {
+    uint32_t id;
+    return enc_lookup(t, a, b, id) ? id : ENC_NONE;
+}
+
+// passes over t[0..len) (shared memory, private to the thread), in place. Returns the final length.
+__device__ __forceinline__ uint32_t enc_chunk_smem(const EncTable &tab, uint32_t *t, uint32_t len) {
+    while (len >= 2) {
+        uint32_t w = 0;
+        bool skip = false, merged = false;
+        for (uint32_t base = 0; base < len; base += 8) {
+            uint32_t v[9], id[8];
+#pragma unroll
+            for (int i = 0; i < 9; i++) v[i] = (base + i < len) ? t[base + i] : 0u;
+#pragma unroll
+            for (int i = 0; i < 8; i++) id[i] = (base + i + 1 < len) ? enc_lookup_id(tab, v[i], v[i + 1]) : ENC_NONE;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if (base + i < len) {
+                    if (skip) {
+                        skip = false;
+                    } else if (id[i] != ENC_NONE) {
+                        t[w++] = id[i];
+                        skip = true;
+                        merged = true;
+                    } else {
+                        t[w++] = v[i];
+                    }
+                }
+            }
+        }
+        len = w;
+        if (!merged) break;
+    }
+    return len;
+}
+
+__global__ void __launch_bounds__(ENC_THREADS, 4) k_encode_tiles(const EncArgs a) {
+    __shared__ uint32_t s_off[ET_CHUNKS + 1];
+    __shared__ uint32_t s_tok[ET_CAP];
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_warp[ENC_THREADS / 32];
     __shared__ unsigned long long s_base;
-    uint32_t t[ENC_SHORT_MAX];
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u); // tiles start in order: look-back cannot deadlock
+        if (tid == 0) s_tile = atomicAdd(a.ticket, 1u); // tiles start in order: look-back cannot deadlock
         __syncthreads();
         const uint32_t tile = s_tile;
         if (tile >= a.n_tiles) return;
-        const uint64_t c = (uint64_t)tile * ENC_THREADS + threadIdx.x;
-        uint32_t len = 0, o = 0;
-        bool is_long = false;
-        if (c < a.n_chunks) {
-            o = __ldg(&a.off[c]);
-            len = __ldg(&a.off[c + 1]) - o;
-            if (len > ENC_SHORT_MAX) {
-                is_long = true;
-                len = a.scratch_b[o];
-            } else {
-                for (uint32_t i = 0; i < len; i++) t[i] = __ldg(&a.bytes[o + i]);
-                bool merged = true;
-                while (merged && len >= 2) len = enc_pass(a.tab, t, len, merged);
+        const uint64_t c0 = (uint64_t)tile * ET_CHUNKS;
+        const uint32_t nc = (uint32_t)min((uint64_t)ET_CHUNKS, a.n_chunks - c0);
+        for (uint32_t i = tid; i <= nc; i += ENC_THREADS) s_off[i] = __ldg(&a.off[c0 + i]);
+        __syncthreads();
+        const uint32_t b0 = s_off[0], b1 = s_off[nc], nb = b1 - b0;
+        const bool staged = nb <= ET_CAP;
+        if (staged) {
+            const uint32_t a0 = b0 & ~15u; // 16-byte aligned window start (cudaMalloc'd buffers are 256-aligned)
+            for (uint32_t v = tid; a0 + v * 16 < b1; v += ENC_THREADS) {
+                const uint32_t g0 = a0 + v * 16;
+                if (g0 + 16 <= a.n_bytes_total) {
+                    uint4 q = __ldg(reinterpret_cast<const uint4 *>(a.bytes + g0));
+                    uint32_t wds[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        uint32_t g = g0 + j;
+                        if (g >= b0 && g < b1) s_tok[g - b0] = (wds[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
+                    }
+                } else {
+                    for (uint32_t g = max(g0, b0); g < b1 && g < g0 + 16; g++) s_tok[g - b0] = __ldg(&a.bytes[g]);
+                }
+            }
+            __syncthreads();
+        }
+        uint32_t cnt[ET_CPT], sum = 0;
+#pragma unroll
+        for (int j = 0; j < ET_CPT; j++) {
+            const uint32_t k = tid * ET_CPT + j;
+            cnt[j] = 0;
+            if (k < nc) {
+                const uint32_t o = s_off[k], len = s_off[k + 1] - o;
+                if (len > ENC_SHORT_MAX) {
+                    cnt[j] = a.scratch_b[o]; // encoded by k_encode_long
+                } else if (staged) {
+                    cnt[j] = enc_chunk_smem(a.tab, &s_tok[o - b0], len);
+                } else { // unstaged tile: count now, encode again when writing
+                    uint32_t t[ENC_SHORT_MAX];
+                    for (uint32_t i = 0; i < len; i++) t[i] = __ldg(&a.bytes[o + i]);
+                    uint32_t l2 = len;
+                    bool merged = true;
+                    while (merged && l2 >= 2) l2 = enc_pass(a.tab, t, l2, merged);
+                    cnt[j] = l2;
+                }
+                sum += cnt[j];
             }
         }
-        // block exclusive scan of len
-        uint32_t incl = len;
+        // block exclusive scan of the per-thread sums
+        uint32_t incl = sum;
         for (int d = 1; d < 32; d <<= 1) {
             uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += v;
@@ -177,27 +256,42 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_tiles(const EncArgs a) {
         if (lane == 31) s_warp[warp] = incl;
         __syncthreads();
         uint32_t warp_base = 0, total = 0;
+#pragma unroll
         for (int w = 0; w < ENC_THREADS / 32; w++) {
             uint32_t v = s_warp[w];
             if (w < (int)warp) warp_base += v;
             total += v;
         }
-        if (threadIdx.x == 0) s_base = lookback_base(a.status, tile, total);
+        if (tid == 0) s_base = lookback_base(a.status, tile, total);
         __syncthreads();
         const uint64_t base = s_base;
-        const uint64_t dst = base + warp_base + (incl - len);
-        if (c < a.n_chunks) {
-            if (a.out_off) a.out_off[c] = dst;
-            if (dst + len <= a.out_cap) {
-                if (is_long)
-                    for (uint32_t i = 0; i < len; i++) a.out[dst + i] = a.scratch_a[o + i];
-                else
-                    for (uint32_t i = 0; i < len; i++) a.out[dst + i] = t[i];
-            } else if (len) {
-                *a.overflow = 1;
+        uint64_t dst = base + warp_base + (incl - sum);
+#pragma unroll
+        for (int j = 0; j < ET_CPT; j++) {
+            const uint32_t k = tid * ET_CPT + j;
+            if (k < nc) {
+                const uint32_t o = s_off[k], len = s_off[k + 1] - o, n = cnt[j];
+                if (a.out_off) a.out_off[c0 + k] = dst;
+                if (dst + n <= a.out_cap) {
+                    if (len > ENC_SHORT_MAX) {
+                        for (uint32_t i = 0; i < n; i++) a.out[dst + i] = a.scratch_a[o + i];
+                    } else if (staged) {
+                        for (uint32_t i = 0; i < n; i++) a.out[dst + i] = s_tok[o - b0 + i];
+                    } else {
+                        uint32_t t[ENC_SHORT_MAX];
+                        for (uint32_t i = 0; i < len; i++) t[i] = __ldg(&a.bytes[o + i]);
+                        uint32_t l2 = len;
+                        bool merged = true;
+                        while (merged && l2 >= 2) l2 = enc_pass(a.tab, t, l2, merged);
+                        for (uint32_t i = 0; i < n; i++) a.out[dst + i] = t[i];
+                    }
+                } else if (n) {
+                    *a.overflow = 1;
+                }
+                dst += n;
             }
         }
-        if (tile == a.n_tiles - 1 && threadIdx.x == 0) {
+        if (tile == a.n_tiles - 1 && tid == 0) {
             *a.d_n_out = base + total;
             if (a.out_off) a.out_off[a.n_chunks] = base + total;
         }
@@ -443,7 +537,7 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
     if (n_bytes >= (1ull << 32)) return set_error(MBPE_E_INVALID, "a device batch must be < 4 GiB of text");
     int rc = mbpe_encode_reserve(e, n_bytes, n_chunks);
     if (rc) return rc;
-    uint64_t n_tiles = (n_chunks + ENC_THREADS - 1) / ENC_THREADS;
+    uint64_t n_tiles = (n_chunks + ET_CHUNKS - 1) / ET_CHUNKS;
     if (n_tiles >= 0xFFFFFFFFull) return set_error(MBPE_E_INVALID, "too many chunks in one batch");
     MB_CUDA(cudaMemsetAsync(e->d_small, 0, 16, st));
     if (n_chunks == 0) {
@@ -483,6 +577,7 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
     EncArgs a{};
     a.tab = tab;
     a.bytes = d_bytes;
+    a.n_bytes_total = n_bytes;
     a.off = d_off;
     a.n_chunks = n_chunks;
     a.out = d_out;

@@ -28,33 +28,166 @@ __global__ void __launch_bounds__(32) k_one(const F f) {
     if (threadIdx.x == 0) f();
 }
 
-struct DevExec {
-    template <class F>
-    __device__ __forceinline__ void par(const F &f) {
-        f(threadIdx.x, blockDim.x);
-        __syncthreads();
-    }
-    template <class F, class G>
-    __device__ __forceinline__ void par2(const F &f, const G &g) {
-        f(threadIdx.x, blockDim.x);
-        g(threadIdx.x, blockDim.x);
-        __syncthreads();
-    }
-    template <class F>
-    __device__ __forceinline__ void one(const F &f) {
-        if (threadIdx.x == 0) f();
-        __syncthreads();
-    }
-    template <class T>
-    __device__ __forceinline__ T load(const T *p) {
-        return __ldcg(p);
-    }
+// ---------------------------------------------------------------------------------------------------------
+// k_persistent: the resident CTA. The control block and (for steps with <= PS_HIT occurrences) the step lists
+// live in shared memory, so the per-step bookkeeping costs shared-memory latency; what remains on the critical
+// path are the dependent L2/HBM round trips of the occurrence walk itself.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int PERSISTENT_THREADS = 1024;
+constexpr uint32_t PS_HIT = 2048;        // occurrences per step served from shared-memory lists
+constexpr uint32_t PS_REC = 2 * PS_HIT;  // each occurrence creates at most two new-pair records
+constexpr int PS_SEL = 4;                // candidates per thread held in registers by the fused selection
+
+struct PersistSmem {
+    Ctl ctl;
+    uint32_t hit[PS_HIT];
+    uint32_t rec_slot[PS_REC];
+    uint32_t rec_pos[PS_REC];
+    uint32_t newp[PS_REC];
 };
 
-constexpr int PERSISTENT_THREADS = 1024;
-__global__ void __launch_bounds__(PERSISTENT_THREADS, 1) k_persistent(const Ctx c) {
-    DevExec ex;
-    persistent_program(c, ex);
+__device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
+    for (int d = 16; d > 0; d >>= 1) {
+        uint64_t o = __shfl_xor_sync(0xffffffffu, v, d);
+        v = o < v ? o : v;
+    }
+    return v;
+}
+
+// get_top_pair_count for the resident CTA: same result as sel_max .. sel_commit, but each candidate's slot is
+// fetched once (one 16-byte load: key, cnt, len) and kept in registers across the three reductions.
+__device__ __forceinline__ void fused_select(const Ctx &c) {
+    Ctl *g = c.ctl; // shared memory
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t n = g->n_cand;
+    const int32_t theta = g->theta, mode = g->mode;
+    if (n > PS_SEL * PERSISTENT_THREADS) { // long candidate list (massive ties at low counts): generic phases
+        phase_sel_max<true>(c, tid, PERSISTENT_THREADS);
+        __syncthreads();
+        phase_sel_tie<true>(c, tid, PERSISTENT_THREADS);
+        __syncthreads();
+        if (tid == 0) phase_sel_check<true>(c);
+        __syncthreads();
+        if (g->n_fix) {
+            phase_sel_fix_scan<true>(c, tid, PERSISTENT_THREADS);
+            __syncthreads();
+            phase_sel_fix_tie<true>(c, tid, PERSISTENT_THREADS);
+            __syncthreads();
+        }
+        phase_sel_pick<true>(c, tid, PERSISTENT_THREADS);
+        __syncthreads();
+        if (tid == 0) phase_sel_commit<true>(c, 1);
+        __syncthreads();
+        return;
+    }
+    uint32_t slot_id[PS_SEL];
+    uint4 head[PS_SEL]; // {key.lo, key.hi, cnt, len}
+    int32_t best = CMAX_NONE;
+    uint32_t live = 0;
+#pragma unroll
+    for (int k = 0; k < PS_SEL; k++) {
+        uint32_t i = tid + k * PERSISTENT_THREADS;
+        slot_id[k] = i < n ? __ldcg(&c.cand[i]) : NIL;
+    }
+#pragma unroll
+    for (int k = 0; k < PS_SEL; k++) {
+        if (slot_id[k] != NIL) {
+            head[k] = __ldcg(reinterpret_cast<const uint4 *>(&c.slot[slot_id[k]]));
+            int32_t v = (int32_t)head[k].z;
+            best = v > best ? v : best;
+            live += (v >= theta);
+        }
+    }
+    best = __reduce_max_sync(0xffffffffu, best);
+    live = __reduce_add_sync(0xffffffffu, live);
+    if (lane == 0) {
+        if (best != CMAX_NONE) atomicMax(&g->cmax, best);
+        if (live) atomicAdd(&g->n_live, live);
+    }
+    __syncthreads();
+    const int32_t cmax = g->cmax;
+    if (cmax == CMAX_NONE || cmax < theta) {
+        __syncthreads();
+        if (tid == 0) g->status = ST_NEED_REBUILD;
+        __syncthreads();
+        return;
+    }
+    uint64_t tie[PS_SEL];
+    uint64_t mine = ~0ull;
+#pragma unroll
+    for (int k = 0; k < PS_SEL; k++) {
+        tie[k] = ~0ull;
+        if (slot_id[k] != NIL && (int32_t)head[k].z == cmax) {
+            if (mode == 1) {
+                tie[k] = ((uint64_t)head[k].y << 32) | head[k].x;
+            } else {
+                uint32_t f = __ldcg(&c.slot[slot_id[k]].first);
+                if (f == NO_FIRST)
+                    c.fix[atomicAdd(&g->n_fix, 1u)] = slot_id[k];
+                else
+                    tie[k] = f;
+            }
+            mine = tie[k] < mine ? tie[k] : mine;
+        }
+    }
+    mine = warp_min_u64(mine);
+    if (lane == 0 && mine != ~0ull) atomicMin((unsigned long long *)&g->best_tie, (unsigned long long)mine);
+    __syncthreads();
+    if (g->n_fix) { // FIRST mode, a tied pair lost its first occurrence: recompute from its segment
+        phase_sel_fix_scan<true>(c, tid, PERSISTENT_THREADS);
+        __syncthreads();
+        phase_sel_fix_tie<true>(c, tid, PERSISTENT_THREADS);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < PS_SEL; k++)
+            if (slot_id[k] != NIL && (int32_t)head[k].z == cmax && tie[k] == ~0ull)
+                tie[k] = __ldcg(&c.slot[slot_id[k]].first);
+    }
+    const uint64_t win = g->best_tie;
+#pragma unroll
+    for (int k = 0; k < PS_SEL; k++)
+        if (slot_id[k] != NIL && (int32_t)head[k].z == cmax && tie[k] == win) { // exactly one thread
+            g->best_slot = slot_id[k];
+            phase_sel_commit<true>(c, 1);
+        }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(PERSISTENT_THREADS, 1) k_persistent(const Ctx cg) {
+    extern __shared__ __align__(16) unsigned char ps_raw[];
+    PersistSmem *sm = reinterpret_cast<PersistSmem *>(ps_raw);
+    const uint32_t tid = threadIdx.x;
+    constexpr uint32_t CTL_WORDS = sizeof(Ctl) / 4;
+    if (tid < CTL_WORDS) reinterpret_cast<uint32_t *>(&sm->ctl)[tid] = __ldcg(reinterpret_cast<const uint32_t *>(cg.ctl) + tid);
+    __syncthreads();
+    Ctx c = cg;
+    c.ctl = &sm->ctl;
+    Ctl *g = &sm->ctl;
+    for (;;) {
+        if (g->status != ST_RUN) break;
+        if (g->selected == 0) {
+            fused_select(c);
+            if (g->status != ST_RUN) break;
+        }
+        Ctx w = c; // small steps keep their lists in shared memory
+        if (g->seg_len <= PS_HIT) {
+            w.hit = sm->hit;
+            w.rec_slot = sm->rec_slot;
+            w.rec_pos = sm->rec_pos;
+            w.newp = sm->newp;
+        }
+        phase_hits<true>(w, tid, PERSISTENT_THREADS);
+        __syncthreads();
+        phase_mutate<true>(w, tid, PERSISTENT_THREADS);   // corpus nodes
+        phase_seg_alloc<true>(w, tid, PERSISTENT_THREADS); // new slots: disjoint data, same barrier
+        __syncthreads();
+        phase_seg_fill<true>(w, tid, PERSISTENT_THREADS);
+        __syncthreads();
+        if (tid == 0) phase_fin<true>(w);
+        __syncthreads();
+    }
+    __syncthreads();
+    if (tid < CTL_WORDS) reinterpret_cast<uint32_t *>(cg.ctl)[tid] = reinterpret_cast<const uint32_t *>(&sm->ctl)[tid];
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -218,7 +351,13 @@ struct CudaBE {
     }
     void persistent(const Ctx &c) {
         if (err != cudaSuccess) return;
-        k_persistent<<<1, PERSISTENT_THREADS, 0, stream>>>(c);
+        static bool attr_set = false;
+        if (!attr_set) {
+            note(cudaFuncSetAttribute(k_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PersistSmem)),
+                 "smem attr");
+            attr_set = true;
+        }
+        k_persistent<<<1, PERSISTENT_THREADS, sizeof(PersistSmem), stream>>>(c);
         n_launch++;
         note(cudaGetLastError(), "k_persistent launch");
     }

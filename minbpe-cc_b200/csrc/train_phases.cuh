@@ -211,6 +211,35 @@ MB_HD Node ld_node(const Node *p) {
 #endif
 }
 
+// Control block / step lists: in the resident CTA (S == true) they live in shared memory, or in global memory
+// written only by this CTA with plain stores, so plain loads are coherent; otherwise they are global words
+// updated by atomics from other SMs and must be read at L2.
+template <bool S, class T>
+MB_HD T ctl_ld(const T *p) {
+#if MB_ON_DEVICE
+    if (S) return *reinterpret_cast<const volatile T *>(p);
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+// opportunistic warp aggregation of "claim one slot of a list": one atomic per warp instead of one per lane
+MB_HD uint32_t claim_one(uint32_t *counter) {
+#if MB_ON_DEVICE
+    const unsigned m = __activemask();
+    const unsigned lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    return base + __popc(m & ((1u << lane) - 1));
+#else
+    uint32_t o = *counter;
+    *counter = o + 1;
+    return o;
+#endif
+}
+
 MB_HD uint64_t pair_key(uint32_t a, uint32_t b) { return ((uint64_t)a << 32) | b; }
 MB_HD uint32_t hash_key(uint64_t k) {
     k ^= k >> 33;
@@ -253,7 +282,8 @@ MB_HD uint32_t slot_upsert(const Ctx &c, uint64_t key, bool *created) {
 // ---------------------------------------------------------------------------------------------------------
 // count updates
 // ---------------------------------------------------------------------------------------------------------
-#define MB_G(field) ld_l2(&g->field) /* Ctl words are updated by atomics / other threads: always read at L2 */
+#define MB_G(field) ctl_ld<S>(&g->field)
+#define MB_L(ptr) ctl_ld<S>(ptr) /* step lists: hit, rec_*, newp, cand, fix */
 
 // -(p,q) x w for the occurrence whose first token sits at position pairpos
 MB_HD void pair_dec(const Ctx &c, int32_t mode, uint32_t p, uint32_t q, uint32_t w, uint32_t pairpos) {
@@ -275,7 +305,7 @@ MB_HD void pair_inc(const Ctx &c, int32_t mode, uint32_t p, uint32_t q, uint32_t
     // cnt (low word) += w and len (high word) += 1 in one 64-bit atomic: both only grow during the birth step
     a_add(reinterpret_cast<uint64_t *>(&c.slot[s].cnt), ((uint64_t)1 << 32) | (uint64_t)w);
     if (mode == 0) a_min(&c.slot[s].first, pairpos);
-    uint32_t r = a_add(&c.ctl->n_rec, 1u);
+    uint32_t r = claim_one(&c.ctl->n_rec);
     c.rec_slot[r] = s;
     c.rec_pos[r] = pairpos;
 }
@@ -284,17 +314,19 @@ MB_HD void pair_inc(const Ctx &c, int32_t mode, uint32_t p, uint32_t q, uint32_t
 // selection: get_top_pair_count. Every sel_* phase is a no-op unless status == ST_RUN and nothing is selected
 // yet, so a driver may enqueue them without looking at the status first.
 // ---------------------------------------------------------------------------------------------------------
+template <bool S>
 MB_HD bool selecting(const Ctl *g) { return MB_G(status) == ST_RUN && MB_G(selected) == 0; }
 
 // sel_max: best count among candidates (+ how many are still >= theta)
+template <bool S = false>
 MB_HD void phase_sel_max(const Ctx &c, uint32_t tid, uint32_t nth) {
     Ctl *g = c.ctl;
-    if (!selecting(g)) return;
+    if (!selecting<S>(g)) return;
     uint32_t n = MB_G(n_cand);
     int32_t theta = MB_G(theta), best = CMAX_NONE;
     uint32_t live = 0;
     for (uint32_t i = tid; i < n; i += nth) {
-        int32_t v = ld_l2(&c.slot[ld_l2(&c.cand[i])].cnt);
+        int32_t v = ld_l2(&c.slot[MB_L(&c.cand[i])].cnt);
         if (v > best) best = v;
         live += (v >= theta);
     }
@@ -303,15 +335,16 @@ MB_HD void phase_sel_max(const Ctx &c, uint32_t tid, uint32_t nth) {
 }
 // sel_tie: among candidates holding the best count, the smallest tie-break key. FIRST-mode pairs whose first
 // position is unknown go to the fix list instead.
+template <bool S = false>
 MB_HD void phase_sel_tie(const Ctx &c, uint32_t tid, uint32_t nth) {
     Ctl *g = c.ctl;
-    if (!selecting(g)) return;
+    if (!selecting<S>(g)) return;
     int32_t cmax = MB_G(cmax);
     if (cmax == CMAX_NONE || cmax < MB_G(theta)) return; // sel_check turns this into ST_NEED_REBUILD
     uint32_t n = MB_G(n_cand);
     int32_t mode = MB_G(mode);
     for (uint32_t i = tid; i < n; i += nth) {
-        uint32_t s = ld_l2(&c.cand[i]);
+        uint32_t s = MB_L(&c.cand[i]);
         if (ld_l2(&c.slot[s].cnt) != cmax) continue;
         if (mode == 1) {
             a_min(&g->best_tie, ld_l2(&c.slot[s].key)); // PairCount.h:195-207
@@ -325,9 +358,10 @@ MB_HD void phase_sel_tie(const Ctx &c, uint32_t tid, uint32_t nth) {
     }
 }
 // sel_check (one thread, after sel_tie): candidate list exhausted?
+template <bool S = false>
 MB_HD void phase_sel_check(const Ctx &c) {
     Ctl *g = c.ctl;
-    if (!selecting(g)) return;
+    if (!selecting<S>(g)) return;
     int32_t cmax = MB_G(cmax);
     if (cmax == CMAX_NONE || cmax < MB_G(theta)) g->status = ST_NEED_REBUILD;
 }
@@ -349,34 +383,37 @@ MB_HD void fix_scan_range(const Ctx &c, uint32_t s, uint32_t k0, uint32_t stride
     if (best != NO_FIRST) a_min(&c.slot[s].first, best);
 }
 constexpr uint32_t FIX_SOLO_LEN = 128;
+template <bool S = false>
 MB_HD void phase_sel_fix_scan(const Ctx &c, uint32_t tid, uint32_t nth) {
     Ctl *g = c.ctl;
-    if (!selecting(g)) return;
+    if (!selecting<S>(g)) return;
     uint32_t nf = MB_G(n_fix);
     for (uint32_t f = tid; f < nf; f += nth) {
-        uint32_t s = ld_l2(&c.fix[f]);
+        uint32_t s = MB_L(&c.fix[f]);
         if (ld_l2(&c.slot[s].len) <= FIX_SOLO_LEN) fix_scan_range(c, s, 0, 1);
     }
     for (uint32_t f = 0; f < nf; f++) {
-        uint32_t s = ld_l2(&c.fix[f]);
+        uint32_t s = MB_L(&c.fix[f]);
         if (ld_l2(&c.slot[s].len) > FIX_SOLO_LEN) fix_scan_range(c, s, tid, nth);
     }
 }
+template <bool S = false>
 MB_HD void phase_sel_fix_tie(const Ctx &c, uint32_t tid, uint32_t nth) {
     Ctl *g = c.ctl;
-    if (!selecting(g)) return;
+    if (!selecting<S>(g)) return;
     uint32_t nf = MB_G(n_fix);
-    for (uint32_t f = tid; f < nf; f += nth) a_min(&g->best_tie, (uint64_t)ld_l2(&c.slot[ld_l2(&c.fix[f])].first));
+    for (uint32_t f = tid; f < nf; f += nth) a_min(&g->best_tie, (uint64_t)ld_l2(&c.slot[MB_L(&c.fix[f])].first));
 }
 // sel_pick: the unique candidate matching (cmax, best_tie)
+template <bool S = false>
 MB_HD void phase_sel_pick(const Ctx &c, uint32_t tid, uint32_t nth) {
     Ctl *g = c.ctl;
-    if (!selecting(g)) return;
+    if (!selecting<S>(g)) return;
     uint32_t n = MB_G(n_cand);
     int32_t cmax = MB_G(cmax), mode = MB_G(mode);
     uint64_t tie = MB_G(best_tie);
     for (uint32_t i = tid; i < n; i += nth) {
-        uint32_t s = ld_l2(&c.cand[i]);
+        uint32_t s = MB_L(&c.cand[i]);
         if (ld_l2(&c.slot[s].cnt) != cmax) continue;
         uint64_t t = mode == 1 ? ld_l2(&c.slot[s].key) : (uint64_t)ld_l2(&c.slot[s].first);
         if (t == tie) g->best_slot = s;
@@ -384,9 +421,10 @@ MB_HD void phase_sel_pick(const Ctx &c, uint32_t tid, uint32_t nth) {
 }
 // sel_commit (one thread): record the merge (Tokenizer.h:578) and decide how the step is executed.
 // persistent != 0: called from the resident CTA, which hands segments longer than big_limit to the grid.
+template <bool S = false>
 MB_HD void phase_sel_commit(const Ctx &c, int persistent) {
     Ctl *g = c.ctl;
-    if (!selecting(g)) return;
+    if (!selecting<S>(g)) return;
     uint32_t s = MB_G(best_slot);
     uint64_t key = ld_l2(&c.slot[s].key);
     uint32_t step = MB_G(step), seg_len = ld_l2(&c.slot[s].len);
@@ -414,6 +452,7 @@ MB_HD void phase_sel_commit(const Ctx &c, int persistent) {
 // the corpus), and record what to rewrite. Net effect == merge_incremental's (Tokenizer.h:239-280): exact
 // counts of the rewritten text; -(a,b) itself is folded into "count(a,b) := 0" in phase_fin.
 // ---------------------------------------------------------------------------------------------------------
+template <bool S = false>
 MB_HD void phase_hits(const Ctx &c, uint32_t tid, uint32_t nth) {
     Ctl *g = c.ctl;
     const uint32_t a = MB_G(a), b = MB_G(b), id = MB_G(new_id), seg = MB_G(seg), len = MB_G(seg_len);
@@ -427,7 +466,7 @@ MB_HD void phase_hits(const Ctx &c, uint32_t tid, uint32_t nth) {
         if (q.tok != b) continue;
         const uint32_t w = p.wt;
         if (a != b) {
-            c.hit[a_add(&g->n_hit, 1u)] = pos;
+            c.hit[claim_one(&g->n_hit)] = pos;
             if (p.prv != NIL) {
                 Node x = ld_node(&c.node[p.prv]);
                 // x is the tail of another occurrence ("abab"): that occurrence's right side covers this gap
@@ -454,7 +493,7 @@ MB_HD void phase_hits(const Ctx &c, uint32_t tid, uint32_t nth) {
             }
             uint32_t cur = pos, second = j;
             for (;;) {
-                c.hit[a_add(&g->n_hit, 1u)] = cur;
+                c.hit[claim_one(&g->n_hit)] = cur;
                 uint32_t r = ld_l2(&c.node[second].nxt);
                 if (r == NIL) break;
                 Node nr = ld_node(&c.node[r]);
@@ -475,11 +514,12 @@ MB_HD void phase_hits(const Ctx &c, uint32_t tid, uint32_t nth) {
 
 // mutate: rewrite the corpus (merge, Tokenizer.h:182-183). Field-wise stores only: different threads own
 // different fields of a shared neighbour node.
+template <bool S = false>
 MB_HD void phase_mutate(const Ctx &c, uint32_t tid, uint32_t nth) {
     Ctl *g = c.ctl;
     const uint32_t id = MB_G(new_id), n = MB_G(n_hit);
     for (uint32_t h = tid; h < n; h += nth) {
-        uint32_t pos = ld_l2(&c.hit[h]);
+        uint32_t pos = MB_L(&c.hit[h]);
         uint32_t j = ld_l2(&c.node[pos].nxt);
         uint32_t y = ld_l2(&c.node[j].nxt);
         c.node[pos].tok = id;
@@ -490,12 +530,13 @@ MB_HD void phase_mutate(const Ctx &c, uint32_t tid, uint32_t nth) {
 }
 
 // seg_alloc: give every pair born in this step its arena segment; join the candidate list if it qualifies
+template <bool S = false>
 MB_HD void phase_seg_alloc(const Ctx &c, uint32_t tid, uint32_t nth) {
     Ctl *g = c.ctl;
     uint32_t n = MB_G(n_newp);
     int32_t theta = MB_G(theta);
     for (uint32_t i = tid; i < n; i += nth) {
-        uint32_t s = ld_l2(&c.newp[i]);
+        uint32_t s = MB_L(&c.newp[i]);
         c.slot[s].seg = a_add(&g->arena_cursor, ld_l2(&c.slot[s].len));
         if (ld_l2(&c.slot[s].cnt) >= theta) {
             uint32_t k = a_add(&g->n_cand, 1u);
@@ -504,16 +545,18 @@ MB_HD void phase_seg_alloc(const Ctx &c, uint32_t tid, uint32_t nth) {
     }
 }
 // seg_fill: scatter this step's occurrence records into their pair's segment
+template <bool S = false>
 MB_HD void phase_seg_fill(const Ctx &c, uint32_t tid, uint32_t nth) {
     Ctl *g = c.ctl;
     uint32_t n = MB_G(n_rec);
     for (uint32_t r = tid; r < n; r += nth) {
-        uint32_t s = ld_l2(&c.rec_slot[r]);
+        uint32_t s = MB_L(&c.rec_slot[r]);
         uint32_t k = a_add(&c.slot[s].fill, 1u);
-        c.occ[ld_l2(&c.slot[s].seg) + k] = ld_l2(&c.rec_pos[r]);
+        c.occ[ld_l2(&c.slot[s].seg) + k] = MB_L(&c.rec_pos[r]);
     }
 }
 // fin (one thread): close the step
+template <bool S = false>
 MB_HD void phase_fin(const Ctx &c) {
     Ctl *g = c.ctl;
     uint64_t live = MB_G(live_tokens);
@@ -537,6 +580,7 @@ MB_HD void phase_fin(const Ctx &c) {
     g->status = st;
 }
 // reset of the selection scratch when a step is (re-)selected after a rebuild / grow
+template <bool S = false>
 MB_HD void phase_sel_reset(const Ctx &c) {
     Ctl *g = c.ctl;
     g->cmax = CMAX_NONE;
@@ -547,6 +591,7 @@ MB_HD void phase_sel_reset(const Ctx &c) {
     if (MB_G(status) != ST_EXHAUSTED) g->status = ST_RUN;
 }
 // a big merge taken over by the grid: same step, status back to RUN
+template <bool S = false>
 MB_HD void phase_take_big(const Ctx &c) {
     Ctl *g = c.ctl;
     if (MB_G(status) == ST_BIG_MERGE) g->status = ST_RUN;
@@ -555,12 +600,14 @@ MB_HD void phase_take_big(const Ctx &c) {
 // ---------------------------------------------------------------------------------------------------------
 // candidate rebuild (full scans of the table)
 // ---------------------------------------------------------------------------------------------------------
+template <bool S = false>
 MB_HD void phase_rebuild_reset(const Ctx &c) {
     Ctl *g = c.ctl;
     g->gmax = 0;
     g->n_positive = 0;
     for (int i = 0; i < 32; i++) g->hist[i] = 0;
 }
+template <bool S = false>
 MB_HD void phase_rebuild_hist(const Ctx &c, uint32_t tid, uint32_t nth) {
     Ctl *g = c.ctl;
     uint32_t cap = c.cap_mask + 1;
@@ -576,6 +623,7 @@ MB_HD void phase_rebuild_hist(const Ctx &c, uint32_t tid, uint32_t nth) {
     }
 }
 // one thread: theta = largest power of two with at least `want` pairs at or above it (or 1)
+template <bool S = false>
 MB_HD void phase_rebuild_theta(const Ctx &c, uint32_t want) {
     Ctl *g = c.ctl;
     g->n_cand = 0;
@@ -594,6 +642,7 @@ MB_HD void phase_rebuild_theta(const Ctx &c, uint32_t want) {
     }
     g->theta = theta;
 }
+template <bool S = false>
 MB_HD void phase_rebuild_collect(const Ctx &c, uint32_t tid, uint32_t nth) {
     Ctl *g = c.ctl;
     if (MB_G(status) == ST_EXHAUSTED) return;
@@ -704,44 +753,50 @@ MB_HD void phase_init_fill(const Ctx &c, uint32_t tid, uint32_t nth) {
 // phase functors: what a backend launches (kernel names in ncu read k_par<mbpe::PhHits> etc.)
 // ---------------------------------------------------------------------------------------------------------
 namespace mbpe {
-#define MB_PHASE_PAR(NAME, CALL)                                                \
-    struct NAME {                                                               \
-        Ctx c;                                                                  \
-        MB_HD void operator()(uint32_t tid, uint32_t nth) const { CALL; }       \
-    };
-#define MB_PHASE_ONE(NAME, CALL)                 \
-    struct NAME {                                \
-        Ctx c;                                   \
-        MB_HD void operator()() const { CALL; }  \
-    };
-MB_PHASE_PAR(PhSelMax, phase_sel_max(c, tid, nth))
-MB_PHASE_PAR(PhSelTie, phase_sel_tie(c, tid, nth))
-MB_PHASE_ONE(PhSelCheck, phase_sel_check(c))
-MB_PHASE_PAR(PhSelFixScan, phase_sel_fix_scan(c, tid, nth))
-MB_PHASE_PAR(PhSelFixTie, phase_sel_fix_tie(c, tid, nth))
-MB_PHASE_PAR(PhSelPick, phase_sel_pick(c, tid, nth))
-MB_PHASE_PAR(PhHits, phase_hits(c, tid, nth))
-MB_PHASE_PAR(PhMutate, phase_mutate(c, tid, nth))
-MB_PHASE_PAR(PhSegAlloc, phase_seg_alloc(c, tid, nth))
-MB_PHASE_PAR(PhSegFill, phase_seg_fill(c, tid, nth))
-MB_PHASE_ONE(PhFin, phase_fin(c))
-MB_PHASE_ONE(PhSelReset, phase_sel_reset(c))
-MB_PHASE_ONE(PhTakeBig, phase_take_big(c))
-MB_PHASE_ONE(PhRebuildReset, phase_rebuild_reset(c))
-MB_PHASE_PAR(PhRebuildHist, phase_rebuild_hist(c, tid, nth))
-MB_PHASE_PAR(PhRebuildCollect, phase_rebuild_collect(c, tid, nth))
-MB_PHASE_PAR(PhInitCount, phase_init_count(c, tid, nth))
-MB_PHASE_PAR(PhInitAlloc, phase_init_alloc(c, tid, nth))
-MB_PHASE_PAR(PhInitFill, phase_init_fill(c, tid, nth))
-struct PhSelCommit {
+#define MB_PHASE_PAR(NAME, FN)                                                          \
+    template <bool S = false>                                                           \
+    struct NAME##T {                                                                    \
+        Ctx c;                                                                          \
+        MB_HD void operator()(uint32_t tid, uint32_t nth) const { FN<S>(c, tid, nth); } \
+    };                                                                                  \
+    using NAME = NAME##T<false>;
+#define MB_PHASE_ONE(NAME, FN)                           \
+    template <bool S = false>                            \
+    struct NAME##T {                                     \
+        Ctx c;                                           \
+        MB_HD void operator()() const { FN<S>(c); }      \
+    };                                                   \
+    using NAME = NAME##T<false>;
+MB_PHASE_PAR(PhSelMax, phase_sel_max)
+MB_PHASE_PAR(PhSelTie, phase_sel_tie)
+MB_PHASE_ONE(PhSelCheck, phase_sel_check)
+MB_PHASE_PAR(PhSelFixScan, phase_sel_fix_scan)
+MB_PHASE_PAR(PhSelFixTie, phase_sel_fix_tie)
+MB_PHASE_PAR(PhSelPick, phase_sel_pick)
+MB_PHASE_PAR(PhHits, phase_hits)
+MB_PHASE_PAR(PhMutate, phase_mutate)
+MB_PHASE_PAR(PhSegAlloc, phase_seg_alloc)
+MB_PHASE_PAR(PhSegFill, phase_seg_fill)
+MB_PHASE_ONE(PhFin, phase_fin)
+MB_PHASE_ONE(PhSelReset, phase_sel_reset)
+MB_PHASE_ONE(PhTakeBig, phase_take_big)
+MB_PHASE_ONE(PhRebuildReset, phase_rebuild_reset)
+MB_PHASE_PAR(PhRebuildHist, phase_rebuild_hist)
+MB_PHASE_PAR(PhRebuildCollect, phase_rebuild_collect)
+struct PhInitCount { Ctx c; MB_HD void operator()(uint32_t tid, uint32_t nth) const { phase_init_count(c, tid, nth); } };
+struct PhInitAlloc { Ctx c; MB_HD void operator()(uint32_t tid, uint32_t nth) const { phase_init_alloc(c, tid, nth); } };
+struct PhInitFill { Ctx c; MB_HD void operator()(uint32_t tid, uint32_t nth) const { phase_init_fill(c, tid, nth); } };
+template <bool S = false>
+struct PhSelCommitT {
     Ctx c;
     int persistent;
-    MB_HD void operator()() const { phase_sel_commit(c, persistent); }
+    MB_HD void operator()() const { phase_sel_commit<S>(c, persistent); }
 };
+using PhSelCommit = PhSelCommitT<false>;
 struct PhRebuildTheta {
     Ctx c;
     uint32_t want;
-    MB_HD void operator()() const { phase_rebuild_theta(c, want); }
+    MB_HD void operator()() const { phase_rebuild_theta<false>(c, want); }
 };
 struct PhRehash {
     Ctx c;
@@ -766,26 +821,26 @@ struct PhInitNodes {
 // The resident program: steps back to back until something needs the grid (status != ST_RUN).
 // Exec supplies the barrier: on the device  par(f) = f(threadIdx.x, blockDim.x); __syncthreads();
 // under the host test driver it is a sequential loop over tid.
-template <class Exec>
+template <bool S, class Exec>
 MB_HD void persistent_program(const Ctx &c, Exec &ex) {
     for (;;) {
         if (ex.load(&c.ctl->status) != ST_RUN) return;
         if (ex.load(&c.ctl->selected) == 0) {
-            ex.par(PhSelMax{c});
-            ex.par(PhSelTie{c});
-            ex.one(PhSelCheck{c});
+            ex.par(PhSelMaxT<S>{c});
+            ex.par(PhSelTieT<S>{c});
+            ex.one(PhSelCheckT<S>{c});
             if (ex.load(&c.ctl->n_fix) != 0) {
-                ex.par(PhSelFixScan{c});
-                ex.par(PhSelFixTie{c});
+                ex.par(PhSelFixScanT<S>{c});
+                ex.par(PhSelFixTieT<S>{c});
             }
-            ex.par(PhSelPick{c});
-            ex.one(PhSelCommit{c, 1});
+            ex.par(PhSelPickT<S>{c});
+            ex.one(PhSelCommitT<S>{c, 1});
             if (ex.load(&c.ctl->status) != ST_RUN) return;
         }
-        ex.par(PhHits{c});
-        ex.par2(PhMutate{c}, PhSegAlloc{c}); // disjoint data: corpus nodes vs. new slots
-        ex.par(PhSegFill{c});
-        ex.one(PhFin{c});
+        ex.par(PhHitsT<S>{c});
+        ex.par2(PhMutateT<S>{c}, PhSegAllocT<S>{c}); // disjoint data: corpus nodes vs. new slots
+        ex.par(PhSegFillT<S>{c});
+        ex.one(PhFinT<S>{c});
     }
 }
 } // namespace mbpe

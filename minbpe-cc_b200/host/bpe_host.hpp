@@ -42,7 +42,7 @@ struct Span {
 
 // Tokenizer.h:506-540: the sequential match loop over text[0, len), restricted to matches that start in
 // [begin, stop). The subject is always the whole text, so look-aheads see past `stop`.
-int split_range(const Regex &re, const uint8_t *text, uint64_t len, uint64_t begin, uint64_t stop,
+int split_range(const Regex &re, const uint8_t *text, uint64_t len, uint64_t begin, uint64_t stop, int fast,
                 std::vector<Span> &out, std::string *err);
 // Same chunk list as split_range over the whole text, computed on n_threads threads by cutting the text at
 // regex-safe points: after '\n' and before a printable non-space ASCII byte. Only used for the
@@ -61,6 +61,10 @@ struct Corpus {
 };
 // unique chunk -> count, unique chunks in first-appearance order
 void dedup_chunks(const uint8_t *text, const std::vector<Span> &chunks, int n_threads, Corpus &out);
+
+// split + dedup in one parallel pass (the train path): same Corpus as split_parallel followed by dedup_chunks
+int split_dedup_parallel(const Regex &re, const std::string &pattern, const uint8_t *text, uint64_t len, int n_threads,
+                         Corpus &out, std::string *err);
 
 // deterministic synthetic Zipfian UTF-8 corpus (SURVEY 8(d) input 3)
 void synth_corpus(uint64_t seed, uint8_t *out, uint64_t n, int n_threads);

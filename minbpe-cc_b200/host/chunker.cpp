@@ -45,10 +45,163 @@ int Regex::compile(const std::string &pattern, std::string *err) {
     return MBPE_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// ASCII fast path for the two built-in patterns. The PCRE2 call costs ~1 us per 5-byte chunk; most text is
+// ASCII, where each alternative of Tokenizer.h:59-60 is a few byte-class tests. The scanner below decides a
+// match ONLY from bytes < 0x80 (including the byte it must look at past the end of the match); as soon as a
+// byte >= 0x80 could influence the decision it reports "unknown" and that one match is taken from PCRE2.
+// Equivalence with PCRE2 is tested on every fixture and on random ASCII/Unicode mixes (tests/test_host.py).
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+enum : uint8_t { C_OTHER = 0, C_LETTER = 1, C_DIGIT = 2, C_SPACE = 3, C_NEWLINE = 4, C_HIGH = 5 };
+struct ByteClass {
+    uint8_t c[256];
+    constexpr ByteClass() : c() {
+        for (int i = 0; i < 256; i++) {
+            uint8_t k = C_OTHER;
+            if (i >= 0x80) k = C_HIGH;
+            else if ((i >= 'a' && i <= 'z') || (i >= 'A' && i <= 'Z')) k = C_LETTER;
+            else if (i >= '0' && i <= '9') k = C_DIGIT;
+            else if (i == '\r' || i == '\n') k = C_NEWLINE;
+            else if (i == ' ' || i == '\t' || i == 0x0B || i == 0x0C) k = C_SPACE; // \s with UCP, ASCII part
+            c[i] = k;
+        }
+    }
+};
+constexpr ByteClass kCls{};
+inline bool is_ws(uint8_t k) { return k == C_SPACE || k == C_NEWLINE; }
+
+// whitespace alternatives shared by both patterns. gpt4 adds `\s*[\r\n]` in front of `\s+(?!\S)|\s+`.
+// Returns 1 = matched (end set), 0 = no match, -1 = unknown (needs PCRE2).
+inline int scan_space(const uint8_t *t, uint64_t len, uint64_t pos, bool gpt4, uint64_t *end) {
+    uint64_t r = pos, last_nl = 0;
+    bool has_nl = false;
+    while (r < len && is_ws(kCls.c[t[r]])) {
+        if (kCls.c[t[r]] == C_NEWLINE) {
+            has_nl = true;
+            last_nl = r;
+        }
+        r++;
+    }
+    if (r == pos) return 0;
+    if (r < len && kCls.c[t[r]] == C_HIGH) return -1; // a multi-byte Unicode space may continue the run
+    if (gpt4 && has_nl) {                              // \s*[\r\n]: up to the last CR/LF of the run
+        *end = last_nl + 1;
+        return 1;
+    }
+    if (r == len || r - pos == 1) { // \s+(?!\S) at end of text; or a single space char: \s+(?!\S) fails, \s+ takes it
+        *end = r;
+        return 1;
+    }
+    *end = r - 1; // \s+(?!\S): leave the last space for the next match
+    return 1;
+}
+
+inline int scan_gpt4(const uint8_t *t, uint64_t len, uint64_t pos, uint64_t *end) {
+    const uint8_t c = t[pos], k = kCls.c[c];
+    if (k == C_HIGH) return -1;
+    if (c == '\'' && pos + 1 < len) { // '(?i:[sdmt]|ll|ve|re)
+        const uint8_t d = t[pos + 1];
+        if (d >= 0x80) return -1; // U+017F / U+212A fold to s / k under CASELESS
+        const uint8_t dl = d | 0x20;
+        if (dl == 's' || dl == 'd' || dl == 'm' || dl == 't') {
+            *end = pos + 2;
+            return 1;
+        }
+        if (pos + 2 < len) {
+            const uint8_t e = t[pos + 2];
+            if (e >= 0x80) {
+                if (dl == 'l' || dl == 'v' || dl == 'r') return -1;
+            } else {
+                const uint8_t el = e | 0x20;
+                if ((dl == 'l' && el == 'l') || (dl == 'v' && el == 'e') || (dl == 'r' && el == 'e')) {
+                    *end = pos + 3;
+                    return 1;
+                }
+            }
+        }
+    }
+    // [^\r\n\p{L}\p{N}]?+\p{L}+
+    if (k != C_NEWLINE && k != C_DIGIT) {
+        uint64_t p = (k == C_LETTER) ? pos : pos + 1;
+        if (p < len) {
+            const uint8_t kp = kCls.c[t[p]];
+            if (kp == C_HIGH) return -1;
+            if (kp == C_LETTER) {
+                uint64_t q = p + 1;
+                while (q < len && kCls.c[t[q]] == C_LETTER) q++;
+                if (q < len && kCls.c[t[q]] == C_HIGH) return -1; // a non-ASCII letter may continue the word
+                *end = q;
+                return 1;
+            }
+        }
+    }
+    if (k == C_DIGIT) { // \p{N}{1,3}
+        uint64_t q = pos + 1;
+        while (q < len && q < pos + 3 && kCls.c[t[q]] == C_DIGIT) q++;
+        if (q < pos + 3 && q < len && kCls.c[t[q]] == C_HIGH) return -1; // a non-ASCII digit may continue
+        *end = q;
+        return 1;
+    }
+    { //  ?[^\s\p{L}\p{N}]++[\r\n]*
+        uint64_t p = (c == ' ') ? pos + 1 : pos;
+        if (p < len) {
+            const uint8_t kp = kCls.c[t[p]];
+            if (kp == C_HIGH) return -1;
+            if (kp == C_OTHER) {
+                uint64_t q = p + 1;
+                while (q < len && kCls.c[t[q]] == C_OTHER) q++;
+                if (q < len && kCls.c[t[q]] == C_HIGH) return -1; // a non-ASCII symbol may continue the run
+                while (q < len && kCls.c[t[q]] == C_NEWLINE) q++;
+                *end = q;
+                return 1;
+            }
+        }
+    }
+    return scan_space(t, len, pos, true, end);
+}
+
+inline int scan_gpt2(const uint8_t *t, uint64_t len, uint64_t pos, uint64_t *end) {
+    const uint8_t c = t[pos], k = kCls.c[c];
+    if (k == C_HIGH) return -1;
+    if (c == '\'' && pos + 1 < len) { // '(?:[sdmt]|ll|ve|re), case-sensitive
+        const uint8_t d = t[pos + 1];
+        if (d == 's' || d == 'd' || d == 'm' || d == 't') {
+            *end = pos + 2;
+            return 1;
+        }
+        if (pos + 2 < len) {
+            const uint8_t e = t[pos + 2];
+            if ((d == 'l' && e == 'l') || (d == 'v' && e == 'e') || (d == 'r' && e == 'e')) {
+                *end = pos + 3;
+                return 1;
+            }
+        }
+    }
+    //  ?\p{L}+ |  ?\p{N}+ |  ?[^\s\p{L}\p{N}]+   (same shape: optional space, then a run of one class)
+    {
+        uint64_t p = (c == ' ') ? pos + 1 : pos;
+        if (p < len) {
+            const uint8_t kp = kCls.c[t[p]];
+            if (kp == C_HIGH) return -1;
+            if (kp == C_LETTER || kp == C_DIGIT || kp == C_OTHER) {
+                uint64_t q = p + 1;
+                while (q < len && kCls.c[t[q]] == kp) q++;
+                if (q < len && kCls.c[t[q]] == C_HIGH) return -1;
+                *end = q;
+                return 1;
+            }
+        }
+    }
+    return scan_space(t, len, pos, false, end);
+}
+} // namespace
+
 // Matches over text[0, len) starting at `begin`, stopping at the first match that starts at or after `stop`.
 // The subject is always the WHOLE text so that look-aheads at the end of a segment see the real next byte.
+// fast: 0 = PCRE2 only, 1 = gpt2 scanner, 2 = gpt4 scanner (PCRE2 only for matches the scanner cannot decide).
 template <class Emit>
-static int match_loop(const Regex &re, const uint8_t *text, uint64_t len, uint64_t begin, uint64_t stop,
+static int match_loop(const Regex &re, const uint8_t *text, uint64_t len, uint64_t begin, uint64_t stop, int fast,
                       std::string *err, Emit emit) {
     pcre2_match_data_8 *md = pcre2_match_data_create_from_pattern_8(re.code(), nullptr);
     if (!md) {
@@ -58,6 +211,15 @@ static int match_loop(const Regex &re, const uint8_t *text, uint64_t len, uint64
     size_t offset = begin;
     int rc_out = MBPE_OK;
     while (offset < stop || (begin == stop && offset == begin)) {
+        if (fast && offset < len) {
+            uint64_t e = 0;
+            int r = fast == 2 ? scan_gpt4(text, len, offset, &e) : scan_gpt2(text, len, offset, &e);
+            if (r == 1) {
+                emit((uint64_t)offset, e);
+                offset = e;
+                continue;
+            }
+        }
         int rc = pcre2_match_8(re.code(), text, len, offset, MBPE_PCRE2_NO_UTF_CHECK, md, nullptr);
         if (rc < 0) {
             if (rc != MBPE_PCRE2_ERROR_NOMATCH) {
@@ -83,13 +245,13 @@ static int match_loop(const Regex &re, const uint8_t *text, uint64_t len, uint64
     return rc_out;
 }
 
-int split_range(const Regex &re, const uint8_t *text, uint64_t len, uint64_t begin, uint64_t stop,
+int split_range(const Regex &re, const uint8_t *text, uint64_t len, uint64_t begin, uint64_t stop, int fast,
                 std::vector<Span> &out, std::string *err) {
     if (re.empty()) { // whole text is one chunk (Tokenizer.h:541-544)
         out.push_back(Span{0, len});
         return MBPE_OK;
     }
-    return match_loop(re, text, len, begin, stop, err, [&](uint64_t s, uint64_t e) { out.push_back(Span{s, e}); });
+    return match_loop(re, text, len, begin, stop, fast, err, [&](uint64_t s, uint64_t e) { out.push_back(Span{s, e}); });
 }
 
 // cut points p (0 < p < len) where no match of the GPT-2/GPT-4 patterns can span p: text[p-1] == '\n' and
@@ -107,21 +269,27 @@ static std::vector<uint64_t> safe_cuts(const uint8_t *text, uint64_t len, int pa
 }
 
 static bool builtin_pattern(const std::string &p) { return p == kGpt2Pattern || p == kGpt4Pattern; }
+static int fast_kind(const std::string &p) {
+    const char *off = getenv("MBPE_NO_FAST_SPLIT"); // debugging aid: force every match through PCRE2
+    if (off && *off == '1') return 0;
+    return p == kGpt4Pattern ? 2 : p == kGpt2Pattern ? 1 : 0;
+}
 
 int split_parallel(const Regex &re, const std::string &pattern, const uint8_t *text, uint64_t len, int n_threads,
                    std::vector<Span> &out, std::string *err) {
     if (n_threads <= 0) n_threads = hardware_threads();
     if (re.empty() || !builtin_pattern(pattern) || n_threads == 1 || len < (1u << 16))
-        return split_range(re, text, len, 0, len, out, err);
+        return split_range(re, text, len, 0, len, fast_kind(pattern), out, err);
     std::vector<uint64_t> cuts = safe_cuts(text, len, n_threads * 4);
     const size_t n_seg = cuts.size() - 1;
     std::vector<std::vector<Span>> parts(n_seg);
     std::vector<int> rcs(n_seg, MBPE_OK);
     std::vector<std::string> errs(n_seg);
     std::atomic<size_t> next{0};
+    const int fast = fast_kind(pattern);
     auto work = [&]() {
         for (size_t s; (s = next.fetch_add(1)) < n_seg;)
-            rcs[s] = split_range(re, text, len, cuts[s], cuts[s + 1], parts[s], &errs[s]);
+            rcs[s] = split_range(re, text, len, cuts[s], cuts[s + 1], fast, parts[s], &errs[s]);
     };
     std::vector<std::thread> th;
     for (int t = 1; t < n_threads; t++) th.emplace_back(work);
@@ -213,6 +381,36 @@ struct UniqueSet {
     }
 };
 
+static void corpus_from_set(const uint8_t *text, const UniqueSet &g, uint64_t n_chunks, Corpus &out) {
+    out.n_chunks = n_chunks;
+    out.off.clear();
+    out.weight.clear();
+    out.tokens.clear();
+    uint64_t total = 0;
+    for (const auto &it : g.items) total += it.len;
+    out.tokens.reserve(total);
+    out.off.reserve(g.items.size() + 1);
+    out.weight.reserve(g.items.size());
+    out.off.push_back(0);
+    for (const auto &it : g.items) {
+        Token id;
+        std::string_view sv(reinterpret_cast<const char *>(text + it.start), it.len);
+        if (it.len && text[it.start] == 0 && marker_token(sv, &id))
+            out.tokens.push_back(id);
+        else
+            for (uint32_t i = 0; i < it.len; i++) out.tokens.push_back(text[it.start + i]);
+        out.off.push_back(out.tokens.size());
+        out.weight.push_back(it.count);
+    }
+}
+
+// merge per-thread sets in thread (= text) order: global first-appearance order is preserved
+static void merge_sets(const uint8_t *text, std::vector<UniqueSet> &local) {
+    UniqueSet &g = local[0];
+    for (size_t t = 1; t < local.size(); t++)
+        for (const auto &it : local[t].items) g.add(text, it.hash, it.start, it.len, it.count);
+}
+
 void dedup_chunks(const uint8_t *text, const std::vector<Span> &chunks, int n_threads, Corpus &out) {
     if (n_threads <= 0) n_threads = hardware_threads();
     const uint64_t n = chunks.size();
@@ -230,31 +428,53 @@ void dedup_chunks(const uint8_t *text, const std::vector<Span> &chunks, int n_th
     for (int t = 1; t < n_threads; t++) th.emplace_back(work, t);
     work(0);
     for (auto &t : th) t.join();
-    // merge in thread (= text) order: global first-appearance order is preserved
-    UniqueSet *g = &local[0];
-    for (int t = 1; t < n_threads; t++)
-        for (const auto &it : local[t].items) g->add(text, it.hash, it.start, it.len, it.count);
+    merge_sets(text, local);
+    corpus_from_set(text, local[0], n, out);
+}
 
-    out.n_chunks = n;
-    out.off.clear();
-    out.weight.clear();
-    out.tokens.clear();
-    uint64_t total = 0;
-    for (const auto &it : g->items) total += it.len;
-    out.tokens.reserve(total);
-    out.off.reserve(g->items.size() + 1);
-    out.weight.reserve(g->items.size());
-    out.off.push_back(0);
-    for (const auto &it : g->items) {
-        Token id;
-        std::string_view sv(reinterpret_cast<const char *>(text + it.start), it.len);
-        if (it.len && text[it.start] == 0 && marker_token(sv, &id))
-            out.tokens.push_back(id);
-        else
-            for (uint32_t i = 0; i < it.len; i++) out.tokens.push_back(text[it.start + i]);
-        out.off.push_back(out.tokens.size());
-        out.weight.push_back(it.count);
+// split + dedup fused: the chunk list of a 1 GiB text (2 x 10^8 spans) is never materialised. Each thread scans
+// one contiguous range of the text (between regex-safe cuts) straight into its own set.
+int split_dedup_parallel(const Regex &re, const std::string &pattern, const uint8_t *text, uint64_t len, int n_threads,
+                         Corpus &out, std::string *err) {
+    if (n_threads <= 0) n_threads = hardware_threads();
+    if (re.empty()) { // whole text is one chunk (Tokenizer.h:541-544)
+        std::vector<Span> one{Span{0, len}};
+        dedup_chunks(text, one, 1, out);
+        return MBPE_OK;
     }
+    if (!builtin_pattern(pattern) || len < (1u << 16)) n_threads = 1;
+    std::vector<uint64_t> cuts = n_threads > 1 ? safe_cuts(text, len, n_threads) : std::vector<uint64_t>{0, len};
+    const int n_seg = (int)cuts.size() - 1;
+    std::vector<UniqueSet> local(n_seg);
+    std::vector<int> rcs(n_seg, MBPE_OK);
+    std::vector<std::string> errs(n_seg);
+    std::vector<uint64_t> counts(n_seg, 0);
+    const int fast = fast_kind(pattern);
+    auto work = [&](int s) {
+        UniqueSet &set = local[s];
+        set.init(1 << 16);
+        uint64_t n = 0;
+        rcs[s] = match_loop(re, text, len, cuts[s], cuts[s + 1], fast, &errs[s], [&](uint64_t a, uint64_t b) {
+            set.add(text, hash_bytes(text + a, b - a), a, (uint32_t)(b - a), 1);
+            n++;
+        });
+        counts[s] = n;
+    };
+    std::vector<std::thread> th;
+    for (int s = 1; s < n_seg; s++) th.emplace_back(work, s);
+    work(0);
+    for (auto &t : th) t.join();
+    uint64_t n_chunks = 0;
+    for (int s = 0; s < n_seg; s++) {
+        if (rcs[s] != MBPE_OK) {
+            if (err) *err = errs[s];
+            return rcs[s];
+        }
+        n_chunks += counts[s];
+    }
+    merge_sets(text, local);
+    corpus_from_set(text, local[0], n_chunks, out);
+    return MBPE_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -64,17 +64,13 @@ int Tokenizer::train(std::string_view text, int vocab_size, CONFLICT_RESOLUTION 
     }
     const uint8_t *bytes = reinterpret_cast<const uint8_t *>(text.data());
     double t0 = now_s();
-    std::vector<Span> spans;
-    int rc = split_parallel(regex_, pattern_, bytes, text.size(), n_threads_, spans, &error_);
-    if (rc) return rc;
-    double t1 = now_s();
-    if (verbose) std::cout << "Split input text into " << spans.size() << " chunks\n"; // Tokenizer.h:547
     Corpus corpus;
-    dedup_chunks(bytes, spans, n_threads_, corpus);
-    std::vector<Span>().swap(spans);
+    int rc = split_dedup_parallel(regex_, pattern_, bytes, text.size(), n_threads_, corpus, &error_);
+    if (rc) return rc;
     double t2 = now_s();
-    last_split_s = t1 - t0;
-    last_dedup_s = t2 - t1;
+    if (verbose) std::cout << "Split input text into " << corpus.n_chunks << " chunks\n"; // Tokenizer.h:547
+    last_split_s = t2 - t0; // regex split and dedup are one fused pass
+    last_dedup_s = 0;
     last_n_chunks = corpus.n_chunks;
     last_n_unique = corpus.weight.size();
 
@@ -527,6 +523,39 @@ extern "C" int mbpe_dedup(const uint8_t *text, const uint64_t *starts, const uin
     if (tokens_out) memcpy(tokens_out, c.tokens.data(), c.tokens.size() * 4);
     if (off_out) memcpy(off_out, c.off.data(), c.off.size() * 8);
     if (weight_out) memcpy(weight_out, c.weight.data(), c.weight.size() * 4);
+    return MBPE_OK;
+}
+
+extern "C" int mbpe_split_dedup(const char *pattern, const uint8_t *text, uint64_t len, int n_threads,
+                                uint32_t *tokens_out, uint64_t tokens_cap, uint64_t *n_tokens, uint64_t *off_out,
+                                uint32_t *weight_out, uint64_t unique_cap, uint64_t *n_unique, uint64_t *n_chunks) {
+    if (!pattern || !n_tokens || !n_unique || (!text && len)) return fail(MBPE_E_INVALID, "null argument");
+    static thread_local Corpus cached; // sizing call followed by the copying call: do the work once
+    static thread_local const uint8_t *cached_text = nullptr;
+    static thread_local uint64_t cached_len = 0;
+    static thread_local std::string cached_pattern;
+    if (!(tokens_out && cached_text == text && cached_len == len && cached_pattern == pattern)) {
+        Regex re;
+        std::string err;
+        int rc = re.compile(pattern, &err);
+        if (rc) return fail(rc, err);
+        rc = split_dedup_parallel(re, pattern, text, len, n_threads, cached, &err);
+        if (rc) return fail(rc, err);
+        cached_text = text;
+        cached_len = len;
+        cached_pattern = pattern;
+    }
+    *n_tokens = cached.tokens.size();
+    *n_unique = cached.weight.size();
+    if (n_chunks) *n_chunks = cached.n_chunks;
+    if (!tokens_out) return MBPE_OK;
+    if (cached.tokens.size() > tokens_cap || cached.weight.size() > unique_cap)
+        return fail(MBPE_E_CAPACITY, "output buffers too small");
+    memcpy(tokens_out, cached.tokens.data(), cached.tokens.size() * 4);
+    if (off_out) memcpy(off_out, cached.off.data(), cached.off.size() * 8);
+    if (weight_out) memcpy(weight_out, cached.weight.data(), cached.weight.size() * 4);
+    cached = Corpus();
+    cached_text = nullptr;
     return MBPE_OK;
 }
 

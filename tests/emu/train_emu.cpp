@@ -66,7 +66,7 @@ struct HostBE {
     void persistent(const Ctx &c) {
         n_launch++;
         Exec ex{this};
-        persistent_program(c, ex);
+        persistent_program<false>(c, ex);
     }
 };
 

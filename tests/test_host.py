@@ -112,3 +112,28 @@ def test_synth_corpus_is_deterministic_and_valid_utf8(pkg):
     assert np.array_equal(a, b) and not np.array_equal(a, c)
     a.tobytes().decode("utf-8")
     assert hashlib.sha256(a.tobytes()).hexdigest() == hashlib.sha256(b.tobytes()).hexdigest()
+
+
+def test_fast_scanner_equals_pcre2_on_random_mixes(pkg, oracle):
+    """The ASCII fast path of host/chunker.cpp may only ever return what PCRE2 returns."""
+    rng = np.random.default_rng(23)
+    pieces = [b"'", b"'s", b"'S", b"'ll", b"'LL", b"'Ve", b"'re", b"'r", b"'l", b"'\xc5\xbf", b"'\xe2\x84\xaa", b"a", b"Zz",
+              b"word", b"WORD", b"0", b"12", b"1234567", b" ", b"  ", b"   ", b"\t", b"\n", b"\r", b"\r\n", b"\x0b",
+              b"\x0c", b"\x00", b"\x01", b"\x1c", b"\x1f", b"\x7f", b".", b",", b"!?", b"--", b"_", b"$", b"(", b"\"",
+              b"\xc3\xa9", b"\xc3\x89t\xc3\xa9", b"\xd0\xb6", b"\xe4\xb8\x96", b"\xf0\x9f\x98\x80", b"\xc2\xa0",
+              b"\xe2\x80\xa8", b"\xe3\x80\x80", b"\xe2\x80\x94", b"\xc2\xb2", b"\xd9\xa3", b"\xe2\x80\x99s", b"x\n", b" \n",
+              b"\n ", b" a", b" 1", b" .", b".a", b"\ta", b"\na", b"1a", b"a1"]
+    for trial in range(40):
+        text = b"".join(pieces[i] for i in rng.integers(0, len(pieces), 20000))
+        for enc in ("gpt4", "gpt2"):
+            s0, e0 = oracle.split(text, oracle.PATTERNS[enc])
+            for threads in (1, 8):
+                s1, e1 = pkg.split(pkg.patterns()[enc], text, threads)
+                assert np.array_equal(s0, s1) and np.array_equal(e0, e1), (trial, enc, threads)
+    # pure random ASCII, every byte value < 0x80
+    for trial in range(10):
+        text = bytes(rng.integers(0, 128, 50000).astype(np.uint8))
+        for enc in ("gpt4", "gpt2"):
+            s0, e0 = oracle.split(text, oracle.PATTERNS[enc])
+            s1, e1 = pkg.split(pkg.patterns()[enc], text, 8)
+            assert np.array_equal(s0, s1) and np.array_equal(e0, e1), (trial, enc)
