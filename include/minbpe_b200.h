@@ -90,6 +90,8 @@ typedef struct mbpe_train_stats {
     uint64_t n_rebuilds;     /* candidate-list rebuilds */
     uint64_t n_grows;        /* pair-table rehashes */
     uint64_t rescan_bytes;   /* sum over merges of 12*T_m + 16*P_m: SURVEY 8(d) full-rescan algorithmic volume */
+    uint64_t resident_cycles[8]; /* SM cycles inside the resident CTA: select, hits, mutate+seg_alloc, seg_fill, fin,
+                                    steps done there, total */
 } mbpe_train_stats;
 
 /* uploads the corpus to `device` (H2D) and keeps a pristine copy so run() can be repeated */

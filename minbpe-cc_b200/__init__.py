@@ -43,10 +43,13 @@ class TrainStats(C.Structure):
     _fields_ = [("gpu_ms", C.c_double), ("build_ms", C.c_double), ("n_positions", C.c_uint64),
                 ("n_pairs", C.c_uint64), ("table_slots", C.c_uint64), ("n_launches", C.c_uint64),
                 ("n_big_merges", C.c_uint64), ("n_rebuilds", C.c_uint64), ("n_grows", C.c_uint64),
-                ("rescan_bytes", C.c_uint64)]
+                ("rescan_bytes", C.c_uint64), ("resident_cycles", C.c_uint64 * 8)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "resident_cycles"}
+        d["resident_cycles"] = dict(zip(["select", "hits", "mutate_alloc", "seg_fill", "fin", "steps", "total", "_"],
+                                        list(self.resident_cycles)))
+        return d
 
 
 _lib = None

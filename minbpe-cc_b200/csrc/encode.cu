@@ -77,10 +77,12 @@ __device__ __forceinline__ uint32_t enc_pass(const EncTable &tab, uint32_t *t, u
 // ---------------------------------------------------------------------------------------------------------
 constexpr uint64_t LB_AGG = 1ull << 62, LB_PREFIX = 2ull << 62, LB_VAL = (1ull << 62) - 1;
 
-__device__ __forceinline__ uint64_t lookback_base(unsigned long long *status, uint32_t tile, uint64_t total) {
+__device__ __forceinline__ uint64_t lookback_base(unsigned long long *status, uint32_t tile, uint64_t total,
+                                                  const unsigned long long *first_base = nullptr) {
     if (tile == 0) {
-        atomicExch(&status[0], LB_PREFIX | total);
-        return 0;
+        const uint64_t b = first_base ? *first_base : 0;
+        atomicExch(&status[0], LB_PREFIX | (b + total));
+        return b;
     }
     atomicExch(&status[tile], LB_AGG | total);
     uint64_t acc = 0;
@@ -124,8 +126,21 @@ __global__ void k_encode_long(EncTable tab, const uint8_t *bytes, const uint32_t
 // ---------------------------------------------------------------------------------------------------------
 // k_encode_tiles
 // ---------------------------------------------------------------------------------------------------------
+struct CacheSlot;
+struct ChunkCache {
+    CacheSlot *slots;    // nullptr = cache disabled
+    uint32_t mask;       // slots - 1
+    CacheSlot *log;      // chunks the current sub-batch had to scan
+    uint32_t *log_count;
+    uint32_t log_cap;
+    uint32_t *used;      // occupied slots (learning stops at half full)
+};
+
 struct EncArgs {
     EncTable tab;
+    ChunkCache cache;
+    uint64_t chunk0, chunk1;   // this launch covers chunks [chunk0, chunk1) in tiles of ET_CHUNKS
+    const unsigned long long *stream_base; // ids produced by earlier sub-batches (device word) = base of tile 0
     const uint8_t *bytes;
     uint64_t n_bytes_total; // bytes readable from `bytes` (vector loads never cross it)
     const uint32_t *off;
@@ -142,158 +157,283 @@ struct EncArgs {
     uint32_t *overflow;          // set when out_cap is too small
 };
 
-// A tile = ET_CHUNKS consecutive chunks. Its text is staged into shared memory with coalesced 16-byte loads,
-// one u32 token slot per byte; each thread owns ET_CPT consecutive chunks (a private, contiguous slot range) and
-// runs the passes in place. Per pass the pair lookups of up to 8 positions are issued together (independent
-// read-only loads in flight), then resolved left to right.
-constexpr int ET_CPT = 4;
-constexpr int ET_CHUNKS = ENC_THREADS * ET_CPT;
-constexpr int ET_CAP = 10240; // staged bytes per tile; a tile with more text takes the unstaged path
-constexpr uint32_t ENC_NONE = 0xFFFFFFFFu;
+// ---------------------------------------------------------------------------------------------------------
+// Chunk cache. The multi-pass scan of a chunk is a pure function of its bytes, and text repeats its chunks
+// (Zipf): the encoder keeps an open-addressed table  chunk bytes (<= 15) -> ids (<= 3)  in HBM (32-byte slots, one
+// sector per probe, L2/L1 resident for the hot words). k_encode_tiles only READS it (read-only path); chunks it
+// does not find are encoded by the scan itself and appended to a log, and k_cache_insert adds the log to the table
+// between sub-batches. No kernel both reads and writes the table, so there is no publication protocol to get
+// wrong. Results are bit-identical with or without the cache (MBPE_ENCODE_CACHE=0 disables it; tests run both).
+// ---------------------------------------------------------------------------------------------------------
+struct CacheSlot {
+    uint64_t k0; // bytes 0..7, little endian, zero padded
+    uint64_t k1; // bytes 8..14 | len << 56; 0 = empty slot (len >= 1 always)
+    uint32_t t[3];
+    uint32_t n; // ids stored (1..3)
+};
+static_assert(sizeof(CacheSlot) == 32, "one sector per probe");
+constexpr uint32_t CACHE_MAX_LEN = 15, CACHE_MAX_IDS = 3;
 
-__device__ __forceinline__ uint32_t enc_lookup_id(const EncTable &t, uint32_t a, uint32_t b) {
-    uint32_t id;
-    return enc_lookup(t, a, b, id) ? id : ENC_NONE;
+__device__ __forceinline__ uint32_t cache_hash(uint64_t k0, uint64_t k1) {
+    uint64_t h = (k0 ^ (k1 * 0x9E3779B97F4A7C15ull)) * 0xff51afd7ed558ccdULL;
+    h ^= h >> 32;
+    h *= 0xc4ceb9fe1a85ec53ULL;
+    return (uint32_t)(h >> 32);
 }
 
-// passes over t[0..len) (shared memory, private to the thread), in place. Returns the final length.
-__device__ __forceinline__ uint32_t enc_chunk_smem(const EncTable &tab, uint32_t *t, uint32_t len) {
-    while (len >= 2) {
-        uint32_t w = 0;
-        bool skip = false, merged = false;
-        for (uint32_t base = 0; base < len; base += 8) {
-            uint32_t v[9], id[8];
-#pragma unroll
-            for (int i = 0; i < 9; i++) v[i] = (base + i < len) ? t[base + i] : 0u;
-#pragma unroll
-            for (int i = 0; i < 8; i++) id[i] = (base + i + 1 < len) ? enc_lookup_id(tab, v[i], v[i + 1]) : ENC_NONE;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                if (base + i < len) {
-                    if (skip) {
-                        skip = false;
-                    } else if (id[i] != ENC_NONE) {
-                        t[w++] = id[i];
-                        skip = true;
-                        merged = true;
-                    } else {
-                        t[w++] = v[i];
-                    }
-                }
+__global__ void k_cache_insert(ChunkCache cc) {
+    const uint32_t n = min(*cc.log_count, cc.log_cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const CacheSlot e = cc.log[i];
+        if (*((volatile uint32_t *)cc.used) * 2 > cc.mask) return; // half full: stop learning
+        uint32_t h = cache_hash(e.k0, e.k1) & cc.mask;
+        for (;;) {
+            unsigned long long *pk1 = reinterpret_cast<unsigned long long *>(&cc.slots[h].k1);
+            unsigned long long cur = *((volatile unsigned long long *)pk1);
+            if (cur == 0) cur = atomicCAS(pk1, 0ull, (unsigned long long)e.k1);
+            if (cur == 0) { // claimed: k1 is the claim word, the rest is written by the winner only
+                cc.slots[h].k0 = e.k0;
+                cc.slots[h].t[0] = e.t[0];
+                cc.slots[h].t[1] = e.t[1];
+                cc.slots[h].t[2] = e.t[2];
+                cc.slots[h].n = e.n;
+                atomicAdd(cc.used, 1u);
+                break;
             }
+            // Same k1 and k0: already there (the log holds duplicates of hot chunks). The k0 of a slot claimed in
+            // THIS launch may not be visible yet; then the duplicate takes a second slot -- harmless, both slots
+            // hold the same ids and the first one found is used.
+            if (cur == e.k1 && *((volatile uint64_t *)&cc.slots[h].k0) == e.k0) break;
+            h = (h + 1) & cc.mask;
         }
-        len = w;
-        if (!merged) break;
     }
+}
+__global__ void k_cache_reset_log(ChunkCache cc) { *cc.log_count = 0; }
+
+// ---------------------------------------------------------------------------------------------------------
+// k_encode_tiles. A tile = ET_CHUNKS consecutive chunks; its boundaries and its text are staged into shared
+// memory with coalesced loads. Each thread owns ET_CPT consecutive chunks:
+//   1. chunks <= 15 bytes: assemble the 16-byte key from shared memory, probe the cache (read-only path);
+//   2. misses go to a tile work list and are encoded by the scan, one chunk per thread, all lanes busy;
+//   3. block scan + decoupled look-back give the tile its place in the flat stream; ids are written in order.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int ET_CPT = 4;
+constexpr int ET_CHUNKS = ENC_THREADS * ET_CPT;
+constexpr int ET_CAP = 16384;        // staged text bytes per tile (avg chunk 5 B -> 5 KB); bigger tiles read HBM directly
+constexpr uint32_t ET_MISS_OUT = 4096; // ids of scanned chunks parked in shared memory until the tile offset is known
+constexpr uint32_t META_NONE = 0xFFFFF;
+
+struct EncSmem {
+    uint32_t off[ET_CHUNKS + 1];
+    alignas(16) uint32_t text[ET_CAP / 4 + 8]; // raw bytes, 16-byte aligned window
+    uint16_t miss[ET_CHUNKS];      // work list: chunk index within the tile
+    uint32_t meta[ET_CHUNKS];      // scanned chunks: start in miss_out (20 bits, META_NONE = not parked) | count << 20
+    uint32_t miss_out[ET_MISS_OUT];
+    uint32_t tile, n_miss, miss_used;
+    uint32_t warp_sum[ENC_THREADS / 32];
+    unsigned long long base;
+};
+
+__device__ __forceinline__ uint8_t tile_byte(const EncArgs &a, const EncSmem &sm, bool staged, uint32_t a0, uint32_t g) {
+    return staged ? reinterpret_cast<const uint8_t *>(sm.text)[g - a0] : __ldg(&a.bytes[g]);
+}
+
+// scan one chunk (<= ENC_SHORT_MAX bytes) into t[]; returns the id count
+__device__ __forceinline__ uint32_t scan_chunk(const EncArgs &a, const EncSmem &sm, bool staged, uint32_t a0, uint32_t o,
+                                               uint32_t len, uint32_t *t) {
+    for (uint32_t i = 0; i < len; i++) t[i] = tile_byte(a, sm, staged, a0, o + i);
+    bool merged = true;
+    while (merged && len >= 2) len = enc_pass(a.tab, t, len, merged);
     return len;
 }
 
-__global__ void __launch_bounds__(ENC_THREADS, 4) k_encode_tiles(const EncArgs a) {
-    __shared__ uint32_t s_off[ET_CHUNKS + 1];
-    __shared__ uint32_t s_tok[ET_CAP];
-    __shared__ uint32_t s_tile;
-    __shared__ uint32_t s_warp[ENC_THREADS / 32];
-    __shared__ unsigned long long s_base;
+__global__ void __launch_bounds__(ENC_THREADS, 3) k_encode_tiles(const EncArgs a) {
+    extern __shared__ __align__(16) unsigned char enc_smem_raw[];
+    EncSmem &sm = *reinterpret_cast<EncSmem *>(enc_smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool use_cache = a.cache.slots != nullptr;
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_tile = atomicAdd(a.ticket, 1u); // tiles start in order: look-back cannot deadlock
+        if (tid == 0) {
+            sm.tile = atomicAdd(a.ticket, 1u); // tiles start in order: look-back cannot deadlock
+            sm.n_miss = 0;
+            sm.miss_used = 0;
+        }
         __syncthreads();
-        const uint32_t tile = s_tile;
+        const uint32_t tile = sm.tile;
         if (tile >= a.n_tiles) return;
-        const uint64_t c0 = (uint64_t)tile * ET_CHUNKS;
-        const uint32_t nc = (uint32_t)min((uint64_t)ET_CHUNKS, a.n_chunks - c0);
-        for (uint32_t i = tid; i <= nc; i += ENC_THREADS) s_off[i] = __ldg(&a.off[c0 + i]);
+        const uint64_t c0 = a.chunk0 + (uint64_t)tile * ET_CHUNKS;
+        const uint32_t nc = (uint32_t)min((uint64_t)ET_CHUNKS, a.chunk1 - c0);
+        for (uint32_t i = tid; i <= nc; i += ENC_THREADS) sm.off[i] = __ldg(&a.off[c0 + i]);
         __syncthreads();
-        const uint32_t b0 = s_off[0], b1 = s_off[nc], nb = b1 - b0;
-        const bool staged = nb <= ET_CAP;
+        const uint32_t b0 = sm.off[0], b1 = sm.off[nc];
+        const uint32_t a0 = b0 & ~15u; // 16-byte aligned window start (device buffers are 256-byte aligned)
+        const bool staged = (b1 - a0) <= ET_CAP;
         if (staged) {
-            const uint32_t a0 = b0 & ~15u; // 16-byte aligned window start (cudaMalloc'd buffers are 256-aligned)
+            uint4 *dst = reinterpret_cast<uint4 *>(sm.text);
             for (uint32_t v = tid; a0 + v * 16 < b1; v += ENC_THREADS) {
                 const uint32_t g0 = a0 + v * 16;
+                uint4 q;
                 if (g0 + 16 <= a.n_bytes_total) {
-                    uint4 q = __ldg(reinterpret_cast<const uint4 *>(a.bytes + g0));
-                    uint32_t wds[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        uint32_t g = g0 + j;
-                        if (g >= b0 && g < b1) s_tok[g - b0] = (wds[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
-                    }
-                } else {
-                    for (uint32_t g = max(g0, b0); g < b1 && g < g0 + 16; g++) s_tok[g - b0] = __ldg(&a.bytes[g]);
+                    q = __ldg(reinterpret_cast<const uint4 *>(a.bytes + g0));
+                } else { // last vector of the buffer
+                    uint32_t w[4] = {0, 0, 0, 0};
+                    for (uint32_t g = g0; g < a.n_bytes_total; g++)
+                        w[(g - g0) >> 2] |= (uint32_t)__ldg(&a.bytes[g]) << (((g - g0) & 3) * 8);
+                    q = make_uint4(w[0], w[1], w[2], w[3]);
                 }
+                dst[v] = q;
             }
             __syncthreads();
         }
-        uint32_t cnt[ET_CPT], sum = 0;
+        // ---- 1. cache probes -------------------------------------------------------------------------------
+        uint32_t cnt[ET_CPT], ids[ET_CPT][CACHE_MAX_IDS];
+        uint32_t state[ET_CPT]; // 0 = ids[] valid (cache hit / empty chunk), 1 = scanned, 2 = long chunk
 #pragma unroll
         for (int j = 0; j < ET_CPT; j++) {
             const uint32_t k = tid * ET_CPT + j;
             cnt[j] = 0;
-            if (k < nc) {
-                const uint32_t o = s_off[k], len = s_off[k + 1] - o;
-                if (len > ENC_SHORT_MAX) {
-                    cnt[j] = a.scratch_b[o]; // encoded by k_encode_long
-                } else if (staged) {
-                    cnt[j] = enc_chunk_smem(a.tab, &s_tok[o - b0], len);
-                } else { // unstaged tile: count now, encode again when writing
-                    uint32_t t[ENC_SHORT_MAX];
-                    for (uint32_t i = 0; i < len; i++) t[i] = __ldg(&a.bytes[o + i]);
-                    uint32_t l2 = len;
-                    bool merged = true;
-                    while (merged && l2 >= 2) l2 = enc_pass(a.tab, t, l2, merged);
-                    cnt[j] = l2;
+            state[j] = 0;
+            if (k >= nc) continue;
+            const uint32_t o = sm.off[k], len = sm.off[k + 1] - o;
+            if (len == 0) continue;
+            if (len > ENC_SHORT_MAX) {
+                state[j] = 2;
+                cnt[j] = a.scratch_b[o]; // encoded by k_encode_long
+                continue;
+            }
+            bool hit = false;
+            if (use_cache && staged && len <= CACHE_MAX_LEN) {
+                // 16 bytes starting at the (unaligned) chunk start, bytes past the chunk zeroed
+                const uint32_t r = o - a0, wi = r >> 2, sh = (r & 3) * 8;
+                const uint32_t w0 = sm.text[wi], w1 = sm.text[wi + 1], w2 = sm.text[wi + 2], w3 = sm.text[wi + 3],
+                               w4 = sm.text[wi + 4];
+                const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh);
+                const uint32_t v2 = __funnelshift_r(w2, w3, sh), v3 = __funnelshift_r(w3, w4, sh);
+                uint64_t k0 = ((uint64_t)v1 << 32) | v0, k1 = ((uint64_t)v3 << 32) | v2;
+                if (len < 8) {
+                    k0 &= (1ull << (len * 8)) - 1;
+                    k1 = 0;
+                } else {
+                    k1 &= (1ull << ((len - 8) * 8)) - 1; // len <= 15: at most 7 bytes in k1
                 }
-                sum += cnt[j];
+                k1 |= (uint64_t)len << 56;
+                uint32_t h = cache_hash(k0, k1) & a.cache.mask;
+                for (;;) {
+                    const ulonglong2 kk = __ldg(reinterpret_cast<const ulonglong2 *>(&a.cache.slots[h]));
+                    if (kk.y == 0) break; // empty: not cached
+                    if (kk.y == k1 && kk.x == k0) {
+                        const uint4 tv = __ldg(reinterpret_cast<const uint4 *>(&a.cache.slots[h]) + 1);
+                        ids[j][0] = tv.x;
+                        ids[j][1] = tv.y;
+                        ids[j][2] = tv.z;
+                        cnt[j] = tv.w;
+                        hit = true;
+                        break;
+                    }
+                    h = (h + 1) & a.cache.mask;
+                }
+            }
+            if (!hit) {
+                state[j] = 1;
+                sm.miss[atomicAdd(&sm.n_miss, 1u)] = (uint16_t)k;
             }
         }
-        // block exclusive scan of the per-thread sums
+        __syncthreads();
+        // ---- 2. scan the misses: one chunk per thread per round, ids parked in shared memory ------------------
+        const uint32_t n_miss = sm.n_miss;
+        for (uint32_t q = tid; q < n_miss; q += ENC_THREADS) {
+            uint32_t t[ENC_SHORT_MAX];
+            const uint32_t mk = sm.miss[q], o = sm.off[mk], mlen = sm.off[mk + 1] - o;
+            const uint32_t mn = scan_chunk(a, sm, staged, a0, o, mlen, t);
+            uint32_t start = atomicAdd(&sm.miss_used, mn);
+            if (start + mn <= ET_MISS_OUT) {
+                for (uint32_t i = 0; i < mn; i++) sm.miss_out[start + i] = t[i];
+            } else {
+                start = META_NONE; // no room: the owner scans it again when writing
+            }
+            sm.meta[mk] = start | (mn << 20);
+            if (use_cache && mlen <= CACHE_MAX_LEN && mn <= CACHE_MAX_IDS) { // teach the cache
+                const uint32_t li = atomicAdd(a.cache.log_count, 1u);
+                if (li < a.cache.log_cap) {
+                    uint64_t k0 = 0, k1 = 0;
+                    for (uint32_t i = 0; i < mlen; i++) {
+                        const uint64_t b = tile_byte(a, sm, staged, a0, o + i);
+                        if (i < 8)
+                            k0 |= b << (i * 8);
+                        else
+                            k1 |= b << ((i - 8) * 8);
+                    }
+                    CacheSlot e;
+                    e.k0 = k0;
+                    e.k1 = k1 | ((uint64_t)mlen << 56);
+                    e.t[0] = t[0];
+                    e.t[1] = mn > 1 ? t[1] : 0;
+                    e.t[2] = mn > 2 ? t[2] : 0;
+                    e.n = mn;
+                    a.cache.log[li] = e;
+                }
+            }
+        }
+        __syncthreads();
+        uint32_t sum = 0;
+#pragma unroll
+        for (int j = 0; j < ET_CPT; j++) {
+            if (state[j] == 1) cnt[j] = sm.meta[tid * ET_CPT + j] >> 20;
+            sum += cnt[j];
+        }
+        // ---- 3. place in the stream: block exclusive scan + look-back -----------------------------------------
         uint32_t incl = sum;
         for (int d = 1; d < 32; d <<= 1) {
             uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += v;
         }
-        if (lane == 31) s_warp[warp] = incl;
+        if (lane == 31) sm.warp_sum[warp] = incl;
         __syncthreads();
         uint32_t warp_base = 0, total = 0;
 #pragma unroll
         for (int w = 0; w < ENC_THREADS / 32; w++) {
-            uint32_t v = s_warp[w];
+            uint32_t v = sm.warp_sum[w];
             if (w < (int)warp) warp_base += v;
             total += v;
         }
-        if (tid == 0) s_base = lookback_base(a.status, tile, total);
+        if (tid == 0) sm.base = lookback_base(a.status, tile, total, a.stream_base);
         __syncthreads();
-        const uint64_t base = s_base;
+        const uint64_t base = sm.base;
         uint64_t dst = base + warp_base + (incl - sum);
 #pragma unroll
         for (int j = 0; j < ET_CPT; j++) {
             const uint32_t k = tid * ET_CPT + j;
-            if (k < nc) {
-                const uint32_t o = s_off[k], len = s_off[k + 1] - o, n = cnt[j];
-                if (a.out_off) a.out_off[c0 + k] = dst;
-                if (dst + n <= a.out_cap) {
-                    if (len > ENC_SHORT_MAX) {
-                        for (uint32_t i = 0; i < n; i++) a.out[dst + i] = a.scratch_a[o + i];
-                    } else if (staged) {
-                        for (uint32_t i = 0; i < n; i++) a.out[dst + i] = s_tok[o - b0 + i];
+            if (k >= nc) continue;
+            const uint32_t n = cnt[j];
+            if (a.out_off) a.out_off[c0 + k] = dst;
+            if (dst + n <= a.out_cap) {
+                if (state[j] == 0) {
+                    if (n > 0) a.out[dst] = ids[j][0];
+                    if (n > 1) a.out[dst + 1] = ids[j][1];
+                    if (n > 2) a.out[dst + 2] = ids[j][2];
+                } else if (state[j] == 1) {
+                    const uint32_t start = sm.meta[k] & 0xFFFFF;
+                    if (start != META_NONE) {
+                        for (uint32_t i = 0; i < n; i++) a.out[dst + i] = sm.miss_out[start + i];
                     } else {
                         uint32_t t[ENC_SHORT_MAX];
-                        for (uint32_t i = 0; i < len; i++) t[i] = __ldg(&a.bytes[o + i]);
-                        uint32_t l2 = len;
-                        bool merged = true;
-                        while (merged && l2 >= 2) l2 = enc_pass(a.tab, t, l2, merged);
+                        const uint32_t o = sm.off[k];
+                        scan_chunk(a, sm, staged, a0, o, sm.off[k + 1] - o, t);
                         for (uint32_t i = 0; i < n; i++) a.out[dst + i] = t[i];
                     }
-                } else if (n) {
-                    *a.overflow = 1;
+                } else {
+                    const uint32_t o = sm.off[k];
+                    for (uint32_t i = 0; i < n; i++) a.out[dst + i] = a.scratch_a[o + i];
                 }
-                dst += n;
+            } else if (n) {
+                *a.overflow = 1;
             }
+            dst += n;
         }
         if (tile == a.n_tiles - 1 && tid == 0) {
             *a.d_n_out = base + total;
-            if (a.out_off) a.out_off[a.n_chunks] = base + total;
+            if (a.out_off && a.chunk1 == a.n_chunks) a.out_off[a.n_chunks] = base + total;
         }
     }
 }
@@ -409,6 +549,11 @@ struct mbpe_encoder {
     uint32_t *d_scratch_a = nullptr, *d_scratch_b = nullptr;
     uint64_t scratch_cap = 0;
     uint64_t launches = 0;
+    // chunk cache (learned across calls)
+    CacheSlot *d_cache = nullptr, *d_cache_log = nullptr;
+    uint32_t cache_slots = 0, cache_log_cap = 0;
+    uint32_t *d_cache_ctr = nullptr; // [0] log count, [1] used slots
+    uint64_t sub_batch_chunks = 1u << 22;
 };
 
 extern "C" int mbpe_encoder_create(const uint32_t *merges, uint32_t n_merges, int device, mbpe_encoder **out) {
@@ -464,6 +609,20 @@ extern "C" int mbpe_encoder_create(const uint32_t *merges, uint32_t n_merges, in
     MB_CUDA(cudaMalloc(&e->d_sp_ids, 4));
     MB_CUDA(cudaMalloc(&e->d_sp_off, 8));
     MB_CUDA(cudaMalloc(&e->d_sp_bytes, 1));
+    const char *cache_env = getenv("MBPE_ENCODE_CACHE"); // "0" disables; otherwise log2 of the slot count (default 21)
+    int cache_log2 = cache_env && *cache_env ? atoi(cache_env) : 21;
+    if (cache_log2 >= 10 && cache_log2 <= 26) {
+        e->cache_slots = 1u << cache_log2;
+        e->cache_log_cap = 1u << 20;
+        MB_CUDA(cudaMalloc(&e->d_cache, (uint64_t)e->cache_slots * sizeof(CacheSlot)));
+        MB_CUDA(cudaMemset(e->d_cache, 0, (uint64_t)e->cache_slots * sizeof(CacheSlot)));
+        MB_CUDA(cudaMalloc(&e->d_cache_log, (uint64_t)e->cache_log_cap * sizeof(CacheSlot)));
+        MB_CUDA(cudaMalloc(&e->d_cache_ctr, 8));
+        MB_CUDA(cudaMemset(e->d_cache_ctr, 0, 8));
+    }
+    const char *sb_env = getenv("MBPE_ENCODE_SUBBATCH");
+    if (sb_env && *sb_env) e->sub_batch_chunks = std::max<uint64_t>(ET_CHUNKS, strtoull(sb_env, nullptr, 10));
+    MB_CUDA(cudaFuncSetAttribute(k_encode_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem)));
     *out = e;
     return MBPE_OK;
 }
@@ -472,7 +631,7 @@ extern "C" void mbpe_encoder_destroy(mbpe_encoder *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     void *ps[] = {e->d_slots, e->d_voff, e->d_vbytes, e->d_sp_ids, e->d_sp_off, e->d_sp_bytes, e->d_status, e->d_small,
-                  e->d_n_out, e->d_long_list, e->d_scratch_a, e->d_scratch_b};
+                  e->d_n_out, e->d_long_list, e->d_scratch_a, e->d_scratch_b, e->d_cache, e->d_cache_log, e->d_cache_ctr};
     for (void *p : ps) cudaFree(p);
     delete e;
 }
@@ -522,7 +681,7 @@ extern "C" int mbpe_encode_reserve(mbpe_encoder *e, uint64_t n_bytes, uint64_t n
     (void)n_bytes;
     int rc = use_device(e->device);
     if (rc) return rc;
-    if ((rc = ensure_status(e, (n_chunks + ENC_THREADS - 1) / ENC_THREADS + 1))) return rc;
+    if ((rc = ensure_status(e, (std::min(n_chunks, e->sub_batch_chunks) + ET_CHUNKS - 1) / ET_CHUNKS + 1))) return rc;
     if (e->long_cap == 0) {
         e->long_cap = 1 << 16;
         MB_CUDA(cudaMalloc(&e->d_long_list, e->long_cap * 4));
@@ -537,15 +696,12 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
     if (n_bytes >= (1ull << 32)) return set_error(MBPE_E_INVALID, "a device batch must be < 4 GiB of text");
     int rc = mbpe_encode_reserve(e, n_bytes, n_chunks);
     if (rc) return rc;
-    uint64_t n_tiles = (n_chunks + ET_CHUNKS - 1) / ET_CHUNKS;
-    if (n_tiles >= 0xFFFFFFFFull) return set_error(MBPE_E_INVALID, "too many chunks in one batch");
     MB_CUDA(cudaMemsetAsync(e->d_small, 0, 16, st));
+    MB_CUDA(cudaMemsetAsync(d_n_out, 0, 8, st));
     if (n_chunks == 0) {
-        MB_CUDA(cudaMemsetAsync(d_n_out, 0, 8, st));
         if (d_out_off) MB_CUDA(cudaMemsetAsync(d_out_off, 0, 8, st));
         return MBPE_OK;
     }
-    MB_CUDA(cudaMemsetAsync(e->d_status, 0, n_tiles * 8, st));
     EncTable tab{e->d_slots, e->mask};
     // long chunks (rare: > 64 bytes) are found on the device; the count comes back to size the scratch path
     unsigned grid = (unsigned)std::min<uint64_t>((n_chunks + 255) / 256, (uint64_t)e->sms * 8);
@@ -576,6 +732,8 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
     }
     EncArgs a{};
     a.tab = tab;
+    a.cache = ChunkCache{e->d_cache, e->cache_slots ? e->cache_slots - 1 : 0, e->d_cache_log, e->d_cache_ctr,
+                         e->cache_log_cap, e->d_cache_ctr ? e->d_cache_ctr + 1 : nullptr};
     a.bytes = d_bytes;
     a.n_bytes_total = n_bytes;
     a.off = d_off;
@@ -583,16 +741,34 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
     a.out = d_out;
     a.out_cap = out_cap;
     a.d_n_out = (unsigned long long *)d_n_out;
+    a.stream_base = (const unsigned long long *)d_n_out;
     a.out_off = d_out_off;
     a.status = e->d_status;
     a.ticket = e->d_small;
-    a.n_tiles = (uint32_t)n_tiles;
     a.scratch_a = e->d_scratch_a;
     a.scratch_b = e->d_scratch_b;
     a.overflow = e->d_small + 2;
-    unsigned g2 = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)e->sms * 8);
-    k_encode_tiles<<<g2, ENC_THREADS, 0, st>>>(a);
-    e->launches++;
+    // Sub-batches of whole tiles: the cache learns from one sub-batch before the next one starts, and the ids of
+    // sub-batch i+1 continue the stream where sub-batch i ended (*d_n_out).
+    for (uint64_t cb = 0; cb < n_chunks; cb += e->sub_batch_chunks) {
+        a.chunk0 = cb;
+        a.chunk1 = std::min(n_chunks, cb + e->sub_batch_chunks);
+        const uint64_t n_tiles = (a.chunk1 - a.chunk0 + ET_CHUNKS - 1) / ET_CHUNKS;
+        a.n_tiles = (uint32_t)n_tiles;
+        MB_CUDA(cudaMemsetAsync(e->d_status, 0, n_tiles * 8, st));
+        MB_CUDA(cudaMemsetAsync(e->d_small, 0, 4, st)); // ticket
+        if (a.cache.slots) {
+            k_cache_reset_log<<<1, 1, 0, st>>>(a.cache);
+            e->launches++;
+        }
+        unsigned g2 = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)e->sms * 3);
+        k_encode_tiles<<<g2, ENC_THREADS, sizeof(EncSmem), st>>>(a);
+        e->launches++;
+        if (a.cache.slots) {
+            k_cache_insert<<<e->sms * 2, 256, 0, st>>>(a.cache);
+            e->launches++;
+        }
+    }
     MB_CUDA(cudaGetLastError());
     return MBPE_OK;
 }

@@ -163,10 +163,31 @@ __global__ void __launch_bounds__(PERSISTENT_THREADS, 1) k_persistent(const Ctx 
     Ctx c = cg;
     c.ctl = &sm->ctl;
     Ctl *g = &sm->ctl;
+    long long t0 = clock64();
+    const long long t_enter = t0;
+    auto lap = [&](int i) { // thread 0 only: cycles since the previous lap go to counter i
+        if (tid == 0) {
+            long long t1 = clock64();
+            g->prof[i] += (uint64_t)(t1 - t0);
+            t0 = t1;
+        }
+    };
     for (;;) {
         if (g->status != ST_RUN) break;
         if (g->selected == 0) {
+            if (tid == 0) { // debug counters: candidate-list length seen by the selection
+                g->prof[7] += g->n_cand;
+                if (g->n_cand > PS_SEL * PERSISTENT_THREADS) g->dbg[0] += 1;
+                if (g->n_cand > g->dbg[1]) g->dbg[1] = g->n_cand;
+            }
+            long long ts = clock64();
             fused_select(c);
+            if (tid == 0) {
+                uint64_t d = (uint64_t)(clock64() - ts);
+                if (d > g->dbg[2]) g->dbg[2] = d;
+                if (d > 20000) g->dbg[3] += 1;
+            }
+            lap(0);
             if (g->status != ST_RUN) break;
         }
         Ctx w = c; // small steps keep their lists in shared memory
@@ -178,14 +199,22 @@ __global__ void __launch_bounds__(PERSISTENT_THREADS, 1) k_persistent(const Ctx 
         }
         phase_hits<true>(w, tid, PERSISTENT_THREADS);
         __syncthreads();
+        lap(1);
         phase_mutate<true>(w, tid, PERSISTENT_THREADS);   // corpus nodes
         phase_seg_alloc<true>(w, tid, PERSISTENT_THREADS); // new slots: disjoint data, same barrier
         __syncthreads();
+        lap(2);
         phase_seg_fill<true>(w, tid, PERSISTENT_THREADS);
         __syncthreads();
-        if (tid == 0) phase_fin<true>(w);
+        lap(3);
+        if (tid == 0) {
+            phase_fin<true>(w);
+            g->prof[5] += 1;
+        }
         __syncthreads();
+        lap(4);
     }
+    if (tid == 0) g->prof[6] += (uint64_t)(clock64() - t_enter);
     __syncthreads();
     if (tid < CTL_WORDS) reinterpret_cast<uint32_t *>(cg.ctl)[tid] = reinterpret_cast<const uint32_t *>(&sm->ctl)[tid];
 }
@@ -451,8 +480,8 @@ extern "C" int mbpe_trainer_run(mbpe_trainer *t, uint32_t vocab_size, int mode, 
     be.stream = (cudaStream_t)stream;
     be.sms = sm_count(t->device);
     be.pinned = t->pinned_ctl;
-    TrainConfig cfg{vocab_size, mode, engine, env_u32("MBPE_BIG_LIMIT", 16384), env_u32("MBPE_CAND_WANT", 1024),
-                    env_u32("MBPE_INIT_SLOTS", 0)};
+    TrainConfig cfg{vocab_size, mode, engine, env_u32("MBPE_BIG_LIMIT", 16384), env_u32("MBPE_CAND_WANT", 512),
+                    env_u32("MBPE_CAND_LIMIT", PS_SEL * PERSISTENT_THREADS), env_u32("MBPE_INIT_SLOTS", 0)};
     TrainOutcome o;
     *n_merges_out = 0;
     MB_CUDA(cudaEventRecord(t->ev[0], be.stream));
@@ -479,6 +508,7 @@ extern "C" int mbpe_trainer_run(mbpe_trainer *t, uint32_t vocab_size, int mode, 
         stats->n_rebuilds = o.n_rebuilds;
         stats->n_grows = o.n_grows;
         stats->rescan_bytes = o.rescan_bytes;
+        for (int i = 0; i < 8; i++) stats->resident_cycles[i] = o.prof[i];
     }
     return MBPE_OK;
 }

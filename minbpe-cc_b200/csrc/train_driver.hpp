@@ -13,6 +13,8 @@
 //   uint64_t launches() const;
 #pragma once
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "train_phases.cuh"
@@ -25,6 +27,7 @@ struct TrainConfig {
     int engine;          // 0 stepwise, 1 persistent
     uint32_t big_limit;  // persistent CTA yields merges with longer segments to the grid
     uint32_t cand_want;  // candidate list target size at a rebuild
+    uint32_t cand_limit; // rebuild when the candidate list grows past this (0 = 4096)
     uint32_t init_slots; // initial pair-table capacity (power of two), 0 = sized for 65536 byte pairs
 };
 
@@ -33,6 +36,7 @@ struct TrainOutcome {
     int32_t final_status;
     uint64_t min_key_ever;
     uint64_t n_pairs, table_slots, n_big, n_rebuilds, n_grows, rescan_bytes;
+    uint64_t prof[8];
 };
 
 inline uint32_t next_pow2_u32(uint64_t v) {
@@ -78,6 +82,7 @@ class TrainLoop {
         h.best_tie = ~0ull;
         h.theta = 1;
         h.big_limit = cfg.big_limit;
+        h.cand_limit = cfg.cand_limit ? cfg.cand_limit : 4096;
         h.min_key_ever = ~0ull;
         h.live_tokens = n_tokens;
         be_.upload(c_.ctl, &h, sizeof h);
@@ -126,6 +131,8 @@ class TrainLoop {
         out->n_rebuilds = n_rebuilds_;
         out->n_grows = n_grows_;
         out->rescan_bytes = h.rescan_bytes;
+        for (int i = 0; i < 8; i++) out->prof[i] = h.prof[i];
+        if (getenv("MBPE_DEBUG")) fprintf(stderr, "[mbpe] select dbg: sum_ncand=%llu generic_steps=%llu max_ncand=%llu max_select_cycles=%llu slow_selects=%llu\n", (unsigned long long)h.prof[7], (unsigned long long)h.dbg[0], (unsigned long long)h.dbg[1], (unsigned long long)h.dbg[2], (unsigned long long)h.dbg[3]);
         if (h.step) {
             be_.download(h_merges, c_.merges_out, (uint64_t)h.step * 8);
             if (h_counts) be_.download(h_counts, c_.counts_out, (uint64_t)h.step * 4);
@@ -138,7 +145,7 @@ class TrainLoop {
     void alloc_table(uint32_t cap) {
         c_.slot = (Slot *)be_.alloc((uint64_t)cap * sizeof(Slot));
         c_.cap_mask = cap - 1;
-        c_.cand_cap = cap / 2 + 64;
+        c_.cand_cap = cap; // >= number of pairs at any load factor
         c_.cand = (uint32_t *)be_.alloc((uint64_t)c_.cand_cap * 4);
         c_.fix = (uint32_t *)be_.alloc((uint64_t)c_.cand_cap * 4);
         be_.par(PhClearSlots{c_.slot, cap}, cap);
@@ -172,8 +179,8 @@ class TrainLoop {
         Slot *old = c_.slot;
         uint32_t old_cap = c_.cap_mask + 1;
         uint64_t need = (uint64_t)h.n_pairs + 2ull * h.seg_len + 64; // same bound as phase_sel_commit
-        uint64_t cap = (uint64_t)old_cap * 4;
-        while (need * 2 > cap) cap *= 2;
+        uint64_t cap = (uint64_t)old_cap * 2; // stay as small as the load limit allows: L2 residency matters
+        while (need * 5 > cap * 3) cap *= 2;
         be_.release(c_.cand);
         be_.release(c_.fix);
         alloc_table((uint32_t)cap);

@@ -42,6 +42,19 @@ constexpr uint32_t DEAD = 0xFFFFFFFFu;     // Node.tok of an unlinked position
 constexpr uint64_t EMPTY_KEY = ~0ull;      // free slot
 constexpr uint32_t NO_FIRST = 0xFFFFFFFFu; // Slot.first unknown
 constexpr int32_t CMAX_NONE = INT32_MIN;
+constexpr int HIST_BUCKETS = 256;
+
+// count -> bucket: floor(log2 v) and the next three mantissa bits (monotone in v); bucket -> its smallest count
+MB_HD uint32_t hist_bucket(uint32_t v) {
+    uint32_t e = 0;
+    for (uint32_t t = v; t > 1; t >>= 1) e++;
+    uint32_t m = e >= 3 ? (v >> (e - 3)) & 7u : (v << (3 - e)) & 7u;
+    return e * 8 + m;
+}
+MB_HD uint32_t hist_floor(uint32_t bkt) {
+    uint32_t e = bkt >> 3, m = bkt & 7;
+    return e >= 3 ? ((8u + m) << (e - 3)) : (((8u + m) >> (3 - e)) + ((((8u + m) & ((1u << (3 - e)) - 1)) != 0) ? 1u : 0u));
+}
 
 enum Status : int32_t {
     ST_RUN = 0,          // keep going
@@ -91,16 +104,20 @@ struct Ctl {
     uint32_t n_pairs;
     uint32_t arena_cursor;
     uint32_t big_limit; // segment length above which the persistent CTA yields
-    uint32_t pad0;
+    uint32_t cand_limit; // candidate-list length that triggers a rebuild ...
+    uint32_t cand_base;  // ... unless the list was already that long right after the last rebuild (massive ties)
     uint64_t min_key_ever;
     // rebuild scratch
     int32_t gmax;
     uint32_t n_positive;
-    uint32_t hist[32]; // pairs per floor(log2(count))
+    uint32_t hist[HIST_BUCKETS]; // pairs per count bucket: 8 sub-buckets per power of two
     // accounting (SURVEY 8(d) rescan-volume figure)
     uint64_t live_tokens;
     uint64_t rescan_bytes;
     uint64_t n_small_steps;
+    // resident-CTA cycle counters (thread 0, clock64): select, hits, mutate+seg_alloc, seg_fill, fin, steps, total
+    uint64_t prof[8];
+    uint64_t dbg[4];
 };
 
 struct Ctx {
@@ -188,6 +205,14 @@ MB_HD uint64_t a_cas(uint64_t *p, uint64_t expect, uint64_t v) {
     return o;
 #endif
 }
+template <bool S, class T>
+MB_HD T ld_tok(const T *p) { // a field of a corpus node, same rule as ld_node
+#if MB_ON_DEVICE
+    return S ? *p : __ldcg(p);
+#else
+    return *p;
+#endif
+}
 // loads of words that other threads update with atomics in an earlier phase: go to L2, not a stale L1 line
 template <class T>
 MB_HD T ld_l2(const T *p) {
@@ -197,9 +222,13 @@ MB_HD T ld_l2(const T *p) {
     return *p;
 #endif
 }
+// Corpus nodes: the resident CTA (S == true) is the only writer while it runs (plain stores from the same SM
+// keep its L1 coherent, and L1 is invalidated at every kernel boundary), so it may use L1-cached loads: the
+// neighbours of an occurrence sit in the same 128-byte line as the occurrence itself.
+template <bool S = false>
 MB_HD Node ld_node(const Node *p) {
 #if MB_ON_DEVICE
-    uint4 v = __ldcg(reinterpret_cast<const uint4 *>(p));
+    uint4 v = S ? *reinterpret_cast<const uint4 *>(p) : __ldcg(reinterpret_cast<const uint4 *>(p));
     Node n;
     n.tok = v.x;
     n.nxt = v.y;
@@ -279,6 +308,33 @@ MB_HD uint32_t slot_upsert(const Ctx &c, uint64_t key, bool *created) {
     }
 }
 
+// probe continuation: `s` = home slot of `key`, `k0` = the key word already loaded from it. Lets a thread start
+// several probes (independent loads in flight) before resolving any of them.
+MB_HD uint32_t slot_find_from(const Ctx &c, uint64_t key, uint32_t s, uint64_t k0) {
+    for (;;) {
+        if (k0 == key) return s;
+        if (k0 == EMPTY_KEY) return NIL;
+        s = (s + 1) & c.cap_mask;
+        k0 = ld_l2(&c.slot[s].key);
+    }
+}
+MB_HD uint32_t slot_upsert_from(const Ctx &c, uint64_t key, uint32_t s, uint64_t k0, bool *created) {
+    *created = false;
+    for (;;) {
+        if (k0 == key) return s;
+        if (k0 == EMPTY_KEY) {
+            uint64_t old = a_cas(&c.slot[s].key, EMPTY_KEY, key);
+            if (old == EMPTY_KEY) {
+                *created = true;
+                return s;
+            }
+            if (old == key) return s;
+        }
+        s = (s + 1) & c.cap_mask;
+        k0 = ld_l2(&c.slot[s].key);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // count updates
 // ---------------------------------------------------------------------------------------------------------
@@ -292,11 +348,20 @@ MB_HD void pair_dec(const Ctx &c, int32_t mode, uint32_t p, uint32_t q, uint32_t
     a_add(&c.slot[s].cnt, -(int32_t)w);
     if (mode == 0 && ld_l2(&c.slot[s].first) == pairpos) c.slot[s].first = NO_FIRST;
 }
+MB_HD void pair_dec_at(const Ctx &c, int32_t mode, uint32_t s, uint32_t w, uint32_t pairpos) {
+    if (s == NIL) return;
+    a_add(&c.slot[s].cnt, -(int32_t)w);
+    if (mode == 0 && ld_l2(&c.slot[s].first) == pairpos) c.slot[s].first = NO_FIRST;
+}
+MB_HD void pair_inc_at(const Ctx &c, int32_t mode, uint32_t s, bool created, uint64_t key, uint32_t w, uint32_t pairpos);
 // +(p,q) x w for a new occurrence at pairpos; q or p is this step's new id, so the pair is born in this step
 MB_HD void pair_inc(const Ctx &c, int32_t mode, uint32_t p, uint32_t q, uint32_t w, uint32_t pairpos) {
     bool created;
     uint64_t key = pair_key(p, q);
     uint32_t s = slot_upsert(c, key, &created);
+    pair_inc_at(c, mode, s, created, key, w, pairpos);
+}
+MB_HD void pair_inc_at(const Ctx &c, int32_t mode, uint32_t s, bool created, uint64_t key, uint32_t w, uint32_t pairpos) {
     if (created) {
         c.newp[a_add(&c.ctl->n_newp, 1u)] = s;
         a_add(&c.ctl->n_pairs, 1u);
@@ -429,9 +494,9 @@ MB_HD void phase_sel_commit(const Ctx &c, int persistent) {
     uint64_t key = ld_l2(&c.slot[s].key);
     uint32_t step = MB_G(step), seg_len = ld_l2(&c.slot[s].len);
     g->seg_len = seg_len;
-    // every occurrence can create two pairs; keep the load factor under 1/2 after the step
+    // every occurrence can create two pairs; keep the load factor under 0.6 after the step
     uint64_t need = (uint64_t)MB_G(n_pairs) + 2ull * seg_len + 64;
-    if (need * 2 > (uint64_t)c.cap_mask + 1) {
+    if (need * 5 > ((uint64_t)c.cap_mask + 1) * 3) {
         g->status = ST_NEED_GROW; // slots move: the step is re-selected after the rehash
         return;
     }
@@ -459,34 +524,58 @@ MB_HD void phase_hits(const Ctx &c, uint32_t tid, uint32_t nth) {
     const int32_t mode = MB_G(mode);
     for (uint32_t k = tid; k < len; k += nth) {
         uint32_t pos = ld_l2(&c.occ[seg + k]);
-        Node p = ld_node(&c.node[pos]);
+        Node p = ld_node<S>(&c.node[pos]);
         if (p.tok != a || p.nxt == NIL) continue; // stale record
         uint32_t j = p.nxt;
-        Node q = ld_node(&c.node[j]);
+        Node q = ld_node<S>(&c.node[j]);
         if (q.tok != b) continue;
         const uint32_t w = p.wt;
         if (a != b) {
             c.hit[claim_one(&g->n_hit)] = pos;
-            if (p.prv != NIL) {
-                Node x = ld_node(&c.node[p.prv]);
-                // x is the tail of another occurrence ("abab"): that occurrence's right side covers this gap
-                bool tail = (x.tok == b && x.prv != NIL && ld_l2(&c.node[x.prv].tok) == a);
-                if (!tail) {
-                    pair_dec(c, mode, x.tok, a, w, p.prv);
-                    pair_inc(c, mode, x.tok, id, w, p.prv);
-                }
+            // Gather the whole neighbourhood first, then start all four table probes, then resolve them: the
+            // loads of each stage are independent, so the dependent chain is ~7 round trips instead of ~15.
+            const bool has_l = p.prv != NIL, has_r = q.nxt != NIL;
+            Node x = p, y = q;
+            if (has_l) x = ld_node<S>(&c.node[p.prv]);
+            if (has_r) y = ld_node<S>(&c.node[q.nxt]);
+            const bool need_xx = has_l && x.tok == b && x.prv != NIL;
+            const bool need_yy = has_r && y.tok == a && y.nxt != NIL;
+            uint32_t xx = DEAD, yy = DEAD;
+            if (need_xx) xx = ld_tok<S>(&c.node[x.prv].tok);
+            if (need_yy) yy = ld_tok<S>(&c.node[y.nxt].tok);
+            // x is the tail of another occurrence ("abab"): that occurrence's right side covers this gap
+            const bool do_l = has_l && !(need_xx && xx == a);
+            const bool head = need_yy && yy == b; // y starts another occurrence: the new right pair is (id, id)
+            const uint64_t kd1 = pair_key(x.tok, a), ki1 = pair_key(x.tok, id);
+            const uint64_t kd2 = pair_key(b, y.tok), ki2 = pair_key(id, head ? id : y.tok);
+            const uint32_t hd1 = hash_key(kd1) & c.cap_mask, hi1 = hash_key(ki1) & c.cap_mask;
+            const uint32_t hd2 = hash_key(kd2) & c.cap_mask, hi2 = hash_key(ki2) & c.cap_mask;
+            uint64_t fd1 = 0, fi1 = 0, fd2 = 0, fi2 = 0;
+            if (do_l) {
+                fd1 = ld_l2(&c.slot[hd1].key);
+                fi1 = ld_l2(&c.slot[hi1].key);
             }
-            if (q.nxt != NIL) {
-                Node y = ld_node(&c.node[q.nxt]);
-                bool head = (y.tok == a && y.nxt != NIL && ld_l2(&c.node[y.nxt].tok) == b);
-                pair_dec(c, mode, b, y.tok, w, j);
-                pair_inc(c, mode, id, head ? id : y.tok, w, pos);
+            if (has_r) {
+                fd2 = ld_l2(&c.slot[hd2].key);
+                fi2 = ld_l2(&c.slot[hi2].key);
+            }
+            if (do_l) {
+                bool created;
+                pair_dec_at(c, mode, slot_find_from(c, kd1, hd1, fd1), w, p.prv);
+                uint32_t s1 = slot_upsert_from(c, ki1, hi1, fi1, &created);
+                pair_inc_at(c, mode, s1, created, ki1, w, p.prv);
+            }
+            if (has_r) {
+                bool created;
+                pair_dec_at(c, mode, slot_find_from(c, kd2, hd2, fd2), w, j);
+                uint32_t s2 = slot_upsert_from(c, ki2, hi2, fi2, &created);
+                pair_inc_at(c, mode, s2, created, ki2, w, pos);
             }
         } else {
             // a == b: left-to-right non-overlapping rule (Tokenizer.h:176-191). Only the start of a run of a's
             // acts; it walks its run and merges the 1st, 3rd, 5th... pair.
             if (p.prv != NIL) {
-                uint32_t xt = ld_l2(&c.node[p.prv].tok);
+                uint32_t xt = ld_tok<S>(&c.node[p.prv].tok);
                 if (xt == a) continue;
                 pair_dec(c, mode, xt, a, w, p.prv);
                 pair_inc(c, mode, xt, id, w, p.prv);
@@ -494,15 +583,15 @@ MB_HD void phase_hits(const Ctx &c, uint32_t tid, uint32_t nth) {
             uint32_t cur = pos, second = j;
             for (;;) {
                 c.hit[claim_one(&g->n_hit)] = cur;
-                uint32_t r = ld_l2(&c.node[second].nxt);
+                uint32_t r = ld_tok<S>(&c.node[second].nxt);
                 if (r == NIL) break;
-                Node nr = ld_node(&c.node[r]);
+                Node nr = ld_node<S>(&c.node[r]);
                 if (nr.tok != a) { // run ended right after this pair
                     pair_dec(c, mode, a, nr.tok, w, second);
                     pair_inc(c, mode, id, nr.tok, w, cur);
                     break;
                 }
-                bool head = (nr.nxt != NIL && ld_l2(&c.node[nr.nxt].tok) == a);
+                bool head = (nr.nxt != NIL && ld_tok<S>(&c.node[nr.nxt].tok) == a);
                 pair_inc(c, mode, id, head ? id : a, w, cur);
                 if (!head) break; // one trailing a stays; its right-hand pair is untouched
                 cur = r;
@@ -520,8 +609,8 @@ MB_HD void phase_mutate(const Ctx &c, uint32_t tid, uint32_t nth) {
     const uint32_t id = MB_G(new_id), n = MB_G(n_hit);
     for (uint32_t h = tid; h < n; h += nth) {
         uint32_t pos = MB_L(&c.hit[h]);
-        uint32_t j = ld_l2(&c.node[pos].nxt);
-        uint32_t y = ld_l2(&c.node[j].nxt);
+        uint32_t j = ld_tok<S>(&c.node[pos].nxt);
+        uint32_t y = ld_tok<S>(&c.node[j].nxt);
         c.node[pos].tok = id;
         c.node[pos].nxt = y;
         c.node[j].tok = DEAD;
@@ -574,8 +663,10 @@ MB_HD void phase_fin(const Ctx &c) {
     g->best_tie = ~0ull;
     g->n_fix = 0;
     int32_t st = (step >= MB_G(n_target)) ? ST_DONE : ST_RUN;
-    // list is mostly dead weight: rebuild (full-grid scan) before the next selection
-    if (st == ST_RUN && n_cand > 2 * MB_G(n_live) + 4096) st = ST_NEED_REBUILD;
+    // list is mostly dead weight, or longer than the resident CTA keeps in registers: rebuild (full-grid scan,
+    // fresh theta) before the next selection
+    if (st == ST_RUN && (n_cand > 2 * MB_G(n_live) + 1024 || (n_cand > MB_G(cand_limit) && n_cand > 2 * MB_G(cand_base))))
+        st = ST_NEED_REBUILD;
     g->n_live = 0;
     g->status = st;
 }
@@ -588,6 +679,7 @@ MB_HD void phase_sel_reset(const Ctx &c) {
     g->n_fix = 0;
     g->n_live = 0;
     g->selected = 0;
+    g->cand_base = MB_G(n_cand);
     if (MB_G(status) != ST_EXHAUSTED) g->status = ST_RUN;
 }
 // a big merge taken over by the grid: same step, status back to RUN
@@ -605,7 +697,7 @@ MB_HD void phase_rebuild_reset(const Ctx &c) {
     Ctl *g = c.ctl;
     g->gmax = 0;
     g->n_positive = 0;
-    for (int i = 0; i < 32; i++) g->hist[i] = 0;
+    for (int i = 0; i < HIST_BUCKETS; i++) g->hist[i] = 0;
 }
 template <bool S = false>
 MB_HD void phase_rebuild_hist(const Ctx &c, uint32_t tid, uint32_t nth) {
@@ -617,12 +709,10 @@ MB_HD void phase_rebuild_hist(const Ctx &c, uint32_t tid, uint32_t nth) {
         if (v <= 0) continue;
         a_max(&g->gmax, v);
         a_add(&g->n_positive, 1u);
-        uint32_t bkt = 0;
-        for (uint32_t t = (uint32_t)v; t > 1; t >>= 1) bkt++;
-        a_add(&g->hist[bkt], 1u);
+        a_add(&g->hist[hist_bucket((uint32_t)v)], 1u);
     }
 }
-// one thread: theta = largest power of two with at least `want` pairs at or above it (or 1)
+// one thread: theta = the largest bucket floor with at least `want` pairs at or above it (or 1)
 template <bool S = false>
 MB_HD void phase_rebuild_theta(const Ctx &c, uint32_t want) {
     Ctl *g = c.ctl;
@@ -633,14 +723,14 @@ MB_HD void phase_rebuild_theta(const Ctx &c, uint32_t want) {
     }
     uint32_t acc = 0;
     int32_t theta = 1;
-    for (int bkt = 31; bkt >= 0; bkt--) {
+    for (int bkt = HIST_BUCKETS - 1; bkt >= 0; bkt--) {
         acc += MB_G(hist[bkt]);
         if (acc >= want) {
-            theta = (int32_t)(1u << bkt);
+            theta = (int32_t)hist_floor((uint32_t)bkt);
             break;
         }
     }
-    g->theta = theta;
+    g->theta = theta < 1 ? 1 : theta;
 }
 template <bool S = false>
 MB_HD void phase_rebuild_collect(const Ctx &c, uint32_t tid, uint32_t nth) {

@@ -76,7 +76,7 @@ extern "C" int emu_train(const uint32_t *tokens, uint64_t n_tokens, const uint64
                          uint32_t *n_merges_out, uint64_t *stats /* 8 */) {
     HostBE be{nth, order};
     TrainLoop<HostBE> loop(be);
-    TrainConfig cfg{vocab_size, mode, engine, big_limit, cand_want, init_slots};
+    TrainConfig cfg{vocab_size, mode, engine, big_limit, cand_want, /*cand_limit*/ cand_want * 4 + 64, init_slots};
     TrainOutcome o;
     int rc = loop.run(tokens, off, weight, n_tokens, n_chunks, cfg, merges_out, counts_out, &o);
     if (rc) return rc;
