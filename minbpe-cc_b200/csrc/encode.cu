@@ -55,6 +55,12 @@ __device__ __forceinline__ bool enc_lookup(const EncTable &t, uint32_t a, uint32
     }
 }
 
+constexpr uint32_t ENC_NONE = 0xFFFFFFFFu;
+__device__ __forceinline__ uint32_t enc_lookup_id(const EncTable &t, uint32_t a, uint32_t b) {
+    uint32_t id;
+    return enc_lookup(t, a, b, id) ? id : ENC_NONE;
+}
+
 // one pass of Tokenizer.h:336-359 over t[0..len): returns new length, sets merged
 __device__ __forceinline__ uint32_t enc_pass(const EncTable &tab, uint32_t *t, uint32_t len, bool &merged) {
     uint32_t w = 0, i = 0;
@@ -77,24 +83,41 @@ __device__ __forceinline__ uint32_t enc_pass(const EncTable &tab, uint32_t *t, u
 // ---------------------------------------------------------------------------------------------------------
 constexpr uint64_t LB_AGG = 1ull << 62, LB_PREFIX = 2ull << 62, LB_VAL = (1ull << 62) - 1;
 
+// Called by all 32 lanes of one warp. Each round inspects 32 predecessors at once (one L2 round trip), so a tile
+// that starts while hundreds of older tiles are still in flight resolves its base in ~14 rounds, not ~440 serial loads.
 __device__ __forceinline__ uint64_t lookback_base(unsigned long long *status, uint32_t tile, uint64_t total,
                                                   const unsigned long long *first_base = nullptr) {
+    const uint32_t lane = threadIdx.x & 31;
     if (tile == 0) {
         const uint64_t b = first_base ? *first_base : 0;
-        atomicExch(&status[0], LB_PREFIX | (b + total));
+        if (lane == 0) atomicExch(&status[0], LB_PREFIX | (b + total));
         return b;
     }
-    atomicExch(&status[tile], LB_AGG | total);
+    if (lane == 0) atomicExch(&status[tile], LB_AGG | total);
     uint64_t acc = 0;
-    for (int64_t j = (int64_t)tile - 1;; j--) {
-        unsigned long long v;
-        do {
-            v = *((volatile unsigned long long *)&status[j]);
-        } while ((v >> 62) == 0);
-        acc += v & LB_VAL;
-        if (v & LB_PREFIX) break;
+    int64_t j = (int64_t)tile - 1; // lane l looks at tile j - l
+    for (;;) {
+        const int64_t idx = j - lane;
+        unsigned long long v = LB_PREFIX; // tiles before 0 do not exist: tile 0 always ends the walk itself
+        if (idx >= 0) {
+            do {
+                v = *((volatile unsigned long long *)&status[idx]);
+            } while ((v >> 62) == 0);
+        }
+        const unsigned pm = __ballot_sync(0xffffffffu, (v & LB_PREFIX) != 0);
+        uint64_t val = v & LB_VAL;
+        if (pm) {
+            const int first = __ffs(pm) - 1; // nearest predecessor that already knows its inclusive prefix
+            if ((int)lane > first || idx < 0) val = 0;
+            for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+            acc += val;
+            break;
+        }
+        for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+        acc += val;
+        j -= 32;
     }
-    atomicExch(&status[tile], LB_PREFIX | (acc + total));
+    if (lane == 0) atomicExch(&status[tile], LB_PREFIX | (acc + total));
     return acc;
 }
 
@@ -127,13 +150,17 @@ __global__ void k_encode_long(EncTable tab, const uint8_t *bytes, const uint32_t
 // k_encode_tiles
 // ---------------------------------------------------------------------------------------------------------
 struct CacheSlot;
+struct CacheLogEntry;
 struct ChunkCache {
     CacheSlot *slots;    // nullptr = cache disabled
     uint32_t mask;       // slots - 1
-    CacheSlot *log;      // chunks the current sub-batch had to scan
+    CacheLogEntry *log;  // chunks the current sub-batch had to scan
     uint32_t *log_count;
     uint32_t log_cap;
     uint32_t *used;      // occupied slots (learning stops at half full)
+    uint32_t *arena;     // ids of entries with more than CACHE_INLINE_IDS ids
+    uint32_t *arena_used;
+    uint32_t arena_cap;
 };
 
 struct EncArgs {
@@ -155,6 +182,7 @@ struct EncArgs {
     const uint32_t *scratch_a;   // long-chunk tokens / counts (may be null)
     const uint32_t *scratch_b;
     uint32_t *overflow;          // set when out_cap is too small
+    uint32_t *miss_count;        // chunks that went through the scan (statistics)
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -165,17 +193,22 @@ struct EncArgs {
 // between sub-batches. No kernel both reads and writes the table, so there is no publication protocol to get
 // wrong. Results are bit-identical with or without the cache (MBPE_ENCODE_CACHE=0 disables it; tests run both).
 // ---------------------------------------------------------------------------------------------------------
-struct CacheSlot {
-    uint64_t k0; // bytes 0..7, little endian, zero padded
-    uint64_t k1; // bytes 8..14 | len << 56; 0 = empty slot (len >= 1 always)
-    uint32_t t[3];
-    uint32_t n; // ids stored (1..3)
+struct CacheSlot { // 64 bytes = two sectors: key, value
+    uint64_t k[4]; // chunk bytes, little endian, zero padded; top byte of k[3] = length (1..31); k[3] == 0: empty
+    uint32_t n;    // number of ids (1..31)
+    uint32_t v[7]; // n <= 7: the ids; otherwise v[0] = offset of the ids in the arena
 };
-static_assert(sizeof(CacheSlot) == 32, "one sector per probe");
-constexpr uint32_t CACHE_MAX_LEN = 15, CACHE_MAX_IDS = 3;
+static_assert(sizeof(CacheSlot) == 64, "two sectors per entry");
+struct CacheLogEntry {
+    uint64_t k[4];
+    uint32_t n;
+    uint32_t ids[31];
+};
+constexpr uint32_t CACHE_MAX_LEN = 31, CACHE_INLINE_IDS = 7;
 
-__device__ __forceinline__ uint32_t cache_hash(uint64_t k0, uint64_t k1) {
+__device__ __forceinline__ uint32_t cache_hash(uint64_t k0, uint64_t k1, uint64_t k2, uint64_t k3) {
     uint64_t h = (k0 ^ (k1 * 0x9E3779B97F4A7C15ull)) * 0xff51afd7ed558ccdULL;
+    h ^= (k2 * 0xc2b2ae3d27d4eb4fULL) ^ (k3 * 0x165667b19e3779f9ULL);
     h ^= h >> 32;
     h *= 0xc4ceb9fe1a85ec53ULL;
     return (uint32_t)(h >> 32);
@@ -184,26 +217,42 @@ __device__ __forceinline__ uint32_t cache_hash(uint64_t k0, uint64_t k1) {
 __global__ void k_cache_insert(ChunkCache cc) {
     const uint32_t n = min(*cc.log_count, cc.log_cap);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const CacheSlot e = cc.log[i];
+        const CacheLogEntry &e = cc.log[i];
         if (*((volatile uint32_t *)cc.used) * 2 > cc.mask) return; // half full: stop learning
-        uint32_t h = cache_hash(e.k0, e.k1) & cc.mask;
+        const uint64_t k0 = e.k[0], k1 = e.k[1], k2 = e.k[2], k3 = e.k[3];
+        const uint32_t en = e.n;
+        uint32_t h = cache_hash(k0, k1, k2, k3) & cc.mask;
         for (;;) {
-            unsigned long long *pk1 = reinterpret_cast<unsigned long long *>(&cc.slots[h].k1);
-            unsigned long long cur = *((volatile unsigned long long *)pk1);
-            if (cur == 0) cur = atomicCAS(pk1, 0ull, (unsigned long long)e.k1);
-            if (cur == 0) { // claimed: k1 is the claim word, the rest is written by the winner only
-                cc.slots[h].k0 = e.k0;
-                cc.slots[h].t[0] = e.t[0];
-                cc.slots[h].t[1] = e.t[1];
-                cc.slots[h].t[2] = e.t[2];
-                cc.slots[h].n = e.n;
-                atomicAdd(cc.used, 1u);
-                break;
+            unsigned long long *claim = reinterpret_cast<unsigned long long *>(&cc.slots[h].k[3]);
+            unsigned long long cur = *((volatile unsigned long long *)claim);
+            if (cur == 0) {
+                uint32_t aoff = 0;
+                if (en > CACHE_INLINE_IDS) { // reserve arena room BEFORE claiming, so a claimed slot is always completed
+                    aoff = atomicAdd(cc.arena_used, en);
+                    if (aoff + en > cc.arena_cap) break;
+                }
+                cur = atomicCAS(claim, 0ull, (unsigned long long)k3);
+                if (cur == 0) { // claimed: k[3] is the claim word, the rest is written by the winner only
+                    cc.slots[h].k[0] = k0;
+                    cc.slots[h].k[1] = k1;
+                    cc.slots[h].k[2] = k2;
+                    cc.slots[h].n = en;
+                    if (en <= CACHE_INLINE_IDS) {
+                        for (uint32_t q = 0; q < en; q++) cc.slots[h].v[q] = e.ids[q];
+                    } else {
+                        cc.slots[h].v[0] = aoff;
+                        for (uint32_t q = 0; q < en; q++) cc.arena[aoff + q] = e.ids[q];
+                    }
+                    atomicAdd(cc.used, 1u);
+                    break;
+                }
             }
-            // Same k1 and k0: already there (the log holds duplicates of hot chunks). The k0 of a slot claimed in
-            // THIS launch may not be visible yet; then the duplicate takes a second slot -- harmless, both slots
-            // hold the same ids and the first one found is used.
-            if (cur == e.k1 && *((volatile uint64_t *)&cc.slots[h].k0) == e.k0) break;
+            // Same key: already there (the log holds duplicates of hot chunks). Words of a slot claimed in THIS launch
+            // may not be visible yet; then the duplicate takes a second slot -- harmless, both slots hold the same ids
+            // and a reader uses the first one it finds.
+            if (cur == k3 && *((volatile uint64_t *)&cc.slots[h].k[0]) == k0 &&
+                *((volatile uint64_t *)&cc.slots[h].k[1]) == k1 && *((volatile uint64_t *)&cc.slots[h].k[2]) == k2)
+                break;
             h = (h + 1) & cc.mask;
         }
     }
@@ -219,9 +268,10 @@ __global__ void k_cache_reset_log(ChunkCache cc) { *cc.log_count = 0; }
 // ---------------------------------------------------------------------------------------------------------
 constexpr int ET_CPT = 4;
 constexpr int ET_CHUNKS = ENC_THREADS * ET_CPT;
-constexpr int ET_CAP = 16384;        // staged text bytes per tile (avg chunk 5 B -> 5 KB); bigger tiles read HBM directly
-constexpr uint32_t ET_MISS_OUT = 4096; // ids of scanned chunks parked in shared memory until the tile offset is known
+constexpr int ET_CAP = 8192;         // staged text bytes per tile (avg chunk 5 B -> 5 KB); bigger tiles read HBM directly
+constexpr uint32_t ET_MISS_OUT = 2048; // ids of scanned chunks parked in shared memory until the tile offset is known
 constexpr uint32_t META_NONE = 0xFFFFF;
+constexpr uint32_t ET_WARP_SCAN_MAX = 48; // up to this many misses per tile are scanned one warp per chunk
 
 struct EncSmem {
     uint32_t off[ET_CHUNKS + 1];
@@ -229,6 +279,7 @@ struct EncSmem {
     uint16_t miss[ET_CHUNKS];      // work list: chunk index within the tile
     uint32_t meta[ET_CHUNKS];      // scanned chunks: start in miss_out (20 bits, META_NONE = not parked) | count << 20
     uint32_t miss_out[ET_MISS_OUT];
+    uint32_t warp_scratch[ENC_THREADS / 32][32];
     uint32_t tile, n_miss, miss_used;
     uint32_t warp_sum[ENC_THREADS / 32];
     unsigned long long base;
@@ -247,7 +298,38 @@ __device__ __forceinline__ uint32_t scan_chunk(const EncArgs &a, const EncSmem &
     return len;
 }
 
-__global__ void __launch_bounds__(ENC_THREADS, 3) k_encode_tiles(const EncArgs a) {
+// One warp scans one chunk of <= 32 bytes: lane i holds token i. Per pass every lane looks its pair up at once (one
+// lookup latency per pass instead of one per position); the left-to-right non-overlapping rule of
+// Tokenizer.h:336-359 is applied to the ballot mask: inside each maximal run of mergeable positions the 1st, 3rd,
+// 5th... merge. Runs are separated by parity of their start bit with the carry trick
+//   runs_even = F & ~(F + even_starts),   runs_odd = F & ~(F + odd_starts)
+// (bit 31 of F is always clear: lane 31 has no right neighbour, so the additions cannot overflow).
+// Returns the final length; on return lane i < length holds id i in `tok`. `scratch` = 32 words of shared memory
+// owned by the warp.
+__device__ __forceinline__ uint32_t scan_chunk_warp(const EncTable &tab, uint32_t &tok, uint32_t len, uint32_t *scratch) {
+    const uint32_t lane = threadIdx.x & 31;
+    while (len >= 2) {
+        const uint32_t nxt = __shfl_down_sync(0xffffffffu, tok, 1);
+        uint32_t id = ENC_NONE;
+        if (lane + 1 < len) id = enc_lookup_id(tab, tok, nxt);
+        const uint32_t F = __ballot_sync(0xffffffffu, id != ENC_NONE);
+        if (F == 0) break;
+        const uint32_t starts = F & ~(F << 1);
+        const uint32_t runs_even = F & ~(F + (starts & 0x55555555u));
+        const uint32_t runs_odd = F & ~(F + (starts & 0xAAAAAAAAu));
+        const uint32_t M = (runs_even & 0x55555555u) | (runs_odd & 0xAAAAAAAAu); // heads of merged pairs
+        const uint32_t valid = len >= 32 ? 0xffffffffu : ((1u << len) - 1);
+        const uint32_t keep = valid & ~(M << 1);                                   // tails disappear
+        if ((keep >> lane) & 1u) scratch[__popc(keep & ((1u << lane) - 1))] = ((M >> lane) & 1u) ? id : tok;
+        __syncwarp();
+        len = __popc(keep);
+        tok = lane < len ? scratch[lane] : 0u;
+        __syncwarp();
+    }
+    return len;
+}
+
+__global__ void __launch_bounds__(ENC_THREADS, 4) k_encode_tiles(const EncArgs a) {
     extern __shared__ __align__(16) unsigned char enc_smem_raw[];
     EncSmem &sm = *reinterpret_cast<EncSmem *>(enc_smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -287,8 +369,9 @@ __global__ void __launch_bounds__(ENC_THREADS, 3) k_encode_tiles(const EncArgs a
             __syncthreads();
         }
         // ---- 1. cache probes -------------------------------------------------------------------------------
-        uint32_t cnt[ET_CPT], ids[ET_CPT][CACHE_MAX_IDS];
-        uint32_t state[ET_CPT]; // 0 = ids[] valid (cache hit / empty chunk), 1 = scanned, 2 = long chunk
+        uint32_t cnt[ET_CPT], ids[ET_CPT][3];
+        uint32_t state[ET_CPT]; // 0 = ids[] valid (hit with <= 3 ids / empty chunk), 1 = scanned, 2 = long chunk,
+                                // 3 = hit with more ids: ids[j][0] = cache slot, ids are fetched again when writing
 #pragma unroll
         for (int j = 0; j < ET_CPT; j++) {
             const uint32_t k = tid * ET_CPT + j;
@@ -304,30 +387,50 @@ __global__ void __launch_bounds__(ENC_THREADS, 3) k_encode_tiles(const EncArgs a
             }
             bool hit = false;
             if (use_cache && staged && len <= CACHE_MAX_LEN) {
-                // 16 bytes starting at the (unaligned) chunk start, bytes past the chunk zeroed
+                // up to 32 bytes starting at the (unaligned) chunk start, bytes past the chunk zeroed
                 const uint32_t r = o - a0, wi = r >> 2, sh = (r & 3) * 8;
-                const uint32_t w0 = sm.text[wi], w1 = sm.text[wi + 1], w2 = sm.text[wi + 2], w3 = sm.text[wi + 3],
-                               w4 = sm.text[wi + 4];
-                const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh);
-                const uint32_t v2 = __funnelshift_r(w2, w3, sh), v3 = __funnelshift_r(w3, w4, sh);
-                uint64_t k0 = ((uint64_t)v1 << 32) | v0, k1 = ((uint64_t)v3 << 32) | v2;
-                if (len < 8) {
-                    k0 &= (1ull << (len * 8)) - 1;
-                    k1 = 0;
-                } else {
-                    k1 &= (1ull << ((len - 8) * 8)) - 1; // len <= 15: at most 7 bytes in k1
+                uint32_t w[9];
+#pragma unroll
+                for (int q = 0; q < 5; q++) w[q] = sm.text[wi + q];
+                uint32_t v[8];
+#pragma unroll
+                for (int q = 0; q < 4; q++) v[q] = __funnelshift_r(w[q], w[q + 1], sh);
+#pragma unroll
+                for (int q = 4; q < 8; q++) v[q] = 0;
+                if (len > 16) {
+#pragma unroll
+                    for (int q = 5; q < 9; q++) w[q] = sm.text[wi + q];
+#pragma unroll
+                    for (int q = 4; q < 8; q++) v[q] = __funnelshift_r(w[q], w[q + 1], sh);
                 }
-                k1 |= (uint64_t)len << 56;
-                uint32_t h = cache_hash(k0, k1) & a.cache.mask;
+                uint64_t key[4] = {((uint64_t)v[1] << 32) | v[0], ((uint64_t)v[3] << 32) | v[2],
+                                   ((uint64_t)v[5] << 32) | v[4], ((uint64_t)v[7] << 32) | v[6]};
+#pragma unroll
+                for (int q = 0; q < 4; q++) { // zero everything at and after byte `len`
+                    const int lo = q * 8;
+                    if ((int)len <= lo)
+                        key[q] = 0;
+                    else if ((int)len < lo + 8)
+                        key[q] &= (1ull << ((len - lo) * 8)) - 1;
+                }
+                key[3] |= (uint64_t)len << 56;
+                uint32_t h = cache_hash(key[0], key[1], key[2], key[3]) & a.cache.mask;
                 for (;;) {
-                    const ulonglong2 kk = __ldg(reinterpret_cast<const ulonglong2 *>(&a.cache.slots[h]));
-                    if (kk.y == 0) break; // empty: not cached
-                    if (kk.y == k1 && kk.x == k0) {
-                        const uint4 tv = __ldg(reinterpret_cast<const uint4 *>(&a.cache.slots[h]) + 1);
-                        ids[j][0] = tv.x;
-                        ids[j][1] = tv.y;
-                        ids[j][2] = tv.z;
-                        cnt[j] = tv.w;
+                    // the whole 64-byte entry at once: four independent 16-byte loads, one round trip
+                    const ulonglong2 *sp = reinterpret_cast<const ulonglong2 *>(&a.cache.slots[h]);
+                    const ulonglong2 lo = __ldg(sp);
+                    const ulonglong2 hi = __ldg(sp + 1);
+                    const uint4 tv = __ldg(reinterpret_cast<const uint4 *>(sp + 2)); // n, v[0..2]
+                    if (hi.y == 0) break; // empty: not cached
+                    if (hi.y == key[3] && hi.x == key[2] && lo.x == key[0] && lo.y == key[1]) {
+                        cnt[j] = tv.x;
+                        ids[j][0] = tv.y;
+                        ids[j][1] = tv.z;
+                        ids[j][2] = tv.w;
+                        if (tv.x > 3) {
+                            state[j] = 3;
+                            ids[j][0] = h;
+                        }
                         hit = true;
                         break;
                     }
@@ -340,11 +443,53 @@ __global__ void __launch_bounds__(ENC_THREADS, 3) k_encode_tiles(const EncArgs a
             }
         }
         __syncthreads();
-        // ---- 2. scan the misses: one chunk per thread per round, ids parked in shared memory ------------------
+        // ---- 2. scan the misses, ids parked in shared memory until the tile knows its place ------------------
         const uint32_t n_miss = sm.n_miss;
+        if (tid == 0 && n_miss) atomicAdd(a.miss_count, n_miss);
+        if (n_miss <= ET_WARP_SCAN_MAX) {
+            // few misses (warm cache): latency matters -- one WARP per chunk, lanes = positions
+            for (uint32_t q = warp; q < n_miss; q += ENC_THREADS / 32) {
+                const uint32_t mk = sm.miss[q], o = sm.off[mk], mlen = sm.off[mk + 1] - o;
+                if (mlen > 32) continue; // 33..64 bytes: serial scan below
+                uint32_t tok = lane < mlen ? tile_byte(a, sm, staged, a0, o + lane) : 0u;
+                const uint32_t mn = scan_chunk_warp(a.tab, tok, mlen, sm.warp_scratch[warp]); // lane i < mn: id i in tok
+                uint32_t start = 0;
+                if (lane == 0) start = atomicAdd(&sm.miss_used, mn);
+                start = __shfl_sync(0xffffffffu, start, 0);
+                if (start + mn <= ET_MISS_OUT) {
+                    if (lane < mn) sm.miss_out[start + lane] = tok;
+                } else {
+                    start = META_NONE;
+                }
+                if (lane == 0) sm.meta[mk] = start | (mn << 20);
+                if (use_cache && mlen <= CACHE_MAX_LEN) { // teach the cache
+                    uint32_t li = 0;
+                    if (lane == 0) li = atomicAdd(a.cache.log_count, 1u);
+                    li = __shfl_sync(0xffffffffu, li, 0);
+                    if (li < a.cache.log_cap) {
+                        CacheLogEntry &e = a.cache.log[li];
+                        if (lane < mn) e.ids[lane] = tok;
+                        if (lane == 0) {
+                            uint64_t key[4] = {0, 0, 0, 0};
+                            for (uint32_t i = 0; i < mlen; i++)
+                                key[i >> 3] |= (uint64_t)tile_byte(a, sm, staged, a0, o + i) << ((i & 7) * 8);
+                            key[3] |= (uint64_t)mlen << 56;
+                            e.k[0] = key[0];
+                            e.k[1] = key[1];
+                            e.k[2] = key[2];
+                            e.k[3] = key[3];
+                            e.n = mn;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
         for (uint32_t q = tid; q < n_miss; q += ENC_THREADS) {
-            uint32_t t[ENC_SHORT_MAX];
+            // many misses (cold cache): throughput matters -- one THREAD per chunk; also chunks of 33..64 bytes
             const uint32_t mk = sm.miss[q], o = sm.off[mk], mlen = sm.off[mk + 1] - o;
+            if (n_miss <= ET_WARP_SCAN_MAX && mlen <= 32) continue;
+            uint32_t t[ENC_SHORT_MAX];
             const uint32_t mn = scan_chunk(a, sm, staged, a0, o, mlen, t);
             uint32_t start = atomicAdd(&sm.miss_used, mn);
             if (start + mn <= ET_MISS_OUT) {
@@ -353,25 +498,20 @@ __global__ void __launch_bounds__(ENC_THREADS, 3) k_encode_tiles(const EncArgs a
                 start = META_NONE; // no room: the owner scans it again when writing
             }
             sm.meta[mk] = start | (mn << 20);
-            if (use_cache && mlen <= CACHE_MAX_LEN && mn <= CACHE_MAX_IDS) { // teach the cache
+            if (use_cache && mlen <= CACHE_MAX_LEN) { // teach the cache
                 const uint32_t li = atomicAdd(a.cache.log_count, 1u);
                 if (li < a.cache.log_cap) {
-                    uint64_t k0 = 0, k1 = 0;
-                    for (uint32_t i = 0; i < mlen; i++) {
-                        const uint64_t b = tile_byte(a, sm, staged, a0, o + i);
-                        if (i < 8)
-                            k0 |= b << (i * 8);
-                        else
-                            k1 |= b << ((i - 8) * 8);
-                    }
-                    CacheSlot e;
-                    e.k0 = k0;
-                    e.k1 = k1 | ((uint64_t)mlen << 56);
-                    e.t[0] = t[0];
-                    e.t[1] = mn > 1 ? t[1] : 0;
-                    e.t[2] = mn > 2 ? t[2] : 0;
+                    uint64_t key[4] = {0, 0, 0, 0};
+                    for (uint32_t i = 0; i < mlen; i++)
+                        key[i >> 3] |= (uint64_t)tile_byte(a, sm, staged, a0, o + i) << ((i & 7) * 8);
+                    key[3] |= (uint64_t)mlen << 56;
+                    CacheLogEntry &e = a.cache.log[li];
+                    e.k[0] = key[0];
+                    e.k[1] = key[1];
+                    e.k[2] = key[2];
+                    e.k[3] = key[3];
                     e.n = mn;
-                    a.cache.log[li] = e;
+                    for (uint32_t i = 0; i < mn; i++) e.ids[i] = t[i];
                 }
             }
         }
@@ -397,7 +537,10 @@ __global__ void __launch_bounds__(ENC_THREADS, 3) k_encode_tiles(const EncArgs a
             if (w < (int)warp) warp_base += v;
             total += v;
         }
-        if (tid == 0) sm.base = lookback_base(a.status, tile, total, a.stream_base);
+        if (warp == 0) {
+            const uint64_t b = lookback_base(a.status, tile, total, a.stream_base);
+            if (lane == 0) sm.base = b;
+        }
         __syncthreads();
         const uint64_t base = sm.base;
         uint64_t dst = base + warp_base + (incl - sum);
@@ -412,6 +555,10 @@ __global__ void __launch_bounds__(ENC_THREADS, 3) k_encode_tiles(const EncArgs a
                     if (n > 0) a.out[dst] = ids[j][0];
                     if (n > 1) a.out[dst + 1] = ids[j][1];
                     if (n > 2) a.out[dst + 2] = ids[j][2];
+                } else if (state[j] == 3) {
+                    const CacheSlot &cs = a.cache.slots[ids[j][0]];
+                    const uint32_t *src = n <= CACHE_INLINE_IDS ? cs.v : a.cache.arena + __ldg(&cs.v[0]);
+                    for (uint32_t i = 0; i < n; i++) a.out[dst + i] = __ldg(&src[i]);
                 } else if (state[j] == 1) {
                     const uint32_t start = sm.meta[k] & 0xFFFFF;
                     if (start != META_NONE) {
@@ -512,7 +659,10 @@ __global__ void __launch_bounds__(ENC_THREADS) k_decode_tiles(const DecArgs a) {
             if (w < (int)warp) warp_base += v;
             total += v;
         }
-        if (threadIdx.x == 0) s_base = lookback_base(a.status, tile, total);
+        if (warp == 0) {
+            const uint64_t b = lookback_base(a.status, tile, total);
+            if (lane == 0) s_base = b;
+        }
         __syncthreads();
         const uint64_t dst = s_base + warp_base + (incl - len);
         if (a.out && dst + len <= a.out_cap)
@@ -550,9 +700,11 @@ struct mbpe_encoder {
     uint64_t scratch_cap = 0;
     uint64_t launches = 0;
     // chunk cache (learned across calls)
-    CacheSlot *d_cache = nullptr, *d_cache_log = nullptr;
-    uint32_t cache_slots = 0, cache_log_cap = 0;
-    uint32_t *d_cache_ctr = nullptr; // [0] log count, [1] used slots
+    CacheSlot *d_cache = nullptr;
+    CacheLogEntry *d_cache_log = nullptr;
+    uint32_t *d_cache_arena = nullptr;
+    uint32_t cache_slots = 0, cache_log_cap = 0, cache_arena_cap = 0;
+    uint32_t *d_cache_ctr = nullptr; // [0] log count, [1] used slots, [2] arena cursor
     uint64_t sub_batch_chunks = 1u << 22;
 };
 
@@ -613,12 +765,14 @@ extern "C" int mbpe_encoder_create(const uint32_t *merges, uint32_t n_merges, in
     int cache_log2 = cache_env && *cache_env ? atoi(cache_env) : 21;
     if (cache_log2 >= 10 && cache_log2 <= 26) {
         e->cache_slots = 1u << cache_log2;
-        e->cache_log_cap = 1u << 20;
+        e->cache_log_cap = 1u << 19;
+        e->cache_arena_cap = 1u << 22;
         MB_CUDA(cudaMalloc(&e->d_cache, (uint64_t)e->cache_slots * sizeof(CacheSlot)));
         MB_CUDA(cudaMemset(e->d_cache, 0, (uint64_t)e->cache_slots * sizeof(CacheSlot)));
-        MB_CUDA(cudaMalloc(&e->d_cache_log, (uint64_t)e->cache_log_cap * sizeof(CacheSlot)));
-        MB_CUDA(cudaMalloc(&e->d_cache_ctr, 8));
-        MB_CUDA(cudaMemset(e->d_cache_ctr, 0, 8));
+        MB_CUDA(cudaMalloc(&e->d_cache_log, (uint64_t)e->cache_log_cap * sizeof(CacheLogEntry)));
+        MB_CUDA(cudaMalloc(&e->d_cache_arena, (uint64_t)e->cache_arena_cap * 4));
+        MB_CUDA(cudaMalloc(&e->d_cache_ctr, 16));
+        MB_CUDA(cudaMemset(e->d_cache_ctr, 0, 16));
     }
     const char *sb_env = getenv("MBPE_ENCODE_SUBBATCH");
     if (sb_env && *sb_env) e->sub_batch_chunks = std::max<uint64_t>(ET_CHUNKS, strtoull(sb_env, nullptr, 10));
@@ -631,7 +785,7 @@ extern "C" void mbpe_encoder_destroy(mbpe_encoder *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     void *ps[] = {e->d_slots, e->d_voff, e->d_vbytes, e->d_sp_ids, e->d_sp_off, e->d_sp_bytes, e->d_status, e->d_small,
-                  e->d_n_out, e->d_long_list, e->d_scratch_a, e->d_scratch_b, e->d_cache, e->d_cache_log, e->d_cache_ctr};
+                  e->d_n_out, e->d_long_list, e->d_scratch_a, e->d_scratch_b, e->d_cache, e->d_cache_log, e->d_cache_ctr, e->d_cache_arena};
     for (void *p : ps) cudaFree(p);
     delete e;
 }
@@ -733,7 +887,8 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
     EncArgs a{};
     a.tab = tab;
     a.cache = ChunkCache{e->d_cache, e->cache_slots ? e->cache_slots - 1 : 0, e->d_cache_log, e->d_cache_ctr,
-                         e->cache_log_cap, e->d_cache_ctr ? e->d_cache_ctr + 1 : nullptr};
+                         e->cache_log_cap, e->d_cache_ctr ? e->d_cache_ctr + 1 : nullptr, e->d_cache_arena,
+                         e->d_cache_ctr ? e->d_cache_ctr + 2 : nullptr, e->cache_arena_cap};
     a.bytes = d_bytes;
     a.n_bytes_total = n_bytes;
     a.off = d_off;
@@ -748,6 +903,7 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
     a.scratch_a = e->d_scratch_a;
     a.scratch_b = e->d_scratch_b;
     a.overflow = e->d_small + 2;
+    a.miss_count = e->d_small + 3;
     // Sub-batches of whole tiles: the cache learns from one sub-batch before the next one starts, and the ids of
     // sub-batch i+1 continue the stream where sub-batch i ended (*d_n_out).
     for (uint64_t cb = 0; cb < n_chunks; cb += e->sub_batch_chunks) {
@@ -761,7 +917,7 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
             k_cache_reset_log<<<1, 1, 0, st>>>(a.cache);
             e->launches++;
         }
-        unsigned g2 = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)e->sms * 3);
+        unsigned g2 = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)e->sms * 4);
         k_encode_tiles<<<g2, ENC_THREADS, sizeof(EncSmem), st>>>(a);
         e->launches++;
         if (a.cache.slots) {
@@ -770,6 +926,15 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
         }
     }
     MB_CUDA(cudaGetLastError());
+    if (getenv("MBPE_DEBUG")) {
+        uint32_t small[4];
+        uint32_t ctr[2] = {0, 0};
+        MB_CUDA(cudaMemcpyAsync(small, e->d_small, 16, cudaMemcpyDeviceToHost, st));
+        if (e->d_cache_ctr) MB_CUDA(cudaMemcpyAsync(ctr, e->d_cache_ctr, 8, cudaMemcpyDeviceToHost, st));
+        MB_CUDA(cudaStreamSynchronize(st));
+        fprintf(stderr, "[mbpe] encode: %llu chunks, %u scanned (cache misses), %u long, cache entries %u of %u\n",
+                (unsigned long long)n_chunks, small[3], small[1], ctr[1], e->cache_slots);
+    }
     return MBPE_OK;
 }
 
