@@ -190,6 +190,10 @@ int mbpe_split_dedup(const char *pattern, const uint8_t *text, uint64_t len, int
 /* .model / .vocab writer given a merge list (Tokenizer.h:875-926) */
 int mbpe_write_model(const char *path, const char *pattern, const char *special_contents, uint64_t special_len,
                      const uint32_t *merges, uint32_t n_merges, int write_vocab);
+/* multi-GPU encode: split n_chunks chunks into n_parts contiguous ranges of (nearly) equal BYTES; the ranges
+ * are whole chunks and in order, so the concatenation of the parts' id streams is the id stream of the whole
+ * (no communication). first_chunk_out gets n_parts+1 chunk indices. */
+int mbpe_plan_shards(const uint64_t *chunk_off, uint64_t n_chunks, uint32_t n_parts, uint64_t *first_chunk_out);
 /* deterministic synthetic Zipfian UTF-8 corpus (SURVEY 8(d) input 3): fills out[0..n) */
 int mbpe_synth_corpus(uint64_t seed, uint8_t *out, uint64_t n, int n_threads);
 

@@ -29,7 +29,7 @@ EXPORTS = [
     "mbpe_tokenizer_set_special_tokens", "mbpe_tokenizer_train", "mbpe_tokenizer_save", "mbpe_tokenizer_load",
     "mbpe_tokenizer_encode", "mbpe_tokenizer_decode", "mbpe_tokenizer_get_merges",
     "mbpe_tokenizer_last_train_stats", "mbpe_tokenizer_set_engine", "mbpe_tokenizer_set_threads",
-    "mbpe_split", "mbpe_dedup", "mbpe_split_dedup", "mbpe_write_model", "mbpe_synth_corpus",
+    "mbpe_split", "mbpe_dedup", "mbpe_split_dedup", "mbpe_plan_shards", "mbpe_write_model", "mbpe_synth_corpus",
 ]
 
 
@@ -367,6 +367,23 @@ def split_dedup(pattern: str, text: bytes, n_threads=0):
     _ck(lib().mbpe_split_dedup(*args, _p(tokens, C.c_uint32), C.c_uint64(len(tokens)), C.byref(nt), _p(off, C.c_uint64),
                                _p(w, C.c_uint32), C.c_uint64(len(w)), C.byref(nu), C.byref(nc)))
     return tokens[:nt.value], off, w[:nu.value], nc.value
+
+
+def plan_shards(chunk_off, n_parts):
+    """contiguous, byte-balanced chunk ranges for n_parts ranks; returns n_parts+1 chunk indices"""
+    off = np.ascontiguousarray(chunk_off, np.uint64)
+    out = np.zeros(n_parts + 1, np.uint64)
+    _ck(lib().mbpe_plan_shards(_p(off, C.c_uint64), C.c_uint64(len(off) - 1), C.c_uint32(n_parts), _p(out, C.c_uint64)))
+    return out
+
+
+def shard_for_rank(text: bytes, chunk_off, rank, world):
+    """this rank's slice of an encode job: (bytes, rebased chunk offsets, first chunk index)"""
+    plan = plan_shards(chunk_off, world)
+    c0, c1 = int(plan[rank]), int(plan[rank + 1])
+    off = np.ascontiguousarray(chunk_off, np.uint64)[c0:c1 + 1]
+    b0, b1 = int(off[0]), int(off[-1])
+    return text[b0:b1], off - np.uint64(b0), c0
 
 
 def write_model(path, pattern, special_contents, merges, write_vocab=False):

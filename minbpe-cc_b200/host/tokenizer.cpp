@@ -584,6 +584,29 @@ extern "C" int mbpe_write_model(const char *path, const char *pattern, const cha
     return rc ? fail(rc, err) : MBPE_OK;
 }
 
+extern "C" int mbpe_plan_shards(const uint64_t *chunk_off, uint64_t n_chunks, uint32_t n_parts,
+                                uint64_t *first_chunk_out) {
+    if (!chunk_off || !first_chunk_out || n_parts == 0) return fail(MBPE_E_INVALID, "null argument");
+    const uint64_t base = chunk_off[0], total = chunk_off[n_chunks] - base;
+    first_chunk_out[0] = 0;
+    uint64_t c = 0;
+    for (uint32_t p = 1; p < n_parts; p++) {
+        const uint64_t target = base + total / n_parts * p; // first chunk that starts at or after the byte target
+        uint64_t lo = c, hi = n_chunks;
+        while (lo < hi) {
+            uint64_t mid = (lo + hi) / 2;
+            if (chunk_off[mid] < target)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        c = lo;
+        first_chunk_out[p] = c;
+    }
+    first_chunk_out[n_parts] = n_chunks;
+    return MBPE_OK;
+}
+
 extern "C" int mbpe_synth_corpus(uint64_t seed, uint8_t *out, uint64_t n, int n_threads) {
     if (!out && n) return fail(MBPE_E_INVALID, "null argument");
     synth_corpus(seed, out, n, n_threads);

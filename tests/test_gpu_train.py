@@ -192,3 +192,15 @@ def test_tokenizer_train_save_bytes(pkg, manifest, name, tmp_path):
     assert hashlib.sha256(out.read_bytes()).hexdigest() == e["model_sha256"]
     if e["write_vocab"]:
         assert hashlib.sha256((tmp_path / "out.model.vocab").read_bytes()).hexdigest() == e["vocab_sha256"]
+
+
+@pytest.mark.parametrize("mode", ["lexical", "first"])
+def test_config3_shape_256mib_32k_vocab_vs_oracle(pkg, oracle, mode):
+    """BASELINE config 3 at a quarter of its corpus (256 MiB, vocab 32768): merge list and counts equal the oracle's.
+    bench.py repeats this diff at the full 1 GiB on every run."""
+    text = pkg.synth_corpus(0x5EED0001, 256 << 20).tobytes()
+    tok, off, w, n_chunks = pkg.split_dedup(pkg.patterns()["gpt4"], text)
+    assert int(w.sum()) == n_chunks
+    om, oc = oracle.train(tok, off, w, 32768, mode)
+    m, c, st = pkg.train(tok, off, w, 32768, mode)
+    assert m.shape == om.shape and (m == om).all() and (c == oc).all(), st
