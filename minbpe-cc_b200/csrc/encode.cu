@@ -266,31 +266,33 @@ __global__ void k_cache_reset_log(ChunkCache cc) { *cc.log_count = 0; }
 //   2. misses go to a tile work list and are encoded by the scan, one chunk per thread, all lanes busy;
 //   3. block scan + decoupled look-back give the tile its place in the flat stream; ids are written in order.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int ET_CPT = 4;
-constexpr int ET_CHUNKS = ENC_THREADS * ET_CPT;
 constexpr int ET_CAP = 8192;         // staged text bytes per tile (avg chunk 5 B -> 5 KB); bigger tiles read HBM directly
 constexpr uint32_t ET_MISS_OUT = 2048; // ids of scanned chunks parked in shared memory until the tile offset is known
 constexpr uint32_t META_NONE = 0xFFFFF;
 constexpr uint32_t ET_WARP_SCAN_MAX = 48; // up to this many misses per tile are scanned one warp per chunk
 
-struct EncSmem {
+template <int THREADS, int ET_CPT>
+struct EncSmemT {
+    static constexpr int ET_CHUNKS = THREADS * ET_CPT;
     uint32_t off[ET_CHUNKS + 1];
     alignas(16) uint32_t text[ET_CAP / 4 + 8]; // raw bytes, 16-byte aligned window
     uint16_t miss[ET_CHUNKS];      // work list: chunk index within the tile
     uint32_t meta[ET_CHUNKS];      // scanned chunks: start in miss_out (20 bits, META_NONE = not parked) | count << 20
     uint32_t miss_out[ET_MISS_OUT];
-    uint32_t warp_scratch[ENC_THREADS / 32][32];
+    uint32_t warp_scratch[THREADS / 32][32];
     uint32_t tile, n_miss, miss_used;
-    uint32_t warp_sum[ENC_THREADS / 32];
+    uint32_t warp_sum[THREADS / 32];
     unsigned long long base;
 };
 
-__device__ __forceinline__ uint8_t tile_byte(const EncArgs &a, const EncSmem &sm, bool staged, uint32_t a0, uint32_t g) {
+template <class SM>
+__device__ __forceinline__ uint8_t tile_byte(const EncArgs &a, const SM &sm, bool staged, uint32_t a0, uint32_t g) {
     return staged ? reinterpret_cast<const uint8_t *>(sm.text)[g - a0] : __ldg(&a.bytes[g]);
 }
 
 // scan one chunk (<= ENC_SHORT_MAX bytes) into t[]; returns the id count
-__device__ __forceinline__ uint32_t scan_chunk(const EncArgs &a, const EncSmem &sm, bool staged, uint32_t a0, uint32_t o,
+template <class SM>
+__device__ __forceinline__ uint32_t scan_chunk(const EncArgs &a, const SM &sm, bool staged, uint32_t a0, uint32_t o,
                                                uint32_t len, uint32_t *t) {
     for (uint32_t i = 0; i < len; i++) t[i] = tile_byte(a, sm, staged, a0, o + i);
     bool merged = true;
@@ -329,7 +331,11 @@ __device__ __forceinline__ uint32_t scan_chunk_warp(const EncTable &tab, uint32_
     return len;
 }
 
-__global__ void __launch_bounds__(ENC_THREADS, 4) k_encode_tiles(const EncArgs a) {
+template <int THREADS, int ET_CPT, int MIN_CTAS>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArgs a) {
+    using EncSmem = EncSmemT<THREADS, ET_CPT>;
+    constexpr int ET_CHUNKS = EncSmem::ET_CHUNKS;
+    constexpr int ENC_THREADS = THREADS; // shadows the file-level default inside this kernel
     extern __shared__ __align__(16) unsigned char enc_smem_raw[];
     EncSmem &sm = *reinterpret_cast<EncSmem *>(enc_smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -706,7 +712,20 @@ struct mbpe_encoder {
     uint32_t cache_slots = 0, cache_log_cap = 0, cache_arena_cap = 0;
     uint32_t *d_cache_ctr = nullptr; // [0] log count, [1] used slots, [2] arena cursor
     uint64_t sub_batch_chunks = 1u << 22;
+    int cfg = 0; // kernel shape, see enc_configs
 };
+
+namespace mbpe {
+struct EncConfig {
+    int threads, cpt, ctas;
+    void (*kernel)(const EncArgs);
+    size_t smem;
+};
+#define ENC_CFG(T, C, M) EncConfig{T, C, M, k_encode_tiles<T, C, M>, sizeof(EncSmemT<T, C>)}
+static const EncConfig enc_configs[] = {ENC_CFG(256, 4, 4), ENC_CFG(128, 4, 8), ENC_CFG(128, 8, 6), ENC_CFG(256, 8, 3),
+                                        ENC_CFG(512, 2, 2), ENC_CFG(64, 8, 16), ENC_CFG(128, 2, 12)};
+constexpr int N_ENC_CONFIGS = sizeof(enc_configs) / sizeof(enc_configs[0]);
+} // namespace mbpe
 
 extern "C" int mbpe_encoder_create(const uint32_t *merges, uint32_t n_merges, int device, mbpe_encoder **out) {
     if (!out || (n_merges && !merges)) return set_error(MBPE_E_INVALID, "null argument");
@@ -775,8 +794,11 @@ extern "C" int mbpe_encoder_create(const uint32_t *merges, uint32_t n_merges, in
         MB_CUDA(cudaMemset(e->d_cache_ctr, 0, 16));
     }
     const char *sb_env = getenv("MBPE_ENCODE_SUBBATCH");
-    if (sb_env && *sb_env) e->sub_batch_chunks = std::max<uint64_t>(ET_CHUNKS, strtoull(sb_env, nullptr, 10));
-    MB_CUDA(cudaFuncSetAttribute(k_encode_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem)));
+    if (sb_env && *sb_env) e->sub_batch_chunks = std::max<uint64_t>(4096, strtoull(sb_env, nullptr, 10)) / 4096 * 4096;
+    const char *cfg_env = getenv("MBPE_ENC_CFG");
+    e->cfg = cfg_env && *cfg_env ? std::min(std::max(atoi(cfg_env), 0), N_ENC_CONFIGS - 1) : 0;
+    for (int i = 0; i < N_ENC_CONFIGS; i++)
+        MB_CUDA(cudaFuncSetAttribute(enc_configs[i].kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_configs[i].smem));
     *out = e;
     return MBPE_OK;
 }
@@ -835,7 +857,8 @@ extern "C" int mbpe_encode_reserve(mbpe_encoder *e, uint64_t n_bytes, uint64_t n
     (void)n_bytes;
     int rc = use_device(e->device);
     if (rc) return rc;
-    if ((rc = ensure_status(e, (std::min(n_chunks, e->sub_batch_chunks) + ET_CHUNKS - 1) / ET_CHUNKS + 1))) return rc;
+    const uint64_t tile_chunks = (uint64_t)enc_configs[e->cfg].threads * enc_configs[e->cfg].cpt;
+    if ((rc = ensure_status(e, (std::min(n_chunks, e->sub_batch_chunks) + tile_chunks - 1) / tile_chunks + 1))) return rc;
     if (e->long_cap == 0) {
         e->long_cap = 1 << 16;
         MB_CUDA(cudaMalloc(&e->d_long_list, e->long_cap * 4));
@@ -906,6 +929,8 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
     a.miss_count = e->d_small + 3;
     // Sub-batches of whole tiles: the cache learns from one sub-batch before the next one starts, and the ids of
     // sub-batch i+1 continue the stream where sub-batch i ended (*d_n_out).
+    const EncConfig &kc = enc_configs[e->cfg];
+    const uint64_t ET_CHUNKS = (uint64_t)kc.threads * kc.cpt;
     for (uint64_t cb = 0; cb < n_chunks; cb += e->sub_batch_chunks) {
         a.chunk0 = cb;
         a.chunk1 = std::min(n_chunks, cb + e->sub_batch_chunks);
@@ -917,8 +942,8 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
             k_cache_reset_log<<<1, 1, 0, st>>>(a.cache);
             e->launches++;
         }
-        unsigned g2 = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)e->sms * 4);
-        k_encode_tiles<<<g2, ENC_THREADS, sizeof(EncSmem), st>>>(a);
+        unsigned g2 = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)e->sms * kc.ctas);
+        kc.kernel<<<g2, kc.threads, kc.smem, st>>>(a);
         e->launches++;
         if (a.cache.slots) {
             k_cache_insert<<<e->sms * 2, 256, 0, st>>>(a.cache);
