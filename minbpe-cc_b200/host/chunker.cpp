@@ -1,9 +1,12 @@
 // chunker.cpp -- regex pre-tokenisation (PCRE2), chunk dedup and the synthetic corpus generator. Host side.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <queue>
 #include <thread>
 
 #include "bpe_host.hpp"
@@ -339,45 +342,79 @@ static inline uint64_t hash_bytes(const uint8_t *p, uint64_t n) {
     return h;
 }
 
+// Open-addressed set of chunks. A slot keeps the chunk's bytes inline when it is <= 15 bytes (almost every
+// chunk of a regex split), so a repeat costs ONE cache line: no trip to the item list or back into the text.
 struct UniqueSet {
     struct Item {
         uint64_t hash, start;
         uint32_t len, count;
     };
-    std::vector<Item> items;      // first-appearance order
-    std::vector<uint32_t> slots;  // index + 1, 0 = empty
+    struct Slot {
+        uint64_t k0, k1; // len <= 15: the bytes (little endian, zero padded) and len in the top byte of k1
+                         // longer: k0 = hash, k1 = len | LONG_TAG; empty: k1 == 0
+        uint32_t idx;    // index into items
+        uint32_t count;  // occurrences seen through this slot (folded into items at the end)
+    };
+    static constexpr uint64_t LONG_TAG = 0xFFull << 56;
+    std::vector<Item> items; // first-appearance order
+    std::vector<Slot> slots;
     uint64_t mask = 0;
 
     void init(uint64_t cap) {
         uint64_t c = 1024;
         while (c < cap) c <<= 1;
-        slots.assign(c, 0);
+        slots.assign(c, Slot{0, 0, 0, 0});
         mask = c - 1;
     }
+    static inline void make_key(const uint8_t *p, uint32_t len, uint64_t hash, uint64_t *k0, uint64_t *k1) {
+        if (len <= 15) {
+            uint64_t a = 0, b = 0;
+            if (len >= 8) {
+                memcpy(&a, p, 8);
+                memcpy(&b, p + 8, len - 8);
+            } else {
+                memcpy(&a, p, len);
+            }
+            *k0 = a;
+            *k1 = b | ((uint64_t)len << 56);
+        } else {
+            *k0 = hash;
+            *k1 = (uint64_t)len | LONG_TAG;
+        }
+    }
     void grow() {
-        std::vector<uint32_t> ns((mask + 1) * 2, 0);
+        std::vector<Slot> ns((mask + 1) * 2, Slot{0, 0, 0, 0});
         uint64_t m = ns.size() - 1;
-        for (uint32_t i = 0; i < items.size(); i++) {
-            uint64_t h = items[i].hash & m;
-            while (ns[h]) h = (h + 1) & m;
-            ns[h] = i + 1;
+        for (const Slot &sl : slots) {
+            if (!sl.k1) continue;
+            uint64_t h = items[sl.idx].hash & m;
+            while (ns[h].k1) h = (h + 1) & m;
+            ns[h] = sl;
         }
         slots.swap(ns);
         mask = m;
     }
     void add(const uint8_t *text, uint64_t hash, uint64_t start, uint32_t len, uint32_t count) {
+        uint64_t k0, k1;
+        make_key(text + start, len, hash, &k0, &k1);
         uint64_t h = hash & mask;
-        while (slots[h]) {
-            Item &it = items[slots[h] - 1];
-            if (it.hash == hash && it.len == len && memcmp(text + it.start, text + start, len) == 0) {
-                it.count += count;
+        for (;;) {
+            Slot &sl = slots[h];
+            if (sl.k1 == 0) break;
+            if (sl.k0 == k0 && sl.k1 == k1 &&
+                (len <= 15 || memcmp(text + items[sl.idx].start, text + start, len) == 0)) {
+                sl.count += count;
                 return;
             }
             h = (h + 1) & mask;
         }
-        items.push_back(Item{hash, start, len, count});
-        slots[h] = (uint32_t)items.size();
+        slots[h] = Slot{k0, k1, (uint32_t)items.size(), count};
+        items.push_back(Item{hash, start, len, 0});
         if (items.size() * 2 > mask) grow();
+    }
+    void finish() { // fold the per-slot counters into the item list
+        for (const Slot &sl : slots)
+            if (sl.k1) items[sl.idx].count += sl.count;
     }
 };
 
@@ -404,11 +441,67 @@ static void corpus_from_set(const uint8_t *text, const UniqueSet &g, uint64_t n_
     }
 }
 
-// merge per-thread sets in thread (= text) order: global first-appearance order is preserved
+// Merge per-thread sets into local[0], keeping global first-appearance order (thread order = text order).
+// Parallel by hash partition: worker p walks every local item list in order and owns the keys whose hash falls
+// in partition p, so each partition list comes out sorted by (thread, index); a P-way merge of the partition
+// lists on that key restores the global order.
 static void merge_sets(const uint8_t *text, std::vector<UniqueSet> &local) {
-    UniqueSet &g = local[0];
-    for (size_t t = 1; t < local.size(); t++)
-        for (const auto &it : local[t].items) g.add(text, it.hash, it.start, it.len, it.count);
+    const size_t T = local.size();
+    if (T == 1) {
+        local[0].finish();
+        return;
+    }
+    const int P = (int)std::min<size_t>(T, (size_t)hardware_threads());
+    std::vector<UniqueSet> part(P);
+    std::vector<std::vector<uint64_t>> order(P); // (thread << 32 | index) of each partition item's first appearance
+    std::vector<std::thread> th;
+    {
+        std::atomic<size_t> next{0};
+        auto fin = [&]() {
+            for (size_t t; (t = next.fetch_add(1)) < T;) local[t].finish();
+        };
+        for (int p = 1; p < P; p++) th.emplace_back(fin);
+        fin();
+        for (auto &t : th) t.join();
+        th.clear();
+    }
+    size_t total = 0;
+    for (auto &l : local) total += l.items.size();
+    auto work = [&](int p) {
+        UniqueSet &g = part[p];
+        g.init(total / P / 2 + 1024);
+        for (size_t t = 0; t < T; t++) {
+            const auto &items = local[t].items;
+            for (size_t i = 0; i < items.size(); i++) {
+                const auto &it = items[i];
+                if ((int)(((it.hash >> 40) * (uint64_t)P) >> 24) != p) continue; // top 24 hash bits pick the partition
+                size_t before = g.items.size();
+                g.add(text, it.hash, it.start, it.len, it.count);
+                if (g.items.size() != before) order[p].push_back(((uint64_t)t << 32) | (uint64_t)i);
+            }
+        }
+        g.finish();
+    };
+    for (int p = 1; p < P; p++) th.emplace_back(work, p);
+    work(0);
+    for (auto &t : th) t.join();
+    // P-way merge on the first-appearance key
+    UniqueSet out;
+    out.items.reserve(total);
+    std::vector<size_t> cur(P, 0);
+    using Head = std::pair<uint64_t, int>;
+    std::priority_queue<Head, std::vector<Head>, std::greater<Head>> heap;
+    for (int p = 0; p < P; p++)
+        if (!order[p].empty()) heap.push({order[p][0], p});
+    while (!heap.empty()) {
+        auto [key, p] = heap.top();
+        heap.pop();
+        out.items.push_back(part[p].items[cur[p]]);
+        if (++cur[p] < order[p].size()) heap.push({order[p][cur[p]], p});
+    }
+    local[0].items.swap(out.items);
+    local[0].slots.clear(); // counts are final in items; the set is not added to again
+    local[0].mask = 0;
 }
 
 void dedup_chunks(const uint8_t *text, const std::vector<Span> &chunks, int n_threads, Corpus &out) {
@@ -460,10 +553,14 @@ int split_dedup_parallel(const Regex &re, const std::string &pattern, const uint
         });
         counts[s] = n;
     };
+    const bool dbg = getenv("MBPE_DEBUG") != nullptr;
+    auto tnow = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = tnow();
     std::vector<std::thread> th;
     for (int s = 1; s < n_seg; s++) th.emplace_back(work, s);
     work(0);
     for (auto &t : th) t.join();
+    const double t1 = tnow();
     uint64_t n_chunks = 0;
     for (int s = 0; s < n_seg; s++) {
         if (rcs[s] != MBPE_OK) {
@@ -473,7 +570,11 @@ int split_dedup_parallel(const Regex &re, const std::string &pattern, const uint
         n_chunks += counts[s];
     }
     merge_sets(text, local);
+    const double t2 = tnow();
     corpus_from_set(text, local[0], n_chunks, out);
+    if (dbg)
+        fprintf(stderr, "[mbpe] split+dedup: %d threads, scan %.3f s, merge %.3f s, build %.3f s\n", n_seg, t1 - t0, t2 - t1,
+                tnow() - t2);
     return MBPE_OK;
 }
 
