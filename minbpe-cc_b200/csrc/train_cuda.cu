@@ -44,6 +44,7 @@ struct PersistSmem {
     uint32_t rec_slot[PS_REC];
     uint32_t rec_pos[PS_REC];
     uint32_t newp[PS_REC];
+    uint32_t cand[PS_SEL * PERSISTENT_THREADS]; // mirror of the candidate list while it fits
 };
 
 __device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
@@ -82,17 +83,20 @@ __device__ __forceinline__ void fused_select(const Ctx &c) {
     }
     uint32_t slot_id[PS_SEL];
     uint4 head[PS_SEL]; // {key.lo, key.hi, cnt, len}
+    uint4 tail[PS_SEL]; // {first, seg, fill, pad}
     int32_t best = CMAX_NONE;
     uint32_t live = 0;
 #pragma unroll
     for (int k = 0; k < PS_SEL; k++) {
         uint32_t i = tid + k * PERSISTENT_THREADS;
-        slot_id[k] = i < n ? __ldcg(&c.cand[i]) : NIL;
+        slot_id[k] = i < n ? ctl_ld<true>(&c.cand[i]) : NIL; // shared-memory mirror (or this CTA's own global list)
     }
 #pragma unroll
     for (int k = 0; k < PS_SEL; k++) {
         if (slot_id[k] != NIL) {
-            head[k] = __ldcg(reinterpret_cast<const uint4 *>(&c.slot[slot_id[k]]));
+            const uint4 *sp = reinterpret_cast<const uint4 *>(&c.slot[slot_id[k]]);
+            head[k] = __ldcg(sp);
+            tail[k] = __ldcg(sp + 1);
             int32_t v = (int32_t)head[k].z;
             best = v > best ? v : best;
             live += (v >= theta);
@@ -121,7 +125,7 @@ __device__ __forceinline__ void fused_select(const Ctx &c) {
             if (mode == 1) {
                 tie[k] = ((uint64_t)head[k].y << 32) | head[k].x;
             } else {
-                uint32_t f = __ldcg(&c.slot[slot_id[k]].first);
+                uint32_t f = tail[k].x;
                 if (f == NO_FIRST)
                     c.fix[atomicAdd(&g->n_fix, 1u)] = slot_id[k];
                 else
@@ -147,8 +151,24 @@ __device__ __forceinline__ void fused_select(const Ctx &c) {
 #pragma unroll
     for (int k = 0; k < PS_SEL; k++)
         if (slot_id[k] != NIL && (int32_t)head[k].z == cmax && tie[k] == win) { // exactly one thread
+            // phase_sel_commit, with the slot already in registers (no further loads on the critical path)
+            const uint32_t seg_len = head[k].w, step = g->step;
             g->best_slot = slot_id[k];
-            phase_sel_commit<true>(c, 1);
+            g->seg_len = seg_len;
+            const uint64_t need = (uint64_t)g->n_pairs + 2ull * seg_len + 64;
+            if (need * MB_LOAD_DEN > ((uint64_t)c.cap_mask + 1) * MB_LOAD_NUM) {
+                g->status = ST_NEED_GROW;
+            } else {
+                g->a = head[k].y;
+                g->b = head[k].x;
+                g->new_id = 256 + step;
+                g->seg = tail[k].y;
+                c.merges_out[2 * step] = head[k].y;
+                c.merges_out[2 * step + 1] = head[k].x;
+                c.counts_out[step] = cmax;
+                g->selected = 1;
+                if (seg_len > g->big_limit) g->status = ST_BIG_MERGE;
+            }
         }
     __syncthreads();
 }
@@ -163,6 +183,14 @@ __global__ void __launch_bounds__(PERSISTENT_THREADS, 1) k_persistent(const Ctx 
     Ctx c = cg;
     c.ctl = &sm->ctl;
     Ctl *g = &sm->ctl;
+    const uint32_t n_cand_in = g->n_cand;
+    const bool cand_in_smem = n_cand_in <= PS_SEL * PERSISTENT_THREADS;
+    if (cand_in_smem) { // the candidate list lives in shared memory while this launch runs
+        for (uint32_t i = tid; i < n_cand_in; i += PERSISTENT_THREADS) sm->cand[i] = __ldcg(&cg.cand[i]);
+        c.cand = sm->cand;
+        c.cand_cap = PS_SEL * PERSISTENT_THREADS; // appends past it are dropped and phase_fin asks for a rebuild
+        __syncthreads();
+    }
     long long t0 = clock64();
     const long long t_enter = t0;
     auto lap = [&](int i) { // thread 0 only: cycles since the previous lap go to counter i
@@ -197,8 +225,16 @@ __global__ void __launch_bounds__(PERSISTENT_THREADS, 1) k_persistent(const Ctx 
             w.rec_pos = sm->rec_pos;
             w.newp = sm->newp;
         }
+        const long long th0 = clock64();
         phase_hits<true>(w, tid, PERSISTENT_THREADS);
         __syncthreads();
+        if (tid == 0) {
+            const uint32_t L = g->seg_len;
+            const int cls = L <= 32 ? 0 : L <= 256 ? 1 : L <= 1024 ? 2 : L <= 2048 ? 3 : L <= 8192 ? 4 : 5;
+            g->hh_steps[cls] += 1;
+            g->hh_cycles[cls] += (uint64_t)(clock64() - th0);
+            g->hh_occ[cls] += L;
+        }
         lap(1);
         phase_mutate<true>(w, tid, PERSISTENT_THREADS);   // corpus nodes
         phase_seg_alloc<true>(w, tid, PERSISTENT_THREADS); // new slots: disjoint data, same barrier
@@ -216,6 +252,10 @@ __global__ void __launch_bounds__(PERSISTENT_THREADS, 1) k_persistent(const Ctx 
     }
     if (tid == 0) g->prof[6] += (uint64_t)(clock64() - t_enter);
     __syncthreads();
+    if (cand_in_smem) {
+        const uint32_t n_out = min(g->n_cand, (uint32_t)(PS_SEL * PERSISTENT_THREADS));
+        for (uint32_t i = tid; i < n_out; i += PERSISTENT_THREADS) cg.cand[i] = sm->cand[i];
+    }
     if (tid < CTL_WORDS) reinterpret_cast<uint32_t *>(cg.ctl)[tid] = reinterpret_cast<const uint32_t *>(&sm->ctl)[tid];
 }
 
@@ -310,6 +350,7 @@ struct CudaBE {
     cudaError_t err = cudaSuccess;
     const char *err_what = "";
     Ctl *pinned = nullptr; // staging for the per-iteration control read
+    size_t l2_window_max = 0, l2_persist_bytes = 0;
 
     void note(cudaError_t e, const char *what) {
         if (e != cudaSuccess && err == cudaSuccess) {
@@ -386,7 +427,25 @@ struct CudaBE {
                  "smem attr");
             attr_set = true;
         }
-        k_persistent<<<1, PERSISTENT_THREADS, sizeof(PersistSmem), stream>>>(c);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(1);
+        cfg.blockDim = dim3(PERSISTENT_THREADS);
+        cfg.dynamicSmemBytes = sizeof(PersistSmem);
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        cfg.attrs = attr;
+        cfg.numAttrs = 0;
+        if (l2_window_max > 0) { // keep the pair table (the randomly probed structure) resident in L2
+            size_t bytes = ((size_t)c.cap_mask + 1) * sizeof(Slot);
+            attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+            attr[0].val.accessPolicyWindow.base_ptr = c.slot;
+            attr[0].val.accessPolicyWindow.num_bytes = std::min(bytes, l2_window_max);
+            attr[0].val.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)l2_persist_bytes / (double)std::min(bytes, l2_window_max));
+            attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cfg.numAttrs = 1;
+        }
+        note(cudaLaunchKernelEx(&cfg, k_persistent, c), "k_persistent launch");
         n_launch++;
         note(cudaGetLastError(), "k_persistent launch");
     }
@@ -480,6 +539,18 @@ extern "C" int mbpe_trainer_run(mbpe_trainer *t, uint32_t vocab_size, int mode, 
     be.stream = (cudaStream_t)stream;
     be.sms = sm_count(t->device);
     be.pinned = t->pinned_ctl;
+    if (!getenv("MBPE_NO_L2_PERSIST")) {
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, t->device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, t->device);
+        if (max_persist > 0 && max_window > 0 &&
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) == cudaSuccess) {
+            be.l2_window_max = (size_t)max_window;
+            be.l2_persist_bytes = (size_t)max_persist;
+        } else {
+            cudaGetLastError();
+        }
+    }
     TrainConfig cfg{vocab_size, mode, engine, env_u32("MBPE_BIG_LIMIT", 16384), env_u32("MBPE_CAND_WANT", 512),
                     env_u32("MBPE_CAND_LIMIT", PS_SEL * PERSISTENT_THREADS), env_u32("MBPE_INIT_SLOTS", 0)};
     TrainOutcome o;

@@ -132,6 +132,13 @@ class TrainLoop {
         out->n_grows = n_grows_;
         out->rescan_bytes = h.rescan_bytes;
         for (int i = 0; i < 8; i++) out->prof[i] = h.prof[i];
+        if (getenv("MBPE_DEBUG")) {
+            const char *names[6] = {"<=32", "<=256", "<=1024", "<=2048", "<=8192", ">8192"};
+            for (int i = 0; i < 6; i++)
+                fprintf(stderr, "[mbpe] hits seg_len %-7s steps %8llu  cycles %12llu (%7.0f/step)  occurrences %10llu\n", names[i],
+                        (unsigned long long)h.hh_steps[i], (unsigned long long)h.hh_cycles[i],
+                        h.hh_steps[i] ? (double)h.hh_cycles[i] / h.hh_steps[i] : 0.0, (unsigned long long)h.hh_occ[i]);
+        }
         if (getenv("MBPE_DEBUG")) fprintf(stderr, "[mbpe] select dbg: sum_ncand=%llu generic_steps=%llu max_ncand=%llu max_select_cycles=%llu slow_selects=%llu\n", (unsigned long long)h.prof[7], (unsigned long long)h.dbg[0], (unsigned long long)h.dbg[1], (unsigned long long)h.dbg[2], (unsigned long long)h.dbg[3]);
         if (h.step) {
             be_.download(h_merges, c_.merges_out, (uint64_t)h.step * 8);
@@ -180,7 +187,7 @@ class TrainLoop {
         uint32_t old_cap = c_.cap_mask + 1;
         uint64_t need = (uint64_t)h.n_pairs + 2ull * h.seg_len + 64; // same bound as phase_sel_commit
         uint64_t cap = (uint64_t)old_cap * 2; // stay as small as the load limit allows: L2 residency matters
-        while (need * 5 > cap * 3) cap *= 2;
+        while (need * MB_LOAD_DEN > cap * MB_LOAD_NUM) cap *= 2;
         be_.release(c_.cand);
         be_.release(c_.fix);
         alloc_table((uint32_t)cap);

@@ -43,6 +43,12 @@ constexpr uint64_t EMPTY_KEY = ~0ull;      // free slot
 constexpr uint32_t NO_FIRST = 0xFFFFFFFFu; // Slot.first unknown
 constexpr int32_t CMAX_NONE = INT32_MIN;
 constexpr int HIST_BUCKETS = 256;
+// pair-table load factor limit MB_LOAD_NUM / MB_LOAD_DEN: linear probing's TAIL (the slowest of a few hundred
+// concurrent probes, each step a dependent DRAM access) sets the step latency, so the table is kept sparse
+#ifndef MB_LOAD_NUM
+#define MB_LOAD_NUM 3
+#define MB_LOAD_DEN 10
+#endif
 
 // count -> bucket: floor(log2 v) and the next three mantissa bits (monotone in v); bucket -> its smallest count
 MB_HD uint32_t hist_bucket(uint32_t v) {
@@ -118,6 +124,7 @@ struct Ctl {
     // resident-CTA cycle counters (thread 0, clock64): select, hits, mutate+seg_alloc, seg_fill, fin, steps, total
     uint64_t prof[8];
     uint64_t dbg[4];
+    uint64_t hh_steps[6], hh_cycles[6], hh_occ[6]; // hits phase by segment length class (debug)
 };
 
 struct Ctx {
@@ -310,17 +317,25 @@ MB_HD uint32_t slot_upsert(const Ctx &c, uint64_t key, bool *created) {
 
 // probe continuation: `s` = home slot of `key`, `k0` = the key word already loaded from it. Lets a thread start
 // several probes (independent loads in flight) before resolving any of them.
+// After the home slot the walk continues FOUR slots per round trip (independent loads, same or adjacent 128-byte
+// line), examined in probe order: the result is the one plain linear probing gives, but a chain of length L costs
+// 1 + ceil((L - 1) / 4) dependent memory accesses instead of L.
 MB_HD uint32_t slot_find_from(const Ctx &c, uint64_t key, uint32_t s, uint64_t k0) {
+    if (k0 == key) return s;
+    if (k0 == EMPTY_KEY) return NIL;
     for (;;) {
-        if (k0 == key) return s;
-        if (k0 == EMPTY_KEY) return NIL;
-        s = (s + 1) & c.cap_mask;
-        k0 = ld_l2(&c.slot[s].key);
+        uint64_t k[4];
+        for (int i = 0; i < 4; i++) k[i] = ld_l2(&c.slot[(s + 1 + i) & c.cap_mask].key);
+        for (int i = 0; i < 4; i++) {
+            if (k[i] == key) return (s + 1 + i) & c.cap_mask;
+            if (k[i] == EMPTY_KEY) return NIL;
+        }
+        s = (s + 4) & c.cap_mask;
     }
 }
 MB_HD uint32_t slot_upsert_from(const Ctx &c, uint64_t key, uint32_t s, uint64_t k0, bool *created) {
     *created = false;
-    for (;;) {
+    for (;;) { // slot s holds k0 (possibly stale if it was EMPTY: the CAS answers that)
         if (k0 == key) return s;
         if (k0 == EMPTY_KEY) {
             uint64_t old = a_cas(&c.slot[s].key, EMPTY_KEY, key);
@@ -330,9 +345,31 @@ MB_HD uint32_t slot_upsert_from(const Ctx &c, uint64_t key, uint32_t s, uint64_t
             }
             if (old == key) return s;
         }
-        s = (s + 1) & c.cap_mask;
-        k0 = ld_l2(&c.slot[s].key);
+        uint64_t k[4];
+        for (int i = 0; i < 4; i++) k[i] = ld_l2(&c.slot[(s + 1 + i) & c.cap_mask].key);
+        int i = 0;
+        for (; i < 4; i++) {
+            if (k[i] == key) return (s + 1 + i) & c.cap_mask;
+            if (k[i] == EMPTY_KEY) break; // try to claim it: back to the top with this slot
+        }
+        if (i < 4) {
+            s = (s + 1 + i) & c.cap_mask;
+            k0 = EMPTY_KEY;
+        } else {
+            s = (s + 4) & c.cap_mask; // k[3] was neither the key nor empty: continue after it
+            k0 = k[3];
+        }
     }
+}
+
+// upsert when the claim of the home slot (CAS EMPTY -> key) was already issued: `old` is its answer
+MB_HD uint32_t upsert_after_claim(const Ctx &c, uint64_t key, uint32_t home, uint64_t first_key, bool tried, uint64_t old,
+                                  bool *created) {
+    if (!tried) return slot_upsert_from(c, key, home, first_key, created);
+    *created = (old == EMPTY_KEY);
+    if (old == EMPTY_KEY || old == key) return home;
+    const uint32_t s = (home + 1) & c.cap_mask; // somebody else took the home slot with another key
+    return slot_upsert_from(c, key, s, ld_l2(&c.slot[s].key), created);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -363,9 +400,11 @@ MB_HD void pair_inc(const Ctx &c, int32_t mode, uint32_t p, uint32_t q, uint32_t
 }
 MB_HD void pair_inc_at(const Ctx &c, int32_t mode, uint32_t s, bool created, uint64_t key, uint32_t w, uint32_t pairpos) {
     if (created) {
-        c.newp[a_add(&c.ctl->n_newp, 1u)] = s;
-        a_add(&c.ctl->n_pairs, 1u);
-        a_min(&c.ctl->min_key_ever, key);
+        // n_pairs is advanced by n_newp in phase_fin; the all-time smallest key only changes when a smaller one
+        // shows up, so the (contended, CAS-loop) 64-bit atomic is behind a plain read
+        c.newp[claim_one(&c.ctl->n_newp)] = s;
+        // (a stale read can only be too LARGE -- the minimum never grows -- so it never skips a needed update)
+        if (key < *reinterpret_cast<const volatile uint64_t *>(&c.ctl->min_key_ever)) a_min(&c.ctl->min_key_ever, key);
     }
     // cnt (low word) += w and len (high word) += 1 in one 64-bit atomic: both only grow during the birth step
     a_add(reinterpret_cast<uint64_t *>(&c.slot[s].cnt), ((uint64_t)1 << 32) | (uint64_t)w);
@@ -496,7 +535,7 @@ MB_HD void phase_sel_commit(const Ctx &c, int persistent) {
     g->seg_len = seg_len;
     // every occurrence can create two pairs; keep the load factor under 0.6 after the step
     uint64_t need = (uint64_t)MB_G(n_pairs) + 2ull * seg_len + 64;
-    if (need * 5 > ((uint64_t)c.cap_mask + 1) * 3) {
+    if (need * MB_LOAD_DEN > ((uint64_t)c.cap_mask + 1) * MB_LOAD_NUM) {
         g->status = ST_NEED_GROW; // slots move: the step is re-selected after the rehash
         return;
     }
@@ -559,16 +598,21 @@ MB_HD void phase_hits(const Ctx &c, uint32_t tid, uint32_t nth) {
                 fd2 = ld_l2(&c.slot[hd2].key);
                 fi2 = ld_l2(&c.slot[hi2].key);
             }
+            // both claims of empty home slots go out before either answer is needed
+            uint64_t o1 = 0, o2 = 0;
+            const bool try1 = do_l && fi1 == EMPTY_KEY, try2 = has_r && fi2 == EMPTY_KEY;
+            if (try1) o1 = a_cas(&c.slot[hi1].key, EMPTY_KEY, ki1);
+            if (try2) o2 = a_cas(&c.slot[hi2].key, EMPTY_KEY, ki2);
             if (do_l) {
                 bool created;
                 pair_dec_at(c, mode, slot_find_from(c, kd1, hd1, fd1), w, p.prv);
-                uint32_t s1 = slot_upsert_from(c, ki1, hi1, fi1, &created);
+                uint32_t s1 = upsert_after_claim(c, ki1, hi1, fi1, try1, o1, &created);
                 pair_inc_at(c, mode, s1, created, ki1, w, p.prv);
             }
             if (has_r) {
                 bool created;
                 pair_dec_at(c, mode, slot_find_from(c, kd2, hd2, fd2), w, j);
-                uint32_t s2 = slot_upsert_from(c, ki2, hi2, fi2, &created);
+                uint32_t s2 = upsert_after_claim(c, ki2, hi2, fi2, try2, o2, &created);
                 pair_inc_at(c, mode, s2, created, ki2, w, pos);
             }
         } else {
@@ -650,6 +694,7 @@ MB_HD void phase_fin(const Ctx &c) {
     Ctl *g = c.ctl;
     uint64_t live = MB_G(live_tokens);
     uint32_t n_hit = MB_G(n_hit), n_cand = MB_G(n_cand), step = MB_G(step) + 1;
+    g->n_pairs = MB_G(n_pairs) + MB_G(n_newp); // every slot created in this step is on the newp list
     // B_train(m) = 4 T_m + 4 T_m + 4 T_{m+1} + 16 P_m
     g->rescan_bytes = MB_G(rescan_bytes) + 8ull * live + 4ull * (live - n_hit) + 16ull * MB_G(n_pairs);
     g->live_tokens = live - n_hit;
@@ -665,8 +710,9 @@ MB_HD void phase_fin(const Ctx &c) {
     int32_t st = (step >= MB_G(n_target)) ? ST_DONE : ST_RUN;
     // list is mostly dead weight, or longer than the resident CTA keeps in registers: rebuild (full-grid scan,
     // fresh theta) before the next selection
-    if (st == ST_RUN && (n_cand > 2 * MB_G(n_live) + 1024 || (n_cand > MB_G(cand_limit) && n_cand > 2 * MB_G(cand_base))))
-        st = ST_NEED_REBUILD;
+    if (st == ST_RUN && (n_cand > 2 * MB_G(n_live) + 1024 || n_cand > c.cand_cap ||
+                         (n_cand > MB_G(cand_limit) && n_cand > 2 * MB_G(cand_base))))
+        st = ST_NEED_REBUILD; // n_cand > cand_cap: appends were dropped, only a table scan restores the list
     g->n_live = 0;
     g->status = st;
 }
