@@ -18,7 +18,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 CU = ["capi.cu", "train_cuda.cu", "encode.cu"]
 CPP = ["chunker.cpp", "tokenizer.cpp"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
+EXTRA_DEFS = [d for d in os.environ.get("MBPE_DEFS", "").split() if d]  # e.g. MBPE_DEFS="-DMBPE_PROFILE_HITS"
+NVCC_FLAGS = EXTRA_DEFS + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
               "-Xcompiler", "-fPIC", "-cudart", "static"]
 CXX_FLAGS = ["-std=c++23", "-O3", "-fPIC", "-Wall", "-pthread"]
 

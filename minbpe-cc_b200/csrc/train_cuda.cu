@@ -234,6 +234,10 @@ __global__ void __launch_bounds__(PERSISTENT_THREADS, 1) k_persistent(const Ctx 
             g->hh_steps[cls] += 1;
             g->hh_cycles[cls] += (uint64_t)(clock64() - th0);
             g->hh_occ[cls] += L;
+            for (int i = 0; i < 6; i++) {
+                g->pt_sum[cls][i] += g->pt_max[i];
+                g->pt_max[i] = 0;
+            }
         }
         lap(1);
         phase_mutate<true>(w, tid, PERSISTENT_THREADS);   // corpus nodes

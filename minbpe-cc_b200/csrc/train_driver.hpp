@@ -138,6 +138,12 @@ class TrainLoop {
                 fprintf(stderr, "[mbpe] hits seg_len %-7s steps %8llu  cycles %12llu (%7.0f/step)  occurrences %10llu\n", names[i],
                         (unsigned long long)h.hh_steps[i], (unsigned long long)h.hh_cycles[i],
                         h.hh_steps[i] ? (double)h.hh_cycles[i] / h.hh_steps[i] : 0.0, (unsigned long long)h.hh_occ[i]);
+            for (int i = 0; i < 6; i++)
+                if (h.pt_sum[i][5])
+                    fprintf(stderr, "[mbpe]   slowest thread, avg cycles at checkpoints (nodes, neighbours, probes out, claims out, left done, right done) %-7s: %.0f %.0f %.0f %.0f %.0f %.0f\n",
+                            names[i], (double)h.pt_sum[i][0] / h.hh_steps[i], (double)h.pt_sum[i][1] / h.hh_steps[i],
+                            (double)h.pt_sum[i][2] / h.hh_steps[i], (double)h.pt_sum[i][3] / h.hh_steps[i],
+                            (double)h.pt_sum[i][4] / h.hh_steps[i], (double)h.pt_sum[i][5] / h.hh_steps[i]);
         }
         if (getenv("MBPE_DEBUG")) fprintf(stderr, "[mbpe] select dbg: sum_ncand=%llu generic_steps=%llu max_ncand=%llu max_select_cycles=%llu slow_selects=%llu\n", (unsigned long long)h.prof[7], (unsigned long long)h.dbg[0], (unsigned long long)h.dbg[1], (unsigned long long)h.dbg[2], (unsigned long long)h.dbg[3]);
         if (h.step) {

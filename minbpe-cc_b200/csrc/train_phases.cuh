@@ -125,6 +125,9 @@ struct Ctl {
     uint64_t prof[8];
     uint64_t dbg[4];
     uint64_t hh_steps[6], hh_cycles[6], hh_occ[6]; // hits phase by segment length class (debug)
+    uint32_t pt_max[6];      // MBPE_PROFILE_HITS: slowest thread of the current step at checkpoints A..F
+    uint32_t pt_pad[2];
+    uint64_t pt_sum[6][6];   // summed per segment length class
 };
 
 struct Ctx {
@@ -556,9 +559,17 @@ MB_HD void phase_sel_commit(const Ctx &c, int persistent) {
 // the corpus), and record what to rewrite. Net effect == merge_incremental's (Tokenizer.h:239-280): exact
 // counts of the rewritten text; -(a,b) itself is folded into "count(a,b) := 0" in phase_fin.
 // ---------------------------------------------------------------------------------------------------------
+#if defined(MBPE_PROFILE_HITS) && MB_ON_DEVICE
+#define MB_PT(i) atomicMax(&g->pt_max[i], (uint32_t)(clock64() - pt_t0))
+#else
+#define MB_PT(i)
+#endif
 template <bool S = false>
 MB_HD void phase_hits(const Ctx &c, uint32_t tid, uint32_t nth) {
     Ctl *g = c.ctl;
+#if defined(MBPE_PROFILE_HITS) && MB_ON_DEVICE
+    const long long pt_t0 = clock64();
+#endif
     const uint32_t a = MB_G(a), b = MB_G(b), id = MB_G(new_id), seg = MB_G(seg), len = MB_G(seg_len);
     const int32_t mode = MB_G(mode);
     for (uint32_t k = tid; k < len; k += nth) {
@@ -568,6 +579,7 @@ MB_HD void phase_hits(const Ctx &c, uint32_t tid, uint32_t nth) {
         uint32_t j = p.nxt;
         Node q = ld_node<S>(&c.node[j]);
         if (q.tok != b) continue;
+        MB_PT(0);
         const uint32_t w = p.wt;
         if (a != b) {
             c.hit[claim_one(&g->n_hit)] = pos;
@@ -582,6 +594,7 @@ MB_HD void phase_hits(const Ctx &c, uint32_t tid, uint32_t nth) {
             uint32_t xx = DEAD, yy = DEAD;
             if (need_xx) xx = ld_tok<S>(&c.node[x.prv].tok);
             if (need_yy) yy = ld_tok<S>(&c.node[y.nxt].tok);
+            MB_PT(1);
             // x is the tail of another occurrence ("abab"): that occurrence's right side covers this gap
             const bool do_l = has_l && !(need_xx && xx == a);
             const bool head = need_yy && yy == b; // y starts another occurrence: the new right pair is (id, id)
@@ -598,23 +611,27 @@ MB_HD void phase_hits(const Ctx &c, uint32_t tid, uint32_t nth) {
                 fd2 = ld_l2(&c.slot[hd2].key);
                 fi2 = ld_l2(&c.slot[hi2].key);
             }
+            MB_PT(2);
             // both claims of empty home slots go out before either answer is needed
             uint64_t o1 = 0, o2 = 0;
             const bool try1 = do_l && fi1 == EMPTY_KEY, try2 = has_r && fi2 == EMPTY_KEY;
             if (try1) o1 = a_cas(&c.slot[hi1].key, EMPTY_KEY, ki1);
             if (try2) o2 = a_cas(&c.slot[hi2].key, EMPTY_KEY, ki2);
+            MB_PT(3);
             if (do_l) {
                 bool created;
                 pair_dec_at(c, mode, slot_find_from(c, kd1, hd1, fd1), w, p.prv);
                 uint32_t s1 = upsert_after_claim(c, ki1, hi1, fi1, try1, o1, &created);
                 pair_inc_at(c, mode, s1, created, ki1, w, p.prv);
             }
+            MB_PT(4);
             if (has_r) {
                 bool created;
                 pair_dec_at(c, mode, slot_find_from(c, kd2, hd2, fd2), w, j);
                 uint32_t s2 = upsert_after_claim(c, ki2, hi2, fi2, try2, o2, &created);
                 pair_inc_at(c, mode, s2, created, ki2, w, pos);
             }
+            MB_PT(5);
         } else {
             // a == b: left-to-right non-overlapping rule (Tokenizer.h:176-191). Only the start of a run of a's
             // acts; it walks its run and merges the 1st, 3rd, 5th... pair.
