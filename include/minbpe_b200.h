@@ -107,6 +107,19 @@ int mbpe_train(const uint32_t *tokens, uint64_t n_tokens, const uint64_t *chunk_
                const uint32_t *chunk_weight, uint32_t vocab_size, int mode, uint32_t *merges_out, int32_t *counts_out,
                uint32_t *n_merges_out);
 
+/* Sharded training, one process per GPU. Rank r owns a contiguous, token-balanced share of the unique
+ * chunks and a full replica of the pair table with GLOBAL counts; every merge step all-gathers the ranks' count
+ * deltas over NCCL/NVLink, so every rank picks the same pair with no broadcast and ends with the same merge list.
+ * Every rank passes the SAME deduplicated corpus. The 128-byte id comes from rank 0 (mbpe_comm_unique_id) and
+ * reaches the other ranks by any means (torch.distributed broadcast in bench.py). NCCL is loaded at run time. */
+typedef struct mbpe_comm mbpe_comm;
+int mbpe_comm_unique_id(uint8_t *id_out /* 128 bytes */);
+int mbpe_comm_create(const uint8_t *id /* 128 bytes */, int rank, int world, int device, mbpe_comm **out);
+void mbpe_comm_destroy(mbpe_comm *c);
+int mbpe_train_sharded(mbpe_comm *comm, const uint32_t *tokens, uint64_t n_tokens, const uint64_t *chunk_off,
+                       uint64_t n_chunks, const uint32_t *chunk_weight, uint32_t vocab_size, int mode, void *stream,
+                       uint32_t *merges_out, int32_t *counts_out, uint32_t *n_merges_out, mbpe_train_stats *stats);
+
 /* ------------------------------------------------------------------------------------------------------------
  * 3. Encode merge scan + decode  (Tokenizer.h:325-377 internal_internal_encode / internal_encode, :714-717
  *    flatten; :725-751 decode; lookup table built as load() does, :833-837, later duplicate pairs overwrite)

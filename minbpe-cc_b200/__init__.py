@@ -23,6 +23,7 @@ EXPORTS = [
     "mbpe_paircount_create", "mbpe_paircount_destroy", "mbpe_paircount_add", "mbpe_paircount_top",
     "mbpe_paircount_get", "mbpe_paircount_size",
     "mbpe_trainer_create", "mbpe_trainer_run", "mbpe_trainer_destroy", "mbpe_train",
+    "mbpe_comm_unique_id", "mbpe_comm_create", "mbpe_comm_destroy", "mbpe_train_sharded",
     "mbpe_encoder_create", "mbpe_encoder_destroy", "mbpe_encoder_set_specials", "mbpe_encode", "mbpe_encode_device",
     "mbpe_encode_reserve", "mbpe_decode",
     "mbpe_gpt2_split_pattern", "mbpe_gpt4_split_pattern", "mbpe_tokenizer_create", "mbpe_tokenizer_destroy",
@@ -70,6 +71,7 @@ def lib():
         L.mbpe_trainer_destroy.restype = None
         L.mbpe_encoder_destroy.restype = None
         L.mbpe_paircount_destroy.restype = None
+        L.mbpe_comm_destroy.restype = None
         L.mbpe_tokenizer_set_engine.restype = None
         L.mbpe_tokenizer_set_threads.restype = None
         _lib = L
@@ -188,6 +190,41 @@ def train(tokens, off, weight, vocab_size, mode, engine="persistent", device=0):
         return t.run(vocab_size, mode, engine)
     finally:
         t.close()
+
+
+class Comm:
+    """NCCL communicator for sharded training (one process per GPU). `bcast` moves rank 0's 128-byte id to the others."""
+
+    def __init__(self, rank, world, device, bcast):
+        ident = np.zeros(128, np.uint8)
+        if rank == 0:
+            _ck(lib().mbpe_comm_unique_id(_p(ident, C.c_uint8)))
+        ident = np.ascontiguousarray(bcast(ident), np.uint8)
+        self.h = C.c_void_p()
+        self.rank, self.world = rank, world
+        _ck(lib().mbpe_comm_create(_p(ident, C.c_uint8), rank, world, device, C.byref(self.h)))
+
+    def train(self, tokens, off, weight, vocab_size, mode, stream=None):
+        tokens = np.ascontiguousarray(tokens, np.uint32)
+        off = np.ascontiguousarray(off, np.uint64)
+        weight = None if weight is None else np.ascontiguousarray(weight, np.uint32)
+        n = max(vocab_size - 256, 1)
+        merges = np.zeros((n, 2), np.uint32)
+        counts = np.zeros(n, np.int32)
+        nm = C.c_uint32()
+        st = TrainStats()
+        tok = tokens if len(tokens) else np.zeros(1, np.uint32)
+        _ck(lib().mbpe_train_sharded(self.h, _p(tok, C.c_uint32), C.c_uint64(len(tokens)), _p(off, C.c_uint64),
+                                     C.c_uint64(len(off) - 1), None if weight is None else _p(weight, C.c_uint32),
+                                     C.c_uint32(vocab_size), MODE[mode] if isinstance(mode, str) else mode,
+                                     C.c_void_p(stream or 0), _p(merges, C.c_uint32), _p(counts, C.c_int32), C.byref(nm),
+                                     C.byref(st)))
+        return merges[:nm.value].copy(), counts[:nm.value].copy(), st.as_dict()
+
+    def close(self):
+        if self.h:
+            lib().mbpe_comm_destroy(self.h)
+            self.h = C.c_void_p()
 
 
 # ---- 3. encode / decode ---------------------------------------------------------------------------------

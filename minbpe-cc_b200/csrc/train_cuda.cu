@@ -8,6 +8,8 @@
 //   k_persistent            persistent_program(): one resident 1024-thread CTA runs merge steps back to back
 //                           (selection, hits, mutate, segment build) with __syncthreads() as the phase barrier
 //   k_pc_*                  PairCount seam (PairCount.h:27-47): batched upsert, block-then-grid arg-max, lookup
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -330,13 +332,13 @@ __global__ void __launch_bounds__(IC_THREADS) k_init_count(const Ctx c) {
                 if (k == key) {
                     atomicAdd(&sm->w[s], nd.w);
                     atomicAdd(&sm->n[s], 1u);
-                    atomicMin(&sm->first[s], (uint32_t)i);
+                    atomicMin(&sm->first[s], c.pos_base + (uint32_t)i);
                     done = true;
                     break;
                 }
                 s = (s + 1) & (IC_SLOTS - 1);
             }
-            if (!done) count_one(c, key, nd.w, 1u, (uint32_t)i); // crowded neighbourhood: straight to HBM
+            if (!done) count_one(c, key, nd.w, 1u, c.pos_base + (uint32_t)i); // crowded neighbourhood: straight to HBM
         }
         __syncthreads();
         if (sm->used > IC_SLOTS / 2) ic_flush(c, sm); // block-uniform: read after the barrier
@@ -347,8 +349,88 @@ __global__ void __launch_bounds__(IC_THREADS) k_init_count(const Ctx c) {
 // ---------------------------------------------------------------------------------------------------------
 // CUDA backend for TrainLoop
 // ---------------------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------
+// NCCL, resolved at run time (libnccl.so.2: the copy already loaded by the host process -- e.g. torch's -- or the
+// system one). Only the sharded trainer needs it; single-GPU use never touches it.
+// ---------------------------------------------------------------------------------------------------------
+struct NcclApi {
+    typedef struct ncclComm *comm_t;
+    struct unique_id {
+        char internal[128];
+    };
+    int (*GetUniqueId)(unique_id *) = nullptr;
+    int (*CommInitRank)(comm_t *, int, unique_id, int) = nullptr;
+    int (*CommDestroy)(comm_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int /*dtype*/, comm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+    static NcclApi &get() {
+        static NcclApi api;
+        static bool tried = false;
+        if (!tried) {
+            tried = true;
+            void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+            if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+            if (h) {
+                api.GetUniqueId = (int (*)(unique_id *))dlsym(h, "ncclGetUniqueId");
+                api.CommInitRank = (int (*)(comm_t *, int, unique_id, int))dlsym(h, "ncclCommInitRank");
+                api.CommDestroy = (int (*)(comm_t))dlsym(h, "ncclCommDestroy");
+                api.AllGather = (int (*)(const void *, void *, size_t, int, comm_t, cudaStream_t))dlsym(h, "ncclAllGather");
+                api.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+                api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather;
+            }
+        }
+        return api;
+    }
+};
+constexpr int NCCL_UINT8 = 1; // ncclUint8 (nccl.h ncclDataType_t)
+
 struct CudaBE {
     cudaStream_t stream = nullptr;
+    // sharded training
+    NcclApi::comm_t nccl = nullptr;
+    uint32_t comm_world = 1, comm_rank = 0;
+    XRec *d_all = nullptr;
+    uint64_t all_cap = 0;
+    uint32_t *d_counts = nullptr, *d_my_count = nullptr;
+    uint32_t world() const { return comm_world; }
+    uint32_t rank() const { return comm_rank; }
+    // all-gather of this step's count deltas over NVLink: counts first (they size the padded second gather)
+    void exchange(const XRec *d_send, uint32_t n_send, const XRec **out_all, const uint32_t **out_counts, uint32_t *stride) {
+        *out_all = d_all;
+        *out_counts = d_counts;
+        *stride = 0;
+        if (err != cudaSuccess) return;
+        NcclApi &api = NcclApi::get();
+        if (!d_counts) {
+            note(cudaMalloc(&d_counts, comm_world * 4), "cudaMalloc counts");
+            note(cudaMalloc(&d_my_count, 4), "cudaMalloc count");
+        }
+        note(cudaMemcpyAsync(d_my_count, &n_send, 4, cudaMemcpyHostToDevice, stream), "H2D count");
+        if (api.AllGather(d_my_count, d_counts, 4, NCCL_UINT8, nccl, stream) != 0) note(cudaErrorUnknown, "ncclAllGather counts");
+        std::vector<uint32_t> h(comm_world);
+        note(cudaMemcpyAsync(h.data(), d_counts, comm_world * 4, cudaMemcpyDeviceToHost, stream), "D2H counts");
+        note(cudaStreamSynchronize(stream), "sync");
+        uint32_t mx = 0;
+        for (uint32_t v : h) mx = std::max(mx, v);
+        if (mx == 0) {
+            *out_counts = d_counts;
+            return;
+        }
+        if ((uint64_t)mx * comm_world > all_cap) {
+            if (d_all) note(cudaFree(d_all), "cudaFree");
+            all_cap = (uint64_t)mx * comm_world * 2;
+            note(cudaMalloc(&d_all, all_cap * sizeof(XRec)), "cudaMalloc exchange buffer");
+        }
+        // every rank sends `mx` records (its own count + padding): all send buffers are sized for the global worst case
+        if (api.AllGather(d_send, d_all, (size_t)mx * sizeof(XRec), NCCL_UINT8, nccl, stream) != 0)
+            note(cudaErrorUnknown, "ncclAllGather records");
+        n_launch += 2;
+        *out_all = d_all;
+        *out_counts = d_counts;
+        *stride = mx;
+    }
+
     int sms = 148;
     uint64_t n_launch = 0;
     cudaError_t err = cudaSuccess;
@@ -598,6 +680,150 @@ extern "C" int mbpe_train(const uint32_t *tokens, uint64_t n_tokens, const uint6
                           nullptr);
     mbpe_trainer_destroy(t);
     return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// C ABI: sharded training over NCCL (one process per GPU)
+// ---------------------------------------------------------------------------------------------------------
+struct mbpe_comm {
+    NcclApi::comm_t nccl = nullptr;
+    int rank = 0, world = 1, device = 0;
+};
+
+extern "C" int mbpe_comm_unique_id(uint8_t *id_out) {
+    if (!id_out) return set_error(MBPE_E_INVALID, "null argument");
+    NcclApi &api = NcclApi::get();
+    if (!api.ok) return set_error(MBPE_E_NO_DEVICE, "libnccl.so.2 could not be loaded");
+    NcclApi::unique_id id;
+    if (api.GetUniqueId(&id) != 0) return set_error(MBPE_E_CUDA, "ncclGetUniqueId failed");
+    memcpy(id_out, id.internal, 128);
+    return MBPE_OK;
+}
+
+extern "C" int mbpe_comm_create(const uint8_t *id_bytes, int rank, int world, int device, mbpe_comm **out) {
+    if (!id_bytes || !out || world < 1 || rank < 0 || rank >= world) return set_error(MBPE_E_INVALID, "bad argument");
+    *out = nullptr;
+    int rc = use_device(device);
+    if (rc) return rc;
+    NcclApi &api = NcclApi::get();
+    if (!api.ok) return set_error(MBPE_E_NO_DEVICE, "libnccl.so.2 could not be loaded");
+    NcclApi::unique_id id;
+    memcpy(id.internal, id_bytes, 128);
+    mbpe_comm *c = new mbpe_comm();
+    c->rank = rank;
+    c->world = world;
+    c->device = device;
+    int nrc = api.CommInitRank(&c->nccl, world, id, rank);
+    if (nrc != 0) {
+        delete c;
+        return set_error(MBPE_E_CUDA, std::string("ncclCommInitRank failed: ") + (api.GetErrorString ? api.GetErrorString(nrc) : "?"));
+    }
+    *out = c;
+    return MBPE_OK;
+}
+
+extern "C" void mbpe_comm_destroy(mbpe_comm *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->nccl) NcclApi::get().CommDestroy(c->nccl);
+    delete c;
+}
+
+extern "C" int mbpe_train_sharded(mbpe_comm *comm, const uint32_t *tokens, uint64_t n_tokens, const uint64_t *chunk_off,
+                                  uint64_t n_chunks, const uint32_t *chunk_weight, uint32_t vocab_size, int mode,
+                                  void *stream, uint32_t *merges_out, int32_t *counts_out, uint32_t *n_merges_out,
+                                  mbpe_train_stats *stats) {
+    if (!comm || !merges_out || !n_merges_out || !chunk_off || (!tokens && n_tokens))
+        return set_error(MBPE_E_INVALID, "null argument");
+    if (vocab_size < 256) return set_error(MBPE_E_INVALID, "vocab_size must be >= 256 (Tokenizer.h:492)");
+    if (mode != MBPE_MODE_FIRST && mode != MBPE_MODE_LEXICAL) return set_error(MBPE_E_INVALID, "bad mode");
+    if (n_tokens >= (1ull << 30)) return set_error(MBPE_E_INVALID, "n_tokens must be < 2^30");
+    if (chunk_off[0] != 0 || chunk_off[n_chunks] != n_tokens)
+        return set_error(MBPE_E_INVALID, "chunk_off must start at 0 and end at n_tokens");
+    int rc = use_device(comm->device);
+    if (rc) return rc;
+    // this rank's contiguous, token-balanced share of the unique chunks (same cut on every rank)
+    auto first_chunk = [&](int r) -> uint64_t {
+        if (r <= 0) return 0;
+        if (r >= comm->world) return n_chunks;
+        const uint64_t target = n_tokens / comm->world * r;
+        uint64_t lo = 0, hi = n_chunks;
+        while (lo < hi) {
+            uint64_t mid = (lo + hi) / 2;
+            if (chunk_off[mid] < target)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        return lo;
+    };
+    const uint64_t c0 = first_chunk(comm->rank), c1 = first_chunk(comm->rank + 1);
+    const uint64_t t0 = chunk_off[c0], t1 = chunk_off[c1], nl = t1 - t0, ncl = c1 - c0;
+    for (uint64_t c = c0; c < c1; c++)
+        if (chunk_off[c + 1] - chunk_off[c] >= 2)
+            for (uint64_t i = chunk_off[c]; i < chunk_off[c + 1]; i++)
+                if (tokens[i] >= 256) return set_error(MBPE_E_INVALID, "token >= 256 inside a multi-token chunk");
+    std::vector<uint64_t> loff(ncl + 1);
+    for (uint64_t c = c0; c <= c1; c++) loff[c - c0] = chunk_off[c] - t0;
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t *d_tokens = nullptr, *d_weight = nullptr;
+    uint64_t *d_off = nullptr;
+    Ctl *pinned = nullptr;
+    MB_CUDA(cudaMalloc(&d_tokens, std::max<uint64_t>(nl, 1) * 4));
+    MB_CUDA(cudaMalloc(&d_off, (ncl + 1) * 8));
+    MB_CUDA(cudaMemcpy(d_tokens, tokens + t0, nl * 4, cudaMemcpyHostToDevice));
+    MB_CUDA(cudaMemcpy(d_off, loff.data(), (ncl + 1) * 8, cudaMemcpyHostToDevice));
+    if (chunk_weight) {
+        MB_CUDA(cudaMalloc(&d_weight, std::max<uint64_t>(ncl, 1) * 4));
+        MB_CUDA(cudaMemcpy(d_weight, chunk_weight + c0, ncl * 4, cudaMemcpyHostToDevice));
+    }
+    MB_CUDA(cudaMallocHost(&pinned, sizeof(Ctl)));
+    cudaEvent_t e0, e1;
+    MB_CUDA(cudaEventCreate(&e0));
+    MB_CUDA(cudaEventCreate(&e1));
+    CudaBE be;
+    be.stream = st;
+    be.sms = sm_count(comm->device);
+    be.pinned = pinned;
+    be.nccl = comm->nccl;
+    be.comm_world = (uint32_t)comm->world;
+    be.comm_rank = (uint32_t)comm->rank;
+    TrainConfig cfg{vocab_size, mode, MBPE_ENGINE_STEPWISE, ~0u, env_u32("MBPE_CAND_WANT", 512), 0, 0};
+    TrainOutcome o;
+    *n_merges_out = 0;
+    MB_CUDA(cudaEventRecord(e0, st));
+    int drc;
+    {
+        TrainLoopSharded<CudaBE> loop(be);
+        drc = loop.run(d_tokens, d_off, d_weight, nl, ncl, t0, n_tokens, cfg, merges_out, counts_out, &o);
+    }
+    MB_CUDA(cudaEventRecord(e1, st));
+    MB_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaFree(d_tokens);
+    cudaFree(d_off);
+    cudaFree(d_weight);
+    cudaFree(be.d_all);
+    cudaFree(be.d_counts);
+    cudaFree(be.d_my_count);
+    cudaFreeHost(pinned);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (be.err != cudaSuccess) return cuda_fail(be.err, be.err_what, __FILE__, __LINE__);
+    if (drc) return set_error(MBPE_E_CUDA, "sharded train loop reached an unexpected state");
+    *n_merges_out = finish_merges(o, vocab_size, mode, merges_out, counts_out);
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->gpu_ms = ms;
+        stats->n_positions = nl;
+        stats->n_pairs = o.n_pairs;
+        stats->table_slots = o.table_slots;
+        stats->n_launches = be.launches();
+        stats->n_big_merges = o.n_big; // = number of per-merge exchanges
+        stats->n_rebuilds = o.n_rebuilds;
+    }
+    return MBPE_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------

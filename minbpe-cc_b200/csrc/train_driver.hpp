@@ -214,6 +214,167 @@ class TrainLoop {
     uint64_t n_rebuilds_ = 0, n_grows_ = 0;
 };
 
+// ---------------------------------------------------------------------------------------------------------
+// Sharded training: rank r of `world` owns a contiguous share of the unique chunks (local position
+// i = global position pos_base + i) and a full replica of the pair table with GLOBAL counts. One step:
+//   select (every rank, same answer)  ->  local occurrence walk + count deltas  ->  exchange of the deltas
+//   (backend: NCCL all-gather over NVLink)  ->  apply the other ranks' deltas  ->  local rewrite + segments.
+// Extra backend interface:
+//   uint32_t world(), rank();
+//   void exchange(const XRec *d_send, uint32_t n_send, const XRec **d_all, const uint32_t **d_counts, uint32_t *stride);
+// The table is sized once for the worst case (no growth: the ranks' step sequences must stay identical).
+// ---------------------------------------------------------------------------------------------------------
+template <class BE>
+class TrainLoopSharded {
+  public:
+    TrainLoopSharded(BE &be) : be_(be) { memset(&c_, 0, sizeof c_); }
+    ~TrainLoopSharded() { free_all(); }
+
+    int run(const uint32_t *d_tokens, const uint64_t *d_off, const uint32_t *d_weight, uint64_t n_tokens_local,
+            uint64_t n_chunks_local, uint64_t pos_base, uint64_t n_tokens_global, const TrainConfig &cfg,
+            uint32_t *h_merges, int32_t *h_counts, TrainOutcome *out) {
+        const uint32_t n_target = cfg.vocab_size - 256;
+        memset(out, 0, sizeof *out);
+        if (n_target == 0) return 0;
+        mode_ = cfg.mode;
+        c_.n_pos = (uint32_t)n_tokens_local;
+        c_.pos_base = (uint32_t)pos_base;
+        const uint64_t np = n_tokens_local ? n_tokens_local : 1, ng = n_tokens_global ? n_tokens_global : 1;
+        c_.node = (Node *)be_.alloc(np * sizeof(Node));
+        c_.arena_cap = (uint32_t)(3 * np + 16);
+        c_.occ = (uint32_t *)be_.alloc((uint64_t)c_.arena_cap * 4);
+        c_.hit = (uint32_t *)be_.alloc((np + 16) * 4);
+        c_.rec_slot = (uint32_t *)be_.alloc((np + 16) * 4);
+        c_.rec_pos = (uint32_t *)be_.alloc((np + 16) * 4);
+        c_.newp = (uint32_t *)be_.alloc((ng + 65536 + 16) * 4); // births of every rank land here
+        // sized by the GLOBAL corpus: the padded all-gather reads max-over-ranks records from every rank's buffer
+        c_.xrec_cap = (uint32_t)(2 * ng + 65536 + 64);
+        c_.xrec = (XRec *)be_.alloc((uint64_t)c_.xrec_cap * sizeof(XRec));
+        c_.ctl = (Ctl *)be_.alloc(sizeof(Ctl));
+        c_.merges_out = (uint32_t *)be_.alloc((uint64_t)n_target * 8);
+        c_.counts_out = (int32_t *)be_.alloc((uint64_t)n_target * 4);
+        // every pair ever: <= 65536 byte pairs + 2 per merged occurrence (< n_tokens_global in total)
+        const uint64_t max_pairs = 65536 + 2 * ng + 2 * np + 128;
+        const uint32_t cap = next_pow2_u32(max_pairs * MB_LOAD_DEN / MB_LOAD_NUM + 1);
+        c_.slot = (Slot *)be_.alloc((uint64_t)cap * sizeof(Slot));
+        c_.cap_mask = cap - 1;
+        c_.cand_cap = cap;
+        c_.cand = (uint32_t *)be_.alloc((uint64_t)c_.cand_cap * 4);
+        c_.fix = (uint32_t *)be_.alloc((uint64_t)c_.cand_cap * 4);
+        be_.par(PhClearSlots{c_.slot, cap}, cap);
+
+        Ctl h;
+        memset(&h, 0, sizeof h);
+        h.n_target = n_target;
+        h.mode = cfg.mode;
+        h.status = ST_NEED_REBUILD;
+        h.cmax = CMAX_NONE;
+        h.best_tie = ~0ull;
+        h.theta = 1;
+        h.big_limit = ~0u;
+        h.cand_limit = cfg.cand_limit ? cfg.cand_limit : 4096;
+        h.min_key_ever = ~0ull;
+        h.live_tokens = n_tokens_local;
+        be_.upload(c_.ctl, &h, sizeof h);
+
+        be_.par(PhInitNodes{c_, d_tokens, d_off, d_weight, n_chunks_local}, n_tokens_local);
+        be_.init_count(c_);
+        be_.par(PhExportAll{c_}, cap); // local histogram -> global histogram on every rank
+        if (exchange_and_apply()) return -1;
+        be_.one(PhAfterInitExchange{c_});
+        be_.par(PhInitAlloc{c_}, cap);
+        be_.par(PhInitFill{c_}, n_tokens_local);
+
+        for (;;) {
+            be_.download(&h, c_.ctl, sizeof h);
+            if (h.status == ST_DONE || h.status == ST_EXHAUSTED) break;
+            if (h.status == ST_NEED_REBUILD) {
+                rebuild(cfg, cap);
+            } else if (h.status == ST_RUN && !h.selected) {
+                if (select_grid(h.n_cand)) return -1;
+            } else if (h.status == ST_RUN) {
+                be_.par(PhHits{c_}, h.seg_len);
+                be_.par(PhExportBirths{c_}, 2ull * h.seg_len);
+                if (exchange_and_apply()) return -1;
+                be_.par(PhMutate{c_}, h.seg_len);
+                be_.par(PhSegAlloc{c_}, 4096);
+                be_.par(PhSegFill{c_}, 2ull * h.seg_len);
+                be_.one(PhFin{c_});
+                if (select_grid(h.n_cand)) return -1;
+                n_exchanges_++;
+            } else {
+                return -1; // ST_NEED_GROW / ST_BIG_MERGE cannot happen: fixed table, no resident CTA
+            }
+        }
+        out->n_merges = h.step;
+        out->final_status = h.status;
+        out->min_key_ever = h.min_key_ever;
+        out->n_pairs = h.n_pairs;
+        out->table_slots = cap;
+        out->n_rebuilds = n_rebuilds_;
+        out->n_big = n_exchanges_;
+        out->rescan_bytes = h.rescan_bytes;
+        if (h.step) {
+            be_.download(h_merges, c_.merges_out, (uint64_t)h.step * 8);
+            if (h_counts) be_.download(h_counts, c_.counts_out, (uint64_t)h.step * 4);
+        }
+        free_all();
+        return 0;
+    }
+
+  private:
+    int exchange_and_apply() {
+        Ctl h;
+        be_.download(&h, c_.ctl, sizeof h); // n_xrec of this rank
+        if (h.n_xrec > c_.xrec_cap) return -1;
+        const XRec *all = nullptr;
+        const uint32_t *counts = nullptr;
+        uint32_t stride = 0;
+        be_.exchange(c_.xrec, h.n_xrec, &all, &counts, &stride);
+        be_.par(PhApplyForeign{c_, all, counts, stride, be_.world(), be_.rank()}, (uint64_t)stride);
+        return 0;
+    }
+    int select_grid(uint32_t n_cand) {
+        be_.par(PhSelMax{c_}, n_cand);
+        be_.par(PhSelTie{c_}, n_cand);
+        be_.one(PhSelCheck{c_});
+        if (mode_ == 0) { // FIRST: tied pairs whose first occurrence died need the minimum over all ranks
+            Ctl h;
+            be_.download(&h, c_.ctl, sizeof h);
+            if (h.status == ST_RUN && !h.selected && h.n_fix) { // same replicas -> same decision on every rank
+                be_.par(PhSelFixScan{c_}, n_cand);
+                be_.par(PhExportFix{c_}, h.n_fix);
+                if (exchange_and_apply()) return -1;
+                be_.one(PhResetXrec{c_});
+                be_.par(PhSelFixTie{c_}, n_cand);
+            }
+        }
+        be_.par(PhSelPick{c_}, n_cand);
+        be_.one(PhSelCommit{c_, 0});
+        return 0;
+    }
+    void rebuild(const TrainConfig &cfg, uint64_t cap) {
+        be_.one(PhRebuildReset{c_});
+        be_.par(PhRebuildHist{c_}, cap);
+        be_.one(PhRebuildTheta{c_, cfg.cand_want});
+        be_.par(PhRebuildCollect{c_}, cap);
+        be_.one(PhSelReset{c_});
+        n_rebuilds_++;
+    }
+    void free_all() {
+        void *ps[] = {c_.node, c_.occ, c_.hit, c_.rec_slot, c_.rec_pos, c_.newp, c_.ctl, c_.merges_out,
+                      c_.counts_out, c_.slot, c_.cand, c_.fix, c_.xrec};
+        for (void *p : ps)
+            if (p) be_.release(p);
+        memset(&c_, 0, sizeof c_);
+    }
+
+    BE &be_;
+    Ctx c_;
+    uint64_t n_rebuilds_ = 0, n_exchanges_ = 0;
+    int mode_ = 1;
+};
+
 // Host epilogue shared by every caller: turn the device outcome into the reference's observable merge list.
 //  FIRST:   stop where the table ran empty (Tokenizer.h:586-588).
 //  LEXICAL: entries are never erased, so once the best count is 0 the smallest pair ever inserted is

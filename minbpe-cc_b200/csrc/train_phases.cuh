@@ -87,6 +87,14 @@ struct Slot {
 };
 static_assert(sizeof(Slot) == 32, "Slot is one 32-byte sector");
 
+// one count delta exchanged between ranks: -(w) for an occurrence that died, +(local count) for a pair born here
+struct XRec {
+    uint64_t key;
+    int32_t delta;
+    uint32_t pos; // global position: first occurrence (births) / the occurrence that died (deaths)
+};
+static_assert(sizeof(XRec) == 16, "exchange record");
+
 struct Ctl {
     // loop state
     uint32_t step;     // merges recorded so far
@@ -104,6 +112,7 @@ struct Ctl {
     uint32_t n_live; // candidates still >= theta, counted by sel_max
     // per-step lists
     uint32_t n_hit, n_rec, n_newp;
+    uint32_t n_xrec, n_newp_own; // sharded: records to send; newp entries created by this rank's own occurrences
     uint32_t n_cand;
     uint32_t selected; // 1 between sel_commit and fin: (a, b, seg...) of the current step are valid
     // table / arena
@@ -147,6 +156,10 @@ struct Ctx {
     Ctl *ctl;
     uint32_t *merges_out; // device copy, 2 * n_target
     int32_t *counts_out;
+    // sharded training (one rank = one GPU = a contiguous share of the unique chunks):
+    XRec *xrec;        // this step's count deltas for the other ranks (nullptr = single GPU)
+    uint32_t xrec_cap;
+    uint32_t pos_base; // global position of local position 0 (first-occurrence keys are global positions)
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -382,16 +395,25 @@ MB_HD uint32_t upsert_after_claim(const Ctx &c, uint64_t key, uint32_t home, uin
 #define MB_L(ptr) ctl_ld<S>(ptr) /* step lists: hit, rec_*, newp, cand, fix */
 
 // -(p,q) x w for the occurrence whose first token sits at position pairpos
+MB_HD void pair_dec_at(const Ctx &c, int32_t mode, uint32_t s, uint32_t w, uint32_t pairpos);
 MB_HD void pair_dec(const Ctx &c, int32_t mode, uint32_t p, uint32_t q, uint32_t w, uint32_t pairpos) {
-    uint32_t s = slot_find(c, pair_key(p, q));
-    if (s == NIL) return; // reference: decrement only if present (Tokenizer.h:250-256); always present
-    a_add(&c.slot[s].cnt, -(int32_t)w);
-    if (mode == 0 && ld_l2(&c.slot[s].first) == pairpos) c.slot[s].first = NO_FIRST;
+    // reference: decrement only if present (Tokenizer.h:250-256); with exact counts it always is
+    pair_dec_at(c, mode, slot_find(c, pair_key(p, q)), w, pairpos);
 }
 MB_HD void pair_dec_at(const Ctx &c, int32_t mode, uint32_t s, uint32_t w, uint32_t pairpos) {
     if (s == NIL) return;
     a_add(&c.slot[s].cnt, -(int32_t)w);
-    if (mode == 0 && ld_l2(&c.slot[s].first) == pairpos) c.slot[s].first = NO_FIRST;
+    if (mode == 0 && ld_l2(&c.slot[s].first) == c.pos_base + pairpos) c.slot[s].first = NO_FIRST;
+    if (c.xrec) { // the other ranks hold the same pair with the same global count: tell them
+        uint32_t r = claim_one(&c.ctl->n_xrec);
+        if (r < c.xrec_cap) {
+            XRec x;
+            x.key = ld_l2(&c.slot[s].key);
+            x.delta = -(int32_t)w;
+            x.pos = c.pos_base + pairpos;
+            c.xrec[r] = x;
+        }
+    }
 }
 MB_HD void pair_inc_at(const Ctx &c, int32_t mode, uint32_t s, bool created, uint64_t key, uint32_t w, uint32_t pairpos);
 // +(p,q) x w for a new occurrence at pairpos; q or p is this step's new id, so the pair is born in this step
@@ -411,7 +433,7 @@ MB_HD void pair_inc_at(const Ctx &c, int32_t mode, uint32_t s, bool created, uin
     }
     // cnt (low word) += w and len (high word) += 1 in one 64-bit atomic: both only grow during the birth step
     a_add(reinterpret_cast<uint64_t *>(&c.slot[s].cnt), ((uint64_t)1 << 32) | (uint64_t)w);
-    if (mode == 0) a_min(&c.slot[s].first, pairpos);
+    if (mode == 0) a_min(&c.slot[s].first, c.pos_base + pairpos);
     uint32_t r = claim_one(&c.ctl->n_rec);
     c.rec_slot[r] = s;
     c.rec_pos[r] = pairpos;
@@ -487,7 +509,7 @@ MB_HD void fix_scan_range(const Ctx &c, uint32_t s, uint32_t k0, uint32_t stride
         if (ld_l2(&c.node[n0.nxt].tok) != q) continue;
         best = pos;
     }
-    if (best != NO_FIRST) a_min(&c.slot[s].first, best);
+    if (best != NO_FIRST) a_min(&c.slot[s].first, c.pos_base + best);
 }
 constexpr uint32_t FIX_SOLO_LEN = 128;
 template <bool S = false>
@@ -721,6 +743,8 @@ MB_HD void phase_fin(const Ctx &c) {
     g->n_hit = 0;
     g->n_rec = 0;
     g->n_newp = 0;
+    g->n_xrec = 0;
+    g->n_newp_own = 0;
     g->cmax = CMAX_NONE;
     g->best_tie = ~0ull;
     g->n_fix = 0;
@@ -880,7 +904,7 @@ MB_HD void phase_init_count(const Ctx &c, uint32_t tid, uint32_t nth) {
     for (uint32_t i = tid; i < c.n_pos; i += nth) {
         Node n = c.node[i];
         if (n.nxt == NIL) continue;
-        count_one(c, pair_key(n.tok, c.node[n.nxt].tok), n.wt, 1u, i);
+        count_one(c, pair_key(n.tok, c.node[n.nxt].tok), n.wt, 1u, c.pos_base + i);
     }
 }
 MB_HD void phase_init_alloc(const Ctx &c, uint32_t tid, uint32_t nth) {
@@ -900,6 +924,97 @@ MB_HD void phase_init_fill(const Ctx &c, uint32_t tid, uint32_t nth) {
     }
 }
 
+} // namespace mbpe
+
+// ---------------------------------------------------------------------------------------------------------
+// sharded training: every rank keeps the WHOLE pair table with GLOBAL counts (so every rank selects the same
+// pair with no broadcast) and only its own share of the corpus. After the local occurrence walk each rank
+// sends its count deltas; applying everybody else's deltas makes the replicas equal again.
+// ---------------------------------------------------------------------------------------------------------
+// births: one record per pair created by this rank's occurrences in this step, with its local count so far
+namespace mbpe {
+MB_HD void phase_export_births(const Ctx &c, uint32_t tid, uint32_t nth) {
+    Ctl *g = c.ctl;
+    const uint32_t n = ld_l2(&g->n_newp);
+    for (uint32_t i = tid; i < n; i += nth) {
+        const uint32_t s = ld_l2(&c.newp[i]);
+        uint32_t r = a_add(&g->n_xrec, 1u);
+        if (r < c.xrec_cap) {
+            XRec x;
+            x.key = ld_l2(&c.slot[s].key);
+            x.delta = ld_l2(&c.slot[s].cnt);
+            x.pos = ld_l2(&c.slot[s].first);
+            c.xrec[r] = x;
+        }
+    }
+    if (tid == 0) g->n_newp_own = n;
+}
+// FIRST mode: after the local sel_fix_scan every rank knows ITS first live occurrence of each tied pair; the
+// global first is the minimum over ranks (positions are global)
+MB_HD void phase_export_fix(const Ctx &c, uint32_t tid, uint32_t nth) {
+    Ctl *g = c.ctl;
+    const uint32_t n = ld_l2(&g->n_fix);
+    for (uint32_t i = tid; i < n; i += nth) {
+        const uint32_t s = ld_l2(&c.fix[i]);
+        XRec x;
+        x.key = ld_l2(&c.slot[s].key);
+        x.delta = 0;
+        x.pos = ld_l2(&c.slot[s].first);
+        c.xrec[i] = x;
+    }
+    if (tid == 0) g->n_xrec = n;
+}
+// initial histogram: every occupied slot is a birth
+MB_HD void phase_export_all(const Ctx &c, uint32_t tid, uint32_t nth) {
+    Ctl *g = c.ctl;
+    const uint32_t cap = c.cap_mask + 1;
+    for (uint32_t s = tid; s < cap; s += nth) {
+        const uint64_t key = c.slot[s].key;
+        if (key == EMPTY_KEY) continue;
+        uint32_t r = a_add(&g->n_xrec, 1u);
+        if (r < c.xrec_cap) {
+            XRec x;
+            x.key = key;
+            x.delta = c.slot[s].cnt;
+            x.pos = c.slot[s].first;
+            c.xrec[r] = x;
+        }
+    }
+}
+// one thread, after the initial exchange: slots created by foreign records count as pairs; lists start empty
+MB_HD void phase_after_init_exchange(const Ctx &c) {
+    Ctl *g = c.ctl;
+    g->n_pairs = ld_l2(&g->n_pairs) + ld_l2(&g->n_newp);
+    g->n_newp = 0;
+    g->n_xrec = 0;
+    g->n_newp_own = 0;
+}
+// all[r * stride .. + counts[r]) = records of rank r; the own block is skipped
+MB_HD void phase_apply_foreign(const Ctx &c, const XRec *all, const uint32_t *counts, uint32_t stride, uint32_t world,
+                               uint32_t my_rank, uint32_t tid, uint32_t nth) {
+    Ctl *g = c.ctl;
+    const int32_t mode = ld_l2(&g->mode);
+    for (uint32_t r = 0; r < world; r++) {
+        if (r == my_rank) continue;
+        const uint32_t n = counts[r];
+        for (uint32_t i = tid; i < n; i += nth) {
+            const XRec x = all[(uint64_t)r * stride + i];
+            bool created;
+            const uint32_t s = slot_upsert(c, x.key, &created);
+            if (created) {
+                c.newp[a_add(&g->n_newp, 1u)] = s; // gets an (empty) segment and a candidate check like local births
+                a_min(&g->min_key_ever, x.key);
+            }
+            if (x.delta) a_add(&c.slot[s].cnt, x.delta);
+            if (mode == 0) {
+                if (x.delta >= 0) // birth, or (delta == 0) a rank's recomputed first live occurrence
+                    a_min(&c.slot[s].first, x.pos);
+                else if (ld_l2(&c.slot[s].first) == x.pos)
+                    c.slot[s].first = NO_FIRST;
+            }
+        }
+    }
+}
 } // namespace mbpe
 
 // ---------------------------------------------------------------------------------------------------------
@@ -950,6 +1065,35 @@ struct PhRebuildTheta {
     Ctx c;
     uint32_t want;
     MB_HD void operator()() const { phase_rebuild_theta<false>(c, want); }
+};
+struct PhExportBirths {
+    Ctx c;
+    MB_HD void operator()(uint32_t tid, uint32_t nth) const { phase_export_births(c, tid, nth); }
+};
+struct PhExportFix {
+    Ctx c;
+    MB_HD void operator()(uint32_t tid, uint32_t nth) const { phase_export_fix(c, tid, nth); }
+};
+struct PhResetXrec {
+    Ctx c;
+    MB_HD void operator()() const { c.ctl->n_xrec = 0; }
+};
+struct PhExportAll {
+    Ctx c;
+    MB_HD void operator()(uint32_t tid, uint32_t nth) const { phase_export_all(c, tid, nth); }
+};
+struct PhAfterInitExchange {
+    Ctx c;
+    MB_HD void operator()() const { phase_after_init_exchange(c); }
+};
+struct PhApplyForeign {
+    Ctx c;
+    const XRec *all;
+    const uint32_t *counts;
+    uint32_t stride, world, my_rank;
+    MB_HD void operator()(uint32_t tid, uint32_t nth) const {
+        phase_apply_foreign(c, all, counts, stride, world, my_rank, tid, nth);
+    }
 };
 struct PhRehash {
     Ctx c;

@@ -20,7 +20,7 @@ EMU_LIB = os.path.join(ROOT, "tests", "emu", "libtrain_emu.so")
 def emu():
     deps = [EMU_SRC] + [os.path.join(ROOT, "minbpe-cc_b200", "csrc", f) for f in ("train_phases.cuh", "train_driver.hpp")]
     if not os.path.exists(EMU_LIB) or any(os.path.getmtime(d) > os.path.getmtime(EMU_LIB) for d in deps):
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-x", "c++", "-o", EMU_LIB, EMU_SRC])
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-pthread", "-x", "c++", "-o", EMU_LIB, EMU_SRC])
     L = C.CDLL(EMU_LIB)
 
     def run(t, o, w, vocab, mode, engine=0, nth=64, order=0, big=1 << 30, want=1024, init=0):
@@ -100,3 +100,36 @@ def test_empty_and_pairless_inputs(emu):
     t = np.asarray([97, 98, 99], np.uint32)  # three single-token chunks: no pairs at all
     m, c, _ = emu(t, np.asarray([0, 1, 2, 3], np.uint64), np.ones(3, np.uint32), 300, "first")
     assert len(m) == 0
+
+
+# ---- sharded training: `world` emulated ranks, one host thread each -------------------------
+def _emu_sharded(t, o, w, vocab, mode, world, nth=16, order=2, want=8):
+    L = C.CDLL(EMU_LIB)
+    n = max(vocab - 256, 1)
+    m = np.zeros((n, 2), np.uint32)
+    c = np.zeros(n, np.int32)
+    nm = C.c_uint32()
+    P = lambda a, ty: a.ctypes.data_as(C.POINTER(ty))
+    rc = L.emu_train_sharded(P(t, C.c_uint32), C.c_uint64(len(t)), P(o, C.c_uint64), C.c_uint64(len(o) - 1),
+                             P(w, C.c_uint32), C.c_uint32(vocab), {"first": 0, "lexical": 1}[mode], world, nth, order,
+                             C.c_uint32(want), P(m, C.c_uint32), P(c, C.c_int32), C.byref(nm))
+    return rc, m[:nm.value], c[:nm.value]
+
+
+@pytest.mark.parametrize("name", ["ts512_gpt4_first", "ts512_gpt4_lexical", "sample512_gpt4_first",
+                                  "sample512_gpt4_lexical", "str_runs_c_gpt4_first", "str_runs_c_basic_lexical",
+                                  "str_exhaust_basic_first", "str_exhaust_basic_lexical", "str_unicode_gpt4_first",
+                                  "ts400_basic_first"])
+def test_sharded_ranks_agree_and_match_reference(emu, oracle, manifest, name):
+    """Every rank keeps a replica of the pair table with global counts and its share of the chunks; after the
+    per-step exchange of count deltas all ranks must pick the same merges -- and they must be the reference's.
+    rc 7 = ranks disagreed. encoder 'basic' = one chunk: one rank owns everything, the others own nothing."""
+    e = manifest["train"][name]
+    _, _, gm = oracle.read_model(os.path.join(GOLDEN, "models", name + ".model"))
+    text = golden_data(e["input"])
+    t, o, w = oracle.flatten(oracle.chunks_of(text, e["encoder"]), True)
+    _, oc = oracle.train(t, o, w, e["vocab_size"], e["mode"])
+    for world in (2, 3):
+        rc, m, c = _emu_sharded(t, o, w, e["vocab_size"], e["mode"], world)
+        assert rc == 0, (name, world, rc)
+        assert m.shape == gm.shape and (m == gm).all() and (c == oc).all(), (name, world)
