@@ -11,8 +11,9 @@ PyTorch is used for plumbing only: torch.distributed (NCCL) barrier/max across r
 encode batch, streams and events. All compute goes through the C ABI of libminbpe_b200.so.
 
 Multi-GPU (N > 1, launched by torchrun): encode shards chunks across ranks with no communication (each rank
-encodes its own batch: weak scaling). The sharded-pair-count train exchange is not built yet, so train runs as
-independent replicas, one corpus per rank, and says so in the JSON line.
+encodes its own batch: weak scaling). Train: `value` counts N independent replicas of the merge loop (weak scaling);
+the sharded trainer (chunks sharded, per-merge NCCL exchange of pair-count deltas) is run once and reported
+under train.sharded -- it is exact but one collective per merge makes it slower than a single GPU.
 """
 import argparse
 import hashlib
@@ -255,7 +256,7 @@ def main():
 
     # ---------------- host prep (outside every timed region): corpus, regex split, dedup -----------------
     t0 = time.time()
-    text = pkg.synth_corpus(SEED_TRAIN + rank, a.corpus_mib << 20)  # one corpus per rank (replicas when N > 1)
+    text = pkg.synth_corpus(SEED_TRAIN, a.corpus_mib << 20)  # N > 1: every rank holds the same corpus
     t_gen = time.time() - t0
     tb = text.tobytes()
     t0 = time.time()
@@ -329,8 +330,8 @@ def main():
         "train": {"merges": int(n_done), "merges_sha256": model_sha, "gpu_s_per_run": ms_per_step / 1e3,
                   "wall_s_text_to_model": e2e_s, "host_prep_s": {"generate": t_gen, "split": t_split, "dedup": t_dedup},
                   "n_chunks": int(n_chunks), "n_unique_chunks": int(len(w)), "stats": stats,
-                  "multi_gpu": None if world == 1 else "independent replicas, one corpus per rank (sharded pair-count "
-                                                       "exchange not built yet)"},
+                  "multi_gpu": None if world == 1 else "value = N independent replicas of the merge loop (weak scaling); the "
+                                                       "sharded trainer is reported under train.sharded"},
     }
     # roofline of the merge loop: SURVEY 8(d) full-rescan algorithmic volume / device time
     ach = stats["rescan_bytes"] / 1e9 / (ms_per_step / 1e3)
@@ -340,6 +341,30 @@ def main():
                         "note": "algorithmic bytes = sum over merges of 12*T_m + 16*P_m, what a full rescan per merge "
                                 "would move (SURVEY 8(d)); the incremental kernels move far fewer real bytes, so the "
                                 "fraction can exceed 1 and the loop is latency-bound, not HBM-bound"}
+
+    if world > 1:
+        # the north star's multi-GPU train: unique chunks sharded over the ranks, per-merge exchange of pair-count
+        # deltas over NCCL/NVLink. It is exact but latency-bound (one collective per merge), so it is reported beside
+        # the replica number, not instead of it.
+        def bcast(ident):
+            t = torch.from_numpy(ident.copy()).to(dev)
+            dist.broadcast(t, 0)
+            return t.cpu().numpy()
+        comm = pkg.Comm(rank, world, local_rank, bcast)
+        barrier()
+        t0 = time.time()
+        sm, sc, sst = comm.train(tok, off, w, a.vocab, a.mode, stream)
+        torch.cuda.synchronize()
+        barrier()
+        sh_s = max_over_ranks(time.time() - t0)
+        same = torch.tensor([int(sm.shape == merges.shape and bool((sm == merges).all()))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        line["train"]["sharded"] = {"merges_per_sec": len(sm) / sh_s, "wall_s": sh_s, "gpu_ms": sst["gpu_ms"],
+                                    "exchanges": sst["n_big_merges"], "launches": sst["n_launches"],
+                                    "equals_single_gpu_merges_on_every_rank": bool(same.item()),
+                                    "what": "mbpe_train_sharded: replicated pair table, chunks sharded over ranks, "
+                                            "one NCCL all-gather of count deltas per merge"}
+        comm.close()
 
     if not a.no_check and rank == 0:
         # parity at the FULL workload size: the CPU oracle (indexed restatement, validated against the compiled
