@@ -208,6 +208,7 @@ def main():
     ap.add_argument("--mode", default="lexical", choices=["first", "lexical"])
     ap.add_argument("--engine", default="persistent", choices=["persistent", "stepwise"])
     ap.add_argument("--encode-mib", type=int, default=1024)
+    ap.add_argument("--encode-batches", type=int, default=1, help="resident batches of --encode-mib per step")
     ap.add_argument("--ref-sample-mib", type=int, default=4)
     ap.add_argument("--ref-merges", type=int, default=128)
     ap.add_argument("--ref-encode-mib", type=int, default=64)
@@ -378,57 +379,80 @@ def main():
 
     # ---------------- encode ----------------------------------------------------------------------------
     if not a.skip_encode:
-        etext = pkg.synth_corpus(SEED_ENCODE + rank, a.encode_mib << 20)
-        etb = etext.tobytes()
-        t0 = time.time()
-        es, ee = pkg.split(pkg.patterns()["gpt4"], etb)
-        t_esplit = time.time() - t0
-        eoff64 = np.concatenate([es, ee[-1:]]).astype(np.uint64)
-        n_echunks = len(es)
+        # B distinct resident batches of encode_mib each (a device batch is < 4 GiB: u32 boundaries); one timed step =
+        # one pass over all of them. --encode-batches 10 --encode-mib 1024 is BASELINE config 4 (10 GiB).
         enc = pkg.Encoder(merges, device=local_rank)
-        d_bytes = torch.from_numpy(etext).to(dev)
-        d_off = torch.from_numpy(eoff64.astype(np.uint32).view(np.int32)).to(dev)
-        d_out = torch.empty(len(etext), dtype=torch.int32, device=dev)
+        batches, t_esplit, n_echunks_total, n_bytes_total = [], 0.0, 0, 0
+        for b in range(a.encode_batches):
+            etext = pkg.synth_corpus(SEED_ENCODE + 1000 * rank + b, a.encode_mib << 20)
+            etb = etext.tobytes()
+            t0 = time.time()
+            es, ee = pkg.split(pkg.patterns()["gpt4"], etb)
+            t_esplit += time.time() - t0
+            eoff64 = np.concatenate([es, ee[-1:]]).astype(np.uint64)
+            batches.append({"n_chunks": len(es), "n_bytes": len(etext),
+                            "d_bytes": torch.from_numpy(etext).to(dev),
+                            "d_off": torch.from_numpy(eoff64.astype(np.uint32).view(np.int32)).to(dev)})
+            n_echunks_total += len(es)
+            n_bytes_total += len(etext)
+            if b + 1 < a.encode_batches:
+                del etext, etb, es, ee, eoff64
+        n_echunks = batches[-1]["n_chunks"]
+        d_out = torch.empty(a.encode_mib << 20, dtype=torch.int32, device=dev)
         d_n = torch.zeros(1, dtype=torch.int64, device=dev)
-        enc.reserve(len(etext), n_echunks)
+        enc.reserve(a.encode_mib << 20, max(bt["n_chunks"] for bt in batches))
         eev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * (a.warmup + a.steps))]
+        n_ids_total = 0
         for i in range(a.warmup + a.steps):
             if i == a.warmup:
                 barrier()
                 ew0 = time.time()
             eev[2 * i].record()
-            enc.encode_device(d_bytes.data_ptr(), len(etext), d_off.data_ptr(), n_echunks, d_out.data_ptr(), len(etext),
-                              d_n.data_ptr(), stream)
+            for bt in batches:
+                enc.encode_device(bt["d_bytes"].data_ptr(), bt["n_bytes"], bt["d_off"].data_ptr(), bt["n_chunks"],
+                                  d_out.data_ptr(), a.encode_mib << 20, d_n.data_ptr(), stream)
             eev[2 * i + 1].record()
         barrier()
         if clocks:
             clocks.mark(ew0, time.time())
         etimes = [eev[2 * i].elapsed_time(eev[2 * i + 1]) for i in range(a.warmup, a.warmup + a.steps)]
         ems = max_over_ranks(sum(etimes) / len(etimes))
-        n_ids = int(d_n.item())
-        b_enc = len(etext) + 4 * n_echunks + 4 * n_ids
+        n_ids = int(d_n.item())  # ids of the last batch (the one still in d_out)
+        n_ids_total = n_ids
+        for bt in batches[:-1]:  # untimed: id counts of the other batches for the algorithmic-byte figure
+            enc.encode_device(bt["d_bytes"].data_ptr(), bt["n_bytes"], bt["d_off"].data_ptr(), bt["n_chunks"],
+                              d_out.data_ptr(), a.encode_mib << 20, d_n.data_ptr(), stream)
+            n_ids_total += int(d_n.item())
+        if len(batches) > 1:  # leave the last batch's ids in d_out for the checks below
+            bt = batches[-1]
+            enc.encode_device(bt["d_bytes"].data_ptr(), bt["n_bytes"], bt["d_off"].data_ptr(), bt["n_chunks"],
+                              d_out.data_ptr(), a.encode_mib << 20, d_n.data_ptr(), stream)
+            torch.cuda.synchronize()
+        b_enc = n_bytes_total + 4 * n_echunks_total + 4 * n_ids_total
+        etext_len = n_bytes_total
         # e2e: host buffers through mbpe_encode (H2D + kernels + D2H)
         t0 = time.time()
-        ids = enc.encode(etb, eoff64)
+        ids = enc.encode(etb, eoff64)  # the last batch
         e2e_enc_s = max_over_ranks(time.time() - t0)
         ids_dev = d_out[:n_ids].cpu().numpy().view(np.uint32)
         assert np.array_equal(ids, ids_dev)
         # size-independent property at full size: decode(encode(x)) == x
         roundtrip = enc.decode(ids) == etb
         line["encode"] = {
-            "metric": "bpe_encode_mb_per_sec", "value": world * len(etext) / 1e6 / (ems / 1e3), "unit": "MB/s",
-            "ms_per_step": ems, "bytes_per_step": len(etext), "n_chunks": int(n_echunks), "n_tokens": n_ids,
-            "workload": f"encode {a.encode_mib} MiB synthetic text per rank (seed 0x{SEED_ENCODE:X}+rank) with the "
-                        f"{a.vocab}-vocab model just trained; inputs and output resident in HBM, batch >> L2",
+            "metric": "bpe_encode_mb_per_sec", "value": world * etext_len / 1e6 / (ems / 1e3), "unit": "MB/s",
+            "ms_per_step": ems, "bytes_per_step": etext_len, "n_chunks": int(n_echunks_total), "n_tokens": int(n_ids_total),
+            "workload": f"encode {a.encode_batches} x {a.encode_mib} MiB synthetic text per rank (seeds 0x{SEED_ENCODE:X}+1000*rank+b) "
+                        f"with the {a.vocab}-vocab model just trained; inputs and output resident in HBM, every batch >> L2",
             "roofline": {"bound": "hbm", "achieved": b_enc / 1e9 / (ems / 1e3), "peak": peak, "unit": "GB/s",
                          "frac": b_enc / 1e9 / (ems / 1e3) / peak, "traffic": None, "peak_source": peak_src,
                          "kernel": "k_encode_tiles", "algorithmic_bytes_per_step": int(b_enc)},
             "e2e": {"value": world * len(etext) / 1e6 / e2e_enc_s, "unit": "MB/s", "h2d_bytes_per_step": int(len(etext) + 4 * (n_echunks + 1)),
+                    "bytes": len(etext),
                     "d2h_bytes_per_step": int(4 * n_ids), "what": "mbpe_encode(host bytes + host chunk offsets)"},
             "host_split_s": t_esplit, "roundtrip_ok": bool(roundtrip), "ids_sha256": hashlib.sha256(ids.tobytes()).hexdigest(),
-            "gpu_launches": 3 * a.steps,
+            "gpu_launches": 3 * a.steps * a.encode_batches * (1 + (n_echunks >> 22)),
         }
-        line["gpu_launches"] += 3 * a.steps
+        line["gpu_launches"] += line["encode"]["gpu_launches"]
 
     # ---------------- CPU baseline (rank 0, N == 1 only) -------------------------------------------------
     if rank == 0 and world == 1 and not a.skip_cpu_baseline:
