@@ -563,8 +563,20 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
                     if (n > 2) a.out[dst + 2] = ids[j][2];
                 } else if (state[j] == 3) {
                     const CacheSlot &cs = a.cache.slots[ids[j][0]];
-                    const uint32_t *src = n <= CACHE_INLINE_IDS ? cs.v : a.cache.arena + __ldg(&cs.v[0]);
-                    for (uint32_t i = 0; i < n; i++) a.out[dst + i] = __ldg(&src[i]);
+                    if (n <= CACHE_INLINE_IDS) { // the value sector again: two vector loads, predicated stores, no loop
+                        const uint4 lo4 = __ldg(reinterpret_cast<const uint4 *>(&cs.n));      // n, v0, v1, v2
+                        const uint4 hi4 = __ldg(reinterpret_cast<const uint4 *>(&cs.v[3]));   // v3 .. v6
+                        a.out[dst] = lo4.y;
+                        a.out[dst + 1] = lo4.z;
+                        a.out[dst + 2] = lo4.w;
+                        a.out[dst + 3] = hi4.x;
+                        if (n > 4) a.out[dst + 4] = hi4.y;
+                        if (n > 5) a.out[dst + 5] = hi4.z;
+                        if (n > 6) a.out[dst + 6] = hi4.w;
+                    } else {
+                        const uint32_t *src = a.cache.arena + __ldg(&cs.v[0]);
+                        for (uint32_t i = 0; i < n; i++) a.out[dst + i] = __ldg(&src[i]);
+                    }
                 } else if (state[j] == 1) {
                     const uint32_t start = sm.meta[k] & 0xFFFFF;
                     if (start != META_NONE) {
