@@ -725,6 +725,7 @@ struct mbpe_encoder {
     uint32_t *d_cache_ctr = nullptr; // [0] log count, [1] used slots, [2] arena cursor
     uint64_t sub_batch_chunks = 1u << 22;
     int cfg = 0; // kernel shape, see enc_configs
+    size_t l2_window_max = 0, l2_persist_bytes = 0;
 };
 
 namespace mbpe {
@@ -807,6 +808,18 @@ extern "C" int mbpe_encoder_create(const uint32_t *merges, uint32_t n_merges, in
     }
     const char *sb_env = getenv("MBPE_ENCODE_SUBBATCH");
     if (sb_env && *sb_env) e->sub_batch_chunks = std::max<uint64_t>(4096, strtoull(sb_env, nullptr, 10)) / 4096 * 4096;
+    if (!getenv("MBPE_NO_L2_PERSIST")) {
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
+        if (max_persist > 0 && max_window > 0 &&
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) == cudaSuccess) {
+            e->l2_window_max = (size_t)max_window;
+            e->l2_persist_bytes = (size_t)max_persist;
+        } else {
+            cudaGetLastError();
+        }
+    }
     const char *cfg_env = getenv("MBPE_ENC_CFG");
     e->cfg = cfg_env && *cfg_env ? std::min(std::max(atoi(cfg_env), 0), N_ENC_CONFIGS - 1) : 0;
     for (int i = 0; i < N_ENC_CONFIGS; i++)
@@ -955,7 +968,26 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
             e->launches++;
         }
         unsigned g2 = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)e->sms * kc.ctas);
-        kc.kernel<<<g2, kc.threads, kc.smem, st>>>(a);
+        cudaLaunchConfig_t lc{};
+        lc.gridDim = dim3(g2);
+        lc.blockDim = dim3(kc.threads);
+        lc.dynamicSmemBytes = kc.smem;
+        lc.stream = st;
+        cudaLaunchAttribute lattr[1];
+        lc.attrs = lattr;
+        lc.numAttrs = 0;
+        if (a.cache.slots && e->l2_window_max) {
+            // the text, boundaries and ids stream through L2 once; the randomly probed chunk cache is what must stay
+            const size_t bytes = std::min((size_t)e->cache_slots * sizeof(CacheSlot), e->l2_window_max);
+            lattr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+            lattr[0].val.accessPolicyWindow.base_ptr = e->d_cache;
+            lattr[0].val.accessPolicyWindow.num_bytes = bytes;
+            lattr[0].val.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)e->l2_persist_bytes / (double)bytes);
+            lattr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            lattr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            lc.numAttrs = 1;
+        }
+        MB_CUDA(cudaLaunchKernelEx(&lc, kc.kernel, a));
         e->launches++;
         if (a.cache.slots) {
             k_cache_insert<<<e->sms * 2, 256, 0, st>>>(a.cache);
