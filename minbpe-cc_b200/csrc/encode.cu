@@ -269,6 +269,7 @@ __global__ void k_cache_reset_log(ChunkCache cc) { *cc.log_count = 0; }
 constexpr int ET_CAP = 8192;         // staged text bytes per tile (avg chunk 5 B -> 5 KB); bigger tiles read HBM directly
 constexpr uint32_t ET_MISS_OUT = 2048; // ids of scanned chunks parked in shared memory until the tile offset is known
 constexpr uint32_t META_NONE = 0xFFFFF;
+constexpr uint64_t ENC_MAX_SUBBATCH = 1ull << 26; // chunks per launch at most (tile ids and look-back words are 32-bit safe)
 constexpr uint32_t ET_WARP_SCAN_MAX = 48; // up to this many misses per tile are scanned one warp per chunk
 
 template <int THREADS, int ET_CPT>
@@ -723,7 +724,8 @@ struct mbpe_encoder {
     uint32_t *d_cache_arena = nullptr;
     uint32_t cache_slots = 0, cache_log_cap = 0, cache_arena_cap = 0;
     uint32_t *d_cache_ctr = nullptr; // [0] log count, [1] used slots, [2] arena cursor
-    uint64_t sub_batch_chunks = 1u << 22;
+    uint64_t sub_batch_chunks = 0; // fixed sub-batch size (MBPE_ENCODE_SUBBATCH), 0 = geometric schedule
+    uint64_t chunks_seen = 0;      // chunks encoded so far with this handle: how warm the cache is
     int cfg = 0; // kernel shape, see enc_configs
     size_t l2_window_max = 0, l2_persist_bytes = 0;
 };
@@ -736,7 +738,8 @@ struct EncConfig {
 };
 #define ENC_CFG(T, C, M) EncConfig{T, C, M, k_encode_tiles<T, C, M>, sizeof(EncSmemT<T, C>)}
 static const EncConfig enc_configs[] = {ENC_CFG(256, 4, 4), ENC_CFG(128, 4, 8), ENC_CFG(128, 8, 6), ENC_CFG(256, 8, 3),
-                                        ENC_CFG(512, 2, 2), ENC_CFG(64, 8, 16), ENC_CFG(128, 2, 12)};
+                                        ENC_CFG(512, 2, 2), ENC_CFG(64, 8, 16), ENC_CFG(128, 2, 12), ENC_CFG(256, 4, 5),
+                                        ENC_CFG(256, 4, 6), ENC_CFG(128, 4, 12)};
 constexpr int N_ENC_CONFIGS = sizeof(enc_configs) / sizeof(enc_configs[0]);
 } // namespace mbpe
 
@@ -793,8 +796,8 @@ extern "C" int mbpe_encoder_create(const uint32_t *merges, uint32_t n_merges, in
     MB_CUDA(cudaMalloc(&e->d_sp_ids, 4));
     MB_CUDA(cudaMalloc(&e->d_sp_off, 8));
     MB_CUDA(cudaMalloc(&e->d_sp_bytes, 1));
-    const char *cache_env = getenv("MBPE_ENCODE_CACHE"); // "0" disables; otherwise log2 of the slot count (default 21)
-    int cache_log2 = cache_env && *cache_env ? atoi(cache_env) : 21;
+    const char *cache_env = getenv("MBPE_ENCODE_CACHE"); // "0" disables; otherwise log2 of the slot count (default 22 = 256 MB)
+    int cache_log2 = cache_env && *cache_env ? atoi(cache_env) : 22;
     if (cache_log2 >= 10 && cache_log2 <= 26) {
         e->cache_slots = 1u << cache_log2;
         e->cache_log_cap = 1u << 19;
@@ -883,7 +886,8 @@ extern "C" int mbpe_encode_reserve(mbpe_encoder *e, uint64_t n_bytes, uint64_t n
     int rc = use_device(e->device);
     if (rc) return rc;
     const uint64_t tile_chunks = (uint64_t)enc_configs[e->cfg].threads * enc_configs[e->cfg].cpt;
-    if ((rc = ensure_status(e, (std::min(n_chunks, e->sub_batch_chunks) + tile_chunks - 1) / tile_chunks + 1))) return rc;
+    const uint64_t max_sb = e->sub_batch_chunks ? e->sub_batch_chunks : ENC_MAX_SUBBATCH;
+    if ((rc = ensure_status(e, (std::min(n_chunks, max_sb) + tile_chunks - 1) / tile_chunks + 1))) return rc;
     if (e->long_cap == 0) {
         e->long_cap = 1 << 16;
         MB_CUDA(cudaMalloc(&e->d_long_list, e->long_cap * 4));
@@ -956,9 +960,17 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
     // sub-batch i+1 continue the stream where sub-batch i ended (*d_n_out).
     const EncConfig &kc = enc_configs[e->cfg];
     const uint64_t ET_CHUNKS = (uint64_t)kc.threads * kc.cpt;
-    for (uint64_t cb = 0; cb < n_chunks; cb += e->sub_batch_chunks) {
+    // Sub-batch schedule: the cache learns between sub-batches, so a cold encoder starts with small ones (1 M chunks)
+    // and doubles; a warm one (chunks_seen) goes straight to large sub-batches, which amortise the launch tail.
+    uint64_t sb = e->sub_batch_chunks ? e->sub_batch_chunks
+                                      : std::min<uint64_t>(ENC_MAX_SUBBATCH, std::max<uint64_t>(1u << 20, e->chunks_seen));
+    sb = (sb + ET_CHUNKS - 1) / ET_CHUNKS * ET_CHUNKS;
+    for (uint64_t cb = 0; cb < n_chunks;) {
         a.chunk0 = cb;
-        a.chunk1 = std::min(n_chunks, cb + e->sub_batch_chunks);
+        a.chunk1 = std::min(n_chunks, cb + sb);
+        cb = a.chunk1;
+        e->chunks_seen += a.chunk1 - a.chunk0;
+        if (!e->sub_batch_chunks) sb = std::min<uint64_t>(ENC_MAX_SUBBATCH, sb * 2);
         const uint64_t n_tiles = (a.chunk1 - a.chunk0 + ET_CHUNKS - 1) / ET_CHUNKS;
         a.n_tiles = (uint32_t)n_tiles;
         MB_CUDA(cudaMemsetAsync(e->d_status, 0, n_tiles * 8, st));

@@ -26,7 +26,10 @@ for cfg in cfgs:
     for env in (os.environ.get("AB_ENV", "").split(";") if os.environ.get("AB_ENV") else [""]):
         for kv in filter(None, env.split(",")):
             k, v = kv.split("=")
-            os.environ[k] = v
+            if v == "-":
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
         os.environ["MBPE_ENC_CFG"] = str(cfg)
         enc = pkg.Encoder(merges)
         enc.reserve(len(text), len(s))
