@@ -183,6 +183,8 @@ struct EncArgs {
     const uint32_t *scratch_b;
     uint32_t *overflow;          // set when out_cap is too small
     uint32_t *miss_count;        // chunks that went through the scan (statistics)
+    uint32_t ablate;             // MBPE_ENC_ABLATE (profiling only; 1, 2, 4 give WRONG results): 1 no look-back wait, 2 no
+                                 // cache probe (every chunk "hits" with two fake ids), 4 no id stores, 16 ids stored by their threads instead of through shared memory
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -272,7 +274,7 @@ constexpr uint32_t META_NONE = 0xFFFFF;
 constexpr uint64_t ENC_MAX_SUBBATCH = 1ull << 26; // chunks per launch at most (tile ids and look-back words are 32-bit safe)
 constexpr uint32_t ET_WARP_SCAN_MAX = 48; // up to this many misses per tile are scanned one warp per chunk
 
-template <int THREADS, int ET_CPT>
+template <int THREADS, int ET_CPT, int STG>
 struct EncSmemT {
     static constexpr int ET_CHUNKS = THREADS * ET_CPT;
     uint32_t off[ET_CHUNKS + 1];
@@ -280,6 +282,7 @@ struct EncSmemT {
     uint16_t miss[ET_CHUNKS];      // work list: chunk index within the tile
     uint32_t meta[ET_CHUNKS];      // scanned chunks: start in miss_out (20 bits, META_NONE = not parked) | count << 20
     uint32_t miss_out[ET_MISS_OUT];
+    uint32_t stage[STG ? STG : 1];
     uint32_t warp_scratch[THREADS / 32][32];
     uint32_t tile, n_miss, miss_used;
     uint32_t warp_sum[THREADS / 32];
@@ -332,9 +335,9 @@ __device__ __forceinline__ uint32_t scan_chunk_warp(const EncTable &tab, uint32_
     return len;
 }
 
-template <int THREADS, int ET_CPT, int MIN_CTAS>
+template <int THREADS, int ET_CPT, int MIN_CTAS, bool STREAM, int STG>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArgs a) {
-    using EncSmem = EncSmemT<THREADS, ET_CPT>;
+    using EncSmem = EncSmemT<THREADS, ET_CPT, STG>;
     constexpr int ET_CHUNKS = EncSmem::ET_CHUNKS;
     constexpr int ENC_THREADS = THREADS; // shadows the file-level default inside this kernel
     extern __shared__ __align__(16) unsigned char enc_smem_raw[];
@@ -353,7 +356,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
         if (tile >= a.n_tiles) return;
         const uint64_t c0 = a.chunk0 + (uint64_t)tile * ET_CHUNKS;
         const uint32_t nc = (uint32_t)min((uint64_t)ET_CHUNKS, a.chunk1 - c0);
-        for (uint32_t i = tid; i <= nc; i += ENC_THREADS) sm.off[i] = __ldg(&a.off[c0 + i]);
+        for (uint32_t i = tid; i <= nc; i += ENC_THREADS) sm.off[i] = STREAM ? __ldcs(&a.off[c0 + i]) : __ldg(&a.off[c0 + i]);
         __syncthreads();
         const uint32_t b0 = sm.off[0], b1 = sm.off[nc];
         const uint32_t a0 = b0 & ~15u; // 16-byte aligned window start (device buffers are 256-byte aligned)
@@ -364,7 +367,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
                 const uint32_t g0 = a0 + v * 16;
                 uint4 q;
                 if (g0 + 16 <= a.n_bytes_total) {
-                    q = __ldg(reinterpret_cast<const uint4 *>(a.bytes + g0));
+                    q = STREAM ? __ldcs(reinterpret_cast<const uint4 *>(a.bytes + g0)) : __ldg(reinterpret_cast<const uint4 *>(a.bytes + g0));
                 } else { // last vector of the buffer
                     uint32_t w[4] = {0, 0, 0, 0};
                     for (uint32_t g = g0; g < a.n_bytes_total; g++)
@@ -379,6 +382,38 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
         uint32_t cnt[ET_CPT], ids[ET_CPT][3];
         uint32_t state[ET_CPT]; // 0 = ids[] valid (hit with <= 3 ids / empty chunk), 1 = scanned, 2 = long chunk,
                                 // 3 = hit with more ids: ids[j][0] = cache slot, ids are fetched again when writing
+        // key of chunk [o, o+len), len <= 31: bytes little endian, zero padded, length in the top byte
+        auto make_key = [&](uint32_t o, uint32_t len, uint64_t *key) {
+            const uint32_t r = o - a0, wi = r >> 2, sh = (r & 3) * 8;
+            uint32_t w[9];
+#pragma unroll
+            for (int q = 0; q < 5; q++) w[q] = sm.text[wi + q];
+            uint32_t v[8];
+#pragma unroll
+            for (int q = 0; q < 4; q++) v[q] = __funnelshift_r(w[q], w[q + 1], sh);
+#pragma unroll
+            for (int q = 4; q < 8; q++) v[q] = 0;
+            if (len > 16) {
+#pragma unroll
+                for (int q = 5; q < 9; q++) w[q] = sm.text[wi + q];
+#pragma unroll
+                for (int q = 4; q < 8; q++) v[q] = __funnelshift_r(w[q], w[q + 1], sh);
+            }
+            key[0] = ((uint64_t)v[1] << 32) | v[0];
+            key[1] = ((uint64_t)v[3] << 32) | v[2];
+            key[2] = ((uint64_t)v[5] << 32) | v[4];
+            key[3] = ((uint64_t)v[7] << 32) | v[6];
+#pragma unroll
+            for (int q = 0; q < 4; q++) { // zero everything at and after byte `len`
+                const int lo = q * 8;
+                if ((int)len <= lo)
+                    key[q] = 0;
+                else if ((int)len < lo + 8)
+                    key[q] &= (1ull << ((len - lo) * 8)) - 1;
+            }
+            key[3] |= (uint64_t)len << 56;
+        };
+        const bool cacheable_tile = use_cache && staged;
 #pragma unroll
         for (int j = 0; j < ET_CPT; j++) {
             const uint32_t k = tid * ET_CPT + j;
@@ -393,37 +428,18 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
                 continue;
             }
             bool hit = false;
-            if (use_cache && staged && len <= CACHE_MAX_LEN) {
-                // up to 32 bytes starting at the (unaligned) chunk start, bytes past the chunk zeroed
-                const uint32_t r = o - a0, wi = r >> 2, sh = (r & 3) * 8;
-                uint32_t w[9];
-#pragma unroll
-                for (int q = 0; q < 5; q++) w[q] = sm.text[wi + q];
-                uint32_t v[8];
-#pragma unroll
-                for (int q = 0; q < 4; q++) v[q] = __funnelshift_r(w[q], w[q + 1], sh);
-#pragma unroll
-                for (int q = 4; q < 8; q++) v[q] = 0;
-                if (len > 16) {
-#pragma unroll
-                    for (int q = 5; q < 9; q++) w[q] = sm.text[wi + q];
-#pragma unroll
-                    for (int q = 4; q < 8; q++) v[q] = __funnelshift_r(w[q], w[q + 1], sh);
-                }
-                uint64_t key[4] = {((uint64_t)v[1] << 32) | v[0], ((uint64_t)v[3] << 32) | v[2],
-                                   ((uint64_t)v[5] << 32) | v[4], ((uint64_t)v[7] << 32) | v[6]};
-#pragma unroll
-                for (int q = 0; q < 4; q++) { // zero everything at and after byte `len`
-                    const int lo = q * 8;
-                    if ((int)len <= lo)
-                        key[q] = 0;
-                    else if ((int)len < lo + 8)
-                        key[q] &= (1ull << ((len - lo) * 8)) - 1;
-                }
-                key[3] |= (uint64_t)len << 56;
+            if (cacheable_tile && len <= CACHE_MAX_LEN) {
+                uint64_t key[4];
+                make_key(o, len, key);
                 uint32_t h = cache_hash(key[0], key[1], key[2], key[3]) & a.cache.mask;
+                if (a.ablate & 2) {
+                    cnt[j] = 2;
+                    ids[j][0] = (uint32_t)key[0];
+                    ids[j][1] = h;
+                    continue;
+                }
                 for (;;) {
-                    // the whole 64-byte entry at once: four independent 16-byte loads, one round trip
+                    // the whole 64-byte entry at once: three independent 16-byte loads, one round trip
                     const ulonglong2 *sp = reinterpret_cast<const ulonglong2 *>(&a.cache.slots[h]);
                     const ulonglong2 lo = __ldg(sp);
                     const ulonglong2 hi = __ldg(sp + 1);
@@ -545,57 +561,71 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
             total += v;
         }
         if (warp == 0) {
-            const uint64_t b = lookback_base(a.status, tile, total, a.stream_base);
+            const uint64_t b = (a.ablate & 1) ? (uint64_t)tile * (ET_CHUNKS * 9 / 4)
+                                              : lookback_base(a.status, tile, total, a.stream_base);
             if (lane == 0) sm.base = b;
         }
         __syncthreads();
         const uint64_t base = sm.base;
-        uint64_t dst = base + warp_base + (incl - sum);
+        // ids go to shared memory first and leave for HBM as whole 128-byte lines (a thread's own stores would touch
+        // one sector per lane); tiles whose ids do not fit the buffer, or the end of a full output buffer, store directly
+        const bool via_smem = STG > 0 && total <= (uint32_t)STG && base + total <= a.out_cap && !(a.ablate & 16);
+        uint32_t loc = warp_base + (incl - sum);
+        uint32_t *const gout = a.out + base; // only dereferenced below out_cap
 #pragma unroll
         for (int j = 0; j < ET_CPT; j++) {
             const uint32_t k = tid * ET_CPT + j;
             if (k >= nc) continue;
             const uint32_t n = cnt[j];
-            if (a.out_off) a.out_off[c0 + k] = dst;
-            if (dst + n <= a.out_cap) {
+            if (a.out_off) a.out_off[c0 + k] = base + loc;
+            if (a.ablate & 4) {
+            } else if (via_smem || base + loc + n <= a.out_cap) {
+                uint32_t *const dstp = (via_smem ? sm.stage : gout) + loc;
                 if (state[j] == 0) {
-                    if (n > 0) a.out[dst] = ids[j][0];
-                    if (n > 1) a.out[dst + 1] = ids[j][1];
-                    if (n > 2) a.out[dst + 2] = ids[j][2];
+                    if (n > 0) dstp[0] = ids[j][0];
+                    if (n > 1) dstp[1] = ids[j][1];
+                    if (n > 2) dstp[2] = ids[j][2];
                 } else if (state[j] == 3) {
                     const CacheSlot &cs = a.cache.slots[ids[j][0]];
                     if (n <= CACHE_INLINE_IDS) { // the value sector again: two vector loads, predicated stores, no loop
                         const uint4 lo4 = __ldg(reinterpret_cast<const uint4 *>(&cs.n));      // n, v0, v1, v2
                         const uint4 hi4 = __ldg(reinterpret_cast<const uint4 *>(&cs.v[3]));   // v3 .. v6
-                        a.out[dst] = lo4.y;
-                        a.out[dst + 1] = lo4.z;
-                        a.out[dst + 2] = lo4.w;
-                        a.out[dst + 3] = hi4.x;
-                        if (n > 4) a.out[dst + 4] = hi4.y;
-                        if (n > 5) a.out[dst + 5] = hi4.z;
-                        if (n > 6) a.out[dst + 6] = hi4.w;
+                        dstp[0] = lo4.y;
+                        dstp[1] = lo4.z;
+                        dstp[2] = lo4.w;
+                        dstp[3] = hi4.x;
+                        if (n > 4) dstp[4] = hi4.y;
+                        if (n > 5) dstp[5] = hi4.z;
+                        if (n > 6) dstp[6] = hi4.w;
                     } else {
                         const uint32_t *src = a.cache.arena + __ldg(&cs.v[0]);
-                        for (uint32_t i = 0; i < n; i++) a.out[dst + i] = __ldg(&src[i]);
+                        for (uint32_t i = 0; i < n; i++) dstp[i] = __ldg(&src[i]);
                     }
                 } else if (state[j] == 1) {
                     const uint32_t start = sm.meta[k] & 0xFFFFF;
                     if (start != META_NONE) {
-                        for (uint32_t i = 0; i < n; i++) a.out[dst + i] = sm.miss_out[start + i];
+                        for (uint32_t i = 0; i < n; i++) dstp[i] = sm.miss_out[start + i];
                     } else {
                         uint32_t t[ENC_SHORT_MAX];
                         const uint32_t o = sm.off[k];
                         scan_chunk(a, sm, staged, a0, o, sm.off[k + 1] - o, t);
-                        for (uint32_t i = 0; i < n; i++) a.out[dst + i] = t[i];
+                        for (uint32_t i = 0; i < n; i++) dstp[i] = t[i];
                     }
                 } else {
                     const uint32_t o = sm.off[k];
-                    for (uint32_t i = 0; i < n; i++) a.out[dst + i] = a.scratch_a[o + i];
+                    for (uint32_t i = 0; i < n; i++) dstp[i] = a.scratch_a[o + i];
                 }
             } else if (n) {
                 *a.overflow = 1;
             }
-            dst += n;
+            loc += n;
+        }
+        if (via_smem && !(a.ablate & 4)) {
+            __syncthreads();
+            for (uint32_t i = tid; i < total; i += ENC_THREADS) {
+                if (STREAM) __stcs(&gout[i], sm.stage[i]);
+                else gout[i] = sm.stage[i];
+            }
         }
         if (tile == a.n_tiles - 1 && tid == 0) {
             *a.d_n_out = base + total;
@@ -736,10 +766,11 @@ struct EncConfig {
     void (*kernel)(const EncArgs);
     size_t smem;
 };
-#define ENC_CFG(T, C, M) EncConfig{T, C, M, k_encode_tiles<T, C, M>, sizeof(EncSmemT<T, C>)}
-static const EncConfig enc_configs[] = {ENC_CFG(256, 4, 4), ENC_CFG(128, 4, 8), ENC_CFG(128, 8, 6), ENC_CFG(256, 8, 3),
-                                        ENC_CFG(512, 2, 2), ENC_CFG(64, 8, 16), ENC_CFG(128, 2, 12), ENC_CFG(256, 4, 5),
-                                        ENC_CFG(256, 4, 6), ENC_CFG(128, 4, 12)};
+#define ENC_CFG(T, C, M, P, G) EncConfig{T, C, M, k_encode_tiles<T, C, M, P, G>, sizeof(EncSmemT<T, C, G>)}
+// (threads, chunks per thread, CTAs per SM, streaming hints on the one-pass loads/stores, staging words); 0 = default
+static const EncConfig enc_configs[] = {ENC_CFG(256, 4, 4, true, 3072),  ENC_CFG(256, 4, 4, true, 4096), ENC_CFG(256, 4, 4, true, 0),
+                                        ENC_CFG(256, 4, 4, false, 0),    ENC_CFG(256, 4, 4, false, 4096), ENC_CFG(128, 4, 8, true, 2048),
+                                        ENC_CFG(128, 4, 8, true, 0),     ENC_CFG(256, 4, 5, true, 3072)};
 constexpr int N_ENC_CONFIGS = sizeof(enc_configs) / sizeof(enc_configs[0]);
 } // namespace mbpe
 
@@ -956,6 +987,7 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
     a.scratch_b = e->d_scratch_b;
     a.overflow = e->d_small + 2;
     a.miss_count = e->d_small + 3;
+    if (const char *ab = getenv("MBPE_ENC_ABLATE")) a.ablate = (uint32_t)atoi(ab);
     // Sub-batches of whole tiles: the cache learns from one sub-batch before the next one starts, and the ids of
     // sub-batch i+1 continue the stream where sub-batch i ended (*d_n_out).
     const EncConfig &kc = enc_configs[e->cfg];
