@@ -191,6 +191,11 @@ void mbpe_tokenizer_set_threads(mbpe_tokenizer *t, int n_threads); /* host pre-t
  * [start,end) pairs. Call with starts == NULL to count. */
 int mbpe_split(const char *pattern, const uint8_t *text, uint64_t len, int n_threads, uint64_t *starts,
                uint64_t *ends, uint64_t cap, uint64_t *n_chunks);
+/* 2-bit class per code point (0 other, 1 \p{L}, 2 \p{N}, 3 \s), 0x110000/4 bytes, read out of the linked PCRE2 with
+ * the reference's compile options (Tokenizer.h:407): what the GPU matcher of the GPT-4 pattern classifies with.
+ * MBPE_E_REGEX if that PCRE2's caseless folding is not the one the matcher assumes. */
+#define MBPE_PRETOK_TABLE_BYTES (0x110000 / 4)
+int mbpe_pretok_class_table(uint8_t *table_out);
 /* chunk dedup in first-appearance order + byte->token widening (Tokenizer.h:85-100). Sizing: n_unique <=
  * n_chunks, n_tokens <= sum of lengths. */
 int mbpe_dedup(const uint8_t *text, const uint64_t *starts, const uint64_t *ends, uint64_t n_chunks,

@@ -30,7 +30,7 @@ EXPORTS = [
     "mbpe_tokenizer_set_special_tokens", "mbpe_tokenizer_train", "mbpe_tokenizer_save", "mbpe_tokenizer_load",
     "mbpe_tokenizer_encode", "mbpe_tokenizer_decode", "mbpe_tokenizer_get_merges",
     "mbpe_tokenizer_last_train_stats", "mbpe_tokenizer_set_engine", "mbpe_tokenizer_set_threads",
-    "mbpe_split", "mbpe_dedup", "mbpe_split_dedup", "mbpe_plan_shards", "mbpe_write_model", "mbpe_synth_corpus",
+    "mbpe_split", "mbpe_pretok_class_table", "mbpe_dedup", "mbpe_split_dedup", "mbpe_plan_shards", "mbpe_write_model", "mbpe_synth_corpus",
 ]
 
 
@@ -375,6 +375,13 @@ def split(pattern: str, text: bytes, n_threads=0):
     _ck(lib().mbpe_split(pattern.encode(), _p(buf, C.c_uint8), C.c_uint64(len(text)), n_threads, _p(s, C.c_uint64),
                          _p(e, C.c_uint64), C.c_uint64(cap), C.byref(n)))
     return s[:n.value].copy(), e[:n.value].copy()
+
+
+def pretok_class_table():
+    """2-bit class per code point as the linked PCRE2 sees it (0 other, 1 letter, 2 number, 3 white space)."""
+    t = np.zeros(0x110000 // 4, np.uint8)
+    _ck(lib().mbpe_pretok_class_table(_p(t, C.c_uint8)))
+    return t
 
 
 def dedup(text: bytes, starts, ends):

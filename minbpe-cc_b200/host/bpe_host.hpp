@@ -50,6 +50,10 @@ int split_range(const Regex &re, const uint8_t *text, uint64_t len, uint64_t beg
 int split_parallel(const Regex &re, const std::string &pattern, const uint8_t *text, uint64_t len, int n_threads,
                    std::vector<Span> &out, std::string *err);
 
+// 2-bit class per code point (0 other, 1 \p{L}, 2 \p{N}, 3 \s) as the linked PCRE2 sees them, for the GPU matcher of
+// the GPT-4 pattern; table = 0x110000 / 4 bytes. Fails if PCRE2's caseless folding differs from the matcher's.
+int pretok_class_table(uint8_t *table, std::string *err);
+
 // Tokenizer.h:85-100: a chunk that starts with NUL and parses as an int becomes that single id.
 bool marker_token(std::string_view chunk, Token *id);
 

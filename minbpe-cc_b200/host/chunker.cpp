@@ -311,6 +311,105 @@ int split_parallel(const Regex &re, const std::string &pattern, const uint8_t *t
     return MBPE_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Code point classes for the GPU matcher of the GPT-4 pattern (csrc/pretok_core.cuh), taken from the linked PCRE2:
+// every code point is written into one buffer and \p{L}+, \p{N}+, \s+ are matched over it with the options the
+// reference compiles with (Tokenizer.h:407), so the table IS that library's Unicode data. 2 bits per code point:
+// 0 other, 1 letter, 2 number, 3 white space.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+inline uint64_t cp_offset(uint32_t cp) { // byte offset of code point cp in the all-code-points buffer
+    if (cp < 0x80) return cp;
+    if (cp < 0x800) return 0x80 + 2ull * (cp - 0x80);
+    const uint64_t base3 = 0x80 + 2ull * (0x800 - 0x80);
+    if (cp < 0xD800) return base3 + 3ull * (cp - 0x800);
+    if (cp < 0x10000) return base3 + 3ull * (cp - 0x800 - 0x800); // surrogates D800..DFFF are left out
+    return base3 + 3ull * (0x10000 - 0x800 - 0x800) + 4ull * (cp - 0x10000);
+}
+inline uint32_t cp_at_offset(uint64_t off) {
+    if (off < 0x80) return (uint32_t)off;
+    const uint64_t base3 = 0x80 + 2ull * (0x800 - 0x80);
+    if (off < base3) return (uint32_t)(0x80 + (off - 0x80) / 2);
+    const uint64_t base4 = base3 + 3ull * (0x10000 - 0x800 - 0x800);
+    if (off < base4) {
+        uint32_t cp = (uint32_t)(0x800 + (off - base3) / 3);
+        return cp >= 0xD800 ? cp + 0x800 : cp;
+    }
+    return (uint32_t)(0x10000 + (off - base4) / 4);
+}
+} // namespace
+
+int pretok_class_table(uint8_t *table, std::string *err) {
+    std::vector<uint8_t> all(cp_offset(0x110000));
+    for (uint32_t cp = 0; cp < 0x110000; cp++) {
+        if (cp >= 0xD800 && cp <= 0xDFFF) continue;
+        uint8_t *o = &all[cp_offset(cp)];
+        if (cp < 0x80) {
+            o[0] = (uint8_t)cp;
+        } else if (cp < 0x800) {
+            o[0] = (uint8_t)(0xC0 | (cp >> 6));
+            o[1] = (uint8_t)(0x80 | (cp & 0x3F));
+        } else if (cp < 0x10000) {
+            o[0] = (uint8_t)(0xE0 | (cp >> 12));
+            o[1] = (uint8_t)(0x80 | ((cp >> 6) & 0x3F));
+            o[2] = (uint8_t)(0x80 | (cp & 0x3F));
+        } else {
+            o[0] = (uint8_t)(0xF0 | (cp >> 18));
+            o[1] = (uint8_t)(0x80 | ((cp >> 12) & 0x3F));
+            o[2] = (uint8_t)(0x80 | ((cp >> 6) & 0x3F));
+            o[3] = (uint8_t)(0x80 | (cp & 0x3F));
+        }
+    }
+    memset(table, 0, 0x110000 / 4);
+    // runs of one class; `cls` 0 collects the caseless partners of the letters of alternative 1 instead
+    auto runs = [&](const char *pattern, uint32_t cls, std::vector<uint32_t> *hits) -> int {
+        Regex re;
+        int rc = re.compile(pattern, err);
+        if (rc) return rc;
+        pcre2_match_data_8 *md = pcre2_match_data_create_from_pattern_8(re.code(), nullptr);
+        if (!md) return MBPE_E_REGEX;
+        size_t off = 0;
+        while (off < all.size()) {
+            int m = pcre2_match_8(re.code(), all.data(), all.size(), off, MBPE_PCRE2_NO_UTF_CHECK, md, nullptr);
+            if (m < 0) break;
+            const size_t *ov = pcre2_get_ovector_pointer_8(md);
+            if (ov[1] <= ov[0]) break;
+            const uint32_t a = cp_at_offset(ov[0]), b = ov[1] >= all.size() ? 0x110000u : cp_at_offset(ov[1]);
+            for (uint32_t cp = a; cp < b; cp++) {
+                if (cp >= 0xD800 && cp <= 0xDFFF) continue;
+                if (hits)
+                    hits->push_back(cp);
+                else
+                    table[cp >> 2] |= (uint8_t)(cls << ((cp & 3) * 2));
+            }
+            off = ov[1];
+        }
+        pcre2_match_data_free_8(md);
+        return MBPE_OK;
+    };
+    int rc;
+    if ((rc = runs("\\p{L}+", 1, nullptr))) return rc;
+    if ((rc = runs("\\p{N}+", 2, nullptr))) return rc;
+    if ((rc = runs("\\s+", 3, nullptr))) return rc;
+    // the matcher hard-codes which code points fold onto s d m t l v e r: ASCII both cases, and U+017F -> s
+    std::vector<uint32_t> hits;
+    if ((rc = runs("(?i:[sdmtlver])+", 0, &hits))) return rc;
+    std::vector<uint32_t> want;
+    for (const char *q = "DELMRSTVdelmrstv"; *q; q++) want.push_back((uint32_t)*q);
+    want.push_back(0x17F);
+    Regex long_s;
+    if ((rc = long_s.compile("^(?i:s)$", err))) return rc;
+    pcre2_match_data_8 *md = pcre2_match_data_create_from_pattern_8(long_s.code(), nullptr);
+    const uint8_t ls[2] = {0xC5, 0xBF};
+    const bool folds = md && pcre2_match_8(long_s.code(), ls, 2, 0, MBPE_PCRE2_NO_UTF_CHECK, md, nullptr) >= 0;
+    if (md) pcre2_match_data_free_8(md);
+    if (hits != want || !folds) {
+        if (err) *err = "the linked PCRE2 folds case differently from the GPU matcher's assumption (U+017F only)";
+        return MBPE_E_REGEX;
+    }
+    return MBPE_OK;
+}
+
 bool marker_token(std::string_view chunk, Token *id) {
     if (chunk.empty() || chunk[0] != '\0') return false;
     try {

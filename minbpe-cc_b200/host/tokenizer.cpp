@@ -510,6 +510,13 @@ extern "C" int mbpe_split(const char *pattern, const uint8_t *text, uint64_t len
     return MBPE_OK;
 }
 
+extern "C" int mbpe_pretok_class_table(uint8_t *table_out) {
+    if (!table_out) return fail(MBPE_E_INVALID, "null argument");
+    std::string err;
+    int rc = pretok_class_table(table_out, &err);
+    return rc ? fail(rc, err) : MBPE_OK;
+}
+
 extern "C" int mbpe_dedup(const uint8_t *text, const uint64_t *starts, const uint64_t *ends, uint64_t n_chunks,
                           uint32_t *tokens_out, uint64_t *n_tokens, uint64_t *off_out, uint32_t *weight_out,
                           uint64_t *n_unique) {

@@ -1,0 +1,123 @@
+"""The hand-written matcher of the GPT-4 split pattern (csrc/pretok_core.cuh) against PCRE2.
+
+CPU tier: the same pretok_window() the CUDA kernel runs, executed window by window on the host
+(tests/emu/pretok_emu.cpp), must mark exactly the chunk starts that the reference's pcre2_match loop produces
+(mbpe_split, Tokenizer.h:506-540) -- for every window size, on the fixtures and on fuzzed Unicode."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+EMU_SRC = os.path.join(ROOT, "tests", "emu", "pretok_emu.cpp")
+EMU_LIB = os.path.join(ROOT, "tests", "emu", "libpretok_emu.so")
+
+
+@pytest.fixture(scope="module")
+def emu(pkg):
+    deps = [EMU_SRC, os.path.join(ROOT, "minbpe-cc_b200", "csrc", "pretok_core.cuh")]
+    if not os.path.exists(EMU_LIB) or any(os.path.getmtime(d) > os.path.getmtime(EMU_LIB) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-x", "c++", "-o", EMU_LIB, EMU_SRC])
+    L = C.CDLL(EMU_LIB)
+    L.emu_pretok.restype = C.c_uint32
+    table = pkg.pretok_class_table()
+
+    def run(text: bytes, window=32, max_crawl=1 << 40, order=0):
+        buf = np.frombuffer(text, np.uint8) if len(text) else np.zeros(1, np.uint8)
+        marks = np.zeros(max(len(text), 1), np.uint8)
+        err = L.emu_pretok(buf.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_uint64(len(text)),
+                           table.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_uint64(window), C.c_uint64(max_crawl), order,
+                           marks.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return np.flatnonzero(marks[:len(text)]).astype(np.uint64), err
+
+    return run
+
+
+@pytest.fixture(scope="module")
+def pcre2_starts(pkg):
+    return lambda text: _pcre2_starts(pkg, text)
+
+
+def _pcre2_starts(pkg, text: bytes):
+    s, e = pkg.split(pkg.patterns()["gpt4"], text, 1)
+    assert len(s) == 0 or (s[0] == 0 and e[-1] == len(text) and np.array_equal(s[1:], e[:-1])), "gpt4 chunks tile the text"
+    return s
+
+
+def test_class_table_matches_known_points(pkg):
+    t = pkg.pretok_class_table()
+    cls = lambda cp: (int(t[cp >> 2]) >> ((cp & 3) * 2)) & 3
+    assert [cls(ord(c)) for c in "aZ09 \n\t!_'"] == [1, 1, 2, 2, 3, 3, 3, 0, 0, 0]
+    assert cls(0xE9) == 1 and cls(0x4E2D) == 1 and cls(0x0416) == 1      # e-acute, CJK, Cyrillic: letters
+    assert cls(0x0663) == 2 and cls(0xBD) == 2 and cls(0x2167) == 2      # Arabic-Indic digit, 1/2, roman numeral: numbers
+    assert cls(0xA0) == 3 and cls(0x3000) == 3 and cls(0x2028) == 3 and cls(0x85) == 3  # Unicode spaces
+    assert cls(0x1F600) == 0 and cls(0x3002) == 0 and cls(0x200B) == 0   # emoji, CJK full stop, zero-width space
+    assert cls(0x17F) == 1
+
+
+@pytest.mark.parametrize("name", ["taylorswift.txt", "shakespeare.txt"])
+@pytest.mark.parametrize("window", [32, 64, 7])
+def test_fixtures(emu, name, window, pcre2_starts):
+    path = os.path.join(ROOT, "tests", "golden", "data", name)
+    text = open(path, "rb").read()
+    if name == "shakespeare.txt" and window == 7:
+        text = text[:200000]
+    got, err = emu(text, window)
+    assert err == 0
+    assert np.array_equal(got, pcre2_starts(text))
+
+
+# every class, the caseless partners of alternative 1 (long s U+017F, Kelvin U+212A), Unicode blanks, combining
+# marks, astral code points, control characters -- and the multi-character shapes the alternatives care about
+ALPHABET = (list(" \n\r\t'.,!?-_0123456789") * 3 + list("abcdefghijklmnopqrstuvwxyzSDMTLVRE") * 2 +
+            ["é", "ß", "ſ", "K", "Ж", "中", "。", " ", "　", " ", " ",
+             "", "٣", "½", "Ⅷ", "\U0001f600", "\U00020000", "​", "́", "\v", "\f", "\x00",
+             "\x1c", "'s", "'S", "'ſ", "'ll", "'LL", "'Ve", "'re", "'t", " '", "  ", "\n\n", "\r\n", " \n ", "123456",
+             "　　"])
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_fuzz_unicode(emu, seed, pcre2_starts):
+    rng = np.random.default_rng(1000 + seed)
+    for _ in range(150):
+        n = int(rng.integers(1, 200))
+        text = "".join(ALPHABET[i] for i in rng.integers(0, len(ALPHABET), n)).encode("utf-8")
+        want = pcre2_starts(text)
+        for window in (int(rng.integers(1, 12)), 32):
+            for order in (0, 1):
+                got, err = emu(text, window, order=order)
+                assert err == 0, text
+                assert np.array_equal(got, want), (text, window, got.tolist(), want.tolist())
+
+
+def test_fuzz_class_runs(emu, pcre2_starts):
+    """long runs of one class (digits, symbols, blanks, newlines) across many windows"""
+    rng = np.random.default_rng(7)
+    pieces = ["7" * 50, "-" * 70, " " * 40, "\n" * 33, "x" * 90, "中" * 30, " \n" * 20, " " * 9, "a1" * 20,
+              "!a" * 20, "'s" * 10, " !" * 10, "\r\n\r\n", "\t\t\t", "1 2  3   4", "　\n　"]
+    for _ in range(200):
+        text = "".join(pieces[i] for i in rng.integers(0, len(pieces), int(rng.integers(1, 8)))).encode()
+        want = pcre2_starts(text)
+        for window in (5, 32, 64):
+            got, err = emu(text, window)
+            assert err == 0 and np.array_equal(got, want), (text, window)
+
+
+def test_edges(emu, pcre2_starts):
+    for text in [b"", b"a", b" ", b"\n", b"'", b"'s", b" a", b"  ", b"  a", b"a  ", b"\n ", b" \n", b"1234", b"a'", b"''s",
+                 " ".encode(), " a".encode(), "   a".encode(), "a　　b".encode()]:
+        got, err = emu(text, 4)
+        assert err == 0 and np.array_equal(got, pcre2_starts(text)), text
+
+
+def test_invalid_utf8_and_pathological_runs_are_reported(emu):
+    for bad in [b"abc \xff def", b"abc \xc3", b"x \xe4\xb8 y", b"\xc0\x80 overlong", b"\xed\xa0\x80 surrogate", b"a \x80 b"]:
+        _, err = emu(bad * 3, 8)
+        assert err & 1, bad
+    _, err = emu(b"a " + b"7" * 5000 + b" b", 32, max_crawl=1024)
+    assert err & 2
+    _, err = emu(b"a " + b"7" * 500 + b" b", 32, max_crawl=1024)
+    assert err == 0
