@@ -31,6 +31,7 @@ extern "C" {
 #define MBPE_E_CAPACITY (-4)   /* caller buffer too small; required size is reported through the out parameter */
 #define MBPE_E_IO (-5)         /* file could not be opened / parsed */
 #define MBPE_E_REGEX (-6)      /* PCRE2 compile or match error */
+#define MBPE_E_UNSUPPORTED (-8) /* the GPU pre-tokeniser declines this text (malformed UTF-8, pathological runs): use the PCRE2 path */
 #define MBPE_E_EMPTY (-7)      /* nothing to do where the reference would assert/abort */
 
 /* Tokenizer::CONFLICT_RESOLUTION (Tokenizer.h:54-57) */
@@ -214,6 +215,40 @@ int mbpe_write_model(const char *path, const char *pattern, const char *special_
 int mbpe_plan_shards(const uint64_t *chunk_off, uint64_t n_chunks, uint32_t n_parts, uint64_t *first_chunk_out);
 /* deterministic synthetic Zipfian UTF-8 corpus (SURVEY 8(d) input 3): fills out[0..n) */
 int mbpe_synth_corpus(uint64_t seed, uint8_t *out, uint64_t n, int n_threads);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 6. GPU pre-tokeniser and chunk dedup for the GPT-4 split pattern  (regex loop Tokenizer.h:500-544
+ *    with the pattern of :60, chunk -> count SURVEY F2)
+ *    Same chunk list as the reference's pcre2_match loop, computed on the device by a hand-written matcher whose
+ *    code point classes are read out of the linked PCRE2. Text it cannot take (malformed UTF-8, pathological runs)
+ *    is refused with MBPE_E_UNSUPPORTED; the caller then uses mbpe_split (PCRE2 itself).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct mbpe_pretok mbpe_pretok;
+int mbpe_pretok_create(int device, mbpe_pretok **out);
+void mbpe_pretok_destroy(mbpe_pretok *p);
+/* resident text (< 4 GiB) -> chunk offsets: d_off_out[0 .. n_chunks] (u32, last = len), the layout
+ * mbpe_encode_device takes. off_cap counts u32 entries; len + 2 always suffices. */
+int mbpe_pretok_split_device(mbpe_pretok *p, const uint8_t *d_text, uint64_t len, uint32_t *d_off_out, uint64_t off_cap,
+                             uint64_t *n_chunks, void *stream);
+/* host text -> host offsets off_out[0 .. n_chunks] (chunk c = [off[c], off[c+1])): GPU twin of mbpe_split */
+int mbpe_pretok_split(mbpe_pretok *p, const uint8_t *text, uint64_t len, uint64_t *off_out, uint64_t off_cap,
+                      uint64_t *n_chunks);
+/* unique chunks resident on the device, in first-appearance order, in the trainer's input layout */
+typedef struct mbpe_device_corpus {
+    uint32_t *d_tokens;  /* bytes of the unique chunks widened to u32, concatenated */
+    uint64_t *d_off;     /* n_unique + 1 */
+    uint32_t *d_weight;  /* multiplicity of each unique chunk */
+    uint64_t n_tokens, n_unique, n_chunks;
+    int device;
+} mbpe_device_corpus;
+int mbpe_pretok_dedup_device(mbpe_pretok *p, const uint8_t *d_text, uint64_t len, const uint32_t *d_off,
+                             uint64_t n_chunks, mbpe_device_corpus *out, void *stream);
+/* host text -> device corpus (H2D + split + dedup): the front end of Tokenizer::train (:500-556) */
+int mbpe_pretok_corpus(mbpe_pretok *p, const uint8_t *text, uint64_t len, mbpe_device_corpus *out);
+int mbpe_device_corpus_download(const mbpe_device_corpus *c, uint32_t *tokens, uint64_t *off, uint32_t *weight);
+void mbpe_device_corpus_free(mbpe_device_corpus *c);
+/* a trainer over a device corpus (copied device to device; the corpus may be freed afterwards) */
+int mbpe_trainer_create_device(const mbpe_device_corpus *c, mbpe_trainer **out);
 
 #ifdef __cplusplus
 }

@@ -30,7 +30,10 @@ EXPORTS = [
     "mbpe_tokenizer_set_special_tokens", "mbpe_tokenizer_train", "mbpe_tokenizer_save", "mbpe_tokenizer_load",
     "mbpe_tokenizer_encode", "mbpe_tokenizer_decode", "mbpe_tokenizer_get_merges",
     "mbpe_tokenizer_last_train_stats", "mbpe_tokenizer_set_engine", "mbpe_tokenizer_set_threads",
-    "mbpe_split", "mbpe_pretok_class_table", "mbpe_dedup", "mbpe_split_dedup", "mbpe_plan_shards", "mbpe_write_model", "mbpe_synth_corpus",
+    "mbpe_split", "mbpe_pretok_class_table", "mbpe_dedup",
+    "mbpe_pretok_create", "mbpe_pretok_destroy", "mbpe_pretok_split_device", "mbpe_pretok_split",
+    "mbpe_pretok_dedup_device", "mbpe_pretok_corpus", "mbpe_device_corpus_download", "mbpe_device_corpus_free",
+    "mbpe_trainer_create_device", "mbpe_split_dedup", "mbpe_plan_shards", "mbpe_write_model", "mbpe_synth_corpus",
 ]
 
 
@@ -175,6 +178,74 @@ class Trainer:
     def close(self):
         if self.h:
             lib().mbpe_trainer_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceCorpus(C.Structure):
+    """mbpe_device_corpus: unique chunks resident on the GPU in the trainer's input layout."""
+    _fields_ = [("d_tokens", C.c_void_p), ("d_off", C.c_void_p), ("d_weight", C.c_void_p), ("n_tokens", C.c_uint64),
+                ("n_unique", C.c_uint64), ("n_chunks", C.c_uint64), ("device", C.c_int)]
+
+    def download(self):
+        tokens = np.zeros(max(self.n_tokens, 1), np.uint32)
+        off = np.zeros(self.n_unique + 1, np.uint64)
+        w = np.zeros(max(self.n_unique, 1), np.uint32)
+        _ck(lib().mbpe_device_corpus_download(C.byref(self), _p(tokens, C.c_uint32), _p(off, C.c_uint64), _p(w, C.c_uint32)))
+        return tokens[:self.n_tokens], off, w[:self.n_unique]
+
+    def trainer(self):
+        t = Trainer.__new__(Trainer)
+        t.h = C.c_void_p()
+        _ck(lib().mbpe_trainer_create_device(C.byref(self), C.byref(t.h)))
+        return t
+
+    def free(self):
+        lib().mbpe_device_corpus_free(C.byref(self))
+
+
+class Pretok:
+    """GPU pre-tokeniser + chunk dedup for the GPT-4 split pattern (Tokenizer.h:500-544)."""
+
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        _ck(lib().mbpe_pretok_create(device, C.byref(self.h)))
+
+    def split(self, text: bytes):
+        """chunk offsets (n_chunks + 1, u64): chunk c = text[off[c]:off[c+1]]"""
+        buf = _u8(text)
+        off = np.zeros(len(text) + 2, np.uint64)
+        n = C.c_uint64()
+        _ck(lib().mbpe_pretok_split(self.h, _p(buf, C.c_uint8), C.c_uint64(len(text)), _p(off, C.c_uint64),
+                                    C.c_uint64(len(off)), C.byref(n)))
+        return off[:n.value + 1].copy()
+
+    def split_device(self, d_text, n_bytes, d_off, off_cap, stream=None):
+        n = C.c_uint64()
+        _ck(lib().mbpe_pretok_split_device(self.h, C.c_void_p(d_text), C.c_uint64(n_bytes), C.c_void_p(d_off),
+                                           C.c_uint64(off_cap), C.byref(n), C.c_void_p(stream or 0)))
+        return n.value
+
+    def dedup_device(self, d_text, n_bytes, d_off, n_chunks, stream=None):
+        c = DeviceCorpus()
+        _ck(lib().mbpe_pretok_dedup_device(self.h, C.c_void_p(d_text), C.c_uint64(n_bytes), C.c_void_p(d_off),
+                                           C.c_uint64(n_chunks), C.byref(c), C.c_void_p(stream or 0)))
+        return c
+
+    def corpus(self, text: bytes):
+        buf = _u8(text)
+        c = DeviceCorpus()
+        _ck(lib().mbpe_pretok_corpus(self.h, _p(buf, C.c_uint8), C.c_uint64(len(text)), C.byref(c)))
+        return c
+
+    def close(self):
+        if self.h:
+            lib().mbpe_pretok_destroy(self.h)
             self.h = C.c_void_p()
 
     def __del__(self):

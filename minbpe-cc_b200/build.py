@@ -16,7 +16,7 @@ LIB = os.path.join(HERE, "lib", "libminbpe_b200.so")
 CLI = os.path.join(HERE, "bin", "minbpe-cc")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-CU = ["capi.cu", "train_cuda.cu", "encode.cu"]
+CU = ["capi.cu", "train_cuda.cu", "encode.cu", "pretok.cu"]
 CPP = ["chunker.cpp", "tokenizer.cpp"]
 EXTRA_DEFS = [d for d in os.environ.get("MBPE_DEFS", "").split() if d]  # e.g. MBPE_DEFS="-DMBPE_PROFILE_HITS"
 NVCC_FLAGS = EXTRA_DEFS + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",

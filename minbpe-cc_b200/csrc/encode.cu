@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "lookback.cuh"
 
 namespace mbpe {
 
@@ -76,49 +77,6 @@ __device__ __forceinline__ uint32_t enc_pass(const EncTable &tab, uint32_t *t, u
         }
     }
     return w;
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// decoupled look-back over tiles (status word = flag:2 | value:62)
-// ---------------------------------------------------------------------------------------------------------
-constexpr uint64_t LB_AGG = 1ull << 62, LB_PREFIX = 2ull << 62, LB_VAL = (1ull << 62) - 1;
-
-// Called by all 32 lanes of one warp. Each round inspects 32 predecessors at once (one L2 round trip), so a tile
-// that starts while hundreds of older tiles are still in flight resolves its base in ~14 rounds, not ~440 serial loads.
-__device__ __forceinline__ uint64_t lookback_base(unsigned long long *status, uint32_t tile, uint64_t total,
-                                                  const unsigned long long *first_base = nullptr) {
-    const uint32_t lane = threadIdx.x & 31;
-    if (tile == 0) {
-        const uint64_t b = first_base ? *first_base : 0;
-        if (lane == 0) atomicExch(&status[0], LB_PREFIX | (b + total));
-        return b;
-    }
-    if (lane == 0) atomicExch(&status[tile], LB_AGG | total);
-    uint64_t acc = 0;
-    int64_t j = (int64_t)tile - 1; // lane l looks at tile j - l
-    for (;;) {
-        const int64_t idx = j - lane;
-        unsigned long long v = LB_PREFIX; // tiles before 0 do not exist: tile 0 always ends the walk itself
-        if (idx >= 0) {
-            do {
-                v = *((volatile unsigned long long *)&status[idx]);
-            } while ((v >> 62) == 0);
-        }
-        const unsigned pm = __ballot_sync(0xffffffffu, (v & LB_PREFIX) != 0);
-        uint64_t val = v & LB_VAL;
-        if (pm) {
-            const int first = __ffs(pm) - 1; // nearest predecessor that already knows its inclusive prefix
-            if ((int)lane > first || idx < 0) val = 0;
-            for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
-            acc += val;
-            break;
-        }
-        for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
-        acc += val;
-        j -= 32;
-    }
-    if (lane == 0) atomicExch(&status[tile], LB_PREFIX | (acc + total));
-    return acc;
 }
 
 // ---------------------------------------------------------------------------------------------------------

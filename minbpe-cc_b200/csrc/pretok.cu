@@ -1,0 +1,582 @@
+// pretok.cu -- GPU pre-tokeniser for the GPT-4 split pattern and GPU chunk dedup: the two host stages
+// in front of the merge loop (Tokenizer.h:500-544 regex split; chunk -> count) moved next to it, so that
+// text -> chunks -> unique chunks -> merge loop never leaves HBM.
+//
+//   k_pretok_mark     one thread per 32-byte window of text runs pretok_window() (pretok_core.cuh) and sets one bit per
+//                     chunk start in a bitmap (1 bit per text byte). Windows are independent; overlap is idempotent.
+//   k_bits_compact    bitmap -> ascending list of set-bit positions (= chunk offsets), single pass: popc per word,
+//                     block scan, decoupled look-back for the tile base, positions staged in shared memory and stored
+//                     as whole lines. Used twice: chunk starts, and first occurrences of unique chunks.
+//   k_dedup_insert    every chunk into an open-addressed table keyed by its bytes (compared against the
+//                     representative's bytes in the text itself): slot = {tag | smallest chunk index, count}.
+//   k_dedup_first     table -> bitmap over chunk indices (bit c = chunk c is the first occurrence of its bytes).
+//   k_dedup_emit      unique chunks in first-appearance order: weight, length; then token offsets (scan) and the
+//                     bytes widened to u32 -- the trainer's input layout (train_cuda.cu), written in place on the GPU.
+// Texts the matcher cannot take (malformed UTF-8, or a stretch without letters/blanks longer than the crawl limit)
+// come back as MBPE_E_UNSUPPORTED and the caller uses the PCRE2 path.
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "lookback.cuh"
+#include "pretok_core.cuh"
+
+namespace mbpe {
+
+struct DevText {
+    const uint8_t *p;
+    __device__ __forceinline__ uint8_t operator[](uint64_t i) const { return __ldg(p + i); }
+};
+
+constexpr int PM_THREADS = 256;
+constexpr uint32_t PT_WINDOW = 32; // bytes per thread = one bitmap word
+
+__global__ void __launch_bounds__(PM_THREADS) k_pretok_mark(const uint8_t *text, uint64_t len, const uint8_t *table,
+                                                             uint32_t *bitmap, uint32_t *err, uint64_t max_crawl) {
+    const uint64_t n_win = (len + PT_WINDOW - 1) / PT_WINDOW;
+    PretokIn<DevText> in{DevText{text}, len, table, err};
+    for (uint64_t w = blockIdx.x * (uint64_t)PM_THREADS + threadIdx.x; w < n_win; w += (uint64_t)gridDim.x * PM_THREADS) {
+        uint64_t cur = ~0ull;
+        uint32_t bits = 0;
+        pretok_window(in, w * PT_WINDOW, (w + 1) * PT_WINDOW, max_crawl, [&](uint64_t p) {
+            const uint64_t wi = p >> 5;
+            if (wi != cur) {
+                if (bits) atomicOr(&bitmap[cur], bits);
+                cur = wi;
+                bits = 0;
+            }
+            bits |= 1u << (p & 31);
+        });
+        if (bits) atomicOr(&bitmap[cur], bits);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// bitmap -> positions
+// ---------------------------------------------------------------------------------------------------------
+constexpr int BC_THREADS = 256, BC_WPT = 4, BC_WORDS = BC_THREADS * BC_WPT; // 1024 words = 32 Ki bits per tile
+constexpr uint32_t BC_STAGE = 12288;                                        // positions staged per tile (48 KB)
+
+struct BcSmem {
+    uint32_t stage[BC_STAGE];
+    uint32_t warp_sum[BC_THREADS / 32];
+    uint32_t tile;
+    unsigned long long base;
+};
+
+// out[k] = position of the k-th set bit (k counted over the whole bitmap); *n_out = number of set bits. Positions
+// are 32-bit (bitmaps cover < 2^32 bits).
+__global__ void __launch_bounds__(BC_THREADS) k_bits_compact(const uint32_t *bitmap, uint64_t n_words, uint32_t *out,
+                                                              uint64_t out_cap, unsigned long long *status, uint32_t *ticket,
+                                                              uint32_t n_tiles, unsigned long long *n_out, uint32_t *overflow) {
+    extern __shared__ __align__(16) unsigned char bc_raw[];
+    BcSmem &sm = *reinterpret_cast<BcSmem *>(bc_raw);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = sm.tile;
+        if (tile >= n_tiles) return;
+        const uint64_t w0 = (uint64_t)tile * BC_WORDS + (uint64_t)tid * BC_WPT;
+        uint32_t w[BC_WPT];
+        if (w0 + BC_WPT <= n_words) {
+            const uint4 q = __ldcs(reinterpret_cast<const uint4 *>(bitmap + w0));
+            w[0] = q.x, w[1] = q.y, w[2] = q.z, w[3] = q.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < BC_WPT; j++) w[j] = w0 + j < n_words ? __ldcs(bitmap + w0 + j) : 0u;
+        }
+        uint32_t sum = 0;
+#pragma unroll
+        for (int j = 0; j < BC_WPT; j++) sum += __popc(w[j]);
+        uint32_t incl = sum;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (lane == 31) sm.warp_sum[warp] = incl;
+        __syncthreads();
+        uint32_t warp_base = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < BC_THREADS / 32; k++) {
+            const uint32_t v = sm.warp_sum[k];
+            if (k < (int)warp) warp_base += v;
+            total += v;
+        }
+        if (warp == 0) {
+            const uint64_t b = lookback_base(status, tile, total);
+            if (lane == 0) sm.base = b;
+        }
+        __syncthreads();
+        const uint64_t base = sm.base;
+        const bool fits = base + total <= out_cap;
+        if (!fits && tid == 0) *overflow = 1;
+        const bool via_smem = total <= BC_STAGE;
+        uint32_t loc = warp_base + (incl - sum);
+        if (fits) {
+#pragma unroll
+            for (int j = 0; j < BC_WPT; j++) {
+                uint32_t bits = w[j];
+                const uint32_t pos0 = (uint32_t)((w0 + j) << 5);
+                while (bits) {
+                    const uint32_t b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    if (via_smem)
+                        sm.stage[loc] = pos0 + b;
+                    else
+                        out[base + loc] = pos0 + b;
+                    loc++;
+                }
+            }
+            if (via_smem) {
+                __syncthreads();
+                for (uint32_t i = tid; i < total; i += BC_THREADS) __stcs(&out[base + i], sm.stage[i]);
+            }
+        }
+        if (tile == n_tiles - 1 && tid == 0) *n_out = base + total;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// chunk dedup: unique chunk -> count, unique chunks in first-appearance order (host twin: chunker.cpp)
+// ---------------------------------------------------------------------------------------------------------
+constexpr unsigned long long DD_EMPTY = ~0ull;
+constexpr uint32_t DD_MAX_PROBES = 1u << 14;
+
+struct DedupArgs {
+    const uint8_t *text;
+    const uint32_t *off; // n_chunks + 1
+    uint64_t n_chunks;
+    unsigned long long *words; // slot: tag(31) << 32 | smallest chunk index with these bytes; DD_EMPTY = free
+    uint32_t *counts;          // slot: occurrences
+    uint32_t mask;
+    uint32_t *used;     // claimed slots
+    uint32_t *overflow; // probe limit hit: table too small
+};
+
+__device__ __forceinline__ uint64_t dd_hash(const uint8_t *text, uint32_t o, uint32_t len) {
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ len;
+    uint32_t i = 0;
+    for (; i + 8 <= len; i += 8) {
+        uint64_t v = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) v |= (uint64_t)__ldg(text + o + i + q) << (8 * q);
+        h = (h ^ v) * 0xff51afd7ed558ccdULL;
+        h ^= h >> 29;
+    }
+    uint64_t v = 0;
+    for (uint32_t q = 0; i + q < len; q++) v |= (uint64_t)__ldg(text + o + i + q) << (8 * q);
+    h = (h ^ v) * 0xc4ceb9fe1a85ec53ULL;
+    h ^= h >> 32;
+    h *= 0xff51afd7ed558ccdULL;
+    h ^= h >> 29;
+    return h;
+}
+
+__device__ __forceinline__ bool dd_equal(const DedupArgs &a, uint32_t o, uint32_t len, uint32_t rep) {
+    const uint32_t ro = __ldg(a.off + rep);
+    if (__ldg(a.off + rep + 1) - ro != len) return false;
+    for (uint32_t i = 0; i < len; i++)
+        if (__ldg(a.text + o + i) != __ldg(a.text + ro + i)) return false;
+    return true;
+}
+
+__global__ void __launch_bounds__(256) k_dedup_insert(const DedupArgs a) {
+    for (uint64_t c = blockIdx.x * 256ull + threadIdx.x; c < a.n_chunks; c += (uint64_t)gridDim.x * 256) {
+        const uint32_t o = __ldg(a.off + c), len = __ldg(a.off + c + 1) - o;
+        const uint64_t h = dd_hash(a.text, o, len);
+        const unsigned long long mine = ((h >> 33) << 32) | (uint32_t)c;
+        uint32_t s = (uint32_t)h & a.mask;
+        for (uint32_t probes = 0;; probes++) {
+            if (probes > DD_MAX_PROBES) {
+                *a.overflow = 1;
+                break;
+            }
+            unsigned long long w = *((volatile unsigned long long *)&a.words[s]);
+            if (w == DD_EMPTY) {
+                w = atomicCAS(&a.words[s], DD_EMPTY, mine);
+                if (w == DD_EMPTY) {
+                    atomicAdd(a.used, 1u);
+                    atomicAdd(&a.counts[s], 1u);
+                    break;
+                }
+            }
+            if ((w >> 32) == (mine >> 32)) {
+                const uint32_t rep = (uint32_t)w;
+                if (rep == (uint32_t)c || dd_equal(a, o, len, rep)) {
+                    if ((uint32_t)c < rep) atomicMin(&a.words[s], mine); // keep the FIRST occurrence as representative
+                    atomicAdd(&a.counts[s], 1u);
+                    break;
+                }
+            }
+            s = (s + 1) & a.mask;
+        }
+    }
+}
+
+// bit c of `first` = chunk c is the first occurrence of its bytes
+__global__ void k_dedup_first(const unsigned long long *words, uint64_t n_slots, uint32_t *first) {
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < n_slots; s += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long w = words[s];
+        if (w != DD_EMPTY) atomicOr(&first[(uint32_t)w >> 5], 1u << ((uint32_t)w & 31));
+    }
+}
+
+// unique u = chunk first_idx[u]: weight, and its place in the token stream (exclusive scan of the lengths)
+constexpr int DE_THREADS = 256;
+__global__ void __launch_bounds__(DE_THREADS) k_dedup_emit(const DedupArgs a, const uint32_t *first_idx, uint32_t n_unique,
+                                                            uint32_t *weight, unsigned long long *tok_off,
+                                                            unsigned long long *status, uint32_t *ticket, uint32_t n_tiles) {
+    __shared__ uint32_t warp_sum[DE_THREADS / 32];
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_base;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= n_tiles) return;
+        const uint32_t u = tile * DE_THREADS + tid;
+        uint32_t len = 0;
+        if (u < n_unique) {
+            const uint32_t c = __ldg(first_idx + u);
+            const uint32_t o = __ldg(a.off + c);
+            len = __ldg(a.off + c + 1) - o;
+            const uint64_t h = dd_hash(a.text, o, len);
+            uint32_t s = (uint32_t)h & a.mask;
+            while ((uint32_t)a.words[s] != c || a.words[s] == DD_EMPTY) s = (s + 1) & a.mask; // the slot this chunk represents
+            weight[u] = a.counts[s];
+        }
+        uint32_t incl = len;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (lane == 31) warp_sum[warp] = incl;
+        __syncthreads();
+        uint32_t warp_base = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < DE_THREADS / 32; k++) {
+            const uint32_t v = warp_sum[k];
+            if (k < (int)warp) warp_base += v;
+            total += v;
+        }
+        if (warp == 0) {
+            const uint64_t b = lookback_base(status, tile, total);
+            if (lane == 0) s_base = b;
+        }
+        __syncthreads();
+        if (u < n_unique) tok_off[u] = s_base + warp_base + (incl - len);
+        if (tile == n_tiles - 1 && tid == 0) tok_off[n_unique] = s_base + total;
+    }
+}
+
+// bytes of the unique chunks widened to u32 tokens (Tokenizer.h:85-100), one warp per chunk
+__global__ void __launch_bounds__(256) k_dedup_tokens(const uint8_t *text, const uint32_t *off, const uint32_t *first_idx,
+                                                       uint32_t n_unique, const unsigned long long *tok_off, uint32_t *tokens) {
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint64_t u = (blockIdx.x * 256ull + threadIdx.x) >> 5; u < n_unique; u += ((uint64_t)gridDim.x * 256) >> 5) {
+        const uint32_t c = __ldg(first_idx + u), o = __ldg(off + c), len = __ldg(off + c + 1) - o;
+        const unsigned long long t0 = tok_off[u];
+        for (uint32_t i = lane; i < len; i += 32) tokens[t0 + i] = __ldg(text + o + i);
+    }
+}
+
+} // namespace mbpe
+
+using namespace mbpe;
+
+struct mbpe_pretok {
+    int device = 0, sms = 148;
+    uint8_t *d_table = nullptr;
+    uint32_t *d_bitmap = nullptr; // 1 bit per text byte
+    uint64_t bitmap_words = 0;
+    unsigned long long *d_status = nullptr;
+    uint64_t status_cap = 0;
+    uint32_t *d_small = nullptr;          // [0] err, [1] ticket, [2] overflow
+    unsigned long long *d_count = nullptr; // set-bit count
+    uint64_t max_crawl = 1u << 16;
+    uint64_t launches = 0;
+};
+
+extern "C" int mbpe_pretok_create(int device, mbpe_pretok **out) {
+    if (!out) return set_error(MBPE_E_INVALID, "null argument");
+    *out = nullptr;
+    std::vector<uint8_t> table(PT_TABLE_BYTES);
+    int rc = mbpe_pretok_class_table(table.data());
+    if (rc) return rc;
+    if ((rc = use_device(device))) return rc;
+    mbpe_pretok *p = new mbpe_pretok();
+    p->device = device;
+    p->sms = sm_count(device);
+    if (const char *mc = getenv("MBPE_PRETOK_MAX_CRAWL")) p->max_crawl = strtoull(mc, nullptr, 10);
+    MB_CUDA(cudaMalloc(&p->d_table, PT_TABLE_BYTES));
+    MB_CUDA(cudaMemcpy(p->d_table, table.data(), PT_TABLE_BYTES, cudaMemcpyHostToDevice));
+    MB_CUDA(cudaMalloc(&p->d_small, 16));
+    MB_CUDA(cudaMalloc(&p->d_count, 8));
+    MB_CUDA(cudaFuncSetAttribute(k_bits_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BcSmem)));
+    *out = p;
+    return MBPE_OK;
+}
+
+extern "C" void mbpe_pretok_destroy(mbpe_pretok *p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    cudaFree(p->d_table);
+    cudaFree(p->d_bitmap);
+    cudaFree(p->d_status);
+    cudaFree(p->d_small);
+    cudaFree(p->d_count);
+    delete p;
+}
+
+namespace mbpe {
+// positions of the set bits of bitmap[0 .. n_words) into d_out (ascending); count left in p->d_count
+int bits_compact(mbpe_pretok *p, const uint32_t *d_bitmap, uint64_t n_words, uint32_t *d_out, uint64_t out_cap, cudaStream_t st) {
+    const uint64_t n_tiles = (n_words + BC_WORDS - 1) / BC_WORDS;
+    if (n_tiles + 1 > p->status_cap) {
+        cudaFree(p->d_status);
+        p->status_cap = n_tiles + n_tiles / 4 + 64;
+        MB_CUDA(cudaMalloc(&p->d_status, p->status_cap * 8));
+    }
+    MB_CUDA(cudaMemsetAsync(p->d_status, 0, std::max<uint64_t>(n_tiles, 1) * 8, st));
+    MB_CUDA(cudaMemsetAsync(p->d_small + 1, 0, 8, st)); // ticket, overflow
+    MB_CUDA(cudaMemsetAsync(p->d_count, 0, 8, st));
+    if (n_tiles == 0) return MBPE_OK;
+    const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)p->sms * 4);
+    k_bits_compact<<<grid, BC_THREADS, sizeof(BcSmem), st>>>(d_bitmap, n_words, d_out, out_cap, p->d_status, p->d_small + 1,
+                                                            (uint32_t)n_tiles, p->d_count, p->d_small + 2);
+    p->launches++;
+    MB_CUDA(cudaGetLastError());
+    return MBPE_OK;
+}
+} // namespace mbpe
+
+// d_off_out: u32[off_cap]; on success holds n_chunks + 1 offsets (the last one = len)
+extern "C" int mbpe_pretok_split_device(mbpe_pretok *p, const uint8_t *d_text, uint64_t len, uint32_t *d_off_out,
+                                        uint64_t off_cap, uint64_t *n_chunks, void *stream) {
+    if (!p || !n_chunks || !d_off_out || (len && !d_text)) return set_error(MBPE_E_INVALID, "null argument");
+    if (len >= (1ull << 32) - 64) return set_error(MBPE_E_INVALID, "a device batch must be < 4 GiB of text");
+    int rc = use_device(p->device);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    *n_chunks = 0;
+    if (off_cap < 1) return set_error(MBPE_E_CAPACITY, "offset buffer too small");
+    if (len == 0) {
+        MB_CUDA(cudaMemsetAsync(d_off_out, 0, 4, st));
+        MB_CUDA(cudaStreamSynchronize(st));
+        return MBPE_OK;
+    }
+    const uint64_t n_words = (len + 31) / 32;
+    if (n_words > p->bitmap_words) {
+        cudaFree(p->d_bitmap);
+        p->bitmap_words = n_words + n_words / 8 + 1024;
+        MB_CUDA(cudaMalloc(&p->d_bitmap, p->bitmap_words * 4));
+    }
+    MB_CUDA(cudaMemsetAsync(p->d_bitmap, 0, n_words * 4, st));
+    MB_CUDA(cudaMemsetAsync(p->d_small, 0, 16, st));
+    const unsigned grid = (unsigned)std::min<uint64_t>((n_words + PM_THREADS - 1) / PM_THREADS, (uint64_t)p->sms * 32);
+    k_pretok_mark<<<grid, PM_THREADS, 0, st>>>(d_text, len, p->d_table, p->d_bitmap, p->d_small, p->max_crawl);
+    p->launches++;
+    MB_CUDA(cudaGetLastError());
+    if ((rc = bits_compact(p, p->d_bitmap, n_words, d_off_out, off_cap - 1, st))) return rc;
+    uint32_t small[4];
+    unsigned long long count = 0;
+    MB_CUDA(cudaMemcpyAsync(small, p->d_small, 16, cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaMemcpyAsync(&count, p->d_count, 8, cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaStreamSynchronize(st));
+    if (small[0] & PT_ERR_UTF8) return set_error(MBPE_E_UNSUPPORTED, "text is not well-formed UTF-8: use the PCRE2 path");
+    if (small[0] & PT_ERR_LONG)
+        return set_error(MBPE_E_UNSUPPORTED, "a stretch without letters or blanks exceeds the crawl limit: use the PCRE2 path");
+    if (small[2]) {
+        *n_chunks = count;
+        return set_error(MBPE_E_CAPACITY, "offset buffer too small");
+    }
+    const uint32_t end = (uint32_t)len;
+    MB_CUDA(cudaMemcpyAsync(d_off_out + count, &end, 4, cudaMemcpyHostToDevice, st));
+    MB_CUDA(cudaStreamSynchronize(st));
+    *n_chunks = count;
+    return MBPE_OK;
+}
+
+// host text in, host offsets out: the GPU counterpart of mbpe_split for the GPT-4 pattern
+extern "C" int mbpe_pretok_split(mbpe_pretok *p, const uint8_t *text, uint64_t len, uint64_t *off_out, uint64_t off_cap,
+                                 uint64_t *n_chunks) {
+    if (!p || !n_chunks || (len && !text)) return set_error(MBPE_E_INVALID, "null argument");
+    int rc = use_device(p->device);
+    if (rc) return rc;
+    uint8_t *d_text = nullptr;
+    uint32_t *d_off = nullptr;
+    const uint64_t cap = len + 2;
+    MB_CUDA(cudaMalloc(&d_text, std::max<uint64_t>(len, 1)));
+    if (cudaMalloc(&d_off, cap * 4) != cudaSuccess) {
+        cudaFree(d_text);
+        return set_error(MBPE_E_CUDA, "out of device memory");
+    }
+    cudaError_t ce = cudaMemcpy(d_text, text, len, cudaMemcpyHostToDevice);
+    rc = ce == cudaSuccess ? mbpe_pretok_split_device(p, d_text, len, d_off, cap, n_chunks, nullptr)
+                           : cuda_fail(ce, "H2D text", __FILE__, __LINE__);
+    if (rc == MBPE_OK && off_out) {
+        if (*n_chunks + 1 > off_cap) {
+            rc = set_error(MBPE_E_CAPACITY, "off_out too small");
+        } else {
+            std::vector<uint32_t> h(*n_chunks + 1);
+            ce = cudaMemcpy(h.data(), d_off, h.size() * 4, cudaMemcpyDeviceToHost);
+            if (ce != cudaSuccess) rc = cuda_fail(ce, "D2H offsets", __FILE__, __LINE__);
+            for (size_t i = 0; i < h.size(); i++) off_out[i] = h[i];
+        }
+    }
+    cudaFree(d_text);
+    cudaFree(d_off);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// C ABI: dedup of resident chunks, device corpus
+// ---------------------------------------------------------------------------------------------------------
+extern "C" void mbpe_device_corpus_free(mbpe_device_corpus *c) {
+    if (!c) return;
+    cudaFree(c->d_tokens);
+    cudaFree(c->d_off);
+    cudaFree(c->d_weight);
+    memset(c, 0, sizeof *c);
+}
+
+extern "C" int mbpe_pretok_dedup_device(mbpe_pretok *p, const uint8_t *d_text, uint64_t len, const uint32_t *d_off,
+                                        uint64_t n_chunks, mbpe_device_corpus *out, void *stream) {
+    if (!p || !out || !d_off || (len && !d_text)) return set_error(MBPE_E_INVALID, "null argument");
+    if (n_chunks >= (1ull << 32) - 64) return set_error(MBPE_E_INVALID, "too many chunks for one device batch");
+    int rc = use_device(p->device);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    memset(out, 0, sizeof *out);
+    out->n_chunks = n_chunks;
+    out->device = p->device;
+    if (n_chunks == 0) {
+        MB_CUDA(cudaMalloc(&out->d_tokens, 4));
+        MB_CUDA(cudaMalloc(&out->d_off, 8));
+        MB_CUDA(cudaMalloc(&out->d_weight, 4));
+        MB_CUDA(cudaMemset(out->d_off, 0, 8));
+        return MBPE_OK;
+    }
+    uint64_t slots = 1u << 16;
+    while (slots < n_chunks / 16 && slots < (1ull << 27)) slots <<= 1;
+    unsigned long long *d_words = nullptr;
+    uint32_t *d_counts = nullptr, *d_first = nullptr, *d_first_idx = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_words);
+        cudaFree(d_counts);
+        cudaFree(d_first);
+        cudaFree(d_first_idx);
+    };
+    uint32_t used = 0;
+    DedupArgs a{};
+    for (;;) {
+        MB_CUDA(cudaMalloc(&d_words, slots * 8));
+        MB_CUDA(cudaMalloc(&d_counts, slots * 4));
+        MB_CUDA(cudaMemsetAsync(d_words, 0xFF, slots * 8, st));
+        MB_CUDA(cudaMemsetAsync(d_counts, 0, slots * 4, st));
+        MB_CUDA(cudaMemsetAsync(p->d_small, 0, 16, st));
+        a = DedupArgs{d_text, d_off, n_chunks, d_words, d_counts, (uint32_t)(slots - 1), p->d_small + 3, p->d_small + 2};
+        const unsigned grid = (unsigned)std::min<uint64_t>((n_chunks + 255) / 256, (uint64_t)p->sms * 16);
+        k_dedup_insert<<<grid, 256, 0, st>>>(a);
+        p->launches++;
+        uint32_t small[4];
+        MB_CUDA(cudaMemcpyAsync(small, p->d_small, 16, cudaMemcpyDeviceToHost, st));
+        MB_CUDA(cudaStreamSynchronize(st));
+        used = small[3];
+        if (!small[2] && (uint64_t)used * 2 <= slots) break;
+        cudaFree(d_words);
+        cudaFree(d_counts);
+        d_words = nullptr;
+        d_counts = nullptr;
+        if (slots >= (1ull << 31)) return set_error(MBPE_E_CUDA, "dedup table cannot grow further");
+        slots <<= 2; // too full for short probe chains: redo in a larger table
+    }
+    const uint64_t first_words = (n_chunks + 31) / 32;
+    if (cudaMalloc(&d_first, first_words * 4) != cudaSuccess || cudaMalloc(&d_first_idx, ((uint64_t)used + 1) * 4) != cudaSuccess) {
+        cleanup();
+        return set_error(MBPE_E_CUDA, "out of device memory");
+    }
+    MB_CUDA(cudaMemsetAsync(d_first, 0, first_words * 4, st));
+    k_dedup_first<<<(unsigned)std::min<uint64_t>((slots + 255) / 256, (uint64_t)p->sms * 16), 256, 0, st>>>(d_words, slots, d_first);
+    p->launches++;
+    if ((rc = bits_compact(p, d_first, first_words, d_first_idx, used, st))) {
+        cleanup();
+        return rc;
+    }
+    out->n_unique = used;
+    if (cudaMalloc(&out->d_off, ((uint64_t)used + 1) * 8) != cudaSuccess || cudaMalloc(&out->d_weight, (uint64_t)used * 4) != cudaSuccess) {
+        cleanup();
+        mbpe_device_corpus_free(out);
+        return set_error(MBPE_E_CUDA, "out of device memory");
+    }
+    const uint32_t n_tiles = (used + DE_THREADS - 1) / DE_THREADS;
+    if ((uint64_t)n_tiles + 1 > p->status_cap) {
+        cudaFree(p->d_status);
+        p->status_cap = n_tiles + 64;
+        MB_CUDA(cudaMalloc(&p->d_status, p->status_cap * 8));
+    }
+    MB_CUDA(cudaMemsetAsync(p->d_status, 0, (uint64_t)n_tiles * 8, st));
+    MB_CUDA(cudaMemsetAsync(p->d_small + 1, 0, 4, st));
+    k_dedup_emit<<<std::min<unsigned>(n_tiles, p->sms * 4), DE_THREADS, 0, st>>>(
+        a, d_first_idx, used, out->d_weight, (unsigned long long *)out->d_off, p->d_status, p->d_small + 1, n_tiles);
+    p->launches++;
+    unsigned long long n_tokens = 0;
+    MB_CUDA(cudaMemcpyAsync(&n_tokens, out->d_off + used, 8, cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaStreamSynchronize(st));
+    out->n_tokens = n_tokens;
+    if (cudaMalloc(&out->d_tokens, std::max<uint64_t>(n_tokens, 1) * 4) != cudaSuccess) {
+        cleanup();
+        mbpe_device_corpus_free(out);
+        return set_error(MBPE_E_CUDA, "out of device memory");
+    }
+    k_dedup_tokens<<<std::min<unsigned>((used + 7) / 8, p->sms * 16), 256, 0, st>>>(
+        d_text, d_off, d_first_idx, used, (const unsigned long long *)out->d_off, out->d_tokens);
+    p->launches++;
+    cudaError_t ce = cudaStreamSynchronize(st);
+    cleanup();
+    if (ce != cudaSuccess) {
+        mbpe_device_corpus_free(out);
+        return cuda_fail(ce, "dedup kernels", __FILE__, __LINE__);
+    }
+    return MBPE_OK;
+}
+
+extern "C" int mbpe_device_corpus_download(const mbpe_device_corpus *c, uint32_t *tokens, uint64_t *off, uint32_t *weight) {
+    if (!c) return set_error(MBPE_E_INVALID, "null argument");
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    if (tokens) MB_CUDA(cudaMemcpy(tokens, c->d_tokens, c->n_tokens * 4, cudaMemcpyDeviceToHost));
+    if (off) MB_CUDA(cudaMemcpy(off, c->d_off, (c->n_unique + 1) * 8, cudaMemcpyDeviceToHost));
+    if (weight) MB_CUDA(cudaMemcpy(weight, c->d_weight, c->n_unique * 4, cudaMemcpyDeviceToHost));
+    return MBPE_OK;
+}
+
+// text in host memory -> unique chunks resident on the device (split + dedup), the front end of Tokenizer::train
+extern "C" int mbpe_pretok_corpus(mbpe_pretok *p, const uint8_t *text, uint64_t len, mbpe_device_corpus *out) {
+    if (!p || !out || (len && !text)) return set_error(MBPE_E_INVALID, "null argument");
+    int rc = use_device(p->device);
+    if (rc) return rc;
+    uint8_t *d_text = nullptr;
+    uint32_t *d_off = nullptr;
+    const uint64_t cap = len + 2;
+    MB_CUDA(cudaMalloc(&d_text, std::max<uint64_t>(len, 1)));
+    if (cudaMalloc(&d_off, cap * 4) != cudaSuccess) {
+        cudaFree(d_text);
+        return set_error(MBPE_E_CUDA, "out of device memory");
+    }
+    uint64_t n_chunks = 0;
+    cudaError_t ce = cudaMemcpy(d_text, text, len, cudaMemcpyHostToDevice);
+    rc = ce == cudaSuccess ? mbpe_pretok_split_device(p, d_text, len, d_off, cap, &n_chunks, nullptr)
+                           : cuda_fail(ce, "H2D text", __FILE__, __LINE__);
+    if (rc == MBPE_OK) rc = mbpe_pretok_dedup_device(p, d_text, len, d_off, n_chunks, out, nullptr);
+    cudaFree(d_text);
+    cudaFree(d_off);
+    return rc;
+}

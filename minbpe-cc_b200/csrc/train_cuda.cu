@@ -595,6 +595,33 @@ extern "C" int mbpe_trainer_create(const uint32_t *tokens, uint64_t n_tokens, co
     return MBPE_OK;
 }
 
+extern "C" int mbpe_trainer_create_device(const mbpe_device_corpus *c, mbpe_trainer **out) {
+    if (!out || !c || !c->d_off) return set_error(MBPE_E_INVALID, "null argument");
+    *out = nullptr;
+    if (c->n_tokens >= (1ull << 30)) return set_error(MBPE_E_INVALID, "n_tokens must be < 2^30 per trainer");
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    mbpe_trainer *t = new mbpe_trainer();
+    t->device = c->device;
+    t->n_tokens = c->n_tokens;
+    t->n_chunks = c->n_unique;
+    MB_CUDA(cudaMalloc(&t->d_tokens, std::max<uint64_t>(c->n_tokens, 1) * 4));
+    MB_CUDA(cudaMalloc(&t->d_off, (c->n_unique + 1) * 8));
+    MB_CUDA(cudaMalloc(&t->d_weight, std::max<uint64_t>(c->n_unique, 1) * 4));
+    MB_CUDA(cudaMemcpy(t->d_tokens, c->d_tokens, c->n_tokens * 4, cudaMemcpyDeviceToDevice));
+    MB_CUDA(cudaMemcpy(t->d_off, c->d_off, (c->n_unique + 1) * 8, cudaMemcpyDeviceToDevice));
+    MB_CUDA(cudaMemcpy(t->d_weight, c->d_weight, c->n_unique * 4, cudaMemcpyDeviceToDevice));
+    MB_CUDA(cudaMallocHost(&t->pinned_ctl, sizeof(Ctl)));
+    for (auto &e : t->ev) MB_CUDA(cudaEventCreate(&e));
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    *out = t;
+    return MBPE_OK;
+}
+
 extern "C" void mbpe_trainer_destroy(mbpe_trainer *t) {
     if (!t) return;
     cudaSetDevice(t->device);

@@ -121,3 +121,74 @@ def test_invalid_utf8_and_pathological_runs_are_reported(emu):
     assert err & 2
     _, err = emu(b"a " + b"7" * 500 + b" b", 32, max_crawl=1024)
     assert err == 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU tier: the same matcher as a kernel, through the C ABI, against PCRE2 (mbpe_split) and the host dedup
+# ---------------------------------------------------------------------------------------------------------
+def _texts(pkg):
+    ts = [open(os.path.join(ROOT, "tests", "golden", "data", n), "rb").read() for n in ("taylorswift.txt", "shakespeare.txt")]
+    ts.append(pkg.synth_corpus(0x5EED0001, 8 << 20).tobytes())
+    rng = np.random.default_rng(5)
+    ts.append("".join(ALPHABET[i] for i in rng.integers(0, len(ALPHABET), 200000)).encode())
+    return ts
+
+
+@pytest.mark.gpu
+def test_gpu_split_matches_pcre2(pkg):
+    pt = pkg.Pretok()
+    for text in _texts(pkg) + [b"", b"a", b" ", b"'s", b"\n\n", " a".encode()]:
+        s, e = pkg.split(pkg.patterns()["gpt4"], text, 0)
+        want = np.concatenate([s, [len(text)]]).astype(np.uint64) if len(s) else np.asarray([len(text)], np.uint64)
+        got = pt.split(text)
+        assert np.array_equal(got, want), (len(text), len(got), len(want))
+    pt.close()
+
+
+@pytest.mark.gpu
+def test_gpu_split_refuses_what_it_cannot_take(pkg):
+    pt = pkg.Pretok()
+    for bad in [b"abc \xff def" * 100, b"x" * 70 + b"\xe4\xb8"]:
+        with pytest.raises(pkg.MbpeError) as ei:
+            pt.split(bad)
+        assert ei.value.code == -8
+    os.environ["MBPE_PRETOK_MAX_CRAWL"] = "1024"
+    try:
+        pt2 = pkg.Pretok()
+        with pytest.raises(pkg.MbpeError) as ei:
+            pt2.split(b"a " + b"7" * 100000 + b" b")
+        assert ei.value.code == -8
+        pt2.close()
+    finally:
+        del os.environ["MBPE_PRETOK_MAX_CRAWL"]
+    assert len(pt.split(b"a " + b"7" * 3000 + b" b")) == 1 + 1000 + 2 + 1  # default limit takes it: a, 1000 x 777, ' b'... + end
+    pt.close()
+
+
+@pytest.mark.gpu
+def test_gpu_dedup_matches_host(pkg):
+    pt = pkg.Pretok()
+    for text in _texts(pkg) + [b"", b"aaaa", b"a a a a b b a"]:
+        tok, off, w, n_chunks = pkg.split_dedup(pkg.patterns()["gpt4"], text)
+        c = pt.corpus(text)
+        assert (c.n_chunks, c.n_unique, c.n_tokens) == (n_chunks, len(w), len(tok))
+        gt, go, gw = c.download()
+        assert np.array_equal(go, off) and np.array_equal(gw, w) and np.array_equal(gt, tok)
+        c.free()
+    pt.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["lexical", "first"])
+def test_gpu_corpus_trains_to_the_same_merges(pkg, mode):
+    text = pkg.synth_corpus(0x5EED0001, 4 << 20).tobytes()
+    tok, off, w, _ = pkg.split_dedup(pkg.patterns()["gpt4"], text)
+    want, wc, _ = pkg.train(tok, off, w, 1024, mode)
+    pt = pkg.Pretok()
+    c = pt.corpus(text)
+    t = c.trainer()
+    c.free()
+    got, gc, _ = t.run(1024, mode)
+    t.close()
+    pt.close()
+    assert np.array_equal(got, want) and np.array_equal(gc, wc)
