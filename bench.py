@@ -292,21 +292,39 @@ def main():
     # ---------------- e2e: reference-facing call, HOST text in -> merges out -----------------------------
     tk = pkg.Tokenizer(pkg.patterns()["gpt4"], device=local_rank)
     tk.set_engine(a.engine)
+    text_pinned = torch.empty(len(text), dtype=torch.uint8, pin_memory=True)  # the step's input, in pinned host memory
+    text_pinned.numpy()[:] = text
     e2e_times = []
     t_budget = time.time()
-    for i in range(max(1, a.steps)):
+    for i in range(1 + max(1, a.steps)):  # the first call is a warm-up: it sizes the tokenizer's resident device buffers
         barrier()
         t0 = time.time()
-        tk.train(tb, a.vocab, a.mode)
+        tk.train(text_pinned.numpy(), a.vocab, a.mode)
         torch.cuda.synchronize()
-        e2e_times.append(time.time() - t0)
-        if time.time() - t_budget > a.e2e_budget_s:
+        if i:
+            e2e_times.append(time.time() - t0)
+        if time.time() - t_budget > a.e2e_budget_s and e2e_times:
             break
     e2e_s = max_over_ranks(sum(e2e_times) / len(e2e_times))
     st2 = tk.last_train_stats()
     assert hashlib.sha256(tk.merges().tobytes()).hexdigest() == model_sha, "tokenizer path and trainer path disagree"
-    h2d = int(st2["n_positions"] * 4 + (st2["n_unique"] + 1) * 8 + st2["n_unique"] * 4)
+    on_gpu = bool(st2.get("split_on_gpu"))
+    h2d = int(len(tb)) if on_gpu else int(st2["n_positions"] * 4 + (st2["n_unique"] + 1) * 8 + st2["n_unique"] * 4)
     d2h = int(n_done * 12)
+    # the same call with pre-tokenisation kept on the host (PCRE2 on all cores), once, for the record
+    e2e_host_split_s = None
+    if on_gpu and rank == 0:
+        os.environ["MBPE_GPU_SPLIT"] = "0"
+        try:
+            tkh = pkg.Tokenizer(pkg.patterns()["gpt4"], device=local_rank)
+            tkh.set_engine(a.engine)
+            t0 = time.time()
+            tkh.train(tb, a.vocab, a.mode)
+            e2e_host_split_s = time.time() - t0
+            assert hashlib.sha256(tkh.merges().tobytes()).hexdigest() == model_sha, "host-split and device-split models differ"
+            del tkh
+        finally:
+            del os.environ["MBPE_GPU_SPLIT"]
     # the C-ABI hot-path boundary with deduplicated HOST buffers (H2D + merge loop + D2H per step)
     abi_times = []
     for i in range(a.steps):
@@ -322,9 +340,12 @@ def main():
         "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": workload_config(a),
         "e2e": {"value": world * n_done / e2e_s, "unit": "merges/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": len(e2e_times), "wall_s_per_step": e2e_s,
-                "what": "mbpe_tokenizer_train(text) = Tokenizer::train: host regex split + dedup + H2D + GPU merge loop "
-                        "+ D2H, text in host memory",
-                "split_s": st2["split_s"], "dedup_s": st2["dedup_s"], "gpu_ms": st2["gpu_ms"]},
+                "wall_s_steps": [round(t, 4) for t in e2e_times],
+                "what": "mbpe_tokenizer_train(text) = Tokenizer::train, text in pinned host memory: " +
+                        ("H2D text + device split (GPT-4 matcher) + device dedup + merge loop + D2H merges" if on_gpu else
+                         "host regex split + dedup + H2D + merge loop + D2H merges"),
+                "split": "device" if on_gpu else "host", "split_dedup_s": st2["split_s"], "gpu_ms": st2["gpu_ms"],
+                "wall_s_with_host_split": e2e_host_split_s},
         "e2e_abi": {"value": world * n_done / abi_s, "unit": "merges/s", "wall_s_per_step": abi_s,
                     "what": "mbpe_train(deduplicated host buffers): H2D + merge loop + D2H"},
         "gpu_launches": int(launches_train),
@@ -382,21 +403,27 @@ def main():
         # B distinct resident batches of encode_mib each (a device batch is < 4 GiB: u32 boundaries); one timed step =
         # one pass over all of them. --encode-batches 10 --encode-mib 1024 is BASELINE config 4 (10 GiB).
         enc = pkg.Encoder(merges, device=local_rank)
+        pt = pkg.Pretok(device=local_rank)
         batches, t_esplit, n_echunks_total, n_bytes_total = [], 0.0, 0, 0
         for b in range(a.encode_batches):
             etext = pkg.synth_corpus(SEED_ENCODE + 1000 * rank + b, a.encode_mib << 20)
-            etb = etext.tobytes()
+            d_bytes = torch.from_numpy(etext).to(dev)
+            d_off_full = torch.empty(len(etext) + 2, dtype=torch.int32, device=dev)
+            torch.cuda.synchronize()
             t0 = time.time()
-            es, ee = pkg.split(pkg.patterns()["gpt4"], etb)
+            nck = pt.split_device(d_bytes.data_ptr(), len(etext), d_off_full.data_ptr(), len(etext) + 2)  # device matcher
             t_esplit += time.time() - t0
-            eoff64 = np.concatenate([es, ee[-1:]]).astype(np.uint64)
-            batches.append({"n_chunks": len(es), "n_bytes": len(etext),
-                            "d_bytes": torch.from_numpy(etext).to(dev),
-                            "d_off": torch.from_numpy(eoff64.astype(np.uint32).view(np.int32)).to(dev)})
-            n_echunks_total += len(es)
+            d_off = d_off_full[:nck + 1].clone()
+            del d_off_full
+            batches.append({"n_chunks": nck, "n_bytes": len(etext), "d_bytes": d_bytes, "d_off": d_off})
+            n_echunks_total += nck
             n_bytes_total += len(etext)
-            if b + 1 < a.encode_batches:
-                del etext, etb, es, ee, eoff64
+        etb = etext.tobytes()  # the last batch also goes through the host paths below
+        t0 = time.time()
+        es, ee = pkg.split(pkg.patterns()["gpt4"], etb)  # PCRE2 on the host: must give the device matcher's offsets
+        t_host_split = time.time() - t0
+        eoff64 = np.concatenate([es, ee[-1:]]).astype(np.uint64)
+        split_equal = bool(np.array_equal(batches[-1]["d_off"].cpu().numpy().view(np.uint32).astype(np.uint64), eoff64))
         n_echunks = batches[-1]["n_chunks"]
         d_out = torch.empty(a.encode_mib << 20, dtype=torch.int32, device=dev)
         d_n = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -430,12 +457,27 @@ def main():
             torch.cuda.synchronize()
         b_enc = n_bytes_total + 4 * n_echunks_total + 4 * n_ids_total
         etext_len = n_bytes_total
-        # e2e: host buffers through mbpe_encode (H2D + kernels + D2H)
-        t0 = time.time()
-        ids = enc.encode(etb, eoff64)  # the last batch
-        e2e_enc_s = max_over_ranks(time.time() - t0)
+        # e2e: host text in, host ids out through the Tokenizer mirror (H2D + device split + merge scan + D2H)
+        etext_pinned = torch.empty(len(etext), dtype=torch.uint8, pin_memory=True)
+        etext_pinned.numpy()[:] = etext
+        ids_pinned = torch.empty(len(etext), dtype=torch.int32, pin_memory=True)
+        ids_out = ids_pinned.numpy().view(np.uint32)
+        tk.encode(etext_pinned.numpy()[:1 << 20], out=ids_out)  # builds the tokenizer's device tables outside the timed calls
+        tk.encode(etext_pinned.numpy(), out=ids_out)             # and sizes its resident buffers
+        e2e_enc_times = []
+        for i in range(max(1, a.steps)):
+            barrier()
+            t0 = time.time()
+            ids = tk.encode(etext_pinned.numpy(), out=ids_out)  # the last batch: pinned text in, pinned ids out
+            e2e_enc_times.append(time.time() - t0)
+        e2e_enc_s = max_over_ranks(sum(e2e_enc_times) / len(e2e_enc_times))
         ids_dev = d_out[:n_ids].cpu().numpy().view(np.uint32)
         assert np.array_equal(ids, ids_dev)
+        # and the hot-path boundary alone: mbpe_encode(host bytes + host chunk offsets)
+        t0 = time.time()
+        ids_abi = enc.encode(etb, eoff64)
+        e2e_abi_s = max_over_ranks(time.time() - t0)
+        assert np.array_equal(ids_abi, ids_dev)
         # size-independent property at full size: decode(encode(x)) == x
         roundtrip = enc.decode(ids) == etb
         line["encode"] = {
@@ -446,10 +488,15 @@ def main():
             "roofline": {"bound": "hbm", "achieved": b_enc / 1e9 / (ems / 1e3), "peak": peak, "unit": "GB/s",
                          "frac": b_enc / 1e9 / (ems / 1e3) / peak, "traffic": None, "peak_source": peak_src,
                          "kernel": "k_encode_tiles", "algorithmic_bytes_per_step": int(b_enc)},
-            "e2e": {"value": world * len(etext) / 1e6 / e2e_enc_s, "unit": "MB/s", "h2d_bytes_per_step": int(len(etext) + 4 * (n_echunks + 1)),
-                    "bytes": len(etext),
-                    "d2h_bytes_per_step": int(4 * n_ids), "what": "mbpe_encode(host bytes + host chunk offsets)"},
-            "host_split_s": t_esplit, "roundtrip_ok": bool(roundtrip), "ids_sha256": hashlib.sha256(ids.tobytes()).hexdigest(),
+            "e2e": {"value": world * len(etext) / 1e6 / e2e_enc_s, "unit": "MB/s", "h2d_bytes_per_step": int(len(etext)),
+                    "bytes": len(etext), "d2h_bytes_per_step": int(4 * n_ids),
+                    "steps": len(e2e_enc_times),
+                    "what": "mbpe_tokenizer_encode(text) = Tokenizer::encode, text and ids in pinned host memory: H2D text + "
+                            "device split + merge scan + D2H ids"},
+            "e2e_abi": {"value": world * len(etext) / 1e6 / e2e_abi_s, "unit": "MB/s",
+                        "what": "mbpe_encode(host bytes + host chunk offsets): H2D + merge scan + D2H"},
+            "device_split_s": t_esplit, "host_split_s_last_batch": t_host_split, "device_split_equals_pcre2": split_equal,
+            "roundtrip_ok": bool(roundtrip), "ids_sha256": hashlib.sha256(ids.tobytes()).hexdigest(),
             "gpu_launches": 3 * a.steps * a.encode_batches * (1 + (n_echunks >> 22)),
         }
         line["gpu_launches"] += line["encode"]["gpu_launches"]

@@ -182,6 +182,7 @@ int mbpe_tokenizer_decode(mbpe_tokenizer *t, const uint32_t *ids, uint64_t n, ui
 int mbpe_tokenizer_get_merges(mbpe_tokenizer *t, uint32_t *merges_out, uint32_t cap_pairs, uint32_t *n_merges);
 int mbpe_tokenizer_last_train_stats(mbpe_tokenizer *t, mbpe_train_stats *stats, double *split_s, double *dedup_s,
                                     uint64_t *n_chunks, uint64_t *n_unique);
+int mbpe_tokenizer_last_split_on_gpu(mbpe_tokenizer *t); /* 1: the last train() pre-tokenised on the device (section 6) */
 void mbpe_tokenizer_set_engine(mbpe_tokenizer *t, int engine);
 void mbpe_tokenizer_set_threads(mbpe_tokenizer *t, int n_threads); /* host pre-tokenisation threads, 0 = all */
 
@@ -243,10 +244,18 @@ typedef struct mbpe_device_corpus {
 } mbpe_device_corpus;
 int mbpe_pretok_dedup_device(mbpe_pretok *p, const uint8_t *d_text, uint64_t len, const uint32_t *d_off,
                              uint64_t n_chunks, mbpe_device_corpus *out, void *stream);
+/* the same over several resident text segments (each < 4 GiB; a corpus larger than one segment): chunk order =
+ * segment order, so first-appearance order is that of the whole text */
+int mbpe_pretok_dedup_segments(mbpe_pretok *p, const uint8_t *const *d_texts, const uint32_t *const *d_offs,
+                               const uint64_t *seg_chunks, uint32_t n_segs, mbpe_device_corpus *out, void *stream);
 /* host text -> device corpus (H2D + split + dedup): the front end of Tokenizer::train (:500-556) */
 int mbpe_pretok_corpus(mbpe_pretok *p, const uint8_t *text, uint64_t len, mbpe_device_corpus *out);
 int mbpe_device_corpus_download(const mbpe_device_corpus *c, uint32_t *tokens, uint64_t *off, uint32_t *weight);
 void mbpe_device_corpus_free(mbpe_device_corpus *c);
+/* host text -> host ids: GPT-4 split + merge scan on the device, segment by segment (Tokenizer::encode for a text
+ * without special tokens, :653-717). out_cap counts ids; len always suffices. */
+int mbpe_encode_text(mbpe_encoder *enc, mbpe_pretok *p, const uint8_t *text, uint64_t len, uint32_t *out,
+                     uint64_t out_cap, uint64_t *n_out);
 /* a trainer over a device corpus (copied device to device; the corpus may be freed afterwards) */
 int mbpe_trainer_create_device(const mbpe_device_corpus *c, mbpe_trainer **out);
 

@@ -29,10 +29,10 @@ EXPORTS = [
     "mbpe_gpt2_split_pattern", "mbpe_gpt4_split_pattern", "mbpe_tokenizer_create", "mbpe_tokenizer_destroy",
     "mbpe_tokenizer_set_special_tokens", "mbpe_tokenizer_train", "mbpe_tokenizer_save", "mbpe_tokenizer_load",
     "mbpe_tokenizer_encode", "mbpe_tokenizer_decode", "mbpe_tokenizer_get_merges",
-    "mbpe_tokenizer_last_train_stats", "mbpe_tokenizer_set_engine", "mbpe_tokenizer_set_threads",
+    "mbpe_tokenizer_last_train_stats", "mbpe_tokenizer_last_split_on_gpu", "mbpe_tokenizer_set_engine", "mbpe_tokenizer_set_threads",
     "mbpe_split", "mbpe_pretok_class_table", "mbpe_dedup",
     "mbpe_pretok_create", "mbpe_pretok_destroy", "mbpe_pretok_split_device", "mbpe_pretok_split",
-    "mbpe_pretok_dedup_device", "mbpe_pretok_corpus", "mbpe_device_corpus_download", "mbpe_device_corpus_free",
+    "mbpe_pretok_dedup_device", "mbpe_pretok_dedup_segments", "mbpe_pretok_corpus", "mbpe_encode_text", "mbpe_device_corpus_download", "mbpe_device_corpus_free",
     "mbpe_trainer_create_device", "mbpe_split_dedup", "mbpe_plan_shards", "mbpe_write_model", "mbpe_synth_corpus",
 ]
 
@@ -243,6 +243,15 @@ class Pretok:
         _ck(lib().mbpe_pretok_corpus(self.h, _p(buf, C.c_uint8), C.c_uint64(len(text)), C.byref(c)))
         return c
 
+    def encode_text(self, encoder, text: bytes):
+        """GPT-4 split + merge scan of host text, ids back in host memory"""
+        buf = _u8(text)
+        out = np.zeros(max(len(text), 1), np.uint32)
+        n = C.c_uint64()
+        _ck(lib().mbpe_encode_text(encoder.h, self.h, _p(buf, C.c_uint8), C.c_uint64(len(text)), _p(out, C.c_uint32),
+                                   C.c_uint64(len(out)), C.byref(n)))
+        return out[:n.value].copy()
+
     def close(self):
         if self.h:
             lib().mbpe_pretok_destroy(self.h)
@@ -373,9 +382,11 @@ class Tokenizer:
         b = contents if isinstance(contents, bytes) else contents.encode()
         _ck(lib().mbpe_tokenizer_set_special_tokens(self.h, b, C.c_uint64(len(b))))
 
-    def train(self, text: bytes, vocab_size, conflict_resolution, verbose=False):
+    def train(self, text, vocab_size, conflict_resolution, verbose=False):
+        """text: bytes or a uint8 array (e.g. pinned memory)"""
         mode = MODE[conflict_resolution] if isinstance(conflict_resolution, str) else conflict_resolution
-        _ck(lib().mbpe_tokenizer_train(self.h, _p(_u8(text), C.c_uint8), C.c_uint64(len(text)), int(vocab_size), mode,
+        buf = text if isinstance(text, np.ndarray) else _u8(text)
+        _ck(lib().mbpe_tokenizer_train(self.h, _p(buf, C.c_uint8), C.c_uint64(len(text)), int(vocab_size), mode,
                                        int(verbose)))
 
     def save(self, path, write_vocab=False):
@@ -384,12 +395,19 @@ class Tokenizer:
     def load(self, path, verbose=False):
         _ck(lib().mbpe_tokenizer_load(self.h, str(path).encode(), int(verbose)))
 
-    def encode(self, text: bytes, verbose=False):
+    def encode(self, text, verbose=False, out=None):
+        """text: bytes or a uint8 array (e.g. pinned memory); out: optional uint32 array to receive the ids (a view of
+        it is returned), otherwise a fresh array."""
         n = C.c_uint64()
-        out = np.zeros(max(len(text), 1), np.uint32)
-        _ck(lib().mbpe_tokenizer_encode(self.h, _p(_u8(text), C.c_uint8), C.c_uint64(len(text)), _p(out, C.c_uint32),
+        buf = text if isinstance(text, np.ndarray) else _u8(text)
+        if out is None:
+            tmp = np.empty(max(len(buf), 1), np.uint32)
+            _ck(lib().mbpe_tokenizer_encode(self.h, _p(buf, C.c_uint8), C.c_uint64(len(text)), _p(tmp, C.c_uint32),
+                                            C.c_uint64(len(tmp)), C.byref(n)))
+            return tmp[:n.value].copy()
+        _ck(lib().mbpe_tokenizer_encode(self.h, _p(buf, C.c_uint8), C.c_uint64(len(text)), _p(out, C.c_uint32),
                                         C.c_uint64(len(out)), C.byref(n)))
-        return out[:n.value].copy()
+        return out[:n.value]
 
     def decode(self, ids, verbose=False):
         ids = np.ascontiguousarray(ids, np.uint32)
@@ -415,7 +433,8 @@ class Tokenizer:
         _ck(lib().mbpe_tokenizer_last_train_stats(self.h, C.byref(st), C.byref(split), C.byref(dedup), C.byref(nc),
                                                   C.byref(nu)))
         d = st.as_dict()
-        d.update(split_s=split.value, dedup_s=dedup.value, n_chunks=nc.value, n_unique=nu.value)
+        d.update(split_s=split.value, dedup_s=dedup.value, n_chunks=nc.value, n_unique=nu.value,
+                 split_on_gpu=bool(lib().mbpe_tokenizer_last_split_on_gpu(self.h)))
         return d
 
     def set_engine(self, engine):

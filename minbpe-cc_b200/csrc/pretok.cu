@@ -147,9 +147,16 @@ __global__ void __launch_bounds__(BC_THREADS) k_bits_compact(const uint32_t *bit
 constexpr unsigned long long DD_EMPTY = ~0ull;
 constexpr uint32_t DD_MAX_PROBES = 1u << 14;
 
-struct DedupArgs {
+// The text may live in several resident segments (each < 4 GiB, so offsets stay 32-bit); chunk indices are global.
+constexpr int DD_MAX_SEGS = 16;
+struct DdSeg {
     const uint8_t *text;
-    const uint32_t *off; // n_chunks + 1
+    const uint32_t *off; // this segment's chunk offsets (n + 1), relative to its text
+    uint64_t chunk0;     // global index of its first chunk
+};
+struct DedupArgs {
+    DdSeg seg[DD_MAX_SEGS];
+    uint32_t n_segs;
     uint64_t n_chunks;
     unsigned long long *words; // slot: tag(31) << 32 | smallest chunk index with these bytes; DD_EMPTY = free
     uint32_t *counts;          // slot: occurrences
@@ -177,18 +184,26 @@ __device__ __forceinline__ uint64_t dd_hash(const uint8_t *text, uint32_t o, uin
     return h;
 }
 
-__device__ __forceinline__ bool dd_equal(const DedupArgs &a, uint32_t o, uint32_t len, uint32_t rep) {
-    const uint32_t ro = __ldg(a.off + rep);
-    if (__ldg(a.off + rep + 1) - ro != len) return false;
+__device__ __forceinline__ const DdSeg &dd_seg(const DedupArgs &a, uint64_t c) {
+    uint32_t k = 0;
+    while (k + 1 < a.n_segs && a.seg[k + 1].chunk0 <= c) k++;
+    return a.seg[k];
+}
+
+__device__ __forceinline__ bool dd_equal(const DedupArgs &a, const uint8_t *text, uint32_t o, uint32_t len, uint32_t rep) {
+    const DdSeg &rs = dd_seg(a, rep);
+    const uint32_t ro = __ldg(rs.off + (rep - rs.chunk0));
+    if (__ldg(rs.off + (rep - rs.chunk0) + 1) - ro != len) return false;
     for (uint32_t i = 0; i < len; i++)
-        if (__ldg(a.text + o + i) != __ldg(a.text + ro + i)) return false;
+        if (__ldg(text + o + i) != __ldg(rs.text + ro + i)) return false;
     return true;
 }
 
 __global__ void __launch_bounds__(256) k_dedup_insert(const DedupArgs a) {
     for (uint64_t c = blockIdx.x * 256ull + threadIdx.x; c < a.n_chunks; c += (uint64_t)gridDim.x * 256) {
-        const uint32_t o = __ldg(a.off + c), len = __ldg(a.off + c + 1) - o;
-        const uint64_t h = dd_hash(a.text, o, len);
+        const DdSeg &sg = dd_seg(a, c);
+        const uint32_t o = __ldg(sg.off + (c - sg.chunk0)), len = __ldg(sg.off + (c - sg.chunk0) + 1) - o;
+        const uint64_t h = dd_hash(sg.text, o, len);
         const unsigned long long mine = ((h >> 33) << 32) | (uint32_t)c;
         uint32_t s = (uint32_t)h & a.mask;
         for (uint32_t probes = 0;; probes++) {
@@ -207,7 +222,7 @@ __global__ void __launch_bounds__(256) k_dedup_insert(const DedupArgs a) {
             }
             if ((w >> 32) == (mine >> 32)) {
                 const uint32_t rep = (uint32_t)w;
-                if (rep == (uint32_t)c || dd_equal(a, o, len, rep)) {
+                if (rep == (uint32_t)c || dd_equal(a, sg.text, o, len, rep)) {
                     if ((uint32_t)c < rep) atomicMin(&a.words[s], mine); // keep the FIRST occurrence as representative
                     atomicAdd(&a.counts[s], 1u);
                     break;
@@ -245,9 +260,10 @@ __global__ void __launch_bounds__(DE_THREADS) k_dedup_emit(const DedupArgs a, co
         uint32_t len = 0;
         if (u < n_unique) {
             const uint32_t c = __ldg(first_idx + u);
-            const uint32_t o = __ldg(a.off + c);
-            len = __ldg(a.off + c + 1) - o;
-            const uint64_t h = dd_hash(a.text, o, len);
+            const DdSeg &sg = dd_seg(a, c);
+            const uint32_t o = __ldg(sg.off + (c - sg.chunk0));
+            len = __ldg(sg.off + (c - sg.chunk0) + 1) - o;
+            const uint64_t h = dd_hash(sg.text, o, len);
             uint32_t s = (uint32_t)h & a.mask;
             while ((uint32_t)a.words[s] != c || a.words[s] == DD_EMPTY) s = (s + 1) & a.mask; // the slot this chunk represents
             weight[u] = a.counts[s];
@@ -277,19 +293,28 @@ __global__ void __launch_bounds__(DE_THREADS) k_dedup_emit(const DedupArgs a, co
 }
 
 // bytes of the unique chunks widened to u32 tokens (Tokenizer.h:85-100), one warp per chunk
-__global__ void __launch_bounds__(256) k_dedup_tokens(const uint8_t *text, const uint32_t *off, const uint32_t *first_idx,
-                                                       uint32_t n_unique, const unsigned long long *tok_off, uint32_t *tokens) {
+__global__ void __launch_bounds__(256) k_dedup_tokens(const DedupArgs a, const uint32_t *first_idx, uint32_t n_unique,
+                                                       const unsigned long long *tok_off, uint32_t *tokens) {
     const uint32_t lane = threadIdx.x & 31;
     for (uint64_t u = (blockIdx.x * 256ull + threadIdx.x) >> 5; u < n_unique; u += ((uint64_t)gridDim.x * 256) >> 5) {
-        const uint32_t c = __ldg(first_idx + u), o = __ldg(off + c), len = __ldg(off + c + 1) - o;
+        const uint32_t c = __ldg(first_idx + u);
+        const DdSeg &sg = dd_seg(a, c);
+        const uint32_t o = __ldg(sg.off + (c - sg.chunk0)), len = __ldg(sg.off + (c - sg.chunk0) + 1) - o;
         const unsigned long long t0 = tok_off[u];
-        for (uint32_t i = lane; i < len; i += 32) tokens[t0 + i] = __ldg(text + o + i);
+        for (uint32_t i = lane; i < len; i += 32) tokens[t0 + i] = __ldg(sg.text + o + i);
     }
 }
 
 } // namespace mbpe
 
 using namespace mbpe;
+
+#include <chrono>
+static double pt_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static bool pt_debug() {
+    static const bool on = getenv("MBPE_DEBUG") != nullptr;
+    return on;
+}
 
 struct mbpe_pretok {
     int device = 0, sms = 148;
@@ -302,6 +327,14 @@ struct mbpe_pretok {
     unsigned long long *d_count = nullptr; // set-bit count
     uint64_t max_crawl = 1u << 16;
     uint64_t launches = 0;
+    uint8_t *d_seg_text = nullptr; // segment buffers of mbpe_encode_text, kept between calls
+    uint32_t *d_seg_off = nullptr, *d_seg_ids = nullptr;
+    uint64_t *d_seg_n = nullptr;
+    uint64_t seg_cap = 0;
+    void *scratch[4] = {nullptr, nullptr, nullptr, nullptr}; // dedup work buffers, grow-only, kept between calls
+    uint64_t scratch_cap[4] = {0, 0, 0, 0};
+    std::vector<uint8_t> h_table;   // host copy: segment boundaries are chosen at cuts (pretok_core.cuh)
+    uint64_t seg_bytes = 1ull << 30; // host text is brought over in segments of about this size
 };
 
 extern "C" int mbpe_pretok_create(int device, mbpe_pretok **out) {
@@ -315,6 +348,9 @@ extern "C" int mbpe_pretok_create(int device, mbpe_pretok **out) {
     p->device = device;
     p->sms = sm_count(device);
     if (const char *mc = getenv("MBPE_PRETOK_MAX_CRAWL")) p->max_crawl = strtoull(mc, nullptr, 10);
+    if (const char *sb = getenv("MBPE_PRETOK_SEG_BYTES")) p->seg_bytes = std::max<uint64_t>(64, strtoull(sb, nullptr, 10));
+    p->seg_bytes = std::min<uint64_t>(p->seg_bytes, 3ull << 30);
+    p->h_table = table;
     MB_CUDA(cudaMalloc(&p->d_table, PT_TABLE_BYTES));
     MB_CUDA(cudaMemcpy(p->d_table, table.data(), PT_TABLE_BYTES, cudaMemcpyHostToDevice));
     MB_CUDA(cudaMalloc(&p->d_small, 16));
@@ -332,10 +368,31 @@ extern "C" void mbpe_pretok_destroy(mbpe_pretok *p) {
     cudaFree(p->d_status);
     cudaFree(p->d_small);
     cudaFree(p->d_count);
+    cudaFree(p->d_seg_text);
+    cudaFree(p->d_seg_off);
+    cudaFree(p->d_seg_ids);
+    cudaFree(p->d_seg_n);
+    for (void *q : p->scratch) cudaFree(q);
     delete p;
 }
 
 namespace mbpe {
+// grow-only work buffer k of the handle (driver allocations of this size cost milliseconds to hundreds of them)
+static void *pt_scratch(mbpe_pretok *p, int k, uint64_t bytes) {
+    if (bytes > p->scratch_cap[k]) {
+        cudaFree(p->scratch[k]);
+        p->scratch[k] = nullptr;
+        p->scratch_cap[k] = 0;
+        const uint64_t want = bytes + bytes / 8 + 256;
+        if (cudaMalloc(&p->scratch[k], want) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        p->scratch_cap[k] = want;
+    }
+    return p->scratch[k];
+}
+
 // positions of the set bits of bitmap[0 .. n_words) into d_out (ascending); count left in p->d_count
 int bits_compact(mbpe_pretok *p, const uint32_t *d_bitmap, uint64_t n_words, uint32_t *d_out, uint64_t out_cap, cudaStream_t st) {
     const uint64_t n_tiles = (n_words + BC_WORDS - 1) / BC_WORDS;
@@ -447,10 +504,13 @@ extern "C" void mbpe_device_corpus_free(mbpe_device_corpus *c) {
     memset(c, 0, sizeof *c);
 }
 
-extern "C" int mbpe_pretok_dedup_device(mbpe_pretok *p, const uint8_t *d_text, uint64_t len, const uint32_t *d_off,
-                                        uint64_t n_chunks, mbpe_device_corpus *out, void *stream) {
-    if (!p || !out || !d_off || (len && !d_text)) return set_error(MBPE_E_INVALID, "null argument");
-    if (n_chunks >= (1ull << 32) - 64) return set_error(MBPE_E_INVALID, "too many chunks for one device batch");
+extern "C" int mbpe_pretok_dedup_segments(mbpe_pretok *p, const uint8_t *const *d_texts, const uint32_t *const *d_offs,
+                                          const uint64_t *seg_chunks, uint32_t n_segs, mbpe_device_corpus *out, void *stream) {
+    if (!p || !out || (n_segs && (!d_texts || !d_offs || !seg_chunks))) return set_error(MBPE_E_INVALID, "null argument");
+    if (n_segs > (uint32_t)DD_MAX_SEGS) return set_error(MBPE_E_INVALID, "too many text segments");
+    uint64_t n_chunks = 0;
+    for (uint32_t k = 0; k < n_segs; k++) n_chunks += seg_chunks[k];
+    if (n_chunks >= (1ull << 32) - 64) return set_error(MBPE_E_INVALID, "too many chunks (>= 2^32)");
     int rc = use_device(p->device);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
@@ -468,21 +528,25 @@ extern "C" int mbpe_pretok_dedup_device(mbpe_pretok *p, const uint8_t *d_text, u
     while (slots < n_chunks / 16 && slots < (1ull << 27)) slots <<= 1;
     unsigned long long *d_words = nullptr;
     uint32_t *d_counts = nullptr, *d_first = nullptr, *d_first_idx = nullptr;
-    auto cleanup = [&]() {
-        cudaFree(d_words);
-        cudaFree(d_counts);
-        cudaFree(d_first);
-        cudaFree(d_first_idx);
-    };
+    auto cleanup = [&]() {};
     uint32_t used = 0;
     DedupArgs a{};
     for (;;) {
-        MB_CUDA(cudaMalloc(&d_words, slots * 8));
-        MB_CUDA(cudaMalloc(&d_counts, slots * 4));
+        d_words = (unsigned long long *)pt_scratch(p, 0, slots * 8);
+        d_counts = (uint32_t *)pt_scratch(p, 1, slots * 4);
+        if (!d_words || !d_counts) return set_error(MBPE_E_CUDA, "out of device memory");
         MB_CUDA(cudaMemsetAsync(d_words, 0xFF, slots * 8, st));
         MB_CUDA(cudaMemsetAsync(d_counts, 0, slots * 4, st));
         MB_CUDA(cudaMemsetAsync(p->d_small, 0, 16, st));
-        a = DedupArgs{d_text, d_off, n_chunks, d_words, d_counts, (uint32_t)(slots - 1), p->d_small + 3, p->d_small + 2};
+        a = DedupArgs{};
+        for (uint32_t k = 0, c0 = 0; k < n_segs; c0 += (uint32_t)seg_chunks[k], k++) a.seg[k] = DdSeg{d_texts[k], d_offs[k], c0};
+        a.n_segs = n_segs;
+        a.n_chunks = n_chunks;
+        a.words = d_words;
+        a.counts = d_counts;
+        a.mask = (uint32_t)(slots - 1);
+        a.used = p->d_small + 3;
+        a.overflow = p->d_small + 2;
         const unsigned grid = (unsigned)std::min<uint64_t>((n_chunks + 255) / 256, (uint64_t)p->sms * 16);
         k_dedup_insert<<<grid, 256, 0, st>>>(a);
         p->launches++;
@@ -491,18 +555,13 @@ extern "C" int mbpe_pretok_dedup_device(mbpe_pretok *p, const uint8_t *d_text, u
         MB_CUDA(cudaStreamSynchronize(st));
         used = small[3];
         if (!small[2] && (uint64_t)used * 2 <= slots) break;
-        cudaFree(d_words);
-        cudaFree(d_counts);
-        d_words = nullptr;
-        d_counts = nullptr;
         if (slots >= (1ull << 31)) return set_error(MBPE_E_CUDA, "dedup table cannot grow further");
         slots <<= 2; // too full for short probe chains: redo in a larger table
     }
     const uint64_t first_words = (n_chunks + 31) / 32;
-    if (cudaMalloc(&d_first, first_words * 4) != cudaSuccess || cudaMalloc(&d_first_idx, ((uint64_t)used + 1) * 4) != cudaSuccess) {
-        cleanup();
-        return set_error(MBPE_E_CUDA, "out of device memory");
-    }
+    d_first = (uint32_t *)pt_scratch(p, 2, first_words * 4);
+    d_first_idx = (uint32_t *)pt_scratch(p, 3, ((uint64_t)used + 1) * 4);
+    if (!d_first || !d_first_idx) return set_error(MBPE_E_CUDA, "out of device memory");
     MB_CUDA(cudaMemsetAsync(d_first, 0, first_words * 4, st));
     k_dedup_first<<<(unsigned)std::min<uint64_t>((slots + 255) / 256, (uint64_t)p->sms * 16), 256, 0, st>>>(d_words, slots, d_first);
     p->launches++;
@@ -537,7 +596,7 @@ extern "C" int mbpe_pretok_dedup_device(mbpe_pretok *p, const uint8_t *d_text, u
         return set_error(MBPE_E_CUDA, "out of device memory");
     }
     k_dedup_tokens<<<std::min<unsigned>((used + 7) / 8, p->sms * 16), 256, 0, st>>>(
-        d_text, d_off, d_first_idx, used, (const unsigned long long *)out->d_off, out->d_tokens);
+        a, d_first_idx, used, (const unsigned long long *)out->d_off, out->d_tokens);
     p->launches++;
     cudaError_t ce = cudaStreamSynchronize(st);
     cleanup();
@@ -546,6 +605,12 @@ extern "C" int mbpe_pretok_dedup_device(mbpe_pretok *p, const uint8_t *d_text, u
         return cuda_fail(ce, "dedup kernels", __FILE__, __LINE__);
     }
     return MBPE_OK;
+}
+
+extern "C" int mbpe_pretok_dedup_device(mbpe_pretok *p, const uint8_t *d_text, uint64_t len, const uint32_t *d_off,
+                                        uint64_t n_chunks, mbpe_device_corpus *out, void *stream) {
+    if (!d_off || (len && !d_text)) return set_error(MBPE_E_INVALID, "null argument");
+    return mbpe_pretok_dedup_segments(p, &d_text, &d_off, &n_chunks, 1, out, stream);
 }
 
 extern "C" int mbpe_device_corpus_download(const mbpe_device_corpus *c, uint32_t *tokens, uint64_t *off, uint32_t *weight) {
@@ -558,25 +623,160 @@ extern "C" int mbpe_device_corpus_download(const mbpe_device_corpus *c, uint32_t
     return MBPE_OK;
 }
 
+namespace mbpe {
+struct HostText {
+    const uint8_t *p;
+    uint8_t operator[](uint64_t i) const { return p[i]; }
+};
+
+// Host text is brought over in segments that end at cuts: a cut is a match start whatever precedes it, and the match
+// that ends there is decided by "the next code point is not of my class", which the end of a segment answers the same
+// way -- so segments are split independently and the chunk lists concatenate. Returns false if no cut is near.
+static bool plan_segments(const mbpe_pretok *pt, const uint8_t *text, uint64_t len, std::vector<uint64_t> &bounds) {
+    bounds.assign(1, 0);
+    uint32_t err = 0;
+    PretokIn<HostText> in{HostText{text}, len, pt->h_table.data(), &err};
+    while (len - bounds.back() > pt->seg_bytes + pt->seg_bytes / 4) {
+        const uint64_t lo = bounds.back() + pt->seg_bytes / 2, hi = bounds.back() + pt->seg_bytes;
+        uint64_t cut = 0;
+        bool bad = false;
+        for (uint64_t q = hi; q > lo && !cut && !bad; q--) {
+            if ((text[q] & 0xC0) == 0x80) continue;
+            const PtCp prev = pt_before(in, q, bad), cur = pt_at(in, q, bad);
+            if (!bad && pt_is_cut(prev.cls, cur)) cut = q;
+        }
+        if (!cut) return false;
+        bounds.push_back(cut);
+    }
+    bounds.push_back(len);
+    return true;
+}
+} // namespace mbpe
+
+static int ensure_segment_buffers(mbpe_pretok *p, uint64_t max_seg) {
+    if (max_seg <= p->seg_cap && p->d_seg_n) return MBPE_OK;
+    cudaFree(p->d_seg_text);
+    cudaFree(p->d_seg_off);
+    cudaFree(p->d_seg_ids);
+    cudaFree(p->d_seg_n);
+    p->d_seg_text = nullptr, p->d_seg_off = nullptr, p->d_seg_ids = nullptr, p->d_seg_n = nullptr;
+    p->seg_cap = 0;
+    const uint64_t cap = max_seg + max_seg / 16 + 64;
+    if (cudaMalloc(&p->d_seg_text, cap) != cudaSuccess || cudaMalloc(&p->d_seg_off, (cap + 2) * 4) != cudaSuccess ||
+        cudaMalloc(&p->d_seg_ids, cap * 4) != cudaSuccess || cudaMalloc(&p->d_seg_n, 8) != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(MBPE_E_CUDA, "out of device memory");
+    }
+    p->seg_cap = cap;
+    return MBPE_OK;
+}
+
 // text in host memory -> unique chunks resident on the device (split + dedup), the front end of Tokenizer::train
 extern "C" int mbpe_pretok_corpus(mbpe_pretok *p, const uint8_t *text, uint64_t len, mbpe_device_corpus *out) {
     if (!p || !out || (len && !text)) return set_error(MBPE_E_INVALID, "null argument");
     int rc = use_device(p->device);
     if (rc) return rc;
-    uint8_t *d_text = nullptr;
-    uint32_t *d_off = nullptr;
-    const uint64_t cap = len + 2;
-    MB_CUDA(cudaMalloc(&d_text, std::max<uint64_t>(len, 1)));
-    if (cudaMalloc(&d_off, cap * 4) != cudaSuccess) {
-        cudaFree(d_text);
-        return set_error(MBPE_E_CUDA, "out of device memory");
+    std::vector<uint64_t> bounds;
+    if (!plan_segments(p, text, len, bounds))
+        return set_error(MBPE_E_UNSUPPORTED, "no safe segment boundary found (malformed UTF-8 or no letters/blanks): use the PCRE2 path");
+    const uint32_t n_segs = (uint32_t)bounds.size() - 1;
+    if (n_segs > (uint32_t)DD_MAX_SEGS) return set_error(MBPE_E_UNSUPPORTED, "text too large for the resident pre-tokeniser");
+    std::vector<uint8_t *> d_text(n_segs, nullptr);
+    std::vector<uint32_t *> d_off(n_segs, nullptr);
+    std::vector<uint64_t> n_chunks(n_segs, 0);
+    auto cleanup = [&]() {
+        if (n_segs == 1) return;
+        for (auto q : d_text) cudaFree(q);
+        for (auto q : d_off) cudaFree(q);
+    };
+    const double t_start = pt_now();
+    double t_h2d = 0, t_split = 0;
+    const bool cached = n_segs == 1; // the usual case: one resident segment, buffers kept in the handle
+    if (cached) {
+        if ((rc = ensure_segment_buffers(p, len))) return rc;
+        d_text[0] = p->d_seg_text;
+        d_off[0] = p->d_seg_off;
     }
-    uint64_t n_chunks = 0;
-    cudaError_t ce = cudaMemcpy(d_text, text, len, cudaMemcpyHostToDevice);
-    rc = ce == cudaSuccess ? mbpe_pretok_split_device(p, d_text, len, d_off, cap, &n_chunks, nullptr)
-                           : cuda_fail(ce, "H2D text", __FILE__, __LINE__);
-    if (rc == MBPE_OK) rc = mbpe_pretok_dedup_device(p, d_text, len, d_off, n_chunks, out, nullptr);
-    cudaFree(d_text);
-    cudaFree(d_off);
+    for (uint32_t k = 0; k < n_segs && rc == MBPE_OK; k++) {
+        const uint64_t b = bounds[k], n = bounds[k + 1] - b;
+        if (!cached && (cudaMalloc(&d_text[k], std::max<uint64_t>(n, 1)) != cudaSuccess || cudaMalloc(&d_off[k], (n + 2) * 4) != cudaSuccess)) {
+            rc = set_error(MBPE_E_CUDA, "out of device memory");
+            break;
+        }
+        double t0 = pt_now();
+        cudaError_t ce = cudaMemcpy(d_text[k], text + b, n, cudaMemcpyHostToDevice);
+        t_h2d += pt_now() - t0, t0 = pt_now();
+        rc = ce == cudaSuccess ? mbpe_pretok_split_device(p, d_text[k], n, d_off[k], n + 2, &n_chunks[k], nullptr)
+                               : cuda_fail(ce, "H2D text", __FILE__, __LINE__);
+        t_split += pt_now() - t0;
+    }
+    double t0 = pt_now();
+    if (rc == MBPE_OK)
+        rc = mbpe_pretok_dedup_segments(p, d_text.data(), d_off.data(), n_chunks.data(), n_segs, out, nullptr);
+    const double t_dedup = pt_now() - t0;
+    t0 = pt_now();
+    cleanup();
+    if (pt_debug())
+        fprintf(stderr, "[mbpe] pretok_corpus: %.1f MB in %u segment(s): H2D %.1f ms, split %.1f ms, dedup %.1f ms, free %.1f ms, total %.1f ms\n",
+                len / 1e6, n_segs, t_h2d * 1e3, t_split * 1e3, t_dedup * 1e3, (pt_now() - t0) * 1e3, (pt_now() - t_start) * 1e3);
+    return rc;
+}
+
+// text in host memory -> ids in host memory: GPT-4 split + merge scan per resident segment, nothing but the text
+// going up and the ids coming down (Tokenizer::encode without special tokens, Tokenizer.h:653-717)
+extern "C" int mbpe_encode_text(mbpe_encoder *enc, mbpe_pretok *p, const uint8_t *text, uint64_t len, uint32_t *out,
+                                uint64_t out_cap, uint64_t *n_out) {
+    if (!enc || !p || !n_out || (len && (!text || !out))) return set_error(MBPE_E_INVALID, "null argument");
+    *n_out = 0;
+    int rc = use_device(p->device);
+    if (rc) return rc;
+    std::vector<uint64_t> bounds;
+    if (!plan_segments(p, text, len, bounds))
+        return set_error(MBPE_E_UNSUPPORTED, "no safe segment boundary found (malformed UTF-8 or no letters/blanks): use the PCRE2 path");
+    uint64_t max_seg = 0;
+    for (size_t k = 0; k + 1 < bounds.size(); k++) max_seg = std::max(max_seg, bounds[k + 1] - bounds[k]);
+    const double t_start = pt_now();
+    if ((rc = ensure_segment_buffers(p, max_seg))) return rc;
+    uint8_t *d_text = p->d_seg_text;
+    uint32_t *d_off = p->d_seg_off, *d_ids = p->d_seg_ids;
+    uint64_t *d_n = p->d_seg_n;
+    auto cleanup = [&]() {};
+    double t_h2d = 0, t_split = 0, t_enc = 0, t_d2h = 0;
+    uint64_t produced = 0;
+    for (size_t k = 0; k + 1 < bounds.size() && rc == MBPE_OK; k++) {
+        const uint64_t b = bounds[k], n = bounds[k + 1] - b;
+        if (n == 0) continue;
+        uint64_t n_chunks = 0, n_ids = 0;
+        double t0 = pt_now();
+        cudaError_t ce = cudaMemcpy(d_text, text + b, n, cudaMemcpyHostToDevice);
+        if (ce != cudaSuccess) {
+            rc = cuda_fail(ce, "H2D text", __FILE__, __LINE__);
+            break;
+        }
+        t_h2d += pt_now() - t0, t0 = pt_now();
+        if ((rc = mbpe_pretok_split_device(p, d_text, n, d_off, n + 2, &n_chunks, nullptr))) break;
+        t_split += pt_now() - t0, t0 = pt_now();
+        if ((rc = mbpe_encode_device(enc, d_text, n, d_off, n_chunks, d_ids, n, d_n, nullptr))) break;
+        if ((ce = cudaMemcpy(&n_ids, d_n, 8, cudaMemcpyDeviceToHost)) != cudaSuccess) {
+            rc = cuda_fail(ce, "D2H count", __FILE__, __LINE__);
+            break;
+        }
+        if (produced + n_ids > out_cap) {
+            rc = set_error(MBPE_E_CAPACITY, "output buffer too small");
+            break;
+        }
+        t_enc += pt_now() - t0, t0 = pt_now();
+        if ((ce = cudaMemcpy(out + produced, d_ids, n_ids * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) {
+            rc = cuda_fail(ce, "D2H ids", __FILE__, __LINE__);
+            break;
+        }
+        t_d2h += pt_now() - t0;
+        produced += n_ids;
+    }
+    cleanup();
+    if (pt_debug())
+        fprintf(stderr, "[mbpe] encode_text: %.1f MB in %zu segment(s): H2D %.1f ms, split %.1f ms, merge scan %.1f ms, D2H %.1f ms, total %.1f ms\n",
+                len / 1e6, bounds.size() - 1, t_h2d * 1e3, t_split * 1e3, t_enc * 1e3, t_d2h * 1e3, (pt_now() - t_start) * 1e3);
+    if (rc == MBPE_OK) *n_out = produced;
     return rc;
 }

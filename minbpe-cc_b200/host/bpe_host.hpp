@@ -1,6 +1,6 @@
 // bpe_host.hpp -- host (C++23) front end: regex pre-tokenisation, chunk dedup, special tokens, model files.
-// Everything here stays on the CPU by design (BASELINE.json north_star); the merge loop, the merge scan and the
-// decode gather are GPU calls through include/minbpe_b200.h.
+// The merge loop, the merge scan and the decode gather are GPU calls through include/minbpe_b200.h; pre-tokenisation
+// and chunk dedup run here on the host (PCRE2, any pattern) or, for the GPT-4 pattern, on the device (section 6 of the ABI).
 #pragma once
 #include <cstdint>
 #include <string>
@@ -88,6 +88,7 @@ class Tokenizer {
     void set_special_tokens_from_file(const std::string &contents);                                    // :476
     int train(std::string_view text, int vocab_size, CONFLICT_RESOLUTION mode, bool verbose);          // :489
     int encode(std::string_view text, bool verbose, std::vector<Token> &out);                          // :653
+    int encode_into(std::string_view text, Token *out, uint64_t cap, uint64_t *n_out); // same ids, caller's buffer
     int decode(const std::vector<Token> &tokens, bool verbose, std::string &out);                      // :725
     int load(const std::string &path, bool verbose);                                                   // :754
     int save(const std::string &path, bool write_vocab);                                               // :875
@@ -102,10 +103,12 @@ class Tokenizer {
     mbpe_train_stats last_stats{};
     double last_split_s = 0, last_dedup_s = 0;
     uint64_t last_n_chunks = 0, last_n_unique = 0;
+    bool last_split_on_gpu = false;
 
   private:
     std::vector<std::string> split_on_special(std::string_view text); // :605-650
     int ensure_encoder();
+    bool use_gpu_split(size_t n_bytes);
     void rebuild_vocab();
 
     std::string pattern_;
@@ -115,6 +118,8 @@ class Tokenizer {
     std::vector<std::pair<Token, Token>> merges_;
     std::vector<std::string> vocab_;
     mbpe_encoder *encoder_ = nullptr;
+    mbpe_pretok *pretok_ = nullptr; // device matcher of the GPT-4 pattern, created on first use
+    bool pretok_failed_ = false;
     bool encoder_stale_ = true;
     int device_ = 0, engine_ = MBPE_ENGINE_PERSISTENT, n_threads_ = 0;
     std::string error_;

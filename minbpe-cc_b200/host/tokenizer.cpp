@@ -22,6 +22,24 @@ Tokenizer::Tokenizer(const std::string &pattern, int device) : pattern_(pattern)
 
 Tokenizer::~Tokenizer() {
     if (encoder_) mbpe_encoder_destroy(encoder_);
+    if (pretok_) mbpe_pretok_destroy(pretok_);
+}
+
+// The GPT-4 pattern has a device matcher (csrc/pretok_core.cuh). Texts of at least this many bytes go through it;
+// MBPE_GPU_SPLIT=0 keeps pre-tokenisation on the host (PCRE2), MBPE_GPU_SPLIT=<n> sets the threshold (1 = always).
+// Under this pattern no chunk can be a ready-made id (a chunk "\0<int>"): a chunk that starts with NUL
+// continues with letters (alternative 2) or symbols (alternative 4), never with a digit, so std::stoi always throws.
+static uint64_t gpu_split_min_bytes() {
+    const char *v = getenv("MBPE_GPU_SPLIT");
+    if (!v || !*v) return 1u << 16;
+    const uint64_t n = strtoull(v, nullptr, 10);
+    return n == 0 ? ~0ull : n;
+}
+
+bool Tokenizer::use_gpu_split(size_t n_bytes) {
+    if (pattern_ != kGpt4Pattern || n_bytes < gpu_split_min_bytes()) return false;
+    if (!pretok_ && !pretok_failed_ && mbpe_pretok_create(device_, &pretok_) != MBPE_OK) pretok_failed_ = true;
+    return pretok_ != nullptr;
 }
 
 void Tokenizer::set_special_tokens_from_file(const std::string &contents) {
@@ -64,30 +82,53 @@ int Tokenizer::train(std::string_view text, int vocab_size, CONFLICT_RESOLUTION 
     }
     const uint8_t *bytes = reinterpret_cast<const uint8_t *>(text.data());
     double t0 = now_s();
-    Corpus corpus;
-    int rc = split_dedup_parallel(regex_, pattern_, bytes, text.size(), n_threads_, corpus, &error_);
-    if (rc) return rc;
+    int rc = MBPE_OK;
+    mbpe_trainer *tr = nullptr;
+    last_split_on_gpu = false;
+    if (use_gpu_split(text.size())) { // split + dedup on the device; the corpus never comes back to the host
+        mbpe_device_corpus dc;
+        rc = mbpe_pretok_corpus(pretok_, bytes, text.size(), &dc);
+        if (rc == MBPE_OK) {
+            last_n_chunks = dc.n_chunks;
+            last_n_unique = dc.n_unique;
+            rc = mbpe_trainer_create_device(&dc, &tr);
+            mbpe_device_corpus_free(&dc);
+            last_split_on_gpu = rc == MBPE_OK;
+        }
+        if (rc != MBPE_OK && rc != MBPE_E_UNSUPPORTED) {
+            error_ = mbpe_last_error();
+            return rc;
+        }
+    }
+    if (!tr) {
+        Corpus corpus;
+        rc = split_dedup_parallel(regex_, pattern_, bytes, text.size(), n_threads_, corpus, &error_);
+        if (rc) return rc;
+        last_n_chunks = corpus.n_chunks;
+        last_n_unique = corpus.weight.size();
+        rc = mbpe_trainer_create(corpus.tokens.data(), corpus.tokens.size(), corpus.off.data(), corpus.weight.size(),
+                                 corpus.weight.data(), device_, &tr);
+        if (rc) {
+            error_ = mbpe_last_error();
+            return rc;
+        }
+    }
     double t2 = now_s();
-    if (verbose) std::cout << "Split input text into " << corpus.n_chunks << " chunks\n"; // Tokenizer.h:547
-    last_split_s = t2 - t0; // regex split and dedup are one fused pass
+    if (verbose) std::cout << "Split input text into " << last_n_chunks << " chunks\n"; // Tokenizer.h:547
+    last_split_s = t2 - t0; // regex split and dedup are one fused pass (host threads, or the device for the GPT-4 pattern)
     last_dedup_s = 0;
-    last_n_chunks = corpus.n_chunks;
-    last_n_unique = corpus.weight.size();
 
     const uint32_t n_target = static_cast<uint32_t>(vocab_size - 256);
     std::vector<uint32_t> m(2ull * std::max<uint32_t>(n_target, 1));
     std::vector<int32_t> counts(std::max<uint32_t>(n_target, 1));
     uint32_t n_merges = 0;
-    mbpe_trainer *tr = nullptr;
-    rc = mbpe_trainer_create(corpus.tokens.data(), corpus.tokens.size(), corpus.off.data(), corpus.weight.size(),
-                             corpus.weight.data(), device_, &tr);
-    if (rc) {
-        error_ = mbpe_last_error();
-        return rc;
-    }
     rc = mbpe_trainer_run(tr, static_cast<uint32_t>(vocab_size), mode, engine_, nullptr, m.data(), counts.data(),
                           &n_merges, &last_stats);
+    double t3 = now_s();
     mbpe_trainer_destroy(tr);
+    if (getenv("MBPE_DEBUG"))
+        fprintf(stderr, "[mbpe] Tokenizer::train: front end %.1f ms (%s), merge loop call %.1f ms (device %.1f ms), destroy %.1f ms\n",
+                (t2 - t0) * 1e3, last_split_on_gpu ? "device" : "host", (t3 - t2) * 1e3, last_stats.gpu_ms, (now_s() - t3) * 1e3);
     if (rc) {
         error_ = mbpe_last_error();
         return rc;
@@ -174,6 +215,32 @@ int Tokenizer::ensure_encoder() {
     return MBPE_OK;
 }
 
+// Tokenizer::encode straight into a caller buffer: for a text without special tokens under the GPT-4 pattern the ids
+// come down from the device into `out` with no intermediate copy; everything else goes through encode() above.
+int Tokenizer::encode_into(std::string_view text, Token *out, uint64_t cap, uint64_t *n_out) {
+    *n_out = 0;
+    int rc = ensure_encoder();
+    if (rc) return rc;
+    if (out && special_tokens_.empty() && use_gpu_split(text.size())) {
+        rc = mbpe_encode_text(encoder_, pretok_, reinterpret_cast<const uint8_t *>(text.data()), text.size(), out, cap, n_out);
+        if (rc == MBPE_OK) return rc;
+        if (rc != MBPE_E_UNSUPPORTED) {
+            error_ = mbpe_last_error();
+            return rc;
+        }
+    }
+    std::vector<Token> ids;
+    if ((rc = encode(text, false, ids))) return rc;
+    *n_out = ids.size();
+    if (!out) return MBPE_OK;
+    if (ids.size() > cap) {
+        error_ = "out too small; *n_out holds the needed count";
+        return MBPE_E_CAPACITY;
+    }
+    memcpy(out, ids.data(), ids.size() * sizeof(Token));
+    return MBPE_OK;
+}
+
 int Tokenizer::encode(std::string_view text, bool verbose, std::vector<Token> &out) {
     out.clear();
     int rc = ensure_encoder();
@@ -183,6 +250,21 @@ int Tokenizer::encode(std::string_view text, bool verbose, std::vector<Token> &o
     if (!single) parts = split_on_special(text);
     const size_t n_parts = single ? 1 : parts.size();
     if (verbose) std::cout << "Splitting input text into " << n_parts << " parts\n";
+    if (single && use_gpu_split(text.size())) { // text up, ids down: split and merge scan both on the device
+        std::vector<Token> ids(std::max<size_t>(text.size(), 1));
+        uint64_t n_ids = 0;
+        rc = mbpe_encode_text(encoder_, pretok_, reinterpret_cast<const uint8_t *>(text.data()), text.size(), ids.data(),
+                              ids.size(), &n_ids);
+        if (rc == MBPE_OK) {
+            ids.resize(n_ids);
+            out.swap(ids);
+            return MBPE_OK;
+        }
+        if (rc != MBPE_E_UNSUPPORTED) {
+            error_ = mbpe_last_error();
+            return rc;
+        }
+    }
 
     // chunk list over one byte arena; ready-made ids (special markers) are spliced in afterwards
     std::vector<uint8_t> arena_copy;
@@ -439,14 +521,8 @@ extern "C" int mbpe_tokenizer_load(mbpe_tokenizer *t, const char *path, int verb
 extern "C" int mbpe_tokenizer_encode(mbpe_tokenizer *t, const uint8_t *text, uint64_t len, uint32_t *out,
                                      uint64_t out_cap, uint64_t *n_out) {
     if (!t || !n_out || (!text && len)) return fail(MBPE_E_INVALID, "null argument");
-    std::vector<Token> ids;
-    int rc = t->tk.encode(std::string_view(reinterpret_cast<const char *>(text), len), false, ids);
-    if (rc) return fail(rc, t->tk.error());
-    *n_out = ids.size();
-    if (!out) return MBPE_OK;
-    if (ids.size() > out_cap) return fail(MBPE_E_CAPACITY, "out too small; *n_out holds the needed count");
-    memcpy(out, ids.data(), ids.size() * sizeof(Token));
-    return MBPE_OK;
+    int rc = t->tk.encode_into(std::string_view(reinterpret_cast<const char *>(text), len), out, out_cap, n_out);
+    return rc ? fail(rc, t->tk.error()) : MBPE_OK;
 }
 extern "C" int mbpe_tokenizer_decode(mbpe_tokenizer *t, const uint32_t *ids, uint64_t n, uint8_t *out,
                                      uint64_t out_cap, uint64_t *n_out) {
@@ -483,6 +559,7 @@ extern "C" int mbpe_tokenizer_last_train_stats(mbpe_tokenizer *t, mbpe_train_sta
     if (n_unique) *n_unique = t->tk.last_n_unique;
     return MBPE_OK;
 }
+extern "C" int mbpe_tokenizer_last_split_on_gpu(mbpe_tokenizer *t) { return t && t->tk.last_split_on_gpu ? 1 : 0; }
 extern "C" void mbpe_tokenizer_set_engine(mbpe_tokenizer *t, int engine) {
     if (t) t->tk.set_engine(engine);
 }

@@ -192,3 +192,59 @@ def test_gpu_corpus_trains_to_the_same_merges(pkg, mode):
     t.close()
     pt.close()
     assert np.array_equal(got, want) and np.array_equal(gc, wc)
+
+
+def _train_cases(manifest):
+    return sorted(k for k, e in manifest["train"].items() if e["rc"] == 0 and e["vocab_size"] <= 4096)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gpu_split", ["0", "1"])
+def test_tokenizer_goldens_with_host_and_device_split(pkg, manifest, tmp_path, monkeypatch, gpu_split):
+    """Tokenizer::train + save and Tokenizer::encode give the reference's bytes whichever side pre-tokenises"""
+    import hashlib
+    from conftest import GOLDEN, golden_data
+    monkeypatch.setenv("MBPE_GPU_SPLIT", gpu_split)
+    for name in _train_cases(manifest):
+        e = manifest["train"][name]
+        tk = pkg.Tokenizer(pkg.patterns()[e["encoder"]])
+        if e["special"]:
+            tk.set_special_tokens_from_file(golden_data(e["special"]))
+        tk.train(golden_data(e["input"]), e["vocab_size"], e["mode"])
+        assert tk.last_train_stats()["split_on_gpu"] == (gpu_split == "1" and e["encoder"] == "gpt4"), name
+        out = tmp_path / "out.model"
+        tk.save(out, write_vocab=False)
+        assert hashlib.sha256(out.read_bytes()).hexdigest() == e["model_sha256"], name
+    for name, e in sorted(manifest["encode"].items()):
+        if e["rc"] != 0:
+            continue
+        tk = pkg.Tokenizer(pkg.patterns()["gpt4"])
+        tk.load(os.path.join(GOLDEN, "models", e["model"] + ".model"))
+        ids = tk.encode(golden_data(e["input"]))
+        assert len(ids) == e["n_tokens"] and hashlib.sha256(ids.tobytes()).hexdigest() == e["enc_sha256"], name
+
+
+@pytest.mark.gpu
+def test_segmented_corpus_and_encode_text(pkg, monkeypatch):
+    """host text brought over in many small segments (cut at matcher cuts) == one piece == host path"""
+    text = open(os.path.join(ROOT, "tests", "golden", "data", "shakespeare.txt"), "rb").read()
+    tok, off, w, n_chunks = pkg.split_dedup(pkg.patterns()["gpt4"], text)
+    merges, _, _ = pkg.train(tok, off, w, 600, "lexical")
+    enc = pkg.Encoder(merges)
+    s, e = pkg.split(pkg.patterns()["gpt4"], text)
+    want_ids = enc.encode(text, np.concatenate([s, e[-1:]]).astype(np.uint64))
+    for seg in ("100000", "4096", str(1 << 30)):
+        monkeypatch.setenv("MBPE_PRETOK_SEG_BYTES", seg)
+        pt = pkg.Pretok()
+        if seg == "4096":  # more than DD_MAX_SEGS segments: the corpus path declines, the encode path streams them
+            with pytest.raises(pkg.MbpeError) as ei:
+                pt.corpus(text)
+            assert ei.value.code == -8
+        else:
+            c = pt.corpus(text)
+            gt, go, gw = c.download()
+            assert c.n_chunks == n_chunks and np.array_equal(go, off) and np.array_equal(gw, w) and np.array_equal(gt, tok)
+            c.free()
+        assert np.array_equal(pt.encode_text(enc, text), want_ids), seg
+        pt.close()
+    enc.close()
