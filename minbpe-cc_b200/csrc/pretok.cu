@@ -327,10 +327,16 @@ struct mbpe_pretok {
     unsigned long long *d_count = nullptr; // set-bit count
     uint64_t max_crawl = 1u << 16;
     uint64_t launches = 0;
-    uint8_t *d_seg_text = nullptr; // segment buffers of mbpe_encode_text, kept between calls
-    uint32_t *d_seg_off = nullptr, *d_seg_ids = nullptr;
+    uint8_t *d_seg_text = nullptr; // segment buffers of mbpe_pretok_corpus, kept between calls
+    uint32_t *d_seg_off = nullptr;
     uint64_t *d_seg_n = nullptr;
     uint64_t seg_cap = 0;
+    cudaStream_t st_in = nullptr, st_c = nullptr, st_out = nullptr; // mbpe_encode_text pipeline
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    uint8_t *d_pipe_text[2] = {nullptr, nullptr};
+    uint32_t *d_pipe_ids[2] = {nullptr, nullptr}, *d_pipe_off = nullptr;
+    uint64_t pipe_cap = 0;
+    uint64_t enc_seg_bytes = 64ull << 20;
     void *scratch[4] = {nullptr, nullptr, nullptr, nullptr}; // dedup work buffers, grow-only, kept between calls
     uint64_t scratch_cap[4] = {0, 0, 0, 0};
     std::vector<uint8_t> h_table;   // host copy: segment boundaries are chosen at cuts (pretok_core.cuh)
@@ -350,6 +356,8 @@ extern "C" int mbpe_pretok_create(int device, mbpe_pretok **out) {
     if (const char *mc = getenv("MBPE_PRETOK_MAX_CRAWL")) p->max_crawl = strtoull(mc, nullptr, 10);
     if (const char *sb = getenv("MBPE_PRETOK_SEG_BYTES")) p->seg_bytes = std::max<uint64_t>(64, strtoull(sb, nullptr, 10));
     p->seg_bytes = std::min<uint64_t>(p->seg_bytes, 3ull << 30);
+    if (const char *sb = getenv("MBPE_ENCODE_SEG_BYTES")) p->enc_seg_bytes = std::max<uint64_t>(64, strtoull(sb, nullptr, 10));
+    p->enc_seg_bytes = std::min<uint64_t>(p->enc_seg_bytes, 3ull << 30);
     p->h_table = table;
     MB_CUDA(cudaMalloc(&p->d_table, PT_TABLE_BYTES));
     MB_CUDA(cudaMemcpy(p->d_table, table.data(), PT_TABLE_BYTES, cudaMemcpyHostToDevice));
@@ -370,9 +378,17 @@ extern "C" void mbpe_pretok_destroy(mbpe_pretok *p) {
     cudaFree(p->d_count);
     cudaFree(p->d_seg_text);
     cudaFree(p->d_seg_off);
-    cudaFree(p->d_seg_ids);
     cudaFree(p->d_seg_n);
     for (void *q : p->scratch) cudaFree(q);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(p->d_pipe_text[i]);
+        cudaFree(p->d_pipe_ids[i]);
+        if (p->ev_in[i]) cudaEventDestroy(p->ev_in[i]);
+        if (p->ev_out[i]) cudaEventDestroy(p->ev_out[i]);
+    }
+    cudaFree(p->d_pipe_off);
+    for (cudaStream_t q : {p->st_in, p->st_c, p->st_out})
+        if (q) cudaStreamDestroy(q);
     delete p;
 }
 
@@ -632,12 +648,12 @@ struct HostText {
 // Host text is brought over in segments that end at cuts: a cut is a match start whatever precedes it, and the match
 // that ends there is decided by "the next code point is not of my class", which the end of a segment answers the same
 // way -- so segments are split independently and the chunk lists concatenate. Returns false if no cut is near.
-static bool plan_segments(const mbpe_pretok *pt, const uint8_t *text, uint64_t len, std::vector<uint64_t> &bounds) {
+static bool plan_segments(const mbpe_pretok *pt, const uint8_t *text, uint64_t len, uint64_t seg_bytes, std::vector<uint64_t> &bounds) {
     bounds.assign(1, 0);
     uint32_t err = 0;
     PretokIn<HostText> in{HostText{text}, len, pt->h_table.data(), &err};
-    while (len - bounds.back() > pt->seg_bytes + pt->seg_bytes / 4) {
-        const uint64_t lo = bounds.back() + pt->seg_bytes / 2, hi = bounds.back() + pt->seg_bytes;
+    while (len - bounds.back() > seg_bytes + seg_bytes / 4) {
+        const uint64_t lo = bounds.back() + seg_bytes / 2, hi = bounds.back() + seg_bytes;
         uint64_t cut = 0;
         bool bad = false;
         for (uint64_t q = hi; q > lo && !cut && !bad; q--) {
@@ -657,13 +673,11 @@ static int ensure_segment_buffers(mbpe_pretok *p, uint64_t max_seg) {
     if (max_seg <= p->seg_cap && p->d_seg_n) return MBPE_OK;
     cudaFree(p->d_seg_text);
     cudaFree(p->d_seg_off);
-    cudaFree(p->d_seg_ids);
-    cudaFree(p->d_seg_n);
-    p->d_seg_text = nullptr, p->d_seg_off = nullptr, p->d_seg_ids = nullptr, p->d_seg_n = nullptr;
+    p->d_seg_text = nullptr, p->d_seg_off = nullptr;
     p->seg_cap = 0;
     const uint64_t cap = max_seg + max_seg / 16 + 64;
     if (cudaMalloc(&p->d_seg_text, cap) != cudaSuccess || cudaMalloc(&p->d_seg_off, (cap + 2) * 4) != cudaSuccess ||
-        cudaMalloc(&p->d_seg_ids, cap * 4) != cudaSuccess || cudaMalloc(&p->d_seg_n, 8) != cudaSuccess) {
+        (!p->d_seg_n && cudaMalloc(&p->d_seg_n, 8) != cudaSuccess)) {
         cudaGetLastError();
         return set_error(MBPE_E_CUDA, "out of device memory");
     }
@@ -677,7 +691,7 @@ extern "C" int mbpe_pretok_corpus(mbpe_pretok *p, const uint8_t *text, uint64_t 
     int rc = use_device(p->device);
     if (rc) return rc;
     std::vector<uint64_t> bounds;
-    if (!plan_segments(p, text, len, bounds))
+    if (!plan_segments(p, text, len, p->seg_bytes, bounds))
         return set_error(MBPE_E_UNSUPPORTED, "no safe segment boundary found (malformed UTF-8 or no letters/blanks): use the PCRE2 path");
     const uint32_t n_segs = (uint32_t)bounds.size() - 1;
     if (n_segs > (uint32_t)DD_MAX_SEGS) return set_error(MBPE_E_UNSUPPORTED, "text too large for the resident pre-tokeniser");
@@ -722,8 +736,43 @@ extern "C" int mbpe_pretok_corpus(mbpe_pretok *p, const uint8_t *text, uint64_t 
     return rc;
 }
 
-// text in host memory -> ids in host memory: GPT-4 split + merge scan per resident segment, nothing but the text
-// going up and the ids coming down (Tokenizer::encode without special tokens, Tokenizer.h:653-717)
+// text in host memory -> ids in host memory (Tokenizer::encode without special tokens, Tokenizer.h:653-717): GPT-4 split
+// + merge scan per resident segment, nothing but text going up and ids coming down. Segments (64 MiB, cut at matcher
+// cuts) are pipelined over three streams -- upload of segment k+1 and download of segment k-1 run under the kernels
+// of segment k -- so with pinned host buffers the call runs at the speed of the slower PCIe direction.
+static int ensure_pipe(mbpe_pretok *p, uint64_t max_seg) {
+    if (!p->st_c) {
+        MB_CUDA(cudaStreamCreateWithFlags(&p->st_in, cudaStreamNonBlocking));
+        MB_CUDA(cudaStreamCreateWithFlags(&p->st_c, cudaStreamNonBlocking));
+        MB_CUDA(cudaStreamCreateWithFlags(&p->st_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            MB_CUDA(cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming));
+            MB_CUDA(cudaEventCreateWithFlags(&p->ev_out[i], cudaEventDisableTiming));
+        }
+    }
+    if (max_seg <= p->pipe_cap) return MBPE_OK;
+    for (int i = 0; i < 2; i++) {
+        cudaFree(p->d_pipe_text[i]);
+        cudaFree(p->d_pipe_ids[i]);
+        p->d_pipe_text[i] = nullptr, p->d_pipe_ids[i] = nullptr;
+    }
+    cudaFree(p->d_pipe_off);
+    p->d_pipe_off = nullptr;
+    p->pipe_cap = 0;
+    const uint64_t cap = max_seg + max_seg / 16 + 64;
+    for (int i = 0; i < 2; i++)
+        if (cudaMalloc(&p->d_pipe_text[i], cap) != cudaSuccess || cudaMalloc(&p->d_pipe_ids[i], cap * 4) != cudaSuccess) {
+            cudaGetLastError();
+            return set_error(MBPE_E_CUDA, "out of device memory");
+        }
+    if (cudaMalloc(&p->d_pipe_off, (cap + 2) * 4) != cudaSuccess || (!p->d_seg_n && cudaMalloc(&p->d_seg_n, 8) != cudaSuccess)) {
+        cudaGetLastError();
+        return set_error(MBPE_E_CUDA, "out of device memory");
+    }
+    p->pipe_cap = cap;
+    return MBPE_OK;
+}
+
 extern "C" int mbpe_encode_text(mbpe_encoder *enc, mbpe_pretok *p, const uint8_t *text, uint64_t len, uint32_t *out,
                                 uint64_t out_cap, uint64_t *n_out) {
     if (!enc || !p || !n_out || (len && (!text || !out))) return set_error(MBPE_E_INVALID, "null argument");
@@ -731,52 +780,48 @@ extern "C" int mbpe_encode_text(mbpe_encoder *enc, mbpe_pretok *p, const uint8_t
     int rc = use_device(p->device);
     if (rc) return rc;
     std::vector<uint64_t> bounds;
-    if (!plan_segments(p, text, len, bounds))
+    if (!plan_segments(p, text, len, p->enc_seg_bytes, bounds))
         return set_error(MBPE_E_UNSUPPORTED, "no safe segment boundary found (malformed UTF-8 or no letters/blanks): use the PCRE2 path");
+    const size_t n_seg = bounds.size() - 1;
     uint64_t max_seg = 0;
-    for (size_t k = 0; k + 1 < bounds.size(); k++) max_seg = std::max(max_seg, bounds[k + 1] - bounds[k]);
+    for (size_t k = 0; k < n_seg; k++) max_seg = std::max(max_seg, bounds[k + 1] - bounds[k]);
     const double t_start = pt_now();
-    if ((rc = ensure_segment_buffers(p, max_seg))) return rc;
-    uint8_t *d_text = p->d_seg_text;
-    uint32_t *d_off = p->d_seg_off, *d_ids = p->d_seg_ids;
-    uint64_t *d_n = p->d_seg_n;
-    auto cleanup = [&]() {};
-    double t_h2d = 0, t_split = 0, t_enc = 0, t_d2h = 0;
+    if ((rc = ensure_pipe(p, max_seg))) return rc;
+    auto upload = [&](size_t k) -> cudaError_t {
+        cudaError_t ce = cudaMemcpyAsync(p->d_pipe_text[k & 1], text + bounds[k], bounds[k + 1] - bounds[k], cudaMemcpyHostToDevice, p->st_in);
+        return ce != cudaSuccess ? ce : cudaEventRecord(p->ev_in[k & 1], p->st_in);
+    };
     uint64_t produced = 0;
-    for (size_t k = 0; k + 1 < bounds.size() && rc == MBPE_OK; k++) {
-        const uint64_t b = bounds[k], n = bounds[k + 1] - b;
-        if (n == 0) continue;
+    cudaError_t ce = n_seg ? upload(0) : cudaSuccess;
+    for (size_t k = 0; k < n_seg && rc == MBPE_OK && ce == cudaSuccess; k++) {
+        const uint64_t n = bounds[k + 1] - bounds[k];
+        // buffer (k+1)&1 is free: the kernels of segment k-1 have finished (the host waited for their id count)
+        if (k + 1 < n_seg && (ce = upload(k + 1)) != cudaSuccess) break;
+        if ((ce = cudaStreamWaitEvent(p->st_c, p->ev_in[k & 1], 0)) != cudaSuccess) break;
+        if (k >= 2 && (ce = cudaStreamWaitEvent(p->st_c, p->ev_out[k & 1], 0)) != cudaSuccess) break; // ids[k&1] drained
         uint64_t n_chunks = 0, n_ids = 0;
-        double t0 = pt_now();
-        cudaError_t ce = cudaMemcpy(d_text, text + b, n, cudaMemcpyHostToDevice);
-        if (ce != cudaSuccess) {
-            rc = cuda_fail(ce, "H2D text", __FILE__, __LINE__);
-            break;
+        if (n) {
+            if ((rc = mbpe_pretok_split_device(p, p->d_pipe_text[k & 1], n, p->d_pipe_off, n + 2, &n_chunks, p->st_c))) break;
+            if ((rc = mbpe_encode_device(enc, p->d_pipe_text[k & 1], n, p->d_pipe_off, n_chunks, p->d_pipe_ids[k & 1], n, p->d_seg_n, p->st_c))) break;
+            if ((ce = cudaMemcpyAsync(&n_ids, p->d_seg_n, 8, cudaMemcpyDeviceToHost, p->st_c)) != cudaSuccess) break;
         }
-        t_h2d += pt_now() - t0, t0 = pt_now();
-        if ((rc = mbpe_pretok_split_device(p, d_text, n, d_off, n + 2, &n_chunks, nullptr))) break;
-        t_split += pt_now() - t0, t0 = pt_now();
-        if ((rc = mbpe_encode_device(enc, d_text, n, d_off, n_chunks, d_ids, n, d_n, nullptr))) break;
-        if ((ce = cudaMemcpy(&n_ids, d_n, 8, cudaMemcpyDeviceToHost)) != cudaSuccess) {
-            rc = cuda_fail(ce, "D2H count", __FILE__, __LINE__);
-            break;
-        }
+        if ((ce = cudaStreamSynchronize(p->st_c)) != cudaSuccess) break;
         if (produced + n_ids > out_cap) {
             rc = set_error(MBPE_E_CAPACITY, "output buffer too small");
             break;
         }
-        t_enc += pt_now() - t0, t0 = pt_now();
-        if ((ce = cudaMemcpy(out + produced, d_ids, n_ids * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) {
-            rc = cuda_fail(ce, "D2H ids", __FILE__, __LINE__);
-            break;
-        }
-        t_d2h += pt_now() - t0;
+        if ((ce = cudaMemcpyAsync(out + produced, p->d_pipe_ids[k & 1], n_ids * 4, cudaMemcpyDeviceToHost, p->st_out)) != cudaSuccess) break;
+        if ((ce = cudaEventRecord(p->ev_out[k & 1], p->st_out)) != cudaSuccess) break;
         produced += n_ids;
     }
-    cleanup();
+    // nothing of this call may still be in flight when it returns, whatever happened
+    cudaError_t e1 = cudaStreamSynchronize(p->st_in), e2 = cudaStreamSynchronize(p->st_c), e3 = cudaStreamSynchronize(p->st_out);
+    if (rc == MBPE_OK) {
+        if (ce == cudaSuccess) ce = e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3;
+        if (ce != cudaSuccess) rc = cuda_fail(ce, "encode_text pipeline", __FILE__, __LINE__);
+    }
     if (pt_debug())
-        fprintf(stderr, "[mbpe] encode_text: %.1f MB in %zu segment(s): H2D %.1f ms, split %.1f ms, merge scan %.1f ms, D2H %.1f ms, total %.1f ms\n",
-                len / 1e6, bounds.size() - 1, t_h2d * 1e3, t_split * 1e3, t_enc * 1e3, t_d2h * 1e3, (pt_now() - t_start) * 1e3);
+        fprintf(stderr, "[mbpe] encode_text: %.1f MB in %zu segment(s), %.1f ms\n", len / 1e6, n_seg, (pt_now() - t_start) * 1e3);
     if (rc == MBPE_OK) *n_out = produced;
     return rc;
 }

@@ -235,6 +235,7 @@ def test_segmented_corpus_and_encode_text(pkg, monkeypatch):
     want_ids = enc.encode(text, np.concatenate([s, e[-1:]]).astype(np.uint64))
     for seg in ("100000", "4096", str(1 << 30)):
         monkeypatch.setenv("MBPE_PRETOK_SEG_BYTES", seg)
+        monkeypatch.setenv("MBPE_ENCODE_SEG_BYTES", seg)
         pt = pkg.Pretok()
         if seg == "4096":  # more than DD_MAX_SEGS segments: the corpus path declines, the encode path streams them
             with pytest.raises(pkg.MbpeError) as ei:

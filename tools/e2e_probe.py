@@ -10,7 +10,10 @@ mib = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 text = pkg.synth_corpus(0x5EED0001, mib << 20)
 pinned = torch.empty(len(text), dtype=torch.uint8, pin_memory=True); pinned.numpy()[:] = text
 tk = pkg.Tokenizer(pkg.patterns()["gpt4"])
-for name, buf in (("pageable", text), ("pinned", pinned.numpy())):
+only_encode = len(sys.argv) > 2 and sys.argv[2] == "encode"
+if only_encode:
+    tk.train(text[:64 << 20], 32768, "lexical")
+for name, buf in [] if only_encode else (("pageable", text), ("pinned", pinned.numpy())):
     for i in range(3):
         t0 = time.time(); tk.train(buf, 32768, "lexical"); torch.cuda.synchronize()
         print(f"train {name} #{i}: {time.time()-t0:.3f} s", flush=True)
