@@ -182,6 +182,8 @@ int mbpe_tokenizer_decode(mbpe_tokenizer *t, const uint32_t *ids, uint64_t n, ui
 int mbpe_tokenizer_get_merges(mbpe_tokenizer *t, uint32_t *merges_out, uint32_t cap_pairs, uint32_t *n_merges);
 int mbpe_tokenizer_last_train_stats(mbpe_tokenizer *t, mbpe_train_stats *stats, double *split_s, double *dedup_s,
                                     uint64_t *n_chunks, uint64_t *n_unique);
+/* streaming --encode: MBPE_E_UNSUPPORTED unless GPT-4 pattern, no special tokens, well-formed UTF-8 */
+int mbpe_tokenizer_encode_file(mbpe_tokenizer *t, const char *in_path, const char *out_path, uint64_t *n_ids);
 int mbpe_tokenizer_last_split_on_gpu(mbpe_tokenizer *t); /* 1: the last train() pre-tokenised on the device (section 6) */
 void mbpe_tokenizer_set_engine(mbpe_tokenizer *t, int engine);
 void mbpe_tokenizer_set_threads(mbpe_tokenizer *t, int n_threads); /* host pre-tokenisation threads, 0 = all */
@@ -256,6 +258,11 @@ void mbpe_device_corpus_free(mbpe_device_corpus *c);
  * without special tokens, :653-717). out_cap counts ids; len always suffices. */
 int mbpe_encode_text(mbpe_encoder *enc, mbpe_pretok *p, const uint8_t *text, uint64_t len, uint32_t *out,
                      uint64_t out_cap, uint64_t *n_out);
+/* file -> .enc file (raw little-endian u32 ids, examples/minbpe-cc.cpp:58-69) in blocks: reader thread, device
+ * pipeline, writer thread; memory use independent of the file size. MBPE_E_UNSUPPORTED if no block
+ * boundary can be found (then read the file and call mbpe_encode_text / mbpe_encode). */
+int mbpe_encode_file(mbpe_encoder *enc, mbpe_pretok *p, const char *in_path, const char *out_path, uint64_t *n_bytes,
+                     uint64_t *n_ids);
 /* a trainer over a device corpus (copied device to device; the corpus may be freed afterwards) */
 int mbpe_trainer_create_device(const mbpe_device_corpus *c, mbpe_trainer **out);
 

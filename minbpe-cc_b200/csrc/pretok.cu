@@ -17,7 +17,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -823,5 +826,238 @@ extern "C" int mbpe_encode_text(mbpe_encoder *enc, mbpe_pretok *p, const uint8_t
     if (pt_debug())
         fprintf(stderr, "[mbpe] encode_text: %.1f MB in %zu segment(s), %.1f ms\n", len / 1e6, n_seg, (pt_now() - t_start) * 1e3);
     if (rc == MBPE_OK) *n_out = produced;
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// File to file (the reference slurps the text through a stringstream and issues one write() per id,
+// examples/minbpe-cc.cpp:36-46, :58-69). Here: a reader thread fills pinned blocks, the calling thread runs the
+// upload / split + merge scan / download pipeline of mbpe_encode_text on them, a writer thread drains pinned id
+// blocks into the .enc file. Memory use is a handful of blocks whatever the file size; blocks end at matcher cuts,
+// the bytes after the last cut of a block are carried into the next one.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct Gate { // hand-over of numbered blocks between two threads
+    std::mutex mu;
+    std::condition_variable cv;
+    long long ready = -1; // highest block index published
+    bool failed = false;
+    void publish(long long k) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            ready = k;
+        }
+        cv.notify_all();
+    }
+    void fail() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            failed = true;
+        }
+        cv.notify_all();
+    }
+    bool wait_for(long long k) { // false: the other side failed
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return ready >= k || failed; });
+        return ready >= k;
+    }
+};
+} // namespace
+
+extern "C" int mbpe_encode_file(mbpe_encoder *enc, mbpe_pretok *p, const char *in_path, const char *out_path,
+                                uint64_t *n_bytes_out, uint64_t *n_ids_out) {
+    if (!enc || !p || !in_path || !out_path) return set_error(MBPE_E_INVALID, "null argument");
+    int rc = use_device(p->device);
+    if (rc) return rc;
+    FILE *fin = fopen(in_path, "rb");
+    if (!fin) return set_error(MBPE_E_IO, std::string("cannot open ") + in_path);
+    FILE *fout = fopen(out_path, "wb");
+    if (!fout) {
+        fclose(fin);
+        return set_error(MBPE_E_IO, std::string("cannot open ") + out_path);
+    }
+    const double t_begin = pt_now();
+    // a block = carried tail (< SEG) + up to SEG fresh bytes; blocks are smaller than the in-memory path's segments so
+    // that the pinned staging memory (3 x 10 x SEG) is allocated in ~0.1 s
+    const uint64_t SEG = std::min<uint64_t>(p->enc_seg_bytes, 16u << 20), CAP = 2 * SEG + 64;
+    constexpr int NB = 3;
+    uint8_t *h_in[NB] = {nullptr, nullptr, nullptr};
+    uint32_t *h_out[NB] = {nullptr, nullptr, nullptr};
+    bool ok_alloc = ensure_pipe(p, CAP) == MBPE_OK;
+    for (int i = 0; i < NB && ok_alloc; i++)
+        ok_alloc = cudaMallocHost(&h_in[i], CAP) == cudaSuccess && cudaMallocHost(&h_out[i], CAP * 4) == cudaSuccess;
+    auto release = [&]() {
+        for (int i = 0; i < NB; i++) {
+            cudaFreeHost(h_in[i]);
+            cudaFreeHost(h_out[i]);
+        }
+        fclose(fin);
+        fclose(fout);
+    };
+    if (!ok_alloc) {
+        release();
+        return set_error(MBPE_E_CUDA, "out of (pinned) memory");
+    }
+    // block k lives in h_in[k % NB]: [0, fill[k]) valid, the segment to encode is [0, cut[k]), the rest is carried over
+    std::vector<uint64_t> fill, cut;
+    std::vector<char> last;
+    std::mutex meta_mu;
+    Gate read_gate, in_free, write_gate, out_free;
+    std::vector<uint64_t> ids_in_block;
+    uint32_t err_flags = 0;
+    PretokIn<HostText> hin{HostText{nullptr}, 0, p->h_table.data(), &err_flags};
+    bool unsupported = false;
+    in_free.publish(NB - 1); // blocks 0..NB-1 may be filled right away
+    out_free.publish(NB - 1);
+    std::thread reader([&]() {
+        uint64_t carry = 0;
+        const uint8_t *carry_src = nullptr;
+        for (long long k = 0;; k++) {
+            if (!in_free.wait_for(k)) return;
+            uint8_t *buf = h_in[k % NB];
+            if (carry) memmove(buf, carry_src, carry); // from the previous block (a different buffer: NB >= 2)
+            const size_t got = fread(buf + carry, 1, SEG, fin);
+            const uint64_t filled = carry + got;
+            const bool eof = got < SEG;
+            uint64_t c = filled;
+            if (!eof) { // last cut of the block, not too close to the end (a code point may be cut off there)
+                c = 0;
+                PretokIn<HostText> in = hin;
+                in.t.p = buf;
+                in.len = filled;
+                bool bad = false;
+                for (uint64_t q = filled - 8; q > filled / 4 && !c && !bad; q--) {
+                    if ((buf[q] & 0xC0) == 0x80) continue;
+                    const PtCp prev = pt_before(in, q, bad), cur = pt_at(in, q, bad);
+                    if (!bad && pt_is_cut(prev.cls, cur)) c = q;
+                }
+                if (!c) {
+                    unsupported = true;
+                    read_gate.fail();
+                    return;
+                }
+            }
+            {
+                std::lock_guard<std::mutex> lk(meta_mu);
+                fill.push_back(filled);
+                cut.push_back(c);
+                last.push_back(eof);
+            }
+            read_gate.publish(k);
+            if (eof) return;
+            carry = filled - c;
+            carry_src = buf + c;
+            if (carry >= SEG) { // no cut in a whole segment: the carried tail would not fit the next block
+                unsupported = true;
+                read_gate.fail();
+                return;
+            }
+        }
+    });
+    bool write_failed = false;
+    long long n_blocks_total = -1; // set by the main thread when it has seen the last block
+    std::mutex total_mu;
+    std::thread writer([&]() {
+        for (long long k = 0;; k++) {
+            {
+                std::lock_guard<std::mutex> lk(total_mu);
+                if (n_blocks_total >= 0 && k >= n_blocks_total) return;
+            }
+            if (!write_gate.wait_for(k)) return;
+            uint64_t n;
+            {
+                std::lock_guard<std::mutex> lk(meta_mu);
+                n = ids_in_block[k];
+            }
+            if (n == ~0ull) return; // sentinel: no more blocks
+            if (fwrite(h_out[k % NB], 4, n, fout) != n) {
+                write_failed = true;
+                out_free.fail();
+                return;
+            }
+            out_free.publish(k + NB);
+        }
+    });
+    uint64_t total_bytes = 0, total_ids = 0;
+    cudaError_t ce = cudaSuccess;
+    long long k = 0;
+    const double t_loop = pt_now();
+    double t_wait_read = 0, t_wait_write = 0;
+    for (;; k++) {
+        double tw = pt_now();
+        const bool have_block = read_gate.wait_for(k);
+        t_wait_read += pt_now() - tw;
+        if (!have_block) {
+            rc = unsupported ? set_error(MBPE_E_UNSUPPORTED, "no safe block boundary found in the file (malformed UTF-8 or no letters/blanks): use the whole-file path")
+                             : set_error(MBPE_E_IO, "read failed");
+            break;
+        }
+        uint64_t n;
+        bool is_last;
+        {
+            std::lock_guard<std::mutex> lk(meta_mu);
+            n = cut[k];
+            is_last = last[k];
+        }
+        tw = pt_now();
+        const bool have_room = out_free.wait_for(k);
+        t_wait_write += pt_now() - tw;
+        if (!have_room) {
+            rc = set_error(MBPE_E_IO, std::string("write failed: ") + out_path);
+            break;
+        }
+        uint64_t n_chunks = 0, n_ids = 0;
+        if (n) {
+            if ((ce = cudaMemcpyAsync(p->d_pipe_text[k & 1], h_in[k % NB], n, cudaMemcpyHostToDevice, p->st_c)) != cudaSuccess) break;
+            if ((rc = mbpe_pretok_split_device(p, p->d_pipe_text[k & 1], n, p->d_pipe_off, n + 2, &n_chunks, p->st_c))) break;
+            if (k >= 2 && (ce = cudaStreamWaitEvent(p->st_c, p->ev_out[k & 1], 0)) != cudaSuccess) break;
+            if ((rc = mbpe_encode_device(enc, p->d_pipe_text[k & 1], n, p->d_pipe_off, n_chunks, p->d_pipe_ids[k & 1], n, p->d_seg_n, p->st_c))) break;
+            if ((ce = cudaMemcpyAsync(&n_ids, p->d_seg_n, 8, cudaMemcpyDeviceToHost, p->st_c)) != cudaSuccess) break;
+            if ((ce = cudaStreamSynchronize(p->st_c)) != cudaSuccess) break;
+        }
+        in_free.publish(k + NB); // the block's bytes are on the device (the reader copied its carried tail before this)
+        // previous block's ids have landed? then hand them to the writer; this block's download runs under the next block
+        if (k >= 1) {
+            if ((ce = cudaEventSynchronize(p->ev_out[(k - 1) & 1])) != cudaSuccess) break;
+            write_gate.publish(k - 1);
+        }
+        if ((ce = cudaMemcpyAsync(h_out[k % NB], p->d_pipe_ids[k & 1], n_ids * 4, cudaMemcpyDeviceToHost, p->st_out)) != cudaSuccess) break;
+        if ((ce = cudaEventRecord(p->ev_out[k & 1], p->st_out)) != cudaSuccess) break;
+        {
+            std::lock_guard<std::mutex> lk(meta_mu);
+            ids_in_block.push_back(n_ids);
+        }
+        total_bytes += n;
+        total_ids += n_ids;
+        if (is_last) {
+            if ((ce = cudaEventSynchronize(p->ev_out[k & 1])) != cudaSuccess) break;
+            {
+                std::lock_guard<std::mutex> lk(total_mu);
+                n_blocks_total = k + 1;
+            }
+            write_gate.publish(k);
+            break;
+        }
+    }
+    if (rc != MBPE_OK || ce != cudaSuccess) { // unblock the helpers
+        in_free.fail();
+        write_gate.fail();
+    }
+    const double t_joining = pt_now();
+    reader.join();
+    writer.join();
+    if (pt_debug())
+        fprintf(stderr, "[mbpe] encode_file: %.1f MB, %lld blocks: setup %.0f ms, pipeline %.0f ms (waiting for the reader %.0f ms, for the writer %.0f ms), "
+                        "writer tail %.0f ms\n", total_bytes / 1e6, k + 1, (t_loop - t_begin) * 1e3, (t_joining - t_loop) * 1e3,
+                t_wait_read * 1e3, t_wait_write * 1e3, (pt_now() - t_joining) * 1e3);
+    cudaStreamSynchronize(p->st_c);
+    cudaStreamSynchronize(p->st_out);
+    if (rc == MBPE_OK && ce != cudaSuccess) rc = cuda_fail(ce, "encode_file pipeline", __FILE__, __LINE__);
+    if (rc == MBPE_OK && (write_failed || fflush(fout) != 0)) rc = set_error(MBPE_E_IO, std::string("write failed: ") + out_path);
+    release();
+    if (rc == MBPE_OK) {
+        if (n_bytes_out) *n_bytes_out = total_bytes;
+        if (n_ids_out) *n_ids_out = total_ids;
+    }
     return rc;
 }

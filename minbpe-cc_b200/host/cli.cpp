@@ -47,7 +47,12 @@ static void usage() {
                  "  --threads INT               host pre-tokenisation threads (0 = all)\n";
 }
 
+static double cli_now() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 int main(int argc, char **argv) {
+    const double t_main = cli_now();
     std::string input_path, output_path, special_path, encoder = "gpt4", model_path = "./output.model";
     std::string conflict = "first", engine = "persistent";
     bool train = false, decode = false, encode = false, write_vocab = false, verbose = false;
@@ -166,8 +171,17 @@ int main(int argc, char **argv) {
         std::cout << "Encoding input file \"" << input_path << "\" encoder " << encoder << " model path " << model_path
                   << " output to " << output_path << "\n";
         rc = rt.load(model_path, verbose);
+        if (getenv("MBPE_DEBUG")) fprintf(stderr, "[mbpe] cli: model loaded %.0f ms after start\n", (cli_now() - t_main) * 1e3);
         std::string text;
-        if (rc == 0 && slurp(input_path, text, err)) {
+        uint64_t n_streamed = 0;
+        std::error_code size_ec;
+        const bool big = rc == 0 && special_path.empty() && !getenv("MBPE_CLI_NO_STREAM") && std::filesystem::file_size(input_path, size_ec) >= (8u << 20) && !size_ec;
+        if (big && (rc = rt.encode_file(input_path, output_path, &n_streamed)) == 0) {
+            // block-wise: disk -> pinned memory -> GPU -> pinned memory -> disk, never the whole file in memory
+            std::cout << "Writing " << n_streamed << " encoded tokens\nSuccess\n";
+        } else if (big && rc != MBPE_E_UNSUPPORTED) {
+            std::cerr << "Encoding failed: " << rt.error() << "\n";
+        } else if ((rc = (rc == MBPE_E_UNSUPPORTED ? 0 : rc)) == 0 && slurp(input_path, text, err)) {
             std::vector<Token> ids;
             rc = rt.encode(text, verbose, ids);
             if (rc == 0) {

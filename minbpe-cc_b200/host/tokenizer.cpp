@@ -241,6 +241,17 @@ int Tokenizer::encode_into(std::string_view text, Token *out, uint64_t cap, uint
     return MBPE_OK;
 }
 
+// File to file without holding either in memory (examples/minbpe-cc.cpp:212-242 slurps and writes id by id): only for
+// the GPT-4 pattern without special tokens; MBPE_E_UNSUPPORTED tells the caller to take the whole-file path.
+int Tokenizer::encode_file(const std::string &in_path, const std::string &out_path, uint64_t *n_ids) {
+    int rc = ensure_encoder();
+    if (rc) return rc;
+    if (!special_tokens_.empty() || !use_gpu_split(~size_t(0) >> 1)) return MBPE_E_UNSUPPORTED;
+    rc = mbpe_encode_file(encoder_, pretok_, in_path.c_str(), out_path.c_str(), nullptr, n_ids);
+    if (rc && rc != MBPE_E_UNSUPPORTED) error_ = mbpe_last_error();
+    return rc;
+}
+
 int Tokenizer::encode(std::string_view text, bool verbose, std::vector<Token> &out) {
     out.clear();
     int rc = ensure_encoder();
@@ -522,6 +533,12 @@ extern "C" int mbpe_tokenizer_encode(mbpe_tokenizer *t, const uint8_t *text, uin
                                      uint64_t out_cap, uint64_t *n_out) {
     if (!t || !n_out || (!text && len)) return fail(MBPE_E_INVALID, "null argument");
     int rc = t->tk.encode_into(std::string_view(reinterpret_cast<const char *>(text), len), out, out_cap, n_out);
+    return rc ? fail(rc, t->tk.error()) : MBPE_OK;
+}
+extern "C" int mbpe_tokenizer_encode_file(mbpe_tokenizer *t, const char *in_path, const char *out_path, uint64_t *n_ids) {
+    if (!t || !in_path || !out_path) return fail(MBPE_E_INVALID, "null argument");
+    int rc = t->tk.encode_file(in_path, out_path, n_ids);
+    if (rc == MBPE_E_UNSUPPORTED) return fail(rc, "streaming encode needs the GPT-4 pattern, no special tokens and well-formed UTF-8");
     return rc ? fail(rc, t->tk.error()) : MBPE_OK;
 }
 extern "C" int mbpe_tokenizer_decode(mbpe_tokenizer *t, const uint32_t *ids, uint64_t n, uint8_t *out,

@@ -249,3 +249,55 @@ def test_segmented_corpus_and_encode_text(pkg, monkeypatch):
         assert np.array_equal(pt.encode_text(enc, text), want_ids), seg
         pt.close()
     enc.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seg", ["65536", "1048576", str(64 << 20)])
+def test_streaming_file_encode_equals_in_memory(pkg, tmp_path, monkeypatch, seg):
+    """mbpe_encode_file (reader thread -> device pipeline -> writer thread, blocks cut at matcher cuts with carried
+    tails) writes the same .enc bytes as encoding the whole text in memory"""
+    monkeypatch.setenv("MBPE_ENCODE_SEG_BYTES", seg)
+    text = pkg.synth_corpus(0x5EED0009, 12 << 20).tobytes()
+    tok, off, w, _ = pkg.split_dedup(pkg.patterns()["gpt4"], text[:4 << 20])
+    merges, _, _ = pkg.train(tok, off, w, 1500, "lexical")
+    model = tmp_path / "m.model"
+    pkg.write_model(str(model), pkg.patterns()["gpt4"], None, merges)
+    tk = pkg.Tokenizer(pkg.patterns()["gpt4"])
+    tk.load(model)
+    want = tk.encode(text)
+    src, dst = tmp_path / "in.txt", tmp_path / "out.enc"
+    src.write_bytes(text)
+    n = tk.encode_file(src, dst)
+    got = np.fromfile(dst, np.uint32)
+    assert n == len(want) == len(got) and np.array_equal(got, want)
+    # empty and tiny files
+    (tmp_path / "e.txt").write_bytes(b"")
+    assert tk.encode_file(tmp_path / "e.txt", tmp_path / "e.enc") == 0 and (tmp_path / "e.enc").stat().st_size == 0
+    (tmp_path / "t.txt").write_bytes(b"hello world")
+    assert tk.encode_file(tmp_path / "t.txt", tmp_path / "t.enc") == len(tk.encode(b"hello world"))
+
+
+@pytest.mark.gpu
+def test_cli_streams_big_inputs_and_matches_whole_file_path(pkg, tmp_path):
+    cli = os.path.join(ROOT, "minbpe-cc_b200", "bin", "minbpe-cc")
+    text = pkg.synth_corpus(0x5EED000A, 9 << 20).tobytes()  # >= 8 MiB: the CLI takes the streaming path
+    src = tmp_path / "in.txt"
+    src.write_bytes(text)
+    model = tmp_path / "m.model"
+    small = tmp_path / "small.txt"
+    small.write_bytes(text[:1 << 20])
+    r = subprocess.run([cli, "--train", "-i", str(small), "-m", str(model), "--vocab-size", "700", "--encoder", "gpt4",
+                        "-c", "lexical"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    outs = {}
+    for name, env in (("stream", {}), ("whole", {"MBPE_GPU_SPLIT": "0"})):
+        out = tmp_path / (name + ".enc")
+        r = subprocess.run([cli, "--encode", "-i", str(src), "-m", str(model), "-o", str(out)], capture_output=True,
+                           text=True, env={**os.environ, **env})
+        assert r.returncode == 0 and "Success" in r.stdout, (r.stdout, r.stderr)
+        outs[name] = out.read_bytes()
+    assert outs["stream"] == outs["whole"] and len(outs["stream"]) > 0
+    back = tmp_path / "back.txt"
+    r = subprocess.run([cli, "--decode", "-i", str(tmp_path / "stream.enc"), "-m", str(model), "-o", str(back)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and back.read_bytes() == text
