@@ -195,6 +195,11 @@ void mbpe_tokenizer_set_threads(mbpe_tokenizer *t, int n_threads); /* host pre-t
  * [start,end) pairs. Call with starts == NULL to count. */
 int mbpe_split(const char *pattern, const uint8_t *text, uint64_t len, int n_threads, uint64_t *starts,
                uint64_t *ends, uint64_t cap, uint64_t *n_chunks);
+/* special-token splitter (Tokenizer.h:605-650) in one sweep per token: parts [starts[i], ends[i]) in text order,
+ * ids[i] < 0 for ordinary text, else the special token's id. special_contents = "token id" lines (:482-485).
+ * Call with starts == NULL to count. */
+int mbpe_special_split(const char *special_contents, uint64_t special_len, const uint8_t *text, uint64_t len,
+                       uint64_t *starts, uint64_t *ends, int64_t *ids, uint64_t cap, uint64_t *n_parts);
 /* 2-bit class per code point (0 other, 1 \p{L}, 2 \p{N}, 3 \s), 0x110000/4 bytes, read out of the linked PCRE2 with
  * the reference's compile options (Tokenizer.h:407): what the GPU matcher of the GPT-4 pattern classifies with.
  * MBPE_E_REGEX if that PCRE2's caseless folding is not the one the matcher assumes. */

@@ -30,7 +30,7 @@ EXPORTS = [
     "mbpe_tokenizer_set_special_tokens", "mbpe_tokenizer_train", "mbpe_tokenizer_save", "mbpe_tokenizer_load",
     "mbpe_tokenizer_encode", "mbpe_tokenizer_decode", "mbpe_tokenizer_get_merges",
     "mbpe_tokenizer_last_train_stats", "mbpe_tokenizer_last_split_on_gpu", "mbpe_tokenizer_encode_file", "mbpe_encode_file", "mbpe_tokenizer_set_engine", "mbpe_tokenizer_set_threads",
-    "mbpe_split", "mbpe_pretok_class_table", "mbpe_dedup",
+    "mbpe_split", "mbpe_special_split", "mbpe_pretok_class_table", "mbpe_dedup",
     "mbpe_pretok_create", "mbpe_pretok_destroy", "mbpe_pretok_split_device", "mbpe_pretok_split",
     "mbpe_pretok_dedup_device", "mbpe_pretok_dedup_segments", "mbpe_pretok_corpus", "mbpe_encode_text", "mbpe_device_corpus_download", "mbpe_device_corpus_free",
     "mbpe_trainer_create_device", "mbpe_split_dedup", "mbpe_plan_shards", "mbpe_write_model", "mbpe_synth_corpus",
@@ -471,6 +471,17 @@ def split(pattern: str, text: bytes, n_threads=0):
     _ck(lib().mbpe_split(pattern.encode(), _p(buf, C.c_uint8), C.c_uint64(len(text)), n_threads, _p(s, C.c_uint64),
                          _p(e, C.c_uint64), C.c_uint64(cap), C.byref(n)))
     return s[:n.value].copy(), e[:n.value].copy()
+
+
+def special_split(special_contents: bytes, text: bytes):
+    """[(start, end, id)]; id < 0 = ordinary text (Tokenizer.h:605-650)"""
+    n = C.c_uint64()
+    buf = _u8(text)
+    args = (special_contents, C.c_uint64(len(special_contents)), _p(buf, C.c_uint8), C.c_uint64(len(text)))
+    _ck(lib().mbpe_special_split(*args, None, None, None, C.c_uint64(0), C.byref(n)))
+    s, e, i = np.zeros(max(n.value, 1), np.uint64), np.zeros(max(n.value, 1), np.uint64), np.zeros(max(n.value, 1), np.int64)
+    _ck(lib().mbpe_special_split(*args, _p(s, C.c_uint64), _p(e, C.c_uint64), _p(i, C.c_int64), C.c_uint64(len(s)), C.byref(n)))
+    return [(int(s[k]), int(e[k]), int(i[k])) for k in range(n.value)]
 
 
 def pretok_class_table():

@@ -75,6 +75,14 @@ void synth_corpus(uint64_t seed, uint8_t *out, uint64_t n, int n_threads);
 
 int hardware_threads();
 
+// Tokenizer.h:605-650: cut the text at special tokens (earliest occurrence first; equal positions go to the token the
+// map iterates first). id < 0: ordinary text [start, end); otherwise the special token with that id.
+struct SpecialPart {
+    size_t start, end;
+    int64_t id;
+};
+std::vector<SpecialPart> split_special_spans(std::string_view text, const std::unordered_map<std::string, Token> &specials);
+
 // The reference's Tokenizer, method for method (Tokenizer.h:379-927).
 class Tokenizer {
   public:

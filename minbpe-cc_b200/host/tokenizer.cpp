@@ -148,34 +148,55 @@ int Tokenizer::train(std::string_view text, int vocab_size, CONFLICT_RESOLUTION 
     return MBPE_OK;
 }
 
-std::vector<std::string> Tokenizer::split_on_special(std::string_view text) {
-    std::vector<std::string> result;
-    if (special_tokens_.empty()) {
-        result.emplace_back(text);
-        return result;
+// Tokenizer.h:605-650 finds, from the current position, the next occurrence of EVERY special token, takes the earliest
+// (ties: the first in the map's iteration order, :618-626) and repeats -- O(occurrences x tokens x text). Same result
+// in one sweep per token: a token's next occurrence is searched again only once the position has
+// passed the one already known, so every token scans the text once overall.
+std::vector<SpecialPart> split_special_spans(std::string_view text,
+                                             const std::unordered_map<std::string, Token> &specials) {
+    std::vector<SpecialPart> parts;
+    if (specials.empty()) {
+        parts.push_back({0, text.size(), -1});
+        return parts;
     }
+    struct Next {
+        const std::string *tok;
+        Token id;
+        size_t at; // next occurrence at or after the position it was searched from; npos = none left
+    };
+    std::vector<Next> next;
+    next.reserve(specials.size());
+    for (const auto &kv : specials) next.push_back({&kv.first, kv.second, 0}); // map iteration order = tie order
+    for (auto &n : next) n.at = n.tok->empty() ? std::string::npos : text.find(*n.tok, 0);
     size_t pos = 0, last = 0;
     while (pos < text.size()) {
-        size_t found_pos = std::string::npos, found_len = 0;
-        Token found_id = 0;
-        for (const auto &kv : special_tokens_) { // earliest occurrence wins; ties go to map order (Tokenizer.h:618-626)
-            size_t p = text.find(kv.first, pos);
-            if (p != std::string::npos && (found_pos == std::string::npos || p < found_pos)) {
-                found_pos = p;
-                found_len = kv.first.size();
-                found_id = kv.second;
-            }
+        const Next *best = nullptr;
+        for (auto &n : next) {
+            if (n.at != std::string::npos && n.at < pos) n.at = text.find(*n.tok, pos); // stale: search on from pos
+            if (n.at != std::string::npos && (!best || n.at < best->at)) best = &n;
         }
-        if (found_pos == std::string::npos) break;
-        if (found_pos > last) result.emplace_back(text.substr(last, found_pos - last));
-        std::string marker(1, '\0');
-        marker += std::to_string(found_id);
-        result.push_back(std::move(marker));
-        pos = found_pos + found_len;
+        if (!best) break;
+        if (best->at > last) parts.push_back({last, best->at, -1});
+        parts.push_back({best->at, best->at + best->tok->size(), (int64_t)best->id});
+        pos = best->at + best->tok->size();
         last = pos;
     }
-    if (last < text.size()) result.emplace_back(text.substr(last));
-    if (result.empty()) result.emplace_back(text);
+    if (last < text.size()) parts.push_back({last, text.size(), -1});
+    if (parts.empty()) parts.push_back({0, text.size(), -1});
+    return parts;
+}
+
+std::vector<std::string> Tokenizer::split_on_special(std::string_view text) {
+    std::vector<std::string> result;
+    for (const auto &p : split_special_spans(text, special_tokens_)) {
+        if (p.id < 0) {
+            result.emplace_back(text.substr(p.start, p.end - p.start));
+        } else { // marker "\0<id>" (Tokenizer.h:631-634)
+            std::string marker(1, '\0');
+            marker += std::to_string(p.id);
+            result.push_back(std::move(marker));
+        }
+    }
     return result;
 }
 
@@ -600,6 +621,26 @@ extern "C" int mbpe_split(const char *pattern, const uint8_t *text, uint64_t len
     for (size_t i = 0; i < spans.size(); i++) {
         starts[i] = spans[i].start;
         ends[i] = spans[i].end;
+    }
+    return MBPE_OK;
+}
+
+extern "C" int mbpe_special_split(const char *special_contents, uint64_t special_len, const uint8_t *text, uint64_t len,
+                                  uint64_t *starts, uint64_t *ends, int64_t *ids, uint64_t cap, uint64_t *n_parts) {
+    if (!n_parts || (!text && len) || (!special_contents && special_len)) return fail(MBPE_E_INVALID, "null argument");
+    std::unordered_map<std::string, Token> specials; // filled exactly as set_special_tokens_from_file does (:482-485)
+    std::istringstream iss(std::string(special_contents ? special_contents : "", special_len));
+    std::string key;
+    Token value;
+    while (iss >> key >> value) specials[key] = value;
+    const auto parts = split_special_spans(std::string_view(reinterpret_cast<const char *>(text), len), specials);
+    *n_parts = parts.size();
+    if (!starts || !ends || !ids) return MBPE_OK;
+    if (parts.size() > cap) return fail(MBPE_E_CAPACITY, "part arrays too small");
+    for (size_t i = 0; i < parts.size(); i++) {
+        starts[i] = parts[i].start;
+        ends[i] = parts[i].end;
+        ids[i] = parts[i].id;
     }
     return MBPE_OK;
 }

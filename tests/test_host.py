@@ -137,3 +137,21 @@ def test_fast_scanner_equals_pcre2_on_random_mixes(pkg, oracle):
             s0, e0 = oracle.split(text, oracle.PATTERNS[enc])
             s1, e1 = pkg.split(pkg.patterns()[enc], text, 8)
             assert np.array_equal(s0, s1) and np.array_equal(e0, e1), (trial, enc)
+
+
+def test_special_split_one_sweep_matches_reference_rule(pkg):
+    """the one-sweep-per-token splitter gives the parts of the reference's find-everything-every-time loop
+    (Tokenizer.h:605-650, restated in oracle.split_on_special), incl. overlapping tokens and tokens that contain others"""
+    from oracle import oracle as O
+    rng = np.random.default_rng(11)
+    specials = [(b"<|a|>", 1000), (b"|><|", 1001), (b"ab", 1002), (b"bca", 1003), (b"<|endoftext|>", 1004), (b"aab", 1005)]
+    contents = b"".join(t + b" " + str(i).encode() + b"\n" for t, i in specials)
+    pieces = [t for t, _ in specials] + [b"a", b"b", b"c", b"<", b"|", b">", b" ", b"x", b"<|", b"|>"]
+    for _ in range(300):
+        text = b"".join(pieces[k] for k in rng.integers(0, len(pieces), int(rng.integers(0, 40))))
+        got = pkg.special_split(contents, text)
+        parts = [text[s:e] if i < 0 else b"\0" + str(i).encode() for s, e, i in got]
+        # no two of these tokens can match at the same position unless one is a prefix of the other; none is
+        assert parts == O.split_on_special(text, specials), text
+    assert pkg.special_split(b"", b"plain") == [(0, 5, -1)]
+    assert pkg.special_split(contents, b"") == [(0, 0, -1)]
