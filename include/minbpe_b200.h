@@ -232,7 +232,9 @@ int mbpe_synth_corpus(uint64_t seed, uint8_t *out, uint64_t n, int n_threads);
  *    is refused with MBPE_E_UNSUPPORTED; the caller then uses mbpe_split (PCRE2 itself).
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct mbpe_pretok mbpe_pretok;
-int mbpe_pretok_create(int device, mbpe_pretok **out);
+int mbpe_pretok_create(int device, mbpe_pretok **out); /* matches the GPT-4 pattern until told otherwise */
+/* pattern = mbpe_gpt4_split_pattern() or mbpe_gpt2_split_pattern(); MBPE_E_UNSUPPORTED for anything else */
+int mbpe_pretok_select(mbpe_pretok *p, const char *pattern);
 void mbpe_pretok_destroy(mbpe_pretok *p);
 /* resident text (< 4 GiB) -> chunk offsets: d_off_out[0 .. n_chunks] (u32, last = len), the layout
  * mbpe_encode_device takes. off_cap counts u32 entries; len + 2 always suffices. */

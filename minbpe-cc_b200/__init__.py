@@ -31,7 +31,7 @@ EXPORTS = [
     "mbpe_tokenizer_encode", "mbpe_tokenizer_decode", "mbpe_tokenizer_get_merges",
     "mbpe_tokenizer_last_train_stats", "mbpe_tokenizer_last_split_on_gpu", "mbpe_tokenizer_encode_file", "mbpe_encode_file", "mbpe_tokenizer_set_engine", "mbpe_tokenizer_set_threads",
     "mbpe_split", "mbpe_special_split", "mbpe_pretok_class_table", "mbpe_dedup",
-    "mbpe_pretok_create", "mbpe_pretok_destroy", "mbpe_pretok_split_device", "mbpe_pretok_split",
+    "mbpe_pretok_create", "mbpe_pretok_select", "mbpe_pretok_destroy", "mbpe_pretok_split_device", "mbpe_pretok_split",
     "mbpe_pretok_dedup_device", "mbpe_pretok_dedup_segments", "mbpe_pretok_corpus", "mbpe_encode_text", "mbpe_device_corpus_download", "mbpe_device_corpus_free",
     "mbpe_trainer_create_device", "mbpe_split_dedup", "mbpe_plan_shards", "mbpe_write_model", "mbpe_synth_corpus",
 ]
@@ -212,9 +212,11 @@ class DeviceCorpus(C.Structure):
 class Pretok:
     """GPU pre-tokeniser + chunk dedup for the GPT-4 split pattern (Tokenizer.h:500-544)."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, pattern=None):
         self.h = C.c_void_p()
         _ck(lib().mbpe_pretok_create(device, C.byref(self.h)))
+        if pattern is not None:
+            _ck(lib().mbpe_pretok_select(self.h, pattern.encode()))
 
     def split(self, text: bytes):
         """chunk offsets (n_chunks + 1, u64): chunk c = text[off[c]:off[c+1]]"""

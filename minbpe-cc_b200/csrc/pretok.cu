@@ -38,9 +38,9 @@ constexpr int PM_THREADS = 256;
 constexpr uint32_t PT_WINDOW = 32; // bytes per thread = one bitmap word
 
 __global__ void __launch_bounds__(PM_THREADS) k_pretok_mark(const uint8_t *text, uint64_t len, const uint8_t *table,
-                                                             uint32_t *bitmap, uint32_t *err, uint64_t max_crawl) {
+                                                             uint32_t *bitmap, uint32_t *err, uint64_t max_crawl, uint32_t kind) {
     const uint64_t n_win = (len + PT_WINDOW - 1) / PT_WINDOW;
-    PretokIn<DevText> in{DevText{text}, len, table, err};
+    PretokIn<DevText> in{DevText{text}, len, table, err, kind};
     for (uint64_t w = blockIdx.x * (uint64_t)PM_THREADS + threadIdx.x; w < n_win; w += (uint64_t)gridDim.x * PM_THREADS) {
         uint64_t cur = ~0ull;
         uint32_t bits = 0;
@@ -329,6 +329,7 @@ struct mbpe_pretok {
     uint32_t *d_small = nullptr;          // [0] err, [1] ticket, [2] overflow
     unsigned long long *d_count = nullptr; // set-bit count
     uint64_t max_crawl = 1u << 16;
+    uint32_t kind = PT_GPT4; // which built-in pattern, mbpe_pretok_select
     uint64_t launches = 0;
     uint8_t *d_seg_text = nullptr; // segment buffers of mbpe_pretok_corpus, kept between calls
     uint32_t *d_seg_off = nullptr;
@@ -368,6 +369,18 @@ extern "C" int mbpe_pretok_create(int device, mbpe_pretok **out) {
     MB_CUDA(cudaMalloc(&p->d_count, 8));
     MB_CUDA(cudaFuncSetAttribute(k_bits_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BcSmem)));
     *out = p;
+    return MBPE_OK;
+}
+
+// which of the two built-in patterns the handle matches (Tokenizer.h:59-60); anything else has no device matcher
+extern "C" int mbpe_pretok_select(mbpe_pretok *p, const char *pattern) {
+    if (!p || !pattern) return set_error(MBPE_E_INVALID, "null argument");
+    if (!strcmp(pattern, mbpe_gpt4_split_pattern()))
+        p->kind = PT_GPT4;
+    else if (!strcmp(pattern, mbpe_gpt2_split_pattern()))
+        p->kind = PT_GPT2;
+    else
+        return set_error(MBPE_E_UNSUPPORTED, "only the GPT-2 and GPT-4 split patterns have a device matcher");
     return MBPE_OK;
 }
 
@@ -457,7 +470,7 @@ extern "C" int mbpe_pretok_split_device(mbpe_pretok *p, const uint8_t *d_text, u
     MB_CUDA(cudaMemsetAsync(p->d_bitmap, 0, n_words * 4, st));
     MB_CUDA(cudaMemsetAsync(p->d_small, 0, 16, st));
     const unsigned grid = (unsigned)std::min<uint64_t>((n_words + PM_THREADS - 1) / PM_THREADS, (uint64_t)p->sms * 32);
-    k_pretok_mark<<<grid, PM_THREADS, 0, st>>>(d_text, len, p->d_table, p->d_bitmap, p->d_small, p->max_crawl);
+    k_pretok_mark<<<grid, PM_THREADS, 0, st>>>(d_text, len, p->d_table, p->d_bitmap, p->d_small, p->max_crawl, p->kind);
     p->launches++;
     MB_CUDA(cudaGetLastError());
     if ((rc = bits_compact(p, p->d_bitmap, n_words, d_off_out, off_cap - 1, st))) return rc;
@@ -654,7 +667,7 @@ struct HostText {
 static bool plan_segments(const mbpe_pretok *pt, const uint8_t *text, uint64_t len, uint64_t seg_bytes, std::vector<uint64_t> &bounds) {
     bounds.assign(1, 0);
     uint32_t err = 0;
-    PretokIn<HostText> in{HostText{text}, len, pt->h_table.data(), &err};
+    PretokIn<HostText> in{HostText{text}, len, pt->h_table.data(), &err, pt->kind};
     while (len - bounds.back() > seg_bytes + seg_bytes / 4) {
         const uint64_t lo = bounds.back() + seg_bytes / 2, hi = bounds.back() + seg_bytes;
         uint64_t cut = 0;
@@ -905,7 +918,7 @@ extern "C" int mbpe_encode_file(mbpe_encoder *enc, mbpe_pretok *p, const char *i
     Gate read_gate, in_free, write_gate, out_free;
     std::vector<uint64_t> ids_in_block;
     uint32_t err_flags = 0;
-    PretokIn<HostText> hin{HostText{nullptr}, 0, p->h_table.data(), &err_flags};
+    PretokIn<HostText> hin{HostText{nullptr}, 0, p->h_table.data(), &err_flags, p->kind};
     bool unsupported = false;
     in_free.publish(NB - 1); // blocks 0..NB-1 may be filled right away
     out_free.publish(NB - 1);

@@ -1,4 +1,5 @@
-// pretok_core.cuh -- the GPT-4 split pattern (Tokenizer.h:60) as a hand-written matcher, host + device.
+// pretok_core.cuh -- the GPT-4 split pattern (Tokenizer.h:60) as a hand-written matcher, host + device (the simpler
+// GPT-2 pattern of :59 rides along, see pretok_match_gpt2).
 //
 //   '(?i:[sdmt]|ll|ve|re) | [^\r\n\p{L}\p{N}]?+\p{L}+ | \p{N}{1,3} |  ?[^\s\p{L}\p{N}]++[\r\n]* | \s*[\r\n] | \s+(?!\S) | \s+
 //
@@ -34,6 +35,7 @@ namespace mbpe {
 enum : uint32_t { PT_O = 0, PT_L = 1, PT_N = 2, PT_S = 3 }; // other, \p{L}, \p{N}, \s
 constexpr uint32_t PT_TABLE_BYTES = 0x110000 / 4;           // 2 bits per code point
 enum : uint32_t { PT_ERR_UTF8 = 1, PT_ERR_LONG = 2 };       // reasons to hand the text back to the host path
+enum : uint32_t { PT_GPT4 = 0, PT_GPT2 = 1 };               // which built-in pattern (Tokenizer.h:60 / :59)
 
 // Text accessor concept: uint8_t operator[](uint64_t) const.
 template <class Text>
@@ -42,6 +44,7 @@ struct PretokIn {
     uint64_t len;         // end of subject (look-aheads see nothing beyond it)
     const uint8_t *table; // PT_TABLE_BYTES
     uint32_t *err;        // or-ed PT_ERR_*
+    uint32_t kind;        // PT_GPT4 or PT_GPT2
 };
 
 PT_HD void pt_raise(uint32_t *err, uint32_t what) {
@@ -113,10 +116,67 @@ PT_HD uint32_t pt_fold(uint32_t cp) {
 }
 PT_HD bool pt_is_nl(uint32_t cp) { return cp == '\r' || cp == '\n'; }
 
+// The GPT-2 pattern (Tokenizer.h:59), compiled by the reference without CASELESS:
+//   '(?:[sdmt]|ll|ve|re) |  ?\p{L}+ |  ?\p{N}+ |  ?[^\s\p{L}\p{N}]+ | \s+(?!\S) | \s+
+// The same two cut rules hold: letters are consumed only by alternatives 1-2, which end where the letters end, and
+// alternatives 1-4 never swallow a following blank.
+template <class Text>
+PT_HD uint64_t pretok_match_gpt2(const PretokIn<Text> &in, uint64_t p, uint32_t *last_cls, bool &bad) {
+    const uint64_t len = in.len;
+    const PtCp c0 = pt_at(in, p, bad);
+    if (c0.cp == '\'' && p + 1 < len) { // 1. case-sensitive, ASCII only
+        const uint32_t d = in.t[p + 1];
+        if (d == 's' || d == 'd' || d == 'm' || d == 't') {
+            *last_cls = PT_L;
+            return p + 2;
+        }
+        if (p + 2 < len) {
+            const uint32_t e = in.t[p + 2];
+            if ((d == 'l' && e == 'l') || (d == 'v' && e == 'e') || (d == 'r' && e == 'e')) {
+                *last_cls = PT_L;
+                return p + 3;
+            }
+        }
+    }
+    { // 2-4. optional blank, then a run of one class (a blank that is not followed by such a run is white space: 5-6)
+        const uint64_t q = (c0.cp == ' ') ? p + 1 : p;
+        if (q < len) {
+            const PtCp cq = (q == p) ? c0 : pt_at(in, q, bad);
+            if (cq.cls != PT_S) {
+                uint64_t r = q + cq.n;
+                while (r < len) {
+                    const PtCp c = pt_at(in, r, bad);
+                    if (c.cls != cq.cls) break;
+                    r += c.n;
+                }
+                *last_cls = cq.cls;
+                return r;
+            }
+        }
+    }
+    uint64_t r = p, last_start = p; // 5-6. white space
+    uint32_t n_cp = 0;
+    while (r < len) {
+        const PtCp c = pt_at(in, r, bad);
+        if (c.cls != PT_S) break;
+        last_start = r;
+        r += c.n;
+        n_cp++;
+    }
+    *last_cls = PT_S;
+    if (n_cp == 0) {
+        bad = true;
+        return p + c0.n;
+    }
+    if (r == len || n_cp < 2) return r; // end of subject, or a single white-space code point (\s+)
+    return last_start;                  // \s+(?!\S): give one code point back
+}
+
 // One match starting at p (p < len). Returns its end; *last_cls = class of the last code point matched (PT_S if it
 // ends with CR/LF), which is what the cut test needs.
 template <class Text>
 PT_HD uint64_t pretok_match(const PretokIn<Text> &in, uint64_t p, uint32_t *last_cls, bool &bad) {
+    if (in.kind == PT_GPT2) return pretok_match_gpt2(in, p, last_cls, bad);
     const uint64_t len = in.len;
     const PtCp c0 = pt_at(in, p, bad);
     // 1. '(?i:[sdmt]|ll|ve|re)

@@ -25,9 +25,9 @@ Tokenizer::~Tokenizer() {
     if (pretok_) mbpe_pretok_destroy(pretok_);
 }
 
-// The GPT-4 pattern has a device matcher (csrc/pretok_core.cuh). Texts of at least this many bytes go through it;
+// The GPT-4 and GPT-2 patterns have a device matcher (csrc/pretok_core.cuh). Texts of at least this many bytes go through it;
 // MBPE_GPU_SPLIT=0 keeps pre-tokenisation on the host (PCRE2), MBPE_GPU_SPLIT=<n> sets the threshold (1 = always).
-// Under this pattern no chunk can be a ready-made id (a chunk "\0<int>"): a chunk that starts with NUL
+// Under these patterns no chunk can be a ready-made id (a chunk "\0<int>"): a chunk that starts with NUL
 // continues with letters (alternative 2) or symbols (alternative 4), never with a digit, so std::stoi always throws.
 static uint64_t gpu_split_min_bytes() {
     const char *v = getenv("MBPE_GPU_SPLIT");
@@ -37,8 +37,14 @@ static uint64_t gpu_split_min_bytes() {
 }
 
 bool Tokenizer::use_gpu_split(size_t n_bytes) {
-    if (pattern_ != kGpt4Pattern || n_bytes < gpu_split_min_bytes()) return false;
-    if (!pretok_ && !pretok_failed_ && mbpe_pretok_create(device_, &pretok_) != MBPE_OK) pretok_failed_ = true;
+    if ((pattern_ != kGpt4Pattern && pattern_ != kGpt2Pattern) || n_bytes < gpu_split_min_bytes()) return false;
+    if (!pretok_ && !pretok_failed_) {
+        if (mbpe_pretok_create(device_, &pretok_) != MBPE_OK || mbpe_pretok_select(pretok_, pattern_.c_str()) != MBPE_OK) {
+            if (pretok_) mbpe_pretok_destroy(pretok_);
+            pretok_ = nullptr;
+            pretok_failed_ = true;
+        }
+    }
     return pretok_ != nullptr;
 }
 

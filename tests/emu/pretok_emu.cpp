@@ -15,11 +15,14 @@ struct HostText {
 };
 
 // marks[i] = 1 where a chunk starts; returns the error flags. order: 0 ascending windows, 1 descending.
+static uint32_t g_kind = PT_GPT4;
+extern "C" void emu_pretok_kind(int kind) { g_kind = (uint32_t)kind; }
+
 extern "C" uint32_t emu_pretok(const uint8_t *text, uint64_t len, const uint8_t *table, uint64_t window,
                                uint64_t max_crawl, int order, uint8_t *marks) {
     uint32_t err = 0;
     memset(marks, 0, len);
-    PretokIn<HostText> in{HostText{text}, len, table, &err};
+    PretokIn<HostText> in{HostText{text}, len, table, &err, g_kind};
     const uint64_t n_win = (len + window - 1) / window;
     for (uint64_t k = 0; k < n_win; k++) {
         const uint64_t w = order ? n_win - 1 - k : k;

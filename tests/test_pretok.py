@@ -25,7 +25,8 @@ def emu(pkg):
     L.emu_pretok.restype = C.c_uint32
     table = pkg.pretok_class_table()
 
-    def run(text: bytes, window=32, max_crawl=1 << 40, order=0):
+    def run(text: bytes, window=32, max_crawl=1 << 40, order=0, kind="gpt4"):
+        L.emu_pretok_kind({"gpt4": 0, "gpt2": 1}[kind])
         buf = np.frombuffer(text, np.uint8) if len(text) else np.zeros(1, np.uint8)
         marks = np.zeros(max(len(text), 1), np.uint8)
         err = L.emu_pretok(buf.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_uint64(len(text)),
@@ -38,12 +39,12 @@ def emu(pkg):
 
 @pytest.fixture(scope="module")
 def pcre2_starts(pkg):
-    return lambda text: _pcre2_starts(pkg, text)
+    return lambda text, kind="gpt4": _pcre2_starts(pkg, text, kind)
 
 
-def _pcre2_starts(pkg, text: bytes):
-    s, e = pkg.split(pkg.patterns()["gpt4"], text, 1)
-    assert len(s) == 0 or (s[0] == 0 and e[-1] == len(text) and np.array_equal(s[1:], e[:-1])), "gpt4 chunks tile the text"
+def _pcre2_starts(pkg, text: bytes, kind="gpt4"):
+    s, e = pkg.split(pkg.patterns()[kind], text, 1)
+    assert len(s) == 0 or (s[0] == 0 and e[-1] == len(text) and np.array_equal(s[1:], e[:-1])), "chunks tile the text"
     return s
 
 
@@ -91,6 +92,21 @@ def test_fuzz_unicode(emu, seed, pcre2_starts):
                 got, err = emu(text, window, order=order)
                 assert err == 0, text
                 assert np.array_equal(got, want), (text, window, got.tolist(), want.tolist())
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_gpt2_pattern_fuzz_and_fixture(emu, seed, pcre2_starts):
+    rng = np.random.default_rng(2000 + seed)
+    for _ in range(150):
+        text = "".join(ALPHABET[i] for i in rng.integers(0, len(ALPHABET), int(rng.integers(1, 200)))).encode("utf-8")
+        want = pcre2_starts(text, "gpt2")
+        for window in (int(rng.integers(1, 12)), 32):
+            got, err = emu(text, window, order=seed & 1, kind="gpt2")
+            assert err == 0 and np.array_equal(got, want), (text, window, got.tolist(), want.tolist())
+    if seed == 0:
+        text = open(os.path.join(ROOT, "tests", "golden", "data", "taylorswift.txt"), "rb").read()
+        got, err = emu(text, 32, kind="gpt2")
+        assert err == 0 and np.array_equal(got, pcre2_starts(text, "gpt2"))
 
 
 def test_fuzz_class_runs(emu, pcre2_starts):
@@ -143,6 +159,19 @@ def test_gpu_split_matches_pcre2(pkg):
         got = pt.split(text)
         assert np.array_equal(got, want), (len(text), len(got), len(want))
     pt.close()
+
+
+@pytest.mark.gpu
+def test_gpu_split_gpt2_pattern(pkg):
+    pt = pkg.Pretok(pattern=pkg.patterns()["gpt2"])
+    for text in _texts(pkg)[:2] + _texts(pkg)[3:] + [b"", b"a 'll b", b"  x"]:
+        s, e = pkg.split(pkg.patterns()["gpt2"], text, 0)
+        want = np.concatenate([s, [len(text)]]).astype(np.uint64) if len(s) else np.asarray([len(text)], np.uint64)
+        assert np.array_equal(pt.split(text), want)
+    pt.close()
+    with pytest.raises(pkg.MbpeError) as ei:
+        pkg.Pretok(pattern="\\w+")
+    assert ei.value.code == -8
 
 
 @pytest.mark.gpu
@@ -211,7 +240,7 @@ def test_tokenizer_goldens_with_host_and_device_split(pkg, manifest, tmp_path, m
         if e["special"]:
             tk.set_special_tokens_from_file(golden_data(e["special"]))
         tk.train(golden_data(e["input"]), e["vocab_size"], e["mode"])
-        assert tk.last_train_stats()["split_on_gpu"] == (gpu_split == "1" and e["encoder"] == "gpt4"), name
+        assert tk.last_train_stats()["split_on_gpu"] == (gpu_split == "1" and e["encoder"] in ("gpt4", "gpt2")), name
         out = tmp_path / "out.model"
         tk.save(out, write_vocab=False)
         assert hashlib.sha256(out.read_bytes()).hexdigest() == e["model_sha256"], name
