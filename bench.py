@@ -480,6 +480,28 @@ def main():
         assert np.array_equal(ids_abi, ids_dev)
         # size-independent property at full size: decode(encode(x)) == x
         roundtrip = enc.decode(ids) == etb
+        # decode gather (Tokenizer.h:725-751), ids and bytes resident: the ids of the last batch are still in d_out
+        d_txt = torch.empty(len(etext) + 64, dtype=torch.uint8, device=dev)
+        d_ntxt = torch.zeros(1, dtype=torch.int64, device=dev)
+        dev_ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * (a.warmup + a.steps))]
+        for i in range(a.warmup + a.steps):
+            flush_buf.fill_(i & 0xFF)
+            dev_ev[2 * i].record()
+            enc.decode_device(d_out.data_ptr(), n_ids, d_txt.data_ptr(), len(etext) + 64, d_ntxt.data_ptr(), stream)
+            dev_ev[2 * i + 1].record()
+        barrier()
+        dms = max_over_ranks(sum(dev_ev[2 * i].elapsed_time(dev_ev[2 * i + 1]) for i in range(a.warmup, a.warmup + a.steps)) / a.steps)
+        n_txt = int(d_ntxt.item())
+        decode_ok = n_txt == len(etext) and bool(torch.equal(d_txt[:n_txt], batches[-1]["d_bytes"]))
+        b_dec = 4 * n_ids + n_txt  # read every id once, write every byte once (the vocabulary tables stay in cache)
+        line["decode"] = {
+            "metric": "bpe_decode_mb_per_sec", "value": world * n_txt / 1e6 / (dms / 1e3), "unit": "MB/s", "ms_per_step": dms,
+            "n_ids": n_ids, "bytes_out": n_txt, "equals_input_text": decode_ok,
+            "roofline": {"bound": "hbm", "achieved": b_dec / 1e9 / (dms / 1e3), "peak": peak, "unit": "GB/s",
+                         "frac": b_dec / 1e9 / (dms / 1e3) / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "k_decode_tiles", "algorithmic_bytes_per_step": int(b_dec)},
+        }
+        line["gpu_launches"] += a.steps
         line["encode"] = {
             "metric": "bpe_encode_mb_per_sec", "value": world * etext_len / 1e6 / (ems / 1e3), "unit": "MB/s",
             "ms_per_step": ems, "bytes_per_step": etext_len, "n_chunks": int(n_echunks_total), "n_tokens": int(n_ids_total),

@@ -151,6 +151,10 @@ int mbpe_encode_reserve(mbpe_encoder *e, uint64_t n_bytes, uint64_t n_chunks);
 /* ids -> bytes. Call with out == NULL to size. Invalid ids are skipped (Tokenizer.h:739-742). */
 int mbpe_decode(mbpe_encoder *e, const uint32_t *ids, uint64_t n_ids, uint8_t *out, uint64_t out_cap,
                 uint64_t *n_out);
+/* resident ids (16-byte aligned) -> resident bytes, one pass, on `stream`. *d_n_out (device) = decoded size; bytes past
+ * out_cap are dropped. d_out == NULL: size only. */
+int mbpe_decode_device(mbpe_encoder *e, const uint32_t *d_ids, uint64_t n_ids, uint8_t *d_out, uint64_t out_cap,
+                       uint64_t *d_n_out, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * 4. Tokenizer mirror (host C++23 front end over 2. and 3.): same method set, argument meaning and error

@@ -25,7 +25,7 @@ EXPORTS = [
     "mbpe_trainer_create", "mbpe_trainer_run", "mbpe_trainer_destroy", "mbpe_train",
     "mbpe_comm_unique_id", "mbpe_comm_create", "mbpe_comm_destroy", "mbpe_train_sharded",
     "mbpe_encoder_create", "mbpe_encoder_destroy", "mbpe_encoder_set_specials", "mbpe_encode", "mbpe_encode_device",
-    "mbpe_encode_reserve", "mbpe_decode",
+    "mbpe_encode_reserve", "mbpe_decode", "mbpe_decode_device",
     "mbpe_gpt2_split_pattern", "mbpe_gpt4_split_pattern", "mbpe_tokenizer_create", "mbpe_tokenizer_destroy",
     "mbpe_tokenizer_set_special_tokens", "mbpe_tokenizer_train", "mbpe_tokenizer_save", "mbpe_tokenizer_load",
     "mbpe_tokenizer_encode", "mbpe_tokenizer_decode", "mbpe_tokenizer_get_merges",
@@ -337,6 +337,11 @@ class Encoder:
                               C.c_uint64(len(off) - 1), _p(out, C.c_uint32), C.c_uint64(len(out)), C.byref(n),
                               None if out_off is None else _p(out_off, C.c_uint64)))
         return (out[:n.value].copy(), out_off) if want_off else out[:n.value].copy()
+
+    def decode_device(self, d_ids, n_ids, d_out, out_cap, d_n_out, stream=None):
+        """All pointers are device addresses (ints); d_out may be 0 to size only."""
+        _ck(lib().mbpe_decode_device(self.h, C.c_void_p(d_ids), C.c_uint64(n_ids), C.c_void_p(d_out), C.c_uint64(out_cap),
+                                     C.c_void_p(d_n_out), C.c_void_p(stream or 0)))
 
     def encode_device(self, d_bytes, n_bytes, d_off32, n_chunks, d_out, out_cap, d_n_out, stream=None):
         """All pointers are device addresses (ints)."""

@@ -601,6 +601,7 @@ struct DecArgs {
     uint64_t n_ids;
     const uint32_t *v_off; // vocab_size + 1
     const uint8_t *v_bytes;
+    const unsigned long long *v_pack; // per id: length in the low byte (0xFF = longer than 7 bytes), then the bytes
     uint32_t vocab_size;
     const uint32_t *sp_ids; // sorted
     const uint32_t *sp_off; // n_sp + 1 into sp_bytes
@@ -614,70 +615,141 @@ struct DecArgs {
     uint32_t n_tiles;
 };
 
-__global__ void __launch_bounds__(ENC_THREADS) k_decode_tiles(const DecArgs a) {
-    __shared__ uint32_t s_tile;
-    __shared__ uint32_t s_warp[ENC_THREADS / 32];
-    __shared__ unsigned long long s_base;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// A tile = DEC_THREADS x DEC_IPT consecutive ids. Each thread owns DEC_IPT consecutive ids: coalesced 16-byte id
+// loads, (offset, length) from the vocabulary index (128 KB for 32k ids: L1/L2 resident), block scan + look-back for
+// the tile's place in the byte stream, then every token's bytes are gathered into shared memory and the tile leaves
+// as aligned 4-byte words, 128 bytes per warp store (tokens average 2-3 bytes: per-thread stores would touch one
+// sector each). Tiles whose bytes do not fit the staging buffer store directly.
+constexpr int DEC_THREADS = 256, DEC_IPT = 8, DEC_IDS = DEC_THREADS * DEC_IPT;
+constexpr uint32_t DEC_STAGE = 24576; // bytes staged per tile (avg ~5 KB)
+
+struct DecSmem {
+    alignas(16) uint8_t stage[DEC_STAGE + 16];
+    uint32_t s_warp[DEC_THREADS / 32];
+    uint32_t s_tile;
+    unsigned long long s_base;
+};
+
+__global__ void __launch_bounds__(DEC_THREADS) k_decode_tiles(const DecArgs a) {
+    __shared__ DecSmem sm;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
+        if (tid == 0) sm.s_tile = atomicAdd(a.ticket, 1u);
         __syncthreads();
-        const uint32_t tile = s_tile;
+        const uint32_t tile = sm.s_tile;
         if (tile >= a.n_tiles) return;
-        const uint64_t k = (uint64_t)tile * ENC_THREADS + threadIdx.x;
-        const uint8_t *src = nullptr;
-        uint32_t len = 0;
-        if (k < a.n_ids) {
-            uint32_t id = __ldg(&a.ids[k]);
-            int lo = 0, hi = (int)a.n_sp - 1, hit = -1; // special tokens override the vocabulary (Tokenizer.h:733)
+        const uint64_t k0 = (uint64_t)tile * DEC_IDS + (uint64_t)tid * DEC_IPT;
+        uint32_t id[DEC_IPT];
+        if (k0 + DEC_IPT <= a.n_ids) { // ids is 16-byte aligned (device allocation), k0 a multiple of 8
+            const uint4 q0 = __ldcs(reinterpret_cast<const uint4 *>(a.ids + k0));
+            const uint4 q1 = __ldcs(reinterpret_cast<const uint4 *>(a.ids + k0 + 4));
+            id[0] = q0.x, id[1] = q0.y, id[2] = q0.z, id[3] = q0.w, id[4] = q1.x, id[5] = q1.y, id[6] = q1.z, id[7] = q1.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < DEC_IPT; j++) id[j] = k0 + j < a.n_ids ? __ldcs(a.ids + k0 + j) : 0xFFFFFFFFu;
+        }
+        // one 8-byte load per id answers "how long, which bytes" for tokens of up to 7 bytes (nearly all of them);
+        // longer tokens and special tokens are resolved again through the index when their bytes are copied
+        unsigned long long pk[DEC_IPT]; // low byte: length (0xFF: long / special -> resolve()), then the bytes
+        uint32_t len[DEC_IPT], sum = 0;
+        auto find_special = [&](uint32_t idv) -> int { // special tokens override the vocabulary (Tokenizer.h:733)
+            int lo = 0, hi = (int)a.n_sp - 1;
             while (lo <= hi) {
-                int mid = (lo + hi) >> 1;
-                uint32_t v = __ldg(&a.sp_ids[mid]);
-                if (v == id) {
-                    hit = mid;
-                    break;
-                }
-                if (v < id)
+                const int mid = (lo + hi) >> 1;
+                const uint32_t v = __ldg(&a.sp_ids[mid]);
+                if (v == idv) return mid;
+                if (v < idv)
                     lo = mid + 1;
                 else
                     hi = mid - 1;
             }
-            if (hit >= 0) {
-                uint32_t so = __ldg(&a.sp_off[hit]);
-                src = a.sp_bytes + so;
-                len = __ldg(&a.sp_off[hit + 1]) - so;
-            } else if (id < a.vocab_size) {
-                uint32_t vo = __ldg(&a.v_off[id]);
-                src = a.v_bytes + vo;
-                len = __ldg(&a.v_off[id + 1]) - vo;
+            return -1;
+        };
+        constexpr unsigned long long PK_SPECIAL = 1ull << 63; // with low byte 0xFF: bits 8..39 = index of the special token
+#pragma unroll
+        for (int j = 0; j < DEC_IPT; j++) pk[j] = (a.v_pack && k0 + j < a.n_ids && id[j] < a.vocab_size) ? __ldg(&a.v_pack[id[j]]) : 0xFFull;
+#pragma unroll
+        for (int j = 0; j < DEC_IPT; j++) {
+            len[j] = 0;
+            if (k0 + j >= a.n_ids) continue;
+            const int sp = a.n_sp ? find_special(id[j]) : -1;
+            if (sp >= 0) {
+                len[j] = __ldg(&a.sp_off[sp + 1]) - __ldg(&a.sp_off[sp]);
+                pk[j] = PK_SPECIAL | ((unsigned long long)(uint32_t)sp << 8) | 0xFF;
+            } else if (id[j] >= a.vocab_size) {
+                pk[j] = 0; // unknown ids contribute nothing (Tokenizer.h:739-742)
+            } else if ((pk[j] & 0xFF) == 0xFF) {
+                len[j] = __ldg(&a.v_off[id[j] + 1]) - __ldg(&a.v_off[id[j]]);
+            } else {
+                len[j] = (uint32_t)(pk[j] & 0xFF);
             }
+            sum += len[j];
         }
-        uint32_t incl = len;
+        uint32_t incl = sum;
         for (int d = 1; d < 32; d <<= 1) {
-            uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += v;
         }
-        if (lane == 31) s_warp[warp] = incl;
+        if (lane == 31) sm.s_warp[warp] = incl;
         __syncthreads();
         uint32_t warp_base = 0, total = 0;
-        for (int w = 0; w < ENC_THREADS / 32; w++) {
-            uint32_t v = s_warp[w];
+#pragma unroll
+        for (int w = 0; w < DEC_THREADS / 32; w++) {
+            const uint32_t v = sm.s_warp[w];
             if (w < (int)warp) warp_base += v;
             total += v;
         }
         if (warp == 0) {
             const uint64_t b = lookback_base(a.status, tile, total);
-            if (lane == 0) s_base = b;
+            if (lane == 0) sm.s_base = b;
         }
         __syncthreads();
-        const uint64_t dst = s_base + warp_base + (incl - len);
-        if (a.out && dst + len <= a.out_cap)
-            for (uint32_t i = 0; i < len; i++) a.out[dst + i] = __ldg(&src[i]);
-        if (tile == a.n_tiles - 1 && threadIdx.x == 0) *a.d_n_out = s_base + total;
+        const uint64_t base = sm.s_base;
+        if (a.out) {
+            // the staged image starts at the 4-byte boundary below `base`: stage[pad + i] = byte i of the tile
+            const uint32_t pad = (uint32_t)(base & 3);
+            const bool via_smem = pad + total <= DEC_STAGE && base + total <= a.out_cap;
+            uint32_t loc = warp_base + (incl - sum);
+#pragma unroll
+            for (int j = 0; j < DEC_IPT; j++) {
+                if (len[j] == 0) continue;
+                if ((pk[j] & 0xFF) != 0xFF) { // bytes are in the register
+                    unsigned long long v = pk[j] >> 8;
+                    if (via_smem) {
+                        for (uint32_t i = 0; i < len[j]; i++, v >>= 8) sm.stage[pad + loc + i] = (uint8_t)v;
+                    } else if (base + loc + len[j] <= a.out_cap) {
+                        for (uint32_t i = 0; i < len[j]; i++, v >>= 8) a.out[base + loc + i] = (uint8_t)v;
+                    }
+                } else {
+                    const uint8_t *src = (pk[j] & PK_SPECIAL) ? a.sp_bytes + __ldg(&a.sp_off[(uint32_t)(pk[j] >> 8)])
+                                                                : a.v_bytes + __ldg(&a.v_off[id[j]]);
+                    if (via_smem) {
+                        for (uint32_t i = 0; i < len[j]; i++) sm.stage[pad + loc + i] = __ldg(src + i);
+                    } else if (base + loc + len[j] <= a.out_cap) {
+                        for (uint32_t i = 0; i < len[j]; i++) a.out[base + loc + i] = __ldg(src + i);
+                    }
+                }
+                loc += len[j];
+            }
+            if (via_smem) {
+                __syncthreads();
+                const uint64_t w0 = base - pad;                       // 4-byte aligned (out is a device allocation)
+                const uint32_t n_words = (pad + total + 3) >> 2;
+                const uint32_t *sw = reinterpret_cast<const uint32_t *>(sm.stage);
+                for (uint32_t w = tid; w < n_words; w += DEC_THREADS) {
+                    const uint32_t lo = w * 4, hi = lo + 4;
+                    if (lo >= pad && hi <= pad + total) {
+                        __stcs(reinterpret_cast<uint32_t *>(a.out + w0) + w, sw[w]);
+                    } else { // first / last word of the tile: shared with the neighbouring tiles, byte stores
+                        for (uint32_t i = max(lo, pad); i < min(hi, pad + total); i++) a.out[w0 + i] = sm.stage[i];
+                    }
+                }
+            }
+        }
+        if (tile == a.n_tiles - 1 && tid == 0) *a.d_n_out = base + total;
     }
 }
-
 } // namespace mbpe
 
 using namespace mbpe;
@@ -693,6 +765,7 @@ struct mbpe_encoder {
     // decode tables
     uint32_t *d_voff = nullptr;
     uint8_t *d_vbytes = nullptr;
+    unsigned long long *d_vpack = nullptr; // decode: length + up to 7 bytes per id in one word
     uint32_t *d_sp_ids = nullptr, *d_sp_off = nullptr;
     uint8_t *d_sp_bytes = nullptr;
     uint32_t n_sp = 0;
@@ -780,6 +853,20 @@ extern "C" int mbpe_encoder_create(const uint32_t *merges, uint32_t n_merges, in
     MB_CUDA(cudaMemcpy(e->d_voff, voff.data(), voff.size() * 4, cudaMemcpyHostToDevice));
     MB_CUDA(cudaMalloc(&e->d_vbytes, vbytes.size()));
     MB_CUDA(cudaMemcpy(e->d_vbytes, vbytes.data(), vbytes.size(), cudaMemcpyHostToDevice));
+    {
+        std::vector<unsigned long long> vpack(256 + (size_t)n_merges);
+        for (size_t i = 0; i < vpack.size(); i++) {
+            const uint32_t l = voff[i + 1] - voff[i];
+            unsigned long long v = 0xFF;
+            if (l <= 7) {
+                v = l;
+                for (uint32_t q = 0; q < l; q++) v |= (unsigned long long)vbytes[voff[i] + q] << (8 * (q + 1));
+            }
+            vpack[i] = v;
+        }
+        MB_CUDA(cudaMalloc(&e->d_vpack, vpack.size() * 8));
+        MB_CUDA(cudaMemcpy(e->d_vpack, vpack.data(), vpack.size() * 8, cudaMemcpyHostToDevice));
+    }
     MB_CUDA(cudaMalloc(&e->d_small, 16));
     MB_CUDA(cudaMalloc(&e->d_n_out, 8));
     MB_CUDA(cudaMalloc(&e->d_sp_ids, 4));
@@ -823,7 +910,7 @@ extern "C" int mbpe_encoder_create(const uint32_t *merges, uint32_t n_merges, in
 extern "C" void mbpe_encoder_destroy(mbpe_encoder *e) {
     if (!e) return;
     cudaSetDevice(e->device);
-    void *ps[] = {e->d_slots, e->d_voff, e->d_vbytes, e->d_sp_ids, e->d_sp_off, e->d_sp_bytes, e->d_status, e->d_small,
+    void *ps[] = {e->d_slots, e->d_voff, e->d_vbytes, e->d_vpack, e->d_sp_ids, e->d_sp_off, e->d_sp_bytes, e->d_status, e->d_small,
                   e->d_n_out, e->d_long_list, e->d_scratch_a, e->d_scratch_b, e->d_cache, e->d_cache_log, e->d_cache_ctr, e->d_cache_arena};
     for (void *p : ps) cudaFree(p);
     delete e;
@@ -1099,6 +1186,52 @@ extern "C" int mbpe_encode(mbpe_encoder *e, const uint8_t *bytes, uint64_t n_byt
     return MBPE_OK;
 }
 
+static int decode_launch(mbpe_encoder *e, const uint32_t *d_ids, uint64_t n_ids, uint8_t *d_out, uint64_t out_cap,
+                         unsigned long long *d_n_out, cudaStream_t st) {
+    const uint64_t n_tiles = (n_ids + DEC_IDS - 1) / DEC_IDS;
+    if (n_tiles >= 0xFFFFFFFFull) return set_error(MBPE_E_INVALID, "too many ids in one call");
+    int rc = ensure_status(e, n_tiles);
+    if (rc) return rc;
+    DecArgs a{};
+    a.ids = d_ids;
+    a.n_ids = n_ids;
+    a.v_off = e->d_voff;
+    a.v_bytes = e->d_vbytes;
+    a.v_pack = getenv("MBPE_DEC_NOPACK") ? nullptr : e->d_vpack;
+    a.vocab_size = e->vocab_size;
+    a.sp_ids = e->d_sp_ids;
+    a.sp_off = e->d_sp_off;
+    a.sp_bytes = e->d_sp_bytes;
+    a.n_sp = e->n_sp;
+    a.d_n_out = d_n_out;
+    a.status = e->d_status;
+    a.ticket = e->d_small;
+    a.n_tiles = (uint32_t)n_tiles;
+    a.out = d_out;
+    a.out_cap = d_out ? out_cap : 0;
+    MB_CUDA(cudaMemsetAsync(e->d_small, 0, 16, st));
+    MB_CUDA(cudaMemsetAsync(e->d_status, 0, n_tiles * 8, st));
+    const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)e->sms * 6);
+    k_decode_tiles<<<grid, DEC_THREADS, 0, st>>>(a);
+    e->launches++;
+    MB_CUDA(cudaGetLastError());
+    return MBPE_OK;
+}
+
+// resident ids -> resident bytes in one pass. *d_n_out receives the decoded size; bytes that do not fit out_cap are
+// dropped (compare the two to detect it). d_out == NULL: size only. d_ids must be 16-byte aligned.
+extern "C" int mbpe_decode_device(mbpe_encoder *e, const uint32_t *d_ids, uint64_t n_ids, uint8_t *d_out, uint64_t out_cap,
+                                  uint64_t *d_n_out, void *stream) {
+    if (!e || !d_n_out || (n_ids && !d_ids)) return set_error(MBPE_E_INVALID, "null argument");
+    if (((uintptr_t)d_ids & 15) != 0) return set_error(MBPE_E_INVALID, "d_ids must be 16-byte aligned");
+    int rc = use_device(e->device);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    MB_CUDA(cudaMemsetAsync(d_n_out, 0, 8, st));
+    if (n_ids == 0) return MBPE_OK;
+    return decode_launch(e, d_ids, n_ids, d_out, out_cap, (unsigned long long *)d_n_out, st);
+}
+
 extern "C" int mbpe_decode(mbpe_encoder *e, const uint32_t *ids, uint64_t n_ids, uint8_t *out, uint64_t out_cap,
                            uint64_t *n_out) {
     if (!e || !n_out || (n_ids && !ids)) return set_error(MBPE_E_INVALID, "null argument");
@@ -1106,50 +1239,23 @@ extern "C" int mbpe_decode(mbpe_encoder *e, const uint32_t *ids, uint64_t n_ids,
     if (rc) return rc;
     *n_out = 0;
     if (n_ids == 0) return MBPE_OK;
-    uint64_t n_tiles = (n_ids + ENC_THREADS - 1) / ENC_THREADS;
-    if (n_tiles >= 0xFFFFFFFFull) return set_error(MBPE_E_INVALID, "too many ids in one call");
-    if ((rc = ensure_status(e, n_tiles))) return rc;
     uint32_t *d_ids = nullptr;
     uint8_t *d_out = nullptr;
     MB_CUDA(cudaMalloc(&d_ids, n_ids * 4));
-    MB_CUDA(cudaMemcpy(d_ids, ids, n_ids * 4, cudaMemcpyHostToDevice));
-    DecArgs a{};
-    a.ids = d_ids;
-    a.n_ids = n_ids;
-    a.v_off = e->d_voff;
-    a.v_bytes = e->d_vbytes;
-    a.vocab_size = e->vocab_size;
-    a.sp_ids = e->d_sp_ids;
-    a.sp_off = e->d_sp_off;
-    a.sp_bytes = e->d_sp_bytes;
-    a.n_sp = e->n_sp;
-    a.d_n_out = e->d_n_out;
-    a.status = e->d_status;
-    a.ticket = e->d_small;
-    a.n_tiles = (uint32_t)n_tiles;
-    unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)e->sms * 8);
+    cudaError_t ce = cudaMemcpy(d_ids, ids, n_ids * 4, cudaMemcpyHostToDevice);
     // pass 1 sizes the output, pass 2 writes it (the caller may also stop after pass 1 with out == NULL)
-    for (int pass = 0; pass < 2; pass++) {
-        MB_CUDA(cudaMemset(e->d_small, 0, 16));
-        MB_CUDA(cudaMemset(e->d_status, 0, n_tiles * 8));
-        a.out = pass ? d_out : nullptr;
-        a.out_cap = pass ? *n_out : 0;
-        k_decode_tiles<<<grid, ENC_THREADS>>>(a);
-        e->launches++;
-        MB_CUDA(cudaGetLastError());
-        if (pass == 0) {
-            MB_CUDA(cudaMemcpy(n_out, e->d_n_out, 8, cudaMemcpyDeviceToHost));
-            if (!out) break;
-            if (*n_out > out_cap) {
-                cudaFree(d_ids);
-                return set_error(MBPE_E_CAPACITY, "out too small; *n_out holds the needed size");
-            }
-            MB_CUDA(cudaMalloc(&d_out, std::max<uint64_t>(*n_out, 1)));
-        } else {
-            MB_CUDA(cudaMemcpy(out, d_out, *n_out, cudaMemcpyDeviceToHost));
+    if (ce == cudaSuccess) rc = decode_launch(e, d_ids, n_ids, nullptr, 0, e->d_n_out, nullptr);
+    if (ce == cudaSuccess && rc == MBPE_OK) ce = cudaMemcpy(n_out, e->d_n_out, 8, cudaMemcpyDeviceToHost);
+    if (ce == cudaSuccess && rc == MBPE_OK && out) {
+        if (*n_out > out_cap) {
+            rc = set_error(MBPE_E_CAPACITY, "out too small; *n_out holds the needed size");
+        } else if ((ce = cudaMalloc(&d_out, std::max<uint64_t>(*n_out, 1))) == cudaSuccess) {
+            rc = decode_launch(e, d_ids, n_ids, d_out, *n_out, e->d_n_out, nullptr);
+            if (rc == MBPE_OK) ce = cudaMemcpy(out, d_out, *n_out, cudaMemcpyDeviceToHost);
         }
     }
     cudaFree(d_ids);
     cudaFree(d_out);
-    return MBPE_OK;
+    if (rc == MBPE_OK && ce != cudaSuccess) rc = cuda_fail(ce, "decode", __FILE__, __LINE__);
+    return rc;
 }

@@ -90,6 +90,46 @@ def test_decode_invalid_ids_and_special_override(pkg, oracle):
     assert enc.decode([]) == b""
 
 
+def test_decode_device_matches_host_api_and_reports_overflow(pkg):
+    """resident ids -> resident bytes (one pass, staged coalesced stores) == mbpe_decode; undersized buffers are
+    reported through the size, bytes past the capacity are not written"""
+    import torch
+    text = pkg.synth_corpus(0x5EED0007, 6 << 20).tobytes()
+    tok, off, w, _ = pkg.split_dedup(pkg.patterns()["gpt4"], text)
+    merges, _, _ = pkg.train(tok, off, w, 2000, "lexical")
+    enc = pkg.Encoder(merges)
+    enc.set_specials({100257: b"<|endoftext|>", 7: b"SEVEN"})
+    s, e = pkg.split(pkg.patterns()["gpt4"], text)
+    ids = enc.encode(text, np.concatenate([s, e[-1:]]).astype(np.uint64))
+    rng = np.random.default_rng(1)
+    ids = ids.copy()
+    ids[rng.integers(0, len(ids), 2000)] = 100257      # special ids override
+    ids[rng.integers(0, len(ids), 2000)] = 7            # ... also ids inside the vocabulary
+    ids[rng.integers(0, len(ids), 2000)] = 4000000      # unknown ids contribute nothing
+    want = enc.decode(ids)
+    dev = torch.device("cuda", 0)
+    for n in (len(ids), 2048, 2049, 5, 1, 0):
+        d_ids = torch.from_numpy(ids[:n].view(np.int32).copy()).to(dev) if n else torch.zeros(4, dtype=torch.int32, device=dev)
+        w_n = enc.decode(ids[:n])
+        d_out = torch.full((len(w_n) + 64,), 0xAA, dtype=torch.uint8, device=dev)
+        d_n = torch.zeros(1, dtype=torch.int64, device=dev)
+        enc.decode_device(d_ids.data_ptr(), n, d_out.data_ptr(), len(w_n), d_n.data_ptr())
+        torch.cuda.synchronize()
+        assert int(d_n.item()) == len(w_n)
+        assert d_out[:len(w_n)].cpu().numpy().tobytes() == w_n and bool((d_out[len(w_n):] == 0xAA).all())
+    assert want == enc.decode(ids)
+    # size only, and a buffer that is too small
+    d_ids = torch.from_numpy(ids.view(np.int32).copy()).to(dev)
+    d_n = torch.zeros(1, dtype=torch.int64, device=dev)
+    enc.decode_device(d_ids.data_ptr(), len(ids), 0, 0, d_n.data_ptr())
+    assert int(d_n.item()) == len(want)
+    small = torch.full((1000 + 64,), 0xAA, dtype=torch.uint8, device=dev)
+    enc.decode_device(d_ids.data_ptr(), len(ids), small.data_ptr(), 1000, d_n.data_ptr())
+    torch.cuda.synchronize()
+    assert int(d_n.item()) == len(want) and bool((small[1000:] == 0xAA).all())
+    enc.close()
+
+
 def test_large_synthetic_roundtrip_and_oracle_slice(pkg, oracle):
     """Size-independent property at a bench-like size: decode(encode(x)) == x; plus an oracle diff on a slice."""
     text = pkg.synth_corpus(0x5EED0002, 64 << 20).tobytes()
