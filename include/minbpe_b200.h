@@ -155,6 +155,9 @@ int mbpe_decode(mbpe_encoder *e, const uint32_t *ids, uint64_t n_ids, uint8_t *o
  * out_cap are dropped. d_out == NULL: size only. */
 int mbpe_decode_device(mbpe_encoder *e, const uint32_t *d_ids, uint64_t n_ids, uint8_t *d_out, uint64_t out_cap,
                        uint64_t *d_n_out, void *stream);
+/* .enc file (raw little-endian u32 ids; a trailing partial word is dropped, examples/minbpe-cc.cpp:79) -> text file,
+ * in blocks: reader thread, device gather, writer thread; memory use independent of the file size */
+int mbpe_decode_file(mbpe_encoder *e, const char *in_path, const char *out_path, uint64_t *n_ids, uint64_t *n_bytes);
 
 /* ------------------------------------------------------------------------------------------------------------
  * 4. Tokenizer mirror (host C++23 front end over 2. and 3.): same method set, argument meaning and error
@@ -186,6 +189,9 @@ int mbpe_tokenizer_decode(mbpe_tokenizer *t, const uint32_t *ids, uint64_t n, ui
 int mbpe_tokenizer_get_merges(mbpe_tokenizer *t, uint32_t *merges_out, uint32_t cap_pairs, uint32_t *n_merges);
 int mbpe_tokenizer_last_train_stats(mbpe_tokenizer *t, mbpe_train_stats *stats, double *split_s, double *dedup_s,
                                     uint64_t *n_chunks, uint64_t *n_unique);
+/* streaming --decode: .enc file -> text file in blocks (any model) */
+int mbpe_tokenizer_decode_file(mbpe_tokenizer *t, const char *in_path, const char *out_path, uint64_t *n_ids,
+                               uint64_t *n_bytes);
 /* streaming --encode: MBPE_E_UNSUPPORTED unless GPT-4 pattern, no special tokens, well-formed UTF-8 */
 int mbpe_tokenizer_encode_file(mbpe_tokenizer *t, const char *in_path, const char *out_path, uint64_t *n_ids);
 int mbpe_tokenizer_last_split_on_gpu(mbpe_tokenizer *t); /* 1: the last train() pre-tokenised on the device (section 6) */

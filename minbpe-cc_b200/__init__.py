@@ -29,7 +29,7 @@ EXPORTS = [
     "mbpe_gpt2_split_pattern", "mbpe_gpt4_split_pattern", "mbpe_tokenizer_create", "mbpe_tokenizer_destroy",
     "mbpe_tokenizer_set_special_tokens", "mbpe_tokenizer_train", "mbpe_tokenizer_save", "mbpe_tokenizer_load",
     "mbpe_tokenizer_encode", "mbpe_tokenizer_decode", "mbpe_tokenizer_get_merges",
-    "mbpe_tokenizer_last_train_stats", "mbpe_tokenizer_last_split_on_gpu", "mbpe_tokenizer_encode_file", "mbpe_encode_file", "mbpe_tokenizer_set_engine", "mbpe_tokenizer_set_threads",
+    "mbpe_tokenizer_last_train_stats", "mbpe_tokenizer_last_split_on_gpu", "mbpe_tokenizer_encode_file", "mbpe_encode_file", "mbpe_tokenizer_decode_file", "mbpe_decode_file", "mbpe_tokenizer_set_engine", "mbpe_tokenizer_set_threads",
     "mbpe_split", "mbpe_special_split", "mbpe_pretok_class_table", "mbpe_dedup",
     "mbpe_pretok_create", "mbpe_pretok_select", "mbpe_pretok_destroy", "mbpe_pretok_split_device", "mbpe_pretok_split",
     "mbpe_pretok_dedup_device", "mbpe_pretok_dedup_segments", "mbpe_pretok_corpus", "mbpe_encode_text", "mbpe_device_corpus_download", "mbpe_device_corpus_free",
@@ -421,6 +421,12 @@ class Tokenizer:
         n = C.c_uint64()
         _ck(lib().mbpe_tokenizer_encode_file(self.h, str(in_path).encode(), str(out_path).encode(), C.byref(n)))
         return n.value
+
+    def decode_file(self, in_path, out_path):
+        """streaming .enc file -> text file; returns (ids read, bytes written)"""
+        ni, nb = C.c_uint64(), C.c_uint64()
+        _ck(lib().mbpe_tokenizer_decode_file(self.h, str(in_path).encode(), str(out_path).encode(), C.byref(ni), C.byref(nb)))
+        return ni.value, nb.value
 
     def decode(self, ids, verbose=False):
         ids = np.ascontiguousarray(ids, np.uint32)

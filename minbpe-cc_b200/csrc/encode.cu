@@ -18,6 +18,10 @@
 // Chunks longer than ENC_SHORT_MAX (encoder "basic": the whole text is one chunk) are encoded first by
 // k_encode_long into a scratch stream and spliced in by k_encode_tiles.
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -1257,5 +1261,175 @@ extern "C" int mbpe_decode(mbpe_encoder *e, const uint32_t *ids, uint64_t n_ids,
     cudaFree(d_ids);
     cudaFree(d_out);
     if (rc == MBPE_OK && ce != cudaSuccess) rc = cuda_fail(ce, "decode", __FILE__, __LINE__);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// .enc file -> text file in blocks: a reader thread fills pinned id blocks, the calling thread uploads
+// a block, sizes and gathers it on the device and downloads the bytes into a pinned block, a writer thread drains
+// those into the output file. Blocks of ids are independent, so there is no boundary problem.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct BlockGate {
+    std::mutex mu;
+    std::condition_variable cv;
+    long long ready = -1;
+    bool failed = false;
+    void publish(long long k) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            ready = k;
+        }
+        cv.notify_all();
+    }
+    void fail() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            failed = true;
+        }
+        cv.notify_all();
+    }
+    bool wait_for(long long k) {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return ready >= k || failed; });
+        return ready >= k;
+    }
+};
+} // namespace
+
+extern "C" int mbpe_decode_file(mbpe_encoder *e, const char *in_path, const char *out_path, uint64_t *n_ids_out,
+                                uint64_t *n_bytes_out) {
+    if (!e || !in_path || !out_path) return set_error(MBPE_E_INVALID, "null argument");
+    int rc = use_device(e->device);
+    if (rc) return rc;
+    FILE *fin = fopen(in_path, "rb");
+    if (!fin) return set_error(MBPE_E_IO, std::string("cannot open ") + in_path);
+    FILE *fout = fopen(out_path, "wb");
+    if (!fout) {
+        fclose(fin);
+        return set_error(MBPE_E_IO, std::string("cannot open ") + out_path);
+    }
+    constexpr uint64_t BLK = 4u << 20; // ids per block (16 MiB)
+    constexpr int NB = 3;
+    uint64_t out_cap = BLK * 8; // bytes per block; grows when a block decodes to more
+    uint32_t *h_in[NB] = {nullptr, nullptr, nullptr}, *d_ids = nullptr;
+    uint8_t *h_out[NB] = {nullptr, nullptr, nullptr}, *d_out = nullptr;
+    unsigned long long *d_n = nullptr;
+    bool ok = cudaMalloc(&d_ids, BLK * 4) == cudaSuccess && cudaMalloc(&d_out, out_cap) == cudaSuccess && cudaMalloc(&d_n, 8) == cudaSuccess;
+    for (int i = 0; i < NB && ok; i++) ok = cudaMallocHost(&h_in[i], BLK * 4) == cudaSuccess && cudaMallocHost(&h_out[i], out_cap) == cudaSuccess;
+    auto release = [&]() {
+        for (int i = 0; i < NB; i++) {
+            cudaFreeHost(h_in[i]);
+            cudaFreeHost(h_out[i]);
+        }
+        cudaFree(d_ids);
+        cudaFree(d_out);
+        cudaFree(d_n);
+        fclose(fin);
+        fclose(fout);
+    };
+    if (!ok) {
+        cudaGetLastError();
+        release();
+        return set_error(MBPE_E_CUDA, "out of (pinned) memory");
+    }
+    std::mutex meta_mu;
+    std::vector<uint64_t> ids_in_block, bytes_in_block;
+    std::vector<char> last_block;
+    BlockGate read_gate, in_free, write_gate, out_free;
+    in_free.publish(NB - 1);
+    out_free.publish(NB - 1);
+    std::thread reader([&]() {
+        for (long long k = 0;; k++) {
+            if (!in_free.wait_for(k)) return;
+            const size_t got = fread(h_in[k % NB], 4, BLK, fin); // a trailing partial word is dropped (minbpe-cc.cpp:79)
+            {
+                std::lock_guard<std::mutex> lk(meta_mu);
+                ids_in_block.push_back(got);
+                last_block.push_back(got < BLK);
+            }
+            read_gate.publish(k);
+            if (got < BLK) return;
+        }
+    });
+    bool write_failed = false;
+    long long n_blocks_total = -1;
+    std::mutex total_mu;
+    std::thread writer([&]() {
+        for (long long k = 0;; k++) {
+            {
+                std::lock_guard<std::mutex> lk(total_mu);
+                if (n_blocks_total >= 0 && k >= n_blocks_total) return;
+            }
+            if (!write_gate.wait_for(k)) return;
+            uint64_t n;
+            {
+                std::lock_guard<std::mutex> lk(meta_mu);
+                n = bytes_in_block[k];
+            }
+            if (fwrite(h_out[k % NB], 1, n, fout) != n) {
+                write_failed = true;
+                out_free.fail();
+                return;
+            }
+            out_free.publish(k + NB);
+        }
+    });
+    uint64_t total_ids = 0, total_bytes = 0;
+    cudaError_t ce = cudaSuccess;
+    for (long long k = 0;; k++) {
+        if (!read_gate.wait_for(k)) {
+            rc = set_error(MBPE_E_IO, "read failed");
+            break;
+        }
+        uint64_t n;
+        bool is_last;
+        {
+            std::lock_guard<std::mutex> lk(meta_mu);
+            n = ids_in_block[k];
+            is_last = last_block[k];
+        }
+        if (!out_free.wait_for(k)) {
+            rc = set_error(MBPE_E_IO, std::string("write failed: ") + out_path);
+            break;
+        }
+        unsigned long long n_bytes = 0;
+        if (n) {
+            if ((ce = cudaMemcpy(d_ids, h_in[k % NB], n * 4, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+            if ((rc = decode_launch(e, d_ids, n, d_out, out_cap, d_n, nullptr))) break;
+            if ((ce = cudaMemcpy(&n_bytes, d_n, 8, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+            if (n_bytes > out_cap) { // a vocabulary of very long tokens: not worth growing pinned buffers mid-stream
+                rc = set_error(MBPE_E_UNSUPPORTED, "a block decodes to more than 8 bytes per id: use the whole-file path");
+                break;
+            }
+            if ((ce = cudaMemcpy(h_out[k % NB], d_out, n_bytes, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+        }
+        in_free.publish(k + NB);
+        {
+            std::lock_guard<std::mutex> lk(meta_mu);
+            bytes_in_block.push_back(n_bytes);
+        }
+        total_ids += n;
+        total_bytes += n_bytes;
+        if (is_last) {
+            std::lock_guard<std::mutex> lk(total_mu);
+            n_blocks_total = k + 1;
+        }
+        write_gate.publish(k);
+        if (is_last) break;
+    }
+    if (rc != MBPE_OK || ce != cudaSuccess) {
+        in_free.fail();
+        write_gate.fail();
+    }
+    reader.join();
+    writer.join();
+    if (rc == MBPE_OK && ce != cudaSuccess) rc = cuda_fail(ce, "decode_file", __FILE__, __LINE__);
+    if (rc == MBPE_OK && (write_failed || fflush(fout) != 0)) rc = set_error(MBPE_E_IO, std::string("write failed: ") + out_path);
+    release();
+    if (rc == MBPE_OK) {
+        if (n_ids_out) *n_ids_out = total_ids;
+        if (n_bytes_out) *n_bytes_out = total_bytes;
+    }
     return rc;
 }

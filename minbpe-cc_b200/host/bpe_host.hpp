@@ -98,6 +98,7 @@ class Tokenizer {
     int encode(std::string_view text, bool verbose, std::vector<Token> &out);                          // :653
     int encode_into(std::string_view text, Token *out, uint64_t cap, uint64_t *n_out); // same ids, caller's buffer
     int encode_file(const std::string &in_path, const std::string &out_path, uint64_t *n_ids); // streaming, .enc layout
+    int decode_file(const std::string &in_path, const std::string &out_path, uint64_t *n_ids, uint64_t *n_bytes);
     int decode(const std::vector<Token> &tokens, bool verbose, std::string &out);                      // :725
     int load(const std::string &path, bool verbose);                                                   // :754
     int save(const std::string &path, bool write_vocab);                                               // :875

@@ -204,7 +204,18 @@ int main(int argc, char **argv) {
                   << " output to " << output_path << "\n";
         rc = rt.load(model_path, verbose);
         std::string raw;
-        if (rc == 0 && slurp(input_path, raw, err)) {
+        std::error_code dsize_ec;
+        const bool big_enc = rc == 0 && !verbose && !getenv("MBPE_CLI_NO_STREAM") &&
+                             std::filesystem::file_size(input_path, dsize_ec) >= (8u << 20) && !dsize_ec;
+        uint64_t s_ids = 0, s_bytes = 0;
+        if (big_enc) { // block-wise: disk -> pinned memory -> GPU -> pinned memory -> disk
+            rc = rt.decode_file(input_path, output_path, &s_ids, &s_bytes);
+            if (rc == 0)
+                std::cout << "Loaded encoding with " << s_ids << " tokens\nWriting " << s_bytes << " decoded tokens to "
+                          << output_path << "\n";
+            else
+                std::cerr << "Decoding failed: " << rt.error() << "\n";
+        } else if (rc == 0 && slurp(input_path, raw, err)) {
             std::vector<Token> ids(raw.size() / sizeof(Token)); // trailing partial word is dropped (minbpe-cc.cpp:79)
             std::memcpy(ids.data(), raw.data(), ids.size() * sizeof(Token));
             std::cout << "Loaded encoding with " << ids.size() << " tokens\n";

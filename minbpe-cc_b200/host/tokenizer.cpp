@@ -388,21 +388,30 @@ int Tokenizer::decode(const std::vector<Token> &tokens, bool verbose, std::strin
     for (Token t : tokens) // same diagnostics as the reference (Tokenizer.h:739-742)
         if (t >= vocab_.size() && special_reverse_.find(t) == special_reverse_.end())
             std::cerr << "Warning: Attempted to decode invalid token ID: " << t << "\n";
+    // one call when the guess (4 bytes per id; text averages 2-3) is large enough, else a second one at the exact size
     uint64_t n = 0;
-    rc = mbpe_decode(encoder_, tokens.data(), tokens.size(), nullptr, 0, &n);
+    out.resize(tokens.size() * 4 + 64);
+    rc = mbpe_decode(encoder_, tokens.data(), tokens.size(), reinterpret_cast<uint8_t *>(out.data()), out.size(), &n);
+    if (rc == MBPE_E_CAPACITY) {
+        out.resize(n);
+        rc = mbpe_decode(encoder_, tokens.data(), tokens.size(), reinterpret_cast<uint8_t *>(out.data()), out.size(), &n);
+    }
     if (rc) {
         error_ = mbpe_last_error();
+        out.clear();
         return rc;
     }
     out.resize(n);
-    if (n) {
-        rc = mbpe_decode(encoder_, tokens.data(), tokens.size(), reinterpret_cast<uint8_t *>(out.data()), n, &n);
-        if (rc) {
-            error_ = mbpe_last_error();
-            return rc;
-        }
-    }
     return MBPE_OK;
+}
+
+// .enc file -> text file in blocks (examples/minbpe-cc.cpp:243-258 slurps both), any model
+int Tokenizer::decode_file(const std::string &in_path, const std::string &out_path, uint64_t *n_ids, uint64_t *n_bytes) {
+    int rc = ensure_encoder();
+    if (rc) return rc;
+    rc = mbpe_decode_file(encoder_, in_path.c_str(), out_path.c_str(), n_ids, n_bytes);
+    if (rc) error_ = mbpe_last_error();
+    return rc;
 }
 
 int Tokenizer::load(const std::string &path, bool verbose) {
@@ -566,6 +575,12 @@ extern "C" int mbpe_tokenizer_encode_file(mbpe_tokenizer *t, const char *in_path
     if (!t || !in_path || !out_path) return fail(MBPE_E_INVALID, "null argument");
     int rc = t->tk.encode_file(in_path, out_path, n_ids);
     if (rc == MBPE_E_UNSUPPORTED) return fail(rc, "streaming encode needs the GPT-4 pattern, no special tokens and well-formed UTF-8");
+    return rc ? fail(rc, t->tk.error()) : MBPE_OK;
+}
+extern "C" int mbpe_tokenizer_decode_file(mbpe_tokenizer *t, const char *in_path, const char *out_path, uint64_t *n_ids,
+                                          uint64_t *n_bytes) {
+    if (!t || !in_path || !out_path) return fail(MBPE_E_INVALID, "null argument");
+    int rc = t->tk.decode_file(in_path, out_path, n_ids, n_bytes);
     return rc ? fail(rc, t->tk.error()) : MBPE_OK;
 }
 extern "C" int mbpe_tokenizer_decode(mbpe_tokenizer *t, const uint32_t *ids, uint64_t n, uint8_t *out,

@@ -299,6 +299,11 @@ def test_streaming_file_encode_equals_in_memory(pkg, tmp_path, monkeypatch, seg)
     n = tk.encode_file(src, dst)
     got = np.fromfile(dst, np.uint32)
     assert n == len(want) == len(got) and np.array_equal(got, want)
+    if seg == "65536":  # and back: .enc file -> text file in blocks
+        back = tmp_path / "back.txt"
+        assert tk.decode_file(dst, back) == (len(want), len(text)) and back.read_bytes() == text
+        (tmp_path / "odd.enc").write_bytes(want[:5].tobytes() + b"\x01\x02")  # trailing partial word is dropped
+        assert tk.decode_file(tmp_path / "odd.enc", back)[0] == 5 and back.read_bytes() == tk.decode(want[:5])
     # empty and tiny files
     (tmp_path / "e.txt").write_bytes(b"")
     assert tk.encode_file(tmp_path / "e.txt", tmp_path / "e.enc") == 0 and (tmp_path / "e.enc").stat().st_size == 0
