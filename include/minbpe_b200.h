@@ -280,8 +280,9 @@ int mbpe_encode_text(mbpe_encoder *enc, mbpe_pretok *p, const uint8_t *text, uin
  * boundary can be found (then read the file and call mbpe_encode_text / mbpe_encode). */
 int mbpe_encode_file(mbpe_encoder *enc, mbpe_pretok *p, const char *in_path, const char *out_path, uint64_t *n_bytes,
                      uint64_t *n_ids);
-/* a trainer over a device corpus (copied device to device; the corpus may be freed afterwards) */
-int mbpe_trainer_create_device(const mbpe_device_corpus *c, mbpe_trainer **out);
+/* a trainer over a device corpus: takes the corpus buffers over (the struct is cleared; freeing it afterwards is a
+ * no-op), nothing is copied */
+int mbpe_trainer_create_device(mbpe_device_corpus *c, mbpe_trainer **out);
 
 #ifdef __cplusplus
 }

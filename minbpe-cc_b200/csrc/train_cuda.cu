@@ -11,6 +11,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -552,8 +553,36 @@ struct mbpe_trainer {
     uint32_t *d_weight = nullptr;
     uint64_t n_tokens = 0, n_chunks = 0;
     Ctl *pinned_ctl = nullptr;
+    bool pooled = false; // d_* came from the stream-ordered pool (mbpe_trainer_create_device)
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
 };
+
+// one pinned control block is kept between trainers: cudaMallocHost / cudaFreeHost per trainer cost milliseconds
+static std::mutex g_pinned_mu;
+static Ctl *g_pinned_spare = nullptr;
+static Ctl *pinned_ctl_take() {
+    {
+        std::lock_guard<std::mutex> lk(g_pinned_mu);
+        if (g_pinned_spare) {
+            Ctl *p = g_pinned_spare;
+            g_pinned_spare = nullptr;
+            return p;
+        }
+    }
+    Ctl *p = nullptr;
+    return cudaMallocHost(&p, sizeof(Ctl)) == cudaSuccess ? p : nullptr;
+}
+static void pinned_ctl_give(Ctl *p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_pinned_mu);
+        if (!g_pinned_spare) {
+            g_pinned_spare = p;
+            return;
+        }
+    }
+    cudaFreeHost(p);
+}
 
 extern "C" int mbpe_trainer_create(const uint32_t *tokens, uint64_t n_tokens, const uint64_t *chunk_off,
                                    uint64_t n_chunks, const uint32_t *chunk_weight, int device, mbpe_trainer **out) {
@@ -583,7 +612,8 @@ extern "C" int mbpe_trainer_create(const uint32_t *tokens, uint64_t n_tokens, co
         MB_CUDA(cudaMalloc(&t->d_weight, std::max<uint64_t>(n_chunks, 1) * 4));
         MB_CUDA(cudaMemcpy(t->d_weight, chunk_weight, n_chunks * 4, cudaMemcpyHostToDevice));
     }
-    MB_CUDA(cudaMallocHost(&t->pinned_ctl, sizeof(Ctl)));
+    t->pinned_ctl = pinned_ctl_take();
+    if (!t->pinned_ctl) return set_error(MBPE_E_CUDA, "out of pinned memory");
     for (auto &e : t->ev) MB_CUDA(cudaEventCreate(&e));
     // keep freed blocks in the stream-ordered pool so repeated runs do not go back to the driver
     cudaMemPool_t pool;
@@ -595,7 +625,8 @@ extern "C" int mbpe_trainer_create(const uint32_t *tokens, uint64_t n_tokens, co
     return MBPE_OK;
 }
 
-extern "C" int mbpe_trainer_create_device(const mbpe_device_corpus *c, mbpe_trainer **out) {
+// takes the corpus buffers over (the struct is cleared): nothing is copied or allocated
+extern "C" int mbpe_trainer_create_device(mbpe_device_corpus *c, mbpe_trainer **out) {
     if (!out || !c || !c->d_off) return set_error(MBPE_E_INVALID, "null argument");
     *out = nullptr;
     if (c->n_tokens >= (1ull << 30)) return set_error(MBPE_E_INVALID, "n_tokens must be < 2^30 per trainer");
@@ -605,16 +636,20 @@ extern "C" int mbpe_trainer_create_device(const mbpe_device_corpus *c, mbpe_trai
     t->device = c->device;
     t->n_tokens = c->n_tokens;
     t->n_chunks = c->n_unique;
-    MB_CUDA(cudaMalloc(&t->d_tokens, std::max<uint64_t>(c->n_tokens, 1) * 4));
-    MB_CUDA(cudaMalloc(&t->d_off, (c->n_unique + 1) * 8));
-    MB_CUDA(cudaMalloc(&t->d_weight, std::max<uint64_t>(c->n_unique, 1) * 4));
-    MB_CUDA(cudaMemcpy(t->d_tokens, c->d_tokens, c->n_tokens * 4, cudaMemcpyDeviceToDevice));
-    MB_CUDA(cudaMemcpy(t->d_off, c->d_off, (c->n_unique + 1) * 8, cudaMemcpyDeviceToDevice));
-    MB_CUDA(cudaMemcpy(t->d_weight, c->d_weight, c->n_unique * 4, cudaMemcpyDeviceToDevice));
-    MB_CUDA(cudaMallocHost(&t->pinned_ctl, sizeof(Ctl)));
+    t->d_tokens = c->d_tokens;
+    t->d_off = c->d_off;
+    t->d_weight = c->d_weight;
+    t->pooled = true;
+    c->d_tokens = nullptr, c->d_off = nullptr, c->d_weight = nullptr;
+    c->n_tokens = c->n_unique = c->n_chunks = 0;
+    t->pinned_ctl = pinned_ctl_take();
+    if (!t->pinned_ctl) {
+        mbpe_trainer_destroy(t);
+        return set_error(MBPE_E_CUDA, "out of pinned memory");
+    }
     for (auto &e : t->ev) MB_CUDA(cudaEventCreate(&e));
     cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
+    if (cudaDeviceGetDefaultMemPool(&pool, t->device) == cudaSuccess) {
         uint64_t keep = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
@@ -625,10 +660,16 @@ extern "C" int mbpe_trainer_create_device(const mbpe_device_corpus *c, mbpe_trai
 extern "C" void mbpe_trainer_destroy(mbpe_trainer *t) {
     if (!t) return;
     cudaSetDevice(t->device);
-    cudaFree(t->d_tokens);
-    cudaFree(t->d_off);
-    cudaFree(t->d_weight);
-    cudaFreeHost(t->pinned_ctl);
+    if (t->pooled) { // buffers taken over from a device corpus: back to the stream-ordered pool
+        if (t->d_tokens) cudaFreeAsync(t->d_tokens, nullptr);
+        if (t->d_off) cudaFreeAsync(t->d_off, nullptr);
+        if (t->d_weight) cudaFreeAsync(t->d_weight, nullptr);
+    } else {
+        cudaFree(t->d_tokens);
+        cudaFree(t->d_off);
+        cudaFree(t->d_weight);
+    }
+    pinned_ctl_give(t->pinned_ctl);
     for (auto &e : t->ev)
         if (e) cudaEventDestroy(e);
     delete t;
