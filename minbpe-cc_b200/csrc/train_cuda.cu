@@ -48,6 +48,11 @@ struct PersistSmem {
     uint32_t rec_pos[PS_REC];
     uint32_t newp[PS_REC];
     uint32_t cand[PS_SEL * PERSISTENT_THREADS]; // mirror of the candidate list while it fits
+    // LEXICAL mode: what the selection needs of every candidate (Ctx::m_*), so that it reads no global memory
+    int32_t ccnt[PS_SEL * PERSISTENT_THREADS];
+    uint32_t clen[PS_SEL * PERSISTENT_THREADS];
+    uint32_t cseg[PS_SEL * PERSISTENT_THREADS];
+    uint64_t ckey[PS_SEL * PERSISTENT_THREADS];
 };
 
 __device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
@@ -81,6 +86,70 @@ __device__ __forceinline__ void fused_select(const Ctx &c) {
         phase_sel_pick<true>(c, tid, PERSISTENT_THREADS);
         __syncthreads();
         if (tid == 0) phase_sel_commit<true>(c, 1);
+        __syncthreads();
+        return;
+    }
+    if (c.m_cnt) { // LEXICAL mode with the candidate mirror: everything below comes from shared memory
+        int32_t cv[PS_SEL], best = CMAX_NONE;
+        uint32_t live = 0;
+#pragma unroll
+        for (int k = 0; k < PS_SEL; k++) {
+            const uint32_t i = tid + k * PERSISTENT_THREADS;
+            cv[k] = i < n ? c.m_cnt[i] : CMAX_NONE;
+            best = cv[k] > best ? cv[k] : best;
+            live += (i < n && cv[k] >= theta);
+        }
+        best = __reduce_max_sync(0xffffffffu, best);
+        live = __reduce_add_sync(0xffffffffu, live);
+        if (lane == 0) {
+            if (best != CMAX_NONE) atomicMax(&g->cmax, best);
+            if (live) atomicAdd(&g->n_live, live);
+        }
+        __syncthreads();
+        const int32_t cmax = g->cmax;
+        if (cmax == CMAX_NONE || cmax < theta) {
+            __syncthreads();
+            if (tid == 0) g->status = ST_NEED_REBUILD;
+            __syncthreads();
+            return;
+        }
+        uint64_t mine = ~0ull;
+#pragma unroll
+        for (int k = 0; k < PS_SEL; k++) {
+            const uint32_t i = tid + k * PERSISTENT_THREADS;
+            if (i < n && cv[k] == cmax) {
+                const uint64_t key = c.m_key[i];
+                mine = key < mine ? key : mine;
+            }
+        }
+        mine = warp_min_u64(mine);
+        if (lane == 0 && mine != ~0ull) atomicMin((unsigned long long *)&g->best_tie, (unsigned long long)mine);
+        __syncthreads();
+        const uint64_t win = g->best_tie;
+#pragma unroll
+        for (int k = 0; k < PS_SEL; k++) {
+            const uint32_t i = tid + k * PERSISTENT_THREADS;
+            if (i < n && cv[k] == cmax && c.m_key[i] == win) { // exactly one thread: keys are unique
+                const uint32_t seg_len = c.m_len[i], step = g->step;
+                g->best_slot = c.cand[i];
+                g->best_cand = i;
+                g->seg_len = seg_len;
+                const uint64_t need = (uint64_t)g->n_pairs + 2ull * seg_len + 64;
+                if (need * MB_LOAD_DEN > ((uint64_t)c.cap_mask + 1) * MB_LOAD_NUM) {
+                    g->status = ST_NEED_GROW;
+                } else {
+                    g->a = (uint32_t)(win >> 32);
+                    g->b = (uint32_t)win;
+                    g->new_id = 256 + step;
+                    g->seg = c.m_seg[i];
+                    c.merges_out[2 * step] = (uint32_t)(win >> 32);
+                    c.merges_out[2 * step + 1] = (uint32_t)win;
+                    c.counts_out[step] = cmax;
+                    g->selected = 1;
+                    if (seg_len > g->big_limit) g->status = ST_BIG_MERGE;
+                }
+            }
+        }
         __syncthreads();
         return;
     }
@@ -193,6 +262,24 @@ __global__ void __launch_bounds__(PERSISTENT_THREADS, 1) k_persistent(const Ctx 
         c.cand = sm->cand;
         c.cand_cap = PS_SEL * PERSISTENT_THREADS; // appends past it are dropped and phase_fin asks for a rebuild
         __syncthreads();
+        if (g->mode == 1 && !cg.xrec && cg.m_cap) { // LEXICAL, single GPU (m_cap != 0: the host allows it): mirror the candidates' slots
+            for (uint32_t i = tid; i < n_cand_in; i += PERSISTENT_THREADS) {
+                const uint32_t s = sm->cand[i];
+                const uint4 *sp = reinterpret_cast<const uint4 *>(&cg.slot[s]);
+                const uint4 head = __ldcg(sp), tail = __ldcg(sp + 1); // {key.lo, key.hi, cnt, len} {first, seg, fill, pad}
+                sm->ccnt[i] = (int32_t)head.z;
+                sm->ckey[i] = ((uint64_t)head.y << 32) | head.x;
+                sm->clen[i] = head.w;
+                sm->cseg[i] = tail.y;
+                if (tail.w != i + 1) cg.slot[s].pad = i + 1; // (kept by seg_alloc / rebuild_collect; cheap insurance)
+            }
+            c.m_cnt = sm->ccnt;
+            c.m_key = sm->ckey;
+            c.m_len = sm->clen;
+            c.m_seg = sm->cseg;
+            c.m_cap = PS_SEL * PERSISTENT_THREADS;
+            __syncthreads();
+        }
     }
     long long t0 = clock64();
     const long long t_enter = t0;
@@ -532,7 +619,10 @@ struct CudaBE {
             attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
             cfg.numAttrs = 1;
         }
-        note(cudaLaunchKernelEx(&cfg, k_persistent, c), "k_persistent launch");
+        Ctx cl = c;
+        static const bool no_mirror = getenv("MBPE_NO_CAND_MIRROR") != nullptr;
+        cl.m_cap = no_mirror ? 0 : 1; // request the shared-memory candidate mirror (the kernel sets the real capacity)
+        note(cudaLaunchKernelEx(&cfg, k_persistent, cl), "k_persistent launch");
         n_launch++;
         note(cudaGetLastError(), "k_persistent launch");
     }

@@ -80,6 +80,7 @@ class TrainLoop {
         h.status = ST_NEED_REBUILD;
         h.cmax = CMAX_NONE;
         h.best_tie = ~0ull;
+        h.best_cand = NIL;
         h.theta = 1;
         h.big_limit = cfg.big_limit;
         h.cand_limit = cfg.cand_limit ? cfg.cand_limit : 4096;
@@ -270,6 +271,7 @@ class TrainLoopSharded {
         h.status = ST_NEED_REBUILD;
         h.cmax = CMAX_NONE;
         h.best_tie = ~0ull;
+        h.best_cand = NIL;
         h.theta = 1;
         h.big_limit = ~0u;
         h.cand_limit = cfg.cand_limit ? cfg.cand_limit : 4096;

@@ -83,7 +83,7 @@ struct Slot {
     uint32_t first; // min live position, or NO_FIRST
     uint32_t seg;   // segment start in the arena
     uint32_t fill;  // segment fill cursor
-    uint32_t pad;
+    uint32_t pad;   // index in the candidate list + 1, 0 = not a candidate (kept by seg_alloc / rebuild_collect)
 };
 static_assert(sizeof(Slot) == 32, "Slot is one 32-byte sector");
 
@@ -106,6 +106,7 @@ struct Ctl {
     uint32_t n_fix;
     uint64_t best_tie;
     uint32_t best_slot;
+    uint32_t best_cand; // resident CTA with the candidate mirror: index of best_slot in the candidate list, else NIL
     uint32_t a, b, new_id;
     uint32_t seg, seg_len;
     int32_t theta;
@@ -160,6 +161,14 @@ struct Ctx {
     XRec *xrec;        // this step's count deltas for the other ranks (nullptr = single GPU)
     uint32_t xrec_cap;
     uint32_t pos_base; // global position of local position 0 (first-occurrence keys are global positions)
+    // resident CTA, LEXICAL mode: shared-memory mirror of the candidates (index = position in the candidate list), so
+    // that the selection reads no global memory at all. m_cnt follows every count change (pair_dec_at finds the
+    // index in Slot::pad); key / len / seg never change once a pair's birth step is over. nullptr elsewhere.
+    int32_t *m_cnt;
+    uint64_t *m_key;
+    uint32_t *m_len;
+    uint32_t *m_seg;
+    uint32_t m_cap;
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -395,14 +404,21 @@ MB_HD uint32_t upsert_after_claim(const Ctx &c, uint64_t key, uint32_t home, uin
 #define MB_L(ptr) ctl_ld<S>(ptr) /* step lists: hit, rec_*, newp, cand, fix */
 
 // -(p,q) x w for the occurrence whose first token sits at position pairpos
-MB_HD void pair_dec_at(const Ctx &c, int32_t mode, uint32_t s, uint32_t w, uint32_t pairpos);
+// (hint_slot, hint_pad): Slot::pad of hint_slot if the caller already loaded it next to the key (NIL: no hint)
+MB_HD void pair_dec_at(const Ctx &c, int32_t mode, uint32_t s, uint32_t w, uint32_t pairpos, uint32_t hint_slot = NIL,
+                       uint32_t hint_pad = 0);
 MB_HD void pair_dec(const Ctx &c, int32_t mode, uint32_t p, uint32_t q, uint32_t w, uint32_t pairpos) {
     // reference: decrement only if present (Tokenizer.h:250-256); with exact counts it always is
     pair_dec_at(c, mode, slot_find(c, pair_key(p, q)), w, pairpos);
 }
-MB_HD void pair_dec_at(const Ctx &c, int32_t mode, uint32_t s, uint32_t w, uint32_t pairpos) {
+MB_HD void pair_dec_at(const Ctx &c, int32_t mode, uint32_t s, uint32_t w, uint32_t pairpos, uint32_t hint_slot,
+                       uint32_t hint_pad) {
     if (s == NIL) return;
     a_add(&c.slot[s].cnt, -(int32_t)w);
+    if (c.m_cnt) { // keep the resident CTA's candidate mirror in step
+        const uint32_t ci = (s == hint_slot) ? hint_pad : ld_l2(&c.slot[s].pad);
+        if (ci != 0 && ci <= c.m_cap) a_add(&c.m_cnt[ci - 1], -(int32_t)w);
+    }
     if (mode == 0 && ld_l2(&c.slot[s].first) == c.pos_base + pairpos) c.slot[s].first = NO_FIRST;
     if (c.xrec) { // the other ranks hold the same pair with the same global count: tell them
         uint32_t r = claim_one(&c.ctl->n_xrec);
@@ -558,6 +574,7 @@ MB_HD void phase_sel_commit(const Ctx &c, int persistent) {
     uint64_t key = ld_l2(&c.slot[s].key);
     uint32_t step = MB_G(step), seg_len = ld_l2(&c.slot[s].len);
     g->seg_len = seg_len;
+    g->best_cand = NIL; // chosen through the table, not through the resident CTA's candidate mirror
     // every occurrence can create two pairs; keep the load factor under 0.6 after the step
     uint64_t need = (uint64_t)MB_G(n_pairs) + 2ull * seg_len + 64;
     if (need * MB_LOAD_DEN > ((uint64_t)c.cap_mask + 1) * MB_LOAD_NUM) {
@@ -625,13 +642,16 @@ MB_HD void phase_hits(const Ctx &c, uint32_t tid, uint32_t nth) {
             const uint32_t hd1 = hash_key(kd1) & c.cap_mask, hi1 = hash_key(ki1) & c.cap_mask;
             const uint32_t hd2 = hash_key(kd2) & c.cap_mask, hi2 = hash_key(ki2) & c.cap_mask;
             uint64_t fd1 = 0, fi1 = 0, fd2 = 0, fi2 = 0;
+            uint32_t pd1 = 0, pd2 = 0; // candidate index of the home slots (same sector as the key: no extra latency)
             if (do_l) {
                 fd1 = ld_l2(&c.slot[hd1].key);
                 fi1 = ld_l2(&c.slot[hi1].key);
+                if (c.m_cnt) pd1 = ld_l2(&c.slot[hd1].pad);
             }
             if (has_r) {
                 fd2 = ld_l2(&c.slot[hd2].key);
                 fi2 = ld_l2(&c.slot[hi2].key);
+                if (c.m_cnt) pd2 = ld_l2(&c.slot[hd2].pad);
             }
             MB_PT(2);
             // both claims of empty home slots go out before either answer is needed
@@ -642,14 +662,14 @@ MB_HD void phase_hits(const Ctx &c, uint32_t tid, uint32_t nth) {
             MB_PT(3);
             if (do_l) {
                 bool created;
-                pair_dec_at(c, mode, slot_find_from(c, kd1, hd1, fd1), w, p.prv);
+                pair_dec_at(c, mode, slot_find_from(c, kd1, hd1, fd1), w, p.prv, hd1, pd1);
                 uint32_t s1 = upsert_after_claim(c, ki1, hi1, fi1, try1, o1, &created);
                 pair_inc_at(c, mode, s1, created, ki1, w, p.prv);
             }
             MB_PT(4);
             if (has_r) {
                 bool created;
-                pair_dec_at(c, mode, slot_find_from(c, kd2, hd2, fd2), w, j);
+                pair_dec_at(c, mode, slot_find_from(c, kd2, hd2, fd2), w, j, hd2, pd2);
                 uint32_t s2 = upsert_after_claim(c, ki2, hi2, fi2, try2, o2, &created);
                 pair_inc_at(c, mode, s2, created, ki2, w, pos);
             }
@@ -709,10 +729,19 @@ MB_HD void phase_seg_alloc(const Ctx &c, uint32_t tid, uint32_t nth) {
     int32_t theta = MB_G(theta);
     for (uint32_t i = tid; i < n; i += nth) {
         uint32_t s = MB_L(&c.newp[i]);
-        c.slot[s].seg = a_add(&g->arena_cursor, ld_l2(&c.slot[s].len));
-        if (ld_l2(&c.slot[s].cnt) >= theta) {
+        const uint32_t len = ld_l2(&c.slot[s].len), seg = a_add(&g->arena_cursor, len);
+        const int32_t cnt = ld_l2(&c.slot[s].cnt);
+        c.slot[s].seg = seg;
+        if (cnt >= theta) {
             uint32_t k = a_add(&g->n_cand, 1u);
             if (k < c.cand_cap) c.cand[k] = s; // cannot overflow: cand_cap >= number of pairs
+            c.slot[s].pad = k + 1;
+            if (c.m_cnt && k < c.m_cap) { // counts and length of a new pair are final here (the hits phase is over)
+                c.m_cnt[k] = cnt;
+                c.m_key[k] = ld_l2(&c.slot[s].key);
+                c.m_len[k] = len;
+                c.m_seg[k] = seg;
+            }
         }
     }
 }
@@ -738,6 +767,11 @@ MB_HD void phase_fin(const Ctx &c) {
     g->rescan_bytes = MB_G(rescan_bytes) + 8ull * live + 4ull * (live - n_hit) + 16ull * MB_G(n_pairs);
     g->live_tokens = live - n_hit;
     c.slot[MB_G(best_slot)].cnt = 0; // every occurrence of (a,b) was merged or destroyed
+    if (c.m_cnt) { // best_cand: the winner's place in the candidate list when the mirror-based selection chose it
+        const uint32_t ci = MB_G(best_cand) != NIL ? MB_G(best_cand) + 1 : ld_l2(&c.slot[MB_G(best_slot)].pad);
+        if (ci != 0 && ci <= c.m_cap) c.m_cnt[ci - 1] = 0;
+    }
+    g->best_cand = NIL;
     g->step = step;
     g->selected = 0;
     g->n_hit = 0;
@@ -766,6 +800,7 @@ MB_HD void phase_sel_reset(const Ctx &c) {
     g->n_fix = 0;
     g->n_live = 0;
     g->selected = 0;
+    g->best_cand = NIL;
     g->cand_base = MB_G(n_cand);
     if (MB_G(status) != ST_EXHAUSTED) g->status = ST_RUN;
 }
@@ -827,7 +862,13 @@ MB_HD void phase_rebuild_collect(const Ctx &c, uint32_t tid, uint32_t nth) {
     int32_t theta = MB_G(theta);
     for (uint32_t s = tid; s < cap; s += nth) {
         if (ld_l2(&c.slot[s].key) == EMPTY_KEY) continue;
-        if (ld_l2(&c.slot[s].cnt) >= theta) c.cand[a_add(&g->n_cand, 1u)] = s;
+        uint32_t idx = 0; // Slot::pad = place in the new list + 1, 0 for everything that is not on it
+        if (ld_l2(&c.slot[s].cnt) >= theta) {
+            const uint32_t k = a_add(&g->n_cand, 1u);
+            c.cand[k] = s;
+            idx = k + 1;
+        }
+        if (ld_l2(&c.slot[s].pad) != idx) c.slot[s].pad = idx;
     }
 }
 
