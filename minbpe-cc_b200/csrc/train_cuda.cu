@@ -53,6 +53,10 @@ struct PersistSmem {
     uint32_t clen[PS_SEL * PERSISTENT_THREADS];
     uint32_t cseg[PS_SEL * PERSISTENT_THREADS];
     uint64_t ckey[PS_SEL * PERSISTENT_THREADS];
+    // block reductions of the mirror-based selection: one word per warp, re-reduced by every warp (no atomics)
+    int32_t red_max[PERSISTENT_THREADS / 32];
+    uint32_t red_live[PERSISTENT_THREADS / 32];
+    uint64_t red_tie[PERSISTENT_THREADS / 32];
 };
 
 __device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
@@ -65,7 +69,8 @@ __device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
 
 // get_top_pair_count for the resident CTA: same result as sel_max .. sel_commit, but each candidate's slot is
 // fetched once (one 16-byte load: key, cnt, len) and kept in registers across the three reductions.
-__device__ __forceinline__ void fused_select(const Ctx &c) {
+struct PersistSmem;
+__device__ __forceinline__ void fused_select(const Ctx &c, PersistSmem *red) {
     Ctl *g = c.ctl; // shared memory
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t n = g->n_cand;
@@ -90,63 +95,83 @@ __device__ __forceinline__ void fused_select(const Ctx &c) {
         return;
     }
     if (c.m_cnt) { // LEXICAL mode with the candidate mirror: everything below comes from shared memory
+        // The selection is issue-bound (32 warps run the same code), so warp w owns candidates [128 w, 128 w + 128) and
+        // warps without candidates only keep the barriers company; partial results travel through one word per
+        // warp and are reduced again by whoever needs them.
+        const uint32_t warp = tid >> 5, i0 = warp * (PS_SEL * 32) + lane;
+        const bool owner = warp * (PS_SEL * 32) < n; // warp-uniform
         int32_t cv[PS_SEL], best = CMAX_NONE;
-        uint32_t live = 0;
+        if (owner) {
+            uint32_t live = 0;
 #pragma unroll
-        for (int k = 0; k < PS_SEL; k++) {
-            const uint32_t i = tid + k * PERSISTENT_THREADS;
-            cv[k] = i < n ? c.m_cnt[i] : CMAX_NONE;
-            best = cv[k] > best ? cv[k] : best;
-            live += (i < n && cv[k] >= theta);
-        }
-        best = __reduce_max_sync(0xffffffffu, best);
-        live = __reduce_add_sync(0xffffffffu, live);
-        if (lane == 0) {
-            if (best != CMAX_NONE) atomicMax(&g->cmax, best);
-            if (live) atomicAdd(&g->n_live, live);
+            for (int k = 0; k < PS_SEL; k++) {
+                const uint32_t i = i0 + k * 32;
+                cv[k] = i < n ? c.m_cnt[i] : CMAX_NONE;
+                best = cv[k] > best ? cv[k] : best;
+                live += (i < n && cv[k] >= theta);
+            }
+            best = __reduce_max_sync(0xffffffffu, best);
+            live = __reduce_add_sync(0xffffffffu, live);
+            if (lane == 0) {
+                red->red_max[warp] = best;
+                red->red_live[warp] = live;
+            }
+        } else if (lane == 0) {
+            red->red_max[warp] = CMAX_NONE;
+            red->red_live[warp] = 0;
         }
         __syncthreads();
-        const int32_t cmax = g->cmax;
-        if (cmax == CMAX_NONE || cmax < theta) {
-            __syncthreads();
-            if (tid == 0) g->status = ST_NEED_REBUILD;
-            __syncthreads();
-            return;
-        }
-        uint64_t mine = ~0ull;
-#pragma unroll
-        for (int k = 0; k < PS_SEL; k++) {
-            const uint32_t i = tid + k * PERSISTENT_THREADS;
-            if (i < n && cv[k] == cmax) {
-                const uint64_t key = c.m_key[i];
-                mine = key < mine ? key : mine;
+        static_assert(PERSISTENT_THREADS / 32 == 32, "one partial result per lane");
+        int32_t cmax = CMAX_NONE;
+        if (owner || warp == 0) cmax = __reduce_max_sync(0xffffffffu, red->red_max[lane]);
+        if (warp == 0) {
+            const uint32_t all_live = __reduce_add_sync(0xffffffffu, red->red_live[lane]);
+            if (lane == 0) {
+                g->cmax = cmax;
+                g->n_live = all_live;
+                if (cmax == CMAX_NONE || cmax < theta) g->status = ST_NEED_REBUILD;
             }
         }
-        mine = warp_min_u64(mine);
-        if (lane == 0 && mine != ~0ull) atomicMin((unsigned long long *)&g->best_tie, (unsigned long long)mine);
-        __syncthreads();
-        const uint64_t win = g->best_tie;
+        uint64_t mine = ~0ull;
+        if (owner && cmax != CMAX_NONE && cmax >= theta && best == cmax) { // only warps that hold the best count
 #pragma unroll
-        for (int k = 0; k < PS_SEL; k++) {
-            const uint32_t i = tid + k * PERSISTENT_THREADS;
-            if (i < n && cv[k] == cmax && c.m_key[i] == win) { // exactly one thread: keys are unique
-                const uint32_t seg_len = c.m_len[i], step = g->step;
-                g->best_slot = c.cand[i];
-                g->best_cand = i;
-                g->seg_len = seg_len;
-                const uint64_t need = (uint64_t)g->n_pairs + 2ull * seg_len + 64;
-                if (need * MB_LOAD_DEN > ((uint64_t)c.cap_mask + 1) * MB_LOAD_NUM) {
-                    g->status = ST_NEED_GROW;
-                } else {
-                    g->a = (uint32_t)(win >> 32);
-                    g->b = (uint32_t)win;
-                    g->new_id = 256 + step;
-                    g->seg = c.m_seg[i];
-                    c.merges_out[2 * step] = (uint32_t)(win >> 32);
-                    c.merges_out[2 * step + 1] = (uint32_t)win;
-                    c.counts_out[step] = cmax;
-                    g->selected = 1;
-                    if (seg_len > g->big_limit) g->status = ST_BIG_MERGE;
+            for (int k = 0; k < PS_SEL; k++) {
+                const uint32_t i = i0 + k * 32;
+                if (i < n && cv[k] == cmax) {
+                    const uint64_t key = c.m_key[i];
+                    mine = key < mine ? key : mine;
+                }
+            }
+            mine = warp_min_u64(mine);
+        }
+        if (lane == 0) red->red_tie[warp] = mine;
+        __syncthreads();
+        if (g->status != ST_RUN) return; // (written by thread 0 before the barrier; uniform)
+        if (owner && best == cmax) {
+            const uint64_t win = warp_min_u64(red->red_tie[lane]);
+#pragma unroll
+            for (int k = 0; k < PS_SEL; k++) {
+                const uint32_t i = i0 + k * 32;
+                if (i < n && cv[k] == cmax && c.m_key[i] == win) { // exactly one thread: keys are unique
+                    const uint32_t seg_len = c.m_len[i], step = g->step;
+                    g->best_tie = win;
+                    g->best_slot = c.cand[i];
+                    g->best_cand = i;
+                    g->seg_len = seg_len;
+                    const uint64_t need = (uint64_t)g->n_pairs + 2ull * seg_len + 64;
+                    if (need * MB_LOAD_DEN > ((uint64_t)c.cap_mask + 1) * MB_LOAD_NUM) {
+                        g->status = ST_NEED_GROW;
+                    } else {
+                        g->a = (uint32_t)(win >> 32);
+                        g->b = (uint32_t)win;
+                        g->new_id = 256 + step;
+                        g->seg = c.m_seg[i];
+                        c.merges_out[2 * step] = (uint32_t)(win >> 32);
+                        c.merges_out[2 * step + 1] = (uint32_t)win;
+                        c.counts_out[step] = cmax;
+                        g->selected = 1;
+                        if (seg_len > g->big_limit) g->status = ST_BIG_MERGE;
+                    }
                 }
             }
         }
@@ -299,7 +324,7 @@ __global__ void __launch_bounds__(PERSISTENT_THREADS, 1) k_persistent(const Ctx 
                 if (g->n_cand > g->dbg[1]) g->dbg[1] = g->n_cand;
             }
             long long ts = clock64();
-            fused_select(c);
+            fused_select(c, sm);
             if (tid == 0) {
                 uint64_t d = (uint64_t)(clock64() - ts);
                 if (d > g->dbg[2]) g->dbg[2] = d;
