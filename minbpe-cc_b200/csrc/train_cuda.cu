@@ -44,6 +44,8 @@ constexpr int PS_SEL = 4;                // candidates per thread held in regist
 struct PersistSmem {
     Ctl ctl;
     uint32_t hit[PS_HIT];
+    uint32_t hit_j[PS_HIT];
+    uint32_t hit_y[PS_HIT];
     uint32_t rec_slot[PS_REC];
     uint32_t rec_pos[PS_REC];
     uint32_t newp[PS_REC];
@@ -336,6 +338,8 @@ __global__ void __launch_bounds__(PERSISTENT_THREADS, 1) k_persistent(const Ctx 
         Ctx w = c; // small steps keep their lists in shared memory
         if (g->seg_len <= PS_HIT) {
             w.hit = sm->hit;
+            w.hit_j = sm->hit_j;
+            w.hit_y = sm->hit_y;
             w.rec_slot = sm->rec_slot;
             w.rec_pos = sm->rec_pos;
             w.newp = sm->newp;

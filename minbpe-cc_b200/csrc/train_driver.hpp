@@ -63,6 +63,8 @@ class TrainLoop {
         c_.arena_cap = (uint32_t)(3 * np + 16);
         c_.occ = (uint32_t *)be_.alloc((uint64_t)c_.arena_cap * 4);
         c_.hit = (uint32_t *)be_.alloc((np + 16) * 4);
+        c_.hit_j = (uint32_t *)be_.alloc((np + 16) * 4);
+        c_.hit_y = (uint32_t *)be_.alloc((np + 16) * 4);
         c_.rec_slot = (uint32_t *)be_.alloc((np + 16) * 4);
         c_.rec_pos = (uint32_t *)be_.alloc((np + 16) * 4);
         c_.newp = (uint32_t *)be_.alloc((np + 16) * 4);
@@ -203,7 +205,7 @@ class TrainLoop {
         n_grows_++;
     }
     void free_all() {
-        void *ps[] = {c_.node, c_.occ, c_.hit, c_.rec_slot, c_.rec_pos, c_.newp, c_.ctl,
+        void *ps[] = {c_.node, c_.occ, c_.hit, c_.hit_j, c_.hit_y, c_.rec_slot, c_.rec_pos, c_.newp, c_.ctl,
                       c_.merges_out, c_.counts_out, c_.slot, c_.cand, c_.fix};
         for (void *p : ps)
             if (p) be_.release(p);
@@ -245,6 +247,8 @@ class TrainLoopSharded {
         c_.arena_cap = (uint32_t)(3 * np + 16);
         c_.occ = (uint32_t *)be_.alloc((uint64_t)c_.arena_cap * 4);
         c_.hit = (uint32_t *)be_.alloc((np + 16) * 4);
+        c_.hit_j = (uint32_t *)be_.alloc((np + 16) * 4);
+        c_.hit_y = (uint32_t *)be_.alloc((np + 16) * 4);
         c_.rec_slot = (uint32_t *)be_.alloc((np + 16) * 4);
         c_.rec_pos = (uint32_t *)be_.alloc((np + 16) * 4);
         c_.newp = (uint32_t *)be_.alloc((ng + 65536 + 16) * 4); // births of every rank land here
@@ -364,7 +368,7 @@ class TrainLoopSharded {
         n_rebuilds_++;
     }
     void free_all() {
-        void *ps[] = {c_.node, c_.occ, c_.hit, c_.rec_slot, c_.rec_pos, c_.newp, c_.ctl, c_.merges_out,
+        void *ps[] = {c_.node, c_.occ, c_.hit, c_.hit_j, c_.hit_y, c_.rec_slot, c_.rec_pos, c_.newp, c_.ctl, c_.merges_out,
                       c_.counts_out, c_.slot, c_.cand, c_.fix, c_.xrec};
         for (void *p : ps)
             if (p) be_.release(p);

@@ -148,6 +148,8 @@ struct Ctx {
     uint32_t *occ;     // occurrence arena
     uint32_t arena_cap;
     uint32_t *hit;      // positions of this step's merges
+    uint32_t *hit_j;    // ... the position of each merge's second token and of the token after it, as the occurrence
+    uint32_t *hit_y;    //     walk saw them: the rewrite (mutate) then needs no loads at all
     uint32_t *rec_slot; // this step's new-occurrence records
     uint32_t *rec_pos;
     uint32_t *newp;     // slots created this step
@@ -621,7 +623,12 @@ MB_HD void phase_hits(const Ctx &c, uint32_t tid, uint32_t nth) {
         MB_PT(0);
         const uint32_t w = p.wt;
         if (a != b) {
-            c.hit[claim_one(&g->n_hit)] = pos;
+            {
+                const uint32_t hk = claim_one(&g->n_hit);
+                c.hit[hk] = pos;
+                c.hit_j[hk] = j;
+                c.hit_y[hk] = q.nxt;
+            }
             // Gather the whole neighbourhood first, then start all four table probes, then resolve them: the
             // loads of each stage are independent, so the dependent chain is ~7 round trips instead of ~15.
             const bool has_l = p.prv != NIL, has_r = q.nxt != NIL;
@@ -685,8 +692,13 @@ MB_HD void phase_hits(const Ctx &c, uint32_t tid, uint32_t nth) {
             }
             uint32_t cur = pos, second = j;
             for (;;) {
-                c.hit[claim_one(&g->n_hit)] = cur;
                 uint32_t r = ld_tok<S>(&c.node[second].nxt);
+                {
+                    const uint32_t hk = claim_one(&g->n_hit);
+                    c.hit[hk] = cur;
+                    c.hit_j[hk] = second;
+                    c.hit_y[hk] = r;
+                }
                 if (r == NIL) break;
                 Node nr = ld_node<S>(&c.node[r]);
                 if (nr.tok != a) { // run ended right after this pair
@@ -711,10 +723,8 @@ MB_HD void phase_mutate(const Ctx &c, uint32_t tid, uint32_t nth) {
     Ctl *g = c.ctl;
     const uint32_t id = MB_G(new_id), n = MB_G(n_hit);
     for (uint32_t h = tid; h < n; h += nth) {
-        uint32_t pos = MB_L(&c.hit[h]);
-        uint32_t j = ld_tok<S>(&c.node[pos].nxt);
-        uint32_t y = ld_tok<S>(&c.node[j].nxt);
-        c.node[pos].tok = id;
+        const uint32_t pos = MB_L(&c.hit[h]), j = MB_L(&c.hit_j[h]), y = MB_L(&c.hit_y[h]); // the corpus is read-only
+        c.node[pos].tok = id;                                                                  // between the two phases
         c.node[pos].nxt = y;
         c.node[j].tok = DEAD;
         if (y != NIL) c.node[y].prv = pos;
