@@ -40,6 +40,15 @@ def test_no_cpu_fallback(pkg):
     with pytest.raises(pkg.MbpeError) as ei:
         pkg.PairCount("first")
     assert ei.value.code == -2
+    with pytest.raises(pkg.MbpeError) as ei:  # the device pre-tokeniser / dedup front end has no CPU twin either
+        pkg.Pretok()
+    assert ei.value.code == -2
+    # the Tokenizer mirror: GPT-4 text large enough for the device front end still ends in "no device", never in a
+    # silent host computation of the merge loop
+    tk = pkg.Tokenizer(pkg.patterns()["gpt4"])
+    with pytest.raises(pkg.MbpeError) as ei:
+        tk.train(b"hello world, hello there " * 4000, 300, "lexical")
+    assert ei.value.code == -2
 
 
 @pytest.mark.parametrize("fname", ["taylorswift.txt", "sample.txt", "str_unicode.txt", "str_ws.txt", "shakespeare.txt"])
