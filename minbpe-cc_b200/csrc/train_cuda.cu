@@ -975,7 +975,7 @@ extern "C" int mbpe_train_sharded(mbpe_comm *comm, const uint32_t *tokens, uint6
     be.nccl = comm->nccl;
     be.comm_world = (uint32_t)comm->world;
     be.comm_rank = (uint32_t)comm->rank;
-    TrainConfig cfg{vocab_size, mode, MBPE_ENGINE_STEPWISE, ~0u, env_u32("MBPE_CAND_WANT", 1024), 0, 0};
+    TrainConfig cfg{vocab_size, mode, MBPE_ENGINE_STEPWISE, ~0u, env_u32("MBPE_CAND_WANT", 512), 0, 0};
     TrainOutcome o;
     *n_merges_out = 0;
     MB_CUDA(cudaEventRecord(e0, st));
