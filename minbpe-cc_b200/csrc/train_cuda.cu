@@ -50,8 +50,9 @@ struct PersistSmem {
     uint32_t rec_pos[PS_REC];
     uint32_t newp[PS_REC];
     uint32_t cand[PS_SEL * PERSISTENT_THREADS]; // mirror of the candidate list while it fits
-    // LEXICAL mode: what the selection needs of every candidate (Ctx::m_*), so that it reads no global memory
+    // what the selection needs of every candidate (Ctx::m_*), so that it reads no global memory
     int32_t ccnt[PS_SEL * PERSISTENT_THREADS];
+    uint32_t cfirst[PS_SEL * PERSISTENT_THREADS];
     uint32_t clen[PS_SEL * PERSISTENT_THREADS];
     uint32_t cseg[PS_SEL * PERSISTENT_THREADS];
     uint64_t ckey[PS_SEL * PERSISTENT_THREADS];
@@ -134,27 +135,62 @@ __device__ __forceinline__ void fused_select(const Ctx &c, PersistSmem *red) {
                 if (cmax == CMAX_NONE || cmax < theta) g->status = ST_NEED_REBUILD;
             }
         }
+        // tie-break value of candidate i: LEXICAL the pair itself, FIRST its first live position (PairCount.h:66-74,
+        // :195-207). FIRST: a best-count pair whose first occurrence died goes to the fix list; after the rescan of those
+        // pairs' segments the mirror is refreshed and the reduction runs once more.
+        const bool tied_warp = owner && cmax != CMAX_NONE && cmax >= theta && best == cmax;
         uint64_t mine = ~0ull;
-        if (owner && cmax != CMAX_NONE && cmax >= theta && best == cmax) { // only warps that hold the best count
+        if (tied_warp) {
 #pragma unroll
             for (int k = 0; k < PS_SEL; k++) {
                 const uint32_t i = i0 + k * 32;
                 if (i < n && cv[k] == cmax) {
-                    const uint64_t key = c.m_key[i];
-                    mine = key < mine ? key : mine;
+                    uint64_t t;
+                    if (mode == 1) {
+                        t = c.m_key[i];
+                    } else {
+                        const uint32_t f = c.m_first[i];
+                        if (f == NO_FIRST) c.fix[atomicAdd(&g->n_fix, 1u)] = c.cand[i];
+                        t = f == NO_FIRST ? ~0ull : (uint64_t)f;
+                    }
+                    mine = t < mine ? t : mine;
                 }
             }
             mine = warp_min_u64(mine);
         }
         if (lane == 0) red->red_tie[warp] = mine;
         __syncthreads();
+        if (mode == 0 && g->status == ST_RUN && g->n_fix) { // uniform: n_fix was complete at the barrier
+            phase_sel_fix_scan<true>(c, tid, PERSISTENT_THREADS); // Slot::first of the fix list, from their segments
+            __syncthreads();
+            mine = ~0ull;
+            if (tied_warp) {
+#pragma unroll
+                for (int k = 0; k < PS_SEL; k++) {
+                    const uint32_t i = i0 + k * 32;
+                    if (i < n && cv[k] == cmax) {
+                        uint32_t f = c.m_first[i];
+                        if (f == NO_FIRST) {
+                            f = __ldcg(&c.slot[c.cand[i]].first);
+                            c.m_first[i] = f;
+                        }
+                        const uint64_t t = f == NO_FIRST ? ~0ull : (uint64_t)f;
+                        mine = t < mine ? t : mine;
+                    }
+                }
+                mine = warp_min_u64(mine);
+            }
+            if (lane == 0) red->red_tie[warp] = mine;
+            __syncthreads();
+        }
         if (g->status != ST_RUN) return; // (written by thread 0 before the barrier; uniform)
         if (owner && best == cmax) {
             const uint64_t win = warp_min_u64(red->red_tie[lane]);
 #pragma unroll
             for (int k = 0; k < PS_SEL; k++) {
                 const uint32_t i = i0 + k * 32;
-                if (i < n && cv[k] == cmax && c.m_key[i] == win) { // exactly one thread: keys are unique
+                if (i < n && cv[k] == cmax && (mode == 1 ? c.m_key[i] : (uint64_t)c.m_first[i]) == win) { // exactly one
+                    const uint64_t key = c.m_key[i]; // thread: keys are unique, and so are first positions
                     const uint32_t seg_len = c.m_len[i], step = g->step;
                     g->best_tie = win;
                     g->best_slot = c.cand[i];
@@ -164,12 +200,12 @@ __device__ __forceinline__ void fused_select(const Ctx &c, PersistSmem *red) {
                     if (need * MB_LOAD_DEN > ((uint64_t)c.cap_mask + 1) * MB_LOAD_NUM) {
                         g->status = ST_NEED_GROW;
                     } else {
-                        g->a = (uint32_t)(win >> 32);
-                        g->b = (uint32_t)win;
+                        g->a = (uint32_t)(key >> 32);
+                        g->b = (uint32_t)key;
                         g->new_id = 256 + step;
                         g->seg = c.m_seg[i];
-                        c.merges_out[2 * step] = (uint32_t)(win >> 32);
-                        c.merges_out[2 * step + 1] = (uint32_t)win;
+                        c.merges_out[2 * step] = (uint32_t)(key >> 32);
+                        c.merges_out[2 * step + 1] = (uint32_t)key;
                         c.counts_out[step] = cmax;
                         g->selected = 1;
                         if (seg_len > g->big_limit) g->status = ST_BIG_MERGE;
@@ -289,18 +325,20 @@ __global__ void __launch_bounds__(PERSISTENT_THREADS, 1) k_persistent(const Ctx 
         c.cand = sm->cand;
         c.cand_cap = PS_SEL * PERSISTENT_THREADS; // appends past it are dropped and phase_fin asks for a rebuild
         __syncthreads();
-        if (g->mode == 1 && !cg.xrec && cg.m_cap) { // LEXICAL, single GPU (m_cap != 0: the host allows it): mirror the candidates' slots
+        if (!cg.xrec && cg.m_cap) { // single GPU (m_cap != 0: the host allows it): mirror the candidates' slots
             for (uint32_t i = tid; i < n_cand_in; i += PERSISTENT_THREADS) {
                 const uint32_t s = sm->cand[i];
                 const uint4 *sp = reinterpret_cast<const uint4 *>(&cg.slot[s]);
                 const uint4 head = __ldcg(sp), tail = __ldcg(sp + 1); // {key.lo, key.hi, cnt, len} {first, seg, fill, pad}
                 sm->ccnt[i] = (int32_t)head.z;
+                sm->cfirst[i] = tail.x;
                 sm->ckey[i] = ((uint64_t)head.y << 32) | head.x;
                 sm->clen[i] = head.w;
                 sm->cseg[i] = tail.y;
                 if (tail.w != i + 1) cg.slot[s].pad = i + 1; // (kept by seg_alloc / rebuild_collect; cheap insurance)
             }
             c.m_cnt = sm->ccnt;
+            c.m_first = sm->cfirst;
             c.m_key = sm->ckey;
             c.m_len = sm->clen;
             c.m_seg = sm->cseg;

@@ -163,10 +163,11 @@ struct Ctx {
     XRec *xrec;        // this step's count deltas for the other ranks (nullptr = single GPU)
     uint32_t xrec_cap;
     uint32_t pos_base; // global position of local position 0 (first-occurrence keys are global positions)
-    // resident CTA, LEXICAL mode: shared-memory mirror of the candidates (index = position in the candidate list), so
+    // resident CTA: shared-memory mirror of the candidates (index = position in the candidate list), so
     // that the selection reads no global memory at all. m_cnt follows every count change (pair_dec_at finds the
     // index in Slot::pad); key / len / seg never change once a pair's birth step is over. nullptr elsewhere.
     int32_t *m_cnt;
+    uint32_t *m_first; // FIRST mode: Slot::first of the candidate (dynamic: dies with its occurrence, recomputed on a tie)
     uint64_t *m_key;
     uint32_t *m_len;
     uint32_t *m_seg;
@@ -417,11 +418,16 @@ MB_HD void pair_dec_at(const Ctx &c, int32_t mode, uint32_t s, uint32_t w, uint3
                        uint32_t hint_pad) {
     if (s == NIL) return;
     a_add(&c.slot[s].cnt, -(int32_t)w);
-    if (c.m_cnt) { // keep the resident CTA's candidate mirror in step
-        const uint32_t ci = (s == hint_slot) ? hint_pad : ld_l2(&c.slot[s].pad);
-        if (ci != 0 && ci <= c.m_cap) a_add(&c.m_cnt[ci - 1], -(int32_t)w);
+    uint32_t ci = 0; // place in the resident CTA's candidate mirror + 1
+    if (c.m_cnt) {
+        ci = (s == hint_slot) ? hint_pad : ld_l2(&c.slot[s].pad);
+        if (ci > c.m_cap) ci = 0;
+        if (ci) a_add(&c.m_cnt[ci - 1], -(int32_t)w);
     }
-    if (mode == 0 && ld_l2(&c.slot[s].first) == c.pos_base + pairpos) c.slot[s].first = NO_FIRST;
+    if (mode == 0 && ld_l2(&c.slot[s].first) == c.pos_base + pairpos) {
+        c.slot[s].first = NO_FIRST;
+        if (ci) c.m_first[ci - 1] = NO_FIRST;
+    }
     if (c.xrec) { // the other ranks hold the same pair with the same global count: tell them
         uint32_t r = claim_one(&c.ctl->n_xrec);
         if (r < c.xrec_cap) {
@@ -748,6 +754,7 @@ MB_HD void phase_seg_alloc(const Ctx &c, uint32_t tid, uint32_t nth) {
             c.slot[s].pad = k + 1;
             if (c.m_cnt && k < c.m_cap) { // counts and length of a new pair are final here (the hits phase is over)
                 c.m_cnt[k] = cnt;
+                c.m_first[k] = ld_l2(&c.slot[s].first);
                 c.m_key[k] = ld_l2(&c.slot[s].key);
                 c.m_len[k] = len;
                 c.m_seg[k] = seg;
