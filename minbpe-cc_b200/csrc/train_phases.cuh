@@ -47,7 +47,7 @@ constexpr int HIST_BUCKETS = 256;
 // concurrent probes, each step a dependent DRAM access) sets the step latency, so the table is kept sparse
 #ifndef MB_LOAD_NUM
 #define MB_LOAD_NUM 3
-#define MB_LOAD_DEN 10
+#define MB_LOAD_DEN 20
 #endif
 
 // count -> bucket: floor(log2 v) and the next three mantissa bits (monotone in v); bucket -> its smallest count
