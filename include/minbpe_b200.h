@@ -265,8 +265,9 @@ int mbpe_pretok_dedup_device(mbpe_pretok *p, const uint8_t *d_text, uint64_t len
                              uint64_t n_chunks, mbpe_device_corpus *out, void *stream);
 /* the same over several resident text segments (each < 4 GiB; a corpus larger than one segment): chunk order =
  * segment order, so first-appearance order is that of the whole text */
-int mbpe_pretok_dedup_segments(mbpe_pretok *p, const uint8_t *const *d_texts, const uint32_t *const *d_offs,
-                               const uint64_t *seg_chunks, uint32_t n_segs, mbpe_device_corpus *out, void *stream);
+int mbpe_pretok_dedup_segments(mbpe_pretok *p, const uint8_t *const *d_texts, const uint64_t *seg_bytes,
+                               const uint32_t *const *d_offs, const uint64_t *seg_chunks, uint32_t n_segs,
+                               mbpe_device_corpus *out, void *stream);
 /* host text -> device corpus (H2D + split + dedup): the front end of Tokenizer::train (:500-556) */
 int mbpe_pretok_corpus(mbpe_pretok *p, const uint8_t *text, uint64_t len, mbpe_device_corpus *out);
 int mbpe_device_corpus_download(const mbpe_device_corpus *c, uint32_t *tokens, uint64_t *off, uint32_t *weight);

@@ -156,6 +156,7 @@ struct DdSeg {
     const uint8_t *text;
     const uint32_t *off; // this segment's chunk offsets (n + 1), relative to its text
     uint64_t chunk0;     // global index of its first chunk
+    uint64_t n_bytes;    // readable bytes of `text` (the 16-byte key loads never cross it)
 };
 struct DedupArgs {
     DdSeg seg[DD_MAX_SEGS];
@@ -166,6 +167,7 @@ struct DedupArgs {
     uint32_t mask;
     uint32_t *used;     // claimed slots
     uint32_t *overflow; // probe limit hit: table too small
+    uint32_t fast;      // every segment's text is 4-byte aligned: chunks of <= 16 bytes are read as five aligned words
 };
 
 __device__ __forceinline__ uint64_t dd_hash(const uint8_t *text, uint32_t o, uint32_t len) {
@@ -187,6 +189,44 @@ __device__ __forceinline__ uint64_t dd_hash(const uint8_t *text, uint32_t o, uin
     return h;
 }
 
+// dd_hash() of a chunk of <= 16 bytes given as two little-endian words (bytes past the chunk zeroed): same value
+__device__ __forceinline__ uint64_t dd_hash16(uint64_t k0, uint64_t k1, uint32_t len) {
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ len;
+    uint64_t v = k0;
+    if (len >= 8) {
+        h = (h ^ k0) * 0xff51afd7ed558ccdULL;
+        h ^= h >> 29;
+        v = k1;
+        if (len == 16) {
+            h = (h ^ k1) * 0xff51afd7ed558ccdULL;
+            h ^= h >> 29;
+            v = 0;
+        }
+    }
+    h = (h ^ v) * 0xc4ceb9fe1a85ec53ULL;
+    h ^= h >> 32;
+    h *= 0xff51afd7ed558ccdULL;
+    h ^= h >> 29;
+    return h;
+}
+// the first 16 bytes of the chunk at o (len <= 16) as two words, bytes past the chunk zeroed. text is 4-byte
+// aligned and o + 20 <= readable bytes: five aligned word loads in flight at once instead of a byte loop
+__device__ __forceinline__ void dd_load16(const uint8_t *text, uint32_t o, uint32_t len, uint64_t &k0, uint64_t &k1) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(text + (o & ~3u));
+    const uint32_t sh = (o & 3) * 8;
+    const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3), w4 = __ldg(w + 4);
+    const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh);
+    const uint32_t v2 = __funnelshift_r(w2, w3, sh), v3 = __funnelshift_r(w3, w4, sh);
+    k0 = ((uint64_t)v1 << 32) | v0;
+    k1 = ((uint64_t)v3 << 32) | v2;
+    if (len < 8) {
+        k0 &= (1ull << (len * 8)) - 1;
+        k1 = 0;
+    } else if (len < 16) {
+        k1 &= (1ull << ((len - 8) * 8)) - 1;
+    }
+}
+
 __device__ __forceinline__ const DdSeg &dd_seg(const DedupArgs &a, uint64_t c) {
     uint32_t k = 0;
     while (k + 1 < a.n_segs && a.seg[k + 1].chunk0 <= c) k++;
@@ -206,7 +246,10 @@ __global__ void __launch_bounds__(256) k_dedup_insert(const DedupArgs a) {
     for (uint64_t c = blockIdx.x * 256ull + threadIdx.x; c < a.n_chunks; c += (uint64_t)gridDim.x * 256) {
         const DdSeg &sg = dd_seg(a, c);
         const uint32_t o = __ldg(sg.off + (c - sg.chunk0)), len = __ldg(sg.off + (c - sg.chunk0) + 1) - o;
-        const uint64_t h = dd_hash(sg.text, o, len);
+        const bool fast = a.fast && len <= 16 && (uint64_t)o + 20 <= sg.n_bytes;
+        uint64_t k0 = 0, k1 = 0;
+        if (fast) dd_load16(sg.text, o, len, k0, k1);
+        const uint64_t h = fast ? dd_hash16(k0, k1, len) : dd_hash(sg.text, o, len);
         const unsigned long long mine = ((h >> 33) << 32) | (uint32_t)c;
         uint32_t s = (uint32_t)h & a.mask;
         for (uint32_t probes = 0;; probes++) {
@@ -225,7 +268,23 @@ __global__ void __launch_bounds__(256) k_dedup_insert(const DedupArgs a) {
             }
             if ((w >> 32) == (mine >> 32)) {
                 const uint32_t rep = (uint32_t)w;
-                if (rep == (uint32_t)c || dd_equal(a, sg.text, o, len, rep)) {
+                bool same = rep == (uint32_t)c;
+                if (!same && fast) { // both chunks as 16-byte keys when the representative allows it too
+                    const DdSeg &rs = dd_seg(a, rep);
+                    const uint32_t ro = __ldg(rs.off + (rep - rs.chunk0)), rl = __ldg(rs.off + (rep - rs.chunk0) + 1) - ro;
+                    if (rl != len) {
+                        same = false;
+                    } else if ((uint64_t)ro + 20 <= rs.n_bytes) {
+                        uint64_t r0, r1;
+                        dd_load16(rs.text, ro, len, r0, r1);
+                        same = r0 == k0 && r1 == k1;
+                    } else {
+                        same = dd_equal(a, sg.text, o, len, rep);
+                    }
+                } else if (!same) {
+                    same = dd_equal(a, sg.text, o, len, rep);
+                }
+                if (same) {
                     if ((uint32_t)c < rep) atomicMin(&a.words[s], mine); // keep the FIRST occurrence as representative
                     atomicAdd(&a.counts[s], 1u);
                     break;
@@ -547,9 +606,10 @@ extern "C" void mbpe_device_corpus_free(mbpe_device_corpus *c) {
     memset(c, 0, sizeof *c);
 }
 
-extern "C" int mbpe_pretok_dedup_segments(mbpe_pretok *p, const uint8_t *const *d_texts, const uint32_t *const *d_offs,
-                                          const uint64_t *seg_chunks, uint32_t n_segs, mbpe_device_corpus *out, void *stream) {
-    if (!p || !out || (n_segs && (!d_texts || !d_offs || !seg_chunks))) return set_error(MBPE_E_INVALID, "null argument");
+extern "C" int mbpe_pretok_dedup_segments(mbpe_pretok *p, const uint8_t *const *d_texts, const uint64_t *seg_bytes,
+                                          const uint32_t *const *d_offs, const uint64_t *seg_chunks, uint32_t n_segs,
+                                          mbpe_device_corpus *out, void *stream) {
+    if (!p || !out || (n_segs && (!d_texts || !seg_bytes || !d_offs || !seg_chunks))) return set_error(MBPE_E_INVALID, "null argument");
     if (n_segs > (uint32_t)DD_MAX_SEGS) return set_error(MBPE_E_INVALID, "too many text segments");
     uint64_t n_chunks = 0;
     for (uint32_t k = 0; k < n_segs; k++) n_chunks += seg_chunks[k];
@@ -584,7 +644,11 @@ extern "C" int mbpe_pretok_dedup_segments(mbpe_pretok *p, const uint8_t *const *
         MB_CUDA(cudaMemsetAsync(d_counts, 0, slots * 4, st));
         MB_CUDA(cudaMemsetAsync(p->d_small, 0, 16, st));
         a = DedupArgs{};
-        for (uint32_t k = 0, c0 = 0; k < n_segs; c0 += (uint32_t)seg_chunks[k], k++) a.seg[k] = DdSeg{d_texts[k], d_offs[k], c0};
+        a.fast = 1;
+        for (uint32_t k = 0, c0 = 0; k < n_segs; c0 += (uint32_t)seg_chunks[k], k++) {
+            a.seg[k] = DdSeg{d_texts[k], d_offs[k], c0, seg_bytes[k]};
+            if (((uintptr_t)d_texts[k] & 3) != 0) a.fast = 0;
+        }
         a.n_segs = n_segs;
         a.n_chunks = n_chunks;
         a.words = d_words;
@@ -655,7 +719,7 @@ extern "C" int mbpe_pretok_dedup_segments(mbpe_pretok *p, const uint8_t *const *
 extern "C" int mbpe_pretok_dedup_device(mbpe_pretok *p, const uint8_t *d_text, uint64_t len, const uint32_t *d_off,
                                         uint64_t n_chunks, mbpe_device_corpus *out, void *stream) {
     if (!d_off || (len && !d_text)) return set_error(MBPE_E_INVALID, "null argument");
-    return mbpe_pretok_dedup_segments(p, &d_text, &d_off, &n_chunks, 1, out, stream);
+    return mbpe_pretok_dedup_segments(p, &d_text, &len, &d_off, &n_chunks, 1, out, stream);
 }
 
 extern "C" int mbpe_device_corpus_download(const mbpe_device_corpus *c, uint32_t *tokens, uint64_t *off, uint32_t *weight) {
@@ -726,7 +790,8 @@ extern "C" int mbpe_pretok_corpus(mbpe_pretok *p, const uint8_t *text, uint64_t 
     if (n_segs > (uint32_t)DD_MAX_SEGS) return set_error(MBPE_E_UNSUPPORTED, "text too large for the resident pre-tokeniser");
     std::vector<uint8_t *> d_text(n_segs, nullptr);
     std::vector<uint32_t *> d_off(n_segs, nullptr);
-    std::vector<uint64_t> n_chunks(n_segs, 0);
+    std::vector<uint64_t> n_chunks(n_segs, 0), seg_len(n_segs, 0);
+    for (uint32_t k = 0; k < n_segs; k++) seg_len[k] = bounds[k + 1] - bounds[k];
     auto cleanup = [&]() {
         if (n_segs == 1) return;
         for (auto q : d_text) cudaFree(q);
@@ -755,7 +820,7 @@ extern "C" int mbpe_pretok_corpus(mbpe_pretok *p, const uint8_t *text, uint64_t 
     }
     double t0 = pt_now();
     if (rc == MBPE_OK)
-        rc = mbpe_pretok_dedup_segments(p, d_text.data(), d_off.data(), n_chunks.data(), n_segs, out, nullptr);
+        rc = mbpe_pretok_dedup_segments(p, d_text.data(), seg_len.data(), d_off.data(), n_chunks.data(), n_segs, out, nullptr);
     const double t_dedup = pt_now() - t0;
     t0 = pt_now();
     cleanup();
