@@ -37,11 +37,13 @@ struct DevText {
 constexpr int PM_THREADS = 256;
 constexpr uint32_t PT_WINDOW = 32; // bytes per thread = one bitmap word
 
+// windows [w_first, ceil(len / 32)) of the subject text[0, len)
 __global__ void __launch_bounds__(PM_THREADS) k_pretok_mark(const uint8_t *text, uint64_t len, const uint8_t *table,
-                                                             uint32_t *bitmap, uint32_t *err, uint64_t max_crawl, uint32_t kind) {
+                                                             uint32_t *bitmap, uint32_t *err, uint64_t max_crawl, uint32_t kind,
+                                                             uint64_t w_first) {
     const uint64_t n_win = (len + PT_WINDOW - 1) / PT_WINDOW;
     PretokIn<DevText> in{DevText{text}, len, table, err, kind};
-    for (uint64_t w = blockIdx.x * (uint64_t)PM_THREADS + threadIdx.x; w < n_win; w += (uint64_t)gridDim.x * PM_THREADS) {
+    for (uint64_t w = w_first + blockIdx.x * (uint64_t)PM_THREADS + threadIdx.x; w < n_win; w += (uint64_t)gridDim.x * PM_THREADS) {
         uint64_t cur = ~0ull;
         uint32_t bits = 0;
         pretok_window(in, w * PT_WINDOW, (w + 1) * PT_WINDOW, max_crawl, [&](uint64_t p) {
@@ -505,34 +507,33 @@ int bits_compact(mbpe_pretok *p, const uint32_t *d_bitmap, uint64_t n_words, uin
 }
 } // namespace mbpe
 
-// d_off_out: u32[off_cap]; on success holds n_chunks + 1 offsets (the last one = len)
-extern "C" int mbpe_pretok_split_device(mbpe_pretok *p, const uint8_t *d_text, uint64_t len, uint32_t *d_off_out,
-                                        uint64_t off_cap, uint64_t *n_chunks, void *stream) {
-    if (!p || !n_chunks || !d_off_out || (len && !d_text)) return set_error(MBPE_E_INVALID, "null argument");
-    if (len >= (1ull << 32) - 64) return set_error(MBPE_E_INVALID, "a device batch must be < 4 GiB of text");
-    int rc = use_device(p->device);
-    if (rc) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
-    *n_chunks = 0;
-    if (off_cap < 1) return set_error(MBPE_E_CAPACITY, "offset buffer too small");
-    if (len == 0) {
-        MB_CUDA(cudaMemsetAsync(d_off_out, 0, 4, st));
-        MB_CUDA(cudaStreamSynchronize(st));
-        return MBPE_OK;
-    }
-    const uint64_t n_words = (len + 31) / 32;
-    if (n_words > p->bitmap_words) {
+namespace mbpe {
+static int split_begin(mbpe_pretok *p, uint64_t len, uint64_t *n_words, cudaStream_t st) {
+    *n_words = (len + 31) / 32;
+    if (*n_words > p->bitmap_words) {
         cudaFree(p->d_bitmap);
-        p->bitmap_words = n_words + n_words / 8 + 1024;
+        p->bitmap_words = *n_words + *n_words / 8 + 1024;
         MB_CUDA(cudaMalloc(&p->d_bitmap, p->bitmap_words * 4));
     }
-    MB_CUDA(cudaMemsetAsync(p->d_bitmap, 0, n_words * 4, st));
+    MB_CUDA(cudaMemsetAsync(p->d_bitmap, 0, *n_words * 4, st));
     MB_CUDA(cudaMemsetAsync(p->d_small, 0, 16, st));
-    const unsigned grid = (unsigned)std::min<uint64_t>((n_words + PM_THREADS - 1) / PM_THREADS, (uint64_t)p->sms * 32);
-    k_pretok_mark<<<grid, PM_THREADS, 0, st>>>(d_text, len, p->d_table, p->d_bitmap, p->d_small, p->max_crawl, p->kind);
+    return MBPE_OK;
+}
+// marks the chunk starts of windows [w_first, ...) of the subject d_text[0, subject_len)
+static int split_mark(mbpe_pretok *p, const uint8_t *d_text, uint64_t subject_len, uint64_t w_first, cudaStream_t st) {
+    const uint64_t n_win = (subject_len + 31) / 32 - w_first;
+    const unsigned grid = (unsigned)std::min<uint64_t>((n_win + PM_THREADS - 1) / PM_THREADS, (uint64_t)p->sms * 32);
+    if (grid == 0) return MBPE_OK;
+    k_pretok_mark<<<grid, PM_THREADS, 0, st>>>(d_text, subject_len, p->d_table, p->d_bitmap, p->d_small, p->max_crawl, p->kind, w_first);
     p->launches++;
     MB_CUDA(cudaGetLastError());
-    if ((rc = bits_compact(p, p->d_bitmap, n_words, d_off_out, off_cap - 1, st))) return rc;
+    return MBPE_OK;
+}
+// bitmap -> offsets, error flags, end offset
+static int split_finish(mbpe_pretok *p, uint64_t len, uint64_t n_words, uint32_t *d_off_out, uint64_t off_cap, uint64_t *n_chunks,
+                        cudaStream_t st) {
+    int rc = bits_compact(p, p->d_bitmap, n_words, d_off_out, off_cap - 1, st);
+    if (rc) return rc;
     uint32_t small[4];
     unsigned long long count = 0;
     MB_CUDA(cudaMemcpyAsync(small, p->d_small, 16, cudaMemcpyDeviceToHost, st));
@@ -550,6 +551,28 @@ extern "C" int mbpe_pretok_split_device(mbpe_pretok *p, const uint8_t *d_text, u
     MB_CUDA(cudaStreamSynchronize(st));
     *n_chunks = count;
     return MBPE_OK;
+}
+} // namespace mbpe
+
+// d_off_out: u32[off_cap]; on success holds n_chunks + 1 offsets (the last one = len)
+extern "C" int mbpe_pretok_split_device(mbpe_pretok *p, const uint8_t *d_text, uint64_t len, uint32_t *d_off_out,
+                                        uint64_t off_cap, uint64_t *n_chunks, void *stream) {
+    if (!p || !n_chunks || !d_off_out || (len && !d_text)) return set_error(MBPE_E_INVALID, "null argument");
+    if (len >= (1ull << 32) - 64) return set_error(MBPE_E_INVALID, "a device batch must be < 4 GiB of text");
+    int rc = use_device(p->device);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    *n_chunks = 0;
+    if (off_cap < 1) return set_error(MBPE_E_CAPACITY, "offset buffer too small");
+    if (len == 0) {
+        MB_CUDA(cudaMemsetAsync(d_off_out, 0, 4, st));
+        MB_CUDA(cudaStreamSynchronize(st));
+        return MBPE_OK;
+    }
+    uint64_t n_words = 0;
+    if ((rc = split_begin(p, len, &n_words, st))) return rc;
+    if ((rc = split_mark(p, d_text, len, 0, st))) return rc;
+    return split_finish(p, len, n_words, d_off_out, off_cap, n_chunks, st);
 }
 
 // host text in, host offsets out: the GPU counterpart of mbpe_split for the GPT-4 pattern
@@ -778,6 +801,39 @@ static int ensure_segment_buffers(mbpe_pretok *p, uint64_t max_seg) {
     return MBPE_OK;
 }
 
+// One segment of host text: its pieces (128 MiB, cut at matcher cuts) are uploaded on one stream while the pieces
+// already on the device are marked on another -- a piece's subject ends at its own end, which is a cut, so the marks
+// are those of the whole segment; then one compaction of the bitmap.
+static int ensure_pipe(mbpe_pretok *p, uint64_t max_seg);
+static int upload_and_split(mbpe_pretok *p, const uint8_t *text, uint64_t len, uint8_t *d_text, uint32_t *d_off, uint64_t off_cap,
+                            uint64_t *n_chunks) {
+    *n_chunks = 0;
+    std::vector<uint64_t> pb;
+    const uint64_t piece = 128ull << 20;
+    if (len < 2 * piece || ensure_pipe(p, 0) != MBPE_OK || !plan_segments(p, text, len, piece, pb)) {
+        cudaError_t ce = cudaMemcpy(d_text, text, len, cudaMemcpyHostToDevice);
+        if (ce != cudaSuccess) return cuda_fail(ce, "H2D text", __FILE__, __LINE__);
+        return mbpe_pretok_split_device(p, d_text, len, d_off, off_cap, n_chunks, nullptr);
+    }
+    uint64_t n_words = 0;
+    int rc = split_begin(p, len, &n_words, p->st_c);
+    for (size_t k = 0; k + 1 < pb.size() && rc == MBPE_OK; k++) {
+        const uint64_t b = pb[k], e = pb[k + 1];
+        cudaError_t ce = cudaMemcpyAsync(d_text + b, text + b, e - b, cudaMemcpyHostToDevice, p->st_in);
+        if (ce == cudaSuccess) ce = cudaEventRecord(p->ev_in[k & 1], p->st_in);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(p->st_c, p->ev_in[k & 1], 0);
+        if (ce != cudaSuccess) {
+            rc = cuda_fail(ce, "H2D text", __FILE__, __LINE__);
+            break;
+        }
+        rc = split_mark(p, d_text, e, b / 32, p->st_c); // windows from the one that holds b; the subject ends at e
+    }
+    if (rc == MBPE_OK) rc = split_finish(p, len, n_words, d_off, off_cap, n_chunks, p->st_c);
+    cudaStreamSynchronize(p->st_in);
+    cudaStreamSynchronize(p->st_c);
+    return rc;
+}
+
 // text in host memory -> unique chunks resident on the device (split + dedup), the front end of Tokenizer::train
 extern "C" int mbpe_pretok_corpus(mbpe_pretok *p, const uint8_t *text, uint64_t len, mbpe_device_corpus *out) {
     if (!p || !out || (len && !text)) return set_error(MBPE_E_INVALID, "null argument");
@@ -812,10 +868,7 @@ extern "C" int mbpe_pretok_corpus(mbpe_pretok *p, const uint8_t *text, uint64_t 
             break;
         }
         double t0 = pt_now();
-        cudaError_t ce = cudaMemcpy(d_text[k], text + b, n, cudaMemcpyHostToDevice);
-        t_h2d += pt_now() - t0, t0 = pt_now();
-        rc = ce == cudaSuccess ? mbpe_pretok_split_device(p, d_text[k], n, d_off[k], n + 2, &n_chunks[k], nullptr)
-                               : cuda_fail(ce, "H2D text", __FILE__, __LINE__);
+        rc = upload_and_split(p, text + b, n, d_text[k], d_off[k], n + 2, &n_chunks[k]);
         t_split += pt_now() - t0;
     }
     double t0 = pt_now();
@@ -825,8 +878,8 @@ extern "C" int mbpe_pretok_corpus(mbpe_pretok *p, const uint8_t *text, uint64_t 
     t0 = pt_now();
     cleanup();
     if (pt_debug())
-        fprintf(stderr, "[mbpe] pretok_corpus: %.1f MB in %u segment(s): H2D %.1f ms, split %.1f ms, dedup %.1f ms, free %.1f ms, total %.1f ms\n",
-                len / 1e6, n_segs, t_h2d * 1e3, t_split * 1e3, t_dedup * 1e3, (pt_now() - t0) * 1e3, (pt_now() - t_start) * 1e3);
+        fprintf(stderr, "[mbpe] pretok_corpus: %.1f MB in %u segment(s): upload + split (overlapped) %.1f ms, dedup %.1f ms, free %.1f ms, total %.1f ms\n",
+                len / 1e6, n_segs, (t_h2d + t_split) * 1e3, t_dedup * 1e3, (pt_now() - t0) * 1e3, (pt_now() - t_start) * 1e3);
     return rc;
 }
 
