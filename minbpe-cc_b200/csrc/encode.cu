@@ -12,11 +12,14 @@
 // {a:21 | b:21 | id:21} (vocab <= 2^21), 2-4x over-provisioned, read through the read-only path: 32k merges =
 // 512 KB, resident in L2 and mostly in L1.
 //
-// k_encode_tiles: one thread per chunk (chunks <= ENC_SHORT_MAX bytes), tokens in a per-thread buffer; the flat
+// k_encode_tiles: tiles of 1024 chunks staged in shared memory; a chunk's ids come from the chunk cache (chunk bytes
+// -> ids, learned between sub-batches) or, on a miss, from the multi-pass scan itself (one warp per chunk); the flat
 // output position comes from a block scan + decoupled look-back over tiles, so the stream is produced in ONE
 // pass: every text byte and boundary is read once, every id written once (SURVEY 8(d) B_enc).
 // Chunks longer than ENC_SHORT_MAX (encoder "basic": the whole text is one chunk) are encoded first by
 // k_encode_long into a scratch stream and spliced in by k_encode_tiles.
+// k_decode_tiles: ids -> bytes gather through a packed (length + bytes) vocabulary word, same look-back.
+// mbpe_decode_file: .enc file -> text file in blocks (reader thread, device, writer thread).
 #include <algorithm>
 #include <condition_variable>
 #include <mutex>

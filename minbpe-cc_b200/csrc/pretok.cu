@@ -1,4 +1,4 @@
-// pretok.cu -- GPU pre-tokeniser for the GPT-4 split pattern and GPU chunk dedup: the two host stages
+// pretok.cu -- GPU pre-tokeniser for the GPT-4 / GPT-2 split patterns and GPU chunk dedup: the two host stages
 // in front of the merge loop (Tokenizer.h:500-544 regex split; chunk -> count) moved next to it, so that
 // text -> chunks -> unique chunks -> merge loop never leaves HBM.
 //
@@ -14,6 +14,9 @@
 //                     bytes widened to u32 -- the trainer's input layout (train_cuda.cu), written in place on the GPU.
 // Texts the matcher cannot take (malformed UTF-8, or a stretch without letters/blanks longer than the crawl limit)
 // come back as MBPE_E_UNSUPPORTED and the caller uses the PCRE2 path.
+// Host-facing entry points built on these: mbpe_pretok_corpus (text -> unique-chunk corpus on the device, upload
+// overlapped with marking), mbpe_encode_text (text -> ids, three-stream pipeline over 64 MiB segments) and
+// mbpe_encode_file (file -> .enc file in blocks with a reader and a writer thread).
 #include <string.h>
 
 #include <algorithm>

@@ -6,7 +6,8 @@
 //                           distinct pair per CTA into the HBM pair table.
 //   k_par<Ph*> / k_one<Ph*> one barrier-separated phase of train_phases.cuh over the whole grid / one thread
 //   k_persistent            persistent_program(): one resident 1024-thread CTA runs merge steps back to back
-//                           (selection, hits, mutate, segment build) with __syncthreads() as the phase barrier
+//                           (selection, hits, mutate, segment build) with __syncthreads() as the phase barrier;
+//                           control block, step lists and a mirror of the candidate list live in shared memory
 //   k_pc_*                  PairCount seam (PairCount.h:27-47): batched upsert, block-then-grid arg-max, lookup
 #include <dlfcn.h>
 
