@@ -149,6 +149,11 @@ int mbpe_encode_device(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t n_bytes
 int mbpe_encode_reserve(mbpe_encoder *e, uint64_t n_bytes, uint64_t n_chunks);
 
 /* ids -> bytes. Call with out == NULL to size. Invalid ids are skipped (Tokenizer.h:739-742). */
+/* special tokens on the encode side: "a chunk with exactly these bytes is this one id" (Tokenizer.h:667-671), kept in
+ * the chunk cache (which is emptied first). ids[i] <-> bytes[off[i] .. off[i+1]). MBPE_E_UNSUPPORTED: cache disabled or
+ * a token longer than 31 bytes -- then special tokens have to be resolved on the host as before. */
+int mbpe_encoder_seed_special_chunks(mbpe_encoder *e, const uint32_t *ids, const uint8_t *bytes, const uint64_t *off,
+                                     uint32_t n);
 int mbpe_decode(mbpe_encoder *e, const uint32_t *ids, uint64_t n_ids, uint8_t *out, uint64_t out_cap,
                 uint64_t *n_out);
 /* resident ids (16-byte aligned) -> resident bytes, one pass, on `stream`. *d_n_out (device) = decoded size; bytes past
@@ -250,6 +255,12 @@ void mbpe_pretok_destroy(mbpe_pretok *p);
  * mbpe_encode_device takes. off_cap counts u32 entries; len + 2 always suffices. */
 int mbpe_pretok_split_device(mbpe_pretok *p, const uint8_t *d_text, uint64_t len, uint32_t *d_off_out, uint64_t off_cap,
                              uint64_t *n_chunks, void *stream);
+/* the same for a text with special tokens (Tokenizer.h:605-650): d_sp_begin / d_sp_end = the occurrences in text
+ * order (device arrays of n_sp offsets into d_text); every ordinary part in between is split as a subject of its own,
+ * every occurrence is one chunk */
+int mbpe_pretok_split_device_parts(mbpe_pretok *p, const uint8_t *d_text, uint64_t len, const uint32_t *d_sp_begin,
+                                   const uint32_t *d_sp_end, uint32_t n_sp, uint32_t *d_off_out, uint64_t off_cap,
+                                   uint64_t *n_chunks, void *stream);
 /* host text -> host offsets off_out[0 .. n_chunks] (chunk c = [off[c], off[c+1])): GPU twin of mbpe_split */
 int mbpe_pretok_split(mbpe_pretok *p, const uint8_t *text, uint64_t len, uint64_t *off_out, uint64_t off_cap,
                       uint64_t *n_chunks);
@@ -276,6 +287,10 @@ void mbpe_device_corpus_free(mbpe_device_corpus *c);
  * without special tokens, :653-717). out_cap counts ids; len always suffices. */
 int mbpe_encode_text(mbpe_encoder *enc, mbpe_pretok *p, const uint8_t *text, uint64_t len, uint32_t *out,
                      uint64_t out_cap, uint64_t *n_out);
+/* ... with special tokens: sp_begin / sp_end = their occurrences in text order (host arrays, as mbpe_special_split
+ * reports them); needs mbpe_encoder_seed_special_chunks on the encoder */
+int mbpe_encode_text_special(mbpe_encoder *enc, mbpe_pretok *p, const uint8_t *text, uint64_t len, const uint64_t *sp_begin,
+                             const uint64_t *sp_end, uint64_t n_sp, uint32_t *out, uint64_t out_cap, uint64_t *n_out);
 /* file -> .enc file (raw little-endian u32 ids, examples/minbpe-cc.cpp:58-69) in blocks: reader thread, device
  * pipeline, writer thread; memory use independent of the file size. MBPE_E_UNSUPPORTED if no block
  * boundary can be found (then read the file and call mbpe_encode_text / mbpe_encode). */

@@ -25,14 +25,15 @@ EXPORTS = [
     "mbpe_trainer_create", "mbpe_trainer_run", "mbpe_trainer_destroy", "mbpe_train",
     "mbpe_comm_unique_id", "mbpe_comm_create", "mbpe_comm_destroy", "mbpe_train_sharded",
     "mbpe_encoder_create", "mbpe_encoder_destroy", "mbpe_encoder_set_specials", "mbpe_encode", "mbpe_encode_device",
-    "mbpe_encode_reserve", "mbpe_decode", "mbpe_decode_device",
+    "mbpe_encode_reserve", "mbpe_decode", "mbpe_decode_device", "mbpe_encoder_seed_special_chunks",
     "mbpe_gpt2_split_pattern", "mbpe_gpt4_split_pattern", "mbpe_tokenizer_create", "mbpe_tokenizer_destroy",
     "mbpe_tokenizer_set_special_tokens", "mbpe_tokenizer_train", "mbpe_tokenizer_save", "mbpe_tokenizer_load",
     "mbpe_tokenizer_encode", "mbpe_tokenizer_decode", "mbpe_tokenizer_get_merges",
     "mbpe_tokenizer_last_train_stats", "mbpe_tokenizer_last_split_on_gpu", "mbpe_tokenizer_encode_file", "mbpe_encode_file", "mbpe_tokenizer_decode_file", "mbpe_decode_file", "mbpe_tokenizer_set_engine", "mbpe_tokenizer_set_threads",
     "mbpe_split", "mbpe_special_split", "mbpe_pretok_class_table", "mbpe_dedup",
     "mbpe_pretok_create", "mbpe_pretok_select", "mbpe_pretok_destroy", "mbpe_pretok_split_device", "mbpe_pretok_split",
-    "mbpe_pretok_dedup_device", "mbpe_pretok_dedup_segments", "mbpe_pretok_corpus", "mbpe_encode_text", "mbpe_device_corpus_download", "mbpe_device_corpus_free",
+    "mbpe_pretok_dedup_device", "mbpe_pretok_dedup_segments", "mbpe_pretok_corpus", "mbpe_encode_text",
+    "mbpe_encode_text_special", "mbpe_pretok_split_device_parts", "mbpe_device_corpus_download", "mbpe_device_corpus_free",
     "mbpe_trainer_create_device", "mbpe_split_dedup", "mbpe_plan_shards", "mbpe_write_model", "mbpe_synth_corpus",
 ]
 

@@ -795,6 +795,7 @@ struct mbpe_encoder {
     uint64_t sub_batch_chunks = 0; // fixed sub-batch size (MBPE_ENCODE_SUBBATCH), 0 = geometric schedule
     uint64_t chunks_seen = 0;      // chunks encoded so far with this handle: how warm the cache is
     int cfg = 0; // kernel shape, see enc_configs
+    bool specials_seeded = false; // mbpe_encoder_seed_special_chunks succeeded
     size_t l2_window_max = 0, l2_persist_bytes = 0;
 };
 
@@ -951,6 +952,47 @@ extern "C" int mbpe_encoder_set_specials(mbpe_encoder *e, const uint32_t *ids, c
     MB_CUDA(cudaMemcpy(e->d_sp_ids, sid.data(), sid.size() * 4, cudaMemcpyHostToDevice));
     MB_CUDA(cudaMemcpy(e->d_sp_off, soff.data(), soff.size() * 4, cudaMemcpyHostToDevice));
     MB_CUDA(cudaMemcpy(e->d_sp_bytes, sb.data(), sb.size(), cudaMemcpyHostToDevice));
+    return MBPE_OK;
+}
+
+// Special tokens on the encode side (Tokenizer.h:605-650, :667-671): a special token is a chunk of its own that becomes
+// one ready-made id. The device front end marks those chunks (mbpe_pretok_split_device_parts); here their bytes are put
+// into the chunk cache as "these bytes -> this id", so the tile kernel needs no special case. An ordinary chunk can never
+// carry the bytes of a special token (the splitter would have cut it out). The cache is emptied first: it may have
+// learned those bytes as ordinary text before. MBPE_E_UNSUPPORTED: no cache, or a token longer than the cache's keys.
+extern "C" int mbpe_encoder_seed_special_chunks(mbpe_encoder *e, const uint32_t *ids, const uint8_t *bytes, const uint64_t *off,
+                                                uint32_t n) {
+    if (!e || (n && (!ids || !bytes || !off))) return set_error(MBPE_E_INVALID, "null argument");
+    int rc = use_device(e->device);
+    if (rc) return rc;
+    e->specials_seeded = false;
+    if (!e->d_cache) return set_error(MBPE_E_UNSUPPORTED, "the chunk cache is disabled");
+    std::vector<CacheLogEntry> log(n);
+    for (uint32_t i = 0; i < n; i++) {
+        const uint64_t len = off[i + 1] - off[i];
+        if (len == 0 || len > CACHE_MAX_LEN) return set_error(MBPE_E_UNSUPPORTED, "special token longer than 31 bytes");
+        if (n > e->cache_log_cap) return set_error(MBPE_E_UNSUPPORTED, "too many special tokens");
+        CacheLogEntry &le = log[i];
+        memset(&le, 0, sizeof le);
+        for (uint64_t q = 0; q < len; q++) le.k[q >> 3] |= (uint64_t)bytes[off[i] + q] << ((q & 7) * 8);
+        le.k[3] |= len << 56;
+        le.n = 1;
+        le.ids[0] = ids[i];
+    }
+    MB_CUDA(cudaMemset(e->d_cache, 0, (uint64_t)e->cache_slots * sizeof(CacheSlot)));
+    MB_CUDA(cudaMemset(e->d_cache_ctr, 0, 16));
+    e->chunks_seen = 0;
+    if (n) {
+        MB_CUDA(cudaMemcpy(e->d_cache_log, log.data(), n * sizeof(CacheLogEntry), cudaMemcpyHostToDevice));
+        const uint32_t cnt = n;
+        MB_CUDA(cudaMemcpy(e->d_cache_ctr, &cnt, 4, cudaMemcpyHostToDevice));
+        ChunkCache cc{e->d_cache, e->cache_slots - 1, e->d_cache_log, e->d_cache_ctr, e->cache_log_cap, e->d_cache_ctr + 1,
+                      e->d_cache_arena, e->d_cache_ctr + 2, e->cache_arena_cap};
+        k_cache_insert<<<1, 256>>>(cc);
+        MB_CUDA(cudaGetLastError());
+        MB_CUDA(cudaDeviceSynchronize());
+    }
+    e->specials_seeded = true;
     return MBPE_OK;
 }
 

@@ -62,6 +62,28 @@ __global__ void __launch_bounds__(PM_THREADS) k_pretok_mark(const uint8_t *text,
     }
 }
 
+// the same with the text cut into independent subjects by special-token occurrences (pretok_window_parts)
+__global__ void __launch_bounds__(PM_THREADS) k_pretok_mark_parts(const uint8_t *text, uint64_t len, const uint8_t *table,
+                                                                   uint32_t *bitmap, uint32_t *err, uint64_t max_crawl, uint32_t kind,
+                                                                   const uint32_t *sp_b, const uint32_t *sp_e, uint32_t n_sp) {
+    const uint64_t n_win = (len + PT_WINDOW - 1) / PT_WINDOW;
+    PretokIn<DevText> in{DevText{text}, len, table, err, kind, 0};
+    for (uint64_t w = blockIdx.x * (uint64_t)PM_THREADS + threadIdx.x; w < n_win; w += (uint64_t)gridDim.x * PM_THREADS) {
+        uint64_t cur = ~0ull;
+        uint32_t bits = 0;
+        pretok_window_parts(in, sp_b, sp_e, n_sp, len, w * PT_WINDOW, (w + 1) * PT_WINDOW, max_crawl, [&](uint64_t p) {
+            const uint64_t wi = p >> 5;
+            if (wi != cur) {
+                if (bits) atomicOr(&bitmap[cur], bits);
+                cur = wi;
+                bits = 0;
+            }
+            bits |= 1u << (p & 31);
+        });
+        if (bits) atomicOr(&bitmap[cur], bits);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // bitmap -> positions
 // ---------------------------------------------------------------------------------------------------------
@@ -405,8 +427,8 @@ struct mbpe_pretok {
     uint32_t *d_pipe_ids[2] = {nullptr, nullptr}, *d_pipe_off = nullptr;
     uint64_t pipe_cap = 0;
     uint64_t enc_seg_bytes = 64ull << 20;
-    void *scratch[4] = {nullptr, nullptr, nullptr, nullptr}; // dedup work buffers, grow-only, kept between calls
-    uint64_t scratch_cap[4] = {0, 0, 0, 0};
+    void *scratch[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // work buffers, grow-only, kept between calls
+    uint64_t scratch_cap[6] = {0, 0, 0, 0, 0, 0}; // 0-3 dedup, 4-5 special-token occurrences of a segment
     std::vector<uint8_t> h_table;   // host copy: segment boundaries are chosen at cuts (pretok_core.cuh)
     uint64_t seg_bytes = 1ull << 30; // host text is brought over in segments of about this size
 };
@@ -575,6 +597,30 @@ extern "C" int mbpe_pretok_split_device(mbpe_pretok *p, const uint8_t *d_text, u
     uint64_t n_words = 0;
     if ((rc = split_begin(p, len, &n_words, st))) return rc;
     if ((rc = split_mark(p, d_text, len, 0, st))) return rc;
+    return split_finish(p, len, n_words, d_off_out, off_cap, n_chunks, st);
+}
+
+// The same for a text with special tokens (Tokenizer.h:605-650): d_sp_begin / d_sp_end = the occurrences of special
+// tokens in text order (device arrays, offsets into d_text). Every ordinary part is split as a subject of its own
+// and every occurrence becomes one chunk.
+extern "C" int mbpe_pretok_split_device_parts(mbpe_pretok *p, const uint8_t *d_text, uint64_t len, const uint32_t *d_sp_begin,
+                                              const uint32_t *d_sp_end, uint32_t n_sp, uint32_t *d_off_out, uint64_t off_cap,
+                                              uint64_t *n_chunks, void *stream) {
+    if (n_sp == 0) return mbpe_pretok_split_device(p, d_text, len, d_off_out, off_cap, n_chunks, stream);
+    if (!p || !n_chunks || !d_off_out || !d_text || !d_sp_begin || !d_sp_end) return set_error(MBPE_E_INVALID, "null argument");
+    if (len >= (1ull << 32) - 64) return set_error(MBPE_E_INVALID, "a device batch must be < 4 GiB of text");
+    int rc = use_device(p->device);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    *n_chunks = 0;
+    if (off_cap < 1 || len == 0) return set_error(MBPE_E_INVALID, "empty text with special occurrences");
+    uint64_t n_words = 0;
+    if ((rc = split_begin(p, len, &n_words, st))) return rc;
+    const unsigned grid = (unsigned)std::min<uint64_t>((n_words + PM_THREADS - 1) / PM_THREADS, (uint64_t)p->sms * 32);
+    k_pretok_mark_parts<<<grid, PM_THREADS, 0, st>>>(d_text, len, p->d_table, p->d_bitmap, p->d_small, p->max_crawl, p->kind,
+                                                    d_sp_begin, d_sp_end, n_sp);
+    p->launches++;
+    MB_CUDA(cudaGetLastError());
     return split_finish(p, len, n_words, d_off_out, off_cap, n_chunks, st);
 }
 
@@ -923,14 +969,55 @@ static int ensure_pipe(mbpe_pretok *p, uint64_t max_seg) {
     return MBPE_OK;
 }
 
+// Segment boundaries for a text with special-token occurrences: the last occurrence that begins in the usual range
+// (its begin ends an ordinary part, so both sides are independent), else an ordinary cut -- which cannot lie inside an
+// occurrence, because none begins in the range and occurrences are at most 31 bytes long.
+static bool plan_segments_special(const mbpe_pretok *pt, const uint8_t *text, uint64_t len, uint64_t seg_bytes, const uint64_t *sp_b,
+                                  uint32_t n_sp, std::vector<uint64_t> &bounds) {
+    bounds.assign(1, 0);
+    uint32_t err = 0;
+    PretokIn<HostText> in{HostText{text}, len, pt->h_table.data(), &err, pt->kind, 0};
+    while (len - bounds.back() > seg_bytes + seg_bytes / 4) {
+        const uint64_t lo = bounds.back() + seg_bytes / 2, hi = bounds.back() + seg_bytes;
+        uint64_t cut = 0;
+        const uint64_t *it = std::upper_bound(sp_b, sp_b + n_sp, hi); // first occurrence that begins after hi
+        if (it != sp_b && it[-1] > lo) {
+            cut = it[-1];
+        } else {
+            bool bad = false;
+            for (uint64_t q = hi; q > lo && !cut && !bad; q--) {
+                if ((text[q] & 0xC0) == 0x80) continue;
+                const PtCp prev = pt_before(in, q, bad), cur = pt_at(in, q, bad);
+                if (!bad && pt_is_cut(prev.cls, cur)) cut = q;
+            }
+        }
+        if (!cut) return false;
+        bounds.push_back(cut);
+    }
+    bounds.push_back(len);
+    return true;
+}
+
 extern "C" int mbpe_encode_text(mbpe_encoder *enc, mbpe_pretok *p, const uint8_t *text, uint64_t len, uint32_t *out,
                                 uint64_t out_cap, uint64_t *n_out) {
-    if (!enc || !p || !n_out || (len && (!text || !out))) return set_error(MBPE_E_INVALID, "null argument");
+    return mbpe_encode_text_special(enc, p, text, len, nullptr, nullptr, 0, out, out_cap, n_out);
+}
+
+// ... with special tokens: sp_begin / sp_end = the occurrences in text order (host arrays, Tokenizer.h:605-650); the
+// encoder must have been told their ids (mbpe_encoder_seed_special_chunks)
+extern "C" int mbpe_encode_text_special(mbpe_encoder *enc, mbpe_pretok *p, const uint8_t *text, uint64_t len,
+                                        const uint64_t *sp_begin, const uint64_t *sp_end, uint64_t n_sp, uint32_t *out,
+                                        uint64_t out_cap, uint64_t *n_out) {
+    if (!enc || !p || !n_out || (len && (!text || !out)) || (n_sp && (!sp_begin || !sp_end)))
+        return set_error(MBPE_E_INVALID, "null argument");
+    if (n_sp >= (1ull << 31)) return set_error(MBPE_E_INVALID, "too many special-token occurrences");
     *n_out = 0;
     int rc = use_device(p->device);
     if (rc) return rc;
     std::vector<uint64_t> bounds;
-    if (!plan_segments(p, text, len, p->enc_seg_bytes, bounds))
+    const bool planned = n_sp ? plan_segments_special(p, text, len, p->enc_seg_bytes, sp_begin, (uint32_t)n_sp, bounds)
+                              : plan_segments(p, text, len, p->enc_seg_bytes, bounds);
+    if (!planned)
         return set_error(MBPE_E_UNSUPPORTED, "no safe segment boundary found (malformed UTF-8 or no letters/blanks): use the PCRE2 path");
     const size_t n_seg = bounds.size() - 1;
     uint64_t max_seg = 0;
@@ -942,6 +1029,7 @@ extern "C" int mbpe_encode_text(mbpe_encoder *enc, mbpe_pretok *p, const uint8_t
         return ce != cudaSuccess ? ce : cudaEventRecord(p->ev_in[k & 1], p->st_in);
     };
     uint64_t produced = 0;
+    std::vector<uint32_t> sp_rel_b, sp_rel_e;
     cudaError_t ce = n_seg ? upload(0) : cudaSuccess;
     for (size_t k = 0; k < n_seg && rc == MBPE_OK && ce == cudaSuccess; k++) {
         const uint64_t n = bounds[k + 1] - bounds[k];
@@ -951,7 +1039,29 @@ extern "C" int mbpe_encode_text(mbpe_encoder *enc, mbpe_pretok *p, const uint8_t
         if (k >= 2 && (ce = cudaStreamWaitEvent(p->st_c, p->ev_out[k & 1], 0)) != cudaSuccess) break; // ids[k&1] drained
         uint64_t n_chunks = 0, n_ids = 0;
         if (n) {
-            if ((rc = mbpe_pretok_split_device(p, p->d_pipe_text[k & 1], n, p->d_pipe_off, n + 2, &n_chunks, p->st_c))) break;
+            // the special-token occurrences that lie in this segment, relative to its start
+            const uint64_t sb0 = bounds[k], sb1 = bounds[k + 1];
+            const uint64_t *o0 = n_sp ? std::lower_bound(sp_begin, sp_begin + n_sp, sb0) : nullptr;
+            const uint64_t *o1 = n_sp ? std::lower_bound(sp_begin, sp_begin + n_sp, sb1) : nullptr;
+            const uint32_t n_here = n_sp ? (uint32_t)(o1 - o0) : 0;
+            if (n_here) {
+                sp_rel_b.resize(n_here);
+                sp_rel_e.resize(n_here);
+                for (uint32_t q = 0; q < n_here; q++) {
+                    sp_rel_b[q] = (uint32_t)(o0[q] - sb0);
+                    sp_rel_e[q] = (uint32_t)(sp_end[(o0 - sp_begin) + q] - sb0);
+                }
+                uint32_t *d_b = (uint32_t *)pt_scratch(p, 4, (uint64_t)n_here * 4), *d_e = (uint32_t *)pt_scratch(p, 5, (uint64_t)n_here * 4);
+                if (!d_b || !d_e) {
+                    rc = set_error(MBPE_E_CUDA, "out of device memory");
+                    break;
+                }
+                if ((ce = cudaMemcpyAsync(d_b, sp_rel_b.data(), (uint64_t)n_here * 4, cudaMemcpyHostToDevice, p->st_c)) != cudaSuccess) break;
+                if ((ce = cudaMemcpyAsync(d_e, sp_rel_e.data(), (uint64_t)n_here * 4, cudaMemcpyHostToDevice, p->st_c)) != cudaSuccess) break;
+                if ((rc = mbpe_pretok_split_device_parts(p, p->d_pipe_text[k & 1], n, d_b, d_e, n_here, p->d_pipe_off, n + 2, &n_chunks, p->st_c))) break;
+            } else if ((rc = mbpe_pretok_split_device(p, p->d_pipe_text[k & 1], n, p->d_pipe_off, n + 2, &n_chunks, p->st_c))) {
+                break;
+            }
             if ((rc = mbpe_encode_device(enc, p->d_pipe_text[k & 1], n, p->d_pipe_off, n_chunks, p->d_pipe_ids[k & 1], n, p->d_seg_n, p->st_c))) break;
             if ((ce = cudaMemcpyAsync(&n_ids, p->d_seg_n, 8, cudaMemcpyDeviceToHost, p->st_c)) != cudaSuccess) break;
         }

@@ -45,6 +45,7 @@ struct PretokIn {
     const uint8_t *table; // PT_TABLE_BYTES
     uint32_t *err;        // or-ed PT_ERR_*
     uint32_t kind;        // PT_GPT4 or PT_GPT2
+    uint64_t begin;       // start of subject (0 unless the text is cut into independent subjects, pretok_window_parts)
 };
 
 PT_HD void pt_raise(uint32_t *err, uint32_t what) {
@@ -277,7 +278,7 @@ PT_HD uint64_t pretok_match(const PretokIn<Text> &in, uint64_t p, uint32_t *last
 template <class Text>
 PT_HD PtCp pt_before(const PretokIn<Text> &in, uint64_t p, bool &bad) {
     uint64_t q = p - 1;
-    while (q > 0 && p - q < 4 && (in.t[q] & 0xC0) == 0x80) q--;
+    while (q > in.begin && p - q < 4 && (in.t[q] & 0xC0) == 0x80) q--;
     PtCp c = pt_at(in, q, bad);
     if (q + c.n != p) bad = true;
     return c;
@@ -294,11 +295,12 @@ PT_HD bool pt_is_cut(uint32_t prev_cls, const PtCp &cur) {
 template <class Text, class Mark>
 PT_HD void pretok_window(const PretokIn<Text> &in, uint64_t w0, uint64_t w1, uint64_t max_crawl, Mark mark) {
     const uint64_t len = in.len;
-    if (w0 >= len) return;
+    if (w0 < in.begin) w0 = in.begin;
     if (w1 > len) w1 = len;
+    if (w0 >= w1) return;
     bool bad = false;
     uint64_t p = w0;
-    if (w0 > 0) {
+    if (w0 > in.begin) {
         while (p < w1 && (in.t[p] & 0xC0) == 0x80) p++; // the code point straddling w0 belongs to the window before
         if (p >= w1) return;
         uint32_t prev = pt_before(in, p, bad).cls;
@@ -328,6 +330,41 @@ PT_HD void pretok_window(const PretokIn<Text> &in, uint64_t w0, uint64_t w1, uin
         }
     }
     if (bad) pt_raise(in.err, PT_ERR_UTF8);
+}
+
+// The text cut into independent subjects by special tokens (Tokenizer.h:605-650, :664-704: every ordinary part is
+// split on its own, a special token is a chunk of its own). sp_b / sp_e: begin / end of the special occurrences in
+// text order. The thread of window [w0, w1) walks the parts that intersect its window: inside an ordinary part it is
+// pretok_window() with that part as the subject (part starts are match starts, look-aheads end at the part's end);
+// it marks the start of every special occurrence that begins in its window.
+template <class Text, class Mark>
+PT_HD void pretok_window_parts(PretokIn<Text> in, const uint32_t *sp_b, const uint32_t *sp_e, uint32_t n_sp, uint64_t total_len,
+                               uint64_t w0, uint64_t w1, uint64_t max_crawl, Mark mark) {
+    if (w1 > total_len) w1 = total_len;
+    uint32_t lo = 0, hi = n_sp; // first special occurrence that ends after w0
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (sp_e[mid] > w0)
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    uint32_t i = lo;
+    uint64_t pos = w0;
+    while (pos < w1) {
+        const uint64_t pb = i ? sp_e[i - 1] : 0, pe = i < n_sp ? sp_b[i] : total_len; // the ordinary part before special i
+        if (pos < pe) {
+            in.begin = pb;
+            in.len = pe;
+            pretok_window(in, pos, w1, max_crawl, mark);
+            if (pe >= w1) return;
+            pos = pe;
+        }
+        if (i >= n_sp) return;
+        if (sp_b[i] >= w0) mark(sp_b[i]);
+        pos = sp_e[i];
+        i++;
+    }
 }
 
 } // namespace mbpe

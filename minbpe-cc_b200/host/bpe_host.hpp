@@ -118,6 +118,8 @@ class Tokenizer {
   private:
     std::vector<std::string> split_on_special(std::string_view text); // :605-650
     int ensure_encoder();
+    int encode_on_device(std::string_view text, Token *out, uint64_t cap, uint64_t *n_out);
+    int encode_host(std::string_view text, bool verbose, std::vector<Token> &out);
     bool use_gpu_split(size_t n_bytes);
     void rebuild_vocab();
 
@@ -130,6 +132,7 @@ class Tokenizer {
     mbpe_encoder *encoder_ = nullptr;
     mbpe_pretok *pretok_ = nullptr; // device matcher of the GPT-4 pattern, created on first use
     bool pretok_failed_ = false;
+    bool specials_on_device_ = false; // the encoder knows the special tokens as ready-made chunks
     bool encoder_stale_ = true;
     int device_ = 0, engine_ = MBPE_ENGINE_PERSISTENT, n_threads_ = 0;
     std::string error_;

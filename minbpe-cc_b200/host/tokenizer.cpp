@@ -244,20 +244,37 @@ int Tokenizer::ensure_encoder() {
 
 // Tokenizer::encode straight into a caller buffer: for a text without special tokens under the GPT-4 pattern the ids
 // come down from the device into `out` with no intermediate copy; everything else goes through encode() above.
+// text up, ids down with split and merge scan both on the device (built-in patterns; special tokens if the encoder
+// knows them as ready-made chunks). MBPE_E_UNSUPPORTED: not applicable to this tokenizer / text -- use the host path.
+int Tokenizer::encode_on_device(std::string_view text, Token *out, uint64_t cap, uint64_t *n_out) {
+    if (!(special_tokens_.empty() || specials_on_device_) || !use_gpu_split(text.size())) return MBPE_E_UNSUPPORTED;
+    int rc;
+    if (special_tokens_.empty()) {
+        rc = mbpe_encode_text(encoder_, pretok_, reinterpret_cast<const uint8_t *>(text.data()), text.size(), out, cap, n_out);
+    } else { // the occurrences of special tokens are found here (one sweep per token); everything else on the device
+        std::vector<uint64_t> sb, se;
+        for (const auto &part : split_special_spans(text, special_tokens_))
+            if (part.id >= 0) {
+                sb.push_back(part.start);
+                se.push_back(part.end);
+            }
+        rc = mbpe_encode_text_special(encoder_, pretok_, reinterpret_cast<const uint8_t *>(text.data()), text.size(), sb.data(),
+                                      se.data(), sb.size(), out, cap, n_out);
+    }
+    if (rc != MBPE_OK && rc != MBPE_E_UNSUPPORTED) error_ = mbpe_last_error();
+    return rc;
+}
+
 int Tokenizer::encode_into(std::string_view text, Token *out, uint64_t cap, uint64_t *n_out) {
     *n_out = 0;
     int rc = ensure_encoder();
     if (rc) return rc;
-    if (out && special_tokens_.empty() && use_gpu_split(text.size())) {
-        rc = mbpe_encode_text(encoder_, pretok_, reinterpret_cast<const uint8_t *>(text.data()), text.size(), out, cap, n_out);
-        if (rc == MBPE_OK) return rc;
-        if (rc != MBPE_E_UNSUPPORTED) {
-            error_ = mbpe_last_error();
-            return rc;
-        }
+    if (out) {
+        rc = encode_on_device(text, out, cap, n_out);
+        if (rc != MBPE_E_UNSUPPORTED) return rc;
     }
     std::vector<Token> ids;
-    if ((rc = encode(text, false, ids))) return rc;
+    if ((rc = encode_host(text, false, ids))) return rc;
     *n_out = ids.size();
     if (!out) return MBPE_OK;
     if (ids.size() > cap) {
@@ -283,26 +300,30 @@ int Tokenizer::encode(std::string_view text, bool verbose, std::vector<Token> &o
     out.clear();
     int rc = ensure_encoder();
     if (rc) return rc;
-    std::vector<std::string> parts;
-    bool single = special_tokens_.empty();
-    if (!single) parts = split_on_special(text);
-    const size_t n_parts = single ? 1 : parts.size();
-    if (verbose) std::cout << "Splitting input text into " << n_parts << " parts\n";
-    if (single && use_gpu_split(text.size())) { // text up, ids down: split and merge scan both on the device
+    if (!verbose) { // (the verbose run reports the parts of the host path)
         std::vector<Token> ids(std::max<size_t>(text.size(), 1));
         uint64_t n_ids = 0;
-        rc = mbpe_encode_text(encoder_, pretok_, reinterpret_cast<const uint8_t *>(text.data()), text.size(), ids.data(),
-                              ids.size(), &n_ids);
+        rc = encode_on_device(text, ids.data(), ids.size(), &n_ids);
         if (rc == MBPE_OK) {
             ids.resize(n_ids);
             out.swap(ids);
             return MBPE_OK;
         }
-        if (rc != MBPE_E_UNSUPPORTED) {
-            error_ = mbpe_last_error();
-            return rc;
-        }
+        if (rc != MBPE_E_UNSUPPORTED) return rc;
     }
+    return encode_host(text, verbose, out);
+}
+
+// the general path: special tokens and the regex on the host (any pattern), the merge scan on the device
+int Tokenizer::encode_host(std::string_view text, bool verbose, std::vector<Token> &out) {
+    out.clear();
+    int rc = ensure_encoder();
+    if (rc) return rc;
+    std::vector<std::string> parts;
+    bool single = special_tokens_.empty();
+    if (!single) parts = split_on_special(text);
+    const size_t n_parts = single ? 1 : parts.size();
+    if (verbose) std::cout << "Splitting input text into " << n_parts << " parts\n";
 
     // chunk list over one byte arena; ready-made ids (special markers) are spliced in afterwards
     std::vector<uint8_t> arena_copy;

@@ -35,3 +35,17 @@ extern "C" uint32_t emu_pretok(const uint8_t *text, uint64_t len, const uint8_t 
 extern "C" uint32_t emu_pretok_sequential(const uint8_t *text, uint64_t len, const uint8_t *table, uint8_t *marks) {
     return emu_pretok(text, len, table, len ? len : 1, ~0ull, 0, marks);
 }
+
+// the same with the text cut into independent subjects by special-token occurrences [sp_b[i], sp_e[i])
+extern "C" uint32_t emu_pretok_parts(const uint8_t *text, uint64_t len, const uint8_t *table, const uint32_t *sp_b,
+                                     const uint32_t *sp_e, uint32_t n_sp, uint64_t window, int order, uint8_t *marks) {
+    uint32_t err = 0;
+    memset(marks, 0, len);
+    PretokIn<HostText> in{HostText{text}, len, table, &err, g_kind, 0};
+    const uint64_t n_win = (len + window - 1) / window;
+    for (uint64_t k = 0; k < n_win; k++) {
+        const uint64_t w = order ? n_win - 1 - k : k;
+        pretok_window_parts(in, sp_b, sp_e, n_sp, len, w * window, (w + 1) * window, ~0ull, [&](uint64_t p) { marks[p] = 1; });
+    }
+    return err;
+}

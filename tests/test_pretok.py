@@ -109,6 +109,47 @@ def test_gpt2_pattern_fuzz_and_fixture(emu, seed, pcre2_starts):
         assert err == 0 and np.array_equal(got, pcre2_starts(text, "gpt2"))
 
 
+def _expected_starts_with_specials(pkg, contents: bytes, text: bytes):
+    """chunk starts the reference produces: special tokens cut out (Tokenizer.h:605-650), every ordinary part split on
+    its own (:664-704), each special token one chunk"""
+    starts, sp = [], []
+    for s0, e0, sid in pkg.special_split(contents, text):
+        if sid >= 0:
+            starts.append(s0)
+            sp.append((s0, e0))
+        elif e0 > s0:
+            ps, _ = pkg.split(pkg.patterns()["gpt4"], text[s0:e0], 1)
+            starts.extend(int(x) + s0 for x in ps)
+    return np.asarray(sorted(starts), np.uint64), sp
+
+
+def test_subjects_cut_by_special_tokens(pkg, emu):
+    L = C.CDLL(EMU_LIB)
+    L.emu_pretok_parts.restype = C.c_uint32
+    L.emu_pretok_kind(0)
+    table = pkg.pretok_class_table()
+    specials = [(b"<|endoftext|>", 100257), (b"<|x|>", 100258), (b"ab", 7)]
+    contents = b"".join(t + b" " + str(i).encode() + b"\n" for t, i in specials)
+    pieces = [t for t, _ in specials] * 2 + [b"hello", b" world", b"  ", b"\n", b" \n ", b"a", b"b", b"'s", b"123", b"!!", b"<|",
+                                             b"|>", " é".encode(), "中文".encode(), b" "]
+    rng = np.random.default_rng(31)
+    P = lambda a, ty: a.ctypes.data_as(C.POINTER(ty))
+    for it in range(400):
+        text = b"".join(pieces[k] for k in rng.integers(0, len(pieces), int(rng.integers(0, 40))))
+        if not text:
+            continue
+        want, sp = _expected_starts_with_specials(pkg, contents, text)
+        sb = np.asarray([a for a, _ in sp] or [0], np.uint32)
+        se = np.asarray([b for _, b in sp] or [0], np.uint32)
+        buf = np.frombuffer(text, np.uint8)
+        for window in (int(rng.integers(1, 20)), 32):
+            marks = np.zeros(len(text), np.uint8)
+            err = L.emu_pretok_parts(P(buf, C.c_uint8), C.c_uint64(len(text)), P(table, C.c_uint8), P(sb, C.c_uint32),
+                                     P(se, C.c_uint32), C.c_uint32(len(sp)), C.c_uint64(window), it & 1, P(marks, C.c_uint8))
+            got = np.flatnonzero(marks).astype(np.uint64)
+            assert err == 0 and np.array_equal(got, want), (text, window, got.tolist(), want.tolist(), sp)
+
+
 def test_fuzz_class_runs(emu, pcre2_starts):
     """long runs of one class (digits, symbols, blanks, newlines) across many windows"""
     rng = np.random.default_rng(7)
@@ -335,3 +376,32 @@ def test_cli_streams_big_inputs_and_matches_whole_file_path(pkg, tmp_path):
     r = subprocess.run([cli, "--decode", "-i", str(tmp_path / "stream.enc"), "-m", str(model), "-o", str(back)],
                        capture_output=True, text=True)
     assert r.returncode == 0 and back.read_bytes() == text
+
+
+@pytest.mark.gpu
+def test_encode_with_special_tokens_on_the_device(pkg, monkeypatch):
+    """Tokenizer::encode of a text full of special tokens: device front end (occurrences found on the host, ordinary parts
+    split as independent subjects by the kernel, special chunks resolved through the seeded chunk cache) == host path"""
+    base = pkg.synth_corpus(0x5EED000B, 3 << 20).tobytes()
+    tok, off, w, _ = pkg.split_dedup(pkg.patterns()["gpt4"], base[:1 << 20])
+    merges, _, _ = pkg.train(tok, off, w, 900, "lexical")
+    specials = b"<|endoftext|> 100257\n<|fim|> 100258\nab 100259\n"
+    rng = np.random.default_rng(4)
+    cuts = np.sort(rng.integers(0, len(base), 4000))
+    toks = [b"<|endoftext|>", b"<|fim|>", b"ab", b"<|endoftext|><|fim|>", b""]
+    text = b"".join(base[a:b] + toks[int(k)] for a, b, k in zip(np.r_[0, cuts], np.r_[cuts, len(base)], rng.integers(0, len(toks), len(cuts) + 1)))
+    text = b"<|fim|>" + text + b"<|endoftext|>"
+    results = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("MBPE_GPU_SPLIT", mode)
+        monkeypatch.setenv("MBPE_ENCODE_SEG_BYTES", str(1 << 20))  # several segments: boundaries at occurrences and at cuts
+        tk = pkg.Tokenizer(pkg.patterns()["gpt4"])
+        import tempfile
+        with tempfile.TemporaryDirectory() as td:
+            mp = os.path.join(td, "m.model")
+            pkg.write_model(mp, pkg.patterns()["gpt4"], specials, merges)
+            tk.load(mp)
+        results[mode] = tk.encode(text)
+        assert tk.decode(results[mode]) == text
+    assert np.array_equal(results["0"], results["1"])
+    assert (results["1"] == 100257).sum() > 1000 and (results["1"] == 100259).sum() > 1000
