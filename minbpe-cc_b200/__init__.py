@@ -255,6 +255,18 @@ class Pretok:
                                    C.c_uint64(len(out)), C.byref(n)))
         return out[:n.value].copy()
 
+    def encode_text_special(self, encoder, text: bytes, sp_begin, sp_end):
+        """... with special-token occurrences [sp_begin[i], sp_end[i]) in text order (encoder.seed_special_chunks first)"""
+        buf = _u8(text)
+        sb, se = np.ascontiguousarray(sp_begin, np.uint64), np.ascontiguousarray(sp_end, np.uint64)
+        out = np.zeros(max(len(text), 1), np.uint32)
+        n = C.c_uint64()
+        _ck(lib().mbpe_encode_text_special(encoder.h, self.h, _p(buf, C.c_uint8), C.c_uint64(len(text)),
+                                           _p(sb if len(sb) else np.zeros(1, np.uint64), C.c_uint64),
+                                           _p(se if len(se) else np.zeros(1, np.uint64), C.c_uint64), C.c_uint64(len(sb)),
+                                           _p(out, C.c_uint32), C.c_uint64(len(out)), C.byref(n)))
+        return out[:n.value].copy()
+
     def close(self):
         if self.h:
             lib().mbpe_pretok_destroy(self.h)
@@ -338,6 +350,15 @@ class Encoder:
                               C.c_uint64(len(off) - 1), _p(out, C.c_uint32), C.c_uint64(len(out)), C.byref(n),
                               None if out_off is None else _p(out_off, C.c_uint64)))
         return (out[:n.value].copy(), out_off) if want_off else out[:n.value].copy()
+
+    def seed_special_chunks(self, tokens):
+        """tokens: [(bytes, id)]: a chunk with exactly these bytes encodes to this one id (special tokens)"""
+        ids = np.asarray([i for _, i in tokens] or [0], np.uint32)
+        blob = b"".join(t for t, _ in tokens)
+        off = np.zeros(len(tokens) + 1, np.uint64)
+        off[1:] = np.cumsum([len(t) for t, _ in tokens])
+        _ck(lib().mbpe_encoder_seed_special_chunks(self.h, _p(ids, C.c_uint32), _p(_u8(blob), C.c_uint8), _p(off, C.c_uint64),
+                                                   C.c_uint32(len(tokens))))
 
     def decode_device(self, d_ids, n_ids, d_out, out_cap, d_n_out, stream=None):
         """All pointers are device addresses (ints); d_out may be 0 to size only."""

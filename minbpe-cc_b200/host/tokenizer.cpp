@@ -238,6 +238,24 @@ int Tokenizer::ensure_encoder() {
             return rc;
         }
     }
+    // encode side: "a chunk with exactly these bytes is this id" (Tokenizer.h:667-671) for the device front end
+    specials_on_device_ = false;
+    if (!special_tokens_.empty()) {
+        std::vector<uint32_t> sids;
+        std::vector<uint8_t> sbytes;
+        std::vector<uint64_t> soff{0};
+        for (const auto &kv : special_tokens_) {
+            sids.push_back(kv.second);
+            sbytes.insert(sbytes.end(), kv.first.begin(), kv.first.end());
+            soff.push_back(sbytes.size());
+        }
+        rc = mbpe_encoder_seed_special_chunks(encoder_, sids.data(), sbytes.data(), soff.data(), static_cast<uint32_t>(sids.size()));
+        if (rc != MBPE_OK && rc != MBPE_E_UNSUPPORTED) {
+            error_ = mbpe_last_error();
+            return rc;
+        }
+        specials_on_device_ = rc == MBPE_OK;
+    }
     encoder_stale_ = false;
     return MBPE_OK;
 }
@@ -247,7 +265,12 @@ int Tokenizer::ensure_encoder() {
 // text up, ids down with split and merge scan both on the device (built-in patterns; special tokens if the encoder
 // knows them as ready-made chunks). MBPE_E_UNSUPPORTED: not applicable to this tokenizer / text -- use the host path.
 int Tokenizer::encode_on_device(std::string_view text, Token *out, uint64_t cap, uint64_t *n_out) {
-    if (!(special_tokens_.empty() || specials_on_device_) || !use_gpu_split(text.size())) return MBPE_E_UNSUPPORTED;
+    if (!(special_tokens_.empty() || specials_on_device_) || !use_gpu_split(text.size())) {
+        if (getenv("MBPE_DEBUG"))
+            fprintf(stderr, "[mbpe] encode: host front end (specials %zu, seeded %d, device matcher %d)\n", special_tokens_.size(),
+                    (int)specials_on_device_, (int)(pretok_ != nullptr));
+        return MBPE_E_UNSUPPORTED;
+    }
     int rc;
     if (special_tokens_.empty()) {
         rc = mbpe_encode_text(encoder_, pretok_, reinterpret_cast<const uint8_t *>(text.data()), text.size(), out, cap, n_out);
@@ -262,6 +285,7 @@ int Tokenizer::encode_on_device(std::string_view text, Token *out, uint64_t cap,
                                       se.data(), sb.size(), out, cap, n_out);
     }
     if (rc != MBPE_OK && rc != MBPE_E_UNSUPPORTED) error_ = mbpe_last_error();
+    if (rc == MBPE_E_UNSUPPORTED && getenv("MBPE_DEBUG")) fprintf(stderr, "[mbpe] encode: device front end declined: %s\n", mbpe_last_error());
     return rc;
 }
 

@@ -388,6 +388,8 @@ def test_encode_with_special_tokens_on_the_device(pkg, monkeypatch):
     specials = b"<|endoftext|> 100257\n<|fim|> 100258\nab 100259\n"
     rng = np.random.default_rng(4)
     cuts = np.sort(rng.integers(0, len(base), 4000))
+    arr = np.frombuffer(base, np.uint8)
+    cuts = np.asarray([c for c in cuts if (arr[c] & 0xC0) != 0x80])  # never inside a UTF-8 sequence: the text stays well formed
     toks = [b"<|endoftext|>", b"<|fim|>", b"ab", b"<|endoftext|><|fim|>", b""]
     text = b"".join(base[a:b] + toks[int(k)] for a, b, k in zip(np.r_[0, cuts], np.r_[cuts, len(base)], rng.integers(0, len(toks), len(cuts) + 1)))
     text = b"<|fim|>" + text + b"<|endoftext|>"
@@ -403,5 +405,17 @@ def test_encode_with_special_tokens_on_the_device(pkg, monkeypatch):
             tk.load(mp)
         results[mode] = tk.encode(text)
         assert tk.decode(results[mode]) == text
+        if mode == "1":  # the device front end really ran: straight through the C ABI as well
+            parts = pkg.special_split(specials, text)
+            sb = np.asarray([a for a, _, i in parts if i >= 0], np.uint64)
+            se = np.asarray([b for _, b, i in parts if i >= 0], np.uint64)
+            enc = pkg.Encoder(merges)
+            toks_ = [(b"<|endoftext|>", 100257), (b"<|fim|>", 100258), (b"ab", 100259)]
+            enc.seed_special_chunks(toks_)
+            pt = pkg.Pretok()
+            direct = pt.encode_text_special(enc, text, sb, se)
+            assert np.array_equal(direct, results[mode])
+            pt.close()
+            enc.close()
     assert np.array_equal(results["0"], results["1"])
     assert (results["1"] == 100257).sum() > 1000 and (results["1"] == 100259).sum() > 1000
