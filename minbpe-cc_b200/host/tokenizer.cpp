@@ -6,6 +6,8 @@
 #include <iomanip>
 #include <iostream>
 #include <sstream>
+#include <thread>
+#include <algorithm>
 
 #include "bpe_host.hpp"
 
@@ -163,6 +165,44 @@ std::vector<SpecialPart> split_special_spans(std::string_view text,
     std::vector<SpecialPart> parts;
     if (specials.empty()) {
         parts.push_back({0, text.size(), -1});
+        return parts;
+    }
+    // Large texts: every occurrence of every token (overlapping ones too) is collected by all host threads over ranges
+    // of the text; the reference's rule then is one pass over that list -- from the current position take the first
+    // occurrence at or after it (equal positions: the token the map iterates first), jump behind it, repeat.
+    const int n_threads = hardware_threads();
+    if (text.size() >= (8u << 20) && n_threads > 1) {
+        std::vector<const std::string *> toks;
+        std::vector<Token> tids;
+        for (const auto &kv : specials) {
+            toks.push_back(&kv.first);
+            tids.push_back(kv.second);
+        }
+        const size_t T = (size_t)std::min(n_threads, 32), step = (text.size() + T - 1) / T;
+        std::vector<std::vector<std::pair<size_t, uint32_t>>> found(T);
+        std::vector<std::thread> th;
+        for (size_t t = 0; t < T; t++)
+            th.emplace_back([&, t]() {
+                const size_t a = t * step, b = std::min(text.size(), a + step);
+                for (uint32_t k = 0; k < toks.size() && a < b; k++) {
+                    const std::string &tok = *toks[k];
+                    if (tok.empty()) continue;
+                    const std::string_view sub = text.substr(a, (b - a) + tok.size() - 1); // occurrences that START in [a, b)
+                    for (size_t q = sub.find(tok); q != std::string_view::npos; q = sub.find(tok, q + 1)) found[t].emplace_back(a + q, k);
+                }
+                std::sort(found[t].begin(), found[t].end());
+            });
+        for (auto &x : th) x.join();
+        size_t pos = 0, last = 0;
+        for (size_t t = 0; t < T; t++)
+            for (const auto &[at, k] : found[t]) {
+                if (at < pos) continue; // overlaps the occurrence taken before it
+                if (at > last) parts.push_back({last, at, -1});
+                parts.push_back({at, at + toks[k]->size(), (int64_t)tids[k]});
+                pos = last = at + toks[k]->size();
+            }
+        if (last < text.size()) parts.push_back({last, text.size(), -1});
+        if (parts.empty()) parts.push_back({0, text.size(), -1});
         return parts;
     }
     struct Next {

@@ -162,5 +162,11 @@ def test_special_split_one_sweep_matches_reference_rule(pkg):
         parts = [text[s:e] if i < 0 else b"\0" + str(i).encode() for s, e, i in got]
         # no two of these tokens can match at the same position unless one is a prefix of the other; none is
         assert parts == O.split_on_special(text, specials), text
+    # large text: the multi-threaded collection of occurrences gives the same parts as the one-sweep loop on slices
+    big = b"".join(pieces[k] for k in rng.integers(0, len(pieces), 4_000_000))
+    assert len(big) >= 8 << 20
+    got = pkg.special_split(contents, big)
+    parts = [big[s:e] if i < 0 else b"\0" + str(i).encode() for s, e, i in got]
+    assert parts == O.split_on_special(big, specials)
     assert pkg.special_split(b"", b"plain") == [(0, 5, -1)]
     assert pkg.special_split(contents, b"") == [(0, 0, -1)]
