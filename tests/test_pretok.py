@@ -109,7 +109,7 @@ def test_gpt2_pattern_fuzz_and_fixture(emu, seed, pcre2_starts):
         assert err == 0 and np.array_equal(got, pcre2_starts(text, "gpt2"))
 
 
-def _expected_starts_with_specials(pkg, contents: bytes, text: bytes):
+def _expected_starts_with_specials(pkg, contents: bytes, text: bytes, kind="gpt4"):
     """chunk starts the reference produces: special tokens cut out (Tokenizer.h:605-650), every ordinary part split on
     its own (:664-704), each special token one chunk"""
     starts, sp = [], []
@@ -118,15 +118,16 @@ def _expected_starts_with_specials(pkg, contents: bytes, text: bytes):
             starts.append(s0)
             sp.append((s0, e0))
         elif e0 > s0:
-            ps, _ = pkg.split(pkg.patterns()["gpt4"], text[s0:e0], 1)
+            ps, _ = pkg.split(pkg.patterns()[kind], text[s0:e0], 1)
             starts.extend(int(x) + s0 for x in ps)
     return np.asarray(sorted(starts), np.uint64), sp
 
 
-def test_subjects_cut_by_special_tokens(pkg, emu):
+@pytest.mark.parametrize("kind", ["gpt4", "gpt2"])
+def test_subjects_cut_by_special_tokens(pkg, emu, kind):
     L = C.CDLL(EMU_LIB)
     L.emu_pretok_parts.restype = C.c_uint32
-    L.emu_pretok_kind(0)
+    L.emu_pretok_kind({"gpt4": 0, "gpt2": 1}[kind])
     table = pkg.pretok_class_table()
     specials = [(b"<|endoftext|>", 100257), (b"<|x|>", 100258), (b"ab", 7)]
     contents = b"".join(t + b" " + str(i).encode() + b"\n" for t, i in specials)
@@ -138,7 +139,7 @@ def test_subjects_cut_by_special_tokens(pkg, emu):
         text = b"".join(pieces[k] for k in rng.integers(0, len(pieces), int(rng.integers(0, 40))))
         if not text:
             continue
-        want, sp = _expected_starts_with_specials(pkg, contents, text)
+        want, sp = _expected_starts_with_specials(pkg, contents, text, kind)
         sb = np.asarray([a for a, _ in sp] or [0], np.uint32)
         se = np.asarray([b for _, b in sp] or [0], np.uint32)
         buf = np.frombuffer(text, np.uint8)
