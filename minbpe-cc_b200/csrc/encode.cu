@@ -21,6 +21,7 @@
 // k_decode_tiles: ids -> bytes gather through a packed (length + bytes) vocabulary word, same look-back.
 // mbpe_decode_file: .enc file -> text file in blocks (reader thread, device, writer thread).
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <mutex>
 #include <string>
@@ -86,9 +87,15 @@ __device__ __forceinline__ uint32_t enc_pass(const EncTable &tab, uint32_t *t, u
     return w;
 }
 
+} // namespace mbpe
+
+#include "encode_tiles.cuh"
+
+namespace mbpe {
 // ---------------------------------------------------------------------------------------------------------
-// k_encode_long: chunks longer than ENC_SHORT_MAX, one thread each, ping-pong in two scratch streams.
-// Result: tokens at scratch_a[off[c] ..], count at scratch_b[off[c]].
+// Long chunks (> ENC_SHORT_MAX bytes; encoder "basic": the whole text is one chunk), one thread each, in place in a
+// scratch stream. The tile kernel reports them (optimistic first launch); k_encode_find_long only runs when that
+// report overflowed. Result: tokens at scratch_a[off[c] ..], count at scratch_b[off[c]].
 // ---------------------------------------------------------------------------------------------------------
 __global__ void k_encode_find_long(const uint32_t *off, uint64_t n_chunks, uint32_t *long_list, uint32_t *n_long,
                                    uint32_t cap) {
@@ -99,503 +106,21 @@ __global__ void k_encode_find_long(const uint32_t *off, uint64_t n_chunks, uint3
         }
 }
 
-__global__ void k_encode_long(EncTable tab, const uint8_t *bytes, const uint32_t *off, const uint32_t *long_list,
+__global__ void k_encode_long(EncTable tab, EncSpecials sp, const uint8_t *bytes, const uint32_t *off, const uint32_t *long_list,
                               uint32_t n_long, uint32_t *scratch_a, uint32_t *scratch_b) {
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_long; k += gridDim.x * blockDim.x) {
         uint32_t c = long_list[k], o = off[c], len = off[c + 1] - o;
         uint32_t *t = scratch_a + o;
+        const uint32_t sid = special_match(sp, len, [&](uint32_t i) { return __ldg(&bytes[o + i]); });
+        if (sid != ENC_NONE) { // a special token longer than ENC_SHORT_MAX bytes (Tokenizer.h:667-671)
+            t[0] = sid;
+            scratch_b[o] = 1;
+            continue;
+        }
         for (uint32_t i = 0; i < len; i++) t[i] = bytes[o + i];
         bool merged = true;
         while (merged && len >= 2) len = enc_pass(tab, t, len, merged); // in place: write index never passes read index
         scratch_b[o] = len;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// k_encode_tiles
-// ---------------------------------------------------------------------------------------------------------
-struct CacheSlot;
-struct CacheLogEntry;
-struct ChunkCache {
-    CacheSlot *slots;    // nullptr = cache disabled
-    uint32_t mask;       // slots - 1
-    CacheLogEntry *log;  // chunks the current sub-batch had to scan
-    uint32_t *log_count;
-    uint32_t log_cap;
-    uint32_t *used;      // occupied slots (learning stops at half full)
-    uint32_t *arena;     // ids of entries with more than CACHE_INLINE_IDS ids
-    uint32_t *arena_used;
-    uint32_t arena_cap;
-};
-
-struct EncArgs {
-    EncTable tab;
-    ChunkCache cache;
-    uint64_t chunk0, chunk1;   // this launch covers chunks [chunk0, chunk1) in tiles of ET_CHUNKS
-    const unsigned long long *stream_base; // ids produced by earlier sub-batches (device word) = base of tile 0
-    const uint8_t *bytes;
-    uint64_t n_bytes_total; // bytes readable from `bytes` (vector loads never cross it)
-    const uint32_t *off;
-    uint64_t n_chunks;
-    uint32_t *out;
-    uint64_t out_cap;
-    unsigned long long *d_n_out;
-    unsigned long long *out_off; // optional per-chunk token offsets (n_chunks + 1)
-    unsigned long long *status;  // look-back words, one per tile, zeroed
-    uint32_t *ticket;            // zeroed
-    uint32_t n_tiles;
-    const uint32_t *scratch_a;   // long-chunk tokens / counts (may be null)
-    const uint32_t *scratch_b;
-    uint32_t *overflow;          // set when out_cap is too small
-    uint32_t *miss_count;        // chunks that went through the scan (statistics)
-    uint32_t ablate;             // MBPE_ENC_ABLATE (profiling only; 1, 2, 4 give WRONG results): 1 no look-back wait, 2 no
-                                 // cache probe (every chunk "hits" with two fake ids), 4 no id stores, 16 ids stored by their threads instead of through shared memory
-};
-
-// ---------------------------------------------------------------------------------------------------------
-// Chunk cache. The multi-pass scan of a chunk is a pure function of its bytes, and text repeats its chunks
-// (Zipf): the encoder keeps an open-addressed table  chunk bytes (<= 15) -> ids (<= 3)  in HBM (32-byte slots, one
-// sector per probe, L2/L1 resident for the hot words). k_encode_tiles only READS it (read-only path); chunks it
-// does not find are encoded by the scan itself and appended to a log, and k_cache_insert adds the log to the table
-// between sub-batches. No kernel both reads and writes the table, so there is no publication protocol to get
-// wrong. Results are bit-identical with or without the cache (MBPE_ENCODE_CACHE=0 disables it; tests run both).
-// ---------------------------------------------------------------------------------------------------------
-struct CacheSlot { // 64 bytes = two sectors: key, value
-    uint64_t k[4]; // chunk bytes, little endian, zero padded; top byte of k[3] = length (1..31); k[3] == 0: empty
-    uint32_t n;    // number of ids (1..31)
-    uint32_t v[7]; // n <= 7: the ids; otherwise v[0] = offset of the ids in the arena
-};
-static_assert(sizeof(CacheSlot) == 64, "two sectors per entry");
-struct CacheLogEntry {
-    uint64_t k[4];
-    uint32_t n;
-    uint32_t ids[31];
-};
-constexpr uint32_t CACHE_MAX_LEN = 31, CACHE_INLINE_IDS = 7;
-
-__device__ __forceinline__ uint32_t cache_hash(uint64_t k0, uint64_t k1, uint64_t k2, uint64_t k3) {
-    uint64_t h = (k0 ^ (k1 * 0x9E3779B97F4A7C15ull)) * 0xff51afd7ed558ccdULL;
-    h ^= (k2 * 0xc2b2ae3d27d4eb4fULL) ^ (k3 * 0x165667b19e3779f9ULL);
-    h ^= h >> 32;
-    h *= 0xc4ceb9fe1a85ec53ULL;
-    return (uint32_t)(h >> 32);
-}
-
-__global__ void k_cache_insert(ChunkCache cc) {
-    const uint32_t n = min(*cc.log_count, cc.log_cap);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const CacheLogEntry &e = cc.log[i];
-        if (*((volatile uint32_t *)cc.used) * 2 > cc.mask) return; // half full: stop learning
-        const uint64_t k0 = e.k[0], k1 = e.k[1], k2 = e.k[2], k3 = e.k[3];
-        const uint32_t en = e.n;
-        uint32_t h = cache_hash(k0, k1, k2, k3) & cc.mask;
-        for (;;) {
-            unsigned long long *claim = reinterpret_cast<unsigned long long *>(&cc.slots[h].k[3]);
-            unsigned long long cur = *((volatile unsigned long long *)claim);
-            if (cur == 0) {
-                uint32_t aoff = 0;
-                if (en > CACHE_INLINE_IDS) { // reserve arena room BEFORE claiming, so a claimed slot is always completed
-                    aoff = atomicAdd(cc.arena_used, en);
-                    if (aoff + en > cc.arena_cap) break;
-                }
-                cur = atomicCAS(claim, 0ull, (unsigned long long)k3);
-                if (cur == 0) { // claimed: k[3] is the claim word, the rest is written by the winner only
-                    cc.slots[h].k[0] = k0;
-                    cc.slots[h].k[1] = k1;
-                    cc.slots[h].k[2] = k2;
-                    cc.slots[h].n = en;
-                    if (en <= CACHE_INLINE_IDS) {
-                        for (uint32_t q = 0; q < en; q++) cc.slots[h].v[q] = e.ids[q];
-                    } else {
-                        cc.slots[h].v[0] = aoff;
-                        for (uint32_t q = 0; q < en; q++) cc.arena[aoff + q] = e.ids[q];
-                    }
-                    atomicAdd(cc.used, 1u);
-                    break;
-                }
-            }
-            // Same key: already there (the log holds duplicates of hot chunks). Words of a slot claimed in THIS launch
-            // may not be visible yet; then the duplicate takes a second slot -- harmless, both slots hold the same ids
-            // and a reader uses the first one it finds.
-            if (cur == k3 && *((volatile uint64_t *)&cc.slots[h].k[0]) == k0 &&
-                *((volatile uint64_t *)&cc.slots[h].k[1]) == k1 && *((volatile uint64_t *)&cc.slots[h].k[2]) == k2)
-                break;
-            h = (h + 1) & cc.mask;
-        }
-    }
-}
-__global__ void k_cache_reset_log(ChunkCache cc) { *cc.log_count = 0; }
-
-// ---------------------------------------------------------------------------------------------------------
-// k_encode_tiles. A tile = ET_CHUNKS consecutive chunks; its boundaries and its text are staged into shared
-// memory with coalesced loads. Each thread owns ET_CPT consecutive chunks:
-//   1. chunks <= 15 bytes: assemble the 16-byte key from shared memory, probe the cache (read-only path);
-//   2. misses go to a tile work list and are encoded by the scan, one chunk per thread, all lanes busy;
-//   3. block scan + decoupled look-back give the tile its place in the flat stream; ids are written in order.
-// ---------------------------------------------------------------------------------------------------------
-constexpr int ET_CAP = 8192;         // staged text bytes per tile (avg chunk 5 B -> 5 KB); bigger tiles read HBM directly
-constexpr uint32_t ET_MISS_OUT = 2048; // ids of scanned chunks parked in shared memory until the tile offset is known
-constexpr uint32_t META_NONE = 0xFFFFF;
-constexpr uint64_t ENC_MAX_SUBBATCH = 1ull << 26; // chunks per launch at most (tile ids and look-back words are 32-bit safe)
-constexpr uint32_t ET_WARP_SCAN_MAX = 48; // up to this many misses per tile are scanned one warp per chunk
-
-template <int THREADS, int ET_CPT, int STG>
-struct EncSmemT {
-    static constexpr int ET_CHUNKS = THREADS * ET_CPT;
-    uint32_t off[ET_CHUNKS + 1];
-    alignas(16) uint32_t text[ET_CAP / 4 + 8]; // raw bytes, 16-byte aligned window
-    uint16_t miss[ET_CHUNKS];      // work list: chunk index within the tile
-    uint32_t meta[ET_CHUNKS];      // scanned chunks: start in miss_out (20 bits, META_NONE = not parked) | count << 20
-    uint32_t miss_out[ET_MISS_OUT];
-    uint32_t stage[STG ? STG : 1];
-    uint32_t warp_scratch[THREADS / 32][32];
-    uint32_t tile, n_miss, miss_used;
-    uint32_t warp_sum[THREADS / 32];
-    unsigned long long base;
-};
-
-template <class SM>
-__device__ __forceinline__ uint8_t tile_byte(const EncArgs &a, const SM &sm, bool staged, uint32_t a0, uint32_t g) {
-    return staged ? reinterpret_cast<const uint8_t *>(sm.text)[g - a0] : __ldg(&a.bytes[g]);
-}
-
-// scan one chunk (<= ENC_SHORT_MAX bytes) into t[]; returns the id count
-template <class SM>
-__device__ __forceinline__ uint32_t scan_chunk(const EncArgs &a, const SM &sm, bool staged, uint32_t a0, uint32_t o,
-                                               uint32_t len, uint32_t *t) {
-    for (uint32_t i = 0; i < len; i++) t[i] = tile_byte(a, sm, staged, a0, o + i);
-    bool merged = true;
-    while (merged && len >= 2) len = enc_pass(a.tab, t, len, merged);
-    return len;
-}
-
-// One warp scans one chunk of <= 32 bytes: lane i holds token i. Per pass every lane looks its pair up at once (one
-// lookup latency per pass instead of one per position); the left-to-right non-overlapping rule of
-// Tokenizer.h:336-359 is applied to the ballot mask: inside each maximal run of mergeable positions the 1st, 3rd,
-// 5th... merge. Runs are separated by parity of their start bit with the carry trick
-//   runs_even = F & ~(F + even_starts),   runs_odd = F & ~(F + odd_starts)
-// (bit 31 of F is always clear: lane 31 has no right neighbour, so the additions cannot overflow).
-// Returns the final length; on return lane i < length holds id i in `tok`. `scratch` = 32 words of shared memory
-// owned by the warp.
-__device__ __forceinline__ uint32_t scan_chunk_warp(const EncTable &tab, uint32_t &tok, uint32_t len, uint32_t *scratch) {
-    const uint32_t lane = threadIdx.x & 31;
-    while (len >= 2) {
-        const uint32_t nxt = __shfl_down_sync(0xffffffffu, tok, 1);
-        uint32_t id = ENC_NONE;
-        if (lane + 1 < len) id = enc_lookup_id(tab, tok, nxt);
-        const uint32_t F = __ballot_sync(0xffffffffu, id != ENC_NONE);
-        if (F == 0) break;
-        const uint32_t starts = F & ~(F << 1);
-        const uint32_t runs_even = F & ~(F + (starts & 0x55555555u));
-        const uint32_t runs_odd = F & ~(F + (starts & 0xAAAAAAAAu));
-        const uint32_t M = (runs_even & 0x55555555u) | (runs_odd & 0xAAAAAAAAu); // heads of merged pairs
-        const uint32_t valid = len >= 32 ? 0xffffffffu : ((1u << len) - 1);
-        const uint32_t keep = valid & ~(M << 1);                                   // tails disappear
-        if ((keep >> lane) & 1u) scratch[__popc(keep & ((1u << lane) - 1))] = ((M >> lane) & 1u) ? id : tok;
-        __syncwarp();
-        len = __popc(keep);
-        tok = lane < len ? scratch[lane] : 0u;
-        __syncwarp();
-    }
-    return len;
-}
-
-template <int THREADS, int ET_CPT, int MIN_CTAS, bool STREAM, int STG>
-__global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArgs a) {
-    using EncSmem = EncSmemT<THREADS, ET_CPT, STG>;
-    constexpr int ET_CHUNKS = EncSmem::ET_CHUNKS;
-    constexpr int ENC_THREADS = THREADS; // shadows the file-level default inside this kernel
-    extern __shared__ __align__(16) unsigned char enc_smem_raw[];
-    EncSmem &sm = *reinterpret_cast<EncSmem *>(enc_smem_raw);
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool use_cache = a.cache.slots != nullptr;
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) {
-            sm.tile = atomicAdd(a.ticket, 1u); // tiles start in order: look-back cannot deadlock
-            sm.n_miss = 0;
-            sm.miss_used = 0;
-        }
-        __syncthreads();
-        const uint32_t tile = sm.tile;
-        if (tile >= a.n_tiles) return;
-        const uint64_t c0 = a.chunk0 + (uint64_t)tile * ET_CHUNKS;
-        const uint32_t nc = (uint32_t)min((uint64_t)ET_CHUNKS, a.chunk1 - c0);
-        for (uint32_t i = tid; i <= nc; i += ENC_THREADS) sm.off[i] = STREAM ? __ldcs(&a.off[c0 + i]) : __ldg(&a.off[c0 + i]);
-        __syncthreads();
-        const uint32_t b0 = sm.off[0], b1 = sm.off[nc];
-        const uint32_t a0 = b0 & ~15u; // 16-byte aligned window start (device buffers are 256-byte aligned)
-        const bool staged = (b1 - a0) <= ET_CAP;
-        if (staged) {
-            uint4 *dst = reinterpret_cast<uint4 *>(sm.text);
-            for (uint32_t v = tid; a0 + v * 16 < b1; v += ENC_THREADS) {
-                const uint32_t g0 = a0 + v * 16;
-                uint4 q;
-                if (g0 + 16 <= a.n_bytes_total) {
-                    q = STREAM ? __ldcs(reinterpret_cast<const uint4 *>(a.bytes + g0)) : __ldg(reinterpret_cast<const uint4 *>(a.bytes + g0));
-                } else { // last vector of the buffer
-                    uint32_t w[4] = {0, 0, 0, 0};
-                    for (uint32_t g = g0; g < a.n_bytes_total; g++)
-                        w[(g - g0) >> 2] |= (uint32_t)__ldg(&a.bytes[g]) << (((g - g0) & 3) * 8);
-                    q = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-                dst[v] = q;
-            }
-            __syncthreads();
-        }
-        // ---- 1. cache probes -------------------------------------------------------------------------------
-        uint32_t cnt[ET_CPT], ids[ET_CPT][3];
-        uint32_t state[ET_CPT]; // 0 = ids[] valid (hit with <= 3 ids / empty chunk), 1 = scanned, 2 = long chunk,
-                                // 3 = hit with more ids: ids[j][0] = cache slot, ids are fetched again when writing
-        // key of chunk [o, o+len), len <= 31: bytes little endian, zero padded, length in the top byte
-        auto make_key = [&](uint32_t o, uint32_t len, uint64_t *key) {
-            const uint32_t r = o - a0, wi = r >> 2, sh = (r & 3) * 8;
-            uint32_t w[9];
-#pragma unroll
-            for (int q = 0; q < 5; q++) w[q] = sm.text[wi + q];
-            uint32_t v[8];
-#pragma unroll
-            for (int q = 0; q < 4; q++) v[q] = __funnelshift_r(w[q], w[q + 1], sh);
-#pragma unroll
-            for (int q = 4; q < 8; q++) v[q] = 0;
-            if (len > 16) {
-#pragma unroll
-                for (int q = 5; q < 9; q++) w[q] = sm.text[wi + q];
-#pragma unroll
-                for (int q = 4; q < 8; q++) v[q] = __funnelshift_r(w[q], w[q + 1], sh);
-            }
-            key[0] = ((uint64_t)v[1] << 32) | v[0];
-            key[1] = ((uint64_t)v[3] << 32) | v[2];
-            key[2] = ((uint64_t)v[5] << 32) | v[4];
-            key[3] = ((uint64_t)v[7] << 32) | v[6];
-#pragma unroll
-            for (int q = 0; q < 4; q++) { // zero everything at and after byte `len`
-                const int lo = q * 8;
-                if ((int)len <= lo)
-                    key[q] = 0;
-                else if ((int)len < lo + 8)
-                    key[q] &= (1ull << ((len - lo) * 8)) - 1;
-            }
-            key[3] |= (uint64_t)len << 56;
-        };
-        const bool cacheable_tile = use_cache && staged;
-#pragma unroll
-        for (int j = 0; j < ET_CPT; j++) {
-            const uint32_t k = tid * ET_CPT + j;
-            cnt[j] = 0;
-            state[j] = 0;
-            if (k >= nc) continue;
-            const uint32_t o = sm.off[k], len = sm.off[k + 1] - o;
-            if (len == 0) continue;
-            if (len > ENC_SHORT_MAX) {
-                state[j] = 2;
-                cnt[j] = a.scratch_b[o]; // encoded by k_encode_long
-                continue;
-            }
-            bool hit = false;
-            if (cacheable_tile && len <= CACHE_MAX_LEN) {
-                uint64_t key[4];
-                make_key(o, len, key);
-                uint32_t h = cache_hash(key[0], key[1], key[2], key[3]) & a.cache.mask;
-                if (a.ablate & 2) {
-                    cnt[j] = 2;
-                    ids[j][0] = (uint32_t)key[0];
-                    ids[j][1] = h;
-                    continue;
-                }
-                for (;;) {
-                    // the whole 64-byte entry at once: three independent 16-byte loads, one round trip
-                    const ulonglong2 *sp = reinterpret_cast<const ulonglong2 *>(&a.cache.slots[h]);
-                    const ulonglong2 lo = __ldg(sp);
-                    const ulonglong2 hi = __ldg(sp + 1);
-                    const uint4 tv = __ldg(reinterpret_cast<const uint4 *>(sp + 2)); // n, v[0..2]
-                    if (hi.y == 0) break; // empty: not cached
-                    if (hi.y == key[3] && hi.x == key[2] && lo.x == key[0] && lo.y == key[1]) {
-                        cnt[j] = tv.x;
-                        ids[j][0] = tv.y;
-                        ids[j][1] = tv.z;
-                        ids[j][2] = tv.w;
-                        if (tv.x > 3) {
-                            state[j] = 3;
-                            ids[j][0] = h;
-                        }
-                        hit = true;
-                        break;
-                    }
-                    h = (h + 1) & a.cache.mask;
-                }
-            }
-            if (!hit) {
-                state[j] = 1;
-                sm.miss[atomicAdd(&sm.n_miss, 1u)] = (uint16_t)k;
-            }
-        }
-        __syncthreads();
-        // ---- 2. scan the misses, ids parked in shared memory until the tile knows its place ------------------
-        const uint32_t n_miss = sm.n_miss;
-        if (tid == 0 && n_miss) atomicAdd(a.miss_count, n_miss);
-        if (n_miss <= ET_WARP_SCAN_MAX) {
-            // few misses (warm cache): latency matters -- one WARP per chunk, lanes = positions
-            for (uint32_t q = warp; q < n_miss; q += ENC_THREADS / 32) {
-                const uint32_t mk = sm.miss[q], o = sm.off[mk], mlen = sm.off[mk + 1] - o;
-                if (mlen > 32) continue; // 33..64 bytes: serial scan below
-                uint32_t tok = lane < mlen ? tile_byte(a, sm, staged, a0, o + lane) : 0u;
-                const uint32_t mn = scan_chunk_warp(a.tab, tok, mlen, sm.warp_scratch[warp]); // lane i < mn: id i in tok
-                uint32_t start = 0;
-                if (lane == 0) start = atomicAdd(&sm.miss_used, mn);
-                start = __shfl_sync(0xffffffffu, start, 0);
-                if (start + mn <= ET_MISS_OUT) {
-                    if (lane < mn) sm.miss_out[start + lane] = tok;
-                } else {
-                    start = META_NONE;
-                }
-                if (lane == 0) sm.meta[mk] = start | (mn << 20);
-                if (use_cache && mlen <= CACHE_MAX_LEN) { // teach the cache
-                    uint32_t li = 0;
-                    if (lane == 0) li = atomicAdd(a.cache.log_count, 1u);
-                    li = __shfl_sync(0xffffffffu, li, 0);
-                    if (li < a.cache.log_cap) {
-                        CacheLogEntry &e = a.cache.log[li];
-                        if (lane < mn) e.ids[lane] = tok;
-                        if (lane == 0) {
-                            uint64_t key[4] = {0, 0, 0, 0};
-                            for (uint32_t i = 0; i < mlen; i++)
-                                key[i >> 3] |= (uint64_t)tile_byte(a, sm, staged, a0, o + i) << ((i & 7) * 8);
-                            key[3] |= (uint64_t)mlen << 56;
-                            e.k[0] = key[0];
-                            e.k[1] = key[1];
-                            e.k[2] = key[2];
-                            e.k[3] = key[3];
-                            e.n = mn;
-                        }
-                    }
-                }
-                __syncwarp();
-            }
-        }
-        for (uint32_t q = tid; q < n_miss; q += ENC_THREADS) {
-            // many misses (cold cache): throughput matters -- one THREAD per chunk; also chunks of 33..64 bytes
-            const uint32_t mk = sm.miss[q], o = sm.off[mk], mlen = sm.off[mk + 1] - o;
-            if (n_miss <= ET_WARP_SCAN_MAX && mlen <= 32) continue;
-            uint32_t t[ENC_SHORT_MAX];
-            const uint32_t mn = scan_chunk(a, sm, staged, a0, o, mlen, t);
-            uint32_t start = atomicAdd(&sm.miss_used, mn);
-            if (start + mn <= ET_MISS_OUT) {
-                for (uint32_t i = 0; i < mn; i++) sm.miss_out[start + i] = t[i];
-            } else {
-                start = META_NONE; // no room: the owner scans it again when writing
-            }
-            sm.meta[mk] = start | (mn << 20);
-            if (use_cache && mlen <= CACHE_MAX_LEN) { // teach the cache
-                const uint32_t li = atomicAdd(a.cache.log_count, 1u);
-                if (li < a.cache.log_cap) {
-                    uint64_t key[4] = {0, 0, 0, 0};
-                    for (uint32_t i = 0; i < mlen; i++)
-                        key[i >> 3] |= (uint64_t)tile_byte(a, sm, staged, a0, o + i) << ((i & 7) * 8);
-                    key[3] |= (uint64_t)mlen << 56;
-                    CacheLogEntry &e = a.cache.log[li];
-                    e.k[0] = key[0];
-                    e.k[1] = key[1];
-                    e.k[2] = key[2];
-                    e.k[3] = key[3];
-                    e.n = mn;
-                    for (uint32_t i = 0; i < mn; i++) e.ids[i] = t[i];
-                }
-            }
-        }
-        __syncthreads();
-        uint32_t sum = 0;
-#pragma unroll
-        for (int j = 0; j < ET_CPT; j++) {
-            if (state[j] == 1) cnt[j] = sm.meta[tid * ET_CPT + j] >> 20;
-            sum += cnt[j];
-        }
-        // ---- 3. place in the stream: block exclusive scan + look-back -----------------------------------------
-        uint32_t incl = sum;
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += v;
-        }
-        if (lane == 31) sm.warp_sum[warp] = incl;
-        __syncthreads();
-        uint32_t warp_base = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < ENC_THREADS / 32; w++) {
-            uint32_t v = sm.warp_sum[w];
-            if (w < (int)warp) warp_base += v;
-            total += v;
-        }
-        if (warp == 0) {
-            const uint64_t b = (a.ablate & 1) ? (uint64_t)tile * (ET_CHUNKS * 9 / 4)
-                                              : lookback_base(a.status, tile, total, a.stream_base);
-            if (lane == 0) sm.base = b;
-        }
-        __syncthreads();
-        const uint64_t base = sm.base;
-        // ids go to shared memory first and leave for HBM as whole 128-byte lines (a thread's own stores would touch
-        // one sector per lane); tiles whose ids do not fit the buffer, or the end of a full output buffer, store directly
-        const bool via_smem = STG > 0 && total <= (uint32_t)STG && base + total <= a.out_cap && !(a.ablate & 16);
-        uint32_t loc = warp_base + (incl - sum);
-        uint32_t *const gout = a.out + base; // only dereferenced below out_cap
-#pragma unroll
-        for (int j = 0; j < ET_CPT; j++) {
-            const uint32_t k = tid * ET_CPT + j;
-            if (k >= nc) continue;
-            const uint32_t n = cnt[j];
-            if (a.out_off) a.out_off[c0 + k] = base + loc;
-            if (a.ablate & 4) {
-            } else if (via_smem || base + loc + n <= a.out_cap) {
-                uint32_t *const dstp = (via_smem ? sm.stage : gout) + loc;
-                if (state[j] == 0) {
-                    if (n > 0) dstp[0] = ids[j][0];
-                    if (n > 1) dstp[1] = ids[j][1];
-                    if (n > 2) dstp[2] = ids[j][2];
-                } else if (state[j] == 3) {
-                    const CacheSlot &cs = a.cache.slots[ids[j][0]];
-                    if (n <= CACHE_INLINE_IDS) { // the value sector again: two vector loads, predicated stores, no loop
-                        const uint4 lo4 = __ldg(reinterpret_cast<const uint4 *>(&cs.n));      // n, v0, v1, v2
-                        const uint4 hi4 = __ldg(reinterpret_cast<const uint4 *>(&cs.v[3]));   // v3 .. v6
-                        dstp[0] = lo4.y;
-                        dstp[1] = lo4.z;
-                        dstp[2] = lo4.w;
-                        dstp[3] = hi4.x;
-                        if (n > 4) dstp[4] = hi4.y;
-                        if (n > 5) dstp[5] = hi4.z;
-                        if (n > 6) dstp[6] = hi4.w;
-                    } else {
-                        const uint32_t *src = a.cache.arena + __ldg(&cs.v[0]);
-                        for (uint32_t i = 0; i < n; i++) dstp[i] = __ldg(&src[i]);
-                    }
-                } else if (state[j] == 1) {
-                    const uint32_t start = sm.meta[k] & 0xFFFFF;
-                    if (start != META_NONE) {
-                        for (uint32_t i = 0; i < n; i++) dstp[i] = sm.miss_out[start + i];
-                    } else {
-                        uint32_t t[ENC_SHORT_MAX];
-                        const uint32_t o = sm.off[k];
-                        scan_chunk(a, sm, staged, a0, o, sm.off[k + 1] - o, t);
-                        for (uint32_t i = 0; i < n; i++) dstp[i] = t[i];
-                    }
-                } else {
-                    const uint32_t o = sm.off[k];
-                    for (uint32_t i = 0; i < n; i++) dstp[i] = a.scratch_a[o + i];
-                }
-            } else if (n) {
-                *a.overflow = 1;
-            }
-            loc += n;
-        }
-        if (via_smem && !(a.ablate & 4)) {
-            __syncthreads();
-            for (uint32_t i = tid; i < total; i += ENC_THREADS) {
-                if (STREAM) __stcs(&gout[i], sm.stage[i]);
-                else gout[i] = sm.stage[i];
-            }
-        }
-        if (tile == a.n_tiles - 1 && tid == 0) {
-            *a.d_n_out = base + total;
-            if (a.out_off && a.chunk1 == a.n_chunks) a.out_off[a.n_chunks] = base + total;
-        }
     }
 }
 
@@ -776,27 +301,40 @@ struct mbpe_encoder {
     uint32_t *d_sp_ids = nullptr, *d_sp_off = nullptr;
     uint8_t *d_sp_bytes = nullptr;
     uint32_t n_sp = 0;
+    // encode-side special tokens: "a chunk with exactly these bytes is this id" (Tokenizer.h:667-671)
+    uint32_t *d_esp_ids = nullptr, *d_esp_off = nullptr;
+    uint8_t *d_esp_bytes = nullptr;
+    uint32_t n_esp = 0;
+    unsigned long long esp_len_mask = 0;
     // scratch (grown on demand)
     unsigned long long *d_status = nullptr;
     uint64_t status_cap = 0;
-    uint32_t *d_small = nullptr; // [0] ticket, [1] n_long, [2] overflow
+    uint32_t *d_small = nullptr; // [0] ticket, [1] n_long, [2] overflow, [3] scanned chunks
     unsigned long long *d_n_out = nullptr;
     uint32_t *d_long_list = nullptr;
     uint64_t long_cap = 0;
     uint32_t *d_scratch_a = nullptr, *d_scratch_b = nullptr;
     uint64_t scratch_cap = 0;
     uint64_t launches = 0;
-    // chunk cache (learned across calls)
+    // chunk caches (learned across calls)
+    SmallSlot *d_cache_small = nullptr;
     CacheSlot *d_cache = nullptr;
     CacheLogEntry *d_cache_log = nullptr;
     uint32_t *d_cache_arena = nullptr;
-    uint32_t cache_slots = 0, cache_log_cap = 0, cache_arena_cap = 0;
-    uint32_t *d_cache_ctr = nullptr; // [0] log count, [1] used slots, [2] arena cursor
+    uint32_t small_slots = 0, small_log2 = 0, cache_slots = 0, cache_log_cap = 0, cache_arena_cap = 0;
+    uint32_t *d_cache_ctr = nullptr; // [0] log count, [1] used BIG slots, [2] used SMALL slots, [3] arena cursor
     uint64_t sub_batch_chunks = 0; // fixed sub-batch size (MBPE_ENCODE_SUBBATCH), 0 = geometric schedule
-    uint64_t chunks_seen = 0;      // chunks encoded so far with this handle: how warm the cache is
+    uint64_t chunks_seen = 0;      // chunks encoded so far with this handle: how warm the caches are
     int cfg = 0; // kernel shape, see enc_configs
-    bool specials_seeded = false; // mbpe_encoder_seed_special_chunks succeeded
     size_t l2_window_max = 0, l2_persist_bytes = 0;
+    // mbpe_encode (host buffers): pinned staging + device buffers of the segment pipeline, two of each
+    struct HostPipe {
+        uint8_t *h_text = nullptr, *d_text = nullptr;
+        uint32_t *h_off = nullptr, *d_off = nullptr, *h_ids = nullptr, *d_ids = nullptr;
+        unsigned long long *h_out_off = nullptr, *d_out_off = nullptr;
+    } pipe[2];
+    uint64_t pipe_bytes = 0, pipe_chunks = 0;
+    cudaStream_t pipe_stream = nullptr;
 };
 
 namespace mbpe {
@@ -805,18 +343,34 @@ struct EncConfig {
     void (*kernel)(const EncArgs);
     size_t smem;
 };
-#define ENC_CFG(T, C, M, P, G) EncConfig{T, C, M, k_encode_tiles<T, C, M, P, G>, sizeof(EncSmemT<T, C, G>)}
-// (threads, chunks per thread, CTAs per SM, streaming hints on the one-pass loads/stores, staging words); 0 = default
-static const EncConfig enc_configs[] = {ENC_CFG(256, 4, 4, true, 3072),  ENC_CFG(256, 4, 4, true, 4096), ENC_CFG(256, 4, 4, true, 0),
-                                        ENC_CFG(256, 4, 4, false, 0),    ENC_CFG(256, 4, 4, false, 4096), ENC_CFG(128, 4, 8, true, 2048),
-                                        ENC_CFG(128, 4, 8, true, 0),     ENC_CFG(256, 4, 5, true, 3072)};
+#define ENC_CFG(T, C, M) EncConfig{T, C, M, k_encode_tiles<T, C, M>, sizeof(EncSmemT<T, C>)}
+// (threads, chunks per thread, CTAs per SM); 0 = default, the others for A/B runs (MBPE_ENC_CFG)
+static const EncConfig enc_configs[] = {ENC_CFG(512, 2, 3), ENC_CFG(256, 2, 6), ENC_CFG(256, 4, 4), ENC_CFG(512, 2, 2),
+                                        ENC_CFG(256, 2, 5), ENC_CFG(1024, 1, 1), ENC_CFG(256, 4, 3), ENC_CFG(128, 2, 12)};
 constexpr int N_ENC_CONFIGS = sizeof(enc_configs) / sizeof(enc_configs[0]);
+
+static ChunkCache cache_view(const mbpe_encoder *e) {
+    ChunkCache cc{};
+    cc.small = e->d_cache_small;
+    cc.small_shift = 32 - e->small_log2;
+    cc.small_mask = e->small_slots ? e->small_slots - 1 : 0;
+    cc.slots = e->d_cache;
+    cc.mask = e->cache_slots ? e->cache_slots - 1 : 0;
+    cc.log = e->d_cache_log;
+    cc.log_count = e->d_cache_ctr;
+    cc.log_cap = e->cache_log_cap;
+    cc.used = e->d_cache_ctr ? e->d_cache_ctr + 1 : nullptr;
+    cc.arena = e->d_cache_arena;
+    cc.arena_used = e->d_cache_ctr ? e->d_cache_ctr + 3 : nullptr;
+    cc.arena_cap = e->cache_arena_cap;
+    return cc;
+}
+static EncSpecials specials_view(const mbpe_encoder *e) {
+    return EncSpecials{e->d_esp_ids, e->d_esp_off, e->d_esp_bytes, e->n_esp, e->esp_len_mask};
+}
 } // namespace mbpe
 
-extern "C" int mbpe_encoder_create(const uint32_t *merges, uint32_t n_merges, int device, mbpe_encoder **out) {
-    if (!out || (n_merges && !merges)) return set_error(MBPE_E_INVALID, "null argument");
-    *out = nullptr;
-    if (256ull + n_merges > (1ull << ENC_ID_BITS)) return set_error(MBPE_E_INVALID, "vocab larger than 2^21 ids");
+static int encoder_create_impl(mbpe_encoder *e, const uint32_t *merges, uint32_t n_merges, int device) {
     // vocabulary as load() rebuilds it (Tokenizer.h:844-861); a pair may only name earlier ids
     std::vector<uint32_t> voff(257 + (size_t)n_merges);
     std::vector<uint8_t> vbytes;
@@ -849,7 +403,6 @@ extern "C" int mbpe_encoder_create(const uint32_t *merges, uint32_t n_merges, in
     }
     int rc = use_device(device);
     if (rc) return rc;
-    mbpe_encoder *e = new mbpe_encoder();
     e->device = device;
     e->sms = sm_count(device);
     e->n_merges = n_merges;
@@ -880,12 +433,17 @@ extern "C" int mbpe_encoder_create(const uint32_t *merges, uint32_t n_merges, in
     MB_CUDA(cudaMalloc(&e->d_sp_ids, 4));
     MB_CUDA(cudaMalloc(&e->d_sp_off, 8));
     MB_CUDA(cudaMalloc(&e->d_sp_bytes, 1));
-    const char *cache_env = getenv("MBPE_ENCODE_CACHE"); // "0" disables; otherwise log2 of the slot count (default 22 = 256 MB)
+    // "0" disables the caches; otherwise log2 of the SMALL slot count (default 22 = 128 MB; BIG = a quarter as many slots)
+    const char *cache_env = getenv("MBPE_ENCODE_CACHE");
     int cache_log2 = cache_env && *cache_env ? atoi(cache_env) : 22;
     if (cache_log2 >= 10 && cache_log2 <= 26) {
-        e->cache_slots = 1u << cache_log2;
+        e->small_log2 = (uint32_t)cache_log2;
+        e->small_slots = 1u << cache_log2;
+        e->cache_slots = e->small_slots / 4;
         e->cache_log_cap = 1u << 19;
         e->cache_arena_cap = 1u << 22;
+        MB_CUDA(cudaMalloc(&e->d_cache_small, (uint64_t)e->small_slots * sizeof(SmallSlot)));
+        MB_CUDA(cudaMemset(e->d_cache_small, 0, (uint64_t)e->small_slots * sizeof(SmallSlot)));
         MB_CUDA(cudaMalloc(&e->d_cache, (uint64_t)e->cache_slots * sizeof(CacheSlot)));
         MB_CUDA(cudaMemset(e->d_cache, 0, (uint64_t)e->cache_slots * sizeof(CacheSlot)));
         MB_CUDA(cudaMalloc(&e->d_cache_log, (uint64_t)e->cache_log_cap * sizeof(CacheLogEntry)));
@@ -911,16 +469,48 @@ extern "C" int mbpe_encoder_create(const uint32_t *merges, uint32_t n_merges, in
     e->cfg = cfg_env && *cfg_env ? std::min(std::max(atoi(cfg_env), 0), N_ENC_CONFIGS - 1) : 0;
     for (int i = 0; i < N_ENC_CONFIGS; i++)
         MB_CUDA(cudaFuncSetAttribute(enc_configs[i].kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_configs[i].smem));
+    return MBPE_OK;
+}
+
+extern "C" int mbpe_encoder_create(const uint32_t *merges, uint32_t n_merges, int device, mbpe_encoder **out) {
+    if (!out || (n_merges && !merges)) return set_error(MBPE_E_INVALID, "null argument");
+    *out = nullptr;
+    if (256ull + n_merges > (1ull << ENC_ID_BITS)) return set_error(MBPE_E_INVALID, "vocab larger than 2^21 ids");
+    mbpe_encoder *e = new mbpe_encoder();
+    const int rc = encoder_create_impl(e, merges, n_merges, device);
+    if (rc) { // nothing half-built survives a failure
+        mbpe_encoder_destroy(e);
+        return rc;
+    }
     *out = e;
     return MBPE_OK;
+}
+
+static void free_host_pipe(mbpe_encoder *e) {
+    for (auto &p : e->pipe) {
+        cudaFreeHost(p.h_text);
+        cudaFreeHost(p.h_off);
+        cudaFreeHost(p.h_ids);
+        cudaFreeHost(p.h_out_off);
+        cudaFree(p.d_text);
+        cudaFree(p.d_off);
+        cudaFree(p.d_ids);
+        cudaFree(p.d_out_off);
+        p = mbpe_encoder::HostPipe();
+    }
+    e->pipe_bytes = e->pipe_chunks = 0;
 }
 
 extern "C" void mbpe_encoder_destroy(mbpe_encoder *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     void *ps[] = {e->d_slots, e->d_voff, e->d_vbytes, e->d_vpack, e->d_sp_ids, e->d_sp_off, e->d_sp_bytes, e->d_status, e->d_small,
-                  e->d_n_out, e->d_long_list, e->d_scratch_a, e->d_scratch_b, e->d_cache, e->d_cache_log, e->d_cache_ctr, e->d_cache_arena};
+                  e->d_n_out, e->d_long_list, e->d_scratch_a, e->d_scratch_b, e->d_cache, e->d_cache_small, e->d_cache_log,
+                  e->d_cache_ctr, e->d_cache_arena, e->d_esp_ids, e->d_esp_off, e->d_esp_bytes};
     for (void *p : ps) cudaFree(p);
+    free_host_pipe(e);
+    if (e->pipe_stream) cudaStreamDestroy(e->pipe_stream);
+    cudaGetLastError();
     delete e;
 }
 
@@ -945,62 +535,92 @@ extern "C" int mbpe_encoder_set_specials(mbpe_encoder *e, const uint32_t *ids, c
     cudaFree(e->d_sp_ids);
     cudaFree(e->d_sp_off);
     cudaFree(e->d_sp_bytes);
-    e->n_sp = (uint32_t)sid.size();
+    e->d_sp_ids = e->d_sp_off = nullptr;
+    e->d_sp_bytes = nullptr;
+    e->n_sp = 0;
     MB_CUDA(cudaMalloc(&e->d_sp_ids, std::max<size_t>(sid.size(), 1) * 4));
     MB_CUDA(cudaMalloc(&e->d_sp_off, soff.size() * 4));
     MB_CUDA(cudaMalloc(&e->d_sp_bytes, std::max<size_t>(sb.size(), 1)));
     MB_CUDA(cudaMemcpy(e->d_sp_ids, sid.data(), sid.size() * 4, cudaMemcpyHostToDevice));
     MB_CUDA(cudaMemcpy(e->d_sp_off, soff.data(), soff.size() * 4, cudaMemcpyHostToDevice));
     MB_CUDA(cudaMemcpy(e->d_sp_bytes, sb.data(), sb.size(), cudaMemcpyHostToDevice));
+    e->n_sp = (uint32_t)sid.size();
     return MBPE_OK;
 }
 
 // Special tokens on the encode side (Tokenizer.h:605-650, :667-671): a special token is a chunk of its own that becomes
-// one ready-made id. The device front end marks those chunks (mbpe_pretok_split_device_parts); here their bytes are put
-// into the chunk cache as "these bytes -> this id", so the tile kernel needs no special case. An ordinary chunk can never
-// carry the bytes of a special token (the splitter would have cut it out). The cache is emptied first: it may have
-// learned those bytes as ordinary text before. MBPE_E_UNSUPPORTED: no cache, or a token longer than the cache's keys.
+// one ready-made id. The device front end marks those chunks (mbpe_pretok_split_device_parts); the merge scan matches
+// them by exact compare in its slow path (tile kernel and long-chunk kernel alike), so the ids never depend on a cache.
+// For speed the tokens of up to 31 bytes are also put into the chunk caches as "these bytes -> this id". An ordinary
+// chunk can never carry the bytes of a special token (the splitter would have cut it out). The caches are emptied
+// first: they may have learned those bytes as ordinary text before. Any token length, any count.
 extern "C" int mbpe_encoder_seed_special_chunks(mbpe_encoder *e, const uint32_t *ids, const uint8_t *bytes, const uint64_t *off,
                                                 uint32_t n) {
     if (!e || (n && (!ids || !bytes || !off))) return set_error(MBPE_E_INVALID, "null argument");
     int rc = use_device(e->device);
     if (rc) return rc;
-    e->specials_seeded = false;
-    if (!e->d_cache) return set_error(MBPE_E_UNSUPPORTED, "the chunk cache is disabled");
-    std::vector<CacheLogEntry> log(n);
+    std::vector<uint32_t> soff(n + 1, 0);
+    unsigned long long len_mask = 0;
     for (uint32_t i = 0; i < n; i++) {
         const uint64_t len = off[i + 1] - off[i];
-        if (len == 0 || len > CACHE_MAX_LEN) return set_error(MBPE_E_UNSUPPORTED, "special token longer than 31 bytes");
-        if (n > e->cache_log_cap) return set_error(MBPE_E_UNSUPPORTED, "too many special tokens");
-        CacheLogEntry &le = log[i];
+        if (len == 0 || off[i + 1] - off[0] >= (1ull << 31)) return set_error(MBPE_E_INVALID, "empty or oversized special token");
+        soff[i + 1] = (uint32_t)(off[i + 1] - off[0]);
+        len_mask |= 1ull << std::min<uint64_t>(len, 63);
+    }
+    MB_CUDA(cudaDeviceSynchronize()); // nothing may still be reading the old tables
+    cudaFree(e->d_esp_ids);
+    cudaFree(e->d_esp_off);
+    cudaFree(e->d_esp_bytes);
+    e->d_esp_ids = e->d_esp_off = nullptr;
+    e->d_esp_bytes = nullptr;
+    e->n_esp = 0;
+    e->esp_len_mask = 0;
+    if (n) {
+        MB_CUDA(cudaMalloc(&e->d_esp_ids, (size_t)n * 4));
+        MB_CUDA(cudaMalloc(&e->d_esp_off, ((size_t)n + 1) * 4));
+        MB_CUDA(cudaMalloc(&e->d_esp_bytes, std::max<size_t>(soff[n], 1)));
+        MB_CUDA(cudaMemcpy(e->d_esp_ids, ids, (size_t)n * 4, cudaMemcpyHostToDevice));
+        MB_CUDA(cudaMemcpy(e->d_esp_off, soff.data(), ((size_t)n + 1) * 4, cudaMemcpyHostToDevice));
+        MB_CUDA(cudaMemcpy(e->d_esp_bytes, bytes + off[0], soff[n], cudaMemcpyHostToDevice));
+        e->n_esp = n;
+        e->esp_len_mask = len_mask;
+    }
+    if (!e->d_cache_small) return MBPE_OK;
+    std::vector<CacheLogEntry> log;
+    for (uint32_t i = 0; i < n && log.size() < e->cache_log_cap; i++) {
+        const uint64_t len = off[i + 1] - off[i];
+        if (len > CACHE_MAX_LEN) continue; // matched by the slow path only
+        CacheLogEntry le;
         memset(&le, 0, sizeof le);
         for (uint64_t q = 0; q < len; q++) le.k[q >> 3] |= (uint64_t)bytes[off[i] + q] << ((q & 7) * 8);
         le.k[3] |= len << 56;
         le.n = 1;
         le.ids[0] = ids[i];
+        log.push_back(le);
     }
+    MB_CUDA(cudaMemset(e->d_cache_small, 0, (uint64_t)e->small_slots * sizeof(SmallSlot)));
     MB_CUDA(cudaMemset(e->d_cache, 0, (uint64_t)e->cache_slots * sizeof(CacheSlot)));
     MB_CUDA(cudaMemset(e->d_cache_ctr, 0, 16));
     e->chunks_seen = 0;
-    if (n) {
-        MB_CUDA(cudaMemcpy(e->d_cache_log, log.data(), n * sizeof(CacheLogEntry), cudaMemcpyHostToDevice));
-        const uint32_t cnt = n;
+    if (!log.empty()) {
+        MB_CUDA(cudaMemcpy(e->d_cache_log, log.data(), log.size() * sizeof(CacheLogEntry), cudaMemcpyHostToDevice));
+        const uint32_t cnt = (uint32_t)log.size();
         MB_CUDA(cudaMemcpy(e->d_cache_ctr, &cnt, 4, cudaMemcpyHostToDevice));
-        ChunkCache cc{e->d_cache, e->cache_slots - 1, e->d_cache_log, e->d_cache_ctr, e->cache_log_cap, e->d_cache_ctr + 1,
-                      e->d_cache_arena, e->d_cache_ctr + 2, e->cache_arena_cap};
-        k_cache_insert<<<1, 256>>>(cc);
+        k_cache_insert<<<1, 256>>>(cache_view(e));
         MB_CUDA(cudaGetLastError());
         MB_CUDA(cudaDeviceSynchronize());
     }
-    e->specials_seeded = true;
     return MBPE_OK;
 }
 
 static int ensure_status(mbpe_encoder *e, uint64_t n_tiles) {
     if (n_tiles > e->status_cap) {
         cudaFree(e->d_status);
-        e->status_cap = n_tiles + n_tiles / 4 + 64;
-        MB_CUDA(cudaMalloc(&e->d_status, e->status_cap * 8));
+        e->d_status = nullptr;
+        e->status_cap = 0;
+        const uint64_t cap = n_tiles + n_tiles / 4 + 64;
+        MB_CUDA(cudaMalloc(&e->d_status, cap * 8));
+        e->status_cap = cap;
     }
     return MBPE_OK;
 }
@@ -1014,8 +634,8 @@ extern "C" int mbpe_encode_reserve(mbpe_encoder *e, uint64_t n_bytes, uint64_t n
     const uint64_t max_sb = e->sub_batch_chunks ? e->sub_batch_chunks : ENC_MAX_SUBBATCH;
     if ((rc = ensure_status(e, (std::min(n_chunks, max_sb) + tile_chunks - 1) / tile_chunks + 1))) return rc;
     if (e->long_cap == 0) {
+        MB_CUDA(cudaMalloc(&e->d_long_list, (1 << 16) * 4));
         e->long_cap = 1 << 16;
-        MB_CUDA(cudaMalloc(&e->d_long_list, e->long_cap * 4));
     }
     return MBPE_OK;
 }
@@ -1027,45 +647,15 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
     if (n_bytes >= (1ull << 32)) return set_error(MBPE_E_INVALID, "a device batch must be < 4 GiB of text");
     int rc = mbpe_encode_reserve(e, n_bytes, n_chunks);
     if (rc) return rc;
-    MB_CUDA(cudaMemsetAsync(e->d_small, 0, 16, st));
-    MB_CUDA(cudaMemsetAsync(d_n_out, 0, 8, st));
     if (n_chunks == 0) {
+        MB_CUDA(cudaMemsetAsync(d_n_out, 0, 8, st));
         if (d_out_off) MB_CUDA(cudaMemsetAsync(d_out_off, 0, 8, st));
         return MBPE_OK;
     }
-    EncTable tab{e->d_slots, e->mask};
-    // long chunks (rare: > 64 bytes) are found on the device; the count comes back to size the scratch path
-    unsigned grid = (unsigned)std::min<uint64_t>((n_chunks + 255) / 256, (uint64_t)e->sms * 8);
-    k_encode_find_long<<<grid, 256, 0, st>>>(d_off, n_chunks, e->d_long_list, e->d_small + 1, (uint32_t)e->long_cap);
-    e->launches++;
-    uint32_t n_long = 0;
-    MB_CUDA(cudaMemcpyAsync(&n_long, e->d_small + 1, 4, cudaMemcpyDeviceToHost, st));
-    MB_CUDA(cudaStreamSynchronize(st));
-    if (n_long > e->long_cap) { // list overflowed: grow and redo
-        cudaFree(e->d_long_list);
-        e->long_cap = n_long + 1024;
-        MB_CUDA(cudaMalloc(&e->d_long_list, e->long_cap * 4));
-        MB_CUDA(cudaMemsetAsync(e->d_small + 1, 0, 4, st));
-        k_encode_find_long<<<grid, 256, 0, st>>>(d_off, n_chunks, e->d_long_list, e->d_small + 1, (uint32_t)e->long_cap);
-        e->launches++;
-    }
-    if (n_long) {
-        if (n_bytes + 1 > e->scratch_cap) {
-            cudaFree(e->d_scratch_a);
-            cudaFree(e->d_scratch_b);
-            e->scratch_cap = n_bytes + 1;
-            MB_CUDA(cudaMalloc(&e->d_scratch_a, e->scratch_cap * 4));
-            MB_CUDA(cudaMalloc(&e->d_scratch_b, e->scratch_cap * 4));
-        }
-        k_encode_long<<<(n_long + 63) / 64, 64, 0, st>>>(tab, d_bytes, d_off, e->d_long_list, n_long, e->d_scratch_a,
-                                                         e->d_scratch_b);
-        e->launches++;
-    }
     EncArgs a{};
-    a.tab = tab;
-    a.cache = ChunkCache{e->d_cache, e->cache_slots ? e->cache_slots - 1 : 0, e->d_cache_log, e->d_cache_ctr,
-                         e->cache_log_cap, e->d_cache_ctr ? e->d_cache_ctr + 1 : nullptr, e->d_cache_arena,
-                         e->d_cache_ctr ? e->d_cache_ctr + 2 : nullptr, e->cache_arena_cap};
+    a.tab = EncTable{e->d_slots, e->mask};
+    a.cache = cache_view(e);
+    a.sp = specials_view(e);
     a.bytes = d_bytes;
     a.n_bytes_total = n_bytes;
     a.off = d_off;
@@ -1077,70 +667,109 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
     a.out_off = d_out_off;
     a.status = e->d_status;
     a.ticket = e->d_small;
-    a.scratch_a = e->d_scratch_a;
-    a.scratch_b = e->d_scratch_b;
+    a.long_list = e->d_long_list;
+    a.n_long = e->d_small + 1;
+    a.long_cap = (uint32_t)e->long_cap;
     a.overflow = e->d_small + 2;
     a.miss_count = e->d_small + 3;
+    // cp.async.bulk needs 16-byte aligned sources (device allocations are; offsets into them may not be)
+    a.bulk = ((((uintptr_t)d_bytes) | ((uintptr_t)d_off)) & 15) == 0 && !getenv("MBPE_ENC_NO_BULK");
     if (const char *ab = getenv("MBPE_ENC_ABLATE")) a.ablate = (uint32_t)atoi(ab);
-    // Sub-batches of whole tiles: the cache learns from one sub-batch before the next one starts, and the ids of
-    // sub-batch i+1 continue the stream where sub-batch i ended (*d_n_out).
     const EncConfig &kc = enc_configs[e->cfg];
     const uint64_t ET_CHUNKS = (uint64_t)kc.threads * kc.cpt;
-    // Sub-batch schedule: the cache learns between sub-batches, so a cold encoder starts with small ones (1 M chunks)
-    // and doubles; a warm one (chunks_seen) goes straight to large sub-batches, which amortise the launch tail.
-    uint64_t sb = e->sub_batch_chunks ? e->sub_batch_chunks
-                                      : std::min<uint64_t>(ENC_MAX_SUBBATCH, std::max<uint64_t>(1u << 20, e->chunks_seen));
-    sb = (sb + ET_CHUNKS - 1) / ET_CHUNKS * ET_CHUNKS;
-    for (uint64_t cb = 0; cb < n_chunks;) {
-        a.chunk0 = cb;
-        a.chunk1 = std::min(n_chunks, cb + sb);
-        cb = a.chunk1;
-        e->chunks_seen += a.chunk1 - a.chunk0;
-        if (!e->sub_batch_chunks) sb = std::min<uint64_t>(ENC_MAX_SUBBATCH, sb * 2);
-        const uint64_t n_tiles = (a.chunk1 - a.chunk0 + ET_CHUNKS - 1) / ET_CHUNKS;
-        a.n_tiles = (uint32_t)n_tiles;
-        MB_CUDA(cudaMemsetAsync(e->d_status, 0, n_tiles * 8, st));
-        MB_CUDA(cudaMemsetAsync(e->d_small, 0, 4, st)); // ticket
-        if (a.cache.slots) {
-            k_cache_reset_log<<<1, 1, 0, st>>>(a.cache);
+    uint32_t small[4] = {0, 0, 0, 0};
+    // First launch sequence is optimistic: no chunk is longer than ENC_SHORT_MAX bytes (true for the regex patterns on
+    // ordinary text), so the boundaries are read exactly once. The tile kernel reports the long chunks it meets
+    // instead of encoding them; if there are any, they go through k_encode_long and the sequence runs again.
+    for (int attempt = 0; attempt < 2; attempt++) {
+        MB_CUDA(cudaMemsetAsync(e->d_small, 0, 16, st));
+        MB_CUDA(cudaMemsetAsync(d_n_out, 0, 8, st));
+        // Launches of whole tiles: the caches learn from one launch before the next one starts (a cold encoder starts
+        // with small launches, 1 M chunks, and doubles; a warm one goes straight to large ones), and the ids of launch
+        // i+1 continue the stream where launch i ended (*d_n_out).
+        uint64_t sb = e->sub_batch_chunks ? e->sub_batch_chunks
+                                          : std::min<uint64_t>(ENC_MAX_SUBBATCH, std::max<uint64_t>(1u << 20, e->chunks_seen));
+        sb = (sb + ET_CHUNKS - 1) / ET_CHUNKS * ET_CHUNKS;
+        for (uint64_t cb = 0; cb < n_chunks;) {
+            a.chunk0 = cb;
+            a.chunk1 = std::min(n_chunks, cb + sb);
+            cb = a.chunk1;
+            e->chunks_seen += a.chunk1 - a.chunk0;
+            if (!e->sub_batch_chunks) sb = std::min<uint64_t>(ENC_MAX_SUBBATCH, sb * 2);
+            const uint64_t n_tiles = (a.chunk1 - a.chunk0 + ET_CHUNKS - 1) / ET_CHUNKS;
+            a.n_tiles = (uint32_t)n_tiles;
+            MB_CUDA(cudaMemsetAsync(e->d_status, 0, n_tiles * 8, st));
+            MB_CUDA(cudaMemsetAsync(e->d_small, 0, 4, st)); // ticket
+            if (a.cache.small) {
+                k_cache_reset_log<<<1, 1, 0, st>>>(a.cache);
+                e->launches++;
+            }
+            unsigned g2 = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)e->sms * kc.ctas);
+            cudaLaunchConfig_t lc{};
+            lc.gridDim = dim3(g2);
+            lc.blockDim = dim3(kc.threads);
+            lc.dynamicSmemBytes = kc.smem;
+            lc.stream = st;
+            cudaLaunchAttribute lattr[1];
+            lc.attrs = lattr;
+            lc.numAttrs = 0;
+            if (a.cache.small && e->l2_window_max) {
+                // the text, boundaries and ids stream through L2 once; the randomly probed SMALL cache is what should stay
+                const size_t bytes = std::min((size_t)e->small_slots * sizeof(SmallSlot), e->l2_window_max);
+                lattr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+                lattr[0].val.accessPolicyWindow.base_ptr = e->d_cache_small;
+                lattr[0].val.accessPolicyWindow.num_bytes = bytes;
+                lattr[0].val.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)e->l2_persist_bytes / (double)bytes);
+                lattr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                lattr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                lc.numAttrs = 1;
+            }
+            MB_CUDA(cudaLaunchKernelEx(&lc, kc.kernel, a));
             e->launches++;
+            if (a.cache.small) {
+                k_cache_insert<<<e->sms * 2, 256, 0, st>>>(a.cache);
+                e->launches++;
+            }
         }
-        unsigned g2 = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)e->sms * kc.ctas);
-        cudaLaunchConfig_t lc{};
-        lc.gridDim = dim3(g2);
-        lc.blockDim = dim3(kc.threads);
-        lc.dynamicSmemBytes = kc.smem;
-        lc.stream = st;
-        cudaLaunchAttribute lattr[1];
-        lc.attrs = lattr;
-        lc.numAttrs = 0;
-        if (a.cache.slots && e->l2_window_max) {
-            // the text, boundaries and ids stream through L2 once; the randomly probed chunk cache is what must stay
-            const size_t bytes = std::min((size_t)e->cache_slots * sizeof(CacheSlot), e->l2_window_max);
-            lattr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-            lattr[0].val.accessPolicyWindow.base_ptr = e->d_cache;
-            lattr[0].val.accessPolicyWindow.num_bytes = bytes;
-            lattr[0].val.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)e->l2_persist_bytes / (double)bytes);
-            lattr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            lattr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            lc.numAttrs = 1;
-        }
-        MB_CUDA(cudaLaunchKernelEx(&lc, kc.kernel, a));
-        e->launches++;
-        if (a.cache.slots) {
-            k_cache_insert<<<e->sms * 2, 256, 0, st>>>(a.cache);
-            e->launches++;
-        }
-    }
-    MB_CUDA(cudaGetLastError());
-    if (getenv("MBPE_DEBUG")) {
-        uint32_t small[4];
-        uint32_t ctr[2] = {0, 0};
+        MB_CUDA(cudaGetLastError());
         MB_CUDA(cudaMemcpyAsync(small, e->d_small, 16, cudaMemcpyDeviceToHost, st));
-        if (e->d_cache_ctr) MB_CUDA(cudaMemcpyAsync(ctr, e->d_cache_ctr, 8, cudaMemcpyDeviceToHost, st));
         MB_CUDA(cudaStreamSynchronize(st));
-        fprintf(stderr, "[mbpe] encode: %llu chunks, %u scanned (cache misses), %u long, cache entries %u of %u\n",
-                (unsigned long long)n_chunks, small[3], small[1], ctr[1], e->cache_slots);
+        const uint32_t n_long = small[1];
+        if (attempt == 1 || n_long == 0) break;
+        if (n_long > e->long_cap) { // the report overflowed: find them all again with a list that is large enough
+            cudaFree(e->d_long_list);
+            e->d_long_list = nullptr;
+            e->long_cap = 0;
+            MB_CUDA(cudaMalloc(&e->d_long_list, ((uint64_t)n_long + 1024) * 4));
+            e->long_cap = (uint64_t)n_long + 1024;
+            a.long_list = e->d_long_list;
+            a.long_cap = (uint32_t)e->long_cap;
+            MB_CUDA(cudaMemsetAsync(e->d_small + 1, 0, 4, st));
+            unsigned grid = (unsigned)std::min<uint64_t>((n_chunks + 255) / 256, (uint64_t)e->sms * 8);
+            k_encode_find_long<<<grid, 256, 0, st>>>(d_off, n_chunks, e->d_long_list, e->d_small + 1, (uint32_t)e->long_cap);
+            e->launches++;
+        }
+        if (n_bytes + 1 > e->scratch_cap) {
+            cudaFree(e->d_scratch_a);
+            cudaFree(e->d_scratch_b);
+            e->d_scratch_a = e->d_scratch_b = nullptr;
+            e->scratch_cap = 0;
+            MB_CUDA(cudaMalloc(&e->d_scratch_a, (n_bytes + 1) * 4));
+            MB_CUDA(cudaMalloc(&e->d_scratch_b, (n_bytes + 1) * 4));
+            e->scratch_cap = n_bytes + 1;
+        }
+        k_encode_long<<<(n_long + 63) / 64, 64, 0, st>>>(a.tab, a.sp, d_bytes, d_off, e->d_long_list, n_long, e->d_scratch_a,
+                                                         e->d_scratch_b);
+        e->launches++;
+        a.scratch_a = e->d_scratch_a;
+        a.scratch_b = e->d_scratch_b;
+    }
+    if (getenv("MBPE_DEBUG")) {
+        uint32_t ctr[4] = {0, 0, 0, 0};
+        if (e->d_cache_ctr) MB_CUDA(cudaMemcpy(ctr, e->d_cache_ctr, 16, cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[mbpe] encode: %llu chunks, %u scanned (cache misses), %u long, cache entries small %u of %u, big %u of %u%s\n",
+                (unsigned long long)n_chunks, small[3], small[1], ctr[2], e->small_slots, ctr[1], e->cache_slots,
+                a.bulk ? ", bulk staging" : ", cooperative staging (unaligned buffers)");
     }
     return MBPE_OK;
 }
@@ -1155,6 +784,48 @@ extern "C" int mbpe_encode_device(mbpe_encoder *e, const uint8_t *d_bytes, uint6
                               (cudaStream_t)stream);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// mbpe_encode: host bytes + host u64 chunk offsets in, host ids out. The chunk list is cut into segments of whole
+// chunks; a segment is staged into pinned memory by a few host threads (text copied, offsets narrowed to u32 relative
+// to the segment), goes up, through the merge scan and down into pinned memory, and is copied out to the caller's
+// buffer -- staging of segment k+1 and copy-out of segment k-1 overlap the device work of segment k.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+constexpr uint64_t HP_SEG_BYTES = 32ull << 20, HP_SEG_CHUNKS = 8ull << 20;
+
+int ensure_host_pipe(mbpe_encoder *e, uint64_t seg_bytes, uint64_t seg_chunks, bool want_off) {
+    if (!e->pipe_stream) MB_CUDA(cudaStreamCreateWithFlags(&e->pipe_stream, cudaStreamNonBlocking));
+    const bool have_off = e->pipe[0].h_out_off != nullptr;
+    if (seg_bytes <= e->pipe_bytes && seg_chunks <= e->pipe_chunks && (!want_off || have_off)) return MBPE_OK;
+    const uint64_t nb = std::max(seg_bytes, e->pipe_bytes), nc = std::max(seg_chunks, e->pipe_chunks);
+    free_host_pipe(e);
+    for (auto &p : e->pipe) {
+        MB_CUDA(cudaMallocHost(&p.h_text, std::max<uint64_t>(nb, 16)));
+        MB_CUDA(cudaMallocHost(&p.h_off, (nc + 1) * 4));
+        MB_CUDA(cudaMallocHost(&p.h_ids, std::max<uint64_t>(nb, 16) * 4));
+        MB_CUDA(cudaMalloc(&p.d_text, std::max<uint64_t>(nb, 16)));
+        MB_CUDA(cudaMalloc(&p.d_off, (nc + 1) * 4));
+        MB_CUDA(cudaMalloc(&p.d_ids, std::max<uint64_t>(nb, 16) * 4));
+        if (want_off || have_off) {
+            MB_CUDA(cudaMallocHost(&p.h_out_off, (nc + 1) * 8));
+            MB_CUDA(cudaMalloc(&p.d_out_off, (nc + 1) * 8));
+        }
+    }
+    e->pipe_bytes = nb;
+    e->pipe_chunks = nc;
+    return MBPE_OK;
+}
+
+// run f(part, n_parts) on a few threads (the calling thread is one of them)
+template <class F>
+void on_threads(unsigned n, const F &f) {
+    std::vector<std::thread> th;
+    for (unsigned i = 1; i < n; i++) th.emplace_back([&f, i, n]() { f(i, n); });
+    f(0u, n);
+    for (auto &t : th) t.join();
+}
+} // namespace
+
 extern "C" int mbpe_encode(mbpe_encoder *e, const uint8_t *bytes, uint64_t n_bytes, const uint64_t *chunk_off,
                            uint64_t n_chunks, uint32_t *out_tokens, uint64_t out_cap, uint64_t *n_out,
                            uint64_t *out_off) {
@@ -1164,72 +835,105 @@ extern "C" int mbpe_encode(mbpe_encoder *e, const uint8_t *bytes, uint64_t n_byt
     int rc = use_device(e->device);
     if (rc) return rc;
     *n_out = 0;
-    // batches of whole chunks, < 2 GiB of text each, so offsets fit u32 on the device
-    const uint64_t BATCH = 1ull << 31;
-    uint64_t c0 = 0, produced = 0;
-    std::vector<uint32_t> off32;
-    uint8_t *d_bytes = nullptr;
-    uint32_t *d_off = nullptr, *d_out = nullptr;
-    unsigned long long *d_out_off = nullptr;
-    uint64_t cap_bytes = 0, cap_chunks = 0;
-    int status = MBPE_OK;
-    auto cleanup = [&]() {
-        cudaFree(d_bytes);
-        cudaFree(d_off);
-        cudaFree(d_out);
-        cudaFree(d_out_off);
-    };
     if (out_off) out_off[0] = 0;
-    while (c0 < n_chunks) {
-        uint64_t b0 = chunk_off[c0], c1 = c0;
-        while (c1 < n_chunks && chunk_off[c1 + 1] - b0 <= BATCH) c1++;
-        if (c1 == c0) {
-            if (chunk_off[c0 + 1] - b0 >= (1ull << 32)) {
-                cleanup();
-                return set_error(MBPE_E_INVALID, "a single chunk of 4 GiB or more is not supported");
-            }
-            c1 = c0 + 1;
+    // segments of whole chunks: [seg[k], seg[k+1]) in chunk indices
+    std::vector<uint64_t> seg{0};
+    uint64_t max_b = 0, max_c = 0;
+    for (uint64_t c0 = 0; c0 < n_chunks;) {
+        const uint64_t b0 = chunk_off[c0];
+        // last chunk that still ends inside the byte budget (binary search: the offsets are checked for order below)
+        uint64_t lo = c0 + 1, hi = std::min(n_chunks, c0 + HP_SEG_CHUNKS);
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi + 1) / 2;
+            if (chunk_off[mid] >= b0 && chunk_off[mid] - b0 <= HP_SEG_BYTES)
+                lo = mid;
+            else
+                hi = mid - 1;
         }
-        uint64_t nb = chunk_off[c1] - b0, nc = c1 - c0;
-        off32.resize(nc + 1);
-        for (uint64_t i = 0; i <= nc; i++) {
-            if (i && chunk_off[c0 + i] < chunk_off[c0 + i - 1]) {
-                cleanup();
-                return set_error(MBPE_E_INVALID, "chunk_off not monotonic");
-            }
-            off32[i] = (uint32_t)(chunk_off[c0 + i] - b0);
-        }
-        if (nb > cap_bytes || nc > cap_chunks) {
-            cleanup();
-            cap_bytes = std::max(nb, cap_bytes);
-            cap_chunks = std::max(nc, cap_chunks);
-            MB_CUDA(cudaMalloc(&d_bytes, std::max<uint64_t>(cap_bytes, 1)));
-            MB_CUDA(cudaMalloc(&d_off, (cap_chunks + 1) * 4));
-            MB_CUDA(cudaMalloc(&d_out, std::max<uint64_t>(cap_bytes, 1) * 4));
-            if (out_off) MB_CUDA(cudaMalloc(&d_out_off, (cap_chunks + 1) * 8));
-        }
-        MB_CUDA(cudaMemcpy(d_bytes, bytes + b0, nb, cudaMemcpyHostToDevice));
-        MB_CUDA(cudaMemcpy(d_off, off32.data(), (nc + 1) * 4, cudaMemcpyHostToDevice));
-        rc = encode_device_impl(e, d_bytes, nb, d_off, nc, d_out, nb, (uint64_t *)e->d_n_out, d_out_off, nullptr);
-        if (rc) {
-            cleanup();
-            return rc;
-        }
-        uint64_t n = 0;
-        MB_CUDA(cudaMemcpy(&n, e->d_n_out, 8, cudaMemcpyDeviceToHost));
-        if (out_tokens && produced + n <= out_cap)
-            MB_CUDA(cudaMemcpy(out_tokens + produced, d_out, n * 4, cudaMemcpyDeviceToHost));
-        else
-            status = MBPE_E_CAPACITY;
-        if (out_off) {
-            MB_CUDA(cudaMemcpy(out_off + c0, d_out_off, (nc + 1) * 8, cudaMemcpyDeviceToHost));
-            if (produced)
-                for (uint64_t i = 0; i <= nc; i++) out_off[c0 + i] += produced;
-        }
-        produced += n;
+        const uint64_t c1 = lo;
+        if (chunk_off[c1] < b0) return set_error(MBPE_E_INVALID, "chunk_off not monotonic");
+        if (chunk_off[c1] - b0 >= (1ull << 32)) return set_error(MBPE_E_INVALID, "a single chunk of 4 GiB or more is not supported");
+        max_b = std::max(max_b, chunk_off[c1] - b0);
+        max_c = std::max(max_c, c1 - c0);
+        seg.push_back(c1);
         c0 = c1;
     }
-    cleanup();
+    const size_t n_seg = seg.size() - 1;
+    if (n_seg == 0) return MBPE_OK;
+    if ((rc = ensure_host_pipe(e, max_b, max_c, out_off != nullptr))) return rc;
+    cudaStream_t st = e->pipe_stream;
+    const unsigned n_thr = (unsigned)std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    std::atomic<int> bad_order{0};
+    auto stage_in = [&](size_t k) {
+        auto &p = e->pipe[k & 1];
+        const uint64_t c0 = seg[k], c1 = seg[k + 1], b0 = chunk_off[c0], nb = chunk_off[c1] - b0, nc = c1 - c0;
+        on_threads(nb + nc * 12 > (4u << 20) ? n_thr : 1u, [&](unsigned part, unsigned parts) {
+            const uint64_t x0 = nb * part / parts, x1 = nb * (part + 1) / parts;
+            memcpy(p.h_text + x0, bytes + b0 + x0, x1 - x0);
+            const uint64_t i0 = (nc + 1) * part / parts, i1 = (nc + 1) * (part + 1) / parts;
+            bool bad = false;
+            for (uint64_t i = i0; i < i1; i++) {
+                const uint64_t v = chunk_off[c0 + i];
+                bad |= (i && v < chunk_off[c0 + i - 1]) || v < b0 || v - b0 > nb;
+                p.h_off[i] = (uint32_t)(v - b0);
+            }
+            if (bad) bad_order.store(1);
+        });
+    };
+    uint64_t produced = 0;
+    int status = MBPE_OK;
+    struct Done {
+        uint64_t n_ids, at;
+    };
+    std::vector<Done> done(n_seg);
+    auto stage_out = [&](size_t k) {
+        auto &p = e->pipe[k & 1];
+        const uint64_t c0 = seg[k], nc = seg[k + 1] - c0, n = done[k].n_ids, at = done[k].at;
+        on_threads(n * 4 + (out_off ? nc * 8 : 0) > (4u << 20) ? n_thr : 1u, [&](unsigned part, unsigned parts) {
+            if (out_tokens && at + n <= out_cap) {
+                const uint64_t x0 = n * part / parts, x1 = n * (part + 1) / parts;
+                memcpy(out_tokens + at + x0, p.h_ids + x0, (x1 - x0) * 4);
+            }
+            if (out_off) {
+                const uint64_t i0 = (nc + 1) * part / parts, i1 = (nc + 1) * (part + 1) / parts;
+                for (uint64_t i = i0; i < i1; i++) out_off[c0 + i] = p.h_out_off[i] + at;
+            }
+        });
+    };
+    stage_in(0);
+    std::thread helper;
+    for (size_t k = 0; k < n_seg && rc == MBPE_OK; k++) {
+        if (bad_order.load()) {
+            rc = set_error(MBPE_E_INVALID, "chunk_off not monotonic");
+            break;
+        }
+        auto &p = e->pipe[k & 1];
+        const uint64_t c0 = seg[k], c1 = seg[k + 1], nb = chunk_off[c1] - chunk_off[c0], nc = c1 - c0;
+        // the other buffer pair is free: segment k-1 was copied out before the device work of k-1 ... see below
+        helper = std::thread([&, k]() {
+            if (k >= 1) stage_out(k - 1);
+            if (k + 1 < n_seg) stage_in(k + 1);
+        });
+        cudaError_t ce = cudaMemcpyAsync(p.d_text, p.h_text, nb, cudaMemcpyHostToDevice, st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(p.d_off, p.h_off, (nc + 1) * 4, cudaMemcpyHostToDevice, st);
+        if (ce == cudaSuccess) rc = encode_device_impl(e, p.d_text, nb, p.d_off, nc, p.d_ids, std::max<uint64_t>(nb, 1), (uint64_t *)e->d_n_out, p.d_out_off && out_off ? p.d_out_off : nullptr, st);
+        uint64_t n = 0;
+        if (ce == cudaSuccess && rc == MBPE_OK) ce = cudaMemcpyAsync(&n, e->d_n_out, 8, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess && rc == MBPE_OK) ce = cudaStreamSynchronize(st);
+        if (ce == cudaSuccess && rc == MBPE_OK && n) ce = cudaMemcpyAsync(p.h_ids, p.d_ids, n * 4, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess && rc == MBPE_OK && out_off) ce = cudaMemcpyAsync(p.h_out_off, p.d_out_off, (nc + 1) * 8, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess && rc == MBPE_OK) ce = cudaStreamSynchronize(st);
+        helper.join();
+        if (rc == MBPE_OK && ce != cudaSuccess) rc = cuda_fail(ce, "mbpe_encode pipeline", __FILE__, __LINE__);
+        if (rc) break;
+        done[k] = Done{n, produced};
+        if (!out_tokens || produced + n > out_cap) status = MBPE_E_CAPACITY;
+        produced += n;
+    }
+    if (helper.joinable()) helper.join();
+    if (rc) return rc;
+    if (bad_order.load()) return set_error(MBPE_E_INVALID, "chunk_off not monotonic");
+    stage_out(n_seg - 1);
     *n_out = produced;
     if (status == MBPE_E_CAPACITY) return set_error(status, "out_tokens too small; *n_out holds the needed count");
     return MBPE_OK;

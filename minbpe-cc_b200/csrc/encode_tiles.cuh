@@ -1,0 +1,790 @@
+// encode_tiles.cuh -- k_encode_tiles: the encode merge scan over tiles of chunks (included by encode.cu only).
+//
+// Replaces internal_internal_encode / internal_encode + flatten (Tokenizer.h:325-377, :714-717) for chunks of up to
+// ENC_SHORT_MAX bytes; longer chunks are encoded by k_encode_long into a scratch stream and spliced in here.
+//
+// One tile = THREADS x CPT consecutive chunks, one CTA:
+//   0. thread 0 takes the tile ticket and brings the tile's boundaries and its text window into shared memory with
+//      two bulk asynchronous copies (cp.async.bulk -> the TMA engine, completion on an mbarrier): no registers, no
+//      per-thread load/store instructions. It does so while the other warps are still storing the previous tile.
+//   1. fast path, every thread CPT chunks: chunks of <= 15 bytes (nine in ten) are looked up in the SMALL chunk cache,
+//      "chunk bytes -> ids" in 32-byte slots = one DRAM sector: two independent 16-byte loads per probe, all probes
+//      of a thread in flight together. Everything else goes on the tile's slow list.
+//   2. slow list: special tokens by exact compare, 16..31-byte chunks and chunks with more than 4 ids through the BIG
+//      chunk cache (64-byte slots), the rest by the multi-pass scan itself (one warp per chunk when few, one thread per
+//      chunk when many); scanned chunks are appended to a log that k_cache_insert folds into the caches between launches.
+//   3. block scan of the id counts; warp 0 resolves the tile's place in the flat stream by decoupled look-back (128
+//      predecessors per round trip) while the other warps gather the tile's ids in shared memory; the ids leave as
+//      whole lines.
+// Results never depend on the caches: a miss is scanned, and special tokens are matched in the slow path itself.
+#pragma once
+#include "lookback.cuh"
+
+namespace mbpe {
+
+// ---------------------------------------------------------------------------------------------------------
+// mbarrier + bulk asynchronous copy (global -> shared through the TMA engine; SASS: UBLKCP + SYNCS)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBPE_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBPE_DONE_%=;\n"
+        "bra MBPE_WAIT_%=;\n"
+        "MBPE_DONE_%=:\n"
+        "}\n" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+// the one-pass streams (text, boundaries) should not push the randomly probed cache tables out of L2
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// bytes: multiple of 16; dst and src 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy)
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Chunk caches. The multi-pass scan of a chunk is a pure function of its bytes, and text repeats its chunks (Zipf):
+// the encoder keeps "chunk bytes -> ids" in two open-addressed tables in HBM.
+//   SMALL: chunks of <= 15 bytes with <= 4 ids, 32-byte slots {key 16 B, ids 16 B} = one sector per probe.
+//   BIG:   chunks of <= 31 bytes (any id count, > 7 ids in an arena), 64-byte slots.
+// The tile kernel only READS them; chunks it had to scan go to a log, and k_cache_insert adds the log to the tables
+// between launches -- no kernel both reads and writes a table, so there is no publication protocol to get wrong.
+// Results are bit-identical with or without the caches (MBPE_ENCODE_CACHE=0 disables them; tests run both).
+// ---------------------------------------------------------------------------------------------------------
+struct SmallSlot { // 32 bytes
+    uint32_t k[4]; // bytes 0..14 little endian, zero padded; k[3] bits 24..27 = length (1..15), bits 28..30 = id count;
+                   // k[3] == 0: empty
+    uint32_t v[4]; // the ids
+};
+static_assert(sizeof(SmallSlot) == 32, "one sector per entry");
+constexpr uint32_t SMALL_MAX_LEN = 15, SMALL_MAX_IDS = 4, SMALL_KEY_MASK = 0x0FFFFFFFu;
+
+struct CacheSlot { // 64 bytes = two sectors: key, value
+    uint64_t k[4]; // chunk bytes, little endian, zero padded; top byte of k[3] = length (1..31); k[3] == 0: empty
+    uint32_t n;    // number of ids (1..31)
+    uint32_t v[7]; // n <= 7: the ids; otherwise v[0] = offset of the ids in the arena
+};
+static_assert(sizeof(CacheSlot) == 64, "two sectors per entry");
+struct CacheLogEntry {
+    uint64_t k[4]; // BIG-table key layout
+    uint32_t n;
+    uint32_t ids[31];
+};
+constexpr uint32_t CACHE_MAX_LEN = 31, CACHE_INLINE_IDS = 7;
+
+struct ChunkCache {
+    SmallSlot *small; // nullptr = caches disabled
+    uint32_t small_shift; // slot = hash >> small_shift
+    uint32_t small_mask;
+    CacheSlot *slots;
+    uint32_t mask;       // slots - 1
+    CacheLogEntry *log;  // chunks the current launch had to scan
+    uint32_t *log_count;
+    uint32_t log_cap;
+    uint32_t *used;      // [0] occupied BIG slots, [1] occupied SMALL slots (learning stops at half full)
+    uint32_t *arena;     // ids of BIG entries with more than CACHE_INLINE_IDS ids
+    uint32_t *arena_used;
+    uint32_t arena_cap;
+};
+
+__host__ __device__ __forceinline__ uint32_t small_hash(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+    const uint64_t lo = ((uint64_t)w1 << 32) | w0, hi = ((uint64_t)w3 << 32) | w2;
+    const uint64_t m = hi * 0x9E3779B97F4A7C15ull;
+    const uint64_t x = lo ^ ((m >> 32) | (m << 32));
+    return (uint32_t)((x * 0xD6E8FEB86659FD93ull) >> 32); // callers use the TOP bits: they depend on every key bit
+}
+__host__ __device__ __forceinline__ uint32_t cache_hash(uint64_t k0, uint64_t k1, uint64_t k2, uint64_t k3) {
+    uint64_t h = (k0 ^ (k1 * 0x9E3779B97F4A7C15ull)) * 0xff51afd7ed558ccdULL;
+    h ^= (k2 * 0xc2b2ae3d27d4eb4fULL) ^ (k3 * 0x165667b19e3779f9ULL);
+    h ^= h >> 32;
+    h *= 0xc4ceb9fe1a85ec53ULL;
+    return (uint32_t)(h >> 32);
+}
+
+__global__ void k_cache_insert(ChunkCache cc) {
+    const uint32_t n = min(*cc.log_count, cc.log_cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const CacheLogEntry &e = cc.log[i];
+        const uint64_t k0 = e.k[0], k1 = e.k[1], k2 = e.k[2], k3 = e.k[3];
+        const uint32_t en = e.n, len = (uint32_t)(k3 >> 56);
+        if (len <= SMALL_MAX_LEN && en <= SMALL_MAX_IDS) {
+            if (*((volatile uint32_t *)(cc.used + 1)) * 2 > cc.small_mask) continue; // half full: stop learning
+            const uint32_t w0 = (uint32_t)k0, w1 = (uint32_t)(k0 >> 32), w2 = (uint32_t)k1;
+            const uint32_t w3 = (uint32_t)(k1 >> 32) | (len << 24); // byte 15 is free: len <= 15
+            uint32_t h = small_hash(w0, w1, w2, w3) >> cc.small_shift;
+            for (;;) {
+                SmallSlot *s = &cc.small[h];
+                uint32_t cur = *((volatile uint32_t *)&s->k[3]);
+                if (cur == 0) {
+                    cur = atomicCAS(&s->k[3], 0u, w3 | (en << 28));
+                    if (cur == 0) { // claimed: k[3] is the claim word, the rest is written by the winner only
+                        s->k[0] = w0;
+                        s->k[1] = w1;
+                        s->k[2] = w2;
+                        for (uint32_t q = 0; q < SMALL_MAX_IDS; q++) s->v[q] = q < en ? e.ids[q] : 0u;
+                        atomicAdd(cc.used + 1, 1u);
+                        break;
+                    }
+                }
+                // Same key: already there (the log holds duplicates of hot chunks). Words of a slot claimed in THIS launch
+                // may not be visible yet; then the duplicate takes a second slot -- harmless, both slots hold the same ids
+                // and a reader uses the first one it finds.
+                if ((cur & SMALL_KEY_MASK) == w3 && *((volatile uint32_t *)&s->k[0]) == w0 &&
+                    *((volatile uint32_t *)&s->k[1]) == w1 && *((volatile uint32_t *)&s->k[2]) == w2)
+                    break;
+                h = (h + 1) & cc.small_mask;
+            }
+            continue;
+        }
+        if (*((volatile uint32_t *)cc.used) * 2 > cc.mask) continue; // half full: stop learning
+        uint32_t h = cache_hash(k0, k1, k2, k3) & cc.mask;
+        for (;;) {
+            unsigned long long *claim = reinterpret_cast<unsigned long long *>(&cc.slots[h].k[3]);
+            unsigned long long cur = *((volatile unsigned long long *)claim);
+            if (cur == 0) {
+                uint32_t aoff = 0;
+                if (en > CACHE_INLINE_IDS) { // reserve arena room BEFORE claiming, so a claimed slot is always completed
+                    aoff = atomicAdd(cc.arena_used, en);
+                    if (aoff + en > cc.arena_cap) break;
+                }
+                cur = atomicCAS(claim, 0ull, (unsigned long long)k3);
+                if (cur == 0) {
+                    cc.slots[h].k[0] = k0;
+                    cc.slots[h].k[1] = k1;
+                    cc.slots[h].k[2] = k2;
+                    cc.slots[h].n = en;
+                    if (en <= CACHE_INLINE_IDS) {
+                        for (uint32_t q = 0; q < en; q++) cc.slots[h].v[q] = e.ids[q];
+                    } else {
+                        cc.slots[h].v[0] = aoff;
+                        for (uint32_t q = 0; q < en; q++) cc.arena[aoff + q] = e.ids[q];
+                    }
+                    atomicAdd(cc.used, 1u);
+                    break;
+                }
+            }
+            if (cur == k3 && *((volatile uint64_t *)&cc.slots[h].k[0]) == k0 &&
+                *((volatile uint64_t *)&cc.slots[h].k[1]) == k1 && *((volatile uint64_t *)&cc.slots[h].k[2]) == k2)
+                break;
+            h = (h + 1) & cc.mask;
+        }
+    }
+}
+__global__ void k_cache_reset_log(ChunkCache cc) { *cc.log_count = 0; }
+
+// ---------------------------------------------------------------------------------------------------------
+// special tokens on the encode side (Tokenizer.h:667-671): a chunk with exactly these bytes is this one id
+// ---------------------------------------------------------------------------------------------------------
+struct EncSpecials {
+    const uint32_t *ids;
+    const uint32_t *off; // n + 1 offsets into bytes
+    const uint8_t *bytes;
+    uint32_t n;
+    unsigned long long len_mask; // bit min(length, 63) set for every token length present
+};
+template <class ByteAt>
+__device__ __forceinline__ uint32_t special_match(const EncSpecials &sp, uint32_t len, ByteAt at) {
+    if (sp.n == 0 || !((sp.len_mask >> (len < 63u ? len : 63u)) & 1ull)) return ENC_NONE;
+    for (uint32_t s = 0; s < sp.n; s++) {
+        const uint32_t b = __ldg(&sp.off[s]);
+        if (__ldg(&sp.off[s + 1]) - b != len) continue;
+        uint32_t i = 0;
+        while (i < len && __ldg(&sp.bytes[b + i]) == at(i)) i++;
+        if (i == len) return __ldg(&sp.ids[s]);
+    }
+    return ENC_NONE;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_encode_tiles
+// ---------------------------------------------------------------------------------------------------------
+struct EncArgs {
+    EncTable tab;
+    ChunkCache cache;
+    EncSpecials sp;
+    uint64_t chunk0, chunk1;   // this launch covers chunks [chunk0, chunk1) in tiles
+    const unsigned long long *stream_base; // ids produced by earlier launches of this call (device word) = base of tile 0
+    const uint8_t *bytes;
+    uint64_t n_bytes_total; // bytes readable from `bytes`
+    const uint32_t *off;
+    uint64_t n_chunks;
+    uint32_t *out;
+    uint64_t out_cap;
+    unsigned long long *d_n_out;
+    unsigned long long *out_off; // optional per-chunk token offsets (n_chunks + 1)
+    unsigned long long *status;  // look-back words, one per tile, zeroed
+    uint32_t *ticket;            // zeroed
+    uint32_t n_tiles;
+    const uint32_t *scratch_a;   // long-chunk tokens / counts; null = no long pre-pass was run (optimistic launch)
+    const uint32_t *scratch_b;
+    uint32_t *long_list;         // optimistic launch: chunks longer than ENC_SHORT_MAX are reported here
+    uint32_t *n_long;
+    uint32_t long_cap;
+    uint32_t *overflow;          // set when out_cap is too small
+    uint32_t *miss_count;        // chunks that went through the scan (statistics)
+    uint32_t bulk;               // bytes / off are 16-byte aligned: stage with cp.async.bulk
+    uint32_t ablate;             // MBPE_ENC_ABLATE (profiling only; 1, 2, 4 give WRONG results): 1 no look-back wait,
+                                 // 2 no cache probe (every short chunk "hits" with two fake ids), 4 no id stores
+};
+
+constexpr uint32_t TILE_NONE = 0xFFFFFFFFu;
+constexpr uint64_t ENC_MAX_SUBBATCH = 1ull << 26; // chunks per launch at most (tile ids and look-back words are 32-bit safe)
+constexpr uint32_t META_NONE = 0xFFFFF;       // scanned chunk whose ids did not fit the parking area
+constexpr uint32_t META_PENDING = 0xFFFFFFFFu; // slow-list entry not resolved by the BIG cache: needs the scan
+constexpr uint32_t ET_WARP_SCAN_MAX = 64;     // up to this many scans per tile run one warp per chunk
+
+template <int THREADS, int CPT>
+struct EncSmemT {
+    static constexpr int TILE = THREADS * CPT;
+    static constexpr int TEXT_CAP = TILE * 10;  // staged text bytes per tile (average chunk ~5 bytes); wider tiles read HBM
+    static constexpr int STAGE = TILE * 5 / 2;  // ids gathered per tile (average ~2.1 per chunk); more: direct stores
+    static constexpr int PARK = TILE;           // ids of slow-list chunks parked until the tile knows its place
+    alignas(128) uint32_t off[TILE + 8];
+    alignas(128) uint32_t text[TEXT_CAP / 4 + 16]; // + halo: key assembly reads whole words past the chunk's end
+    uint32_t stage[STAGE];
+    uint32_t park[PARK];
+    uint32_t meta[TILE];       // per slow-list entry: start in park (20 bits) | id count << 20
+    uint16_t slow[TILE];       // slow list: chunk index within the tile
+    uint16_t scan[TILE];       // of those, the entries that need the scan (slow-list positions)
+    uint4 len_mask[16];        // len_mask[l] keeps the first l bytes of a 16-byte key
+    uint32_t warp_scratch[THREADS / 32][32];
+    uint32_t warp_sum[THREADS / 32];
+    alignas(8) uint64_t bar_off, bar_tile; // mbarriers: boundaries landed (thread 0 only waits), tile ready (all wait)
+    unsigned long long base;
+    uint32_t tile, a0, staged, n_slow, n_scan, park_used;
+};
+
+template <class SM>
+__device__ __forceinline__ uint8_t tile_byte(const EncArgs &a, const SM &sm, bool staged, uint32_t a0, uint32_t g) {
+    return staged ? reinterpret_cast<const uint8_t *>(sm.text)[g - a0] : __ldg(&a.bytes[g]);
+}
+
+// scan one chunk (<= ENC_SHORT_MAX bytes) into t[]; returns the id count
+template <class SM>
+__device__ __forceinline__ uint32_t scan_chunk(const EncArgs &a, const SM &sm, bool staged, uint32_t a0, uint32_t o,
+                                               uint32_t len, uint32_t *t) {
+    const uint32_t sid = special_match(a.sp, len, [&](uint32_t i) { return tile_byte(a, sm, staged, a0, o + i); });
+    if (sid != ENC_NONE) {
+        t[0] = sid;
+        return 1;
+    }
+    for (uint32_t i = 0; i < len; i++) t[i] = tile_byte(a, sm, staged, a0, o + i);
+    bool merged = true;
+    while (merged && len >= 2) len = enc_pass(a.tab, t, len, merged);
+    return len;
+}
+
+// One warp scans one chunk of <= 32 bytes: lane i holds token i. Per pass every lane looks its pair up at once (one
+// lookup latency per pass instead of one per position); the left-to-right non-overlapping rule of
+// Tokenizer.h:336-359 is applied to the ballot mask: inside each maximal run of mergeable positions the 1st, 3rd,
+// 5th... merge. Runs are separated by parity of their start bit with the carry trick
+//   runs_even = F & ~(F + even_starts),   runs_odd = F & ~(F + odd_starts)
+// (bit 31 of F is always clear: lane 31 has no right neighbour, so the additions cannot overflow).
+// Returns the final length; on return lane i < length holds id i in `tok`. `scratch` = 32 words of shared memory
+// owned by the warp.
+__device__ __forceinline__ uint32_t scan_chunk_warp(const EncTable &tab, uint32_t &tok, uint32_t len, uint32_t *scratch) {
+    const uint32_t lane = threadIdx.x & 31;
+    while (len >= 2) {
+        const uint32_t nxt = __shfl_down_sync(0xffffffffu, tok, 1);
+        uint32_t id = ENC_NONE;
+        if (lane + 1 < len) id = enc_lookup_id(tab, tok, nxt);
+        const uint32_t F = __ballot_sync(0xffffffffu, id != ENC_NONE);
+        if (F == 0) break;
+        const uint32_t starts = F & ~(F << 1);
+        const uint32_t runs_even = F & ~(F + (starts & 0x55555555u));
+        const uint32_t runs_odd = F & ~(F + (starts & 0xAAAAAAAAu));
+        const uint32_t M = (runs_even & 0x55555555u) | (runs_odd & 0xAAAAAAAAu); // heads of merged pairs
+        const uint32_t valid = len >= 32 ? 0xffffffffu : ((1u << len) - 1);
+        const uint32_t keep = valid & ~(M << 1);                                   // tails disappear
+        if ((keep >> lane) & 1u) scratch[__popc(keep & ((1u << lane) - 1))] = ((M >> lane) & 1u) ? id : tok;
+        __syncwarp();
+        len = __popc(keep);
+        tok = lane < len ? scratch[lane] : 0u;
+        __syncwarp();
+    }
+    return len;
+}
+
+// BIG-table key of chunk [o, o + len), len <= 31: bytes little endian, zero padded, length in the top byte
+template <class SM>
+__device__ __forceinline__ void big_key(const EncArgs &a, const SM &sm, bool staged, uint32_t a0, uint32_t o, uint32_t len,
+                                        uint64_t *key) {
+    key[0] = key[1] = key[2] = key[3] = 0;
+    for (uint32_t i = 0; i < len; i++) key[i >> 3] |= (uint64_t)tile_byte(a, sm, staged, a0, o + i) << ((i & 7) * 8);
+    key[3] |= (uint64_t)len << 56;
+}
+
+template <class SM>
+__device__ __forceinline__ void log_scanned(const EncArgs &a, const SM &sm, bool staged, uint32_t a0, uint32_t o,
+                                            uint32_t len, const uint32_t *ids, uint32_t n) {
+    if (!a.cache.small || len > CACHE_MAX_LEN) return;
+    const uint32_t li = atomicAdd(a.cache.log_count, 1u);
+    if (li >= a.cache.log_cap) return;
+    CacheLogEntry &e = a.cache.log[li];
+    uint64_t key[4];
+    big_key(a, sm, staged, a0, o, len, key);
+    e.k[0] = key[0];
+    e.k[1] = key[1];
+    e.k[2] = key[2];
+    e.k[3] = key[3];
+    e.n = n;
+    for (uint32_t i = 0; i < n; i++) e.ids[i] = ids[i];
+}
+
+// thread 0: ticket, then the tile's boundaries and text window into shared memory by bulk copies.
+// Publishes sm.tile / sm.a0 / sm.staged and completes sm.bar_tile when everything has landed.
+template <class SM>
+__device__ __forceinline__ void fetch_tile_bulk(const EncArgs &a, SM &sm, uint32_t &off_parity, uint64_t policy) {
+    const uint32_t t = atomicAdd(a.ticket, 1u); // tiles start in order: look-back cannot deadlock
+    if (t >= a.n_tiles) {
+        sm.tile = TILE_NONE;
+        mbar_arrive(&sm.bar_tile);
+        return;
+    }
+    const uint64_t c0 = a.chunk0 + (uint64_t)t * SM::TILE;
+    const uint32_t nc = (uint32_t)min((uint64_t)SM::TILE, a.chunk1 - c0);
+    const uint32_t nw = nc + 1, nb = nw & ~3u; // whole 16-byte vectors by bulk copy, the last <= 3 words by hand
+    if (nb) {
+        mbar_arrive_expect_tx(&sm.bar_off, nb * 4);
+        bulk_g2s(sm.off, a.off + c0, nb * 4, &sm.bar_off, policy);
+    } else {
+        mbar_arrive(&sm.bar_off);
+    }
+    for (uint32_t i = nb; i < nw; i++) sm.off[i] = __ldg(&a.off[c0 + i]);
+    mbar_wait(&sm.bar_off, off_parity);
+    off_parity ^= 1;
+    const uint32_t b0 = sm.off[0], b1 = sm.off[nc];
+    const uint32_t a0 = b0 & ~15u; // 16-byte aligned window start
+    const uint32_t span = b1 - a0;
+    const bool staged = span <= (uint32_t)SM::TEXT_CAP;
+    sm.tile = t;
+    sm.a0 = a0;
+    sm.staged = staged;
+    if (staged) {
+        // whole vectors that lie inside the buffer by bulk copy, the last (< 16) bytes of the buffer by hand
+        const uint64_t avail = (a.n_bytes_total - a0) & ~15ull;
+        const uint32_t full = (uint32_t)min((uint64_t)((span + 15) & ~15u), avail);
+        for (uint32_t g = a0 + full; g < b1; g++) reinterpret_cast<uint8_t *>(sm.text)[g - a0] = __ldg(&a.bytes[g]);
+        if (full) {
+            mbar_arrive_expect_tx(&sm.bar_tile, full);
+            bulk_g2s(sm.text, a.bytes + a0, full, &sm.bar_tile, policy);
+            return;
+        }
+    }
+    mbar_arrive(&sm.bar_tile);
+}
+
+// The tile's slow list, by all threads of the CTA (contains barriers). Kept out of line: its register needs (31-byte
+// keys, id arrays) must not be charged to the fast path, which runs for nine chunks in ten.
+//   2a. one thread per entry: special tokens by exact compare; a chunk of <= 15 bytes continues its probe sequence in
+//       the SMALL cache; then the BIG cache;
+//   2b. what is still unknown is scanned: one WARP per chunk when few (warm caches: latency matters), one THREAD per
+//       chunk when many (cold caches: throughput matters) and for chunks of 33..64 bytes.
+// Result per entry q: sm.meta[q] = start in sm.park (META_NONE: did not fit) | id count << 20.
+template <int THREADS, class SM>
+__device__ __noinline__ void resolve_slow_list(const EncArgs &a, SM &sm, uint32_t a0, bool staged, uint32_t n_slow) {
+    constexpr int NW = THREADS / 32;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool use_cache = a.cache.small != nullptr && !(a.ablate & 2);
+    for (uint32_t q = tid; q < n_slow; q += THREADS) {
+        const uint32_t k = sm.slow[q], so = sm.off[k], len = sm.off[k + 1] - so;
+        uint32_t n = 0, start = META_NONE;
+        const uint32_t *src = nullptr;
+        uint32_t one[CACHE_INLINE_IDS];
+        const uint32_t sid = special_match(a.sp, len, [&](uint32_t i) { return tile_byte(a, sm, staged, a0, so + i); });
+        if (sid != ENC_NONE) {
+            one[0] = sid;
+            n = 1;
+        } else if (use_cache && len <= CACHE_MAX_LEN) {
+            uint64_t key[4];
+            big_key(a, sm, staged, a0, so, len, key);
+            if (len <= SMALL_MAX_LEN) { // the whole probe sequence again (the fast path only looked at the home slot)
+                const uint32_t w0 = (uint32_t)key[0], w1 = (uint32_t)(key[0] >> 32), w2 = (uint32_t)key[1];
+                const uint32_t w3 = (uint32_t)(key[1] >> 32) | (len << 24);
+                uint32_t h = small_hash(w0, w1, w2, w3) >> a.cache.small_shift;
+                for (;;) {
+                    const uint4 *sp = reinterpret_cast<const uint4 *>(&a.cache.small[h]);
+                    const uint4 kq = __ldg(sp);
+                    if (kq.w == 0) break;
+                    if ((kq.w & SMALL_KEY_MASK) == w3 && kq.x == w0 && kq.y == w1 && kq.z == w2) {
+                        const uint4 vq = __ldg(sp + 1);
+                        n = kq.w >> 28;
+                        one[0] = vq.x, one[1] = vq.y, one[2] = vq.z, one[3] = vq.w;
+                        break;
+                    }
+                    h = (h + 1) & a.cache.small_mask;
+                }
+            }
+            if (n == 0) {
+                uint32_t h = cache_hash(key[0], key[1], key[2], key[3]) & a.cache.mask;
+                for (;;) {
+                    const ulonglong2 *sp = reinterpret_cast<const ulonglong2 *>(&a.cache.slots[h]);
+                    const ulonglong2 lo = __ldg(sp), hi = __ldg(sp + 1);
+                    if (hi.y == 0) break;
+                    if (hi.y == key[3] && hi.x == key[2] && lo.x == key[0] && lo.y == key[1]) {
+                        const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(sp + 2)); // n, v[0..2]
+                        n = v0.x;
+                        if (n <= CACHE_INLINE_IDS) {
+                            const uint4 v1 = __ldg(reinterpret_cast<const uint4 *>(sp + 3));
+                            one[0] = v0.y, one[1] = v0.z, one[2] = v0.w, one[3] = v1.x, one[4] = v1.y, one[5] = v1.z, one[6] = v1.w;
+                        } else {
+                            src = a.cache.arena + v0.y;
+                        }
+                        break;
+                    }
+                    h = (h + 1) & a.cache.mask;
+                }
+            }
+        }
+        if (n == 0) { // not known: the scan decides
+            sm.meta[q] = META_PENDING;
+            sm.scan[atomicAdd(&sm.n_scan, 1u)] = (uint16_t)q;
+            continue;
+        }
+        const uint32_t at = atomicAdd(&sm.park_used, n);
+        if (at + n <= (uint32_t)SM::PARK) {
+            start = at;
+            for (uint32_t i = 0; i < n; i++) sm.park[at + i] = src ? __ldg(&src[i]) : one[i];
+        }
+        sm.meta[q] = start | (n << 20);
+    }
+    __syncthreads();
+    const uint32_t n_scan = sm.n_scan;
+    if (n_scan == 0) return;
+    if (tid == 0) atomicAdd(a.miss_count, n_scan);
+    const bool by_warp = n_scan <= ET_WARP_SCAN_MAX;
+    if (by_warp) {
+        for (uint32_t s = warp; s < n_scan; s += NW) {
+            const uint32_t q = sm.scan[s], k = sm.slow[q], so = sm.off[k], mlen = sm.off[k + 1] - so;
+            if (mlen > 32) continue; // 33..64 bytes: serial scan below
+            uint32_t tok = lane < mlen ? tile_byte(a, sm, staged, a0, so + lane) : 0u;
+            const uint32_t mn = scan_chunk_warp(a.tab, tok, mlen, sm.warp_scratch[warp]); // lane i < mn: id i in tok
+            uint32_t start = 0;
+            if (lane == 0) start = atomicAdd(&sm.park_used, mn);
+            start = __shfl_sync(0xffffffffu, start, 0);
+            if (start + mn <= (uint32_t)SM::PARK) {
+                if (lane < mn) sm.park[start + lane] = tok;
+            } else {
+                start = META_NONE;
+            }
+            if (lane == 0) sm.meta[q] = start | (mn << 20);
+            if (a.cache.small && mlen <= CACHE_MAX_LEN) { // teach the caches
+                uint32_t li = 0;
+                if (lane == 0) li = atomicAdd(a.cache.log_count, 1u);
+                li = __shfl_sync(0xffffffffu, li, 0);
+                if (li < a.cache.log_cap) {
+                    CacheLogEntry &e = a.cache.log[li];
+                    if (lane < mn) e.ids[lane] = tok;
+                    if (lane == 0) {
+                        uint64_t key[4];
+                        big_key(a, sm, staged, a0, so, mlen, key);
+                        e.k[0] = key[0];
+                        e.k[1] = key[1];
+                        e.k[2] = key[2];
+                        e.k[3] = key[3];
+                        e.n = mn;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    for (uint32_t s = tid; s < n_scan; s += THREADS) {
+        const uint32_t q = sm.scan[s], k = sm.slow[q], so = sm.off[k], mlen = sm.off[k + 1] - so;
+        if (by_warp && mlen <= 32) continue;
+        uint32_t t[ENC_SHORT_MAX];
+        const uint32_t mn = scan_chunk(a, sm, staged, a0, so, mlen, t);
+        uint32_t start = atomicAdd(&sm.park_used, mn);
+        if (start + mn <= (uint32_t)SM::PARK) {
+            for (uint32_t i = 0; i < mn; i++) sm.park[start + i] = t[i];
+        } else {
+            start = META_NONE; // no room: the owner scans it again when writing
+        }
+        sm.meta[q] = start | (mn << 20);
+        log_scanned(a, sm, staged, a0, so, mlen, t, mn);
+    }
+    __syncthreads();
+}
+
+// ids of a slow-list chunk that did not fit the parking area: resolve it again, straight into place (rare)
+template <class SM>
+__device__ __noinline__ void rescan_into(const EncArgs &a, const SM &sm, uint32_t a0, bool staged, uint32_t o, uint32_t len,
+                                         uint32_t *dst, uint32_t n) {
+    uint32_t t[ENC_SHORT_MAX];
+    scan_chunk(a, sm, staged, a0, o, len, t);
+    for (uint32_t i = 0; i < n; i++) dst[i] = t[i];
+}
+
+// one chunk's ids -> dst[0 .. n) (shared-memory gather buffer, or the stream itself for oversized tiles)
+template <class SM>
+__device__ __forceinline__ void emit_chunk(const EncArgs &a, const SM &sm, uint32_t a0, bool staged, uint32_t n, uint32_t slowq,
+                                           uint32_t o0, uint32_t o1, uint4 v, uint32_t *dst, uint64_t room) {
+    if (n == 0) return;
+    if (n > room) {
+        *a.overflow = 1;
+        return;
+    }
+    if (slowq == TILE_NONE) {
+        if (o1 - o0 > ENC_SHORT_MAX) {
+            for (uint32_t i = 0; i < n; i++) dst[i] = a.scratch_a[o0 + i];
+        } else {
+            dst[0] = v.x;
+            if (n > 1) dst[1] = v.y;
+            if (n > 2) dst[2] = v.z;
+            if (n > 3) dst[3] = v.w;
+        }
+    } else {
+        const uint32_t start = sm.meta[slowq] & 0xFFFFF;
+        if (start != META_NONE) {
+            for (uint32_t i = 0; i < n; i++) dst[i] = sm.park[start + i];
+        } else {
+            rescan_into(a, sm, a0, staged, o0, o1 - o0, dst, n);
+        }
+    }
+}
+
+template <int THREADS, int CPT, int MIN_CTAS>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArgs a) {
+    using SM = EncSmemT<THREADS, CPT>;
+    constexpr int TILE = SM::TILE, NW = THREADS / 32;
+    extern __shared__ __align__(128) unsigned char enc_smem_raw[];
+    SM &sm = *reinterpret_cast<SM *>(enc_smem_raw);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool bulk = a.bulk != 0;
+    if (tid < 16) { // len_mask[l]: ones over the first l bytes
+        uint32_t m[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int nb = (int)tid - 4 * q;
+            m[q] = nb >= 4 ? 0xFFFFFFFFu : nb <= 0 ? 0u : ((1u << (8 * nb)) - 1);
+        }
+        sm.len_mask[tid] = make_uint4(m[0], m[1], m[2], m[3]);
+    }
+    if (tid == 0) {
+        mbar_init(&sm.bar_off, 1);
+        mbar_init(&sm.bar_tile, 1);
+        mbar_init_fence();
+        sm.n_slow = 0;
+        sm.n_scan = 0;
+        sm.park_used = 0;
+    }
+    __syncthreads();
+    uint32_t tile_parity = 0, off_parity = 0;
+    uint64_t policy = 0;
+    if (bulk && tid == 0) {
+        policy = l2_evict_first_policy();
+        fetch_tile_bulk(a, sm, off_parity, policy);
+    }
+    for (;;) {
+        // ---- 0. the tile's boundaries and text in shared memory ----------------------------------------------------
+        if (bulk) {
+            mbar_wait(&sm.bar_tile, tile_parity);
+            tile_parity ^= 1;
+        } else { // unaligned caller buffers: ticket and cooperative loads
+            __syncthreads();
+            if (tid == 0) {
+                const uint32_t t = atomicAdd(a.ticket, 1u);
+                sm.tile = t < a.n_tiles ? t : TILE_NONE;
+                sm.n_slow = 0;
+                sm.n_scan = 0;
+                sm.park_used = 0;
+            }
+            __syncthreads();
+        }
+        const uint32_t tile = sm.tile;
+        if (tile == TILE_NONE) return;
+        const uint64_t c0 = a.chunk0 + (uint64_t)tile * TILE;
+        const uint32_t nc = (uint32_t)min((uint64_t)TILE, a.chunk1 - c0);
+        if (!bulk) {
+            for (uint32_t i = tid; i <= nc; i += THREADS) sm.off[i] = __ldg(&a.off[c0 + i]);
+            __syncthreads();
+            const uint32_t b0 = sm.off[0], b1 = sm.off[nc], w0 = b0 & ~3u;
+            const bool st = (b1 - w0) <= (uint32_t)SM::TEXT_CAP;
+            if (st) // byte loads: nothing is known about the alignment of the buffer
+                for (uint32_t g = b0 + tid; g < b1; g += THREADS) reinterpret_cast<uint8_t *>(sm.text)[g - w0] = __ldg(&a.bytes[g]);
+            __syncthreads();
+            if (tid == 0) {
+                sm.a0 = w0;
+                sm.staged = st;
+            }
+            __syncthreads();
+        }
+        const uint32_t a0 = sm.a0;
+        const bool staged = sm.staged != 0;
+        // ---- 1. fast path: the home slot of every chunk in the SMALL cache, all of a thread's probes in flight ------
+        uint32_t o[CPT + 1];
+#pragma unroll
+        for (int j = 0; j <= CPT; j++) o[j] = sm.off[min(tid * CPT + j, nc)];
+        uint32_t cnt[CPT];
+        uint32_t slowq[CPT]; // place on the slow list, or TILE_NONE: cnt / vq are final
+        uint4 vq[CPT];       // hit: the chunk's ids
+        const bool keyed = a.cache.small != nullptr && staged; // (an unstaged tile -- very long chunks -- goes to the slow list)
+        if (keyed && !(a.ablate & 2)) {
+            uint4 kw[CPT], kq[CPT];
+#pragma unroll
+            for (int j = 0; j < CPT; j++) {
+                const uint32_t len = o[j + 1] - o[j];
+                // the 16 bytes at the chunk's start, bytes at and after `len` cleared, length in the top byte
+                const uint32_t r = o[j] - a0, wi = r >> 2, sh = (r & 3) * 8;
+                const uint4 lm = sm.len_mask[len & 15];
+                const uint32_t t0 = sm.text[wi], t1 = sm.text[wi + 1], t2 = sm.text[wi + 2], t3 = sm.text[wi + 3], t4 = sm.text[wi + 4];
+                kw[j].x = __funnelshift_r(t0, t1, sh) & lm.x;
+                kw[j].y = __funnelshift_r(t1, t2, sh) & lm.y;
+                kw[j].z = __funnelshift_r(t2, t3, sh) & lm.z;
+                kw[j].w = (__funnelshift_r(t3, t4, sh) & lm.w) | (len << 24);
+                const uint32_t h = small_hash(kw[j].x, kw[j].y, kw[j].z, kw[j].w) >> a.cache.small_shift;
+                const uint4 *sp = reinterpret_cast<const uint4 *>(&a.cache.small[h]); // (empty / long chunks probe too:
+                kq[j] = __ldg(sp);                                                      //  the answer is ignored)
+                vq[j] = __ldg(sp + 1);
+            }
+#pragma unroll
+            for (int j = 0; j < CPT; j++) {
+                const uint32_t len = o[j + 1] - o[j];
+                const bool hit = len - 1u < SMALL_MAX_LEN && (kq[j].w & SMALL_KEY_MASK) == kw[j].w && kq[j].x == kw[j].x &&
+                                 kq[j].y == kw[j].y && kq[j].z == kw[j].z;
+                cnt[j] = hit ? kq[j].w >> 28 : 0u;
+                slowq[j] = hit ? TILE_NONE : 0u; // 0: undecided, see below
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < CPT; j++) {
+                cnt[j] = 0;
+                slowq[j] = 0;
+                vq[j] = make_uint4(0, 0, 0, 0);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < CPT; j++) {
+            if (slowq[j] == TILE_NONE) continue; // hit
+            slowq[j] = TILE_NONE;
+            const uint32_t k = tid * CPT + j, len = o[j + 1] - o[j];
+            if (k >= nc || len == 0) continue;
+            if (len > ENC_SHORT_MAX) {
+                if (a.scratch_b) {
+                    cnt[j] = a.scratch_b[o[j]]; // encoded by k_encode_long
+                } else {                         // optimistic launch: report it, the host runs the long path and repeats
+                    const uint32_t q = atomicAdd(a.n_long, 1u);
+                    if (q < a.long_cap) a.long_list[q] = (uint32_t)(c0 + k);
+                }
+                continue;
+            }
+            if (a.ablate & 2) {
+                cnt[j] = 2;
+                vq[j].x = o[j];
+                vq[j].y = len;
+                continue;
+            }
+            const uint32_t q = atomicAdd(&sm.n_slow, 1u);
+            sm.slow[q] = (uint16_t)k;
+            slowq[j] = q;
+        }
+        __syncthreads();
+        // ---- 2. slow list ----------------------------------------------------------------------------------------------
+        {
+            const uint32_t n_slow = sm.n_slow;
+            if (n_slow) resolve_slow_list<THREADS>(a, sm, a0, staged, n_slow);
+        }
+        uint32_t sum = 0;
+#pragma unroll
+        for (int j = 0; j < CPT; j++) {
+            if (slowq[j] != TILE_NONE) cnt[j] = sm.meta[slowq[j]] >> 20;
+            sum += cnt[j];
+        }
+        // ---- 3. place in the stream: block exclusive scan + look-back; ids gathered in shared memory ------------------
+        uint32_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (lane == 31) sm.warp_sum[warp] = incl;
+        __syncthreads();
+        uint32_t warp_base = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            const uint32_t v = sm.warp_sum[w];
+            if (w < (int)warp) warp_base += v;
+            total += v;
+        }
+        if (warp == 0) { // the other warps gather their ids meanwhile
+            const uint64_t b = (a.ablate & 1) ? (uint64_t)tile * (TILE * 9 / 4)
+                                              : lookback_base<4>(a.status, tile, total, a.stream_base);
+            if (lane == 0) sm.base = b;
+        }
+        const bool via_smem = total <= (uint32_t)SM::STAGE;
+        const uint32_t loc0 = warp_base + (incl - sum);
+        if (via_smem && !(a.ablate & 4)) {
+            uint32_t loc = loc0;
+#pragma unroll
+            for (int j = 0; j < CPT; j++) {
+                emit_chunk(a, sm, a0, staged, cnt[j], slowq[j], o[j], o[j + 1], vq[j], sm.stage + loc, ~0ull);
+                loc += cnt[j];
+            }
+        }
+        __syncthreads();
+        const uint64_t base = sm.base;
+        if (!via_smem && !(a.ablate & 4)) { // a tile with more ids than the gather buffer holds: every thread stores its own
+            uint32_t loc = loc0;
+#pragma unroll
+            for (int j = 0; j < CPT; j++) {
+                const uint64_t at = base + loc;
+                emit_chunk(a, sm, a0, staged, cnt[j], slowq[j], o[j], o[j + 1], vq[j], a.out + at, at < a.out_cap ? a.out_cap - at : 0);
+                loc += cnt[j];
+            }
+            __syncthreads(); // (emit may read the tile's text and lists: they are replaced below)
+        }
+        // ---- 4. the next tile's loads start now; this tile's ids leave as whole lines --------------------------------
+        if (bulk && tid == 0) {
+            sm.n_slow = 0; // (everybody is past the slow list; the next tile's appends come after the next mbarrier wait)
+            sm.n_scan = 0;
+            sm.park_used = 0;
+            fetch_tile_bulk(a, sm, off_parity, policy);
+        }
+        if (a.out_off) {
+            uint32_t loc = loc0;
+#pragma unroll
+            for (int j = 0; j < CPT; j++) {
+                const uint32_t k = tid * CPT + j;
+                if (k < nc) a.out_off[c0 + k] = base + loc;
+                loc += cnt[j];
+            }
+        }
+        if (via_smem && !(a.ablate & 4)) {
+            if (base + total <= a.out_cap) {
+                uint32_t *const gout = a.out + base;
+                for (uint32_t i = tid; i < total; i += THREADS) __stcs(&gout[i], sm.stage[i]);
+            } else {
+                for (uint32_t i = tid; i < total; i += THREADS)
+                    if (base + i < a.out_cap) a.out[base + i] = sm.stage[i];
+                if (tid == 0) *a.overflow = 1;
+            }
+        }
+        if (tile == a.n_tiles - 1 && tid == 0) {
+            *a.d_n_out = base + total;
+            if (a.out_off && a.chunk1 == a.n_chunks) a.out_off[a.n_chunks] = base + total;
+        }
+    }
+}
+
+} // namespace mbpe

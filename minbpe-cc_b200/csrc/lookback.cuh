@@ -1,5 +1,5 @@
 // lookback.cuh -- single-pass ordered placement of variable-sized tile outputs (decoupled look-back), shared by the
-// encode kernel (ids of a tile) and the pre-tokeniser (chunk starts of a tile).
+// encode kernel (ids of a tile), the decode kernel (bytes of a tile) and the pre-tokeniser (chunk starts of a tile).
 #pragma once
 #include <stdint.h>
 
@@ -10,8 +10,11 @@ namespace mbpe {
 // ---------------------------------------------------------------------------------------------------------
 constexpr uint64_t LB_AGG = 1ull << 62, LB_PREFIX = 2ull << 62, LB_VAL = (1ull << 62) - 1;
 
-// Called by all 32 lanes of one warp. Each round inspects 32 predecessors at once (one L2 round trip), so a tile
-// that starts while hundreds of older tiles are still in flight resolves its base in ~14 rounds, not ~440 serial loads.
+// Called by all 32 lanes of one warp. Each round inspects 32 * W predecessors at once (W independent loads per lane,
+// one L2 round trip), so a tile that starts while several hundred older tiles are still in flight resolves its base
+// in a handful of rounds instead of hundreds of serial loads. W = 1 is the round-1 behaviour; the tile kernels of
+// encode and decode use W = 4 (128 predecessors per round trip: with ~900 tiles in flight the walk is <= 8 rounds).
+template <int W = 1>
 __device__ __forceinline__ uint64_t lookback_base(unsigned long long *status, uint32_t tile, uint64_t total,
                                                   const unsigned long long *first_base = nullptr) {
     const uint32_t lane = threadIdx.x & 31;
@@ -22,31 +25,37 @@ __device__ __forceinline__ uint64_t lookback_base(unsigned long long *status, ui
     }
     if (lane == 0) atomicExch(&status[tile], LB_AGG | total);
     uint64_t acc = 0;
-    int64_t j = (int64_t)tile - 1; // lane l looks at tile j - l
+    int64_t j = (int64_t)tile - 1; // lane l, word w looks at tile j - (w * 32 + l): nearest predecessors first
     for (;;) {
-        const int64_t idx = j - lane;
-        unsigned long long v = LB_PREFIX; // tiles before 0 do not exist: tile 0 always ends the walk itself
-        if (idx >= 0) {
-            do {
-                v = *((volatile unsigned long long *)&status[idx]);
-            } while ((v >> 62) == 0);
+        unsigned long long v[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            const int64_t idx = j - (w * 32 + (int)lane);
+            // tiles before 0 do not exist: tile 0 always ends the walk itself
+            v[w] = idx >= 0 ? *((volatile unsigned long long *)&status[idx]) : LB_PREFIX;
         }
-        const unsigned pm = __ballot_sync(0xffffffffu, (v & LB_PREFIX) != 0);
-        uint64_t val = v & LB_VAL;
-        if (pm) {
-            const int first = __ffs(pm) - 1; // nearest predecessor that already knows its inclusive prefix
-            if ((int)lane > first || idx < 0) val = 0;
+        bool done = false;
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            const int64_t idx = j - (w * 32 + (int)lane);
+            if (idx >= 0)
+                while ((v[w] >> 62) == 0) v[w] = *((volatile unsigned long long *)&status[idx]); // not published yet
+            const unsigned pm = __ballot_sync(0xffffffffu, (v[w] & LB_PREFIX) != 0);
+            uint64_t val = v[w] & LB_VAL;
+            if (pm) {
+                const int first = __ffs(pm) - 1; // nearest predecessor that already knows its inclusive prefix
+                if ((int)lane > first || idx < 0) val = 0;
+                done = true;
+            }
             for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
             acc += val;
-            break;
+            if (done) break;
         }
-        for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
-        acc += val;
-        j -= 32;
+        if (done) break;
+        j -= 32 * W;
     }
     if (lane == 0) atomicExch(&status[tile], LB_PREFIX | (acc + total));
     return acc;
 }
-
 
 } // namespace mbpe

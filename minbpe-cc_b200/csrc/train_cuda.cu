@@ -649,12 +649,9 @@ struct CudaBE {
     }
     void init_count(const Ctx &c) {
         if (err != cudaSuccess) return;
-        static bool attr_set = false;
-        if (!attr_set) {
-            note(cudaFuncSetAttribute(k_init_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IcSmem)),
-                 "smem attr");
-            attr_set = true;
-        }
+        // the attribute belongs to the current device's context: set it on every launch (it is cheap), so a process
+        // that trains on device 0 and then on device 1 works
+        note(cudaFuncSetAttribute(k_init_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IcSmem)), "smem attr");
         uint64_t tiles = ((uint64_t)c.n_pos + IC_THREADS * IC_ITEMS - 1) / (IC_THREADS * IC_ITEMS);
         unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)sms * 2));
         k_init_count<<<grid, IC_THREADS, sizeof(IcSmem), stream>>>(c);
@@ -663,12 +660,8 @@ struct CudaBE {
     }
     void persistent(const Ctx &c) {
         if (err != cudaSuccess) return;
-        static bool attr_set = false;
-        if (!attr_set) {
-            note(cudaFuncSetAttribute(k_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PersistSmem)),
-                 "smem attr");
-            attr_set = true;
-        }
+        note(cudaFuncSetAttribute(k_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PersistSmem)),
+             "smem attr"); // per device, see init_count
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(1);
         cfg.blockDim = dim3(PERSISTENT_THREADS);

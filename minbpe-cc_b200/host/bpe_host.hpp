@@ -27,6 +27,7 @@ class Regex {
     ~Regex();
     Regex(const Regex &) = delete;
     Regex &operator=(const Regex &) = delete;
+    Regex &operator=(Regex &&o) noexcept;
     // options as the reference picks them (Tokenizer.h:407-415); JIT always (results do not depend on it)
     int compile(const std::string &pattern, std::string *err);
     bool empty() const { return code_ == nullptr; }
@@ -132,6 +133,7 @@ class Tokenizer {
     mbpe_encoder *encoder_ = nullptr;
     mbpe_pretok *pretok_ = nullptr; // device matcher of the GPT-4 pattern, created on first use
     bool pretok_failed_ = false;
+    std::string pretok_pattern_;     // the pattern the device matcher was last told to match
     bool specials_on_device_ = false; // the encoder knows the special tokens as ready-made chunks
     bool encoder_stale_ = true;
     int device_ = 0, engine_ = MBPE_ENGINE_PERSISTENT, n_threads_ = 0;

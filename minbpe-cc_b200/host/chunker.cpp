@@ -26,6 +26,15 @@ Regex::~Regex() {
     if (code_) pcre2_code_free_8(code_);
 }
 
+Regex &Regex::operator=(Regex &&o) noexcept {
+    if (this != &o) {
+        if (code_) pcre2_code_free_8(code_);
+        code_ = o.code_;
+        o.code_ = nullptr;
+    }
+    return *this;
+}
+
 int Regex::compile(const std::string &pattern, std::string *err) {
     if (code_) {
         pcre2_code_free_8(code_);

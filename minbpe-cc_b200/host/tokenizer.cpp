@@ -41,10 +41,22 @@ static uint64_t gpu_split_min_bytes() {
 bool Tokenizer::use_gpu_split(size_t n_bytes) {
     if ((pattern_ != kGpt4Pattern && pattern_ != kGpt2Pattern) || n_bytes < gpu_split_min_bytes()) return false;
     if (!pretok_ && !pretok_failed_) {
-        if (mbpe_pretok_create(device_, &pretok_) != MBPE_OK || mbpe_pretok_select(pretok_, pattern_.c_str()) != MBPE_OK) {
+        if (mbpe_pretok_create(device_, &pretok_) != MBPE_OK) {
             if (pretok_) mbpe_pretok_destroy(pretok_);
             pretok_ = nullptr;
             pretok_failed_ = true;
+        }
+        pretok_pattern_.clear();
+    }
+    // load() may have replaced the pattern since the matcher was set up (Tokenizer.h:782-814 recompiles the regex):
+    // the device matcher must follow, or large texts would split under the old pattern and small ones under the new
+    if (pretok_ && pretok_pattern_ != pattern_) {
+        if (mbpe_pretok_select(pretok_, pattern_.c_str()) != MBPE_OK) {
+            mbpe_pretok_destroy(pretok_);
+            pretok_ = nullptr;
+            pretok_failed_ = true;
+        } else {
+            pretok_pattern_ = pattern_;
         }
     }
     return pretok_ != nullptr;
@@ -513,35 +525,46 @@ int Tokenizer::load(const std::string &path, bool verbose) {
         error_ = "unexpected version line";
         return MBPE_E_IO;
     }
-    merges_.clear();
-    std::getline(in, pattern_);
-    if (regex_.compile(pattern_, &error_) != MBPE_OK) {
+    // Everything is parsed into locals and committed only when the whole file was good: a failed load leaves the
+    // tokenizer exactly as it was (the reference returns false half-way with its members already overwritten).
+    std::string new_pattern;
+    std::getline(in, new_pattern);
+    Regex new_regex;
+    if (new_regex.compile(new_pattern, &error_) != MBPE_OK) {
         std::cerr << "PCRE2 compilation failed on load: " << error_ << "\n";
         return MBPE_E_REGEX;
     }
     int num_special = 0;
     in >> num_special;
-    for (int i = 0; i < num_special; i++) { // existing specials are kept, as in the reference
+    std::vector<std::pair<std::string, Token>> new_specials;
+    for (int i = 0; i < num_special; i++) {
         std::string token;
         Token id;
         in >> token >> id;
-        special_tokens_[token] = id;
-        special_reverse_[id] = token;
+        new_specials.emplace_back(token, id);
         if (verbose) std::cout << "Loaded special token: " << token << " with ID " << id << "\n";
     }
+    std::vector<std::pair<Token, Token>> new_merges;
     Token a, b;
     while (in >> a >> b) {
-        if (a >= 256 + merges_.size() || b >= 256 + merges_.size()) { // the reference would index past vocab
+        if (a >= 256 + new_merges.size() || b >= 256 + new_merges.size()) { // the reference would index past vocab
             error_ = "merge line names an id that does not exist yet";
             return MBPE_E_IO;
         }
-        merges_.emplace_back(a, b);
+        new_merges.emplace_back(a, b);
     }
+    pattern_ = std::move(new_pattern);
+    regex_ = std::move(new_regex);
+    for (auto &[token, id] : new_specials) { // existing specials are kept, as in the reference
+        special_tokens_[token] = id;
+        special_reverse_[id] = token;
+    }
+    merges_ = std::move(new_merges);
     if (verbose) std::cout << "Read input model from " << path << "\n";
     rebuild_vocab();
     if (verbose)
         std::cout << "Loaded vocab with " << merges_.size() << " merges, vocab size is " << vocab_.size() << "\n";
-    encoder_stale_ = true;
+    encoder_stale_ = true; // device tables, and (use_gpu_split) the device matcher's pattern, follow on next use
     return MBPE_OK;
 }
 

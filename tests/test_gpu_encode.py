@@ -164,3 +164,129 @@ def test_cli_end_to_end(pkg, manifest, tmp_path):
     run("-e", "-i", f"{data}/specialtokensample.txt", "-m", m2, "-o", str(tmp_path / "t.enc"))
     run("-d", "-i", str(tmp_path / "t.enc"), "-m", m2, "-o", str(tmp_path / "t.txt"))
     assert (tmp_path / "t.txt").read_bytes() == golden_data("specialtokensample.txt")
+
+
+def _long_chunk_text(n_bytes, specials, seed=5):
+    """text whose chunks average well over 10 bytes (CJK runs, long identifiers, URLs) with special tokens sprinkled in:
+    the tile kernel cannot stage such tiles in shared memory and takes its slow path for every chunk"""
+    rng = np.random.default_rng(seed)
+    cjk = "".join(chr(int(c)) for c in rng.integers(0x4E00, 0x9FA5, 4000))
+    parts, size = [], 0
+    while size < n_bytes:
+        k = int(rng.integers(0, 5))
+        if k == 0:
+            a = int(rng.integers(0, 3900))
+            p = cjk[a:a + int(rng.integers(8, 30))]
+        elif k == 1:
+            p = "https://example.org/" + "".join(rng.choice(list("abcdefghij_"), int(rng.integers(20, 60))))
+        elif k == 2:
+            p = "".join(rng.choice(list("ABCDEFabcdef"), int(rng.integers(16, 40))))
+        elif k == 3:
+            p = specials[int(rng.integers(0, len(specials)))]
+        else:
+            p = " " if rng.random() < 0.7 else "\n"
+        parts.append(p)
+        size += len(p.encode())
+    return "".join(parts).encode()
+
+
+def test_special_tokens_in_long_chunk_text_and_of_any_length(pkg, monkeypatch):
+    """specials must come out as their ids wherever they sit -- in tiles too wide for shared memory,
+    with the caches off, and when the token itself is longer than a cache key (31 bytes) or than ENC_SHORT_MAX (64)."""
+    specials = ["<|endoftext|>", "<|fim_prefix|>", "<|a_special_token_that_is_longer_than_31_bytes|>",
+                "<|" + "x" * 80 + "|>"]
+    contents = "".join(f"{s} {100257 + i}\n" for i, s in enumerate(specials))
+    text = _long_chunk_text(3 << 20, specials)
+    train_text = pkg.synth_corpus(0x5EED0011, 4 << 20).tobytes() + text[: 1 << 20]
+    results = {}
+    for name, env in (("device", {}), ("device_nocache", {"MBPE_ENCODE_CACHE": "0"}), ("host_split", {"MBPE_GPU_SPLIT": "0"})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        tk = pkg.Tokenizer(pkg.patterns()["gpt4"])
+        tk.train(train_text, 256 + 600, "lexical")
+        tk.set_special_tokens_from_file(contents)
+        ids = tk.encode(text)
+        assert tk.decode(ids) == text
+        results[name] = ids
+        for k in env:
+            monkeypatch.delenv(k)
+        tk.close()
+    assert np.array_equal(results["device"], results["host_split"])
+    assert np.array_equal(results["device_nocache"], results["host_split"])
+    for i, s in enumerate(specials):  # every occurrence became its one id (the host path resolves them on the host)
+        assert int((results["device"] == 100257 + i).sum()) == text.count(s.encode()) > 0
+
+
+def test_load_reselects_the_device_matcher(pkg, tmp_path, monkeypatch):
+    """load() replaces the pattern; large texts must then split under the NEW pattern on
+    the device too. GPT-2 and GPT-4 split "Hello's 12345   world" differently, so a stale matcher shows in the ids."""
+    text = pkg.synth_corpus(0x5EED0012, 2 << 20).tobytes() + b" it's 1234567 HELLO'S   x\n" * 4000
+    t2 = pkg.Tokenizer(pkg.patterns()["gpt2"])
+    t2.train(text, 256 + 300, "lexical")
+    t2.save(tmp_path / "gpt2.model")
+    tk = pkg.Tokenizer(pkg.patterns()["gpt4"])
+    tk.train(text, 256 + 50, "lexical")  # the device matcher now matches the GPT-4 pattern
+    tk.load(tmp_path / "gpt2.model")
+    ids = tk.encode(text)
+    assert np.array_equal(ids, t2.encode(text))
+    monkeypatch.setenv("MBPE_GPU_SPLIT", "0")
+    th = pkg.Tokenizer(pkg.patterns()["gpt4"])
+    th.load(tmp_path / "gpt2.model")
+    assert np.array_equal(ids, th.encode(text))
+    monkeypatch.delenv("MBPE_GPU_SPLIT")
+    # and training after the load follows the loaded pattern as well
+    tk.train(text, 256 + 300, "lexical")
+    assert np.array_equal(tk.merges(), t2.merges())
+
+
+def test_unaligned_device_buffers_take_the_cooperative_path(pkg, oracle):
+    """mbpe_encode_device with text / boundary pointers that are not 16-byte aligned (no bulk copies possible)"""
+    import torch
+    _, _, merges = oracle.read_model(os.path.join(GOLDEN, "models", "shk4096_gpt4_lexical_special.model"))
+    text = golden_data("shakespeare.txt")
+    s, e = oracle.split(text, oracle.GPT4_SPLIT_PATTERN)
+    off32 = np.concatenate([s, e[-1:]]).astype(np.uint32)
+    oids, _ = oracle.encode_chunks(merges, text, s, e)
+    dev = torch.device("cuda", 0)
+    enc = pkg.Encoder(merges)
+    for shift_b, shift_o in ((0, 0), (1, 0), (0, 1), (3, 3)):
+        d_bytes = torch.zeros(len(text) + 64, dtype=torch.uint8, device=dev)
+        d_bytes[shift_b:shift_b + len(text)] = torch.from_numpy(np.frombuffer(text, np.uint8).copy()).to(dev)
+        d_off = torch.zeros(len(off32) + 8, dtype=torch.int32, device=dev)
+        d_off[shift_o:shift_o + len(off32)] = torch.from_numpy(off32.view(np.int32).copy()).to(dev)
+        d_out = torch.zeros(len(text), dtype=torch.int32, device=dev)
+        d_n = torch.zeros(1, dtype=torch.int64, device=dev)
+        enc.encode_device(d_bytes.data_ptr() + shift_b, len(text), d_off.data_ptr() + 4 * shift_o, len(s), d_out.data_ptr(),
+                          len(text), d_n.data_ptr())
+        torch.cuda.synchronize()
+        n = int(d_n.item())
+        assert n == len(oids) and np.array_equal(d_out[:n].cpu().numpy().view(np.uint32), oids), (shift_b, shift_o)
+    enc.close()
+
+
+def test_encode_is_the_same_for_every_kernel_shape_and_without_caches(pkg, oracle, monkeypatch):
+    """every k_encode_tiles configuration, bulk and cooperative staging, caches on / off / tiny: identical ids, cold and warm"""
+    text = pkg.synth_corpus(0x5EED0013, 6 << 20).tobytes() + golden_data("sample.txt") * 20
+    tok, off, w, _ = pkg.split_dedup(pkg.patterns()["gpt4"], text[: 4 << 20])
+    merges, _, _ = pkg.train(tok, off, w, 256 + 3000, "lexical")
+    s, e = pkg.split(pkg.patterns()["gpt4"], text)
+    chunk_off = np.concatenate([s, e[-1:]]).astype(np.uint64)
+    cut = text.rfind(b"\nq", 0, 1 << 20) + 1 or (1 << 20)
+    so, eo = oracle.split(text[:cut], oracle.GPT4_SPLIT_PATTERN)
+    oids, _ = oracle.encode_chunks(merges, text[:cut], so, eo)
+    ref = None
+    envs = [{"MBPE_ENC_CFG": str(c)} for c in range(8)] + [{"MBPE_ENC_NO_BULK": "1"}, {"MBPE_ENCODE_CACHE": "0"},
+                                                            {"MBPE_ENCODE_CACHE": "12"}, {"MBPE_ENCODE_SUBBATCH": "8192"}]
+    for env in envs:
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        enc = pkg.Encoder(merges)
+        for rep in range(2):  # cold caches, then warm
+            ids = enc.encode(text, chunk_off)
+            if ref is None:
+                ref = ids
+                assert np.array_equal(ids[:len(oids)], oids)
+            assert np.array_equal(ids, ref), (env, rep)
+        enc.close()
+        for k in env:
+            monkeypatch.delenv(k)

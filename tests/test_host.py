@@ -170,3 +170,26 @@ def test_special_split_one_sweep_matches_reference_rule(pkg):
     assert parts == O.split_on_special(big, specials)
     assert pkg.special_split(b"", b"plain") == [(0, 5, -1)]
     assert pkg.special_split(contents, b"") == [(0, 0, -1)]
+
+
+def test_failed_load_leaves_the_tokenizer_as_it_was(pkg, tmp_path):
+    """load() parses into locals and commits only a wholly good file"""
+    good = os.path.join(GOLDEN, "models", "ts512_gpt4_lexical.model")
+    tk = pkg.Tokenizer(pkg.patterns()["gpt2"])
+    tk.load(good)
+    before = tk.merges()
+    assert len(before) == 256
+    lines = open(good, "rb").read().split(b"\n")
+    bad_merge = tmp_path / "bad_merge.model"
+    bad_merge.write_bytes(b"\n".join(lines[:40] + [b"999999 5"] + lines[40:]))
+    bad_regex = tmp_path / "bad_regex.model"
+    bad_regex.write_bytes(b"\n".join([lines[0], b"(unclosed"] + lines[2:]))
+    bad_version = tmp_path / "bad_version.model"
+    bad_version.write_bytes(b"minbpe v9\n" + b"\n".join(lines[1:]))
+    for p in (bad_merge, bad_regex, bad_version, tmp_path / "missing.model"):
+        with pytest.raises(pkg.MbpeError):
+            tk.load(p)
+        assert np.array_equal(tk.merges(), before)
+    out = tmp_path / "again.model"
+    tk.save(out)  # pattern, specials and merges still those of the good file: byte-identical model
+    assert out.read_bytes() == open(good, "rb").read()
