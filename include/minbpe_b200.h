@@ -109,14 +109,36 @@ int mbpe_train(const uint32_t *tokens, uint64_t n_tokens, const uint64_t *chunk_
                uint32_t *n_merges_out);
 
 /* Sharded training, one process per GPU. Rank r owns a contiguous, token-balanced share of the unique
- * chunks and a full replica of the pair table with GLOBAL counts; every merge step all-gathers the ranks' count
- * deltas over NCCL/NVLink, so every rank picks the same pair with no broadcast and ends with the same merge list.
+ * chunks and a full replica of the pair table with GLOBAL counts; every merge step the ranks exchange their count
+ * deltas over NVLink, so every rank picks the same pair with no broadcast and ends with the same merge list.
+ * MBPE_ENGINE_PERSISTENT: one resident CTA per rank runs the merges back to back and does the exchange itself -- it
+ * stores its records straight into the peers' memory (mapped with cudaIpc by mbpe_comm_create) and polls the flag words
+ * the peers store into its own; only rebuilds and the few early merges with very large counts are driven from the host.
+ * MBPE_ENGINE_STEPWISE (or no peer mapping: mbpe_comm_resident() == 0): grid kernels + one NCCL all-gather per merge.
  * Every rank passes the SAME deduplicated corpus. The 128-byte id comes from rank 0 (mbpe_comm_unique_id) and
  * reaches the other ranks by any means (torch.distributed broadcast in bench.py). NCCL is loaded at run time. */
 typedef struct mbpe_comm mbpe_comm;
 int mbpe_comm_unique_id(uint8_t *id_out /* 128 bytes */);
 int mbpe_comm_create(const uint8_t *id /* 128 bytes */, int rank, int world, int device, mbpe_comm **out);
+int mbpe_comm_resident(const mbpe_comm *c); /* 1: every rank mapped every peer: the resident exchange is available */
 void mbpe_comm_destroy(mbpe_comm *c);
+/* this rank's share of the corpus uploaded once; run() can be repeated (what bench.py times at N > 1) */
+typedef struct mbpe_sharded_trainer mbpe_sharded_trainer;
+int mbpe_sharded_trainer_create(mbpe_comm *comm, const uint32_t *tokens, uint64_t n_tokens, const uint64_t *chunk_off,
+                                uint64_t n_chunks, const uint32_t *chunk_weight, mbpe_sharded_trainer **out);
+int mbpe_sharded_trainer_run(mbpe_sharded_trainer *t, uint32_t vocab_size, int mode, int engine, void *stream,
+                             uint32_t *merges_out, int32_t *counts_out, uint32_t *n_merges_out, mbpe_train_stats *stats);
+void mbpe_sharded_trainer_destroy(mbpe_sharded_trainer *t);
+/* Tokenizer::train over a text that is sharded over the ranks ("shard what shards naturally"): rank r passes
+ * ITS contiguous part of the text (parts in rank order, cut at chunk boundaries); every rank splits and deduplicates its
+ * part on its GPU, one all-gather moves the unique chunks (bytes + offsets + weights), every rank merges them into the
+ * same corpus (first-appearance order of the whole text) and runs the merge loop on it -- identical merge list on every
+ * rank, no per-merge communication. GPT-2 / GPT-4 patterns (the device front end); MBPE_E_UNSUPPORTED as mbpe_pretok_corpus. */
+typedef struct mbpe_pretok mbpe_pretok;
+int mbpe_train_text_sharded(mbpe_comm *comm, mbpe_pretok *p, const uint8_t *text_part, uint64_t len, uint32_t vocab_size, int mode,
+                            uint32_t *merges_out, int32_t *counts_out, uint32_t *n_merges_out, mbpe_train_stats *stats,
+                            double *front_end_s /* optional: split + dedup + gather + merge */);
+/* one-shot with host buffers: create + run (resident engine when available) + destroy */
 int mbpe_train_sharded(mbpe_comm *comm, const uint32_t *tokens, uint64_t n_tokens, const uint64_t *chunk_off,
                        uint64_t n_chunks, const uint32_t *chunk_weight, uint32_t vocab_size, int mode, void *stream,
                        uint32_t *merges_out, int32_t *counts_out, uint32_t *n_merges_out, mbpe_train_stats *stats);
@@ -145,6 +167,7 @@ int mbpe_encode(mbpe_encoder *e, const uint8_t *bytes, uint64_t n_bytes, const u
 int mbpe_encode_device(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t n_bytes, const uint32_t *d_chunk_off32,
                        uint64_t n_chunks, uint32_t *d_out_tokens, uint64_t out_cap, uint64_t *d_n_out,
                        void *stream);
+uint64_t mbpe_encoder_launches(const mbpe_encoder *e); /* kernels launched through this handle so far */
 /* bytes of device scratch mbpe_encode_device needs for a batch of that shape (kept inside the handle) */
 int mbpe_encode_reserve(mbpe_encoder *e, uint64_t n_bytes, uint64_t n_chunks);
 
@@ -232,12 +255,19 @@ int mbpe_split_dedup(const char *pattern, const uint8_t *text, uint64_t len, int
 /* .model / .vocab writer given a merge list (Tokenizer.h:875-926) */
 int mbpe_write_model(const char *path, const char *pattern, const char *special_contents, uint64_t special_len,
                      const uint32_t *merges, uint32_t n_merges, int write_vocab);
+/* .vocab in karpathy/minbpe's layout (base.py save / render_token) instead of the reference's */
+int mbpe_write_vocab_karpathy(const char *path, const char *special_contents, uint64_t special_len, const uint32_t *merges,
+                              uint32_t n_merges);
+int mbpe_tokenizer_save_vocab_karpathy(mbpe_tokenizer *t, const char *path);
 /* multi-GPU encode: split n_chunks chunks into n_parts contiguous ranges of (nearly) equal BYTES; the ranges
  * are whole chunks and in order, so the concatenation of the parts' id streams is the id stream of the whole
  * (no communication). first_chunk_out gets n_parts+1 chunk indices. */
 int mbpe_plan_shards(const uint64_t *chunk_off, uint64_t n_chunks, uint32_t n_parts, uint64_t *first_chunk_out);
 /* deterministic synthetic Zipfian UTF-8 corpus (SURVEY 8(d) input 3): fills out[0..n) */
 int mbpe_synth_corpus(uint64_t seed, uint8_t *out, uint64_t n, int n_threads);
+/* the same corpus from 1 MiB block `first_block` on: out[0..n) = bytes [first_block MiB, first_block MiB + n) of it (a rank
+ * of a sharded run generates only its own part) */
+int mbpe_synth_corpus_at(uint64_t seed, uint64_t first_block, uint8_t *out, uint64_t n, int n_threads);
 
 /* ------------------------------------------------------------------------------------------------------------
  * 6. GPU pre-tokeniser and chunk dedup for the GPT-4 split pattern  (regex loop Tokenizer.h:500-544
@@ -246,7 +276,6 @@ int mbpe_synth_corpus(uint64_t seed, uint8_t *out, uint64_t n, int n_threads);
  *    code point classes are read out of the linked PCRE2. Text it cannot take (malformed UTF-8, pathological runs)
  *    is refused with MBPE_E_UNSUPPORTED; the caller then uses mbpe_split (PCRE2 itself).
  * ---------------------------------------------------------------------------------------------------------- */
-typedef struct mbpe_pretok mbpe_pretok;
 int mbpe_pretok_create(int device, mbpe_pretok **out); /* matches the GPT-4 pattern until told otherwise */
 /* pattern = mbpe_gpt4_split_pattern() or mbpe_gpt2_split_pattern(); MBPE_E_UNSUPPORTED for anything else */
 int mbpe_pretok_select(mbpe_pretok *p, const char *pattern);
@@ -279,6 +308,11 @@ int mbpe_pretok_dedup_device(mbpe_pretok *p, const uint8_t *d_text, uint64_t len
 int mbpe_pretok_dedup_segments(mbpe_pretok *p, const uint8_t *const *d_texts, const uint64_t *seg_bytes,
                                const uint32_t *const *d_offs, const uint64_t *seg_chunks, uint32_t n_segs,
                                mbpe_device_corpus *out, void *stream);
+/* several ALREADY deduplicated chunk lists (bytes + u32 offsets + weights per list, resident; lists in text order) into
+ * one device corpus: the second stage of a sharded train front end (every rank deduplicates its part of the text) */
+int mbpe_pretok_merge_corpora(mbpe_pretok *p, const uint8_t *const *d_texts, const uint64_t *seg_bytes,
+                              const uint32_t *const *d_offs, const uint32_t *const *d_weights, const uint64_t *seg_chunks,
+                              uint32_t n_segs, mbpe_device_corpus *out, void *stream);
 /* host text -> device corpus (H2D + split + dedup): the front end of Tokenizer::train (:500-556) */
 int mbpe_pretok_corpus(mbpe_pretok *p, const uint8_t *text, uint64_t len, mbpe_device_corpus *out);
 int mbpe_device_corpus_download(const mbpe_device_corpus *c, uint32_t *tokens, uint64_t *off, uint32_t *weight);

@@ -23,7 +23,8 @@ EXPORTS = [
     "mbpe_paircount_create", "mbpe_paircount_destroy", "mbpe_paircount_add", "mbpe_paircount_top",
     "mbpe_paircount_get", "mbpe_paircount_size",
     "mbpe_trainer_create", "mbpe_trainer_run", "mbpe_trainer_destroy", "mbpe_train",
-    "mbpe_comm_unique_id", "mbpe_comm_create", "mbpe_comm_destroy", "mbpe_train_sharded",
+    "mbpe_comm_unique_id", "mbpe_comm_create", "mbpe_comm_destroy", "mbpe_comm_resident", "mbpe_train_sharded",
+    "mbpe_write_vocab_karpathy", "mbpe_tokenizer_save_vocab_karpathy", "mbpe_train_text_sharded", "mbpe_pretok_merge_corpora", "mbpe_sharded_trainer_create", "mbpe_sharded_trainer_run", "mbpe_sharded_trainer_destroy", "mbpe_encoder_launches",
     "mbpe_encoder_create", "mbpe_encoder_destroy", "mbpe_encoder_set_specials", "mbpe_encode", "mbpe_encode_device",
     "mbpe_encode_reserve", "mbpe_decode", "mbpe_decode_device", "mbpe_encoder_seed_special_chunks",
     "mbpe_gpt2_split_pattern", "mbpe_gpt4_split_pattern", "mbpe_tokenizer_create", "mbpe_tokenizer_destroy",
@@ -34,7 +35,7 @@ EXPORTS = [
     "mbpe_pretok_create", "mbpe_pretok_select", "mbpe_pretok_destroy", "mbpe_pretok_split_device", "mbpe_pretok_split",
     "mbpe_pretok_dedup_device", "mbpe_pretok_dedup_segments", "mbpe_pretok_corpus", "mbpe_encode_text",
     "mbpe_encode_text_special", "mbpe_pretok_split_device_parts", "mbpe_device_corpus_download", "mbpe_device_corpus_free",
-    "mbpe_trainer_create_device", "mbpe_split_dedup", "mbpe_plan_shards", "mbpe_write_model", "mbpe_synth_corpus",
+    "mbpe_trainer_create_device", "mbpe_split_dedup", "mbpe_plan_shards", "mbpe_write_model", "mbpe_synth_corpus", "mbpe_synth_corpus_at",
 ]
 
 
@@ -296,7 +297,7 @@ class Comm:
             _ck(lib().mbpe_comm_unique_id(_p(ident, C.c_uint8)))
         ident = np.ascontiguousarray(bcast(ident), np.uint8)
         self.h = C.c_void_p()
-        self.rank, self.world = rank, world
+        self.rank, self.world, self.device = rank, world, device
         _ck(lib().mbpe_comm_create(_p(ident, C.c_uint8), rank, world, device, C.byref(self.h)))
 
     def train(self, tokens, off, weight, vocab_size, mode, stream=None):
@@ -316,10 +317,72 @@ class Comm:
                                      C.byref(st)))
         return merges[:nm.value].copy(), counts[:nm.value].copy(), st.as_dict()
 
+    def train_text(self, text_part, vocab_size, mode, pretok=None):
+        """Tokenizer::train over a text sharded over the ranks: text_part = this rank's contiguous part (bytes or uint8 array)"""
+        buf = text_part if isinstance(text_part, np.ndarray) else _u8(text_part)
+        own = pretok is None
+        pt = Pretok(device=self.device) if own else pretok
+        n = max(vocab_size - 256, 1)
+        merges = np.zeros((n, 2), np.uint32)
+        counts = np.zeros(n, np.int32)
+        nm = C.c_uint32()
+        st = TrainStats()
+        fe = C.c_double()
+        try:
+            _ck(lib().mbpe_train_text_sharded(self.h, pt.h, _p(buf, C.c_uint8), C.c_uint64(len(text_part)), C.c_uint32(vocab_size),
+                                              MODE[mode] if isinstance(mode, str) else mode, _p(merges, C.c_uint32),
+                                              _p(counts, C.c_int32), C.byref(nm), C.byref(st), C.byref(fe)))
+        finally:
+            if own:
+                pt.close()
+        d = st.as_dict()
+        d["front_end_s"] = fe.value
+        return merges[:nm.value].copy(), counts[:nm.value].copy(), d
+
+    def resident(self):
+        """True: the ranks mapped each other's inboxes, merges run in one resident CTA per rank that exchanges by itself"""
+        return bool(lib().mbpe_comm_resident(self.h))
+
     def close(self):
         if self.h:
             lib().mbpe_comm_destroy(self.h)
             self.h = C.c_void_p()
+
+
+class ShardedTrainer:
+    """This rank's share of the deduplicated corpus resident on its GPU (every rank passes the same corpus); run() can be repeated."""
+
+    def __init__(self, comm, tokens, off, weight):
+        tokens = np.ascontiguousarray(tokens, np.uint32)
+        off = np.ascontiguousarray(off, np.uint64)
+        weight = None if weight is None else np.ascontiguousarray(weight, np.uint32)
+        self.h = C.c_void_p()
+        tok = tokens if len(tokens) else np.zeros(1, np.uint32)
+        _ck(lib().mbpe_sharded_trainer_create(comm.h, _p(tok, C.c_uint32), C.c_uint64(len(tokens)), _p(off, C.c_uint64),
+                                              C.c_uint64(len(off) - 1), None if weight is None else _p(weight, C.c_uint32),
+                                              C.byref(self.h)))
+
+    def run(self, vocab_size, mode, stream=None, engine="persistent"):
+        n = max(vocab_size - 256, 1)
+        merges = np.zeros((n, 2), np.uint32)
+        counts = np.zeros(n, np.int32)
+        nm = C.c_uint32()
+        st = TrainStats()
+        _ck(lib().mbpe_sharded_trainer_run(self.h, C.c_uint32(vocab_size), MODE[mode] if isinstance(mode, str) else mode,
+                                           ENGINE[engine] if isinstance(engine, str) else engine, C.c_void_p(stream or 0),
+                                           _p(merges, C.c_uint32), _p(counts, C.c_int32), C.byref(nm), C.byref(st)))
+        return merges[:nm.value].copy(), counts[:nm.value].copy(), st.as_dict()
+
+    def close(self):
+        if self.h:
+            lib().mbpe_sharded_trainer_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 # ---- 3. encode / decode ---------------------------------------------------------------------------------
@@ -373,6 +436,11 @@ class Encoder:
 
     def reserve(self, n_bytes, n_chunks):
         _ck(lib().mbpe_encode_reserve(self.h, C.c_uint64(n_bytes), C.c_uint64(n_chunks)))
+
+    def launches(self):
+        """kernels launched through this encoder so far"""
+        lib().mbpe_encoder_launches.restype = C.c_uint64
+        return int(lib().mbpe_encoder_launches(self.h))
 
     def decode(self, ids):
         ids = np.ascontiguousarray(ids, np.uint32)
@@ -579,7 +647,16 @@ def write_model(path, pattern, special_contents, merges, write_vocab=False):
                                C.c_uint32(len(m)), int(write_vocab)))
 
 
-def synth_corpus(seed, n_bytes, n_threads=0):
-    out = np.zeros(n_bytes, np.uint8)
-    _ck(lib().mbpe_synth_corpus(C.c_uint64(seed), _p(out, C.c_uint8), C.c_uint64(n_bytes), n_threads))
-    return out
+def write_vocab_karpathy(path, special_contents, merges):
+    """.vocab in karpathy/minbpe's layout"""
+    m = np.ascontiguousarray(merges, np.uint32).reshape(-1, 2)
+    sp = special_contents or b""
+    _ck(lib().mbpe_write_vocab_karpathy(str(path).encode(), sp, C.c_uint64(len(sp)), _p(m, C.c_uint32), C.c_uint32(len(m))))
+
+
+def synth_corpus(seed, n_bytes, n_threads=0, first_block=0, out=None):
+    """bytes [first_block MiB, first_block MiB + n_bytes) of the synthetic corpus `seed` (into `out` if given)"""
+    if out is None:
+        out = np.empty(n_bytes, np.uint8)
+    _ck(lib().mbpe_synth_corpus_at(C.c_uint64(seed), C.c_uint64(first_block), _p(out, C.c_uint8), C.c_uint64(n_bytes), n_threads))
+    return out[:n_bytes]

@@ -625,6 +625,8 @@ static int ensure_status(mbpe_encoder *e, uint64_t n_tiles) {
     return MBPE_OK;
 }
 
+extern "C" uint64_t mbpe_encoder_launches(const mbpe_encoder *e) { return e ? e->launches : 0; }
+
 extern "C" int mbpe_encode_reserve(mbpe_encoder *e, uint64_t n_bytes, uint64_t n_chunks) {
     if (!e) return set_error(MBPE_E_INVALID, "null argument");
     (void)n_bytes;

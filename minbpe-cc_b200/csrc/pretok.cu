@@ -184,6 +184,7 @@ struct DdSeg {
     const uint32_t *off; // this segment's chunk offsets (n + 1), relative to its text
     uint64_t chunk0;     // global index of its first chunk
     uint64_t n_bytes;    // readable bytes of `text` (the 16-byte key loads never cross it)
+    const uint32_t *weight; // multiplicity of each chunk of this segment (merging already deduplicated corpora); null = 1
 };
 struct DedupArgs {
     DdSeg seg[DD_MAX_SEGS];
@@ -274,6 +275,7 @@ __global__ void __launch_bounds__(256) k_dedup_insert(const DedupArgs a) {
         const DdSeg &sg = dd_seg(a, c);
         const uint32_t o = __ldg(sg.off + (c - sg.chunk0)), len = __ldg(sg.off + (c - sg.chunk0) + 1) - o;
         const bool fast = a.fast && len <= 16 && (uint64_t)o + 20 <= sg.n_bytes;
+        const uint32_t wt = sg.weight ? __ldg(sg.weight + (c - sg.chunk0)) : 1u;
         uint64_t k0 = 0, k1 = 0;
         if (fast) dd_load16(sg.text, o, len, k0, k1);
         const uint64_t h = fast ? dd_hash16(k0, k1, len) : dd_hash(sg.text, o, len);
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(256) k_dedup_insert(const DedupArgs a) {
                 w = atomicCAS(&a.words[s], DD_EMPTY, mine);
                 if (w == DD_EMPTY) {
                     atomicAdd(a.used, 1u);
-                    atomicAdd(&a.counts[s], 1u);
+                    atomicAdd(&a.counts[s], wt);
                     break;
                 }
             }
@@ -313,7 +315,7 @@ __global__ void __launch_bounds__(256) k_dedup_insert(const DedupArgs a) {
                 }
                 if (same) {
                     if ((uint32_t)c < rep) atomicMin(&a.words[s], mine); // keep the FIRST occurrence as representative
-                    atomicAdd(&a.counts[s], 1u);
+                    atomicAdd(&a.counts[s], wt);
                     break;
                 }
             }
@@ -678,9 +680,9 @@ extern "C" void mbpe_device_corpus_free(mbpe_device_corpus *c) {
     memset(c, 0, sizeof *c);
 }
 
-extern "C" int mbpe_pretok_dedup_segments(mbpe_pretok *p, const uint8_t *const *d_texts, const uint64_t *seg_bytes,
-                                          const uint32_t *const *d_offs, const uint64_t *seg_chunks, uint32_t n_segs,
-                                          mbpe_device_corpus *out, void *stream) {
+static int dedup_segments_impl(mbpe_pretok *p, const uint8_t *const *d_texts, const uint64_t *seg_bytes,
+                               const uint32_t *const *d_offs, const uint32_t *const *d_weights, const uint64_t *seg_chunks,
+                               uint32_t n_segs, mbpe_device_corpus *out, void *stream) {
     if (!p || !out || (n_segs && (!d_texts || !seg_bytes || !d_offs || !seg_chunks))) return set_error(MBPE_E_INVALID, "null argument");
     if (n_segs > (uint32_t)DD_MAX_SEGS) return set_error(MBPE_E_INVALID, "too many text segments");
     uint64_t n_chunks = 0;
@@ -701,8 +703,8 @@ extern "C" int mbpe_pretok_dedup_segments(mbpe_pretok *p, const uint8_t *const *
         MB_CUDA(cudaStreamSynchronize(st));
         return MBPE_OK;
     }
-    uint64_t slots = 1u << 16;
-    while (slots < n_chunks / 16 && slots < (1ull << 27)) slots <<= 1;
+    uint64_t slots = 1u << 16; // raw text repeats its chunks ~100x; corpora that are already deduplicated hardly at all
+    while (slots < (d_weights ? n_chunks * 2 : n_chunks / 16) && slots < (1ull << 27)) slots <<= 1;
     unsigned long long *d_words = nullptr;
     uint32_t *d_counts = nullptr, *d_first = nullptr, *d_first_idx = nullptr;
     auto cleanup = [&]() {};
@@ -718,7 +720,7 @@ extern "C" int mbpe_pretok_dedup_segments(mbpe_pretok *p, const uint8_t *const *
         a = DedupArgs{};
         a.fast = 1;
         for (uint32_t k = 0, c0 = 0; k < n_segs; c0 += (uint32_t)seg_chunks[k], k++) {
-            a.seg[k] = DdSeg{d_texts[k], d_offs[k], c0, seg_bytes[k]};
+            a.seg[k] = DdSeg{d_texts[k], d_offs[k], c0, seg_bytes[k], d_weights ? d_weights[k] : nullptr};
             if (((uintptr_t)d_texts[k] & 3) != 0) a.fast = 0;
         }
         a.n_segs = n_segs;
@@ -786,6 +788,21 @@ extern "C" int mbpe_pretok_dedup_segments(mbpe_pretok *p, const uint8_t *const *
         return cuda_fail(ce, "dedup kernels", __FILE__, __LINE__);
     }
     return MBPE_OK;
+}
+
+extern "C" int mbpe_pretok_dedup_segments(mbpe_pretok *p, const uint8_t *const *d_texts, const uint64_t *seg_bytes,
+                                          const uint32_t *const *d_offs, const uint64_t *seg_chunks, uint32_t n_segs,
+                                          mbpe_device_corpus *out, void *stream) {
+    return dedup_segments_impl(p, d_texts, seg_bytes, d_offs, nullptr, seg_chunks, n_segs, out, stream);
+}
+
+// Several already deduplicated chunk lists (the ranks of a sharded train front end, in text order) into one: same
+// kernels, every chunk counting with its weight. First-appearance order of the result = order over the whole text.
+extern "C" int mbpe_pretok_merge_corpora(mbpe_pretok *p, const uint8_t *const *d_texts, const uint64_t *seg_bytes,
+                                         const uint32_t *const *d_offs, const uint32_t *const *d_weights,
+                                         const uint64_t *seg_chunks, uint32_t n_segs, mbpe_device_corpus *out, void *stream) {
+    if (n_segs && !d_weights) return set_error(MBPE_E_INVALID, "null argument");
+    return dedup_segments_impl(p, d_texts, seg_bytes, d_offs, d_weights, seg_chunks, n_segs, out, stream);
 }
 
 extern "C" int mbpe_pretok_dedup_device(mbpe_pretok *p, const uint8_t *d_text, uint64_t len, const uint32_t *d_off,

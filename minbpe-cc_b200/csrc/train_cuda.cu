@@ -12,6 +12,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
 #include <mutex>
 #include <vector>
 
@@ -209,7 +210,7 @@ __device__ __forceinline__ void fused_select(const Ctx &c, PersistSmem *red) {
                         c.merges_out[2 * step + 1] = (uint32_t)key;
                         c.counts_out[step] = cmax;
                         g->selected = 1;
-                        if (seg_len > g->big_limit) g->status = ST_BIG_MERGE;
+                        if (seg_len > g->big_limit || (g->big_count && (uint32_t)cmax > g->big_count)) g->status = ST_BIG_MERGE;
                     }
                 }
             }
@@ -303,7 +304,7 @@ __device__ __forceinline__ void fused_select(const Ctx &c, PersistSmem *red) {
                 c.merges_out[2 * step + 1] = head[k].x;
                 c.counts_out[step] = cmax;
                 g->selected = 1;
-                if (seg_len > g->big_limit) g->status = ST_BIG_MERGE;
+                if (seg_len > g->big_limit || (g->big_count && (uint32_t)cmax > g->big_count)) g->status = ST_BIG_MERGE;
             }
         }
     __syncthreads();
@@ -412,6 +413,177 @@ __global__ void __launch_bounds__(PERSISTENT_THREADS, 1) k_persistent(const Ctx 
         __syncthreads();
         lap(4);
     }
+    if (tid == 0) g->prof[6] += (uint64_t)(clock64() - t_enter);
+    __syncthreads();
+    if (cand_in_smem) {
+        const uint32_t n_out = min(g->n_cand, (uint32_t)(PS_SEL * PERSISTENT_THREADS));
+        for (uint32_t i = tid; i < n_out; i += PERSISTENT_THREADS) cg.cand[i] = sm->cand[i];
+    }
+    if (tid < CTL_WORDS) reinterpret_cast<uint32_t *>(cg.ctl)[tid] = reinterpret_cast<const uint32_t *>(&sm->ctl)[tid];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_persistent_sharded: the resident CTA of SHARDED training (one per rank = per GPU). Same step structure as
+// k_persistent -- the device transcription of persistent_program_sharded() in train_phases.cuh, which the CPU test tier
+// runs on emulated ranks -- plus the exchange of the step's count deltas with the other ranks done by the CTA itself:
+// every rank has mapped the other ranks' inboxes (cudaIpc), so the records leave as plain 16-byte stores over NVLink,
+// followed by a system-scope fence and one flag word per peer {exchange number, record count}; then the CTA polls the
+// flag words the peers write into ITS memory and applies their records. No kernel launch, no host round trip and no
+// NCCL call per merge. Two buffers per (sender, receiver) by exchange parity: a rank can be at most one exchange ahead
+// of a peer (it needs the peer's records of exchange k to finish k), so a buffer is never overwritten before it was read.
+// ---------------------------------------------------------------------------------------------------------
+constexpr uint32_t XCH_MAX_WORLD = 8;
+struct PeerLinks {
+    XRec *send_to[XCH_MAX_WORLD];               // peer p's inbox block for THIS rank: [parity][cap] (mapped peer memory; self: null)
+    unsigned long long *flag_to[XCH_MAX_WORLD]; // peer p's flag words for this rank: [parity]
+    const XRec *inbox;                          // this rank's inbox: [source rank][parity][cap]
+    unsigned long long *flags;                  // this rank's flag words: [source rank][parity]
+    uint32_t cap, world, rank;
+};
+
+struct ShardSmem {
+    Ctl ctl;
+    uint32_t hit[PS_HIT];
+    uint32_t hit_j[PS_HIT];
+    uint32_t hit_y[PS_HIT];
+    uint32_t rec_slot[PS_REC];
+    uint32_t rec_pos[PS_REC];
+    uint32_t cand[PS_SEL * PERSISTENT_THREADS];
+    uint32_t counts[XCH_MAX_WORLD];
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// send c.xrec[0 .. n_xrec) to every peer, receive theirs, apply them. All threads of the CTA. false: ST_FAILED.
+__device__ __forceinline__ bool xch_apply(const Ctx &c, ShardSmem *sm, const PeerLinks &pl) {
+    Ctl *g = c.ctl; // shared memory
+    const uint32_t tid = threadIdx.x;
+    const uint32_t n = g->n_xrec, xs = g->xstep, par = xs & 1u, tag = xs + 1u;
+    if (n > pl.cap || n > c.xrec_cap) { // cannot happen while Ctl::big_count <= cap / 4; never send a truncated list
+        __syncthreads();
+        if (tid == 0) g->status = ST_FAILED;
+        __syncthreads();
+        return false;
+    }
+    const uint4 *src = reinterpret_cast<const uint4 *>(c.xrec);
+    for (uint32_t p = 0; p < pl.world; p++) {
+        if (p == pl.rank) continue;
+        uint4 *dst = reinterpret_cast<uint4 *>(pl.send_to[p] + (size_t)par * pl.cap);
+        for (uint32_t i = tid; i < n; i += PERSISTENT_THREADS) dst[i] = __ldcg(&src[i]);
+    }
+    __threadfence_system(); // every thread's records are visible system-wide before the flags go out
+    __syncthreads();
+    if (tid < pl.world) {
+        uint32_t cnt = 0;
+        if (tid != pl.rank) {
+            st_release_sys(pl.flag_to[tid] + par, ((unsigned long long)tag << 32) | n);
+            const unsigned long long *f = pl.flags + tid * 2 + par;
+            const long long t0 = clock64();
+            for (;;) {
+                const unsigned long long v = ld_acquire_sys(f);
+                if ((uint32_t)(v >> 32) == tag) {
+                    cnt = (uint32_t)v;
+                    break;
+                }
+                if (clock64() - t0 > 8000000000ll) { // ~4 s: the peer is gone (or the ranks' step sequences diverged)
+                    g->status = ST_FAILED;
+                    break;
+                }
+            }
+        }
+        sm->counts[tid] = cnt;
+    }
+    __syncthreads();
+    if (g->status == ST_FAILED) return false;
+    phase_apply_foreign<true>(c, pl.inbox + (size_t)par * pl.cap, sm->counts, 2 * pl.cap, pl.world, pl.rank, tid, PERSISTENT_THREADS);
+    if (tid == 0) g->xstep = xs + 1u;
+    __syncthreads();
+    return true;
+}
+
+__global__ void __launch_bounds__(PERSISTENT_THREADS, 1) k_persistent_sharded(const Ctx cg, const PeerLinks pl) {
+    extern __shared__ __align__(16) unsigned char ps_raw[];
+    ShardSmem *sm = reinterpret_cast<ShardSmem *>(ps_raw);
+    const uint32_t tid = threadIdx.x;
+    constexpr uint32_t CTL_WORDS = sizeof(Ctl) / 4;
+    if (tid < CTL_WORDS) reinterpret_cast<uint32_t *>(&sm->ctl)[tid] = __ldcg(reinterpret_cast<const uint32_t *>(cg.ctl) + tid);
+    __syncthreads();
+    Ctx c = cg;
+    c.ctl = &sm->ctl;
+    c.m_cnt = nullptr; // no candidate mirror: counts also change through the other ranks' records
+    c.m_cap = 0;
+    Ctl *g = &sm->ctl;
+    const uint32_t n_cand_in = g->n_cand;
+    const bool cand_in_smem = n_cand_in <= PS_SEL * PERSISTENT_THREADS;
+    if (cand_in_smem) {
+        for (uint32_t i = tid; i < n_cand_in; i += PERSISTENT_THREADS) sm->cand[i] = __ldcg(&cg.cand[i]);
+        c.cand = sm->cand;
+        c.cand_cap = PS_SEL * PERSISTENT_THREADS; // appends past it are dropped and phase_fin asks for a rebuild
+        __syncthreads();
+    }
+    const long long t_enter = clock64();
+    for (;;) {
+        if (g->status != ST_RUN) break;
+        if (g->selected == 0) {
+            if (g->mode == 1) {
+                fused_select(c, nullptr); // LEXICAL: a function of the replicated table only
+            } else { // FIRST: a tied pair that lost its first occurrence needs the minimum over ALL ranks' occurrences
+                phase_sel_max<true>(c, tid, PERSISTENT_THREADS);
+                __syncthreads();
+                phase_sel_tie<true>(c, tid, PERSISTENT_THREADS);
+                __syncthreads();
+                if (tid == 0) phase_sel_check<true>(c);
+                __syncthreads();
+                if (g->status == ST_RUN && g->n_fix) { // same replicas: same decision on every rank
+                    phase_sel_fix_scan<true>(c, tid, PERSISTENT_THREADS);
+                    __syncthreads();
+                    phase_export_fix<true>(c, tid, PERSISTENT_THREADS);
+                    __syncthreads();
+                    if (!xch_apply(c, sm, pl)) break;
+                    if (tid == 0) g->n_xrec = 0;
+                    __syncthreads();
+                    phase_sel_fix_tie<true>(c, tid, PERSISTENT_THREADS);
+                    __syncthreads();
+                }
+                phase_sel_pick<true>(c, tid, PERSISTENT_THREADS);
+                __syncthreads();
+                if (tid == 0) phase_sel_commit<true>(c, 1);
+                __syncthreads();
+            }
+            if (g->status != ST_RUN) break;
+        }
+        Ctx w = c; // small steps keep their lists in shared memory (newp stays global: the other ranks' births land there too)
+        if (g->seg_len <= PS_HIT) {
+            w.hit = sm->hit;
+            w.hit_j = sm->hit_j;
+            w.hit_y = sm->hit_y;
+            w.rec_slot = sm->rec_slot;
+            w.rec_pos = sm->rec_pos;
+        }
+        phase_hits<true>(w, tid, PERSISTENT_THREADS);
+        __syncthreads();
+        phase_export_births<true>(w, tid, PERSISTENT_THREADS);
+        __syncthreads();
+        if (!xch_apply(w, sm, pl)) break;
+        phase_mutate<true>(w, tid, PERSISTENT_THREADS);
+        phase_seg_alloc<true>(w, tid, PERSISTENT_THREADS);
+        __syncthreads();
+        phase_seg_fill<true>(w, tid, PERSISTENT_THREADS);
+        __syncthreads();
+        if (tid == 0) {
+            phase_fin<true>(w);
+            g->prof[5] += 1;
+        }
+        __syncthreads();
+    }
+    __syncthreads();
     if (tid == 0) g->prof[6] += (uint64_t)(clock64() - t_enter);
     __syncthreads();
     if (cand_in_smem) {
@@ -551,6 +723,22 @@ struct CudaBE {
     uint32_t *d_counts = nullptr, *d_my_count = nullptr;
     uint32_t world() const { return comm_world; }
     uint32_t rank() const { return comm_rank; }
+    // resident sharded program (k_persistent_sharded): peer inboxes mapped by mbpe_comm_create, null = not available
+    const PeerLinks *links = nullptr;
+    uint32_t *xstep_ptr = nullptr; // exchanges done so far on this communicator (continues from run to run)
+    uint32_t resident_limit() const { return links ? links->cap / 4 : 0; } // <= 4 records per live local occurrence <= count
+    uint32_t xstep() const { return xstep_ptr ? *xstep_ptr : 0; }
+    void set_xstep(uint32_t v) {
+        if (xstep_ptr) *xstep_ptr = v;
+    }
+    void persistent_sharded(const Ctx &c) {
+        if (err != cudaSuccess) return;
+        note(cudaFuncSetAttribute(k_persistent_sharded, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ShardSmem)),
+             "smem attr");
+        k_persistent_sharded<<<1, PERSISTENT_THREADS, sizeof(ShardSmem), stream>>>(c, *links);
+        n_launch++;
+        note(cudaGetLastError(), "k_persistent_sharded launch");
+    }
     // all-gather of this step's count deltas over NVLink: counts first (they size the padded second gather)
     void exchange(const XRec *d_send, uint32_t n_send, const XRec **out_all, const uint32_t **out_counts, uint32_t *stride) {
         *out_all = d_all;
@@ -907,6 +1095,13 @@ extern "C" int mbpe_train(const uint32_t *tokens, uint64_t n_tokens, const uint6
 struct mbpe_comm {
     NcclApi::comm_t nccl = nullptr;
     int rank = 0, world = 1, device = 0;
+    // resident exchange (k_persistent_sharded): this rank's inbox + flag words, and the peers' mapped into this process
+    XRec *d_inbox = nullptr;
+    unsigned long long *d_flags = nullptr;
+    void *peer_inbox[XCH_MAX_WORLD] = {}, *peer_flags[XCH_MAX_WORLD] = {};
+    PeerLinks links{};
+    bool resident_ok = false;
+    uint32_t xstep = 0;
 };
 
 extern "C" int mbpe_comm_unique_id(uint8_t *id_out) {
@@ -916,6 +1111,75 @@ extern "C" int mbpe_comm_unique_id(uint8_t *id_out) {
     NcclApi::unique_id id;
     if (api.GetUniqueId(&id) != 0) return set_error(MBPE_E_CUDA, "ncclGetUniqueId failed");
     memcpy(id_out, id.internal, 128);
+    return MBPE_OK;
+}
+
+// all-gather of `bytes` host bytes per rank through the communicator (setup only)
+static int comm_allgather_host(mbpe_comm *c, const void *mine, void *all, size_t bytes) {
+    uint8_t *d = nullptr;
+    MB_CUDA(cudaMalloc(&d, bytes * ((size_t)c->world + 1)));
+    cudaError_t ce = cudaMemcpy(d, mine, bytes, cudaMemcpyHostToDevice);
+    int nrc = 0;
+    if (ce == cudaSuccess) nrc = NcclApi::get().AllGather(d, d + bytes, bytes, NCCL_UINT8, c->nccl, nullptr);
+    if (ce == cudaSuccess && nrc == 0) ce = cudaDeviceSynchronize();
+    if (ce == cudaSuccess && nrc == 0) ce = cudaMemcpy(all, d + bytes, bytes * c->world, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (nrc != 0) return set_error(MBPE_E_CUDA, "ncclAllGather failed during communicator setup");
+    if (ce != cudaSuccess) return cuda_fail(ce, "communicator setup", __FILE__, __LINE__);
+    return MBPE_OK;
+}
+
+// Map every peer's inbox into this process (cudaIpc) so that the resident CTA can store its records there directly.
+// All ranks agree on the outcome (one more all-gather): either every rank has every mapping, or nobody uses them and
+// the sharded trainer stays on the host-driven path.
+static int comm_setup_peer_links(mbpe_comm *c) {
+    c->resident_ok = false;
+    if (c->world < 2 || c->world > (int)XCH_MAX_WORLD || getenv("MBPE_NO_PEER_EXCHANGE")) return MBPE_OK;
+    uint32_t cap = 1u << 19; // records per (sender, parity): 8 MB; resident merges have a count <= cap / 4
+    if (const char *v = getenv("MBPE_XCH_CAP")) cap = std::max<uint32_t>(1024, (uint32_t)strtoul(v, nullptr, 10));
+    const size_t inbox_bytes = (size_t)c->world * 2 * cap * sizeof(XRec), flag_bytes = 4096;
+    struct Handles {
+        cudaIpcMemHandle_t inbox, flags;
+        int ok;
+    } mine;
+    memset(&mine, 0, sizeof mine);
+    mine.ok = cudaMalloc(&c->d_inbox, inbox_bytes) == cudaSuccess && cudaMalloc(&c->d_flags, flag_bytes) == cudaSuccess &&
+              cudaMemset(c->d_flags, 0, flag_bytes) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine.inbox, c->d_inbox) == cudaSuccess && cudaIpcGetMemHandle(&mine.flags, c->d_flags) == cudaSuccess;
+    cudaGetLastError();
+    std::vector<Handles> all(c->world);
+    int rc = comm_allgather_host(c, &mine, all.data(), sizeof(Handles));
+    if (rc) return rc;
+    int ok = 1;
+    for (int r = 0; r < c->world; r++) ok &= all[r].ok;
+    for (int r = 0; r < c->world && ok; r++) {
+        if (r == c->rank) continue;
+        int can = 0;
+        // (ranks of one box: the peer's device is visible here under SOME ordinal; lazy peer access enables the mapping)
+        ok = cudaIpcOpenMemHandle(&c->peer_inbox[r], all[r].inbox, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
+             cudaIpcOpenMemHandle(&c->peer_flags[r], all[r].flags, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+        (void)can;
+    }
+    cudaGetLastError();
+    std::vector<int> oks(c->world);
+    rc = comm_allgather_host(c, &ok, oks.data(), sizeof(int));
+    if (rc) return rc;
+    for (int r = 0; r < c->world; r++) ok &= oks[r];
+    if (!ok) return MBPE_OK; // host-driven path only
+    PeerLinks &pl = c->links;
+    memset(&pl, 0, sizeof pl);
+    for (int r = 0; r < c->world; r++) {
+        if (r == c->rank) continue;
+        // inside peer r's inbox, the block [source = this rank][parity][cap]
+        pl.send_to[r] = (XRec *)c->peer_inbox[r] + (size_t)c->rank * 2 * cap;
+        pl.flag_to[r] = (unsigned long long *)c->peer_flags[r] + (size_t)c->rank * 2;
+    }
+    pl.inbox = c->d_inbox;
+    pl.flags = c->d_flags;
+    pl.cap = cap;
+    pl.world = (uint32_t)c->world;
+    pl.rank = (uint32_t)c->rank;
+    c->resident_ok = true;
     return MBPE_OK;
 }
 
@@ -937,30 +1201,56 @@ extern "C" int mbpe_comm_create(const uint8_t *id_bytes, int rank, int world, in
         delete c;
         return set_error(MBPE_E_CUDA, std::string("ncclCommInitRank failed: ") + (api.GetErrorString ? api.GetErrorString(nrc) : "?"));
     }
+    if ((rc = comm_setup_peer_links(c))) {
+        mbpe_comm_destroy(c);
+        return rc;
+    }
     *out = c;
     return MBPE_OK;
 }
 
+extern "C" int mbpe_comm_resident(const mbpe_comm *c) { return c && c->resident_ok ? 1 : 0; }
+
 extern "C" void mbpe_comm_destroy(mbpe_comm *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    if (c->nccl) NcclApi::get().CommDestroy(c->nccl);
+    cudaDeviceSynchronize();
+    for (uint32_t r = 0; r < XCH_MAX_WORLD; r++) {
+        if (c->peer_inbox[r]) cudaIpcCloseMemHandle(c->peer_inbox[r]);
+        if (c->peer_flags[r]) cudaIpcCloseMemHandle(c->peer_flags[r]);
+    }
+    if (c->nccl) NcclApi::get().CommDestroy(c->nccl); // (a collective teardown: the peers have closed their mappings too)
+    cudaFree(c->d_inbox);
+    cudaFree(c->d_flags);
+    cudaGetLastError();
     delete c;
 }
 
-extern "C" int mbpe_train_sharded(mbpe_comm *comm, const uint32_t *tokens, uint64_t n_tokens, const uint64_t *chunk_off,
-                                  uint64_t n_chunks, const uint32_t *chunk_weight, uint32_t vocab_size, int mode,
-                                  void *stream, uint32_t *merges_out, int32_t *counts_out, uint32_t *n_merges_out,
-                                  mbpe_train_stats *stats) {
-    if (!comm || !merges_out || !n_merges_out || !chunk_off || (!tokens && n_tokens))
-        return set_error(MBPE_E_INVALID, "null argument");
-    if (vocab_size < 256) return set_error(MBPE_E_INVALID, "vocab_size must be >= 256 (Tokenizer.h:492)");
-    if (mode != MBPE_MODE_FIRST && mode != MBPE_MODE_LEXICAL) return set_error(MBPE_E_INVALID, "bad mode");
-    if (n_tokens >= (1ull << 30)) return set_error(MBPE_E_INVALID, "n_tokens must be < 2^30");
-    if (chunk_off[0] != 0 || chunk_off[n_chunks] != n_tokens)
-        return set_error(MBPE_E_INVALID, "chunk_off must start at 0 and end at n_tokens");
-    int rc = use_device(comm->device);
-    if (rc) return rc;
+// this rank's share of the corpus, resident; run() can be repeated (the merge loop works on copies)
+struct mbpe_sharded_trainer {
+    mbpe_comm *comm = nullptr;
+    uint32_t *d_tokens = nullptr, *d_weight = nullptr;
+    uint64_t *d_off = nullptr;
+    uint64_t n_local = 0, n_chunks_local = 0, pos_base = 0, n_global = 0;
+    Ctl *pinned = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+
+extern "C" void mbpe_sharded_trainer_destroy(mbpe_sharded_trainer *t) {
+    if (!t) return;
+    if (t->comm) cudaSetDevice(t->comm->device);
+    cudaFree(t->d_tokens);
+    cudaFree(t->d_off);
+    cudaFree(t->d_weight);
+    if (t->pinned) cudaFreeHost(t->pinned);
+    if (t->e0) cudaEventDestroy(t->e0);
+    if (t->e1) cudaEventDestroy(t->e1);
+    cudaGetLastError();
+    delete t;
+}
+
+static int sharded_trainer_create_impl(mbpe_sharded_trainer *t, mbpe_comm *comm, const uint32_t *tokens, uint64_t n_tokens,
+                                       const uint64_t *chunk_off, uint64_t n_chunks, const uint32_t *chunk_weight) {
     // this rank's contiguous, token-balanced share of the unique chunks (same cut on every rank)
     auto first_chunk = [&](int r) -> uint64_t {
         if (r <= 0) return 0;
@@ -984,65 +1274,223 @@ extern "C" int mbpe_train_sharded(mbpe_comm *comm, const uint32_t *tokens, uint6
                 if (tokens[i] >= 256) return set_error(MBPE_E_INVALID, "token >= 256 inside a multi-token chunk");
     std::vector<uint64_t> loff(ncl + 1);
     for (uint64_t c = c0; c <= c1; c++) loff[c - c0] = chunk_off[c] - t0;
-    cudaStream_t st = (cudaStream_t)stream;
-    uint32_t *d_tokens = nullptr, *d_weight = nullptr;
-    uint64_t *d_off = nullptr;
-    Ctl *pinned = nullptr;
-    MB_CUDA(cudaMalloc(&d_tokens, std::max<uint64_t>(nl, 1) * 4));
-    MB_CUDA(cudaMalloc(&d_off, (ncl + 1) * 8));
-    MB_CUDA(cudaMemcpy(d_tokens, tokens + t0, nl * 4, cudaMemcpyHostToDevice));
-    MB_CUDA(cudaMemcpy(d_off, loff.data(), (ncl + 1) * 8, cudaMemcpyHostToDevice));
+    t->comm = comm;
+    t->n_local = nl;
+    t->n_chunks_local = ncl;
+    t->pos_base = t0;
+    t->n_global = n_tokens;
+    MB_CUDA(cudaMalloc(&t->d_tokens, std::max<uint64_t>(nl, 1) * 4));
+    MB_CUDA(cudaMalloc(&t->d_off, (ncl + 1) * 8));
+    MB_CUDA(cudaMemcpy(t->d_tokens, tokens + t0, nl * 4, cudaMemcpyHostToDevice));
+    MB_CUDA(cudaMemcpy(t->d_off, loff.data(), (ncl + 1) * 8, cudaMemcpyHostToDevice));
     if (chunk_weight) {
-        MB_CUDA(cudaMalloc(&d_weight, std::max<uint64_t>(ncl, 1) * 4));
-        MB_CUDA(cudaMemcpy(d_weight, chunk_weight + c0, ncl * 4, cudaMemcpyHostToDevice));
+        MB_CUDA(cudaMalloc(&t->d_weight, std::max<uint64_t>(ncl, 1) * 4));
+        MB_CUDA(cudaMemcpy(t->d_weight, chunk_weight + c0, ncl * 4, cudaMemcpyHostToDevice));
     }
-    MB_CUDA(cudaMallocHost(&pinned, sizeof(Ctl)));
-    cudaEvent_t e0, e1;
-    MB_CUDA(cudaEventCreate(&e0));
-    MB_CUDA(cudaEventCreate(&e1));
+    MB_CUDA(cudaMallocHost(&t->pinned, sizeof(Ctl)));
+    MB_CUDA(cudaEventCreate(&t->e0));
+    MB_CUDA(cudaEventCreate(&t->e1));
+    cudaMemPool_t pool; // keep freed blocks in the stream-ordered pool: repeated runs do not go back to the driver
+    if (cudaDeviceGetDefaultMemPool(&pool, comm->device) == cudaSuccess) {
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    return MBPE_OK;
+}
+
+extern "C" int mbpe_sharded_trainer_create(mbpe_comm *comm, const uint32_t *tokens, uint64_t n_tokens, const uint64_t *chunk_off,
+                                           uint64_t n_chunks, const uint32_t *chunk_weight, mbpe_sharded_trainer **out) {
+    if (!comm || !out || !chunk_off || (!tokens && n_tokens)) return set_error(MBPE_E_INVALID, "null argument");
+    *out = nullptr;
+    if (n_tokens >= (1ull << 30)) return set_error(MBPE_E_INVALID, "n_tokens must be < 2^30");
+    if (chunk_off[0] != 0 || chunk_off[n_chunks] != n_tokens)
+        return set_error(MBPE_E_INVALID, "chunk_off must start at 0 and end at n_tokens");
+    int rc = use_device(comm->device);
+    if (rc) return rc;
+    mbpe_sharded_trainer *t = new mbpe_sharded_trainer();
+    if ((rc = sharded_trainer_create_impl(t, comm, tokens, n_tokens, chunk_off, n_chunks, chunk_weight))) {
+        mbpe_sharded_trainer_destroy(t);
+        return rc;
+    }
+    *out = t;
+    return MBPE_OK;
+}
+
+extern "C" int mbpe_sharded_trainer_run(mbpe_sharded_trainer *t, uint32_t vocab_size, int mode, int engine, void *stream,
+                                        uint32_t *merges_out, int32_t *counts_out, uint32_t *n_merges_out, mbpe_train_stats *stats) {
+    if (!t || !merges_out || !n_merges_out) return set_error(MBPE_E_INVALID, "null argument");
+    if (vocab_size < 256) return set_error(MBPE_E_INVALID, "vocab_size must be >= 256 (Tokenizer.h:492)");
+    if (mode != MBPE_MODE_FIRST && mode != MBPE_MODE_LEXICAL) return set_error(MBPE_E_INVALID, "bad mode");
+    if (engine != MBPE_ENGINE_STEPWISE && engine != MBPE_ENGINE_PERSISTENT) return set_error(MBPE_E_INVALID, "bad engine");
+    mbpe_comm *comm = t->comm;
+    int rc = use_device(comm->device);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
     CudaBE be;
     be.stream = st;
     be.sms = sm_count(comm->device);
-    be.pinned = pinned;
+    be.pinned = t->pinned;
     be.nccl = comm->nccl;
     be.comm_world = (uint32_t)comm->world;
     be.comm_rank = (uint32_t)comm->rank;
-    TrainConfig cfg{vocab_size, mode, MBPE_ENGINE_STEPWISE, ~0u, env_u32("MBPE_CAND_WANT", 512), 0, 0};
+    if (comm->resident_ok && engine == MBPE_ENGINE_PERSISTENT) {
+        be.links = &comm->links;
+        be.xstep_ptr = &comm->xstep;
+    }
+    TrainConfig cfg{vocab_size, mode, engine, ~0u, env_u32("MBPE_CAND_WANT", 512), env_u32("MBPE_CAND_LIMIT", PS_SEL * PERSISTENT_THREADS), 0};
     TrainOutcome o;
     *n_merges_out = 0;
-    MB_CUDA(cudaEventRecord(e0, st));
+    MB_CUDA(cudaEventRecord(t->e0, st));
     int drc;
     {
         TrainLoopSharded<CudaBE> loop(be);
-        drc = loop.run(d_tokens, d_off, d_weight, nl, ncl, t0, n_tokens, cfg, merges_out, counts_out, &o);
+        drc = loop.run(t->d_tokens, t->d_off, t->d_weight, t->n_local, t->n_chunks_local, t->pos_base, t->n_global, cfg, merges_out,
+                       counts_out, &o);
     }
-    MB_CUDA(cudaEventRecord(e1, st));
+    MB_CUDA(cudaEventRecord(t->e1, st));
     MB_CUDA(cudaStreamSynchronize(st));
     float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1);
-    cudaFree(d_tokens);
-    cudaFree(d_off);
-    cudaFree(d_weight);
+    cudaEventElapsedTime(&ms, t->e0, t->e1);
     cudaFree(be.d_all);
     cudaFree(be.d_counts);
     cudaFree(be.d_my_count);
-    cudaFreeHost(pinned);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     if (be.err != cudaSuccess) return cuda_fail(be.err, be.err_what, __FILE__, __LINE__);
+    if (drc == -2) return set_error(MBPE_E_CUDA, "sharded train: a peer did not answer inside the resident kernel (ranks out of step?)");
     if (drc) return set_error(MBPE_E_CUDA, "sharded train loop reached an unexpected state");
     *n_merges_out = finish_merges(o, vocab_size, mode, merges_out, counts_out);
     if (stats) {
         memset(stats, 0, sizeof *stats);
         stats->gpu_ms = ms;
-        stats->n_positions = nl;
+        stats->n_positions = t->n_local;
         stats->n_pairs = o.n_pairs;
         stats->table_slots = o.table_slots;
         stats->n_launches = be.launches();
-        stats->n_big_merges = o.n_big; // = number of per-merge exchanges
+        stats->n_big_merges = o.n_big; // merges driven from the host (grid kernels + one all-gather each)
         stats->n_rebuilds = o.n_rebuilds;
+        stats->rescan_bytes = o.rescan_bytes;
+        for (int i = 0; i < 8; i++) stats->resident_cycles[i] = o.prof[i];
     }
     return MBPE_OK;
+}
+
+extern "C" int mbpe_train_sharded(mbpe_comm *comm, const uint32_t *tokens, uint64_t n_tokens, const uint64_t *chunk_off,
+                                  uint64_t n_chunks, const uint32_t *chunk_weight, uint32_t vocab_size, int mode,
+                                  void *stream, uint32_t *merges_out, int32_t *counts_out, uint32_t *n_merges_out,
+                                  mbpe_train_stats *stats) {
+    mbpe_sharded_trainer *t = nullptr;
+    int rc = mbpe_sharded_trainer_create(comm, tokens, n_tokens, chunk_off, n_chunks, chunk_weight, &t);
+    if (rc) return rc;
+    const int engine = getenv("MBPE_SHARDED_STEPWISE") ? MBPE_ENGINE_STEPWISE : MBPE_ENGINE_PERSISTENT;
+    rc = mbpe_sharded_trainer_run(t, vocab_size, mode, engine, stream, merges_out, counts_out, n_merges_out, stats);
+    mbpe_sharded_trainer_destroy(t);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Sharded train front end: every rank pre-tokenises and deduplicates ITS part of the text, one all-gather moves the
+// unique chunks, every rank merges them into the same corpus and runs the merge loop (Tokenizer.h:500-589 as a whole).
+// ---------------------------------------------------------------------------------------------------------
+namespace mbpe {
+__global__ void k_pack_corpus(const uint32_t *tokens, uint64_t n_tokens, const uint64_t *off, uint64_t n_unique, uint8_t *bytes,
+                              uint32_t *off32) {
+    const uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = i0; i < n_tokens; i += stride) bytes[i] = (uint8_t)tokens[i]; // chunk tokens are bytes before training
+    for (uint64_t i = i0; i <= n_unique; i += stride) off32[i] = (uint32_t)off[i];
+}
+} // namespace mbpe
+
+extern "C" int mbpe_train_text_sharded(mbpe_comm *comm, mbpe_pretok *p, const uint8_t *text_part, uint64_t len, uint32_t vocab_size,
+                                       int mode, uint32_t *merges_out, int32_t *counts_out, uint32_t *n_merges_out,
+                                       mbpe_train_stats *stats, double *front_end_s) {
+    if (!comm || !p || !merges_out || !n_merges_out || (len && !text_part)) return set_error(MBPE_E_INVALID, "null argument");
+    int rc = use_device(comm->device);
+    if (rc) return rc;
+    const auto t_start = std::chrono::steady_clock::now();
+    const int W = comm->world;
+    mbpe_device_corpus mine{};
+    rc = mbpe_pretok_corpus(p, text_part, len, &mine);
+    // the outcome of the local front end is agreed on before any collective that depends on it
+    struct Sizes {
+        uint64_t n_tokens, n_unique;
+        int64_t rc;
+    } sz{mine.n_tokens, mine.n_unique, rc};
+    std::vector<Sizes> all(W);
+    int grc = comm_allgather_host(comm, &sz, all.data(), sizeof(Sizes));
+    if (grc) {
+        mbpe_device_corpus_free(&mine);
+        return grc;
+    }
+    for (int r = 0; r < W; r++)
+        if (all[r].rc) {
+            mbpe_device_corpus_free(&mine);
+            return rc ? rc : set_error((int)all[r].rc, "the device front end failed on another rank");
+        }
+    uint64_t max_t = 0, max_u = 0;
+    for (int r = 0; r < W; r++) {
+        if (all[r].n_tokens >= (1ull << 32) - 64) {
+            mbpe_device_corpus_free(&mine);
+            return set_error(MBPE_E_INVALID, "a rank's unique chunks exceed 4 GiB");
+        }
+        max_t = std::max(max_t, all[r].n_tokens);
+        max_u = std::max(max_u, all[r].n_unique);
+    }
+    max_t = (max_t + 63) & ~63ull; // every rank's block starts 64-byte aligned
+    const uint64_t off_stride = (max_u + 1 + 15) & ~15ull, w_stride = (max_u + 15) & ~15ull;
+    uint8_t *d_bytes = nullptr;
+    uint32_t *d_off = nullptr, *d_w = nullptr;
+    auto release = [&]() {
+        cudaFree(d_bytes);
+        cudaFree(d_off);
+        cudaFree(d_w);
+        mbpe_device_corpus_free(&mine);
+    };
+    cudaError_t ce = cudaMalloc(&d_bytes, (size_t)(W + 1) * max_t + 64);
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_off, (size_t)(W + 1) * off_stride * 4);
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_w, (size_t)(W + 1) * std::max<uint64_t>(w_stride, 16) * 4);
+    if (ce != cudaSuccess) {
+        release();
+        return cuda_fail(ce, "sharded front end buffers", __FILE__, __LINE__);
+    }
+    // block W = this rank's send buffers, blocks 0..W-1 = everybody's
+    uint8_t *s_bytes = d_bytes + (size_t)W * max_t;
+    uint32_t *s_off = d_off + (size_t)W * off_stride, *s_w = d_w + (size_t)W * std::max<uint64_t>(w_stride, 16);
+    k_pack_corpus<<<sm_count(comm->device) * 8, 256>>>(mine.d_tokens, mine.n_tokens, mine.d_off, mine.n_unique, s_bytes, s_off);
+    ce = cudaGetLastError();
+    if (ce == cudaSuccess && mine.n_unique) ce = cudaMemcpyAsync(s_w, mine.d_weight, mine.n_unique * 4, cudaMemcpyDeviceToDevice, nullptr);
+    NcclApi &api = NcclApi::get();
+    int nrc = 0;
+    if (ce == cudaSuccess && max_t) nrc = api.AllGather(s_bytes, d_bytes, max_t, NCCL_UINT8, comm->nccl, nullptr);
+    if (ce == cudaSuccess && !nrc) nrc = api.AllGather(s_off, d_off, off_stride * 4, NCCL_UINT8, comm->nccl, nullptr);
+    if (ce == cudaSuccess && !nrc && w_stride) nrc = api.AllGather(s_w, d_w, w_stride * 4, NCCL_UINT8, comm->nccl, nullptr);
+    if (ce == cudaSuccess && !nrc) ce = cudaDeviceSynchronize();
+    if (ce != cudaSuccess || nrc) {
+        release();
+        return nrc ? set_error(MBPE_E_CUDA, "ncclAllGather of the unique chunks failed") : cuda_fail(ce, "sharded front end", __FILE__, __LINE__);
+    }
+    std::vector<const uint8_t *> texts(W);
+    std::vector<const uint32_t *> offs(W), ws(W);
+    std::vector<uint64_t> nbytes(W), nchunks(W);
+    for (int r = 0; r < W; r++) {
+        texts[r] = d_bytes + (size_t)r * max_t;
+        offs[r] = d_off + (size_t)r * off_stride;
+        ws[r] = d_w + (size_t)r * w_stride;
+        nbytes[r] = max_t + 64; // readable: the blocks are contiguous and the buffer has slack at its end
+        nchunks[r] = all[r].n_unique;
+    }
+    mbpe_device_corpus merged{};
+    rc = mbpe_pretok_merge_corpora(p, texts.data(), nbytes.data(), offs.data(), ws.data(), nchunks.data(), (uint32_t)W, &merged, nullptr);
+    uint64_t n_chunks_total = 0;
+    for (int r = 0; r < W; r++) n_chunks_total += all[r].n_unique;
+    release();
+    if (rc) return rc;
+    if (front_end_s) *front_end_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+    mbpe_trainer *tr = nullptr;
+    rc = mbpe_trainer_create_device(&merged, &tr);
+    mbpe_device_corpus_free(&merged);
+    if (rc) return rc;
+    rc = mbpe_trainer_run(tr, vocab_size, mode, MBPE_ENGINE_PERSISTENT, nullptr, merges_out, counts_out, n_merges_out, stats);
+    mbpe_trainer_destroy(tr);
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------------------

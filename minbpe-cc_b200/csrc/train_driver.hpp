@@ -225,6 +225,12 @@ class TrainLoop {
 // Extra backend interface:
 //   uint32_t world(), rank();
 //   void exchange(const XRec *d_send, uint32_t n_send, const XRec **d_all, const uint32_t **d_counts, uint32_t *stride);
+//   uint32_t resident_limit();            // 0: no resident program; else the largest best COUNT it takes (Ctl::big_count)
+//   void persistent_sharded(const Ctx &c); // persistent_program_sharded until status != ST_RUN
+// With engine 1 and a backend that has it, merges whose count is at most resident_limit() run in ONE resident CTA per
+// rank that exchanges the deltas itself (CUDA: stores into the peers' memory over NVLink, no launch and no host
+// round trip per merge); bigger merges, rebuilds and everything under engine 0 are driven from the host, one grid
+// kernel per phase and one all-gather per exchange.
 // The table is sized once for the worst case (no growth: the ranks' step sequences must stay identical).
 // ---------------------------------------------------------------------------------------------------------
 template <class BE>
@@ -278,6 +284,10 @@ class TrainLoopSharded {
         h.best_cand = NIL;
         h.theta = 1;
         h.big_limit = ~0u;
+        const uint32_t resident_limit = cfg.engine == 1 ? be_.resident_limit() : 0;
+        resident_limit_ = resident_limit;
+        h.big_count = resident_limit;
+        h.xstep = be_.xstep();
         h.cand_limit = cfg.cand_limit ? cfg.cand_limit : 4096;
         h.min_key_ever = ~0ull;
         h.live_tokens = n_tokens_local;
@@ -296,30 +306,32 @@ class TrainLoopSharded {
             if (h.status == ST_DONE || h.status == ST_EXHAUSTED) break;
             if (h.status == ST_NEED_REBUILD) {
                 rebuild(cfg, cap);
+            } else if (h.status == ST_FAILED) {
+                return -2;
+            } else if (h.status == ST_BIG_MERGE) { // the resident CTA handed this merge to the grid (same on every rank)
+                be_.one(PhTakeBig{c_});
+                if (step_grid(h)) return -1;
+                out->n_big++;
+            } else if (h.status == ST_RUN && resident_limit) {
+                be_.persistent_sharded(c_);
             } else if (h.status == ST_RUN && !h.selected) {
                 if (select_grid(h.n_cand)) return -1;
             } else if (h.status == ST_RUN) {
-                be_.par(PhHits{c_}, h.seg_len);
-                be_.par(PhExportBirths{c_}, 2ull * h.seg_len);
-                if (exchange_and_apply()) return -1;
-                be_.par(PhMutate{c_}, h.seg_len);
-                be_.par(PhSegAlloc{c_}, 4096);
-                be_.par(PhSegFill{c_}, 2ull * h.seg_len);
-                be_.one(PhFin{c_});
-                if (select_grid(h.n_cand)) return -1;
-                n_exchanges_++;
+                if (step_grid(h)) return -1;
             } else {
-                return -1; // ST_NEED_GROW / ST_BIG_MERGE cannot happen: fixed table, no resident CTA
+                return -1; // ST_NEED_GROW cannot happen: fixed table
             }
         }
+        be_.set_xstep(h.xstep);
         out->n_merges = h.step;
         out->final_status = h.status;
         out->min_key_ever = h.min_key_ever;
         out->n_pairs = h.n_pairs;
         out->table_slots = cap;
         out->n_rebuilds = n_rebuilds_;
-        out->n_big = n_exchanges_;
+        out->n_big = resident_limit ? out->n_big : n_exchanges_;
         out->rescan_bytes = h.rescan_bytes;
+        for (int i = 0; i < 8; i++) out->prof[i] = h.prof[i];
         if (h.step) {
             be_.download(h_merges, c_.merges_out, (uint64_t)h.step * 8);
             if (h_counts) be_.download(h_counts, c_.counts_out, (uint64_t)h.step * 4);
@@ -329,6 +341,18 @@ class TrainLoopSharded {
     }
 
   private:
+    // one merge driven from the host: the selection is done (h.selected), grid kernels + one all-gather
+    int step_grid(const Ctl &h) {
+        be_.par(PhHits{c_}, h.seg_len);
+        be_.par(PhExportBirths{c_}, 2ull * h.seg_len);
+        if (exchange_and_apply()) return -1;
+        be_.par(PhMutate{c_}, h.seg_len);
+        be_.par(PhSegAlloc{c_}, 4096);
+        be_.par(PhSegFill{c_}, 2ull * h.seg_len);
+        be_.one(PhFin{c_});
+        n_exchanges_++;
+        return select_grid(h.n_cand);
+    }
     int exchange_and_apply() {
         Ctl h;
         be_.download(&h, c_.ctl, sizeof h); // n_xrec of this rank
@@ -356,7 +380,7 @@ class TrainLoopSharded {
             }
         }
         be_.par(PhSelPick{c_}, n_cand);
-        be_.one(PhSelCommit{c_, 0});
+        be_.one(PhSelCommit{c_, resident_limit_ ? 1 : 0}); // (1: a merge above Ctl::big_count is marked ST_BIG_MERGE)
         return 0;
     }
     void rebuild(const TrainConfig &cfg, uint64_t cap) {
@@ -378,6 +402,7 @@ class TrainLoopSharded {
     BE &be_;
     Ctx c_;
     uint64_t n_rebuilds_ = 0, n_exchanges_ = 0;
+    uint32_t resident_limit_ = 0;
     int mode_ = 1;
 };
 

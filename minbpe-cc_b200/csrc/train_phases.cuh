@@ -69,6 +69,7 @@ enum Status : int32_t {
     ST_NEED_REBUILD = 3, // candidate list no longer holds the best pair
     ST_NEED_GROW = 4,    // pair table too full for the next step
     ST_BIG_MERGE = 5,    // selected pair has more occurrences than one CTA should walk
+    ST_FAILED = 6,       // sharded resident kernel: a peer did not answer in time / an exchange buffer overflowed
 };
 
 struct Node {
@@ -120,6 +121,9 @@ struct Ctl {
     uint32_t n_pairs;
     uint32_t arena_cursor;
     uint32_t big_limit; // segment length above which the persistent CTA yields
+    uint32_t big_count; // sharded resident CTA: best COUNT above which it yields (the count is the same on every rank, a
+                        // local segment length is not; live local occurrences <= count bounds the exchange volume); 0 = off
+    uint32_t xstep;     // sharded resident CTA: exchanges done so far (tag and buffer parity of the next one)
     uint32_t cand_limit; // candidate-list length that triggers a rebuild ...
     uint32_t cand_base;  // ... unless the list was already that long right after the last rebuild (massive ties)
     uint64_t min_key_ever;
@@ -598,7 +602,7 @@ MB_HD void phase_sel_commit(const Ctx &c, int persistent) {
     c.merges_out[2 * step + 1] = (uint32_t)key;
     c.counts_out[step] = MB_G(cmax);
     g->selected = 1;
-    if (persistent && seg_len > MB_G(big_limit)) g->status = ST_BIG_MERGE;
+    if (persistent && (seg_len > MB_G(big_limit) || (MB_G(big_count) && (uint32_t)MB_G(cmax) > MB_G(big_count)))) g->status = ST_BIG_MERGE;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -991,9 +995,10 @@ MB_HD void phase_init_fill(const Ctx &c, uint32_t tid, uint32_t nth) {
 // ---------------------------------------------------------------------------------------------------------
 // births: one record per pair created by this rank's occurrences in this step, with its local count so far
 namespace mbpe {
+template <bool S = false>
 MB_HD void phase_export_births(const Ctx &c, uint32_t tid, uint32_t nth) {
     Ctl *g = c.ctl;
-    const uint32_t n = ld_l2(&g->n_newp);
+    const uint32_t n = MB_G(n_newp);
     for (uint32_t i = tid; i < n; i += nth) {
         const uint32_t s = ld_l2(&c.newp[i]);
         uint32_t r = a_add(&g->n_xrec, 1u);
@@ -1009,9 +1014,10 @@ MB_HD void phase_export_births(const Ctx &c, uint32_t tid, uint32_t nth) {
 }
 // FIRST mode: after the local sel_fix_scan every rank knows ITS first live occurrence of each tied pair; the
 // global first is the minimum over ranks (positions are global)
+template <bool S = false>
 MB_HD void phase_export_fix(const Ctx &c, uint32_t tid, uint32_t nth) {
     Ctl *g = c.ctl;
-    const uint32_t n = ld_l2(&g->n_fix);
+    const uint32_t n = MB_G(n_fix);
     for (uint32_t i = tid; i < n; i += nth) {
         const uint32_t s = ld_l2(&c.fix[i]);
         XRec x;
@@ -1047,16 +1053,31 @@ MB_HD void phase_after_init_exchange(const Ctx &c) {
     g->n_xrec = 0;
     g->n_newp_own = 0;
 }
+// a record another rank wrote into this rank's memory while this kernel runs (resident sharded CTA: peer stores over
+// NVLink land in L2; an L1 line from the exchange before last must not answer)
+MB_HD XRec ld_xrec(const XRec *p) {
+#if MB_ON_DEVICE
+    const uint4 v = __ldcv(reinterpret_cast<const uint4 *>(p));
+    XRec x;
+    x.key = ((uint64_t)v.y << 32) | v.x;
+    x.delta = (int32_t)v.z;
+    x.pos = v.w;
+    return x;
+#else
+    return *p;
+#endif
+}
 // all[r * stride .. + counts[r]) = records of rank r; the own block is skipped
+template <bool S = false>
 MB_HD void phase_apply_foreign(const Ctx &c, const XRec *all, const uint32_t *counts, uint32_t stride, uint32_t world,
                                uint32_t my_rank, uint32_t tid, uint32_t nth) {
     Ctl *g = c.ctl;
-    const int32_t mode = ld_l2(&g->mode);
+    const int32_t mode = MB_G(mode);
     for (uint32_t r = 0; r < world; r++) {
         if (r == my_rank) continue;
         const uint32_t n = counts[r];
         for (uint32_t i = tid; i < n; i += nth) {
-            const XRec x = all[(uint64_t)r * stride + i];
+            const XRec x = ld_xrec(&all[(uint64_t)r * stride + i]);
             bool created;
             const uint32_t s = slot_upsert(c, x.key, &created);
             if (created) {
@@ -1124,14 +1145,8 @@ struct PhRebuildTheta {
     uint32_t want;
     MB_HD void operator()() const { phase_rebuild_theta<false>(c, want); }
 };
-struct PhExportBirths {
-    Ctx c;
-    MB_HD void operator()(uint32_t tid, uint32_t nth) const { phase_export_births(c, tid, nth); }
-};
-struct PhExportFix {
-    Ctx c;
-    MB_HD void operator()(uint32_t tid, uint32_t nth) const { phase_export_fix(c, tid, nth); }
-};
+MB_PHASE_PAR(PhExportBirths, phase_export_births)
+MB_PHASE_PAR(PhExportFix, phase_export_fix)
 struct PhResetXrec {
     Ctx c;
     MB_HD void operator()() const { c.ctl->n_xrec = 0; }
@@ -1144,15 +1159,17 @@ struct PhAfterInitExchange {
     Ctx c;
     MB_HD void operator()() const { phase_after_init_exchange(c); }
 };
-struct PhApplyForeign {
+template <bool S = false>
+struct PhApplyForeignT {
     Ctx c;
     const XRec *all;
     const uint32_t *counts;
     uint32_t stride, world, my_rank;
     MB_HD void operator()(uint32_t tid, uint32_t nth) const {
-        phase_apply_foreign(c, all, counts, stride, world, my_rank, tid, nth);
+        phase_apply_foreign<S>(c, all, counts, stride, world, my_rank, tid, nth);
     }
 };
+using PhApplyForeign = PhApplyForeignT<false>;
 struct PhRehash {
     Ctx c;
     const Slot *old;
@@ -1194,6 +1211,43 @@ MB_HD void persistent_program(const Ctx &c, Exec &ex) {
         }
         ex.par(PhHitsT<S>{c});
         ex.par2(PhMutateT<S>{c}, PhSegAllocT<S>{c}); // disjoint data: corpus nodes vs. new slots
+        ex.par(PhSegFillT<S>{c});
+        ex.one(PhFinT<S>{c});
+    }
+}
+
+// The resident program of SHARDED training: like persistent_program, plus one exchange of count deltas per merge
+// (and one more in FIRST mode when a tied pair lost its first occurrence). Exec also supplies
+//   bool select(c)           optional fast selection (device: fused_select in LEXICAL mode); false = not done
+//   bool exchange_apply(c)   send c.xrec[0 .. n_xrec) to every other rank, receive theirs, apply them (phase_apply_foreign);
+//                            false = failed (status is ST_FAILED)
+// Every rank runs the same sequence of steps and leaves the program at the same step: all decisions below are
+// functions of the replicated pair table only (never of a rank's local segment lengths).
+template <bool S, class Exec>
+MB_HD void persistent_program_sharded(const Ctx &c, Exec &ex) {
+    for (;;) {
+        if (ex.load(&c.ctl->status) != ST_RUN) return;
+        if (ex.load(&c.ctl->selected) == 0) {
+            if (!ex.select(c)) {
+                ex.par(PhSelMaxT<S>{c});
+                ex.par(PhSelTieT<S>{c});
+                ex.one(PhSelCheckT<S>{c});
+                if (ex.load(&c.ctl->status) == ST_RUN && ex.load(&c.ctl->n_fix) != 0) {
+                    ex.par(PhSelFixScanT<S>{c});
+                    ex.par(PhExportFixT<S>{c});
+                    if (!ex.exchange_apply(c)) return;
+                    ex.one(PhResetXrec{c});
+                    ex.par(PhSelFixTieT<S>{c});
+                }
+                ex.par(PhSelPickT<S>{c});
+                ex.one(PhSelCommitT<S>{c, 1});
+            }
+            if (ex.load(&c.ctl->status) != ST_RUN) return;
+        }
+        ex.par(PhHitsT<S>{c});
+        ex.par(PhExportBirthsT<S>{c});
+        if (!ex.exchange_apply(c)) return;
+        ex.par2(PhMutateT<S>{c}, PhSegAllocT<S>{c});
         ex.par(PhSegFillT<S>{c});
         ex.one(PhFinT<S>{c});
     }

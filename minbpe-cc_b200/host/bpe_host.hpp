@@ -73,6 +73,7 @@ int split_dedup_parallel(const Regex &re, const std::string &pattern, const uint
 
 // deterministic synthetic Zipfian UTF-8 corpus (SURVEY 8(d) input 3)
 void synth_corpus(uint64_t seed, uint8_t *out, uint64_t n, int n_threads);
+void synth_corpus_at(uint64_t seed, uint64_t first_block, uint8_t *out, uint64_t n, int n_threads);
 
 int hardware_threads();
 
@@ -103,6 +104,7 @@ class Tokenizer {
     int decode(const std::vector<Token> &tokens, bool verbose, std::string &out);                      // :725
     int load(const std::string &path, bool verbose);                                                   // :754
     int save(const std::string &path, bool write_vocab);                                               // :875
+    int save_vocab_karpathy(const std::string &path); // .vocab in karpathy/minbpe's layout
 
     const std::vector<std::pair<Token, Token>> &merges() const { return merges_; }
     const std::string &pattern() const { return pattern_; }
@@ -140,6 +142,9 @@ class Tokenizer {
     std::string error_;
 };
 
+int write_vocab_karpathy(const std::string &path, const std::vector<std::pair<std::string, Token>> &specials,
+                         const std::vector<std::pair<Token, Token>> &merges, const std::vector<std::string> &vocab,
+                         std::string *err);
 // .model / .vocab bytes (Tokenizer.h:878-918)
 int write_model_files(const std::string &path, const std::string &pattern,
                       const std::unordered_map<std::string, Token> &specials,

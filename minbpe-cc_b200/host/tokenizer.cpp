@@ -608,6 +608,135 @@ int write_model_files(const std::string &path, const std::string &pattern,
     return MBPE_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// .vocab in karpathy/minbpe's layout (base.py: save + render_token), the format the reference's README compares its
+// models with; the reference's own .vocab layout (Tokenizer.h:894-918) stays the default.
+//   [<left>][<right>] -> [<token>] <id>      for a merged token
+//   [<token>] <id>                             for a byte / special token
+// <token> = the bytes decoded as UTF-8 with U+FFFD for every maximal invalid subpart (Python's errors="replace"), and
+// every code point of general category C* written as \uXXXX. The categories are the linked PCRE2's (\p{C}).
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct ControlClass { // \p{C} of the linked PCRE2, asked once per code point and remembered
+    pcre2_code_8 *code = nullptr;
+    pcre2_match_data_8 *md = nullptr;
+    std::unordered_map<uint32_t, bool> memo;
+    ControlClass() {
+        int ec = 0;
+        size_t eo = 0;
+        code = pcre2_compile_8(reinterpret_cast<const uint8_t *>("\\p{C}"), 5, MBPE_PCRE2_UTF | MBPE_PCRE2_UCP, &ec, &eo, nullptr);
+        if (code) md = pcre2_match_data_create_from_pattern_8(code, nullptr);
+    }
+    ~ControlClass() {
+        if (md) pcre2_match_data_free_8(md);
+        if (code) pcre2_code_free_8(code);
+    }
+    bool is_c(uint32_t cp, const std::string &utf8) {
+        if (cp < 0x20 || (cp >= 0x7F && cp < 0xA0)) return true; // Cc
+        if (cp < 0x7F) return false;
+        auto it = memo.find(cp);
+        if (it != memo.end()) return it->second;
+        const bool c = code && md && pcre2_match_8(code, reinterpret_cast<const uint8_t *>(utf8.data()), utf8.size(), 0, 0, md, nullptr) >= 0;
+        memo[cp] = c;
+        return c;
+    }
+};
+
+std::string render_token(const std::string &t, ControlClass &cc) {
+    std::string out;
+    const size_t n = t.size();
+    auto cont = [&](size_t i, unsigned lo, unsigned hi) { return i < n && (unsigned char)t[i] >= lo && (unsigned char)t[i] <= hi; };
+    auto emit = [&](uint32_t cp, const std::string &utf8) {
+        if (cc.is_c(cp, utf8)) {
+            char buf[16];
+            snprintf(buf, sizeof buf, "\\u%04x", cp);
+            out += buf;
+        } else {
+            out += utf8;
+        }
+    };
+    for (size_t i = 0; i < n;) {
+        const unsigned b = (unsigned char)t[i];
+        size_t len = 0; // bytes of a well-formed sequence starting at i, 0 = ill-formed
+        size_t bad = 1; // ill-formed: length of the maximal subpart to replace by one U+FFFD
+        if (b < 0x80) {
+            len = 1;
+        } else if (b >= 0xC2 && b <= 0xDF) {
+            if (cont(i + 1, 0x80, 0xBF)) len = 2;
+        } else if (b >= 0xE0 && b <= 0xEF) {
+            const unsigned lo = b == 0xE0 ? 0xA0 : 0x80, hi = b == 0xED ? 0x9F : 0xBF;
+            if (cont(i + 1, lo, hi)) {
+                if (cont(i + 2, 0x80, 0xBF)) len = 3;
+                else bad = 2;
+            }
+        } else if (b >= 0xF0 && b <= 0xF4) {
+            const unsigned lo = b == 0xF0 ? 0x90 : 0x80, hi = b == 0xF4 ? 0x8F : 0xBF;
+            if (cont(i + 1, lo, hi)) {
+                if (cont(i + 2, 0x80, 0xBF)) {
+                    if (cont(i + 3, 0x80, 0xBF)) len = 4;
+                    else bad = 3;
+                } else {
+                    bad = 2;
+                }
+            }
+        }
+        if (len == 0) {
+            out += "\xEF\xBF\xBD";
+            i += bad;
+            continue;
+        }
+        uint32_t cp = b;
+        if (len == 2) cp = ((b & 0x1F) << 6) | ((unsigned char)t[i + 1] & 0x3F);
+        else if (len == 3) cp = ((b & 0x0F) << 12) | (((unsigned char)t[i + 1] & 0x3F) << 6) | ((unsigned char)t[i + 2] & 0x3F);
+        else if (len == 4)
+            cp = ((b & 0x07) << 18) | (((unsigned char)t[i + 1] & 0x3F) << 12) | (((unsigned char)t[i + 2] & 0x3F) << 6) |
+                 ((unsigned char)t[i + 3] & 0x3F);
+        emit(cp, t.substr(i, len));
+        i += len;
+    }
+    return out;
+}
+} // namespace
+
+// specials: (token, id) in the order they should be listed (karpathy lists them in registration order, after the merges)
+int write_vocab_karpathy(const std::string &path, const std::vector<std::pair<std::string, Token>> &specials,
+                         const std::vector<std::pair<Token, Token>> &merges, const std::vector<std::string> &vocab,
+                         std::string *err) {
+    std::ofstream vf(path, std::ios::out | std::ios::binary);
+    if (!vf.is_open()) {
+        std::cerr << "Failed to open .vocab file for writing: " << path << std::endl;
+        if (err) *err = "cannot open " + path;
+        return MBPE_E_IO;
+    }
+    ControlClass cc;
+    for (size_t id = 0; id < vocab.size(); id++) {
+        const std::string s = render_token(vocab[id], cc);
+        if (id >= 256 && id - 256 < merges.size()) {
+            const auto &[a, b] = merges[id - 256];
+            vf << '[' << render_token(vocab[a], cc) << "][" << render_token(vocab[b], cc) << "] -> [" << s << "] " << id << '\n';
+        } else {
+            vf << '[' << s << "] " << id << '\n';
+        }
+    }
+    for (const auto &[tok, id] : specials) vf << '[' << render_token(tok, cc) << "] " << id << '\n';
+    vf.close();
+    if (!vf) {
+        if (err) *err = "write failed: " + path;
+        return MBPE_E_IO;
+    }
+    return MBPE_OK;
+}
+
+int Tokenizer::save_vocab_karpathy(const std::string &path) {
+    if (merges_.empty()) {
+        error_ = "no merges to save";
+        return MBPE_E_EMPTY;
+    }
+    std::vector<std::pair<std::string, Token>> sp(special_tokens_.begin(), special_tokens_.end());
+    std::sort(sp.begin(), sp.end(), [](const auto &x, const auto &y) { return x.second < y.second; }); // by id: deterministic
+    return write_vocab_karpathy(path, sp, merges_, vocab_, &error_);
+}
+
 int Tokenizer::save(const std::string &path, bool write_vocab) {
     if (merges_.empty()) { // assert in the reference (Tokenizer.h:876)
         error_ = "no merges to save";
@@ -882,4 +1011,40 @@ extern "C" int mbpe_synth_corpus(uint64_t seed, uint8_t *out, uint64_t n, int n_
     if (!out && n) return fail(MBPE_E_INVALID, "null argument");
     synth_corpus(seed, out, n, n_threads);
     return MBPE_OK;
+}
+
+extern "C" int mbpe_synth_corpus_at(uint64_t seed, uint64_t first_block, uint8_t *out, uint64_t n, int n_threads) {
+    if (!out && n) return fail(MBPE_E_INVALID, "null argument");
+    synth_corpus_at(seed, first_block, out, n, n_threads);
+    return MBPE_OK;
+}
+
+extern "C" int mbpe_write_vocab_karpathy(const char *path, const char *special_contents, uint64_t special_len,
+                                         const uint32_t *merges, uint32_t n_merges) {
+    if (!path || (n_merges && !merges)) return fail(MBPE_E_INVALID, "null argument");
+    std::vector<std::pair<std::string, Token>> specials; // file order = registration order
+    if (special_contents && special_len) {
+        std::istringstream iss(std::string(special_contents, special_len));
+        std::string key;
+        Token value;
+        while (iss >> key >> value) specials.emplace_back(key, value);
+    }
+    std::vector<std::pair<Token, Token>> m;
+    std::vector<std::string> vocab;
+    for (int i = 0; i < 256; i++) vocab.push_back(std::string(1, static_cast<char>(i)));
+    for (uint32_t i = 0; i < n_merges; i++) {
+        Token a = merges[2 * i], b = merges[2 * i + 1];
+        if (a >= vocab.size() || b >= vocab.size()) return fail(MBPE_E_INVALID, "merge names an id that does not exist yet");
+        m.emplace_back(a, b);
+        vocab.push_back(vocab[a] + vocab[b]);
+    }
+    std::string err;
+    int rc = write_vocab_karpathy(path, specials, m, vocab, &err);
+    return rc ? fail(rc, err) : MBPE_OK;
+}
+
+extern "C" int mbpe_tokenizer_save_vocab_karpathy(mbpe_tokenizer *t, const char *path) {
+    if (!t || !path) return fail(MBPE_E_INVALID, "null argument");
+    int rc = t->tk.save_vocab_karpathy(path);
+    return rc ? fail(rc, t->tk.error()) : MBPE_OK;
 }

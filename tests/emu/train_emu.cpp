@@ -115,6 +115,32 @@ struct HostBE {
         Exec ex{this};
         persistent_program<false>(c, ex);
     }
+    // sharded resident program: the exchange is the same barrier + memcpy as the host-driven one
+    struct ExecSharded : Exec {
+        bool select(const Ctx &) { return false; }
+        bool exchange_apply(const Ctx &c) {
+            const mbpe::XRec *all = nullptr;
+            const uint32_t *counts = nullptr;
+            uint32_t stride = 0;
+            if (c.ctl->n_xrec > c.xrec_cap) {
+                c.ctl->status = ST_FAILED;
+                return false;
+            }
+            be->exchange(c.xrec, c.ctl->n_xrec, &all, &counts, &stride);
+            par(PhApplyForeign{c, all, counts, stride, be->world(), be->rank()});
+            c.ctl->xstep++;
+            return true;
+        }
+    };
+    uint32_t resident_count_limit = 0, xstep_ = 0;
+    uint32_t resident_limit() const { return resident_count_limit; }
+    uint32_t xstep() const { return xstep_; }
+    void set_xstep(uint32_t v) { xstep_ = v; }
+    void persistent_sharded(const Ctx &c) {
+        n_launch++;
+        ExecSharded ex{{this}};
+        persistent_program_sharded<false>(c, ex);
+    }
 };
 
 extern "C" int emu_train(const uint32_t *tokens, uint64_t n_tokens, const uint64_t *off, uint64_t n_chunks,
@@ -139,10 +165,12 @@ extern "C" int emu_train(const uint32_t *tokens, uint64_t n_tokens, const uint64
 
 // `world` emulated ranks, one host thread each; rank r owns a contiguous, token-balanced range of the chunks.
 // Every rank must end with the same merge list; rank 0's is returned, rc 7 if any rank disagrees.
+// resident_limit: 0 = every step driven from the "host" (engine 0); else merges whose count is at most that run in the
+// resident program (engine 1) and the others fall back to the host-driven step.
 extern "C" int emu_train_sharded(const uint32_t *tokens, uint64_t n_tokens, const uint64_t *off, uint64_t n_chunks,
                                  const uint32_t *weight, uint32_t vocab_size, int mode, uint32_t world, uint32_t nth,
-                                 int order, uint32_t cand_want, uint32_t *merges_out, int32_t *counts_out,
-                                 uint32_t *n_merges_out) {
+                                 int order, uint32_t cand_want, uint32_t resident_limit, uint32_t *merges_out,
+                                 int32_t *counts_out, uint32_t *n_merges_out) {
     HostComm comm(world);
     std::vector<uint64_t> first(world + 1, n_chunks);
     first[0] = 0;
@@ -163,11 +191,12 @@ extern "C" int emu_train_sharded(const uint32_t *tokens, uint64_t n_tokens, cons
         be.comm = &comm;
         be.my_rank = r;
         be.rng += r * 0x1234567ull;
+        be.resident_count_limit = resident_limit;
         const uint64_t c0 = first[r], c1 = first[r + 1], t0 = off[c0], t1 = off[c1];
         std::vector<uint64_t> loff(c1 - c0 + 1);
         for (uint64_t c = c0; c <= c1; c++) loff[c - c0] = off[c] - t0;
         TrainLoopSharded<HostBE> loop(be);
-        TrainConfig cfg{vocab_size, mode, 0, ~0u, cand_want, cand_want * 4 + 64, 0};
+        TrainConfig cfg{vocab_size, mode, resident_limit ? 1 : 0, ~0u, cand_want, cand_want * 4 + 64, 0};
         TrainOutcome o;
         rcs[r] = loop.run(tokens + t0, loff.data(), weight + c0, t1 - t0, c1 - c0, t0, n_tokens, cfg, m[r].data(),
                           cn[r].data(), &o);

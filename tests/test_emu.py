@@ -103,7 +103,7 @@ def test_empty_and_pairless_inputs(emu):
 
 
 # ---- sharded training: `world` emulated ranks, one host thread each -------------------------
-def _emu_sharded(t, o, w, vocab, mode, world, nth=16, order=2, want=8):
+def _emu_sharded(t, o, w, vocab, mode, world, nth=16, order=2, want=8, resident_limit=0):
     L = C.CDLL(EMU_LIB)
     n = max(vocab - 256, 1)
     m = np.zeros((n, 2), np.uint32)
@@ -112,7 +112,7 @@ def _emu_sharded(t, o, w, vocab, mode, world, nth=16, order=2, want=8):
     P = lambda a, ty: a.ctypes.data_as(C.POINTER(ty))
     rc = L.emu_train_sharded(P(t, C.c_uint32), C.c_uint64(len(t)), P(o, C.c_uint64), C.c_uint64(len(o) - 1),
                              P(w, C.c_uint32), C.c_uint32(vocab), {"first": 0, "lexical": 1}[mode], world, nth, order,
-                             C.c_uint32(want), P(m, C.c_uint32), P(c, C.c_int32), C.byref(nm))
+                             C.c_uint32(want), C.c_uint32(resident_limit), P(m, C.c_uint32), P(c, C.c_int32), C.byref(nm))
     return rc, m[:nm.value], c[:nm.value]
 
 
@@ -129,7 +129,9 @@ def test_sharded_ranks_agree_and_match_reference(emu, oracle, manifest, name):
     text = golden_data(e["input"])
     t, o, w = oracle.flatten(oracle.chunks_of(text, e["encoder"]), True)
     _, oc = oracle.train(t, o, w, e["vocab_size"], e["mode"])
-    for world in (2, 3):
-        rc, m, c = _emu_sharded(t, o, w, e["vocab_size"], e["mode"], world)
-        assert rc == 0, (name, world, rc)
-        assert m.shape == gm.shape and (m == gm).all() and (c == oc).all(), (name, world)
+    # resident_limit 0: every step driven from the host; 40: merges with a count <= 40 run in the resident program (the
+    # exchange happens inside it, FIRST mode's extra exchange too) and the others fall back; 1 << 30: all resident
+    for world, limit in ((2, 0), (3, 0), (2, 40), (3, 1 << 30), (2, 1 << 30)):
+        rc, m, c = _emu_sharded(t, o, w, e["vocab_size"], e["mode"], world, resident_limit=limit)
+        assert rc == 0, (name, world, limit, rc)
+        assert m.shape == gm.shape and (m == gm).all() and (c == oc).all(), (name, world, limit)

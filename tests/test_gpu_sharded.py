@@ -28,15 +28,34 @@ def _worker(rank, world, port, ret):
 
     comm = pkg.Comm(rank, world, rank, bcast)
     ok = True
-    for name in ("ts512_gpt4_first", "ts512_gpt4_lexical", "ts400_basic_first"):
-        import json
+    import json
+    for name in ("ts512_gpt4_first", "ts512_gpt4_lexical", "ts400_basic_first", "str_runs_c_gpt4_first",
+                 "str_exhaust_basic_lexical", "sample512_gpt4_first"):
         e = json.load(open(os.path.join(GOLDEN, "manifest.json")))["train"][name]
         _, _, gm = O.read_model(os.path.join(GOLDEN, "models", name + ".model"))
         text = golden_data(e["input"])
         tok, off, w, _ = pkg.split_dedup(pkg.patterns()[e["encoder"]], text)
-        m, c, st = comm.train(tok, off, w, e["vocab_size"], e["mode"])
-        ok = ok and m.shape == gm.shape and bool((m == gm).all())
+        _, oc = O.train(tok, off, w, e["vocab_size"], e["mode"])
+        tr = pkg.ShardedTrainer(comm, tok, off, w)
+        # resident engine (one CTA per rank, exchange through the peers' mapped memory) and host-driven engine
+        for engine in ("persistent", "stepwise", "persistent"):
+            m, c, st = tr.run(e["vocab_size"], e["mode"], engine=engine)
+            ok = ok and m.shape == gm.shape and bool((m == gm).all()) and bool((c == oc).all())
+        tr.close()
+    # a corpus large enough for early merges above the resident limit (host-driven steps in between resident ones)
+    text = pkg.synth_corpus(0x5EED0021, 24 << 20).tobytes()
+    tok, off, w, _ = pkg.split_dedup(pkg.patterns()["gpt4"], text)
+    for mode in ("lexical", "first"):
+        om, oc = O.train(tok, off, w, 256 + 1500, mode)
+        m, c, st = comm.train(tok, off, w, 256 + 1500, mode)
+        ok = ok and m.shape == om.shape and bool((m == om).all()) and bool((c == oc).all())
+        # the text itself sharded (parts cut at 1 MiB block ends = chunk boundaries): split + dedup per rank, one all-gather
+        # of the unique chunks, merge loop on the combined corpus
+        cut = [0, 11 << 20, len(text)] if world == 2 else [len(text) * r // world // (1 << 20) * (1 << 20) for r in range(world)] + [len(text)]
+        m, c, st = comm.train_text(text[cut[rank]:cut[rank + 1]], 256 + 1500, mode)
+        ok = ok and m.shape == om.shape and bool((m == om).all()) and bool((c == oc).all())
     ret[rank] = ok
+    ret["resident"] = comm.resident()
     comm.close()
     dist.barrier()
     dist.destroy_process_group()
@@ -51,3 +70,4 @@ def test_sharded_training_two_gpus(pkg):
         ret = mgr.dict()
         mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
         assert ret[0] and ret[1]
+        print("resident exchange available:", ret["resident"])

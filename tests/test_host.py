@@ -193,3 +193,78 @@ def test_failed_load_leaves_the_tokenizer_as_it_was(pkg, tmp_path):
     out = tmp_path / "again.model"
     tk.save(out)  # pattern, specials and merges still those of the good file: byte-identical model
     assert out.read_bytes() == open(good, "rb").read()
+
+
+def _karpathy_vocab_lines(merges, specials):
+    """karpathy/minbpe base.py: save() + render_token(), restated with Python's own UTF-8 decoder and unicodedata"""
+    import unicodedata
+
+    def render(t: bytes) -> str:
+        s = t.decode("utf-8", errors="replace")
+        return "".join(ch if unicodedata.category(ch)[0] != "C" else f"\\u{ord(ch):04x}" for ch in s)
+
+    vocab = {i: bytes([i]) for i in range(256)}
+    for i, (a, b) in enumerate(merges):
+        vocab[256 + i] = vocab[int(a)] + vocab[int(b)]
+    lines = []
+    for idx, tok in vocab.items():
+        if idx >= 256:
+            a, b = merges[idx - 256]
+            lines.append(f"[{render(vocab[int(a)])}][{render(vocab[int(b)])}] -> [{render(tok)}] {idx}\n")
+        else:
+            lines.append(f"[{render(tok)}] {idx}\n")
+    for tok, idx in specials:
+        lines.append(f"[{render(tok.encode())}] {idx}\n")
+    return "".join(lines).encode("utf-8")
+
+
+@pytest.mark.parametrize("model", ["ts512_gpt4_first_special", "str_unicode_gpt4_first", "sample512_gpt4_lexical"])
+def test_karpathy_format_vocab(pkg, oracle, tmp_path, model):
+    """the .vocab layout of karpathy/minbpe as an option (partial UTF-8 sequences inside tokens become
+    U+FFFD by Python's maximal-subpart rule, control characters are escaped)"""
+    _, sp, merges = oracle.read_model(os.path.join(GOLDEN, "models", model + ".model"))
+    specials = [(k if isinstance(k, str) else k.decode(), int(v)) for k, v in (sp.items() if isinstance(sp, dict) else sp)]
+    contents = "".join(f"{k} {v}\n" for k, v in specials).encode()
+    out = tmp_path / "k.vocab"
+    pkg.write_vocab_karpathy(out, contents, merges)
+    assert out.read_bytes() == _karpathy_vocab_lines(merges, specials)
+
+
+def test_karpathy_render_of_broken_utf8_and_controls(pkg, tmp_path):
+    # merges that build: a truncated 3-byte sequence, an overlong lead, a surrogate half, an astral char, a C1 control, U+200B (Cf)
+    seqs = [b"\xe4\xb8", b"\xc0\xaf", b"\xed\xa0\x80", b"\xf0\x9f\x98\x80", b"\xc2\x85", b"\xe2\x80\x8b", b"\xf4\x90\x80\x80", b"a\x00\x7f"]
+    merges, ids = [], {}
+    for s in seqs:
+        cur = s[0]
+        for b in s[1:]:
+            key = (cur, b)
+            if key not in ids:
+                ids[key] = 256 + len(merges)
+                merges.append(key)
+            cur = ids[key]
+    out = tmp_path / "k.vocab"
+    pkg.write_vocab_karpathy(out, b"", np.asarray(merges, np.uint32))
+    assert out.read_bytes() == _karpathy_vocab_lines(merges, [])
+
+
+def test_load_of_a_100k_merge_model_is_fast(pkg, tmp_path):
+    """big-vocab load (config 5 has 99 744 merges). Linear in the vocabulary bytes, well under a second."""
+    import time
+    n = 99744
+    rng = np.random.default_rng(3)
+    seen, rows = set(), []
+    while len(rows) < n:  # distinct pairs of earlier ids, biased towards short tokens like a real model
+        a, b = (int(x) for x in rng.integers(0, min(256 + len(rows), 3000), 2))
+        if (a, b) not in seen:
+            seen.add((a, b))
+            rows.append((a, b))
+    merges = np.asarray(rows, np.uint32)
+    path = tmp_path / "big.model"
+    pkg.write_model(path, pkg.patterns()["gpt4"], None, merges)
+    tk = pkg.Tokenizer(pkg.patterns()["gpt4"])
+    t0 = time.time()
+    tk.load(path)
+    dt = time.time() - t0
+    assert np.array_equal(tk.merges(), merges)
+    assert dt < 2.0, dt
+    print(f"load of {len(merges)} merges: {dt * 1e3:.0f} ms")
