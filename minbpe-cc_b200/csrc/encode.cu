@@ -148,28 +148,30 @@ struct DecArgs {
 };
 
 // A tile = DEC_THREADS x DEC_IPT consecutive ids. Each thread owns DEC_IPT consecutive ids: coalesced 16-byte id
-// loads, (offset, length) from the vocabulary index (128 KB for 32k ids: L1/L2 resident), block scan + look-back for
-// the tile's place in the byte stream, then every token's bytes are gathered into shared memory and the tile leaves
-// as aligned 4-byte words, 128 bytes per warp store (tokens average 2-3 bytes: per-thread stores would touch one
-// sector each). Tiles whose bytes do not fit the staging buffer store directly.
+// loads; one 8-byte load per id from a packed table answers "how long, which bytes" for tokens of up to 7 bytes (nearly
+// all of them; the table is 8 B x vocab, L2 resident); block scan of the lengths; then warp 0 resolves the tile's place in
+// the byte stream by decoupled look-back (128 predecessors per round trip) and takes the NEXT tile's ticket WHILE the other
+// warps gather the tile's bytes in shared memory at tile-local offsets. The tile leaves as aligned 4-byte words (128 bytes
+// per warp store): the misalignment of the tile's base is absorbed by a funnel shift over the shared-memory image.
+// Tiles whose bytes do not fit the staging buffer store directly.
 constexpr int DEC_THREADS = 256, DEC_IPT = 8, DEC_IDS = DEC_THREADS * DEC_IPT;
 constexpr uint32_t DEC_STAGE = 24576; // bytes staged per tile (avg ~5 KB)
 
 struct DecSmem {
-    alignas(16) uint8_t stage[DEC_STAGE + 16];
+    alignas(16) uint32_t stage[DEC_STAGE / 4 + 4];
     uint32_t s_warp[DEC_THREADS / 32];
-    uint32_t s_tile;
+    uint32_t s_tile[2];
     unsigned long long s_base;
 };
 
 __global__ void __launch_bounds__(DEC_THREADS) k_decode_tiles(const DecArgs a) {
     __shared__ DecSmem sm;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) sm.s_tile = atomicAdd(a.ticket, 1u);
-        __syncthreads();
-        const uint32_t tile = sm.s_tile;
+    uint8_t *const stage8 = reinterpret_cast<uint8_t *>(sm.stage);
+    if (tid == 0) sm.s_tile[0] = atomicAdd(a.ticket, 1u); // tiles start in order: look-back cannot deadlock
+    __syncthreads();
+    for (uint32_t it = 0;; it++) {
+        const uint32_t tile = sm.s_tile[it & 1];
         if (tile >= a.n_tiles) return;
         const uint64_t k0 = (uint64_t)tile * DEC_IDS + (uint64_t)tid * DEC_IPT;
         uint32_t id[DEC_IPT];
@@ -181,9 +183,7 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode_tiles(const DecArgs a) {
 #pragma unroll
             for (int j = 0; j < DEC_IPT; j++) id[j] = k0 + j < a.n_ids ? __ldcs(a.ids + k0 + j) : 0xFFFFFFFFu;
         }
-        // one 8-byte load per id answers "how long, which bytes" for tokens of up to 7 bytes (nearly all of them);
-        // longer tokens and special tokens are resolved again through the index when their bytes are copied
-        unsigned long long pk[DEC_IPT]; // low byte: length (0xFF: long / special -> resolve()), then the bytes
+        unsigned long long pk[DEC_IPT]; // low byte: length (0xFF: long / special -> resolved through the index), then the bytes
         uint32_t len[DEC_IPT], sum = 0;
         auto find_special = [&](uint32_t idv) -> int { // special tokens override the vocabulary (Tokenizer.h:733)
             int lo = 0, hi = (int)a.n_sp - 1;
@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode_tiles(const DecArgs a) {
             sum += len[j];
         }
         uint32_t incl = sum;
+#pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += v;
@@ -232,54 +233,64 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode_tiles(const DecArgs a) {
             if (w < (int)warp) warp_base += v;
             total += v;
         }
-        if (warp == 0) {
-            const uint64_t b = lookback_base(a.status, tile, total);
-            if (lane == 0) sm.s_base = b;
+        if (warp == 0) { // the other warps gather their bytes meanwhile
+            const uint64_t b = lookback_base<4>(a.status, tile, total);
+            if (lane == 0) {
+                sm.s_base = b;
+                sm.s_tile[(it + 1) & 1] = atomicAdd(a.ticket, 1u); // (this tile's size is published: successors do not wait for us)
+            }
         }
-        __syncthreads();
-        const uint64_t base = sm.s_base;
-        if (a.out) {
-            // the staged image starts at the 4-byte boundary below `base`: stage[pad + i] = byte i of the tile
-            const uint32_t pad = (uint32_t)(base & 3);
-            const bool via_smem = pad + total <= DEC_STAGE && base + total <= a.out_cap;
-            uint32_t loc = warp_base + (incl - sum);
+        const bool via_smem = a.out != nullptr && total <= DEC_STAGE;
+        const uint32_t loc0 = warp_base + (incl - sum);
+        // the bytes of this thread's tokens -> dst[0 ..), dst = the shared-memory image or the stream itself
+        auto emit = [&](uint8_t *dst, uint64_t room) {
+            uint32_t loc = 0;
 #pragma unroll
             for (int j = 0; j < DEC_IPT; j++) {
                 if (len[j] == 0) continue;
-                if ((pk[j] & 0xFF) != 0xFF) { // bytes are in the register
-                    unsigned long long v = pk[j] >> 8;
-                    if (via_smem) {
-                        for (uint32_t i = 0; i < len[j]; i++, v >>= 8) sm.stage[pad + loc + i] = (uint8_t)v;
-                    } else if (base + loc + len[j] <= a.out_cap) {
-                        for (uint32_t i = 0; i < len[j]; i++, v >>= 8) a.out[base + loc + i] = (uint8_t)v;
-                    }
-                } else {
-                    const uint8_t *src = (pk[j] & PK_SPECIAL) ? a.sp_bytes + __ldg(&a.sp_off[(uint32_t)(pk[j] >> 8)])
-                                                                : a.v_bytes + __ldg(&a.v_off[id[j]]);
-                    if (via_smem) {
-                        for (uint32_t i = 0; i < len[j]; i++) sm.stage[pad + loc + i] = __ldg(src + i);
-                    } else if (base + loc + len[j] <= a.out_cap) {
-                        for (uint32_t i = 0; i < len[j]; i++) a.out[base + loc + i] = __ldg(src + i);
+                if (loc + len[j] <= room) {
+                    if ((pk[j] & 0xFF) != 0xFF) { // bytes are in the register
+                        unsigned long long v = pk[j] >> 8;
+                        for (uint32_t i = 0; i < len[j]; i++, v >>= 8) dst[loc + i] = (uint8_t)v;
+                    } else {
+                        const uint8_t *src = (pk[j] & PK_SPECIAL) ? a.sp_bytes + __ldg(&a.sp_off[(uint32_t)(pk[j] >> 8)])
+                                                                    : a.v_bytes + __ldg(&a.v_off[id[j]]);
+                        for (uint32_t i = 0; i < len[j]; i++) dst[loc + i] = __ldg(src + i);
                     }
                 }
                 loc += len[j];
             }
-            if (via_smem) {
-                __syncthreads();
-                const uint64_t w0 = base - pad;                       // 4-byte aligned (out is a device allocation)
+        };
+        if (via_smem) emit(stage8 + loc0, ~0ull);
+        __syncthreads();
+        const uint64_t base = sm.s_base;
+        if (a.out) {
+            if (via_smem && base + total <= a.out_cap) {
+                // global word k of the tile = bytes [4k - pad, 4k - pad + 4) of the image; whole words by funnel shift
+                const uint32_t pad = (uint32_t)(base & 3), sh = ((4 - pad) & 3) * 8;
+                const uint64_t w0 = base - pad; // 4-byte aligned (out is a device allocation)
                 const uint32_t n_words = (pad + total + 3) >> 2;
-                const uint32_t *sw = reinterpret_cast<const uint32_t *>(sm.stage);
-                for (uint32_t w = tid; w < n_words; w += DEC_THREADS) {
-                    const uint32_t lo = w * 4, hi = lo + 4;
-                    if (lo >= pad && hi <= pad + total) {
-                        __stcs(reinterpret_cast<uint32_t *>(a.out + w0) + w, sw[w]);
+                uint32_t *const gw = reinterpret_cast<uint32_t *>(a.out + w0);
+                for (uint32_t k = tid; k < n_words; k += DEC_THREADS) {
+                    const int lo = (int)(4 * k) - (int)pad; // tile-local offset of the word's first byte
+                    if (lo >= 0 && (uint32_t)lo + 4 <= total) {
+                        const uint32_t j = (uint32_t)lo >> 2;
+                        const uint32_t v = pad ? __funnelshift_r(sm.stage[j], sm.stage[j + 1], sh) : sm.stage[j];
+                        __stcs(gw + k, v);
                     } else { // first / last word of the tile: shared with the neighbouring tiles, byte stores
-                        for (uint32_t i = max(lo, pad); i < min(hi, pad + total); i++) a.out[w0 + i] = sm.stage[i];
+                        for (int i = lo < 0 ? 0 : lo; i < lo + 4 && (uint32_t)i < total; i++) a.out[base + i] = stage8[i];
                     }
                 }
+            } else if (via_smem) { // the end of a buffer that is too small: what fits, byte by byte
+                for (uint32_t i = tid; i < total; i += DEC_THREADS)
+                    if (base + i < a.out_cap) a.out[base + i] = stage8[i];
+            } else {
+                const uint64_t at = base + loc0;
+                emit(a.out + at, at < a.out_cap ? a.out_cap - at : 0);
             }
         }
         if (tile == a.n_tiles - 1 && tid == 0) *a.d_n_out = base + total;
+        // (the image is rewritten only after the next tile's first barrier, which every thread reaches after its stores)
     }
 }
 } // namespace mbpe
@@ -310,6 +321,7 @@ struct mbpe_encoder {
     unsigned long long *d_status = nullptr;
     uint64_t status_cap = 0;
     uint32_t *d_small = nullptr; // [0] ticket, [1] n_long, [2] overflow, [3] scanned chunks
+    unsigned long long *d_prof = nullptr; // MBPE_DEBUG: cycles per phase of k_encode_tiles (ENC_PROF_*)
     unsigned long long *d_n_out = nullptr;
     uint32_t *d_long_list = nullptr;
     uint64_t long_cap = 0;
@@ -430,6 +442,10 @@ static int encoder_create_impl(mbpe_encoder *e, const uint32_t *merges, uint32_t
     }
     MB_CUDA(cudaMalloc(&e->d_small, 16));
     MB_CUDA(cudaMalloc(&e->d_n_out, 8));
+    if (getenv("MBPE_DEBUG")) {
+        MB_CUDA(cudaMalloc(&e->d_prof, ENC_PROF_N * 8));
+        MB_CUDA(cudaMemset(e->d_prof, 0, ENC_PROF_N * 8));
+    }
     MB_CUDA(cudaMalloc(&e->d_sp_ids, 4));
     MB_CUDA(cudaMalloc(&e->d_sp_off, 8));
     MB_CUDA(cudaMalloc(&e->d_sp_bytes, 1));
@@ -506,7 +522,7 @@ extern "C" void mbpe_encoder_destroy(mbpe_encoder *e) {
     cudaSetDevice(e->device);
     void *ps[] = {e->d_slots, e->d_voff, e->d_vbytes, e->d_vpack, e->d_sp_ids, e->d_sp_off, e->d_sp_bytes, e->d_status, e->d_small,
                   e->d_n_out, e->d_long_list, e->d_scratch_a, e->d_scratch_b, e->d_cache, e->d_cache_small, e->d_cache_log,
-                  e->d_cache_ctr, e->d_cache_arena, e->d_esp_ids, e->d_esp_off, e->d_esp_bytes};
+                  e->d_cache_ctr, e->d_cache_arena, e->d_esp_ids, e->d_esp_off, e->d_esp_bytes, e->d_prof};
     for (void *p : ps) cudaFree(p);
     free_host_pipe(e);
     if (e->pipe_stream) cudaStreamDestroy(e->pipe_stream);
@@ -674,6 +690,7 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
     a.long_cap = (uint32_t)e->long_cap;
     a.overflow = e->d_small + 2;
     a.miss_count = e->d_small + 3;
+    a.prof = e->d_prof;
     // cp.async.bulk needs 16-byte aligned sources (device allocations are; offsets into them may not be)
     a.bulk = ((((uintptr_t)d_bytes) | ((uintptr_t)d_off)) & 15) == 0 && !getenv("MBPE_ENC_NO_BULK");
     if (const char *ab = getenv("MBPE_ENC_ABLATE")) a.ablate = (uint32_t)atoi(ab);
@@ -772,6 +789,15 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
         fprintf(stderr, "[mbpe] encode: %llu chunks, %u scanned (cache misses), %u long, cache entries small %u of %u, big %u of %u%s\n",
                 (unsigned long long)n_chunks, small[3], small[1], ctr[2], e->small_slots, ctr[1], e->cache_slots,
                 a.bulk ? ", bulk staging" : ", cooperative staging (unaligned buffers)");
+        if (e->d_prof) {
+            unsigned long long pr[ENC_PROF_N];
+            MB_CUDA(cudaMemcpy(pr, e->d_prof, sizeof pr, cudaMemcpyDeviceToHost));
+            MB_CUDA(cudaMemset(e->d_prof, 0, sizeof pr));
+            const double t = pr[7] ? (double)pr[7] : 1.0;
+            fprintf(stderr, "[mbpe] encode tiles %llu, cycles per tile: wait data %.0f, fast path %.0f, slow list %.0f, count scan %.0f, "
+                            "look-back+gather %.0f, fetch next %.0f, store %.0f\n",
+                    pr[7], pr[0] / t, pr[1] / t, pr[2] / t, pr[3] / t, pr[4] / t, pr[5] / t, pr[6] / t);
+        }
     }
     return MBPE_OK;
 }

@@ -92,6 +92,9 @@ struct CacheLogEntry {
     uint32_t ids[31];
 };
 constexpr uint32_t CACHE_MAX_LEN = 31, CACHE_INLINE_IDS = 7;
+// An entry lives at most this many slots from its home: inserts give up beyond it (the chunk is simply not cached), so
+// lookups may stop there too -- no probe loop depends on the table having a free slot.
+constexpr uint32_t CACHE_MAX_PROBES = 64;
 
 struct ChunkCache {
     SmallSlot *small; // nullptr = caches disabled
@@ -133,7 +136,7 @@ __global__ void k_cache_insert(ChunkCache cc) {
             const uint32_t w0 = (uint32_t)k0, w1 = (uint32_t)(k0 >> 32), w2 = (uint32_t)k1;
             const uint32_t w3 = (uint32_t)(k1 >> 32) | (len << 24); // byte 15 is free: len <= 15
             uint32_t h = small_hash(w0, w1, w2, w3) >> cc.small_shift;
-            for (;;) {
+            for (uint32_t probes = 0; probes < CACHE_MAX_PROBES; probes++) {
                 SmallSlot *s = &cc.small[h];
                 uint32_t cur = *((volatile uint32_t *)&s->k[3]);
                 if (cur == 0) {
@@ -159,7 +162,7 @@ __global__ void k_cache_insert(ChunkCache cc) {
         }
         if (*((volatile uint32_t *)cc.used) * 2 > cc.mask) continue; // half full: stop learning
         uint32_t h = cache_hash(k0, k1, k2, k3) & cc.mask;
-        for (;;) {
+        for (uint32_t probes = 0; probes < CACHE_MAX_PROBES; probes++) {
             unsigned long long *claim = reinterpret_cast<unsigned long long *>(&cc.slots[h].k[3]);
             unsigned long long cur = *((volatile unsigned long long *)claim);
             if (cur == 0) {
@@ -244,10 +247,16 @@ struct EncArgs {
     uint32_t *overflow;          // set when out_cap is too small
     uint32_t *miss_count;        // chunks that went through the scan (statistics)
     uint32_t bulk;               // bytes / off are 16-byte aligned: stage with cp.async.bulk
+    unsigned long long *prof;    // optional: SM cycles per phase summed over CTAs (thread 0's clock), see ENC_PROF_*
     uint32_t ablate;             // MBPE_ENC_ABLATE (profiling only; 1, 2, 4 give WRONG results): 1 no look-back wait,
-                                 // 2 no cache probe (every short chunk "hits" with two fake ids), 4 no id stores
+                                 // 2 no cache probe (every short chunk "hits" with two fake ids), 4 no id stores,
+                                 // 8 slow-list entries are not resolved (one fake id each)
 };
 
+// EncArgs::prof[i]: cycles thread 0 spent ... 0 waiting for the tile's data, 1 fast path (+ barrier), 2 slow list,
+// 3 count scan (+ barrier), 4 look-back / gather (+ barrier), 5 fetching the next tile (ticket + two bulk copies),
+// 6 storing the ids, 7 tiles processed
+constexpr int ENC_PROF_N = 8;
 constexpr uint32_t TILE_NONE = 0xFFFFFFFFu;
 constexpr uint64_t ENC_MAX_SUBBATCH = 1ull << 26; // chunks per launch at most (tile ids and look-back words are 32-bit safe)
 constexpr uint32_t META_NONE = 0xFFFFF;       // scanned chunk whose ids did not fit the parking area
@@ -273,6 +282,7 @@ struct EncSmemT {
     alignas(8) uint64_t bar_off, bar_tile; // mbarriers: boundaries landed (thread 0 only waits), tile ready (all wait)
     unsigned long long base;
     uint32_t tile, a0, staged, n_slow, n_scan, park_used;
+    unsigned long long prof[ENC_PROF_N];
 };
 
 template <class SM>
@@ -423,7 +433,7 @@ __device__ __noinline__ void resolve_slow_list(const EncArgs &a, SM &sm, uint32_
                 const uint32_t w0 = (uint32_t)key[0], w1 = (uint32_t)(key[0] >> 32), w2 = (uint32_t)key[1];
                 const uint32_t w3 = (uint32_t)(key[1] >> 32) | (len << 24);
                 uint32_t h = small_hash(w0, w1, w2, w3) >> a.cache.small_shift;
-                for (;;) {
+                for (uint32_t probes = 0; probes < CACHE_MAX_PROBES; probes++) {
                     const uint4 *sp = reinterpret_cast<const uint4 *>(&a.cache.small[h]);
                     const uint4 kq = __ldg(sp);
                     if (kq.w == 0) break;
@@ -438,7 +448,7 @@ __device__ __noinline__ void resolve_slow_list(const EncArgs &a, SM &sm, uint32_
             }
             if (n == 0) {
                 uint32_t h = cache_hash(key[0], key[1], key[2], key[3]) & a.cache.mask;
-                for (;;) {
+                for (uint32_t probes = 0; probes < CACHE_MAX_PROBES; probes++) {
                     const ulonglong2 *sp = reinterpret_cast<const ulonglong2 *>(&a.cache.slots[h]);
                     const ulonglong2 lo = __ldg(sp), hi = __ldg(sp + 1);
                     if (hi.y == 0) break;
@@ -588,8 +598,17 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
         sm.n_slow = 0;
         sm.n_scan = 0;
         sm.park_used = 0;
+        for (int i = 0; i < ENC_PROF_N; i++) sm.prof[i] = 0;
     }
     __syncthreads();
+    long long t_lap = clock64();
+    auto lap = [&](int i) { // thread 0: cycles since the previous lap go to counter i
+        if (a.prof && tid == 0) {
+            const long long t = clock64();
+            sm.prof[i] += (unsigned long long)(t - t_lap);
+            t_lap = t;
+        }
+    };
     uint32_t tile_parity = 0, off_parity = 0;
     uint64_t policy = 0;
     if (bulk && tid == 0) {
@@ -613,7 +632,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
             __syncthreads();
         }
         const uint32_t tile = sm.tile;
-        if (tile == TILE_NONE) return;
+        if (tile == TILE_NONE) break;
         const uint64_t c0 = a.chunk0 + (uint64_t)tile * TILE;
         const uint32_t nc = (uint32_t)min((uint64_t)TILE, a.chunk1 - c0);
         if (!bulk) {
@@ -632,6 +651,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
         }
         const uint32_t a0 = sm.a0;
         const bool staged = sm.staged != 0;
+        lap(0);
         // ---- 1. fast path: the home slot of every chunk in the SMALL cache, all of a thread's probes in flight ------
         uint32_t o[CPT + 1];
 #pragma unroll
@@ -700,15 +720,25 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
             slowq[j] = q;
         }
         __syncthreads();
+        lap(1);
         // ---- 2. slow list ----------------------------------------------------------------------------------------------
-        {
+        if (!(a.ablate & 8)) {
             const uint32_t n_slow = sm.n_slow;
             if (n_slow) resolve_slow_list<THREADS>(a, sm, a0, staged, n_slow);
         }
+        lap(2);
         uint32_t sum = 0;
 #pragma unroll
         for (int j = 0; j < CPT; j++) {
-            if (slowq[j] != TILE_NONE) cnt[j] = sm.meta[slowq[j]] >> 20;
+            if (slowq[j] != TILE_NONE) {
+                if (a.ablate & 8) {
+                    cnt[j] = 1;
+                    vq[j].x = slowq[j];
+                    slowq[j] = TILE_NONE;
+                } else {
+                    cnt[j] = sm.meta[slowq[j]] >> 20;
+                }
+            }
             sum += cnt[j];
         }
         // ---- 3. place in the stream: block exclusive scan + look-back; ids gathered in shared memory ------------------
@@ -720,6 +750,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
         }
         if (lane == 31) sm.warp_sum[warp] = incl;
         __syncthreads();
+        lap(3);
         uint32_t warp_base = 0, total = 0;
 #pragma unroll
         for (int w = 0; w < NW; w++) {
@@ -743,6 +774,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
             }
         }
         __syncthreads();
+        lap(4);
         const uint64_t base = sm.base;
         if (!via_smem && !(a.ablate & 4)) { // a tile with more ids than the gather buffer holds: every thread stores its own
             uint32_t loc = loc0;
@@ -761,6 +793,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
             sm.park_used = 0;
             fetch_tile_bulk(a, sm, off_parity, policy);
         }
+        lap(5);
         if (a.out_off) {
             uint32_t loc = loc0;
 #pragma unroll
@@ -784,7 +817,11 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
             *a.d_n_out = base + total;
             if (a.out_off && a.chunk1 == a.n_chunks) a.out_off[a.n_chunks] = base + total;
         }
+        lap(6);
+        if (a.prof && tid == 0) sm.prof[7] += 1;
     }
+    if (a.prof && tid == 0)
+        for (int i = 0; i < ENC_PROF_N; i++) atomicAdd(&a.prof[i], sm.prof[i]);
 }
 
 } // namespace mbpe
