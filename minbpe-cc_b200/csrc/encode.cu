@@ -693,6 +693,7 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
     a.prof = e->d_prof;
     // cp.async.bulk needs 16-byte aligned sources (device allocations are; offsets into them may not be)
     a.bulk = ((((uintptr_t)d_bytes) | ((uintptr_t)d_off)) & 15) == 0 && !getenv("MBPE_ENC_NO_BULK");
+    a.out_aligned = (((uintptr_t)d_out) & 15) == 0;
     if (const char *ab = getenv("MBPE_ENC_ABLATE")) a.ablate = (uint32_t)atoi(ab);
     const EncConfig &kc = enc_configs[e->cfg];
     const uint64_t ET_CHUNKS = (uint64_t)kc.threads * kc.cpt;
@@ -794,9 +795,9 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
             MB_CUDA(cudaMemcpy(pr, e->d_prof, sizeof pr, cudaMemcpyDeviceToHost));
             MB_CUDA(cudaMemset(e->d_prof, 0, sizeof pr));
             const double t = pr[7] ? (double)pr[7] : 1.0;
-            fprintf(stderr, "[mbpe] encode tiles %llu, cycles per tile: wait data %.0f, fast path %.0f, slow list %.0f, count scan %.0f, "
-                            "look-back+gather %.0f, fetch next %.0f, store %.0f\n",
-                    pr[7], pr[0] / t, pr[1] / t, pr[2] / t, pr[3] / t, pr[4] / t, pr[5] / t, pr[6] / t);
+            fprintf(stderr, "[mbpe] encode tiles %llu, cycles per tile: wait data %.0f, probes + open chunks %.0f, count scan %.0f, "
+                            "look-back+gather %.0f, next text copy %.0f, store %.0f\n",
+                    pr[7], pr[0] / t, pr[1] / t, pr[3] / t, pr[4] / t, pr[5] / t, pr[6] / t);
         }
     }
     return MBPE_OK;

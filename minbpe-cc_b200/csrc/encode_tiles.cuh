@@ -247,6 +247,7 @@ struct EncArgs {
     uint32_t *overflow;          // set when out_cap is too small
     uint32_t *miss_count;        // chunks that went through the scan (statistics)
     uint32_t bulk;               // bytes / off are 16-byte aligned: stage with cp.async.bulk
+    uint32_t out_aligned;        // out is 16-byte aligned: ids leave as 16-byte stores
     unsigned long long *prof;    // optional: SM cycles per phase summed over CTAs (thread 0's clock), see ENC_PROF_*
     uint32_t ablate;             // MBPE_ENC_ABLATE (profiling only; 1, 2, 4 give WRONG results): 1 no look-back wait,
                                  // 2 no cache probe (every short chunk "hits" with two fake ids), 4 no id stores,
@@ -259,50 +260,30 @@ struct EncArgs {
 constexpr int ENC_PROF_N = 8;
 constexpr uint32_t TILE_NONE = 0xFFFFFFFFu;
 constexpr uint64_t ENC_MAX_SUBBATCH = 1ull << 26; // chunks per launch at most (tile ids and look-back words are 32-bit safe)
-constexpr uint32_t META_NONE = 0xFFFFF;       // scanned chunk whose ids did not fit the parking area
-constexpr uint32_t META_PENDING = 0xFFFFFFFFu; // slow-list entry not resolved by the BIG cache: needs the scan
-constexpr uint32_t ET_WARP_SCAN_MAX = 64;     // up to this many scans per tile run one warp per chunk
+constexpr uint32_t PARK_NONE = 0xFFFFFFFFu; // ids of a chunk with more than 4 ids did not fit the parking area
 
 template <int THREADS, int CPT>
 struct EncSmemT {
     static constexpr int TILE = THREADS * CPT;
     static constexpr int TEXT_CAP = TILE * 10;  // staged text bytes per tile (average chunk ~5 bytes); wider tiles read HBM
     static constexpr int STAGE = TILE * 5 / 2;  // ids gathered per tile (average ~2.1 per chunk); more: direct stores
-    static constexpr int PARK = TILE;           // ids of slow-list chunks parked until the tile knows its place
-    alignas(128) uint32_t off[TILE + 8];
+    static constexpr int PARK = TILE / 2;       // ids of chunks with more than 4 ids, parked until the tile knows its place
+    alignas(128) uint32_t off[2][TILE + 8];     // boundaries, double buffered: the next tile's arrive during this tile's gather
     alignas(128) uint32_t text[TEXT_CAP / 4 + 16]; // + halo: key assembly reads whole words past the chunk's end
-    uint32_t stage[STAGE];
+    alignas(16) uint32_t stage[STAGE + 4];
     uint32_t park[PARK];
-    uint32_t meta[TILE];       // per slow-list entry: start in park (20 bits) | id count << 20
-    uint16_t slow[TILE];       // slow list: chunk index within the tile
-    uint16_t scan[TILE];       // of those, the entries that need the scan (slow-list positions)
     uint4 len_mask[16];        // len_mask[l] keeps the first l bytes of a 16-byte key
     uint32_t warp_scratch[THREADS / 32][32];
     uint32_t warp_sum[THREADS / 32];
     alignas(8) uint64_t bar_off, bar_tile; // mbarriers: boundaries landed (thread 0 only waits), tile ready (all wait)
     unsigned long long base;
-    uint32_t tile, a0, staged, n_slow, n_scan, park_used;
+    uint32_t tile[2], a0, staged, park_used;
     unsigned long long prof[ENC_PROF_N];
 };
 
 template <class SM>
 __device__ __forceinline__ uint8_t tile_byte(const EncArgs &a, const SM &sm, bool staged, uint32_t a0, uint32_t g) {
     return staged ? reinterpret_cast<const uint8_t *>(sm.text)[g - a0] : __ldg(&a.bytes[g]);
-}
-
-// scan one chunk (<= ENC_SHORT_MAX bytes) into t[]; returns the id count
-template <class SM>
-__device__ __forceinline__ uint32_t scan_chunk(const EncArgs &a, const SM &sm, bool staged, uint32_t a0, uint32_t o,
-                                               uint32_t len, uint32_t *t) {
-    const uint32_t sid = special_match(a.sp, len, [&](uint32_t i) { return tile_byte(a, sm, staged, a0, o + i); });
-    if (sid != ENC_NONE) {
-        t[0] = sid;
-        return 1;
-    }
-    for (uint32_t i = 0; i < len; i++) t[i] = tile_byte(a, sm, staged, a0, o + i);
-    bool merged = true;
-    while (merged && len >= 2) len = enc_pass(a.tab, t, len, merged);
-    return len;
 }
 
 // One warp scans one chunk of <= 32 bytes: lane i holds token i. Per pass every lane looks its pair up at once (one
@@ -345,6 +326,7 @@ __device__ __forceinline__ void big_key(const EncArgs &a, const SM &sm, bool sta
     key[3] |= (uint64_t)len << 56;
 }
 
+// a chunk the scan had to encode goes to the log that k_cache_insert folds into the caches after the launch
 template <class SM>
 __device__ __forceinline__ void log_scanned(const EncArgs &a, const SM &sm, bool staged, uint32_t a0, uint32_t o,
                                             uint32_t len, const uint32_t *ids, uint32_t n) {
@@ -362,33 +344,178 @@ __device__ __forceinline__ void log_scanned(const EncArgs &a, const SM &sm, bool
     for (uint32_t i = 0; i < n; i++) e.ids[i] = ids[i];
 }
 
-// thread 0: ticket, then the tile's boundaries and text window into shared memory by bulk copies.
-// Publishes sm.tile / sm.a0 / sm.staged and completes sm.bar_tile when everything has landed.
+// What the tile kernel knows about a chunk once it is resolved: n ids; n <= 4: the ids themselves in v, otherwise v.x = start
+// of the ids in the tile's parking area (PARK_NONE: no room, the owner encodes the chunk again when it writes).
+struct Resolved {
+    uint32_t n; // 0: not known yet
+    uint4 v;
+};
 template <class SM>
-__device__ __forceinline__ void fetch_tile_bulk(const EncArgs &a, SM &sm, uint32_t &off_parity, uint64_t policy) {
-    const uint32_t t = atomicAdd(a.ticket, 1u); // tiles start in order: look-back cannot deadlock
-    if (t >= a.n_tiles) {
-        sm.tile = TILE_NONE;
-        mbar_arrive(&sm.bar_tile);
+__device__ __forceinline__ Resolved park_ids(SM &sm, const uint32_t *ids, uint32_t n) {
+    Resolved r;
+    r.n = n;
+    if (n <= 4) {
+        r.v = make_uint4(ids[0], n > 1 ? ids[1] : 0u, n > 2 ? ids[2] : 0u, n > 3 ? ids[3] : 0u);
+        return r;
+    }
+    const uint32_t at = atomicAdd(&sm.park_used, n);
+    r.v = make_uint4(PARK_NONE, 0, 0, 0);
+    if (at + n <= (uint32_t)SM::PARK) {
+        r.v.x = at;
+        for (uint32_t i = 0; i < n; i++) sm.park[at + i] = ids[i];
+    }
+    return r;
+}
+
+// A chunk the fast path did not resolve, by its own thread (no barrier inside: lanes that need it diverge, the others
+// wait at the warp's next convergence point). Kept out of line so that its registers (31-byte keys, id arrays) are not
+// charged to the fast path. Order: special tokens by exact compare; the rest of the chunk's probe sequence in the SMALL
+// cache (the fast path only saw the home slot); the BIG cache. n == 0: unknown, the scan has to decide.
+template <class SM>
+__device__ __noinline__ Resolved resolve_cached(const EncArgs &a, SM &sm, uint32_t a0, bool staged, uint32_t o, uint32_t len,
+                                                bool small_home_taken) {
+    Resolved r;
+    r.n = 0;
+    r.v = make_uint4(0, 0, 0, 0);
+    const uint32_t sid = special_match(a.sp, len, [&](uint32_t i) { return tile_byte(a, sm, staged, a0, o + i); });
+    if (sid != ENC_NONE) {
+        r.n = 1;
+        r.v.x = sid;
+        return r;
+    }
+    if (!a.cache.small || len > CACHE_MAX_LEN || (a.ablate & 2)) return r;
+    uint64_t key[4];
+    big_key(a, sm, staged, a0, o, len, key);
+    if (len <= SMALL_MAX_LEN && (small_home_taken || !staged)) {
+        const uint32_t w0 = (uint32_t)key[0], w1 = (uint32_t)(key[0] >> 32), w2 = (uint32_t)key[1];
+        const uint32_t w3 = (uint32_t)(key[1] >> 32) | (len << 24);
+        uint32_t h = small_hash(w0, w1, w2, w3) >> a.cache.small_shift;
+        for (uint32_t probes = 0; probes < CACHE_MAX_PROBES; probes++) {
+            const uint4 *sp = reinterpret_cast<const uint4 *>(&a.cache.small[h]);
+            const uint4 kq = __ldg(sp);
+            if (kq.w == 0) break;
+            if ((kq.w & SMALL_KEY_MASK) == w3 && kq.x == w0 && kq.y == w1 && kq.z == w2) {
+                r.v = __ldg(sp + 1);
+                r.n = kq.w >> 28;
+                return r;
+            }
+            h = (h + 1) & a.cache.small_mask;
+        }
+    }
+    uint32_t h = cache_hash(key[0], key[1], key[2], key[3]) & a.cache.mask;
+    for (uint32_t probes = 0; probes < CACHE_MAX_PROBES; probes++) {
+        const ulonglong2 *sp = reinterpret_cast<const ulonglong2 *>(&a.cache.slots[h]);
+        const ulonglong2 lo = __ldg(sp), hi = __ldg(sp + 1);
+        const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(sp + 2)); // n, v[0..2]: fetched with the key, one round trip
+        if (hi.y == 0) break;
+        if (hi.y == key[3] && hi.x == key[2] && lo.x == key[0] && lo.y == key[1]) {
+            const uint32_t n = v0.x;
+            if (n <= 4) {
+                r.n = n;
+                r.v = make_uint4(v0.y, v0.z, v0.w, n > 3 ? __ldg(reinterpret_cast<const uint32_t *>(sp + 3)) : 0u);
+                return r;
+            }
+            uint32_t ids[CACHE_MAX_LEN];
+            if (n <= CACHE_INLINE_IDS) {
+                const uint4 v1 = __ldg(reinterpret_cast<const uint4 *>(sp + 3));
+                ids[0] = v0.y, ids[1] = v0.z, ids[2] = v0.w, ids[3] = v1.x, ids[4] = v1.y, ids[5] = v1.z, ids[6] = v1.w;
+            } else {
+                const uint32_t *src = a.cache.arena + v0.y;
+                for (uint32_t i = 0; i < n; i++) ids[i] = __ldg(&src[i]);
+            }
+            return park_ids(sm, ids, n);
+        }
+        h = (h + 1) & a.cache.mask;
+    }
+    return r;
+}
+
+// the multi-pass scan of one chunk (<= ENC_SHORT_MAX bytes) by ONE thread; the result is parked / logged
+template <class SM>
+__device__ __noinline__ Resolved scan_serial(const EncArgs &a, SM &sm, uint32_t a0, bool staged, uint32_t o, uint32_t len, bool log) {
+    uint32_t t[ENC_SHORT_MAX];
+    for (uint32_t i = 0; i < len; i++) t[i] = tile_byte(a, sm, staged, a0, o + i);
+    uint32_t n = len;
+    bool merged = true;
+    while (merged && n >= 2) n = enc_pass(a.tab, t, n, merged);
+    if (log) log_scanned(a, sm, staged, a0, o, len, t, n);
+    return park_ids(sm, t, n);
+}
+
+// ids of a chunk that did not fit the parking area: encode it again, straight into place (rare)
+template <class SM>
+__device__ __noinline__ void rescan_into(const EncArgs &a, SM &sm, uint32_t a0, bool staged, uint32_t o, uint32_t len, uint32_t *dst,
+                                         uint32_t n) {
+    uint32_t t[ENC_SHORT_MAX];
+    const uint32_t sid = special_match(a.sp, len, [&](uint32_t i) { return tile_byte(a, sm, staged, a0, o + i); });
+    uint32_t m = len;
+    if (sid != ENC_NONE) {
+        t[0] = sid;
+        m = 1;
+    } else {
+        for (uint32_t i = 0; i < len; i++) t[i] = tile_byte(a, sm, staged, a0, o + i);
+        bool merged = true;
+        while (merged && m >= 2) m = enc_pass(a.tab, t, m, merged);
+    }
+    for (uint32_t i = 0; i < n && i < m; i++) dst[i] = t[i];
+}
+
+// one chunk's ids -> dst[0 .. n) (shared-memory gather buffer, or the stream itself for oversized tiles)
+template <class SM>
+__device__ __forceinline__ void emit_chunk(const EncArgs &a, SM &sm, uint32_t a0, bool staged, uint32_t n, uint32_t o0, uint32_t o1,
+                                           uint4 v, uint32_t *dst, uint64_t room) {
+    if (n == 0) return;
+    if (n > room) {
+        *a.overflow = 1;
         return;
     }
+    if (n <= 4 && o1 - o0 <= ENC_SHORT_MAX) {
+        dst[0] = v.x;
+        if (n > 1) dst[1] = v.y;
+        if (n > 2) dst[2] = v.z;
+        if (n > 3) dst[3] = v.w;
+    } else if (o1 - o0 > ENC_SHORT_MAX) {
+        for (uint32_t i = 0; i < n; i++) dst[i] = a.scratch_a[o0 + i];
+    } else if (v.x != PARK_NONE) {
+        for (uint32_t i = 0; i < n; i++) dst[i] = sm.park[v.x + i];
+    } else {
+        rescan_into(a, sm, a0, staged, o0, o1 - o0, dst, n);
+    }
+}
+
+// thread 0, first half of a tile fetch: the ticket, and the tile's boundaries on their way into off[buf]
+template <class SM>
+__device__ __forceinline__ void fetch_tile_begin(const EncArgs &a, SM &sm, uint32_t buf, uint64_t policy) {
+    const uint32_t t = atomicAdd(a.ticket, 1u); // tiles start in order: look-back cannot deadlock
+    sm.tile[buf] = t < a.n_tiles ? t : TILE_NONE;
+    if (t >= a.n_tiles) return;
     const uint64_t c0 = a.chunk0 + (uint64_t)t * SM::TILE;
     const uint32_t nc = (uint32_t)min((uint64_t)SM::TILE, a.chunk1 - c0);
     const uint32_t nw = nc + 1, nb = nw & ~3u; // whole 16-byte vectors by bulk copy, the last <= 3 words by hand
     if (nb) {
         mbar_arrive_expect_tx(&sm.bar_off, nb * 4);
-        bulk_g2s(sm.off, a.off + c0, nb * 4, &sm.bar_off, policy);
+        bulk_g2s(sm.off[buf], a.off + c0, nb * 4, &sm.bar_off, policy);
     } else {
         mbar_arrive(&sm.bar_off);
     }
-    for (uint32_t i = nb; i < nw; i++) sm.off[i] = __ldg(&a.off[c0 + i]);
+    for (uint32_t i = nb; i < nw; i++) sm.off[buf][i] = __ldg(&a.off[c0 + i]);
+}
+// second half (nobody reads the previous tile's text any more): the text window; completes sm.bar_tile
+template <class SM>
+__device__ __forceinline__ void fetch_tile_finish(const EncArgs &a, SM &sm, uint32_t buf, uint32_t &off_parity, uint64_t policy) {
+    const uint32_t t = sm.tile[buf];
+    if (t == TILE_NONE) {
+        mbar_arrive(&sm.bar_tile);
+        return;
+    }
     mbar_wait(&sm.bar_off, off_parity);
     off_parity ^= 1;
-    const uint32_t b0 = sm.off[0], b1 = sm.off[nc];
+    const uint64_t c0 = a.chunk0 + (uint64_t)t * SM::TILE;
+    const uint32_t nc = (uint32_t)min((uint64_t)SM::TILE, a.chunk1 - c0);
+    const uint32_t b0 = sm.off[buf][0], b1 = sm.off[buf][nc];
     const uint32_t a0 = b0 & ~15u; // 16-byte aligned window start
     const uint32_t span = b1 - a0;
     const bool staged = span <= (uint32_t)SM::TEXT_CAP;
-    sm.tile = t;
     sm.a0 = a0;
     sm.staged = staged;
     if (staged) {
@@ -405,179 +532,11 @@ __device__ __forceinline__ void fetch_tile_bulk(const EncArgs &a, SM &sm, uint32
     mbar_arrive(&sm.bar_tile);
 }
 
-// The tile's slow list, by all threads of the CTA (contains barriers). Kept out of line: its register needs (31-byte
-// keys, id arrays) must not be charged to the fast path, which runs for nine chunks in ten.
-//   2a. one thread per entry: special tokens by exact compare; a chunk of <= 15 bytes continues its probe sequence in
-//       the SMALL cache; then the BIG cache;
-//   2b. what is still unknown is scanned: one WARP per chunk when few (warm caches: latency matters), one THREAD per
-//       chunk when many (cold caches: throughput matters) and for chunks of 33..64 bytes.
-// Result per entry q: sm.meta[q] = start in sm.park (META_NONE: did not fit) | id count << 20.
-template <int THREADS, class SM>
-__device__ __noinline__ void resolve_slow_list(const EncArgs &a, SM &sm, uint32_t a0, bool staged, uint32_t n_slow) {
-    constexpr int NW = THREADS / 32;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool use_cache = a.cache.small != nullptr && !(a.ablate & 2);
-    for (uint32_t q = tid; q < n_slow; q += THREADS) {
-        const uint32_t k = sm.slow[q], so = sm.off[k], len = sm.off[k + 1] - so;
-        uint32_t n = 0, start = META_NONE;
-        const uint32_t *src = nullptr;
-        uint32_t one[CACHE_INLINE_IDS];
-        const uint32_t sid = special_match(a.sp, len, [&](uint32_t i) { return tile_byte(a, sm, staged, a0, so + i); });
-        if (sid != ENC_NONE) {
-            one[0] = sid;
-            n = 1;
-        } else if (use_cache && len <= CACHE_MAX_LEN) {
-            uint64_t key[4];
-            big_key(a, sm, staged, a0, so, len, key);
-            if (len <= SMALL_MAX_LEN) { // the whole probe sequence again (the fast path only looked at the home slot)
-                const uint32_t w0 = (uint32_t)key[0], w1 = (uint32_t)(key[0] >> 32), w2 = (uint32_t)key[1];
-                const uint32_t w3 = (uint32_t)(key[1] >> 32) | (len << 24);
-                uint32_t h = small_hash(w0, w1, w2, w3) >> a.cache.small_shift;
-                for (uint32_t probes = 0; probes < CACHE_MAX_PROBES; probes++) {
-                    const uint4 *sp = reinterpret_cast<const uint4 *>(&a.cache.small[h]);
-                    const uint4 kq = __ldg(sp);
-                    if (kq.w == 0) break;
-                    if ((kq.w & SMALL_KEY_MASK) == w3 && kq.x == w0 && kq.y == w1 && kq.z == w2) {
-                        const uint4 vq = __ldg(sp + 1);
-                        n = kq.w >> 28;
-                        one[0] = vq.x, one[1] = vq.y, one[2] = vq.z, one[3] = vq.w;
-                        break;
-                    }
-                    h = (h + 1) & a.cache.small_mask;
-                }
-            }
-            if (n == 0) {
-                uint32_t h = cache_hash(key[0], key[1], key[2], key[3]) & a.cache.mask;
-                for (uint32_t probes = 0; probes < CACHE_MAX_PROBES; probes++) {
-                    const ulonglong2 *sp = reinterpret_cast<const ulonglong2 *>(&a.cache.slots[h]);
-                    const ulonglong2 lo = __ldg(sp), hi = __ldg(sp + 1);
-                    if (hi.y == 0) break;
-                    if (hi.y == key[3] && hi.x == key[2] && lo.x == key[0] && lo.y == key[1]) {
-                        const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(sp + 2)); // n, v[0..2]
-                        n = v0.x;
-                        if (n <= CACHE_INLINE_IDS) {
-                            const uint4 v1 = __ldg(reinterpret_cast<const uint4 *>(sp + 3));
-                            one[0] = v0.y, one[1] = v0.z, one[2] = v0.w, one[3] = v1.x, one[4] = v1.y, one[5] = v1.z, one[6] = v1.w;
-                        } else {
-                            src = a.cache.arena + v0.y;
-                        }
-                        break;
-                    }
-                    h = (h + 1) & a.cache.mask;
-                }
-            }
-        }
-        if (n == 0) { // not known: the scan decides
-            sm.meta[q] = META_PENDING;
-            sm.scan[atomicAdd(&sm.n_scan, 1u)] = (uint16_t)q;
-            continue;
-        }
-        const uint32_t at = atomicAdd(&sm.park_used, n);
-        if (at + n <= (uint32_t)SM::PARK) {
-            start = at;
-            for (uint32_t i = 0; i < n; i++) sm.park[at + i] = src ? __ldg(&src[i]) : one[i];
-        }
-        sm.meta[q] = start | (n << 20);
-    }
-    __syncthreads();
-    const uint32_t n_scan = sm.n_scan;
-    if (n_scan == 0) return;
-    if (tid == 0) atomicAdd(a.miss_count, n_scan);
-    const bool by_warp = n_scan <= ET_WARP_SCAN_MAX;
-    if (by_warp) {
-        for (uint32_t s = warp; s < n_scan; s += NW) {
-            const uint32_t q = sm.scan[s], k = sm.slow[q], so = sm.off[k], mlen = sm.off[k + 1] - so;
-            if (mlen > 32) continue; // 33..64 bytes: serial scan below
-            uint32_t tok = lane < mlen ? tile_byte(a, sm, staged, a0, so + lane) : 0u;
-            const uint32_t mn = scan_chunk_warp(a.tab, tok, mlen, sm.warp_scratch[warp]); // lane i < mn: id i in tok
-            uint32_t start = 0;
-            if (lane == 0) start = atomicAdd(&sm.park_used, mn);
-            start = __shfl_sync(0xffffffffu, start, 0);
-            if (start + mn <= (uint32_t)SM::PARK) {
-                if (lane < mn) sm.park[start + lane] = tok;
-            } else {
-                start = META_NONE;
-            }
-            if (lane == 0) sm.meta[q] = start | (mn << 20);
-            if (a.cache.small && mlen <= CACHE_MAX_LEN) { // teach the caches
-                uint32_t li = 0;
-                if (lane == 0) li = atomicAdd(a.cache.log_count, 1u);
-                li = __shfl_sync(0xffffffffu, li, 0);
-                if (li < a.cache.log_cap) {
-                    CacheLogEntry &e = a.cache.log[li];
-                    if (lane < mn) e.ids[lane] = tok;
-                    if (lane == 0) {
-                        uint64_t key[4];
-                        big_key(a, sm, staged, a0, so, mlen, key);
-                        e.k[0] = key[0];
-                        e.k[1] = key[1];
-                        e.k[2] = key[2];
-                        e.k[3] = key[3];
-                        e.n = mn;
-                    }
-                }
-            }
-            __syncwarp();
-        }
-    }
-    for (uint32_t s = tid; s < n_scan; s += THREADS) {
-        const uint32_t q = sm.scan[s], k = sm.slow[q], so = sm.off[k], mlen = sm.off[k + 1] - so;
-        if (by_warp && mlen <= 32) continue;
-        uint32_t t[ENC_SHORT_MAX];
-        const uint32_t mn = scan_chunk(a, sm, staged, a0, so, mlen, t);
-        uint32_t start = atomicAdd(&sm.park_used, mn);
-        if (start + mn <= (uint32_t)SM::PARK) {
-            for (uint32_t i = 0; i < mn; i++) sm.park[start + i] = t[i];
-        } else {
-            start = META_NONE; // no room: the owner scans it again when writing
-        }
-        sm.meta[q] = start | (mn << 20);
-        log_scanned(a, sm, staged, a0, so, mlen, t, mn);
-    }
-    __syncthreads();
-}
-
-// ids of a slow-list chunk that did not fit the parking area: resolve it again, straight into place (rare)
-template <class SM>
-__device__ __noinline__ void rescan_into(const EncArgs &a, const SM &sm, uint32_t a0, bool staged, uint32_t o, uint32_t len,
-                                         uint32_t *dst, uint32_t n) {
-    uint32_t t[ENC_SHORT_MAX];
-    scan_chunk(a, sm, staged, a0, o, len, t);
-    for (uint32_t i = 0; i < n; i++) dst[i] = t[i];
-}
-
-// one chunk's ids -> dst[0 .. n) (shared-memory gather buffer, or the stream itself for oversized tiles)
-template <class SM>
-__device__ __forceinline__ void emit_chunk(const EncArgs &a, const SM &sm, uint32_t a0, bool staged, uint32_t n, uint32_t slowq,
-                                           uint32_t o0, uint32_t o1, uint4 v, uint32_t *dst, uint64_t room) {
-    if (n == 0) return;
-    if (n > room) {
-        *a.overflow = 1;
-        return;
-    }
-    if (slowq == TILE_NONE) {
-        if (o1 - o0 > ENC_SHORT_MAX) {
-            for (uint32_t i = 0; i < n; i++) dst[i] = a.scratch_a[o0 + i];
-        } else {
-            dst[0] = v.x;
-            if (n > 1) dst[1] = v.y;
-            if (n > 2) dst[2] = v.z;
-            if (n > 3) dst[3] = v.w;
-        }
-    } else {
-        const uint32_t start = sm.meta[slowq] & 0xFFFFF;
-        if (start != META_NONE) {
-            for (uint32_t i = 0; i < n; i++) dst[i] = sm.park[start + i];
-        } else {
-            rescan_into(a, sm, a0, staged, o0, o1 - o0, dst, n);
-        }
-    }
-}
-
 template <int THREADS, int CPT, int MIN_CTAS>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArgs a) {
     using SM = EncSmemT<THREADS, CPT>;
     constexpr int TILE = SM::TILE, NW = THREADS / 32;
+    static_assert(NW >= 2, "warp 0 looks back while the last warp starts the next tile's fetch");
     extern __shared__ __align__(128) unsigned char enc_smem_raw[];
     SM &sm = *reinterpret_cast<SM *>(enc_smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -595,8 +554,6 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
         mbar_init(&sm.bar_off, 1);
         mbar_init(&sm.bar_tile, 1);
         mbar_init_fence();
-        sm.n_slow = 0;
-        sm.n_scan = 0;
         sm.park_used = 0;
         for (int i = 0; i < ENC_PROF_N; i++) sm.prof[i] = 0;
     }
@@ -610,12 +567,13 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
         }
     };
     uint32_t tile_parity = 0, off_parity = 0;
-    uint64_t policy = 0;
+    const uint64_t policy = l2_evict_first_policy();
     if (bulk && tid == 0) {
-        policy = l2_evict_first_policy();
-        fetch_tile_bulk(a, sm, off_parity, policy);
+        fetch_tile_begin(a, sm, 0, policy);
+        fetch_tile_finish(a, sm, 0, off_parity, policy);
     }
-    for (;;) {
+    for (uint32_t it = 0;; it++) {
+        const uint32_t buf = it & 1;
         // ---- 0. the tile's boundaries and text in shared memory ----------------------------------------------------
         if (bulk) {
             mbar_wait(&sm.bar_tile, tile_parity);
@@ -624,21 +582,20 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
             __syncthreads();
             if (tid == 0) {
                 const uint32_t t = atomicAdd(a.ticket, 1u);
-                sm.tile = t < a.n_tiles ? t : TILE_NONE;
-                sm.n_slow = 0;
-                sm.n_scan = 0;
+                sm.tile[buf] = t < a.n_tiles ? t : TILE_NONE;
                 sm.park_used = 0;
             }
             __syncthreads();
         }
-        const uint32_t tile = sm.tile;
+        const uint32_t tile = sm.tile[buf];
         if (tile == TILE_NONE) break;
         const uint64_t c0 = a.chunk0 + (uint64_t)tile * TILE;
         const uint32_t nc = (uint32_t)min((uint64_t)TILE, a.chunk1 - c0);
+        const uint32_t *const soff = sm.off[buf];
         if (!bulk) {
-            for (uint32_t i = tid; i <= nc; i += THREADS) sm.off[i] = __ldg(&a.off[c0 + i]);
+            for (uint32_t i = tid; i <= nc; i += THREADS) sm.off[buf][i] = __ldg(&a.off[c0 + i]);
             __syncthreads();
-            const uint32_t b0 = sm.off[0], b1 = sm.off[nc], w0 = b0 & ~3u;
+            const uint32_t b0 = soff[0], b1 = soff[nc], w0 = b0 & ~3u;
             const bool st = (b1 - w0) <= (uint32_t)SM::TEXT_CAP;
             if (st) // byte loads: nothing is known about the alignment of the buffer
                 for (uint32_t g = b0 + tid; g < b1; g += THREADS) reinterpret_cast<uint8_t *>(sm.text)[g - w0] = __ldg(&a.bytes[g]);
@@ -655,11 +612,11 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
         // ---- 1. fast path: the home slot of every chunk in the SMALL cache, all of a thread's probes in flight ------
         uint32_t o[CPT + 1];
 #pragma unroll
-        for (int j = 0; j <= CPT; j++) o[j] = sm.off[min(tid * CPT + j, nc)];
+        for (int j = 0; j <= CPT; j++) o[j] = soff[min(tid * CPT + j, nc)];
         uint32_t cnt[CPT];
-        uint32_t slowq[CPT]; // place on the slow list, or TILE_NONE: cnt / vq are final
-        uint4 vq[CPT];       // hit: the chunk's ids
-        const bool keyed = a.cache.small != nullptr && staged; // (an unstaged tile -- very long chunks -- goes to the slow list)
+        uint4 vq[CPT];      // the chunk's ids (cnt <= 4), or where they are parked
+        uint32_t todo = 0;  // bit j: chunk j still unknown; bit 8 + j: ... and its home slot in the SMALL cache was taken
+        const bool keyed = a.cache.small != nullptr && staged; // (an unstaged tile -- very long chunks -- skips the fast path)
         if (keyed && !(a.ablate & 2)) {
             uint4 kw[CPT], kq[CPT];
 #pragma unroll
@@ -681,66 +638,106 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
 #pragma unroll
             for (int j = 0; j < CPT; j++) {
                 const uint32_t len = o[j + 1] - o[j];
-                const bool hit = len - 1u < SMALL_MAX_LEN && (kq[j].w & SMALL_KEY_MASK) == kw[j].w && kq[j].x == kw[j].x &&
-                                 kq[j].y == kw[j].y && kq[j].z == kw[j].z;
+                const bool small = len - 1u < SMALL_MAX_LEN;
+                const bool hit = small && (kq[j].w & SMALL_KEY_MASK) == kw[j].w && kq[j].x == kw[j].x && kq[j].y == kw[j].y && kq[j].z == kw[j].z;
                 cnt[j] = hit ? kq[j].w >> 28 : 0u;
-                slowq[j] = hit ? TILE_NONE : 0u; // 0: undecided, see below
+                if (!hit) todo |= (1u << j) | ((small && kq[j].w != 0) ? 0x100u << j : 0u);
             }
         } else {
 #pragma unroll
             for (int j = 0; j < CPT; j++) {
                 cnt[j] = 0;
-                slowq[j] = 0;
                 vq[j] = make_uint4(0, 0, 0, 0);
             }
+            todo = (1u << CPT) - 1;
         }
+        // ---- 2. what the fast path left open: by the chunk's own thread, then by its warp; no block barrier ------------
 #pragma unroll
         for (int j = 0; j < CPT; j++) {
-            if (slowq[j] == TILE_NONE) continue; // hit
-            slowq[j] = TILE_NONE;
             const uint32_t k = tid * CPT + j, len = o[j + 1] - o[j];
-            if (k >= nc || len == 0) continue;
-            if (len > ENC_SHORT_MAX) {
+            bool open = (todo >> j) & 1u;
+            if (open && (k >= nc || len == 0)) open = false; // nothing to encode
+            if (open && len > ENC_SHORT_MAX) {
                 if (a.scratch_b) {
                     cnt[j] = a.scratch_b[o[j]]; // encoded by k_encode_long
                 } else {                         // optimistic launch: report it, the host runs the long path and repeats
                     const uint32_t q = atomicAdd(a.n_long, 1u);
                     if (q < a.long_cap) a.long_list[q] = (uint32_t)(c0 + k);
                 }
-                continue;
+                open = false;
             }
-            if (a.ablate & 2) {
-                cnt[j] = 2;
-                vq[j].x = o[j];
-                vq[j].y = len;
-                continue;
+            if (open && (a.ablate & 10)) { // (profiling only: 2 = every chunk "hits", 8 = no slow path)
+                cnt[j] = (a.ablate & 2) ? 2 : 1;
+                vq[j] = make_uint4(o[j], len, 0, 0);
+                open = false;
             }
-            const uint32_t q = atomicAdd(&sm.n_slow, 1u);
-            sm.slow[q] = (uint16_t)k;
-            slowq[j] = q;
-        }
-        __syncthreads();
-        lap(1);
-        // ---- 2. slow list ----------------------------------------------------------------------------------------------
-        if (!(a.ablate & 8)) {
-            const uint32_t n_slow = sm.n_slow;
-            if (n_slow) resolve_slow_list<THREADS>(a, sm, a0, staged, n_slow);
-        }
-        lap(2);
-        uint32_t sum = 0;
-#pragma unroll
-        for (int j = 0; j < CPT; j++) {
-            if (slowq[j] != TILE_NONE) {
-                if (a.ablate & 8) {
-                    cnt[j] = 1;
-                    vq[j].x = slowq[j];
-                    slowq[j] = TILE_NONE;
-                } else {
-                    cnt[j] = sm.meta[slowq[j]] >> 20;
+            if (open) { // special tokens, the rest of the SMALL probe sequence, the BIG cache
+                const Resolved r = resolve_cached(a, sm, a0, staged, o[j], len, (todo >> (8 + j)) & 1u);
+                if (r.n) {
+                    cnt[j] = r.n;
+                    vq[j] = r.v;
+                    open = false;
                 }
             }
-            sum += cnt[j];
+            // the scan itself: chunks nobody has seen before. Few in the warp (warm caches): one after the other, the whole
+            // warp on each (lanes = positions, one lookup latency per pass). Many (cold caches): every lane scans its own.
+            uint32_t pending = __ballot_sync(0xffffffffu, open);
+            if (pending && lane == 0) atomicAdd(a.miss_count, (uint32_t)__popc(pending));
+            if (__popc(pending) > 6 || __any_sync(0xffffffffu, open && len > 32)) { // (chunks of 33..64 bytes do not fit the lanes)
+                if (open) {
+                    const Resolved r = scan_serial(a, sm, a0, staged, o[j], len, true);
+                    cnt[j] = r.n;
+                    vq[j] = r.v;
+                }
+                pending = 0;
+            }
+            while (pending) {
+                const int src = __ffs(pending) - 1;
+                pending &= pending - 1;
+                const uint32_t so = __shfl_sync(0xffffffffu, o[j], src), mlen = __shfl_sync(0xffffffffu, len, src);
+                uint32_t tok = lane < mlen ? tile_byte(a, sm, staged, a0, so + lane) : 0u;
+                const uint32_t mn = scan_chunk_warp(a.tab, tok, mlen, sm.warp_scratch[warp]); // lane i < mn: id i in tok
+                if (a.cache.small && mlen <= CACHE_MAX_LEN) { // teach the caches
+                    uint32_t li = 0;
+                    if (lane == 0) li = atomicAdd(a.cache.log_count, 1u);
+                    li = __shfl_sync(0xffffffffu, li, 0);
+                    if (li < a.cache.log_cap) {
+                        CacheLogEntry &e = a.cache.log[li];
+                        if (lane < mn) e.ids[lane] = tok;
+                        if (lane == 0) {
+                            uint64_t key[4];
+                            big_key(a, sm, staged, a0, so, mlen, key);
+                            e.k[0] = key[0];
+                            e.k[1] = key[1];
+                            e.k[2] = key[2];
+                            e.k[3] = key[3];
+                            e.n = mn;
+                        }
+                    }
+                }
+                // hand the ids to the owner: up to 4 through shuffles, more through the parking area
+                const uint32_t i0 = __shfl_sync(0xffffffffu, tok, 0), i1 = __shfl_sync(0xffffffffu, tok, 1);
+                const uint32_t i2 = __shfl_sync(0xffffffffu, tok, 2), i3 = __shfl_sync(0xffffffffu, tok, 3);
+                uint32_t at = PARK_NONE;
+                if (mn > 4) {
+                    if (lane == 0) {
+                        at = atomicAdd(&sm.park_used, mn);
+                        if (at + mn > (uint32_t)SM::PARK) at = PARK_NONE;
+                    }
+                    at = __shfl_sync(0xffffffffu, at, 0);
+                    if (at != PARK_NONE && lane < mn) sm.park[at + lane] = tok;
+                }
+                if ((int)lane == src) {
+                    cnt[j] = mn;
+                    vq[j] = mn > 4 ? make_uint4(at, 0, 0, 0) : make_uint4(i0, i1, i2, i3);
+                }
+                __syncwarp();
+            }
         }
+        lap(1);
+        uint32_t sum = 0;
+#pragma unroll
+        for (int j = 0; j < CPT; j++) sum += cnt[j];
         // ---- 3. place in the stream: block exclusive scan + look-back; ids gathered in shared memory ------------------
         uint32_t incl = sum;
 #pragma unroll
@@ -762,6 +759,9 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
             const uint64_t b = (a.ablate & 1) ? (uint64_t)tile * (TILE * 9 / 4)
                                               : lookback_base<4>(a.status, tile, total, a.stream_base);
             if (lane == 0) sm.base = b;
+        } else if (bulk && tid == THREADS - 32) {
+            // while warp 0 looks back: the next tile's ticket, and its boundaries on their way into off[buf ^ 1]
+            fetch_tile_begin(a, sm, buf ^ 1, policy);
         }
         const bool via_smem = total <= (uint32_t)SM::STAGE;
         const uint32_t loc0 = warp_base + (incl - sum);
@@ -769,7 +769,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
             uint32_t loc = loc0;
 #pragma unroll
             for (int j = 0; j < CPT; j++) {
-                emit_chunk(a, sm, a0, staged, cnt[j], slowq[j], o[j], o[j + 1], vq[j], sm.stage + loc, ~0ull);
+                emit_chunk(a, sm, a0, staged, cnt[j], o[j], o[j + 1], vq[j], sm.stage + loc, ~0ull);
                 loc += cnt[j];
             }
         }
@@ -781,17 +781,15 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
 #pragma unroll
             for (int j = 0; j < CPT; j++) {
                 const uint64_t at = base + loc;
-                emit_chunk(a, sm, a0, staged, cnt[j], slowq[j], o[j], o[j + 1], vq[j], a.out + at, at < a.out_cap ? a.out_cap - at : 0);
+                emit_chunk(a, sm, a0, staged, cnt[j], o[j], o[j + 1], vq[j], a.out + at, at < a.out_cap ? a.out_cap - at : 0);
                 loc += cnt[j];
             }
-            __syncthreads(); // (emit may read the tile's text and lists: they are replaced below)
+            __syncthreads(); // (emit may read the tile's text and parking area: they are replaced below)
         }
-        // ---- 4. the next tile's loads start now; this tile's ids leave as whole lines --------------------------------
+        // ---- 4. the next tile's text starts now; this tile's ids leave as whole lines --------------------------------
         if (bulk && tid == 0) {
-            sm.n_slow = 0; // (everybody is past the slow list; the next tile's appends come after the next mbarrier wait)
-            sm.n_scan = 0;
-            sm.park_used = 0;
-            fetch_tile_bulk(a, sm, off_parity, policy);
+            sm.park_used = 0; // (the next tile parks after the next mbarrier wait)
+            fetch_tile_finish(a, sm, buf ^ 1, off_parity, policy);
         }
         lap(5);
         if (a.out_off) {
@@ -804,13 +802,24 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
             }
         }
         if (via_smem && !(a.ablate & 4)) {
-            if (base + total <= a.out_cap) {
-                uint32_t *const gout = a.out + base;
-                for (uint32_t i = tid; i < total; i += THREADS) __stcs(&gout[i], sm.stage[i]);
+            if (base + total <= a.out_cap && a.out_aligned) {
+                // 16-byte stores: vector v = stream words [w0 + 4v, w0 + 4v + 4), w0 = base rounded down to 4 words
+                const uint32_t pad = (uint32_t)(base & 3);
+                uint32_t *const gout = a.out + (base - pad);
+                const uint32_t n_vec = (pad + total + 3) >> 2;
+                for (uint32_t v = tid; v < n_vec; v += THREADS) {
+                    const int lo = (int)(4 * v) - (int)pad; // index of the vector's first word in the gather buffer
+                    if (lo >= 0 && (uint32_t)lo + 4 <= total) {
+                        const uint4 q = make_uint4(sm.stage[lo], sm.stage[lo + 1], sm.stage[lo + 2], sm.stage[lo + 3]);
+                        __stcs(reinterpret_cast<uint4 *>(gout) + v, q);
+                    } else {
+                        for (int i = lo < 0 ? 0 : lo; i < lo + 4 && (uint32_t)i < total; i++) __stcs(&a.out[base + i], sm.stage[i]);
+                    }
+                }
             } else {
                 for (uint32_t i = tid; i < total; i += THREADS)
                     if (base + i < a.out_cap) a.out[base + i] = sm.stage[i];
-                if (tid == 0) *a.overflow = 1;
+                if (tid == 0 && base + total > a.out_cap) *a.overflow = 1;
             }
         }
         if (tile == a.n_tiles - 1 && tid == 0) {
