@@ -616,7 +616,7 @@ def main():
             while off_abi[n_abi] != nb_abi and n_abi > 0:  # (block boundaries are chunk boundaries: exact hit expected)
                 n_abi -= 1
             etb = etb[:int(off_abi[n_abi])]
-            enc.encode(etb[:MIB], off_abi[:int(np.searchsorted(off_abi, MIB, side="right"))])  # pinned pipeline buffers (untimed)
+            enc.encode(etb, off_abi[:n_abi + 1])  # first call: sizes the handle's pinned staging buffers (untimed)
             t0 = time.time()
             ids_abi = enc.encode(etb, off_abi[:n_abi + 1])
             abi_s = time.time() - t0

@@ -357,8 +357,8 @@ struct EncConfig {
 };
 #define ENC_CFG(T, C, M) EncConfig{T, C, M, k_encode_tiles<T, C, M>, sizeof(EncSmemT<T, C>)}
 // (threads, chunks per thread, CTAs per SM); 0 = default, the others for A/B runs (MBPE_ENC_CFG)
-static const EncConfig enc_configs[] = {ENC_CFG(512, 2, 3), ENC_CFG(256, 2, 6), ENC_CFG(256, 4, 4), ENC_CFG(512, 2, 2),
-                                        ENC_CFG(256, 2, 5), ENC_CFG(1024, 1, 1), ENC_CFG(256, 4, 3), ENC_CFG(128, 2, 12)};
+static const EncConfig enc_configs[] = {ENC_CFG(256, 4, 3), ENC_CFG(256, 4, 4), ENC_CFG(512, 4, 2), ENC_CFG(512, 2, 3),
+                                        ENC_CFG(256, 8, 2), ENC_CFG(512, 4, 1), ENC_CFG(256, 2, 6), ENC_CFG(128, 4, 6)};
 constexpr int N_ENC_CONFIGS = sizeof(enc_configs) / sizeof(enc_configs[0]);
 
 static ChunkCache cache_view(const mbpe_encoder *e) {
@@ -795,9 +795,9 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
             MB_CUDA(cudaMemcpy(pr, e->d_prof, sizeof pr, cudaMemcpyDeviceToHost));
             MB_CUDA(cudaMemset(e->d_prof, 0, sizeof pr));
             const double t = pr[7] ? (double)pr[7] : 1.0;
-            fprintf(stderr, "[mbpe] encode tiles %llu, cycles per tile: wait data %.0f, probes + open chunks %.0f, count scan %.0f, "
-                            "look-back+gather %.0f, next text copy %.0f, store %.0f\n",
-                    pr[7], pr[0] / t, pr[1] / t, pr[3] / t, pr[4] / t, pr[5] / t, pr[6] / t);
+            fprintf(stderr, "[mbpe] encode tiles %llu, cycles per tile: wait data %.0f, probes %.0f, open chunks %.0f, count scan %.0f, "
+                            "look-back+gather %.0f, fetch next %.0f, store %.0f\n",
+                    pr[7], pr[0] / t, pr[1] / t, pr[2] / t, pr[3] / t, pr[4] / t, pr[5] / t, pr[6] / t);
         }
     }
     return MBPE_OK;

@@ -63,6 +63,14 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  : "memory");
 }
 
+// one 32-byte slot of the SMALL cache in ONE load (LDG.E.256, new with sm_100): one L1 wavefront per probe instead of two
+__device__ __forceinline__ void ld_slot256(const void *slot, uint4 &k, uint4 &v) {
+    unsigned long long q0, q1, q2, q3;
+    asm("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(q0), "=l"(q1), "=l"(q2), "=l"(q3) : "l"(slot));
+    k = make_uint4((uint32_t)q0, (uint32_t)(q0 >> 32), (uint32_t)q1, (uint32_t)(q1 >> 32));
+    v = make_uint4((uint32_t)q2, (uint32_t)(q2 >> 32), (uint32_t)q3, (uint32_t)(q3 >> 32));
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Chunk caches. The multi-pass scan of a chunk is a pure function of its bytes, and text repeats its chunks (Zipf):
 // the encoder keeps "chunk bytes -> ids" in two open-addressed tables in HBM.
@@ -260,24 +268,28 @@ struct EncArgs {
 constexpr int ENC_PROF_N = 8;
 constexpr uint32_t TILE_NONE = 0xFFFFFFFFu;
 constexpr uint64_t ENC_MAX_SUBBATCH = 1ull << 26; // chunks per launch at most (tile ids and look-back words are 32-bit safe)
-constexpr uint32_t PARK_NONE = 0xFFFFFFFFu; // ids of a chunk with more than 4 ids did not fit the parking area
+constexpr uint32_t PARK_NONE = 0xFFFFF;       // (20 bits) the ids of an open chunk did not fit the parking area
+constexpr uint32_t ET_WARP_SCAN_MAX = 48;     // up to this many scans per tile run one warp per chunk
 
 template <int THREADS, int CPT>
 struct EncSmemT {
     static constexpr int TILE = THREADS * CPT;
     static constexpr int TEXT_CAP = TILE * 10;  // staged text bytes per tile (average chunk ~5 bytes); wider tiles read HBM
     static constexpr int STAGE = TILE * 5 / 2;  // ids gathered per tile (average ~2.1 per chunk); more: direct stores
-    static constexpr int PARK = TILE / 2;       // ids of chunks with more than 4 ids, parked until the tile knows its place
-    alignas(128) uint32_t off[2][TILE + 8];     // boundaries, double buffered: the next tile's arrive during this tile's gather
+    static constexpr int PARK = TILE;           // ids of open chunks parked until the tile knows its place
+    alignas(128) uint32_t off[TILE + 8];
     alignas(128) uint32_t text[TEXT_CAP / 4 + 16]; // + halo: key assembly reads whole words past the chunk's end
     alignas(16) uint32_t stage[STAGE + 4];
     uint32_t park[PARK];
-    uint4 len_mask[16];        // len_mask[l] keeps the first l bytes of a 16-byte key
+    uint32_t meta[TILE];       // per open chunk (index = its place on the open list): start in park (20 bits) | id count << 20
+    uint16_t open_k[TILE];     // open list: chunk index within the tile
+    uint16_t mid[TILE];        // open chunks that may still be in a cache (beyond the SMALL home slot): open-list places
+    uint16_t scan[TILE];       // open chunks nobody has seen before: the scan has to encode them
     uint32_t warp_scratch[THREADS / 32][32];
     uint32_t warp_sum[THREADS / 32];
     alignas(8) uint64_t bar_off, bar_tile; // mbarriers: boundaries landed (thread 0 only waits), tile ready (all wait)
     unsigned long long base;
-    uint32_t tile[2], a0, staged, park_used;
+    uint32_t tile, a0, staged, n_open, n_mid, n_scan, n_scan2, park_used;
     unsigned long long prof[ENC_PROF_N];
 };
 
@@ -321,8 +333,22 @@ __device__ __forceinline__ uint32_t scan_chunk_warp(const EncTable &tab, uint32_
 template <class SM>
 __device__ __forceinline__ void big_key(const EncArgs &a, const SM &sm, bool staged, uint32_t a0, uint32_t o, uint32_t len,
                                         uint64_t *key) {
-    key[0] = key[1] = key[2] = key[3] = 0;
-    for (uint32_t i = 0; i < len; i++) key[i >> 3] |= (uint64_t)tile_byte(a, sm, staged, a0, o + i) << ((i & 7) * 8);
+    if (staged) { // whole words of the staged text (the halo makes the over-read safe), bytes past the chunk cleared
+        const uint32_t r = o - a0, wi = r >> 2, sh = (r & 3) * 8;
+        uint32_t w[9];
+#pragma unroll
+        for (int q = 0; q < 9; q++) w[q] = sm.text[wi + q];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t lo = __funnelshift_r(w[2 * q], w[2 * q + 1], sh), hi = __funnelshift_r(w[2 * q + 1], w[2 * q + 2], sh);
+            const int nb = (int)len - 8 * q; // bytes of this word that belong to the chunk
+            const uint64_t v = ((uint64_t)hi << 32) | lo;
+            key[q] = nb >= 8 ? v : nb <= 0 ? 0ull : (v & ((1ull << (8 * nb)) - 1));
+        }
+    } else {
+        key[0] = key[1] = key[2] = key[3] = 0;
+        for (uint32_t i = 0; i < len; i++) key[i >> 3] |= (uint64_t)tile_byte(a, sm, staged, a0, o + i) << ((i & 7) * 8);
+    }
     key[3] |= (uint64_t)len << 56;
 }
 
@@ -344,105 +370,187 @@ __device__ __forceinline__ void log_scanned(const EncArgs &a, const SM &sm, bool
     for (uint32_t i = 0; i < n; i++) e.ids[i] = ids[i];
 }
 
-// What the tile kernel knows about a chunk once it is resolved: n ids; n <= 4: the ids themselves in v, otherwise v.x = start
-// of the ids in the tile's parking area (PARK_NONE: no room, the owner encodes the chunk again when it writes).
-struct Resolved {
-    uint32_t n; // 0: not known yet
-    uint4 v;
-};
+// result of an open chunk: its ids go to the parking area, meta = start | n << 20 (start PARK_NONE: no room, the owner
+// encodes the chunk again when it writes)
 template <class SM>
-__device__ __forceinline__ Resolved park_ids(SM &sm, const uint32_t *ids, uint32_t n) {
-    Resolved r;
-    r.n = n;
-    if (n <= 4) {
-        r.v = make_uint4(ids[0], n > 1 ? ids[1] : 0u, n > 2 ? ids[2] : 0u, n > 3 ? ids[3] : 0u);
-        return r;
-    }
+__device__ __forceinline__ uint32_t park_ids(SM &sm, const uint32_t *ids, uint32_t n) {
     const uint32_t at = atomicAdd(&sm.park_used, n);
-    r.v = make_uint4(PARK_NONE, 0, 0, 0);
-    if (at + n <= (uint32_t)SM::PARK) {
-        r.v.x = at;
-        for (uint32_t i = 0; i < n; i++) sm.park[at + i] = ids[i];
-    }
-    return r;
+    if (at + n > (uint32_t)SM::PARK) return PARK_NONE | (n << 20);
+    for (uint32_t i = 0; i < n; i++) sm.park[at + i] = ids[i];
+    return at | (n << 20);
 }
 
-// A chunk the fast path did not resolve, by its own thread (no barrier inside: lanes that need it diverge, the others
-// wait at the warp's next convergence point). Kept out of line so that its registers (31-byte keys, id arrays) are not
-// charged to the fast path. Order: special tokens by exact compare; the rest of the chunk's probe sequence in the SMALL
-// cache (the fast path only saw the home slot); the BIG cache. n == 0: unknown, the scan has to decide.
+// the multi-pass scan of one chunk (<= ENC_SHORT_MAX bytes) by ONE thread (special tokens first); returns meta
 template <class SM>
-__device__ __noinline__ Resolved resolve_cached(const EncArgs &a, SM &sm, uint32_t a0, bool staged, uint32_t o, uint32_t len,
-                                                bool small_home_taken) {
-    Resolved r;
-    r.n = 0;
-    r.v = make_uint4(0, 0, 0, 0);
+__device__ __forceinline__ uint32_t scan_serial(const EncArgs &a, SM &sm, uint32_t a0, bool staged, uint32_t o, uint32_t len) {
+    uint32_t t[ENC_SHORT_MAX];
     const uint32_t sid = special_match(a.sp, len, [&](uint32_t i) { return tile_byte(a, sm, staged, a0, o + i); });
     if (sid != ENC_NONE) {
-        r.n = 1;
-        r.v.x = sid;
-        return r;
+        t[0] = sid;
+        return park_ids(sm, t, 1);
     }
-    if (!a.cache.small || len > CACHE_MAX_LEN || (a.ablate & 2)) return r;
-    uint64_t key[4];
-    big_key(a, sm, staged, a0, o, len, key);
-    if (len <= SMALL_MAX_LEN && (small_home_taken || !staged)) {
-        const uint32_t w0 = (uint32_t)key[0], w1 = (uint32_t)(key[0] >> 32), w2 = (uint32_t)key[1];
-        const uint32_t w3 = (uint32_t)(key[1] >> 32) | (len << 24);
-        uint32_t h = small_hash(w0, w1, w2, w3) >> a.cache.small_shift;
-        for (uint32_t probes = 0; probes < CACHE_MAX_PROBES; probes++) {
-            const uint4 *sp = reinterpret_cast<const uint4 *>(&a.cache.small[h]);
-            const uint4 kq = __ldg(sp);
-            if (kq.w == 0) break;
-            if ((kq.w & SMALL_KEY_MASK) == w3 && kq.x == w0 && kq.y == w1 && kq.z == w2) {
-                r.v = __ldg(sp + 1);
-                r.n = kq.w >> 28;
-                return r;
-            }
-            h = (h + 1) & a.cache.small_mask;
-        }
-    }
-    uint32_t h = cache_hash(key[0], key[1], key[2], key[3]) & a.cache.mask;
-    for (uint32_t probes = 0; probes < CACHE_MAX_PROBES; probes++) {
-        const ulonglong2 *sp = reinterpret_cast<const ulonglong2 *>(&a.cache.slots[h]);
-        const ulonglong2 lo = __ldg(sp), hi = __ldg(sp + 1);
-        const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(sp + 2)); // n, v[0..2]: fetched with the key, one round trip
-        if (hi.y == 0) break;
-        if (hi.y == key[3] && hi.x == key[2] && lo.x == key[0] && lo.y == key[1]) {
-            const uint32_t n = v0.x;
-            if (n <= 4) {
-                r.n = n;
-                r.v = make_uint4(v0.y, v0.z, v0.w, n > 3 ? __ldg(reinterpret_cast<const uint32_t *>(sp + 3)) : 0u);
-                return r;
-            }
-            uint32_t ids[CACHE_MAX_LEN];
-            if (n <= CACHE_INLINE_IDS) {
-                const uint4 v1 = __ldg(reinterpret_cast<const uint4 *>(sp + 3));
-                ids[0] = v0.y, ids[1] = v0.z, ids[2] = v0.w, ids[3] = v1.x, ids[4] = v1.y, ids[5] = v1.z, ids[6] = v1.w;
-            } else {
-                const uint32_t *src = a.cache.arena + v0.y;
-                for (uint32_t i = 0; i < n; i++) ids[i] = __ldg(&src[i]);
-            }
-            return park_ids(sm, ids, n);
-        }
-        h = (h + 1) & a.cache.mask;
-    }
-    return r;
-}
-
-// the multi-pass scan of one chunk (<= ENC_SHORT_MAX bytes) by ONE thread; the result is parked / logged
-template <class SM>
-__device__ __noinline__ Resolved scan_serial(const EncArgs &a, SM &sm, uint32_t a0, bool staged, uint32_t o, uint32_t len, bool log) {
-    uint32_t t[ENC_SHORT_MAX];
     for (uint32_t i = 0; i < len; i++) t[i] = tile_byte(a, sm, staged, a0, o + i);
     uint32_t n = len;
     bool merged = true;
     while (merged && n >= 2) n = enc_pass(a.tab, t, n, merged);
-    if (log) log_scanned(a, sm, staged, a0, o, len, t, n);
+    log_scanned(a, sm, staged, a0, o, len, t, n);
     return park_ids(sm, t, n);
 }
 
-// ids of a chunk that did not fit the parking area: encode it again, straight into place (rare)
+// one warp encodes the open chunk at open-list place q (<= 32 bytes) and parks its ids
+template <class SM>
+__device__ __forceinline__ void scan_by_warp(const EncArgs &a, SM &sm, uint32_t a0, bool staged, uint32_t q, uint32_t *scratch) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t k = sm.open_k[q], so = sm.off[k], mlen = sm.off[k + 1] - so;
+    uint32_t sid = ENC_NONE;
+    if (a.sp.n) sid = special_match(a.sp, mlen, [&](uint32_t i) { return tile_byte(a, sm, staged, a0, so + i); });
+    uint32_t tok = lane < mlen ? tile_byte(a, sm, staged, a0, so + lane) : 0u;
+    uint32_t mn = 1;
+    if (sid != ENC_NONE)
+        tok = sid; // (every lane found the same token)
+    else
+        mn = scan_chunk_warp(a.tab, tok, mlen, scratch); // lane i < mn: id i in tok
+    uint32_t start = 0;
+    if (lane == 0) start = atomicAdd(&sm.park_used, mn);
+    start = __shfl_sync(0xffffffffu, start, 0);
+    if (start + mn <= (uint32_t)SM::PARK) {
+        if (lane < mn) sm.park[start + lane] = tok;
+    } else {
+        start = PARK_NONE;
+    }
+    if (lane == 0) sm.meta[q] = start | (mn << 20);
+    if (a.cache.small && mlen <= CACHE_MAX_LEN && sid == ENC_NONE) { // teach the caches
+        uint32_t li = 0;
+        if (lane == 0) li = atomicAdd(a.cache.log_count, 1u);
+        li = __shfl_sync(0xffffffffu, li, 0);
+        if (li < a.cache.log_cap) {
+            CacheLogEntry &e = a.cache.log[li];
+            if (lane < mn) e.ids[lane] = tok;
+            if (lane == 0) {
+                uint64_t key[4];
+                big_key(a, sm, staged, a0, so, mlen, key);
+                e.k[0] = key[0];
+                e.k[1] = key[1];
+                e.k[2] = key[2];
+                e.k[3] = key[3];
+                e.n = mn;
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// The tile's open chunks, by all threads of the CTA (contains barriers). Kept out of line: its register needs (31-byte
+// keys, id arrays) must not be charged to the fast path, which runs for nine chunks in ten.
+//   round 1, at the same time: the first half of the warps looks the MID list up, one thread per entry -- special tokens
+//            by exact compare, the rest of the SMALL probe sequence (the fast path saw the home slot only), the BIG cache
+//            (key and value sectors of a slot in flight together); the second half scans the SCAN list, one warp per
+//            chunk (lanes = positions, one lookup latency per pass). Many scans (cold caches): one thread per chunk.
+//   round 2 (rare): MID entries that were in no cache are scanned.
+template <int THREADS, class SM>
+__device__ __noinline__ void resolve_open_chunks(const EncArgs &a, SM &sm, uint32_t a0, bool staged) {
+    constexpr int NW = THREADS / 32, HALF = NW / 2;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t n_mid = sm.n_mid, n_scan = sm.n_scan;
+    const bool crowd = n_scan > ET_WARP_SCAN_MAX;
+    if (warp < HALF || crowd || n_scan == 0) {
+        const uint32_t first = (crowd || n_scan == 0) ? tid : tid, step = (crowd || n_scan == 0) ? THREADS : HALF * 32;
+        for (uint32_t i = first; i < n_mid; i += step) {
+            const uint32_t q = sm.mid[i], k = sm.open_k[q], so = sm.off[k], len = sm.off[k + 1] - so;
+            uint32_t ids[CACHE_MAX_LEN], n = 0;
+            const uint32_t sid = special_match(a.sp, len, [&](uint32_t b) { return tile_byte(a, sm, staged, a0, so + b); });
+            if (sid != ENC_NONE) {
+                ids[0] = sid;
+                n = 1;
+            } else if (a.cache.small && len <= CACHE_MAX_LEN) {
+                uint64_t key[4];
+                big_key(a, sm, staged, a0, so, len, key);
+                if (len <= SMALL_MAX_LEN) {
+                    const uint32_t w0 = (uint32_t)key[0], w1 = (uint32_t)(key[0] >> 32), w2 = (uint32_t)key[1];
+                    const uint32_t w3 = (uint32_t)(key[1] >> 32) | (len << 24);
+                    uint32_t h = small_hash(w0, w1, w2, w3) >> a.cache.small_shift;
+                    for (uint32_t probes = 0; probes < CACHE_MAX_PROBES; probes++) {
+                        uint4 kq, vv;
+                        ld_slot256(&a.cache.small[h], kq, vv);
+                        if (kq.w == 0) break;
+                        if ((kq.w & SMALL_KEY_MASK) == w3 && kq.x == w0 && kq.y == w1 && kq.z == w2) {
+                            n = kq.w >> 28;
+                            ids[0] = vv.x, ids[1] = vv.y, ids[2] = vv.z, ids[3] = vv.w;
+                            break;
+                        }
+                        h = (h + 1) & a.cache.small_mask;
+                    }
+                }
+                if (n == 0) {
+                    uint32_t h = cache_hash(key[0], key[1], key[2], key[3]) & a.cache.mask;
+                    for (uint32_t probes = 0; probes < CACHE_MAX_PROBES; probes++) {
+                        uint4 k0, k1, v0, v1; // the whole 64-byte slot: two 32-byte loads in flight together
+                        ld_slot256(&a.cache.slots[h], k0, k1);
+                        ld_slot256(reinterpret_cast<const uint8_t *>(&a.cache.slots[h]) + 32, v0, v1);
+                        if ((k1.z | k1.w) == 0) break; // k[3] == 0: empty
+                        if (k0.x == (uint32_t)key[0] && k0.y == (uint32_t)(key[0] >> 32) && k0.z == (uint32_t)key[1] &&
+                            k0.w == (uint32_t)(key[1] >> 32) && k1.x == (uint32_t)key[2] && k1.y == (uint32_t)(key[2] >> 32) &&
+                            k1.z == (uint32_t)key[3] && k1.w == (uint32_t)(key[3] >> 32)) {
+                            n = v0.x;
+                            if (n <= CACHE_INLINE_IDS) {
+                                ids[0] = v0.y, ids[1] = v0.z, ids[2] = v0.w, ids[3] = v1.x, ids[4] = v1.y, ids[5] = v1.z, ids[6] = v1.w;
+                            } else {
+                                const uint32_t *src = a.cache.arena + v0.y;
+                                for (uint32_t b = 0; b < n; b++) ids[b] = __ldg(&src[b]);
+                            }
+                            break;
+                        }
+                        h = (h + 1) & a.cache.mask;
+                    }
+                }
+            }
+            if (n == 0) { // in no cache: round 2
+                sm.scan[(uint32_t)SM::TILE - 1 - atomicAdd(&sm.n_scan2, 1u)] = (uint16_t)q;
+                continue;
+            }
+            sm.meta[q] = park_ids(sm, ids, n);
+        }
+    }
+    if (crowd) {
+        for (uint32_t s = tid; s < n_scan; s += THREADS) {
+            const uint32_t q = sm.scan[s], k = sm.open_k[q], so = sm.off[k];
+            sm.meta[q] = scan_serial(a, sm, a0, staged, so, sm.off[k + 1] - so);
+        }
+    } else if (warp >= HALF) {
+        for (uint32_t s = warp - HALF; s < n_scan; s += NW - HALF) {
+            const uint32_t q = sm.scan[s], k = sm.open_k[q];
+            if (sm.off[k + 1] - sm.off[k] > 32) { // 33..64 bytes do not fit the lanes
+                if ((tid & 31) == 0) sm.meta[q] = scan_serial(a, sm, a0, staged, sm.off[k], sm.off[k + 1] - sm.off[k]);
+                __syncwarp();
+                continue;
+            }
+            scan_by_warp(a, sm, a0, staged, q, sm.warp_scratch[warp]);
+        }
+    }
+    __syncthreads();
+    const uint32_t n2 = sm.n_scan2;
+    if (tid == 0 && (n_scan + n2)) atomicAdd(a.miss_count, n_scan + n2);
+    if (n2 == 0) return;
+    if (n2 > ET_WARP_SCAN_MAX) {
+        for (uint32_t s = tid; s < n2; s += THREADS) {
+            const uint32_t q = sm.scan[(uint32_t)SM::TILE - 1 - s], k = sm.open_k[q], so = sm.off[k];
+            sm.meta[q] = scan_serial(a, sm, a0, staged, so, sm.off[k + 1] - so);
+        }
+    } else {
+        for (uint32_t s = warp; s < n2; s += NW) {
+            const uint32_t q = sm.scan[(uint32_t)SM::TILE - 1 - s], k = sm.open_k[q];
+            if (sm.off[k + 1] - sm.off[k] > 32) {
+                if ((tid & 31) == 0) sm.meta[q] = scan_serial(a, sm, a0, staged, sm.off[k], sm.off[k + 1] - sm.off[k]);
+                __syncwarp();
+                continue;
+            }
+            scan_by_warp(a, sm, a0, staged, q, sm.warp_scratch[warp]);
+        }
+    }
+    __syncthreads();
+}
+
+// ids of an open chunk that did not fit the parking area: encode it again, straight into place (rare)
 template <class SM>
 __device__ __noinline__ void rescan_into(const EncArgs &a, SM &sm, uint32_t a0, bool staged, uint32_t o, uint32_t len, uint32_t *dst,
                                          uint32_t n) {
@@ -460,62 +568,62 @@ __device__ __noinline__ void rescan_into(const EncArgs &a, SM &sm, uint32_t a0, 
     for (uint32_t i = 0; i < n && i < m; i++) dst[i] = t[i];
 }
 
-// one chunk's ids -> dst[0 .. n) (shared-memory gather buffer, or the stream itself for oversized tiles)
+// one chunk's ids -> dst[0 .. n) (shared-memory gather buffer, or the stream itself for oversized tiles).
+// openq: the chunk's place on the open list, or TILE_NONE: its (<= 4) ids are in v
 template <class SM>
-__device__ __forceinline__ void emit_chunk(const EncArgs &a, SM &sm, uint32_t a0, bool staged, uint32_t n, uint32_t o0, uint32_t o1,
-                                           uint4 v, uint32_t *dst, uint64_t room) {
+__device__ __forceinline__ void emit_chunk(const EncArgs &a, SM &sm, uint32_t a0, bool staged, uint32_t n, uint32_t openq, uint32_t o0,
+                                           uint32_t o1, uint4 v, uint32_t *dst, uint64_t room) {
     if (n == 0) return;
     if (n > room) {
         *a.overflow = 1;
         return;
     }
-    if (n <= 4 && o1 - o0 <= ENC_SHORT_MAX) {
-        dst[0] = v.x;
-        if (n > 1) dst[1] = v.y;
-        if (n > 2) dst[2] = v.z;
-        if (n > 3) dst[3] = v.w;
-    } else if (o1 - o0 > ENC_SHORT_MAX) {
-        for (uint32_t i = 0; i < n; i++) dst[i] = a.scratch_a[o0 + i];
-    } else if (v.x != PARK_NONE) {
-        for (uint32_t i = 0; i < n; i++) dst[i] = sm.park[v.x + i];
+    if (openq == TILE_NONE) {
+        if (o1 - o0 > ENC_SHORT_MAX) {
+            for (uint32_t i = 0; i < n; i++) dst[i] = a.scratch_a[o0 + i];
+        } else {
+            dst[0] = v.x;
+            if (n > 1) dst[1] = v.y;
+            if (n > 2) dst[2] = v.z;
+            if (n > 3) dst[3] = v.w;
+        }
     } else {
-        rescan_into(a, sm, a0, staged, o0, o1 - o0, dst, n);
+        const uint32_t start = sm.meta[openq] & 0xFFFFF;
+        if (start != PARK_NONE) {
+            for (uint32_t i = 0; i < n; i++) dst[i] = sm.park[start + i];
+        } else {
+            rescan_into(a, sm, a0, staged, o0, o1 - o0, dst, n);
+        }
     }
 }
 
-// thread 0, first half of a tile fetch: the ticket, and the tile's boundaries on their way into off[buf]
+// thread 0: ticket, then the tile's boundaries and text window into shared memory by bulk copies.
+// Publishes sm.tile / sm.a0 / sm.staged and completes sm.bar_tile when everything has landed.
 template <class SM>
-__device__ __forceinline__ void fetch_tile_begin(const EncArgs &a, SM &sm, uint32_t buf, uint64_t policy) {
+__device__ __forceinline__ void fetch_tile_bulk(const EncArgs &a, SM &sm, uint32_t &off_parity, uint64_t policy) {
     const uint32_t t = atomicAdd(a.ticket, 1u); // tiles start in order: look-back cannot deadlock
-    sm.tile[buf] = t < a.n_tiles ? t : TILE_NONE;
-    if (t >= a.n_tiles) return;
+    if (t >= a.n_tiles) {
+        sm.tile = TILE_NONE;
+        mbar_arrive(&sm.bar_tile);
+        return;
+    }
     const uint64_t c0 = a.chunk0 + (uint64_t)t * SM::TILE;
     const uint32_t nc = (uint32_t)min((uint64_t)SM::TILE, a.chunk1 - c0);
     const uint32_t nw = nc + 1, nb = nw & ~3u; // whole 16-byte vectors by bulk copy, the last <= 3 words by hand
     if (nb) {
         mbar_arrive_expect_tx(&sm.bar_off, nb * 4);
-        bulk_g2s(sm.off[buf], a.off + c0, nb * 4, &sm.bar_off, policy);
+        bulk_g2s(sm.off, a.off + c0, nb * 4, &sm.bar_off, policy);
     } else {
         mbar_arrive(&sm.bar_off);
     }
-    for (uint32_t i = nb; i < nw; i++) sm.off[buf][i] = __ldg(&a.off[c0 + i]);
-}
-// second half (nobody reads the previous tile's text any more): the text window; completes sm.bar_tile
-template <class SM>
-__device__ __forceinline__ void fetch_tile_finish(const EncArgs &a, SM &sm, uint32_t buf, uint32_t &off_parity, uint64_t policy) {
-    const uint32_t t = sm.tile[buf];
-    if (t == TILE_NONE) {
-        mbar_arrive(&sm.bar_tile);
-        return;
-    }
+    for (uint32_t i = nb; i < nw; i++) sm.off[i] = __ldg(&a.off[c0 + i]);
     mbar_wait(&sm.bar_off, off_parity);
     off_parity ^= 1;
-    const uint64_t c0 = a.chunk0 + (uint64_t)t * SM::TILE;
-    const uint32_t nc = (uint32_t)min((uint64_t)SM::TILE, a.chunk1 - c0);
-    const uint32_t b0 = sm.off[buf][0], b1 = sm.off[buf][nc];
+    const uint32_t b0 = sm.off[0], b1 = sm.off[nc];
     const uint32_t a0 = b0 & ~15u; // 16-byte aligned window start
     const uint32_t span = b1 - a0;
     const bool staged = span <= (uint32_t)SM::TEXT_CAP;
+    sm.tile = t;
     sm.a0 = a0;
     sm.staged = staged;
     if (staged) {
@@ -536,25 +644,16 @@ template <int THREADS, int CPT, int MIN_CTAS>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArgs a) {
     using SM = EncSmemT<THREADS, CPT>;
     constexpr int TILE = SM::TILE, NW = THREADS / 32;
-    static_assert(NW >= 2, "warp 0 looks back while the last warp starts the next tile's fetch");
+    static_assert(NW >= 2, "the open chunks are split over two halves of the warps");
     extern __shared__ __align__(128) unsigned char enc_smem_raw[];
     SM &sm = *reinterpret_cast<SM *>(enc_smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool bulk = a.bulk != 0;
-    if (tid < 16) { // len_mask[l]: ones over the first l bytes
-        uint32_t m[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int nb = (int)tid - 4 * q;
-            m[q] = nb >= 4 ? 0xFFFFFFFFu : nb <= 0 ? 0u : ((1u << (8 * nb)) - 1);
-        }
-        sm.len_mask[tid] = make_uint4(m[0], m[1], m[2], m[3]);
-    }
     if (tid == 0) {
         mbar_init(&sm.bar_off, 1);
         mbar_init(&sm.bar_tile, 1);
         mbar_init_fence();
-        sm.park_used = 0;
+        sm.n_open = sm.n_mid = sm.n_scan = sm.n_scan2 = sm.park_used = 0;
         for (int i = 0; i < ENC_PROF_N; i++) sm.prof[i] = 0;
     }
     __syncthreads();
@@ -568,12 +667,8 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
     };
     uint32_t tile_parity = 0, off_parity = 0;
     const uint64_t policy = l2_evict_first_policy();
-    if (bulk && tid == 0) {
-        fetch_tile_begin(a, sm, 0, policy);
-        fetch_tile_finish(a, sm, 0, off_parity, policy);
-    }
-    for (uint32_t it = 0;; it++) {
-        const uint32_t buf = it & 1;
+    if (bulk && tid == 0) fetch_tile_bulk(a, sm, off_parity, policy);
+    for (;;) {
         // ---- 0. the tile's boundaries and text in shared memory ----------------------------------------------------
         if (bulk) {
             mbar_wait(&sm.bar_tile, tile_parity);
@@ -582,20 +677,19 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
             __syncthreads();
             if (tid == 0) {
                 const uint32_t t = atomicAdd(a.ticket, 1u);
-                sm.tile[buf] = t < a.n_tiles ? t : TILE_NONE;
-                sm.park_used = 0;
+                sm.tile = t < a.n_tiles ? t : TILE_NONE;
+                sm.n_open = sm.n_mid = sm.n_scan = sm.n_scan2 = sm.park_used = 0;
             }
             __syncthreads();
         }
-        const uint32_t tile = sm.tile[buf];
+        const uint32_t tile = sm.tile;
         if (tile == TILE_NONE) break;
         const uint64_t c0 = a.chunk0 + (uint64_t)tile * TILE;
         const uint32_t nc = (uint32_t)min((uint64_t)TILE, a.chunk1 - c0);
-        const uint32_t *const soff = sm.off[buf];
         if (!bulk) {
-            for (uint32_t i = tid; i <= nc; i += THREADS) sm.off[buf][i] = __ldg(&a.off[c0 + i]);
+            for (uint32_t i = tid; i <= nc; i += THREADS) sm.off[i] = __ldg(&a.off[c0 + i]);
             __syncthreads();
-            const uint32_t b0 = soff[0], b1 = soff[nc], w0 = b0 & ~3u;
+            const uint32_t b0 = sm.off[0], b1 = sm.off[nc], w0 = b0 & ~3u;
             const bool st = (b1 - w0) <= (uint32_t)SM::TEXT_CAP;
             if (st) // byte loads: nothing is known about the alignment of the buffer
                 for (uint32_t g = b0 + tid; g < b1; g += THREADS) reinterpret_cast<uint8_t *>(sm.text)[g - w0] = __ldg(&a.bytes[g]);
@@ -612,28 +706,32 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
         // ---- 1. fast path: the home slot of every chunk in the SMALL cache, all of a thread's probes in flight ------
         uint32_t o[CPT + 1];
 #pragma unroll
-        for (int j = 0; j <= CPT; j++) o[j] = soff[min(tid * CPT + j, nc)];
+        for (int j = 0; j <= CPT; j++) o[j] = sm.off[min(tid * CPT + j, nc)];
         uint32_t cnt[CPT];
-        uint4 vq[CPT];      // the chunk's ids (cnt <= 4), or where they are parked
-        uint32_t todo = 0;  // bit j: chunk j still unknown; bit 8 + j: ... and its home slot in the SMALL cache was taken
-        const bool keyed = a.cache.small != nullptr && staged; // (an unstaged tile -- very long chunks -- skips the fast path)
-        if (keyed && !(a.ablate & 2)) {
+        uint32_t openq[CPT]; // place on the open list, or TILE_NONE: cnt / vq are final
+        uint4 vq[CPT];       // hit: the chunk's ids
+        uint32_t home_taken = 0; // bit j: the chunk's home slot in the SMALL cache holds another chunk
+        const bool keyed = a.cache.small != nullptr && staged && !(a.ablate & 2); // (an unstaged tile -- very long chunks -- is all "open")
+        if (keyed) {
             uint4 kw[CPT], kq[CPT];
 #pragma unroll
             for (int j = 0; j < CPT; j++) {
                 const uint32_t len = o[j + 1] - o[j];
                 // the 16 bytes at the chunk's start, bytes at and after `len` cleared, length in the top byte
                 const uint32_t r = o[j] - a0, wi = r >> 2, sh = (r & 3) * 8;
-                const uint4 lm = sm.len_mask[len & 15];
+                const uint32_t nb = len < 16 ? len : 0; // ones over the key's first `len` bytes, word by word
+                uint4 lm;
+                lm.x = (uint32_t)((1ull << (8 * min(nb, 4u))) - 1);
+                lm.y = (uint32_t)((1ull << (8 * (min(max(nb, 4u), 8u) - 4))) - 1);
+                lm.z = (uint32_t)((1ull << (8 * (min(max(nb, 8u), 12u) - 8))) - 1);
+                lm.w = (uint32_t)((1ull << (8 * (min(max(nb, 12u), 16u) - 12))) - 1);
                 const uint32_t t0 = sm.text[wi], t1 = sm.text[wi + 1], t2 = sm.text[wi + 2], t3 = sm.text[wi + 3], t4 = sm.text[wi + 4];
                 kw[j].x = __funnelshift_r(t0, t1, sh) & lm.x;
                 kw[j].y = __funnelshift_r(t1, t2, sh) & lm.y;
                 kw[j].z = __funnelshift_r(t2, t3, sh) & lm.z;
                 kw[j].w = (__funnelshift_r(t3, t4, sh) & lm.w) | (len << 24);
                 const uint32_t h = small_hash(kw[j].x, kw[j].y, kw[j].z, kw[j].w) >> a.cache.small_shift;
-                const uint4 *sp = reinterpret_cast<const uint4 *>(&a.cache.small[h]); // (empty / long chunks probe too:
-                kq[j] = __ldg(sp);                                                      //  the answer is ignored)
-                vq[j] = __ldg(sp + 1);
+                ld_slot256(&a.cache.small[h], kq[j], vq[j]); // (empty / long chunks probe too: the answer is ignored)
             }
 #pragma unroll
             for (int j = 0; j < CPT; j++) {
@@ -641,103 +739,60 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
                 const bool small = len - 1u < SMALL_MAX_LEN;
                 const bool hit = small && (kq[j].w & SMALL_KEY_MASK) == kw[j].w && kq[j].x == kw[j].x && kq[j].y == kw[j].y && kq[j].z == kw[j].z;
                 cnt[j] = hit ? kq[j].w >> 28 : 0u;
-                if (!hit) todo |= (1u << j) | ((small && kq[j].w != 0) ? 0x100u << j : 0u);
+                openq[j] = hit ? TILE_NONE : 0u; // 0: undecided, see below
+                if (small && kq[j].w != 0) home_taken |= 1u << j;
             }
         } else {
 #pragma unroll
             for (int j = 0; j < CPT; j++) {
                 cnt[j] = 0;
+                openq[j] = 0;
                 vq[j] = make_uint4(0, 0, 0, 0);
             }
-            todo = (1u << CPT) - 1;
+            home_taken = a.cache.small ? ~0u : 0u; // (no home slot was looked at: the whole probe sequence is open)
         }
-        // ---- 2. what the fast path left open: by the chunk's own thread, then by its warp; no block barrier ------------
 #pragma unroll
         for (int j = 0; j < CPT; j++) {
+            if (openq[j] == TILE_NONE) continue; // hit
+            openq[j] = TILE_NONE;
             const uint32_t k = tid * CPT + j, len = o[j + 1] - o[j];
-            bool open = (todo >> j) & 1u;
-            if (open && (k >= nc || len == 0)) open = false; // nothing to encode
-            if (open && len > ENC_SHORT_MAX) {
+            if (k >= nc || len == 0) continue;
+            if (len > ENC_SHORT_MAX) {
                 if (a.scratch_b) {
                     cnt[j] = a.scratch_b[o[j]]; // encoded by k_encode_long
                 } else {                         // optimistic launch: report it, the host runs the long path and repeats
                     const uint32_t q = atomicAdd(a.n_long, 1u);
                     if (q < a.long_cap) a.long_list[q] = (uint32_t)(c0 + k);
                 }
-                open = false;
+                continue;
             }
-            if (open && (a.ablate & 10)) { // (profiling only: 2 = every chunk "hits", 8 = no slow path)
+            if (a.ablate & 10) { // (profiling only: 2 = every chunk "hits", 8 = no slow path)
                 cnt[j] = (a.ablate & 2) ? 2 : 1;
                 vq[j] = make_uint4(o[j], len, 0, 0);
-                open = false;
+                continue;
             }
-            if (open) { // special tokens, the rest of the SMALL probe sequence, the BIG cache
-                const Resolved r = resolve_cached(a, sm, a0, staged, o[j], len, (todo >> (8 + j)) & 1u);
-                if (r.n) {
-                    cnt[j] = r.n;
-                    vq[j] = r.v;
-                    open = false;
-                }
-            }
-            // the scan itself: chunks nobody has seen before. Few in the warp (warm caches): one after the other, the whole
-            // warp on each (lanes = positions, one lookup latency per pass). Many (cold caches): every lane scans its own.
-            uint32_t pending = __ballot_sync(0xffffffffu, open);
-            if (pending && lane == 0) atomicAdd(a.miss_count, (uint32_t)__popc(pending));
-            if (__popc(pending) > 6 || __any_sync(0xffffffffu, open && len > 32)) { // (chunks of 33..64 bytes do not fit the lanes)
-                if (open) {
-                    const Resolved r = scan_serial(a, sm, a0, staged, o[j], len, true);
-                    cnt[j] = r.n;
-                    vq[j] = r.v;
-                }
-                pending = 0;
-            }
-            while (pending) {
-                const int src = __ffs(pending) - 1;
-                pending &= pending - 1;
-                const uint32_t so = __shfl_sync(0xffffffffu, o[j], src), mlen = __shfl_sync(0xffffffffu, len, src);
-                uint32_t tok = lane < mlen ? tile_byte(a, sm, staged, a0, so + lane) : 0u;
-                const uint32_t mn = scan_chunk_warp(a.tab, tok, mlen, sm.warp_scratch[warp]); // lane i < mn: id i in tok
-                if (a.cache.small && mlen <= CACHE_MAX_LEN) { // teach the caches
-                    uint32_t li = 0;
-                    if (lane == 0) li = atomicAdd(a.cache.log_count, 1u);
-                    li = __shfl_sync(0xffffffffu, li, 0);
-                    if (li < a.cache.log_cap) {
-                        CacheLogEntry &e = a.cache.log[li];
-                        if (lane < mn) e.ids[lane] = tok;
-                        if (lane == 0) {
-                            uint64_t key[4];
-                            big_key(a, sm, staged, a0, so, mlen, key);
-                            e.k[0] = key[0];
-                            e.k[1] = key[1];
-                            e.k[2] = key[2];
-                            e.k[3] = key[3];
-                            e.n = mn;
-                        }
-                    }
-                }
-                // hand the ids to the owner: up to 4 through shuffles, more through the parking area
-                const uint32_t i0 = __shfl_sync(0xffffffffu, tok, 0), i1 = __shfl_sync(0xffffffffu, tok, 1);
-                const uint32_t i2 = __shfl_sync(0xffffffffu, tok, 2), i3 = __shfl_sync(0xffffffffu, tok, 3);
-                uint32_t at = PARK_NONE;
-                if (mn > 4) {
-                    if (lane == 0) {
-                        at = atomicAdd(&sm.park_used, mn);
-                        if (at + mn > (uint32_t)SM::PARK) at = PARK_NONE;
-                    }
-                    at = __shfl_sync(0xffffffffu, at, 0);
-                    if (at != PARK_NONE && lane < mn) sm.park[at + lane] = tok;
-                }
-                if ((int)lane == src) {
-                    cnt[j] = mn;
-                    vq[j] = mn > 4 ? make_uint4(at, 0, 0, 0) : make_uint4(i0, i1, i2, i3);
-                }
-                __syncwarp();
-            }
+            const uint32_t q = atomicAdd(&sm.n_open, 1u);
+            sm.open_k[q] = (uint16_t)k;
+            openq[j] = q;
+            // may it still be in a cache? a special token; a chunk of 16..31 bytes (BIG); a short one whose home slot holds
+            // somebody else (its probe sequence continues; or it has more than 4 ids and lives in BIG)
+            const bool maybe_cached = a.cache.small != nullptr && len <= CACHE_MAX_LEN && (len > SMALL_MAX_LEN || ((home_taken >> j) & 1u));
+            if (maybe_cached || (a.sp.n && ((a.sp.len_mask >> (len < 63u ? len : 63u)) & 1ull)))
+                sm.mid[atomicAdd(&sm.n_mid, 1u)] = (uint16_t)q;
+            else
+                sm.scan[atomicAdd(&sm.n_scan, 1u)] = (uint16_t)q;
         }
+        __syncthreads();
         lap(1);
+        // ---- 2. open chunks ----------------------------------------------------------------------------------------------
+        if (sm.n_open) resolve_open_chunks<THREADS>(a, sm, a0, staged);
+        lap(2);
         uint32_t sum = 0;
 #pragma unroll
-        for (int j = 0; j < CPT; j++) sum += cnt[j];
+        for (int j = 0; j < CPT; j++) {
+            if (openq[j] != TILE_NONE) cnt[j] = sm.meta[openq[j]] >> 20;
+            sum += cnt[j];
+        }
         // ---- 3. place in the stream: block exclusive scan + look-back; ids gathered in shared memory ------------------
         uint32_t incl = sum;
 #pragma unroll
@@ -759,9 +814,6 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
             const uint64_t b = (a.ablate & 1) ? (uint64_t)tile * (TILE * 9 / 4)
                                               : lookback_base<4>(a.status, tile, total, a.stream_base);
             if (lane == 0) sm.base = b;
-        } else if (bulk && tid == THREADS - 32) {
-            // while warp 0 looks back: the next tile's ticket, and its boundaries on their way into off[buf ^ 1]
-            fetch_tile_begin(a, sm, buf ^ 1, policy);
         }
         const bool via_smem = total <= (uint32_t)SM::STAGE;
         const uint32_t loc0 = warp_base + (incl - sum);
@@ -769,7 +821,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
             uint32_t loc = loc0;
 #pragma unroll
             for (int j = 0; j < CPT; j++) {
-                emit_chunk(a, sm, a0, staged, cnt[j], o[j], o[j + 1], vq[j], sm.stage + loc, ~0ull);
+                emit_chunk(a, sm, a0, staged, cnt[j], openq[j], o[j], o[j + 1], vq[j], sm.stage + loc, ~0ull);
                 loc += cnt[j];
             }
         }
@@ -781,15 +833,15 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
 #pragma unroll
             for (int j = 0; j < CPT; j++) {
                 const uint64_t at = base + loc;
-                emit_chunk(a, sm, a0, staged, cnt[j], o[j], o[j + 1], vq[j], a.out + at, at < a.out_cap ? a.out_cap - at : 0);
+                emit_chunk(a, sm, a0, staged, cnt[j], openq[j], o[j], o[j + 1], vq[j], a.out + at, at < a.out_cap ? a.out_cap - at : 0);
                 loc += cnt[j];
             }
-            __syncthreads(); // (emit may read the tile's text and parking area: they are replaced below)
+            __syncthreads(); // (emit may read the tile's text and lists: they are replaced below)
         }
-        // ---- 4. the next tile's text starts now; this tile's ids leave as whole lines --------------------------------
+        // ---- 4. the next tile's loads start now; this tile's ids leave as whole lines --------------------------------
         if (bulk && tid == 0) {
-            sm.park_used = 0; // (the next tile parks after the next mbarrier wait)
-            fetch_tile_finish(a, sm, buf ^ 1, off_parity, policy);
+            sm.n_open = sm.n_mid = sm.n_scan = sm.n_scan2 = sm.park_used = 0; // (the next tile's appends come after the next mbarrier wait)
+            fetch_tile_bulk(a, sm, off_parity, policy);
         }
         lap(5);
         if (a.out_off) {
