@@ -81,12 +81,13 @@ __device__ __forceinline__ void ld_slot256(const void *slot, uint4 &k, uint4 &v)
 // Results are bit-identical with or without the caches (MBPE_ENCODE_CACHE=0 disables them; tests run both).
 // ---------------------------------------------------------------------------------------------------------
 struct SmallSlot { // 32 bytes
-    uint32_t k[4]; // bytes 0..14 little endian, zero padded; k[3] bits 24..27 = length (1..15), bits 28..30 = id count;
+    uint32_t k[4]; // bytes 0..14 little endian, zero padded; k[3] bits 24..27 = length (1..15), bits 28..30 = id count (7: stub);
                    // k[3] == 0: empty
     uint32_t v[4]; // the ids
 };
 static_assert(sizeof(SmallSlot) == 32, "one sector per entry");
 constexpr uint32_t SMALL_MAX_LEN = 15, SMALL_MAX_IDS = 4, SMALL_KEY_MASK = 0x0FFFFFFFu;
+constexpr uint32_t SMALL_STUB = 7; // id count of a stub: the chunk has more than 4 ids, they are in the BIG cache
 
 struct CacheSlot { // 64 bytes = two sectors: key, value
     uint64_t k[4]; // chunk bytes, little endian, zero padded; top byte of k[3] = length (1..31); k[3] == 0: empty
@@ -139,34 +140,38 @@ __global__ void k_cache_insert(ChunkCache cc) {
         const CacheLogEntry &e = cc.log[i];
         const uint64_t k0 = e.k[0], k1 = e.k[1], k2 = e.k[2], k3 = e.k[3];
         const uint32_t en = e.n, len = (uint32_t)(k3 >> 56);
-        if (len <= SMALL_MAX_LEN && en <= SMALL_MAX_IDS) {
-            if (*((volatile uint32_t *)(cc.used + 1)) * 2 > cc.small_mask) continue; // half full: stop learning
-            const uint32_t w0 = (uint32_t)k0, w1 = (uint32_t)(k0 >> 32), w2 = (uint32_t)k1;
-            const uint32_t w3 = (uint32_t)(k1 >> 32) | (len << 24); // byte 15 is free: len <= 15
-            uint32_t h = small_hash(w0, w1, w2, w3) >> cc.small_shift;
-            for (uint32_t probes = 0; probes < CACHE_MAX_PROBES; probes++) {
-                SmallSlot *s = &cc.small[h];
-                uint32_t cur = *((volatile uint32_t *)&s->k[3]);
-                if (cur == 0) {
-                    cur = atomicCAS(&s->k[3], 0u, w3 | (en << 28));
-                    if (cur == 0) { // claimed: k[3] is the claim word, the rest is written by the winner only
-                        s->k[0] = w0;
-                        s->k[1] = w1;
-                        s->k[2] = w2;
-                        for (uint32_t q = 0; q < SMALL_MAX_IDS; q++) s->v[q] = q < en ? e.ids[q] : 0u;
-                        atomicAdd(cc.used + 1, 1u);
-                        break;
+        // SMALL entry: the ids themselves (<= 4), or -- for a short chunk with more ids -- a stub (id count 7) that says
+        // "look in BIG": the tile kernel's fast path then knows the chunk is cached without probing BIG for every miss
+        if (len <= SMALL_MAX_LEN) {
+            const bool stub = en > SMALL_MAX_IDS;
+            if (*((volatile uint32_t *)(cc.used + 1)) * 2 <= cc.small_mask) { // (half full: stop learning)
+                const uint32_t w0 = (uint32_t)k0, w1 = (uint32_t)(k0 >> 32), w2 = (uint32_t)k1;
+                const uint32_t w3 = (uint32_t)(k1 >> 32) | (len << 24); // byte 15 is free: len <= 15
+                uint32_t h = small_hash(w0, w1, w2, w3) >> cc.small_shift;
+                for (uint32_t probes = 0; probes < CACHE_MAX_PROBES; probes++) {
+                    SmallSlot *s = &cc.small[h];
+                    uint32_t cur = *((volatile uint32_t *)&s->k[3]);
+                    if (cur == 0) {
+                        cur = atomicCAS(&s->k[3], 0u, w3 | ((stub ? SMALL_STUB : en) << 28));
+                        if (cur == 0) { // claimed: k[3] is the claim word, the rest is written by the winner only
+                            s->k[0] = w0;
+                            s->k[1] = w1;
+                            s->k[2] = w2;
+                            for (uint32_t q = 0; q < SMALL_MAX_IDS; q++) s->v[q] = (!stub && q < en) ? e.ids[q] : 0u;
+                            atomicAdd(cc.used + 1, 1u);
+                            break;
+                        }
                     }
+                    // Same key: already there (the log holds duplicates of hot chunks). Words of a slot claimed in THIS launch
+                    // may not be visible yet; then the duplicate takes a second slot -- harmless, both slots hold the same ids
+                    // and a reader uses the first one it finds.
+                    if ((cur & SMALL_KEY_MASK) == w3 && *((volatile uint32_t *)&s->k[0]) == w0 &&
+                        *((volatile uint32_t *)&s->k[1]) == w1 && *((volatile uint32_t *)&s->k[2]) == w2)
+                        break;
+                    h = (h + 1) & cc.small_mask;
                 }
-                // Same key: already there (the log holds duplicates of hot chunks). Words of a slot claimed in THIS launch
-                // may not be visible yet; then the duplicate takes a second slot -- harmless, both slots hold the same ids
-                // and a reader uses the first one it finds.
-                if ((cur & SMALL_KEY_MASK) == w3 && *((volatile uint32_t *)&s->k[0]) == w0 &&
-                    *((volatile uint32_t *)&s->k[1]) == w1 && *((volatile uint32_t *)&s->k[2]) == w2)
-                    break;
-                h = (h + 1) & cc.small_mask;
             }
-            continue;
+            if (!stub) continue;
         }
         if (*((volatile uint32_t *)cc.used) * 2 > cc.mask) continue; // half full: stop learning
         uint32_t h = cache_hash(k0, k1, k2, k3) & cc.mask;
@@ -283,13 +288,12 @@ struct EncSmemT {
     uint32_t park[PARK];
     uint32_t meta[TILE];       // per open chunk (index = its place on the open list): start in park (20 bits) | id count << 20
     uint16_t open_k[TILE];     // open list: chunk index within the tile
-    uint16_t mid[TILE];        // open chunks that may still be in a cache (beyond the SMALL home slot): open-list places
     uint16_t scan[TILE];       // open chunks nobody has seen before: the scan has to encode them
     uint32_t warp_scratch[THREADS / 32][32];
     uint32_t warp_sum[THREADS / 32];
     alignas(8) uint64_t bar_off, bar_tile; // mbarriers: boundaries landed (thread 0 only waits), tile ready (all wait)
     unsigned long long base;
-    uint32_t tile, a0, staged, n_open, n_mid, n_scan, n_scan2, park_used;
+    uint32_t tile, a0, staged, n_open, park_used;
     unsigned long long prof[ENC_PROF_N];
 };
 
@@ -440,114 +444,100 @@ __device__ __forceinline__ void scan_by_warp(const EncArgs &a, SM &sm, uint32_t 
     __syncwarp();
 }
 
-// The tile's open chunks, by all threads of the CTA (contains barriers). Kept out of line: its register needs (31-byte
-// keys, id arrays) must not be charged to the fast path, which runs for nine chunks in ten.
-//   round 1, at the same time: the first half of the warps looks the MID list up, one thread per entry -- special tokens
-//            by exact compare, the rest of the SMALL probe sequence (the fast path saw the home slot only), the BIG cache
-//            (key and value sectors of a slot in flight together); the second half scans the SCAN list, one warp per
-//            chunk (lanes = positions, one lookup latency per pass). Many scans (cold caches): one thread per chunk.
-//   round 2 (rare): MID entries that were in no cache are scanned.
-template <int THREADS, class SM>
-__device__ __noinline__ void resolve_open_chunks(const EncArgs &a, SM &sm, uint32_t a0, bool staged) {
-    constexpr int NW = THREADS / 32, HALF = NW / 2;
-    const uint32_t tid = threadIdx.x, warp = tid >> 5;
-    const uint32_t n_mid = sm.n_mid, n_scan = sm.n_scan;
-    const bool crowd = n_scan > ET_WARP_SCAN_MAX;
-    if (warp < HALF || crowd || n_scan == 0) {
-        const uint32_t first = (crowd || n_scan == 0) ? tid : tid, step = (crowd || n_scan == 0) ? THREADS : HALF * 32;
-        for (uint32_t i = first; i < n_mid; i += step) {
-            const uint32_t q = sm.mid[i], k = sm.open_k[q], so = sm.off[k], len = sm.off[k + 1] - so;
-            uint32_t ids[CACHE_MAX_LEN], n = 0;
-            const uint32_t sid = special_match(a.sp, len, [&](uint32_t b) { return tile_byte(a, sm, staged, a0, so + b); });
-            if (sid != ENC_NONE) {
-                ids[0] = sid;
-                n = 1;
-            } else if (a.cache.small && len <= CACHE_MAX_LEN) {
-                uint64_t key[4];
-                big_key(a, sm, staged, a0, so, len, key);
-                if (len <= SMALL_MAX_LEN) {
-                    const uint32_t w0 = (uint32_t)key[0], w1 = (uint32_t)(key[0] >> 32), w2 = (uint32_t)key[1];
-                    const uint32_t w3 = (uint32_t)(key[1] >> 32) | (len << 24);
-                    uint32_t h = small_hash(w0, w1, w2, w3) >> a.cache.small_shift;
-                    for (uint32_t probes = 0; probes < CACHE_MAX_PROBES; probes++) {
-                        uint4 kq, vv;
-                        ld_slot256(&a.cache.small[h], kq, vv);
-                        if (kq.w == 0) break;
-                        if ((kq.w & SMALL_KEY_MASK) == w3 && kq.x == w0 && kq.y == w1 && kq.z == w2) {
-                            n = kq.w >> 28;
-                            ids[0] = vv.x, ids[1] = vv.y, ids[2] = vv.z, ids[3] = vv.w;
-                            break;
-                        }
-                        h = (h + 1) & a.cache.small_mask;
-                    }
-                }
-                if (n == 0) {
-                    uint32_t h = cache_hash(key[0], key[1], key[2], key[3]) & a.cache.mask;
-                    for (uint32_t probes = 0; probes < CACHE_MAX_PROBES; probes++) {
-                        uint4 k0, k1, v0, v1; // the whole 64-byte slot: two 32-byte loads in flight together
-                        ld_slot256(&a.cache.slots[h], k0, k1);
-                        ld_slot256(reinterpret_cast<const uint8_t *>(&a.cache.slots[h]) + 32, v0, v1);
-                        if ((k1.z | k1.w) == 0) break; // k[3] == 0: empty
-                        if (k0.x == (uint32_t)key[0] && k0.y == (uint32_t)(key[0] >> 32) && k0.z == (uint32_t)key[1] &&
-                            k0.w == (uint32_t)(key[1] >> 32) && k1.x == (uint32_t)key[2] && k1.y == (uint32_t)(key[2] >> 32) &&
-                            k1.z == (uint32_t)key[3] && k1.w == (uint32_t)(key[3] >> 32)) {
-                            n = v0.x;
-                            if (n <= CACHE_INLINE_IDS) {
-                                ids[0] = v0.y, ids[1] = v0.z, ids[2] = v0.w, ids[3] = v1.x, ids[4] = v1.y, ids[5] = v1.z, ids[6] = v1.w;
-                            } else {
-                                const uint32_t *src = a.cache.arena + v0.y;
-                                for (uint32_t b = 0; b < n; b++) ids[b] = __ldg(&src[b]);
-                            }
-                            break;
-                        }
-                        h = (h + 1) & a.cache.mask;
-                    }
-                }
-            }
-            if (n == 0) { // in no cache: round 2
-                sm.scan[(uint32_t)SM::TILE - 1 - atomicAdd(&sm.n_scan2, 1u)] = (uint16_t)q;
-                continue;
-            }
-            sm.meta[q] = park_ids(sm, ids, n);
-        }
+// A chunk the fast path left open but that may well be cached -- 16..31 bytes (BIG cache), a short chunk whose home slot
+// in the SMALL cache holds somebody else (its probe sequence goes on) or a stub (more than 4 ids: BIG), a special token.
+// By the chunk's own thread, no barrier: the lanes that need it diverge for ~one L2 round trip (key and value sectors of
+// a BIG slot are fetched together). Out of line so that its registers are not charged to the fast path.
+// Returns the id count (0: in no cache -- the scan has to encode it); <= 4 ids come back in v, more are parked (v.x = start
+// in the parking area, PARK_NONE: no room).
+template <class SM>
+__device__ __noinline__ uint32_t resolve_cached(const EncArgs &a, SM &sm, uint32_t a0, bool staged, uint32_t o, uint32_t len, uint4 &v) {
+    const uint32_t sid = special_match(a.sp, len, [&](uint32_t i) { return tile_byte(a, sm, staged, a0, o + i); });
+    if (sid != ENC_NONE) {
+        v.x = sid;
+        return 1;
     }
-    if (crowd) {
+    if (!a.cache.small || len > CACHE_MAX_LEN) return 0;
+    uint64_t key[4];
+    big_key(a, sm, staged, a0, o, len, key);
+    if (len <= SMALL_MAX_LEN) {
+        const uint32_t w0 = (uint32_t)key[0], w1 = (uint32_t)(key[0] >> 32), w2 = (uint32_t)key[1];
+        const uint32_t w3 = (uint32_t)(key[1] >> 32) | (len << 24);
+        uint32_t h = small_hash(w0, w1, w2, w3) >> a.cache.small_shift;
+        bool stub = false;
+        for (uint32_t probes = 0; probes < CACHE_MAX_PROBES; probes++) {
+            uint4 kq, vv;
+            ld_slot256(&a.cache.small[h], kq, vv);
+            if (kq.w == 0) return 0; // not cached at all
+            if ((kq.w & SMALL_KEY_MASK) == w3 && kq.x == w0 && kq.y == w1 && kq.z == w2) {
+                if ((kq.w >> 28) <= SMALL_MAX_IDS) {
+                    v = vv;
+                    return kq.w >> 28;
+                }
+                stub = true;
+                break;
+            }
+            h = (h + 1) & a.cache.small_mask;
+        }
+        if (!stub) return 0;
+    }
+    uint32_t h = cache_hash(key[0], key[1], key[2], key[3]) & a.cache.mask;
+    for (uint32_t probes = 0; probes < CACHE_MAX_PROBES; probes++) {
+        uint4 k0, k1, v0, v1; // the whole 64-byte slot: two 32-byte loads in flight together
+        ld_slot256(&a.cache.slots[h], k0, k1);
+        ld_slot256(reinterpret_cast<const uint8_t *>(&a.cache.slots[h]) + 32, v0, v1);
+        if ((k1.z | k1.w) == 0) return 0; // k[3] == 0: empty
+        if (k0.x == (uint32_t)key[0] && k0.y == (uint32_t)(key[0] >> 32) && k0.z == (uint32_t)key[1] &&
+            k0.w == (uint32_t)(key[1] >> 32) && k1.x == (uint32_t)key[2] && k1.y == (uint32_t)(key[2] >> 32) &&
+            k1.z == (uint32_t)key[3] && k1.w == (uint32_t)(key[3] >> 32)) {
+            const uint32_t n = v0.x;
+            if (n <= 4) {
+                v = make_uint4(v0.y, v0.z, v0.w, v1.x);
+                return n;
+            }
+            const uint32_t at = atomicAdd(&sm.park_used, n);
+            v.x = PARK_NONE;
+            if (at + n <= (uint32_t)SM::PARK) {
+                v.x = at;
+                if (n <= CACHE_INLINE_IDS) {
+                    const uint32_t ids[CACHE_INLINE_IDS] = {v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                    for (uint32_t i = 0; i < n; i++) sm.park[at + i] = ids[i];
+                } else {
+                    const uint32_t *src = a.cache.arena + v0.y;
+                    for (uint32_t i = 0; i < n; i++) sm.park[at + i] = __ldg(&src[i]);
+                }
+            }
+            return n;
+        }
+        h = (h + 1) & a.cache.mask;
+    }
+    return 0;
+}
+
+// The chunks nobody has seen before (the tile's scan list), by all threads of the CTA; the caller's barrier follows.
+// Few (warm caches): latency matters -- one WARP per chunk, lanes = positions, one lookup latency per pass. Many (cold
+// caches): throughput matters -- one THREAD per chunk; also for chunks of 33..64 bytes.
+template <int THREADS, class SM>
+__device__ __noinline__ void scan_open_chunks(const EncArgs &a, SM &sm, uint32_t a0, bool staged, uint32_t n_scan) {
+    constexpr int NW = THREADS / 32;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) atomicAdd(a.miss_count, n_scan);
+    if (n_scan > ET_WARP_SCAN_MAX) {
         for (uint32_t s = tid; s < n_scan; s += THREADS) {
             const uint32_t q = sm.scan[s], k = sm.open_k[q], so = sm.off[k];
             sm.meta[q] = scan_serial(a, sm, a0, staged, so, sm.off[k + 1] - so);
         }
-    } else if (warp >= HALF) {
-        for (uint32_t s = warp - HALF; s < n_scan; s += NW - HALF) {
-            const uint32_t q = sm.scan[s], k = sm.open_k[q];
-            if (sm.off[k + 1] - sm.off[k] > 32) { // 33..64 bytes do not fit the lanes
-                if ((tid & 31) == 0) sm.meta[q] = scan_serial(a, sm, a0, staged, sm.off[k], sm.off[k + 1] - sm.off[k]);
-                __syncwarp();
-                continue;
-            }
-            scan_by_warp(a, sm, a0, staged, q, sm.warp_scratch[warp]);
-        }
+        return;
     }
-    __syncthreads();
-    const uint32_t n2 = sm.n_scan2;
-    if (tid == 0 && (n_scan + n2)) atomicAdd(a.miss_count, n_scan + n2);
-    if (n2 == 0) return;
-    if (n2 > ET_WARP_SCAN_MAX) {
-        for (uint32_t s = tid; s < n2; s += THREADS) {
-            const uint32_t q = sm.scan[(uint32_t)SM::TILE - 1 - s], k = sm.open_k[q], so = sm.off[k];
-            sm.meta[q] = scan_serial(a, sm, a0, staged, so, sm.off[k + 1] - so);
+    for (uint32_t s = warp; s < n_scan; s += NW) {
+        const uint32_t q = sm.scan[s], k = sm.open_k[q];
+        if (sm.off[k + 1] - sm.off[k] > 32) { // 33..64 bytes do not fit the lanes
+            if ((tid & 31) == 0) sm.meta[q] = scan_serial(a, sm, a0, staged, sm.off[k], sm.off[k + 1] - sm.off[k]);
+            __syncwarp();
+            continue;
         }
-    } else {
-        for (uint32_t s = warp; s < n2; s += NW) {
-            const uint32_t q = sm.scan[(uint32_t)SM::TILE - 1 - s], k = sm.open_k[q];
-            if (sm.off[k + 1] - sm.off[k] > 32) {
-                if ((tid & 31) == 0) sm.meta[q] = scan_serial(a, sm, a0, staged, sm.off[k], sm.off[k + 1] - sm.off[k]);
-                __syncwarp();
-                continue;
-            }
-            scan_by_warp(a, sm, a0, staged, q, sm.warp_scratch[warp]);
-        }
+        scan_by_warp(a, sm, a0, staged, q, sm.warp_scratch[warp]);
     }
-    __syncthreads();
 }
 
 // ids of an open chunk that did not fit the parking area: encode it again, straight into place (rare)
@@ -581,11 +571,15 @@ __device__ __forceinline__ void emit_chunk(const EncArgs &a, SM &sm, uint32_t a0
     if (openq == TILE_NONE) {
         if (o1 - o0 > ENC_SHORT_MAX) {
             for (uint32_t i = 0; i < n; i++) dst[i] = a.scratch_a[o0 + i];
-        } else {
+        } else if (n <= 4) {
             dst[0] = v.x;
             if (n > 1) dst[1] = v.y;
             if (n > 2) dst[2] = v.z;
             if (n > 3) dst[3] = v.w;
+        } else if (v.x != PARK_NONE) { // a cached chunk with more than 4 ids: parked by resolve_cached
+            for (uint32_t i = 0; i < n; i++) dst[i] = sm.park[v.x + i];
+        } else {
+            rescan_into(a, sm, a0, staged, o0, o1 - o0, dst, n);
         }
     } else {
         const uint32_t start = sm.meta[openq] & 0xFFFFF;
@@ -653,7 +647,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
         mbar_init(&sm.bar_off, 1);
         mbar_init(&sm.bar_tile, 1);
         mbar_init_fence();
-        sm.n_open = sm.n_mid = sm.n_scan = sm.n_scan2 = sm.park_used = 0;
+        sm.n_open = sm.park_used = 0;
         for (int i = 0; i < ENC_PROF_N; i++) sm.prof[i] = 0;
     }
     __syncthreads();
@@ -678,7 +672,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
             if (tid == 0) {
                 const uint32_t t = atomicAdd(a.ticket, 1u);
                 sm.tile = t < a.n_tiles ? t : TILE_NONE;
-                sm.n_open = sm.n_mid = sm.n_scan = sm.n_scan2 = sm.park_used = 0;
+                sm.n_open = sm.park_used = 0;
             }
             __syncthreads();
         }
@@ -738,8 +732,9 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
                 const uint32_t len = o[j + 1] - o[j];
                 const bool small = len - 1u < SMALL_MAX_LEN;
                 const bool hit = small && (kq[j].w & SMALL_KEY_MASK) == kw[j].w && kq[j].x == kw[j].x && kq[j].y == kw[j].y && kq[j].z == kw[j].z;
-                cnt[j] = hit ? kq[j].w >> 28 : 0u;
-                openq[j] = hit ? TILE_NONE : 0u; // 0: undecided, see below
+                const bool final = hit && (kq[j].w >> 28) <= SMALL_MAX_IDS; // (a stub is a hit that only says "BIG has it")
+                cnt[j] = final ? kq[j].w >> 28 : 0u;
+                openq[j] = final ? TILE_NONE : 0u; // 0: undecided, see below
                 if (small && kq[j].w != 0) home_taken |= 1u << j;
             }
         } else {
@@ -771,21 +766,31 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
                 vq[j] = make_uint4(o[j], len, 0, 0);
                 continue;
             }
-            const uint32_t q = atomicAdd(&sm.n_open, 1u);
-            sm.open_k[q] = (uint16_t)k;
-            openq[j] = q;
             // may it still be in a cache? a special token; a chunk of 16..31 bytes (BIG); a short one whose home slot holds
-            // somebody else (its probe sequence continues; or it has more than 4 ids and lives in BIG)
+            // somebody else (its probe sequence continues) or a stub. Its own thread looks, no barrier (resolve_cached).
             const bool maybe_cached = a.cache.small != nullptr && len <= CACHE_MAX_LEN && (len > SMALL_MAX_LEN || ((home_taken >> j) & 1u));
-            if (maybe_cached || (a.sp.n && ((a.sp.len_mask >> (len < 63u ? len : 63u)) & 1ull)))
-                sm.mid[atomicAdd(&sm.n_mid, 1u)] = (uint16_t)q;
-            else
-                sm.scan[atomicAdd(&sm.n_scan, 1u)] = (uint16_t)q;
+            if (maybe_cached || (a.sp.n && ((a.sp.len_mask >> (len < 63u ? len : 63u)) & 1ull))) {
+                const uint32_t n = resolve_cached(a, sm, a0, staged, o[j], len, vq[j]);
+                if (n) {
+                    cnt[j] = n;
+                    continue;
+                }
+            }
+            const uint32_t q = atomicAdd(&sm.n_open, 1u); // nobody has seen it before: the scan list
+            sm.open_k[q] = (uint16_t)k;
+            sm.scan[q] = (uint16_t)q;
+            openq[j] = q;
         }
         __syncthreads();
         lap(1);
-        // ---- 2. open chunks ----------------------------------------------------------------------------------------------
-        if (sm.n_open) resolve_open_chunks<THREADS>(a, sm, a0, staged);
+        // ---- 2. chunks nobody has seen before ----------------------------------------------------------------------------
+        {
+            const uint32_t n_scan = sm.n_open;
+            if (n_scan) {
+                scan_open_chunks<THREADS>(a, sm, a0, staged, n_scan);
+                __syncthreads();
+            }
+        }
         lap(2);
         uint32_t sum = 0;
 #pragma unroll
@@ -840,7 +845,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
         }
         // ---- 4. the next tile's loads start now; this tile's ids leave as whole lines --------------------------------
         if (bulk && tid == 0) {
-            sm.n_open = sm.n_mid = sm.n_scan = sm.n_scan2 = sm.park_used = 0; // (the next tile's appends come after the next mbarrier wait)
+            sm.n_open = sm.park_used = 0; // (the next tile's appends come after the next mbarrier wait)
             fetch_tile_bulk(a, sm, off_parity, policy);
         }
         lap(5);

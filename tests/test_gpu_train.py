@@ -204,3 +204,24 @@ def test_config3_shape_256mib_32k_vocab_vs_oracle(pkg, oracle, mode):
     om, oc = oracle.train(tok, off, w, 32768, mode)
     m, c, st = pkg.train(tok, off, w, 32768, mode)
     assert m.shape == om.shape and (m == om).all() and (c == oc).all(), st
+
+
+def test_full_32k_vocab_model_equals_the_reference_on_a_16mib_slice(pkg, tmp_path):
+    """the un-extrapolated comparison. The compiled reference trained the first 16 MiB (cut at a regex-safe
+    point) of the synthetic corpus to the FULL 32768 vocabulary once (44.5 min of one CPU core, profiles/reference_full_16MiB.json);
+    its .model is a golden. Tokenizer::train on the same slice must write the same file, byte for byte."""
+    import re
+    text = pkg.synth_corpus(0x5EED0001, 16 << 20).tobytes()
+    lo = len(text) - 65536
+    last = None
+    for m in re.finditer(rb"\n[\x21-\x7e]", text[lo:]):
+        last = m
+    text = text[:lo + last.start() + 1]
+    assert len(text) == 16777011 and hashlib.sha256(text).hexdigest() == "abf7b4e4880ca7f70bac62d1b0755a313fd0da49adc4a01323cc2c05c223889f"
+    tk = pkg.Tokenizer(pkg.patterns()["gpt4"])
+    tk.train(text, 32768, "lexical")
+    out = tmp_path / "m.model"
+    tk.save(out)
+    golden = open(os.path.join(GOLDEN, "models", "synth16m_gpt4_lexical_32768.model"), "rb").read()
+    assert hashlib.sha256(golden).hexdigest() == "38103cba13ea420b7077d1baa80125551fa7cbb03d5d5566c5ddf39087a64119"
+    assert out.read_bytes() == golden
