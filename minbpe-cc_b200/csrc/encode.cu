@@ -318,9 +318,10 @@ struct mbpe_encoder {
     uint32_t n_esp = 0;
     unsigned long long esp_len_mask = 0;
     // scratch (grown on demand)
-    unsigned long long *d_status = nullptr;
+    unsigned long long *d_status = nullptr; // encode: place of every tile of a launch (k_tile_scan); decode: look-back words
+    uint32_t *d_tile_total = nullptr;       // encode: ids of every tile of a launch (pass 1)
     uint64_t status_cap = 0;
-    uint32_t *d_small = nullptr; // [0] ticket, [1] n_long, [2] overflow, [3] scanned chunks
+    uint32_t *d_small = nullptr; // [0] ticket (decode), [1] n_long, [2] overflow, [3] scanned chunks
     unsigned long long *d_prof = nullptr; // MBPE_DEBUG: cycles per phase of k_encode_tiles (ENC_PROF_*)
     unsigned long long *d_n_out = nullptr;
     uint32_t *d_long_list = nullptr;
@@ -352,10 +353,11 @@ struct mbpe_encoder {
 namespace mbpe {
 struct EncConfig {
     int threads, cpt, ctas;
-    void (*kernel)(const EncArgs);
+    void (*count)(const EncArgs); // pass 1
+    void (*write)(const EncArgs); // pass 2
     size_t smem;
 };
-#define ENC_CFG(T, C, M) EncConfig{T, C, M, k_encode_tiles<T, C, M>, sizeof(EncSmemT<T, C>)}
+#define ENC_CFG(T, C, M) EncConfig{T, C, M, k_encode_tiles<T, C, M, 1>, k_encode_tiles<T, C, M, 2>, sizeof(EncSmemT<T, C>)}
 // (threads, chunks per thread, CTAs per SM); 0 = default, the others for A/B runs (MBPE_ENC_CFG)
 static const EncConfig enc_configs[] = {ENC_CFG(256, 4, 3), ENC_CFG(256, 4, 4), ENC_CFG(512, 4, 2), ENC_CFG(512, 2, 3),
                                         ENC_CFG(256, 8, 2), ENC_CFG(512, 4, 1), ENC_CFG(256, 2, 6), ENC_CFG(128, 4, 6)};
@@ -483,8 +485,10 @@ static int encoder_create_impl(mbpe_encoder *e, const uint32_t *merges, uint32_t
     }
     const char *cfg_env = getenv("MBPE_ENC_CFG");
     e->cfg = cfg_env && *cfg_env ? std::min(std::max(atoi(cfg_env), 0), N_ENC_CONFIGS - 1) : 0;
-    for (int i = 0; i < N_ENC_CONFIGS; i++)
-        MB_CUDA(cudaFuncSetAttribute(enc_configs[i].kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_configs[i].smem));
+    for (int i = 0; i < N_ENC_CONFIGS; i++) {
+        MB_CUDA(cudaFuncSetAttribute(enc_configs[i].count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_configs[i].smem));
+        MB_CUDA(cudaFuncSetAttribute(enc_configs[i].write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_configs[i].smem));
+    }
     return MBPE_OK;
 }
 
@@ -522,7 +526,7 @@ extern "C" void mbpe_encoder_destroy(mbpe_encoder *e) {
     cudaSetDevice(e->device);
     void *ps[] = {e->d_slots, e->d_voff, e->d_vbytes, e->d_vpack, e->d_sp_ids, e->d_sp_off, e->d_sp_bytes, e->d_status, e->d_small,
                   e->d_n_out, e->d_long_list, e->d_scratch_a, e->d_scratch_b, e->d_cache, e->d_cache_small, e->d_cache_log,
-                  e->d_cache_ctr, e->d_cache_arena, e->d_esp_ids, e->d_esp_off, e->d_esp_bytes, e->d_prof};
+                  e->d_cache_ctr, e->d_cache_arena, e->d_esp_ids, e->d_esp_off, e->d_esp_bytes, e->d_prof, e->d_tile_total};
     for (void *p : ps) cudaFree(p);
     free_host_pipe(e);
     if (e->pipe_stream) cudaStreamDestroy(e->pipe_stream);
@@ -632,10 +636,13 @@ extern "C" int mbpe_encoder_seed_special_chunks(mbpe_encoder *e, const uint32_t 
 static int ensure_status(mbpe_encoder *e, uint64_t n_tiles) {
     if (n_tiles > e->status_cap) {
         cudaFree(e->d_status);
+        cudaFree(e->d_tile_total);
         e->d_status = nullptr;
+        e->d_tile_total = nullptr;
         e->status_cap = 0;
         const uint64_t cap = n_tiles + n_tiles / 4 + 64;
         MB_CUDA(cudaMalloc(&e->d_status, cap * 8));
+        MB_CUDA(cudaMalloc(&e->d_tile_total, cap * 4));
         e->status_cap = cap;
     }
     return MBPE_OK;
@@ -681,10 +688,9 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
     a.out = d_out;
     a.out_cap = out_cap;
     a.d_n_out = (unsigned long long *)d_n_out;
-    a.stream_base = (const unsigned long long *)d_n_out;
     a.out_off = d_out_off;
-    a.status = e->d_status;
-    a.ticket = e->d_small;
+    a.tile_total = e->d_tile_total;
+    a.tile_base = e->d_status;
     a.long_list = e->d_long_list;
     a.n_long = e->d_small + 1;
     a.long_cap = (uint32_t)e->long_cap;
@@ -718,8 +724,6 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
             if (!e->sub_batch_chunks) sb = std::min<uint64_t>(ENC_MAX_SUBBATCH, sb * 2);
             const uint64_t n_tiles = (a.chunk1 - a.chunk0 + ET_CHUNKS - 1) / ET_CHUNKS;
             a.n_tiles = (uint32_t)n_tiles;
-            MB_CUDA(cudaMemsetAsync(e->d_status, 0, n_tiles * 8, st));
-            MB_CUDA(cudaMemsetAsync(e->d_small, 0, 4, st)); // ticket
             if (a.cache.small) {
                 k_cache_reset_log<<<1, 1, 0, st>>>(a.cache);
                 e->launches++;
@@ -734,7 +738,7 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
             lc.attrs = lattr;
             lc.numAttrs = 0;
             if (a.cache.small && e->l2_window_max) {
-                // the text, boundaries and ids stream through L2 once; the randomly probed SMALL cache is what should stay
+                // the text, boundaries and ids stream through L2; the randomly probed SMALL cache is what should stay
                 const size_t bytes = std::min((size_t)e->small_slots * sizeof(SmallSlot), e->l2_window_max);
                 lattr[0].id = cudaLaunchAttributeAccessPolicyWindow;
                 lattr[0].val.accessPolicyWindow.base_ptr = e->d_cache_small;
@@ -744,12 +748,16 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
                 lattr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
                 lc.numAttrs = 1;
             }
-            MB_CUDA(cudaLaunchKernelEx(&lc, kc.kernel, a));
+            // pass 1: id count of every tile; what it had to scan goes into the caches; pass 2 writes at the scanned places
+            MB_CUDA(cudaLaunchKernelEx(&lc, kc.count, a));
             e->launches++;
             if (a.cache.small) {
                 k_cache_insert<<<e->sms * 2, 256, 0, st>>>(a.cache);
                 e->launches++;
             }
+            k_tile_scan<<<1, 1024, 0, st>>>(e->d_tile_total, a.n_tiles, e->d_status, (unsigned long long *)d_n_out);
+            MB_CUDA(cudaLaunchKernelEx(&lc, kc.write, a));
+            e->launches += 2;
         }
         MB_CUDA(cudaGetLastError());
         MB_CUDA(cudaMemcpyAsync(small, e->d_small, 16, cudaMemcpyDeviceToHost, st));

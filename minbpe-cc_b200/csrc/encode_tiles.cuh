@@ -3,20 +3,30 @@
 // Replaces internal_internal_encode / internal_encode + flatten (Tokenizer.h:325-377, :714-717) for chunks of up to
 // ENC_SHORT_MAX bytes; longer chunks are encoded by k_encode_long into a scratch stream and spliced in here.
 //
+// The flat id stream needs every tile's place = the number of ids before it. Round 1 (and the first versions of round 2)
+// resolved that inside ONE pass by decoupled look-back; measured per tile (thread 0's clock, 1024 chunks): ~40 k cycles,
+// of which ~13 k waiting in the look-back for the predecessors' counts (their arrival times jitter by the whole chain of
+// ticket -> boundaries -> text -> probes) and ~7 k in that fetch chain, which cannot be prefetched because tiles must
+// START in ticket order. So the stream is produced in TWO passes that have no dependency between tiles at all:
+//   pass 1 (count)  every tile: probes, open chunks -> the tile's id count                      -> tile_total[t]
+//   k_tile_scan     exclusive scan of tile_total (+ the ids of earlier launches)                -> tile_base[t]
+//   pass 2 (write)  every tile: probes again (the slots are hot in L2), ids gathered in shared memory, stored at
+//                   tile_base[t] as whole lines.
+// With nothing to wait for, tiles are dealt statically (tile = CTA index + k x grid) and the NEXT tile's boundaries and
+// text arrive by bulk asynchronous copy (cp.async.bulk -> the TMA engine, completion on mbarriers, double buffered) while
+// the current one is processed. The text and the boundaries are read twice (2 x 1.8 B per text byte against 4.4 B of
+// ids: +25 % traffic); chunks pass 1 had to scan are in the caches before pass 2 (k_cache_insert runs in between).
+//
 // One tile = THREADS x CPT consecutive chunks, one CTA:
-//   0. thread 0 takes the tile ticket and brings the tile's boundaries and its text window into shared memory with
-//      two bulk asynchronous copies (cp.async.bulk -> the TMA engine, completion on an mbarrier): no registers, no
-//      per-thread load/store instructions. It does so while the other warps are still storing the previous tile.
 //   1. fast path, every thread CPT chunks: chunks of <= 15 bytes (nine in ten) are looked up in the SMALL chunk cache,
-//      "chunk bytes -> ids" in 32-byte slots = one DRAM sector: two independent 16-byte loads per probe, all probes
-//      of a thread in flight together. Everything else goes on the tile's slow list.
-//   2. slow list: special tokens by exact compare, 16..31-byte chunks and chunks with more than 4 ids through the BIG
-//      chunk cache (64-byte slots), the rest by the multi-pass scan itself (one warp per chunk when few, one thread per
-//      chunk when many); scanned chunks are appended to a log that k_cache_insert folds into the caches between launches.
-//   3. block scan of the id counts; warp 0 resolves the tile's place in the flat stream by decoupled look-back (128
-//      predecessors per round trip) while the other warps gather the tile's ids in shared memory; the ids leave as
-//      whole lines.
-// Results never depend on the caches: a miss is scanned, and special tokens are matched in the slow path itself.
+//      "chunk bytes -> ids" in 32-byte slots = one DRAM sector, fetched by ONE 256-bit load (LDG.E.256) per probe, all
+//      probes of a thread in flight together.
+//   2. what that leaves open: chunks that may be cached elsewhere (16..31 bytes or more than 4 ids: BIG cache, 64-byte
+//      slots; a taken home slot: the probe sequence goes on) are resolved by their own thread, no barrier; chunks nobody
+//      has seen go to the tile's scan list: the multi-pass scan itself, one warp per chunk when few, one thread per chunk
+//      when many; pass 1 appends them to a log that k_cache_insert folds into the caches.
+//   3. pass 1: block sum. pass 2: block scan, gather, 16-byte stores.
+// Results never depend on the caches: a miss is scanned, and special tokens are matched in the open-chunk path itself.
 #pragma once
 #include "lookback.cuh"
 
@@ -249,8 +259,8 @@ struct EncArgs {
     uint64_t out_cap;
     unsigned long long *d_n_out;
     unsigned long long *out_off; // optional per-chunk token offsets (n_chunks + 1)
-    unsigned long long *status;  // look-back words, one per tile, zeroed
-    uint32_t *ticket;            // zeroed
+    uint32_t *tile_total;        // pass 1 out: ids of every tile of this launch
+    const unsigned long long *tile_base; // pass 2 in: place of every tile in the stream (k_tile_scan)
     uint32_t n_tiles;
     const uint32_t *scratch_a;   // long-chunk tokens / counts; null = no long pre-pass was run (optimistic launch)
     const uint32_t *scratch_b;
@@ -262,15 +272,14 @@ struct EncArgs {
     uint32_t bulk;               // bytes / off are 16-byte aligned: stage with cp.async.bulk
     uint32_t out_aligned;        // out is 16-byte aligned: ids leave as 16-byte stores
     unsigned long long *prof;    // optional: SM cycles per phase summed over CTAs (thread 0's clock), see ENC_PROF_*
-    uint32_t ablate;             // MBPE_ENC_ABLATE (profiling only; 1, 2, 4 give WRONG results): 1 no look-back wait,
-                                 // 2 no cache probe (every short chunk "hits" with two fake ids), 4 no id stores,
-                                 // 8 slow-list entries are not resolved (one fake id each)
+    uint32_t ablate;             // MBPE_ENC_ABLATE (profiling only, WRONG results): 2 no cache probe (every short chunk
+                                 // "hits" with two fake ids), 4 no id stores, 8 open chunks are not resolved (one fake id)
 };
 
-// EncArgs::prof[i]: cycles thread 0 spent ... 0 waiting for the tile's data, 1 fast path (+ barrier), 2 slow list,
-// 3 count scan (+ barrier), 4 look-back / gather (+ barrier), 5 fetching the next tile (ticket + two bulk copies),
-// 6 storing the ids, 7 tiles processed
-constexpr int ENC_PROF_N = 8;
+// EncArgs::prof[pass * 8 + i]: cycles thread 0 spent ... 0 waiting for the tile's data, 1 cache probes + cached open chunks
+// (+ barrier), 2 scan list, 3 block sum / scan (+ barrier), 4 gather (+ barrier), 5 issuing the prefetch, 6 storing the
+// ids, 7 tiles processed
+constexpr int ENC_PROF_N = 16;
 constexpr uint32_t TILE_NONE = 0xFFFFFFFFu;
 constexpr uint64_t ENC_MAX_SUBBATCH = 1ull << 26; // chunks per launch at most (tile ids and look-back words are 32-bit safe)
 constexpr uint32_t PARK_NONE = 0xFFFFF;       // (20 bits) the ids of an open chunk did not fit the parking area
@@ -281,20 +290,20 @@ struct EncSmemT {
     static constexpr int TILE = THREADS * CPT;
     static constexpr int TEXT_CAP = TILE * 10;  // staged text bytes per tile (average chunk ~5 bytes); wider tiles read HBM
     static constexpr int STAGE = TILE * 5 / 2;  // ids gathered per tile (average ~2.1 per chunk); more: direct stores
-    static constexpr int PARK = TILE;           // ids of open chunks parked until the tile knows its place
-    alignas(128) uint32_t off[TILE + 8];
-    alignas(128) uint32_t text[TEXT_CAP / 4 + 16]; // + halo: key assembly reads whole words past the chunk's end
+    static constexpr int PARK = TILE / 2;       // ids of open chunks parked until they are written
+    alignas(128) uint32_t off_buf[2][TILE + 8];          // double buffered: the next tile's data arrives during this tile
+    alignas(128) uint32_t text_buf[2][TEXT_CAP / 4 + 16]; // + halo: key assembly reads whole words past the chunk's end
     alignas(16) uint32_t stage[STAGE + 4];
     uint32_t park[PARK];
     uint32_t meta[TILE];       // per open chunk (index = its place on the open list): start in park (20 bits) | id count << 20
-    uint16_t open_k[TILE];     // open list: chunk index within the tile
-    uint16_t scan[TILE];       // open chunks nobody has seen before: the scan has to encode them
+    uint16_t open_k[TILE];     // open list (chunks nobody has seen before): chunk index within the tile
     uint32_t warp_scratch[THREADS / 32][32];
     uint32_t warp_sum[THREADS / 32];
-    alignas(8) uint64_t bar_off, bar_tile; // mbarriers: boundaries landed (thread 0 only waits), tile ready (all wait)
-    unsigned long long base;
-    uint32_t tile, a0, staged, n_open, park_used;
-    unsigned long long prof[ENC_PROF_N];
+    alignas(8) uint64_t bar_off[2], bar_txt[2]; // mbarriers per buffer: boundaries landed (thread 0 waits), text landed (all wait)
+    const uint32_t *off;       // the current tile's buffers
+    const uint32_t *text;
+    uint32_t a0[2], staged[2], n_open, park_used;
+    unsigned long long prof[8];
 };
 
 template <class SM>
@@ -386,7 +395,7 @@ __device__ __forceinline__ uint32_t park_ids(SM &sm, const uint32_t *ids, uint32
 
 // the multi-pass scan of one chunk (<= ENC_SHORT_MAX bytes) by ONE thread (special tokens first); returns meta
 template <class SM>
-__device__ __forceinline__ uint32_t scan_serial(const EncArgs &a, SM &sm, uint32_t a0, bool staged, uint32_t o, uint32_t len) {
+__device__ __forceinline__ uint32_t scan_serial(const EncArgs &a, SM &sm, uint32_t a0, bool staged, uint32_t o, uint32_t len, bool log) {
     uint32_t t[ENC_SHORT_MAX];
     const uint32_t sid = special_match(a.sp, len, [&](uint32_t i) { return tile_byte(a, sm, staged, a0, o + i); });
     if (sid != ENC_NONE) {
@@ -397,13 +406,13 @@ __device__ __forceinline__ uint32_t scan_serial(const EncArgs &a, SM &sm, uint32
     uint32_t n = len;
     bool merged = true;
     while (merged && n >= 2) n = enc_pass(a.tab, t, n, merged);
-    log_scanned(a, sm, staged, a0, o, len, t, n);
+    if (log) log_scanned(a, sm, staged, a0, o, len, t, n);
     return park_ids(sm, t, n);
 }
 
 // one warp encodes the open chunk at open-list place q (<= 32 bytes) and parks its ids
 template <class SM>
-__device__ __forceinline__ void scan_by_warp(const EncArgs &a, SM &sm, uint32_t a0, bool staged, uint32_t q, uint32_t *scratch) {
+__device__ __forceinline__ void scan_by_warp(const EncArgs &a, SM &sm, uint32_t a0, bool staged, uint32_t q, uint32_t *scratch, bool log) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t k = sm.open_k[q], so = sm.off[k], mlen = sm.off[k + 1] - so;
     uint32_t sid = ENC_NONE;
@@ -423,7 +432,7 @@ __device__ __forceinline__ void scan_by_warp(const EncArgs &a, SM &sm, uint32_t 
         start = PARK_NONE;
     }
     if (lane == 0) sm.meta[q] = start | (mn << 20);
-    if (a.cache.small && mlen <= CACHE_MAX_LEN && sid == ENC_NONE) { // teach the caches
+    if (log && a.cache.small && mlen <= CACHE_MAX_LEN && sid == ENC_NONE) { // teach the caches
         uint32_t li = 0;
         if (lane == 0) li = atomicAdd(a.cache.log_count, 1u);
         li = __shfl_sync(0xffffffffu, li, 0);
@@ -518,25 +527,25 @@ __device__ __noinline__ uint32_t resolve_cached(const EncArgs &a, SM &sm, uint32
 // Few (warm caches): latency matters -- one WARP per chunk, lanes = positions, one lookup latency per pass. Many (cold
 // caches): throughput matters -- one THREAD per chunk; also for chunks of 33..64 bytes.
 template <int THREADS, class SM>
-__device__ __noinline__ void scan_open_chunks(const EncArgs &a, SM &sm, uint32_t a0, bool staged, uint32_t n_scan) {
+__device__ __noinline__ void scan_open_chunks(const EncArgs &a, SM &sm, uint32_t a0, bool staged, uint32_t n_scan, bool log) {
     constexpr int NW = THREADS / 32;
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
-    if (tid == 0) atomicAdd(a.miss_count, n_scan);
+    if (tid == 0 && log) atomicAdd(a.miss_count, n_scan);
     if (n_scan > ET_WARP_SCAN_MAX) {
         for (uint32_t s = tid; s < n_scan; s += THREADS) {
-            const uint32_t q = sm.scan[s], k = sm.open_k[q], so = sm.off[k];
-            sm.meta[q] = scan_serial(a, sm, a0, staged, so, sm.off[k + 1] - so);
+            const uint32_t q = s, k = sm.open_k[q], so = sm.off[k];
+            sm.meta[q] = scan_serial(a, sm, a0, staged, so, sm.off[k + 1] - so, log);
         }
         return;
     }
     for (uint32_t s = warp; s < n_scan; s += NW) {
-        const uint32_t q = sm.scan[s], k = sm.open_k[q];
+        const uint32_t q = s, k = sm.open_k[q];
         if (sm.off[k + 1] - sm.off[k] > 32) { // 33..64 bytes do not fit the lanes
-            if ((tid & 31) == 0) sm.meta[q] = scan_serial(a, sm, a0, staged, sm.off[k], sm.off[k + 1] - sm.off[k]);
+            if ((tid & 31) == 0) sm.meta[q] = scan_serial(a, sm, a0, staged, sm.off[k], sm.off[k + 1] - sm.off[k], log);
             __syncwarp();
             continue;
         }
-        scan_by_warp(a, sm, a0, staged, q, sm.warp_scratch[warp]);
+        scan_by_warp(a, sm, a0, staged, q, sm.warp_scratch[warp], log);
     }
 }
 
@@ -591,64 +600,63 @@ __device__ __forceinline__ void emit_chunk(const EncArgs &a, SM &sm, uint32_t a0
     }
 }
 
-// thread 0: ticket, then the tile's boundaries and text window into shared memory by bulk copies.
-// Publishes sm.tile / sm.a0 / sm.staged and completes sm.bar_tile when everything has landed.
+// thread 0, first half of a tile fetch: the tile's boundaries on their way into off_buf[buf]
 template <class SM>
-__device__ __forceinline__ void fetch_tile_bulk(const EncArgs &a, SM &sm, uint32_t &off_parity, uint64_t policy) {
-    const uint32_t t = atomicAdd(a.ticket, 1u); // tiles start in order: look-back cannot deadlock
-    if (t >= a.n_tiles) {
-        sm.tile = TILE_NONE;
-        mbar_arrive(&sm.bar_tile);
-        return;
-    }
-    const uint64_t c0 = a.chunk0 + (uint64_t)t * SM::TILE;
+__device__ __forceinline__ void fetch_off(const EncArgs &a, SM &sm, uint32_t tile, uint32_t buf, uint64_t policy) {
+    const uint64_t c0 = a.chunk0 + (uint64_t)tile * SM::TILE;
     const uint32_t nc = (uint32_t)min((uint64_t)SM::TILE, a.chunk1 - c0);
     const uint32_t nw = nc + 1, nb = nw & ~3u; // whole 16-byte vectors by bulk copy, the last <= 3 words by hand
     if (nb) {
-        mbar_arrive_expect_tx(&sm.bar_off, nb * 4);
-        bulk_g2s(sm.off, a.off + c0, nb * 4, &sm.bar_off, policy);
+        mbar_arrive_expect_tx(&sm.bar_off[buf], nb * 4);
+        bulk_g2s(sm.off_buf[buf], a.off + c0, nb * 4, &sm.bar_off[buf], policy);
     } else {
-        mbar_arrive(&sm.bar_off);
+        mbar_arrive(&sm.bar_off[buf]);
     }
-    for (uint32_t i = nb; i < nw; i++) sm.off[i] = __ldg(&a.off[c0 + i]);
-    mbar_wait(&sm.bar_off, off_parity);
-    off_parity ^= 1;
-    const uint32_t b0 = sm.off[0], b1 = sm.off[nc];
+    for (uint32_t i = nb; i < nw; i++) sm.off_buf[buf][i] = __ldg(&a.off[c0 + i]);
+}
+// second half, once the boundaries have landed: the text window into text_buf[buf]; completes bar_txt[buf]
+template <class SM>
+__device__ __forceinline__ void fetch_text(const EncArgs &a, SM &sm, uint32_t tile, uint32_t buf, uint32_t off_parity, uint64_t policy) {
+    mbar_wait(&sm.bar_off[buf], off_parity);
+    const uint64_t c0 = a.chunk0 + (uint64_t)tile * SM::TILE;
+    const uint32_t nc = (uint32_t)min((uint64_t)SM::TILE, a.chunk1 - c0);
+    const uint32_t b0 = sm.off_buf[buf][0], b1 = sm.off_buf[buf][nc];
     const uint32_t a0 = b0 & ~15u; // 16-byte aligned window start
     const uint32_t span = b1 - a0;
     const bool staged = span <= (uint32_t)SM::TEXT_CAP;
-    sm.tile = t;
-    sm.a0 = a0;
-    sm.staged = staged;
+    sm.a0[buf] = a0;
+    sm.staged[buf] = staged;
     if (staged) {
         // whole vectors that lie inside the buffer by bulk copy, the last (< 16) bytes of the buffer by hand
         const uint64_t avail = (a.n_bytes_total - a0) & ~15ull;
         const uint32_t full = (uint32_t)min((uint64_t)((span + 15) & ~15u), avail);
-        for (uint32_t g = a0 + full; g < b1; g++) reinterpret_cast<uint8_t *>(sm.text)[g - a0] = __ldg(&a.bytes[g]);
+        for (uint32_t g = a0 + full; g < b1; g++) reinterpret_cast<uint8_t *>(sm.text_buf[buf])[g - a0] = __ldg(&a.bytes[g]);
         if (full) {
-            mbar_arrive_expect_tx(&sm.bar_tile, full);
-            bulk_g2s(sm.text, a.bytes + a0, full, &sm.bar_tile, policy);
+            mbar_arrive_expect_tx(&sm.bar_txt[buf], full);
+            bulk_g2s(sm.text_buf[buf], a.bytes + a0, full, &sm.bar_txt[buf], policy);
             return;
         }
     }
-    mbar_arrive(&sm.bar_tile);
+    mbar_arrive(&sm.bar_txt[buf]);
 }
 
-template <int THREADS, int CPT, int MIN_CTAS>
+// PASS 1: count (tile_total). PASS 2: write (ids at tile_base).
+template <int THREADS, int CPT, int MIN_CTAS, int PASS>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArgs a) {
     using SM = EncSmemT<THREADS, CPT>;
     constexpr int TILE = SM::TILE, NW = THREADS / 32;
-    static_assert(NW >= 2, "the open chunks are split over two halves of the warps");
     extern __shared__ __align__(128) unsigned char enc_smem_raw[];
     SM &sm = *reinterpret_cast<SM *>(enc_smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool bulk = a.bulk != 0;
     if (tid == 0) {
-        mbar_init(&sm.bar_off, 1);
-        mbar_init(&sm.bar_tile, 1);
+        for (int b = 0; b < 2; b++) {
+            mbar_init(&sm.bar_off[b], 1);
+            mbar_init(&sm.bar_txt[b], 1);
+        }
         mbar_init_fence();
         sm.n_open = sm.park_used = 0;
-        for (int i = 0; i < ENC_PROF_N; i++) sm.prof[i] = 0;
+        for (int i = 0; i < 8; i++) sm.prof[i] = 0;
     }
     __syncthreads();
     long long t_lap = clock64();
@@ -659,52 +667,53 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
             t_lap = t;
         }
     };
-    uint32_t tile_parity = 0, off_parity = 0;
     const uint64_t policy = l2_evict_first_policy();
-    if (bulk && tid == 0) fetch_tile_bulk(a, sm, off_parity, policy);
-    for (;;) {
-        // ---- 0. the tile's boundaries and text in shared memory ----------------------------------------------------
-        if (bulk) {
-            mbar_wait(&sm.bar_tile, tile_parity);
-            tile_parity ^= 1;
-        } else { // unaligned caller buffers: ticket and cooperative loads
-            __syncthreads();
-            if (tid == 0) {
-                const uint32_t t = atomicAdd(a.ticket, 1u);
-                sm.tile = t < a.n_tiles ? t : TILE_NONE;
-                sm.n_open = sm.park_used = 0;
-            }
-            __syncthreads();
-        }
-        const uint32_t tile = sm.tile;
-        if (tile == TILE_NONE) break;
+    // tiles of this CTA: blockIdx.x, + gridDim.x, ... (no tile depends on another one)
+    if (bulk && tid == 0 && blockIdx.x < a.n_tiles) {
+        fetch_off(a, sm, blockIdx.x, 0, policy);
+        fetch_text(a, sm, blockIdx.x, 0, 0, policy);
+        if (blockIdx.x + gridDim.x < a.n_tiles) fetch_off(a, sm, blockIdx.x + gridDim.x, 1, policy);
+    }
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, it++) {
+        const uint32_t buf = it & 1, par = (it >> 1) & 1; // buffer of this tile, and how often it has been used before (parity)
         const uint64_t c0 = a.chunk0 + (uint64_t)tile * TILE;
         const uint32_t nc = (uint32_t)min((uint64_t)TILE, a.chunk1 - c0);
-        if (!bulk) {
-            for (uint32_t i = tid; i <= nc; i += THREADS) sm.off[i] = __ldg(&a.off[c0 + i]);
+        // ---- 0. the tile's boundaries and text in shared memory ----------------------------------------------------
+        if (bulk) {
+            mbar_wait(&sm.bar_txt[buf], par);
+        } else { // unaligned caller buffers: cooperative loads, no prefetch
             __syncthreads();
-            const uint32_t b0 = sm.off[0], b1 = sm.off[nc], w0 = b0 & ~3u;
+            uint32_t *ob = sm.off_buf[buf];
+            for (uint32_t i = tid; i <= nc; i += THREADS) ob[i] = __ldg(&a.off[c0 + i]);
+            __syncthreads();
+            const uint32_t b0 = ob[0], b1 = ob[nc], w0 = b0 & ~3u;
             const bool st = (b1 - w0) <= (uint32_t)SM::TEXT_CAP;
             if (st) // byte loads: nothing is known about the alignment of the buffer
-                for (uint32_t g = b0 + tid; g < b1; g += THREADS) reinterpret_cast<uint8_t *>(sm.text)[g - w0] = __ldg(&a.bytes[g]);
-            __syncthreads();
+                for (uint32_t g = b0 + tid; g < b1; g += THREADS) reinterpret_cast<uint8_t *>(sm.text_buf[buf])[g - w0] = __ldg(&a.bytes[g]);
             if (tid == 0) {
-                sm.a0 = w0;
-                sm.staged = st;
+                sm.a0[buf] = w0;
+                sm.staged[buf] = st;
             }
             __syncthreads();
         }
-        const uint32_t a0 = sm.a0;
-        const bool staged = sm.staged != 0;
+        // (every thread stores the same two pointers: whoever reads them -- the out-of-line helpers -- has either written
+        // them itself or sees an identical value; the previous tile's readers are all past that tile's last barrier)
+        sm.off = sm.off_buf[buf];
+        sm.text = sm.text_buf[buf];
+        const uint32_t *const soff = sm.off_buf[buf];
+        const uint32_t *const stext = sm.text_buf[buf];
+        const uint32_t a0 = sm.a0[buf];
+        const bool staged = sm.staged[buf] != 0;
         lap(0);
         // ---- 1. fast path: the home slot of every chunk in the SMALL cache, all of a thread's probes in flight ------
         uint32_t o[CPT + 1];
 #pragma unroll
-        for (int j = 0; j <= CPT; j++) o[j] = sm.off[min(tid * CPT + j, nc)];
+        for (int j = 0; j <= CPT; j++) o[j] = soff[min(tid * CPT + j, nc)];
         uint32_t cnt[CPT];
         uint32_t openq[CPT]; // place on the open list, or TILE_NONE: cnt / vq are final
         uint4 vq[CPT];       // hit: the chunk's ids
-        uint32_t home_taken = 0; // bit j: the chunk's home slot in the SMALL cache holds another chunk
+        uint32_t home_taken = 0; // bit j: the chunk's home slot in the SMALL cache holds another chunk (or a stub)
         const bool keyed = a.cache.small != nullptr && staged && !(a.ablate & 2); // (an unstaged tile -- very long chunks -- is all "open")
         if (keyed) {
             uint4 kw[CPT], kq[CPT];
@@ -719,7 +728,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
                 lm.y = (uint32_t)((1ull << (8 * (min(max(nb, 4u), 8u) - 4))) - 1);
                 lm.z = (uint32_t)((1ull << (8 * (min(max(nb, 8u), 12u) - 8))) - 1);
                 lm.w = (uint32_t)((1ull << (8 * (min(max(nb, 12u), 16u) - 12))) - 1);
-                const uint32_t t0 = sm.text[wi], t1 = sm.text[wi + 1], t2 = sm.text[wi + 2], t3 = sm.text[wi + 3], t4 = sm.text[wi + 4];
+                const uint32_t t0 = stext[wi], t1 = stext[wi + 1], t2 = stext[wi + 2], t3 = stext[wi + 3], t4 = stext[wi + 4];
                 kw[j].x = __funnelshift_r(t0, t1, sh) & lm.x;
                 kw[j].y = __funnelshift_r(t1, t2, sh) & lm.y;
                 kw[j].z = __funnelshift_r(t2, t3, sh) & lm.z;
@@ -746,6 +755,12 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
             }
             home_taken = a.cache.small ? ~0u : 0u; // (no home slot was looked at: the whole probe sequence is open)
         }
+        // the next tile's boundaries have had a whole fast path to land: start its text on its way, and the boundaries
+        // of the tile after it (their buffers belong to tiles that are completely done)
+        if (bulk && tid == 0) {
+            const uint32_t t1 = tile + gridDim.x;
+            if (t1 < a.n_tiles) fetch_text(a, sm, t1, buf ^ 1, ((it + 1) >> 1) & 1, policy);
+        }
 #pragma unroll
         for (int j = 0; j < CPT; j++) {
             if (openq[j] == TILE_NONE) continue; // hit
@@ -755,13 +770,13 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
             if (len > ENC_SHORT_MAX) {
                 if (a.scratch_b) {
                     cnt[j] = a.scratch_b[o[j]]; // encoded by k_encode_long
-                } else {                         // optimistic launch: report it, the host runs the long path and repeats
+                } else if (PASS == 1) {         // optimistic launch: report it, the host runs the long path and repeats
                     const uint32_t q = atomicAdd(a.n_long, 1u);
                     if (q < a.long_cap) a.long_list[q] = (uint32_t)(c0 + k);
                 }
                 continue;
             }
-            if (a.ablate & 10) { // (profiling only: 2 = every chunk "hits", 8 = no slow path)
+            if (a.ablate & 10) { // (profiling only: 2 = every chunk "hits", 8 = open chunks are not resolved)
                 cnt[j] = (a.ablate & 2) ? 2 : 1;
                 vq[j] = make_uint4(o[j], len, 0, 0);
                 continue;
@@ -778,7 +793,6 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
             }
             const uint32_t q = atomicAdd(&sm.n_open, 1u); // nobody has seen it before: the scan list
             sm.open_k[q] = (uint16_t)k;
-            sm.scan[q] = (uint16_t)q;
             openq[j] = q;
         }
         __syncthreads();
@@ -787,7 +801,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
         {
             const uint32_t n_scan = sm.n_open;
             if (n_scan) {
-                scan_open_chunks<THREADS>(a, sm, a0, staged, n_scan);
+                scan_open_chunks<THREADS>(a, sm, a0, staged, n_scan, PASS == 1);
                 __syncthreads();
             }
         }
@@ -798,7 +812,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
             if (openq[j] != TILE_NONE) cnt[j] = sm.meta[openq[j]] >> 20;
             sum += cnt[j];
         }
-        // ---- 3. place in the stream: block exclusive scan + look-back; ids gathered in shared memory ------------------
+        // ---- 3. the tile's id count (pass 1) / every thread's place in the tile (pass 2) -----------------------------
         uint32_t incl = sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -807,7 +821,6 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
         }
         if (lane == 31) sm.warp_sum[warp] = incl;
         __syncthreads();
-        lap(3);
         uint32_t warp_base = 0, total = 0;
 #pragma unroll
         for (int w = 0; w < NW; w++) {
@@ -815,79 +828,118 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
             if (w < (int)warp) warp_base += v;
             total += v;
         }
-        if (warp == 0) { // the other warps gather their ids meanwhile
-            const uint64_t b = (a.ablate & 1) ? (uint64_t)tile * (TILE * 9 / 4)
-                                              : lookback_base<4>(a.status, tile, total, a.stream_base);
-            if (lane == 0) sm.base = b;
-        }
-        const bool via_smem = total <= (uint32_t)SM::STAGE;
-        const uint32_t loc0 = warp_base + (incl - sum);
-        if (via_smem && !(a.ablate & 4)) {
-            uint32_t loc = loc0;
+        lap(3);
+        if (tid == 0) sm.n_open = sm.park_used = 0; // (everybody is past the open list; the next appends come after a barrier below)
+        if (PASS == 1) {
+            if (tid == 0) a.tile_total[tile] = total;
+            __syncthreads();
+        } else {
+            const uint64_t base = a.tile_base[tile];
+            const bool via_smem = total <= (uint32_t)SM::STAGE;
+            const uint32_t loc0 = warp_base + (incl - sum);
+            if (!(a.ablate & 4)) {
+                uint32_t loc = loc0;
 #pragma unroll
-            for (int j = 0; j < CPT; j++) {
-                emit_chunk(a, sm, a0, staged, cnt[j], openq[j], o[j], o[j + 1], vq[j], sm.stage + loc, ~0ull);
-                loc += cnt[j];
-            }
-        }
-        __syncthreads();
-        lap(4);
-        const uint64_t base = sm.base;
-        if (!via_smem && !(a.ablate & 4)) { // a tile with more ids than the gather buffer holds: every thread stores its own
-            uint32_t loc = loc0;
-#pragma unroll
-            for (int j = 0; j < CPT; j++) {
-                const uint64_t at = base + loc;
-                emit_chunk(a, sm, a0, staged, cnt[j], openq[j], o[j], o[j + 1], vq[j], a.out + at, at < a.out_cap ? a.out_cap - at : 0);
-                loc += cnt[j];
-            }
-            __syncthreads(); // (emit may read the tile's text and lists: they are replaced below)
-        }
-        // ---- 4. the next tile's loads start now; this tile's ids leave as whole lines --------------------------------
-        if (bulk && tid == 0) {
-            sm.n_open = sm.park_used = 0; // (the next tile's appends come after the next mbarrier wait)
-            fetch_tile_bulk(a, sm, off_parity, policy);
-        }
-        lap(5);
-        if (a.out_off) {
-            uint32_t loc = loc0;
-#pragma unroll
-            for (int j = 0; j < CPT; j++) {
-                const uint32_t k = tid * CPT + j;
-                if (k < nc) a.out_off[c0 + k] = base + loc;
-                loc += cnt[j];
-            }
-        }
-        if (via_smem && !(a.ablate & 4)) {
-            if (base + total <= a.out_cap && a.out_aligned) {
-                // 16-byte stores: vector v = stream words [w0 + 4v, w0 + 4v + 4), w0 = base rounded down to 4 words
-                const uint32_t pad = (uint32_t)(base & 3);
-                uint32_t *const gout = a.out + (base - pad);
-                const uint32_t n_vec = (pad + total + 3) >> 2;
-                for (uint32_t v = tid; v < n_vec; v += THREADS) {
-                    const int lo = (int)(4 * v) - (int)pad; // index of the vector's first word in the gather buffer
-                    if (lo >= 0 && (uint32_t)lo + 4 <= total) {
-                        const uint4 q = make_uint4(sm.stage[lo], sm.stage[lo + 1], sm.stage[lo + 2], sm.stage[lo + 3]);
-                        __stcs(reinterpret_cast<uint4 *>(gout) + v, q);
-                    } else {
-                        for (int i = lo < 0 ? 0 : lo; i < lo + 4 && (uint32_t)i < total; i++) __stcs(&a.out[base + i], sm.stage[i]);
-                    }
+                for (int j = 0; j < CPT; j++) {
+                    const uint64_t at = base + loc;
+                    if (via_smem)
+                        emit_chunk(a, sm, a0, staged, cnt[j], openq[j], o[j], o[j + 1], vq[j], sm.stage + loc, ~0ull);
+                    else // a tile with more ids than the gather buffer holds: every thread stores its own
+                        emit_chunk(a, sm, a0, staged, cnt[j], openq[j], o[j], o[j + 1], vq[j], a.out + at, at < a.out_cap ? a.out_cap - at : 0);
+                    loc += cnt[j];
                 }
-            } else {
-                for (uint32_t i = tid; i < total; i += THREADS)
-                    if (base + i < a.out_cap) a.out[base + i] = sm.stage[i];
-                if (tid == 0 && base + total > a.out_cap) *a.overflow = 1;
             }
+            if (a.out_off) {
+                uint32_t loc = loc0;
+#pragma unroll
+                for (int j = 0; j < CPT; j++) {
+                    const uint32_t k = tid * CPT + j;
+                    if (k < nc) a.out_off[c0 + k] = base + loc;
+                    loc += cnt[j];
+                }
+            }
+            __syncthreads();
+            lap(4);
+            if (via_smem && !(a.ablate & 4)) {
+                if (base + total <= a.out_cap && a.out_aligned) {
+                    // 16-byte stores: vector v = stream words [w0 + 4v, w0 + 4v + 4), w0 = base rounded down to 4 words
+                    const uint32_t pad = (uint32_t)(base & 3);
+                    uint32_t *const gout = a.out + (base - pad);
+                    const uint32_t n_vec = (pad + total + 3) >> 2;
+                    for (uint32_t v = tid; v < n_vec; v += THREADS) {
+                        const int lo = (int)(4 * v) - (int)pad; // index of the vector's first word in the gather buffer
+                        if (lo >= 0 && (uint32_t)lo + 4 <= total) {
+                            const uint4 q = make_uint4(sm.stage[lo], sm.stage[lo + 1], sm.stage[lo + 2], sm.stage[lo + 3]);
+                            __stcs(reinterpret_cast<uint4 *>(gout) + v, q);
+                        } else {
+                            for (int i = lo < 0 ? 0 : lo; i < lo + 4 && (uint32_t)i < total; i++) __stcs(&a.out[base + i], sm.stage[i]);
+                        }
+                    }
+                } else {
+                    for (uint32_t i = tid; i < total; i += THREADS)
+                        if (base + i < a.out_cap) a.out[base + i] = sm.stage[i];
+                    if (tid == 0 && base + total > a.out_cap) *a.overflow = 1;
+                }
+            }
+            if (tile == a.n_tiles - 1 && tid == 0 && a.out_off && a.chunk1 == a.n_chunks) a.out_off[a.n_chunks] = base + total;
         }
-        if (tile == a.n_tiles - 1 && tid == 0) {
-            *a.d_n_out = base + total;
-            if (a.out_off && a.chunk1 == a.n_chunks) a.out_off[a.n_chunks] = base + total;
+        // the boundaries of the tile after the next one go into this tile's buffer: the whole CTA is past a barrier that
+        // follows its last read of them (pass 2 reads the gather buffer only from here on)
+        if (bulk && tid == 0) {
+            const uint32_t t2 = tile + 2 * gridDim.x;
+            if (t2 < a.n_tiles) fetch_off(a, sm, t2, buf, policy);
         }
         lap(6);
         if (a.prof && tid == 0) sm.prof[7] += 1;
     }
     if (a.prof && tid == 0)
-        for (int i = 0; i < ENC_PROF_N; i++) atomicAdd(&a.prof[i], sm.prof[i]);
+        for (int i = 0; i < 8; i++) atomicAdd(&a.prof[(PASS - 1) * 8 + i], sm.prof[i]);
+}
+
+// tile_total[0 .. n) -> tile_base[0 .. n) (exclusive scan, starting at the ids of earlier launches); *d_n_out = the new total.
+// One CTA: a launch has at most 2^26 / 256 tiles.
+__global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t *tile_total, uint32_t n, unsigned long long *tile_base,
+                                                   unsigned long long *d_n_out) {
+    __shared__ unsigned long long warp_sum[32];
+    __shared__ unsigned long long carry;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = *d_n_out;
+    __syncthreads();
+    for (uint32_t i0 = 0; i0 < n; i0 += 1024 * 4) {
+        uint32_t v[4];
+        unsigned long long mine = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t i = i0 + tid * 4 + q;
+            v[q] = i < n ? tile_total[i] : 0u;
+            mine += v[q];
+        }
+        unsigned long long incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long x = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += x;
+        }
+        if (lane == 31) warp_sum[warp] = incl;
+        __syncthreads();
+        unsigned long long wb = 0, all = 0;
+        for (int w = 0; w < 32; w++) {
+            const unsigned long long x = warp_sum[w];
+            if (w < (int)warp) wb += x;
+            all += x;
+        }
+        unsigned long long at = carry + wb + (incl - mine);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t i = i0 + tid * 4 + q;
+            if (i < n) tile_base[i] = at;
+            at += v[q];
+        }
+        __syncthreads();
+        if (tid == 0) carry += all;
+        __syncthreads();
+    }
+    if (tid == 0) *d_n_out = carry;
 }
 
 } // namespace mbpe
