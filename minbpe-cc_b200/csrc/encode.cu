@@ -320,6 +320,8 @@ struct mbpe_encoder {
     // scratch (grown on demand)
     unsigned long long *d_status = nullptr; // encode: place of every tile of a launch (k_tile_scan); decode: look-back words
     uint32_t *d_tile_total = nullptr;       // encode: ids of every tile of a launch (pass 1)
+    uint32_t *d_spill = nullptr;            // encode: parking overflow, one block per CTA of the tile kernel
+    uint64_t spill_words = 0;
     uint64_t status_cap = 0;
     uint32_t *d_small = nullptr; // [0] ticket (decode), [1] n_long, [2] overflow, [3] scanned chunks
     unsigned long long *d_prof = nullptr; // MBPE_DEBUG: cycles per phase of k_encode_tiles (ENC_PROF_*)
@@ -526,7 +528,7 @@ extern "C" void mbpe_encoder_destroy(mbpe_encoder *e) {
     cudaSetDevice(e->device);
     void *ps[] = {e->d_slots, e->d_voff, e->d_vbytes, e->d_vpack, e->d_sp_ids, e->d_sp_off, e->d_sp_bytes, e->d_status, e->d_small,
                   e->d_n_out, e->d_long_list, e->d_scratch_a, e->d_scratch_b, e->d_cache, e->d_cache_small, e->d_cache_log,
-                  e->d_cache_ctr, e->d_cache_arena, e->d_esp_ids, e->d_esp_off, e->d_esp_bytes, e->d_prof, e->d_tile_total};
+                  e->d_cache_ctr, e->d_cache_arena, e->d_esp_ids, e->d_esp_off, e->d_esp_bytes, e->d_prof, e->d_tile_total, e->d_spill};
     for (void *p : ps) cudaFree(p);
     free_host_pipe(e);
     if (e->pipe_stream) cudaStreamDestroy(e->pipe_stream);
@@ -662,6 +664,16 @@ extern "C" int mbpe_encode_reserve(mbpe_encoder *e, uint64_t n_bytes, uint64_t n
         MB_CUDA(cudaMalloc(&e->d_long_list, (1 << 16) * 4));
         e->long_cap = 1 << 16;
     }
+    // parking overflow of the tile kernel: one block of TILE * ENC_SHORT_MAX words per CTA (the worst case; untouched pages
+    // cost nothing but address space)
+    const uint64_t need = (uint64_t)e->sms * enc_configs[e->cfg].ctas * tile_chunks * ENC_SHORT_MAX;
+    if (need > e->spill_words) {
+        cudaFree(e->d_spill);
+        e->d_spill = nullptr;
+        e->spill_words = 0;
+        MB_CUDA(cudaMalloc(&e->d_spill, need * 4));
+        e->spill_words = need;
+    }
     return MBPE_OK;
 }
 
@@ -696,6 +708,7 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
     a.long_cap = (uint32_t)e->long_cap;
     a.overflow = e->d_small + 2;
     a.miss_count = e->d_small + 3;
+    a.spill = e->d_spill;
     a.prof = e->d_prof;
     // cp.async.bulk needs 16-byte aligned sources (device allocations are; offsets into them may not be)
     a.bulk = ((((uintptr_t)d_bytes) | ((uintptr_t)d_off)) & 15) == 0 && !getenv("MBPE_ENC_NO_BULK");

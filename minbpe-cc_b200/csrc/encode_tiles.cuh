@@ -269,6 +269,7 @@ struct EncArgs {
     uint32_t long_cap;
     uint32_t *overflow;          // set when out_cap is too small
     uint32_t *miss_count;        // chunks that went through the scan (statistics)
+    uint32_t *spill;             // parking overflow: gridDim.x blocks of EncSmemT::SPILL words
     uint32_t bulk;               // bytes / off are 16-byte aligned: stage with cp.async.bulk
     uint32_t out_aligned;        // out is 16-byte aligned: ids leave as 16-byte stores
     unsigned long long *prof;    // optional: SM cycles per phase summed over CTAs (thread 0's clock), see ENC_PROF_*
@@ -282,7 +283,9 @@ struct EncArgs {
 constexpr int ENC_PROF_N = 16;
 constexpr uint32_t TILE_NONE = 0xFFFFFFFFu;
 constexpr uint64_t ENC_MAX_SUBBATCH = 1ull << 26; // chunks per launch at most (tile ids and look-back words are 32-bit safe)
-constexpr uint32_t PARK_NONE = 0xFFFFF;       // (20 bits) the ids of an open chunk did not fit the parking area
+// Parking area of a tile = ids of its open chunks until they are written: the first PARK words live in shared memory, the
+// rest in the CTA's spill block in HBM (one index space; every id covers at least one byte of text, so a tile of
+// ENC_SHORT_MAX-byte chunks at most needs TILE * ENC_SHORT_MAX words: it always fits, nothing is ever encoded twice).
 constexpr uint32_t ET_WARP_SCAN_MAX = 48;     // up to this many scans per tile run one warp per chunk
 
 template <int THREADS, int CPT>
@@ -290,7 +293,8 @@ struct EncSmemT {
     static constexpr int TILE = THREADS * CPT;
     static constexpr int TEXT_CAP = TILE * 10;  // staged text bytes per tile (average chunk ~5 bytes); wider tiles read HBM
     static constexpr int STAGE = TILE * 5 / 2;  // ids gathered per tile (average ~2.1 per chunk); more: direct stores
-    static constexpr int PARK = TILE / 2;       // ids of open chunks parked until they are written
+    static constexpr int PARK = TILE;           // parking words in shared memory (warm caches park a few dozen ids per tile)
+    static constexpr int SPILL = TILE * 64;     // parking words per CTA in HBM (EncArgs::spill): the worst case
     alignas(128) uint32_t off_buf[2][TILE + 8];          // double buffered: the next tile's data arrives during this tile
     alignas(128) uint32_t text_buf[2][TEXT_CAP / 4 + 16]; // + halo: key assembly reads whole words past the chunk's end
     alignas(16) uint32_t stage[STAGE + 4];
@@ -300,8 +304,8 @@ struct EncSmemT {
     uint32_t warp_scratch[THREADS / 32][32];
     uint32_t warp_sum[THREADS / 32];
     alignas(8) uint64_t bar_off[2], bar_txt[2]; // mbarriers per buffer: boundaries landed (thread 0 waits), text landed (all wait)
-    const uint32_t *off;       // the current tile's buffers
-    const uint32_t *text;
+    const uint32_t *off;       // the current tile's buffers (set by thread 0 before the tile's first barrier; helpers that run
+    const uint32_t *text;      // after a barrier read them)
     uint32_t a0[2], staged[2], n_open, park_used;
     unsigned long long prof[8];
 };
@@ -383,13 +387,22 @@ __device__ __forceinline__ void log_scanned(const EncArgs &a, const SM &sm, bool
     for (uint32_t i = 0; i < n; i++) e.ids[i] = ids[i];
 }
 
-// result of an open chunk: its ids go to the parking area, meta = start | n << 20 (start PARK_NONE: no room, the owner
-// encodes the chunk again when it writes)
 template <class SM>
-__device__ __forceinline__ uint32_t park_ids(SM &sm, const uint32_t *ids, uint32_t n) {
+__device__ __forceinline__ void park_store(const EncArgs &a, SM &sm, uint32_t at, uint32_t v) {
+    if (at < (uint32_t)SM::PARK)
+        sm.park[at] = v;
+    else
+        __stcg(a.spill + (size_t)blockIdx.x * SM::SPILL + (at - SM::PARK), v);
+}
+template <class SM>
+__device__ __forceinline__ uint32_t park_load(const EncArgs &a, const SM &sm, uint32_t at) {
+    return at < (uint32_t)SM::PARK ? sm.park[at] : __ldcg(a.spill + (size_t)blockIdx.x * SM::SPILL + (at - SM::PARK));
+}
+// result of an open chunk: its ids go to the parking area, meta = start | n << 20
+template <class SM>
+__device__ __forceinline__ uint32_t park_ids(const EncArgs &a, SM &sm, const uint32_t *ids, uint32_t n) {
     const uint32_t at = atomicAdd(&sm.park_used, n);
-    if (at + n > (uint32_t)SM::PARK) return PARK_NONE | (n << 20);
-    for (uint32_t i = 0; i < n; i++) sm.park[at + i] = ids[i];
+    for (uint32_t i = 0; i < n; i++) park_store(a, sm, at + i, ids[i]);
     return at | (n << 20);
 }
 
@@ -400,14 +413,14 @@ __device__ __forceinline__ uint32_t scan_serial(const EncArgs &a, SM &sm, uint32
     const uint32_t sid = special_match(a.sp, len, [&](uint32_t i) { return tile_byte(a, sm, staged, a0, o + i); });
     if (sid != ENC_NONE) {
         t[0] = sid;
-        return park_ids(sm, t, 1);
+        return park_ids(a, sm, t, 1);
     }
     for (uint32_t i = 0; i < len; i++) t[i] = tile_byte(a, sm, staged, a0, o + i);
     uint32_t n = len;
     bool merged = true;
     while (merged && n >= 2) n = enc_pass(a.tab, t, n, merged);
     if (log) log_scanned(a, sm, staged, a0, o, len, t, n);
-    return park_ids(sm, t, n);
+    return park_ids(a, sm, t, n);
 }
 
 // one warp encodes the open chunk at open-list place q (<= 32 bytes) and parks its ids
@@ -426,11 +439,7 @@ __device__ __forceinline__ void scan_by_warp(const EncArgs &a, SM &sm, uint32_t 
     uint32_t start = 0;
     if (lane == 0) start = atomicAdd(&sm.park_used, mn);
     start = __shfl_sync(0xffffffffu, start, 0);
-    if (start + mn <= (uint32_t)SM::PARK) {
-        if (lane < mn) sm.park[start + lane] = tok;
-    } else {
-        start = PARK_NONE;
-    }
+    if (lane < mn) park_store(a, sm, start + lane, tok);
     if (lane == 0) sm.meta[q] = start | (mn << 20);
     if (log && a.cache.small && mlen <= CACHE_MAX_LEN && sid == ENC_NONE) { // teach the caches
         uint32_t li = 0;
@@ -455,26 +464,31 @@ __device__ __forceinline__ void scan_by_warp(const EncArgs &a, SM &sm, uint32_t 
 
 // A chunk the fast path left open but that may well be cached -- 16..31 bytes (BIG cache), a short chunk whose home slot
 // in the SMALL cache holds somebody else (its probe sequence goes on) or a stub (more than 4 ids: BIG), a special token.
-// By the chunk's own thread, no barrier: the lanes that need it diverge for ~one L2 round trip (key and value sectors of
-// a BIG slot are fetched together). Out of line so that its registers are not charged to the fast path.
-// Returns the id count (0: in no cache -- the scan has to encode it); <= 4 ids come back in v, more are parked (v.x = start
-// in the parking area, PARK_NONE: no room).
+// By the chunk's own thread, no barrier: the lanes that need it diverge for ONE round trip in the common cases (the
+// caller says what the home slot showed, so a stub or a long chunk goes straight to BIG, whose key and value sectors are
+// fetched together). Out of line so that its registers are not charged to the fast path.
+// hint: 0 = whole SMALL probe sequence (home slot not seen), 1 = home slot taken by another chunk (continue behind it),
+//       2 = stub / long chunk: BIG only.
+// Returns the id count (0: in no cache -- the scan has to encode it); <= 4 ids come back in v, more are parked (v.x = start).
 template <class SM>
-__device__ __noinline__ uint32_t resolve_cached(const EncArgs &a, SM &sm, uint32_t a0, bool staged, uint32_t o, uint32_t len, uint4 &v) {
-    const uint32_t sid = special_match(a.sp, len, [&](uint32_t i) { return tile_byte(a, sm, staged, a0, o + i); });
-    if (sid != ENC_NONE) {
-        v.x = sid;
-        return 1;
+__device__ __noinline__ uint32_t resolve_cached(const EncArgs &a, SM &sm, uint32_t a0, bool staged, uint32_t o, uint32_t len, uint32_t hint,
+                                                uint4 &v) {
+    if (a.sp.n) {
+        const uint32_t sid = special_match(a.sp, len, [&](uint32_t i) { return tile_byte(a, sm, staged, a0, o + i); });
+        if (sid != ENC_NONE) {
+            v.x = sid;
+            return 1;
+        }
     }
     if (!a.cache.small || len > CACHE_MAX_LEN) return 0;
     uint64_t key[4];
     big_key(a, sm, staged, a0, o, len, key);
-    if (len <= SMALL_MAX_LEN) {
+    if (len <= SMALL_MAX_LEN && hint != 2) {
         const uint32_t w0 = (uint32_t)key[0], w1 = (uint32_t)(key[0] >> 32), w2 = (uint32_t)key[1];
         const uint32_t w3 = (uint32_t)(key[1] >> 32) | (len << 24);
-        uint32_t h = small_hash(w0, w1, w2, w3) >> a.cache.small_shift;
+        uint32_t h = ((small_hash(w0, w1, w2, w3) >> a.cache.small_shift) + (hint == 1 ? 1u : 0u)) & a.cache.small_mask;
         bool stub = false;
-        for (uint32_t probes = 0; probes < CACHE_MAX_PROBES; probes++) {
+        for (uint32_t probes = hint == 1 ? 1u : 0u; probes < CACHE_MAX_PROBES; probes++) {
             uint4 kq, vv;
             ld_slot256(&a.cache.small[h], kq, vv);
             if (kq.w == 0) return 0; // not cached at all
@@ -505,16 +519,13 @@ __device__ __noinline__ uint32_t resolve_cached(const EncArgs &a, SM &sm, uint32
                 return n;
             }
             const uint32_t at = atomicAdd(&sm.park_used, n);
-            v.x = PARK_NONE;
-            if (at + n <= (uint32_t)SM::PARK) {
-                v.x = at;
-                if (n <= CACHE_INLINE_IDS) {
-                    const uint32_t ids[CACHE_INLINE_IDS] = {v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-                    for (uint32_t i = 0; i < n; i++) sm.park[at + i] = ids[i];
-                } else {
-                    const uint32_t *src = a.cache.arena + v0.y;
-                    for (uint32_t i = 0; i < n; i++) sm.park[at + i] = __ldg(&src[i]);
-                }
+            v.x = at;
+            if (n <= CACHE_INLINE_IDS) {
+                const uint32_t ids[CACHE_INLINE_IDS] = {v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                for (uint32_t i = 0; i < n; i++) park_store(a, sm, at + i, ids[i]);
+            } else {
+                const uint32_t *src = a.cache.arena + v0.y;
+                for (uint32_t i = 0; i < n; i++) park_store(a, sm, at + i, __ldg(&src[i]));
             }
             return n;
         }
@@ -549,54 +560,26 @@ __device__ __noinline__ void scan_open_chunks(const EncArgs &a, SM &sm, uint32_t
     }
 }
 
-// ids of an open chunk that did not fit the parking area: encode it again, straight into place (rare)
-template <class SM>
-__device__ __noinline__ void rescan_into(const EncArgs &a, SM &sm, uint32_t a0, bool staged, uint32_t o, uint32_t len, uint32_t *dst,
-                                         uint32_t n) {
-    uint32_t t[ENC_SHORT_MAX];
-    const uint32_t sid = special_match(a.sp, len, [&](uint32_t i) { return tile_byte(a, sm, staged, a0, o + i); });
-    uint32_t m = len;
-    if (sid != ENC_NONE) {
-        t[0] = sid;
-        m = 1;
-    } else {
-        for (uint32_t i = 0; i < len; i++) t[i] = tile_byte(a, sm, staged, a0, o + i);
-        bool merged = true;
-        while (merged && m >= 2) m = enc_pass(a.tab, t, m, merged);
-    }
-    for (uint32_t i = 0; i < n && i < m; i++) dst[i] = t[i];
-}
-
 // one chunk's ids -> dst[0 .. n) (shared-memory gather buffer, or the stream itself for oversized tiles).
-// openq: the chunk's place on the open list, or TILE_NONE: its (<= 4) ids are in v
+// openq: the chunk's place on the open list, or TILE_NONE: its ids are in v (<= 4) or parked at v.x (more)
 template <class SM>
-__device__ __forceinline__ void emit_chunk(const EncArgs &a, SM &sm, uint32_t a0, bool staged, uint32_t n, uint32_t openq, uint32_t o0,
-                                           uint32_t o1, uint4 v, uint32_t *dst, uint64_t room) {
+__device__ __forceinline__ void emit_chunk(const EncArgs &a, SM &sm, uint32_t n, uint32_t openq, uint32_t o0, uint32_t o1, uint4 v,
+                                           uint32_t *dst, uint64_t room) {
     if (n == 0) return;
     if (n > room) {
         *a.overflow = 1;
         return;
     }
-    if (openq == TILE_NONE) {
-        if (o1 - o0 > ENC_SHORT_MAX) {
-            for (uint32_t i = 0; i < n; i++) dst[i] = a.scratch_a[o0 + i];
-        } else if (n <= 4) {
-            dst[0] = v.x;
-            if (n > 1) dst[1] = v.y;
-            if (n > 2) dst[2] = v.z;
-            if (n > 3) dst[3] = v.w;
-        } else if (v.x != PARK_NONE) { // a cached chunk with more than 4 ids: parked by resolve_cached
-            for (uint32_t i = 0; i < n; i++) dst[i] = sm.park[v.x + i];
-        } else {
-            rescan_into(a, sm, a0, staged, o0, o1 - o0, dst, n);
-        }
+    if (openq == TILE_NONE && o1 - o0 > ENC_SHORT_MAX) {
+        for (uint32_t i = 0; i < n; i++) dst[i] = a.scratch_a[o0 + i];
+    } else if (openq == TILE_NONE && n <= 4) {
+        dst[0] = v.x;
+        if (n > 1) dst[1] = v.y;
+        if (n > 2) dst[2] = v.z;
+        if (n > 3) dst[3] = v.w;
     } else {
-        const uint32_t start = sm.meta[openq] & 0xFFFFF;
-        if (start != PARK_NONE) {
-            for (uint32_t i = 0; i < n; i++) dst[i] = sm.park[start + i];
-        } else {
-            rescan_into(a, sm, a0, staged, o0, o1 - o0, dst, n);
-        }
+        const uint32_t start = openq == TILE_NONE ? v.x : (sm.meta[openq] & 0xFFFFF);
+        for (uint32_t i = 0; i < n; i++) dst[i] = park_load(a, sm, start + i);
     }
 }
 
@@ -697,10 +680,8 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
             }
             __syncthreads();
         }
-        // (every thread stores the same two pointers: whoever reads them -- the out-of-line helpers -- has either written
-        // them itself or sees an identical value; the previous tile's readers are all past that tile's last barrier)
-        sm.off = sm.off_buf[buf];
-        sm.text = sm.text_buf[buf];
+        sm.off = sm.off_buf[buf]; // (every thread stores the same two pointers: a reader has written them itself or sees the
+        sm.text = sm.text_buf[buf]; //  identical value; every tile ends with a barrier, so nobody still reads the previous ones)
         const uint32_t *const soff = sm.off_buf[buf];
         const uint32_t *const stext = sm.text_buf[buf];
         const uint32_t a0 = sm.a0[buf];
@@ -713,7 +694,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
         uint32_t cnt[CPT];
         uint32_t openq[CPT]; // place on the open list, or TILE_NONE: cnt / vq are final
         uint4 vq[CPT];       // hit: the chunk's ids
-        uint32_t home_taken = 0; // bit j: the chunk's home slot in the SMALL cache holds another chunk (or a stub)
+        uint32_t hints = 0;  // two bits per chunk: what its home slot in the SMALL cache showed (see resolve_cached)
         const bool keyed = a.cache.small != nullptr && staged && !(a.ablate & 2); // (an unstaged tile -- very long chunks -- is all "open")
         if (keyed) {
             uint4 kw[CPT], kq[CPT];
@@ -734,7 +715,10 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
                 kw[j].z = __funnelshift_r(t2, t3, sh) & lm.z;
                 kw[j].w = (__funnelshift_r(t3, t4, sh) & lm.w) | (len << 24);
                 const uint32_t h = small_hash(kw[j].x, kw[j].y, kw[j].z, kw[j].w) >> a.cache.small_shift;
-                ld_slot256(&a.cache.small[h], kq[j], vq[j]); // (empty / long chunks probe too: the answer is ignored)
+                if (PASS == 1) // (counting needs the key half only; empty / long chunks probe too: the answer is ignored)
+                    kq[j] = __ldg(reinterpret_cast<const uint4 *>(&a.cache.small[h]));
+                else
+                    ld_slot256(&a.cache.small[h], kq[j], vq[j]);
             }
 #pragma unroll
             for (int j = 0; j < CPT; j++) {
@@ -744,7 +728,8 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
                 const bool final = hit && (kq[j].w >> 28) <= SMALL_MAX_IDS; // (a stub is a hit that only says "BIG has it")
                 cnt[j] = final ? kq[j].w >> 28 : 0u;
                 openq[j] = final ? TILE_NONE : 0u; // 0: undecided, see below
-                if (small && kq[j].w != 0) home_taken |= 1u << j;
+                // what the home slot showed, for resolve_cached: 1 = another chunk, 2 = this chunk's stub (or a long chunk)
+                hints |= (hit ? 2u : (small && kq[j].w != 0) ? 1u : (small ? 3u : 2u)) << (2 * j); // 3: empty home slot = not cached
             }
         } else {
 #pragma unroll
@@ -753,7 +738,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
                 openq[j] = 0;
                 vq[j] = make_uint4(0, 0, 0, 0);
             }
-            home_taken = a.cache.small ? ~0u : 0u; // (no home slot was looked at: the whole probe sequence is open)
+            hints = 0; // (no home slot was looked at: the whole probe sequence is open)
         }
         // the next tile's boundaries have had a whole fast path to land: start its text on its way, and the boundaries
         // of the tile after it (their buffers belong to tiles that are completely done)
@@ -761,6 +746,8 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
             const uint32_t t1 = tile + gridDim.x;
             if (t1 < a.n_tiles) fetch_text(a, sm, t1, buf ^ 1, ((it + 1) >> 1) & 1, policy);
         }
+        // open chunks: bit j of `open`. First the ones that need no look-up at all ...
+        uint32_t open = 0;
 #pragma unroll
         for (int j = 0; j < CPT; j++) {
             if (openq[j] == TILE_NONE) continue; // hit
@@ -781,18 +768,41 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
                 vq[j] = make_uint4(o[j], len, 0, 0);
                 continue;
             }
-            // may it still be in a cache? a special token; a chunk of 16..31 bytes (BIG); a short one whose home slot holds
-            // somebody else (its probe sequence continues) or a stub. Its own thread looks, no barrier (resolve_cached).
-            const bool maybe_cached = a.cache.small != nullptr && len <= CACHE_MAX_LEN && (len > SMALL_MAX_LEN || ((home_taken >> j) & 1u));
-            if (maybe_cached || (a.sp.n && ((a.sp.len_mask >> (len < 63u ? len : 63u)) & 1ull))) {
-                const uint32_t n = resolve_cached(a, sm, a0, staged, o[j], len, vq[j]);
-                if (n) {
-                    cnt[j] = n;
-                    continue;
+            open |= 1u << j;
+        }
+        // ... then, one open chunk per lane and round (a lane rarely has two), the ones that may be cached elsewhere: a special
+        // token; a chunk of 16..31 bytes or a stub (BIG); a short one whose home slot holds somebody else. No barrier: the lanes
+        // that have one diverge into resolve_cached for about one memory round trip.
+        for (uint32_t todo = open; todo;) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            uint32_t oj = 0, ej = 0;
+#pragma unroll
+            for (int q = 0; q < CPT; q++)
+                if (q == j) {
+                    oj = o[q];
+                    ej = o[q + 1];
                 }
-            }
-            const uint32_t q = atomicAdd(&sm.n_open, 1u); // nobody has seen it before: the scan list
-            sm.open_k[q] = (uint16_t)k;
+            const uint32_t len = ej - oj, hint = (hints >> (2 * j)) & 3u;
+            const bool maybe_cached = a.cache.small != nullptr && len <= CACHE_MAX_LEN && hint != 3u;
+            if (!(maybe_cached || (a.sp.n && ((a.sp.len_mask >> (len < 63u ? len : 63u)) & 1ull)))) continue;
+            uint4 r = make_uint4(0, 0, 0, 0);
+            const uint32_t n = resolve_cached(a, sm, a0, staged, oj, len, hint == 3u ? 0u : hint, r);
+            if (n == 0) continue;
+            open &= ~(1u << j);
+#pragma unroll
+            for (int q = 0; q < CPT; q++)
+                if (q == j) {
+                    cnt[q] = n;
+                    vq[q] = r;
+                }
+        }
+        // ... and what nobody has seen before goes on the tile's scan list
+#pragma unroll
+        for (int j = 0; j < CPT; j++) {
+            if (!((open >> j) & 1u)) continue;
+            const uint32_t q = atomicAdd(&sm.n_open, 1u);
+            sm.open_k[q] = (uint16_t)(tid * CPT + j);
             openq[j] = q;
         }
         __syncthreads();
@@ -843,9 +853,9 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
                 for (int j = 0; j < CPT; j++) {
                     const uint64_t at = base + loc;
                     if (via_smem)
-                        emit_chunk(a, sm, a0, staged, cnt[j], openq[j], o[j], o[j + 1], vq[j], sm.stage + loc, ~0ull);
+                        emit_chunk(a, sm, cnt[j], openq[j], o[j], o[j + 1], vq[j], sm.stage + loc, ~0ull);
                     else // a tile with more ids than the gather buffer holds: every thread stores its own
-                        emit_chunk(a, sm, a0, staged, cnt[j], openq[j], o[j], o[j + 1], vq[j], a.out + at, at < a.out_cap ? a.out_cap - at : 0);
+                        emit_chunk(a, sm, cnt[j], openq[j], o[j], o[j + 1], vq[j], a.out + at, at < a.out_cap ? a.out_cap - at : 0);
                     loc += cnt[j];
                 }
             }
@@ -883,8 +893,8 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
             }
             if (tile == a.n_tiles - 1 && tid == 0 && a.out_off && a.chunk1 == a.n_chunks) a.out_off[a.n_chunks] = base + total;
         }
-        // the boundaries of the tile after the next one go into this tile's buffer: the whole CTA is past a barrier that
-        // follows its last read of them (pass 2 reads the gather buffer only from here on)
+        if (PASS == 2) __syncthreads(); // every tile ends with a barrier: nothing of it is still read when the next one starts
+        // the boundaries of the tile after the next one go into this tile's buffer
         if (bulk && tid == 0) {
             const uint32_t t2 = tile + 2 * gridDim.x;
             if (t2 < a.n_tiles) fetch_off(a, sm, t2, buf, policy);
