@@ -318,12 +318,11 @@ struct mbpe_encoder {
     uint32_t n_esp = 0;
     unsigned long long esp_len_mask = 0;
     // scratch (grown on demand)
-    unsigned long long *d_status = nullptr; // encode: place of every tile of a launch (k_tile_scan); decode: look-back words
-    uint32_t *d_tile_total = nullptr;       // encode: ids of every tile of a launch (pass 1)
+    unsigned long long *d_status = nullptr; // look-back words of the tile kernels, one per tile of a launch
     uint32_t *d_spill = nullptr;            // encode: parking overflow, one block per CTA of the tile kernel
     uint64_t spill_words = 0;
     uint64_t status_cap = 0;
-    uint32_t *d_small = nullptr; // [0] ticket (decode), [1] n_long, [2] overflow, [3] scanned chunks
+    uint32_t *d_small = nullptr; // [0] ticket, [1] n_long, [2] overflow, [3] scanned chunks
     unsigned long long *d_prof = nullptr; // MBPE_DEBUG: cycles per phase of k_encode_tiles (ENC_PROF_*)
     unsigned long long *d_n_out = nullptr;
     uint32_t *d_long_list = nullptr;
@@ -331,13 +330,12 @@ struct mbpe_encoder {
     uint32_t *d_scratch_a = nullptr, *d_scratch_b = nullptr;
     uint64_t scratch_cap = 0;
     uint64_t launches = 0;
-    // chunk caches (learned across calls)
-    SmallSlot *d_cache_small = nullptr;
+    // chunk cache (learned across calls)
     CacheSlot *d_cache = nullptr;
     CacheLogEntry *d_cache_log = nullptr;
     uint32_t *d_cache_arena = nullptr;
-    uint32_t small_slots = 0, small_log2 = 0, cache_slots = 0, cache_log_cap = 0, cache_arena_cap = 0;
-    uint32_t *d_cache_ctr = nullptr; // [0] log count, [1] used BIG slots, [2] used SMALL slots, [3] arena cursor
+    uint32_t cache_log2 = 0, cache_slots = 0, cache_log_cap = 0, cache_arena_cap = 0;
+    uint32_t *d_cache_ctr = nullptr; // [0] log count, [1] used slots, [3] arena cursor
     uint64_t sub_batch_chunks = 0; // fixed sub-batch size (MBPE_ENCODE_SUBBATCH), 0 = geometric schedule
     uint64_t chunks_seen = 0;      // chunks encoded so far with this handle: how warm the caches are
     int cfg = 0; // kernel shape, see enc_configs
@@ -355,22 +353,19 @@ struct mbpe_encoder {
 namespace mbpe {
 struct EncConfig {
     int threads, cpt, ctas;
-    void (*count)(const EncArgs); // pass 1
-    void (*write)(const EncArgs); // pass 2
+    void (*kernel)(const EncArgs);
     size_t smem;
 };
-#define ENC_CFG(T, C, M) EncConfig{T, C, M, k_encode_tiles<T, C, M, 1>, k_encode_tiles<T, C, M, 2>, sizeof(EncSmemT<T, C>)}
-// (threads, chunks per thread, CTAs per SM); 0 = default, the others for A/B runs (MBPE_ENC_CFG)
-static const EncConfig enc_configs[] = {ENC_CFG(256, 4, 3), ENC_CFG(256, 4, 4), ENC_CFG(512, 4, 2), ENC_CFG(512, 2, 3),
-                                        ENC_CFG(256, 8, 2), ENC_CFG(512, 4, 1), ENC_CFG(256, 2, 6), ENC_CFG(128, 4, 6)};
+#define ENC_CFG(T, C, M, P) EncConfig{T, C, M, k_encode_tiles<T, C, M, P>, sizeof(EncSmemT<T, C>)}
+// (threads, chunks per thread, CTAs per SM, probes in flight per thread); 0 = default, the others for A/B runs (MBPE_ENC_CFG)
+static const EncConfig enc_configs[] = {ENC_CFG(256, 4, 4, 1), ENC_CFG(256, 4, 3, 1), ENC_CFG(256, 4, 3, 2), ENC_CFG(256, 4, 4, 2),
+                                        ENC_CFG(256, 8, 2, 1), ENC_CFG(128, 4, 8, 1), ENC_CFG(512, 4, 2, 1), ENC_CFG(256, 8, 2, 2)};
 constexpr int N_ENC_CONFIGS = sizeof(enc_configs) / sizeof(enc_configs[0]);
 
 static ChunkCache cache_view(const mbpe_encoder *e) {
     ChunkCache cc{};
-    cc.small = e->d_cache_small;
-    cc.small_shift = 32 - e->small_log2;
-    cc.small_mask = e->small_slots ? e->small_slots - 1 : 0;
     cc.slots = e->d_cache;
+    cc.shift = 32 - e->cache_log2;
     cc.mask = e->cache_slots ? e->cache_slots - 1 : 0;
     cc.log = e->d_cache_log;
     cc.log_count = e->d_cache_ctr;
@@ -453,17 +448,14 @@ static int encoder_create_impl(mbpe_encoder *e, const uint32_t *merges, uint32_t
     MB_CUDA(cudaMalloc(&e->d_sp_ids, 4));
     MB_CUDA(cudaMalloc(&e->d_sp_off, 8));
     MB_CUDA(cudaMalloc(&e->d_sp_bytes, 1));
-    // "0" disables the caches; otherwise log2 of the SMALL slot count (default 22 = 128 MB; BIG = a quarter as many slots)
+    // "0" disables the cache; otherwise log2 of the slot count (default 22 = 256 MB)
     const char *cache_env = getenv("MBPE_ENCODE_CACHE");
     int cache_log2 = cache_env && *cache_env ? atoi(cache_env) : 22;
     if (cache_log2 >= 10 && cache_log2 <= 26) {
-        e->small_log2 = (uint32_t)cache_log2;
-        e->small_slots = 1u << cache_log2;
-        e->cache_slots = e->small_slots / 4;
+        e->cache_log2 = (uint32_t)cache_log2;
+        e->cache_slots = 1u << cache_log2;
         e->cache_log_cap = 1u << 19;
         e->cache_arena_cap = 1u << 22;
-        MB_CUDA(cudaMalloc(&e->d_cache_small, (uint64_t)e->small_slots * sizeof(SmallSlot)));
-        MB_CUDA(cudaMemset(e->d_cache_small, 0, (uint64_t)e->small_slots * sizeof(SmallSlot)));
         MB_CUDA(cudaMalloc(&e->d_cache, (uint64_t)e->cache_slots * sizeof(CacheSlot)));
         MB_CUDA(cudaMemset(e->d_cache, 0, (uint64_t)e->cache_slots * sizeof(CacheSlot)));
         MB_CUDA(cudaMalloc(&e->d_cache_log, (uint64_t)e->cache_log_cap * sizeof(CacheLogEntry)));
@@ -488,8 +480,7 @@ static int encoder_create_impl(mbpe_encoder *e, const uint32_t *merges, uint32_t
     const char *cfg_env = getenv("MBPE_ENC_CFG");
     e->cfg = cfg_env && *cfg_env ? std::min(std::max(atoi(cfg_env), 0), N_ENC_CONFIGS - 1) : 0;
     for (int i = 0; i < N_ENC_CONFIGS; i++) {
-        MB_CUDA(cudaFuncSetAttribute(enc_configs[i].count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_configs[i].smem));
-        MB_CUDA(cudaFuncSetAttribute(enc_configs[i].write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_configs[i].smem));
+        MB_CUDA(cudaFuncSetAttribute(enc_configs[i].kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_configs[i].smem));
     }
     return MBPE_OK;
 }
@@ -527,8 +518,8 @@ extern "C" void mbpe_encoder_destroy(mbpe_encoder *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     void *ps[] = {e->d_slots, e->d_voff, e->d_vbytes, e->d_vpack, e->d_sp_ids, e->d_sp_off, e->d_sp_bytes, e->d_status, e->d_small,
-                  e->d_n_out, e->d_long_list, e->d_scratch_a, e->d_scratch_b, e->d_cache, e->d_cache_small, e->d_cache_log,
-                  e->d_cache_ctr, e->d_cache_arena, e->d_esp_ids, e->d_esp_off, e->d_esp_bytes, e->d_prof, e->d_tile_total, e->d_spill};
+                  e->d_n_out, e->d_long_list, e->d_scratch_a, e->d_scratch_b, e->d_cache, e->d_cache_log,
+                  e->d_cache_ctr, e->d_cache_arena, e->d_esp_ids, e->d_esp_off, e->d_esp_bytes, e->d_prof, e->d_spill};
     for (void *p : ps) cudaFree(p);
     free_host_pipe(e);
     if (e->pipe_stream) cudaStreamDestroy(e->pipe_stream);
@@ -607,7 +598,7 @@ extern "C" int mbpe_encoder_seed_special_chunks(mbpe_encoder *e, const uint32_t 
         e->n_esp = n;
         e->esp_len_mask = len_mask;
     }
-    if (!e->d_cache_small) return MBPE_OK;
+    if (!e->d_cache) return MBPE_OK;
     std::vector<CacheLogEntry> log;
     for (uint32_t i = 0; i < n && log.size() < e->cache_log_cap; i++) {
         const uint64_t len = off[i + 1] - off[i];
@@ -620,7 +611,6 @@ extern "C" int mbpe_encoder_seed_special_chunks(mbpe_encoder *e, const uint32_t 
         le.ids[0] = ids[i];
         log.push_back(le);
     }
-    MB_CUDA(cudaMemset(e->d_cache_small, 0, (uint64_t)e->small_slots * sizeof(SmallSlot)));
     MB_CUDA(cudaMemset(e->d_cache, 0, (uint64_t)e->cache_slots * sizeof(CacheSlot)));
     MB_CUDA(cudaMemset(e->d_cache_ctr, 0, 16));
     e->chunks_seen = 0;
@@ -638,13 +628,10 @@ extern "C" int mbpe_encoder_seed_special_chunks(mbpe_encoder *e, const uint32_t 
 static int ensure_status(mbpe_encoder *e, uint64_t n_tiles) {
     if (n_tiles > e->status_cap) {
         cudaFree(e->d_status);
-        cudaFree(e->d_tile_total);
         e->d_status = nullptr;
-        e->d_tile_total = nullptr;
         e->status_cap = 0;
         const uint64_t cap = n_tiles + n_tiles / 4 + 64;
         MB_CUDA(cudaMalloc(&e->d_status, cap * 8));
-        MB_CUDA(cudaMalloc(&e->d_tile_total, cap * 4));
         e->status_cap = cap;
     }
     return MBPE_OK;
@@ -701,8 +688,9 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
     a.out_cap = out_cap;
     a.d_n_out = (unsigned long long *)d_n_out;
     a.out_off = d_out_off;
-    a.tile_total = e->d_tile_total;
-    a.tile_base = e->d_status;
+    a.stream_base = (const unsigned long long *)d_n_out;
+    a.status = e->d_status;
+    a.ticket = e->d_small;
     a.long_list = e->d_long_list;
     a.n_long = e->d_small + 1;
     a.long_cap = (uint32_t)e->long_cap;
@@ -723,7 +711,7 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
     for (int attempt = 0; attempt < 2; attempt++) {
         MB_CUDA(cudaMemsetAsync(e->d_small, 0, 16, st));
         MB_CUDA(cudaMemsetAsync(d_n_out, 0, 8, st));
-        // Launches of whole tiles: the caches learn from one launch before the next one starts (a cold encoder starts
+        // Launches of whole tiles: the cache learns from one launch before the next one starts (a cold encoder starts
         // with small launches, 1 M chunks, and doubles; a warm one goes straight to large ones), and the ids of launch
         // i+1 continue the stream where launch i ended (*d_n_out).
         uint64_t sb = e->sub_batch_chunks ? e->sub_batch_chunks
@@ -737,7 +725,9 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
             if (!e->sub_batch_chunks) sb = std::min<uint64_t>(ENC_MAX_SUBBATCH, sb * 2);
             const uint64_t n_tiles = (a.chunk1 - a.chunk0 + ET_CHUNKS - 1) / ET_CHUNKS;
             a.n_tiles = (uint32_t)n_tiles;
-            if (a.cache.small) {
+            MB_CUDA(cudaMemsetAsync(e->d_status, 0, n_tiles * 8, st));
+            MB_CUDA(cudaMemsetAsync(e->d_small, 0, 4, st)); // ticket
+            if (a.cache.slots) {
                 k_cache_reset_log<<<1, 1, 0, st>>>(a.cache);
                 e->launches++;
             }
@@ -750,27 +740,23 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
             cudaLaunchAttribute lattr[1];
             lc.attrs = lattr;
             lc.numAttrs = 0;
-            if (a.cache.small && e->l2_window_max) {
-                // the text, boundaries and ids stream through L2; the randomly probed SMALL cache is what should stay
-                const size_t bytes = std::min((size_t)e->small_slots * sizeof(SmallSlot), e->l2_window_max);
+            if (a.cache.slots && e->l2_window_max) {
+                // the text, boundaries and ids stream through L2 once; the randomly probed chunk cache is what should stay
+                const size_t bytes = std::min((size_t)e->cache_slots * sizeof(CacheSlot), e->l2_window_max);
                 lattr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-                lattr[0].val.accessPolicyWindow.base_ptr = e->d_cache_small;
+                lattr[0].val.accessPolicyWindow.base_ptr = e->d_cache;
                 lattr[0].val.accessPolicyWindow.num_bytes = bytes;
                 lattr[0].val.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)e->l2_persist_bytes / (double)bytes);
                 lattr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
                 lattr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
                 lc.numAttrs = 1;
             }
-            // pass 1: id count of every tile; what it had to scan goes into the caches; pass 2 writes at the scanned places
-            MB_CUDA(cudaLaunchKernelEx(&lc, kc.count, a));
+            MB_CUDA(cudaLaunchKernelEx(&lc, kc.kernel, a));
             e->launches++;
-            if (a.cache.small) {
+            if (a.cache.slots) { // what the launch had to scan goes into the cache before the next one starts
                 k_cache_insert<<<e->sms * 2, 256, 0, st>>>(a.cache);
                 e->launches++;
             }
-            k_tile_scan<<<1, 1024, 0, st>>>(e->d_tile_total, a.n_tiles, e->d_status, (unsigned long long *)d_n_out);
-            MB_CUDA(cudaLaunchKernelEx(&lc, kc.write, a));
-            e->launches += 2;
         }
         MB_CUDA(cudaGetLastError());
         MB_CUDA(cudaMemcpyAsync(small, e->d_small, 16, cudaMemcpyDeviceToHost, st));
@@ -808,15 +794,15 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
     if (getenv("MBPE_DEBUG")) {
         uint32_t ctr[4] = {0, 0, 0, 0};
         if (e->d_cache_ctr) MB_CUDA(cudaMemcpy(ctr, e->d_cache_ctr, 16, cudaMemcpyDeviceToHost));
-        fprintf(stderr, "[mbpe] encode: %llu chunks, %u scanned (cache misses), %u long, cache entries small %u of %u, big %u of %u%s\n",
-                (unsigned long long)n_chunks, small[3], small[1], ctr[2], e->small_slots, ctr[1], e->cache_slots,
+        fprintf(stderr, "[mbpe] encode: %llu chunks, %u scanned (cache misses), %u long, cache entries %u of %u%s\n",
+                (unsigned long long)n_chunks, small[3], small[1], ctr[1], e->cache_slots,
                 a.bulk ? ", bulk staging" : ", cooperative staging (unaligned buffers)");
         if (e->d_prof) {
             unsigned long long pr[ENC_PROF_N];
             MB_CUDA(cudaMemcpy(pr, e->d_prof, sizeof pr, cudaMemcpyDeviceToHost));
             MB_CUDA(cudaMemset(e->d_prof, 0, sizeof pr));
             const double t = pr[7] ? (double)pr[7] : 1.0;
-            fprintf(stderr, "[mbpe] encode tiles %llu, cycles per tile: wait data %.0f, probes %.0f, open chunks %.0f, count scan %.0f, "
+            fprintf(stderr, "[mbpe] encode tiles %llu, cycles per tile: wait data %.0f, probes %.0f, scan list %.0f, count scan %.0f, "
                             "look-back+gather %.0f, fetch next %.0f, store %.0f\n",
                     pr[7], pr[0] / t, pr[1] / t, pr[2] / t, pr[3] / t, pr[4] / t, pr[5] / t, pr[6] / t);
         }

@@ -3,30 +3,23 @@
 // Replaces internal_internal_encode / internal_encode + flatten (Tokenizer.h:325-377, :714-717) for chunks of up to
 // ENC_SHORT_MAX bytes; longer chunks are encoded by k_encode_long into a scratch stream and spliced in here.
 //
-// The flat id stream needs every tile's place = the number of ids before it. Round 1 (and the first versions of round 2)
-// resolved that inside ONE pass by decoupled look-back; measured per tile (thread 0's clock, 1024 chunks): ~40 k cycles,
-// of which ~13 k waiting in the look-back for the predecessors' counts (their arrival times jitter by the whole chain of
-// ticket -> boundaries -> text -> probes) and ~7 k in that fetch chain, which cannot be prefetched because tiles must
-// START in ticket order. So the stream is produced in TWO passes that have no dependency between tiles at all:
-//   pass 1 (count)  every tile: probes, open chunks -> the tile's id count                      -> tile_total[t]
-//   k_tile_scan     exclusive scan of tile_total (+ the ids of earlier launches)                -> tile_base[t]
-//   pass 2 (write)  every tile: probes again (the slots are hot in L2), ids gathered in shared memory, stored at
-//                   tile_base[t] as whole lines.
-// With nothing to wait for, tiles are dealt statically (tile = CTA index + k x grid) and the NEXT tile's boundaries and
-// text arrive by bulk asynchronous copy (cp.async.bulk -> the TMA engine, completion on mbarriers, double buffered) while
-// the current one is processed. The text and the boundaries are read twice (2 x 1.8 B per text byte against 4.4 B of
-// ids: +25 % traffic); chunks pass 1 had to scan are in the caches before pass 2 (k_cache_insert runs in between).
-//
-// One tile = THREADS x CPT consecutive chunks, one CTA:
-//   1. fast path, every thread CPT chunks: chunks of <= 15 bytes (nine in ten) are looked up in the SMALL chunk cache,
-//      "chunk bytes -> ids" in 32-byte slots = one DRAM sector, fetched by ONE 256-bit load (LDG.E.256) per probe, all
-//      probes of a thread in flight together.
-//   2. what that leaves open: chunks that may be cached elsewhere (16..31 bytes or more than 4 ids: BIG cache, 64-byte
-//      slots; a taken home slot: the probe sequence goes on) are resolved by their own thread, no barrier; chunks nobody
-//      has seen go to the tile's scan list: the multi-pass scan itself, one warp per chunk when few, one thread per chunk
-//      when many; pass 1 appends them to a log that k_cache_insert folds into the caches.
-//   3. pass 1: block sum. pass 2: block scan, gather, 16-byte stores.
-// Results never depend on the caches: a miss is scanned, and special tokens are matched in the open-chunk path itself.
+// One tile = THREADS x CPT consecutive chunks, one CTA, one pass over the data:
+//   0. thread 0 takes the next tile (ticket: tiles START in stream order, which is what makes the look-back of step 3
+//      deadlock free) and brings its boundaries and its text window into shared memory with two bulk asynchronous copies
+//      (cp.async.bulk -> the TMA engine, completion on mbarriers); the request for the next tile is issued while this
+//      tile's ids are still being stored.
+//   1. every thread, CPT chunks: the chunk's bytes (<= 31) are the key of the chunk cache, "chunk bytes -> ids" in
+//      64-byte slots (key sector, value sector). One 256-bit load (LDG.E.256) fetches the key sector, one 128-bit load
+//      the id count and the first three ids: nineteen chunks in twenty are done after that one round trip, and every lane
+//      runs the same instructions (the measured cost of this kernel is instruction issue and divergence, not bytes:
+//      see DESIGN.md "encode: what was tried").
+//   2. chunks the cache does not hold (cold cache, chunks of 32..64 bytes, a full table) go to the tile's scan list: the
+//      multi-pass scan itself, one warp per chunk when few, one thread per chunk when many; their ids wait in a parking
+//      area (shared memory, overflow in HBM), and a log hands them to k_cache_insert, which runs between launches.
+//   3. block scan of the id counts; warp 0 resolves the tile's place in the stream by decoupled look-back over the
+//      predecessors' counts (128 per round trip) WHILE the other warps gather the tile's ids in shared memory; the ids
+//      leave as 16-byte stores.
+// Results never depend on the cache: a miss is scanned, and special tokens are matched in the scan path itself.
 #pragma once
 #include "lookback.cuh"
 
@@ -73,118 +66,93 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  : "memory");
 }
 
-// one 32-byte slot of the SMALL cache in ONE load (LDG.E.256, new with sm_100): one L1 wavefront per probe instead of two
-__device__ __forceinline__ void ld_slot256(const void *slot, uint4 &k, uint4 &v) {
-    unsigned long long q0, q1, q2, q3;
-    asm("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(q0), "=l"(q1), "=l"(q2), "=l"(q3) : "l"(slot));
-    k = make_uint4((uint32_t)q0, (uint32_t)(q0 >> 32), (uint32_t)q1, (uint32_t)(q1 >> 32));
-    v = make_uint4((uint32_t)q2, (uint32_t)(q2 >> 32), (uint32_t)q3, (uint32_t)(q3 >> 32));
+// one 32-byte sector in ONE load (LDG.E.256, new with sm_100): one L1 wavefront instead of two
+__device__ __forceinline__ void ld_sector256(const void *p, uint64_t &q0, uint64_t &q1, uint64_t &q2, uint64_t &q3) {
+    unsigned long long a0, a1, a2, a3;
+    asm("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a0), "=l"(a1), "=l"(a2), "=l"(a3) : "l"(p));
+    q0 = a0;
+    q1 = a1;
+    q2 = a2;
+    q3 = a3;
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Chunk caches. The multi-pass scan of a chunk is a pure function of its bytes, and text repeats its chunks (Zipf):
-// the encoder keeps "chunk bytes -> ids" in two open-addressed tables in HBM.
-//   SMALL: chunks of <= 15 bytes with <= 4 ids, 32-byte slots {key 16 B, ids 16 B} = one sector per probe.
-//   BIG:   chunks of <= 31 bytes (any id count, > 7 ids in an arena), 64-byte slots.
-// The tile kernel only READS them; chunks it had to scan go to a log, and k_cache_insert adds the log to the tables
-// between launches -- no kernel both reads and writes a table, so there is no publication protocol to get wrong.
-// Results are bit-identical with or without the caches (MBPE_ENCODE_CACHE=0 disables them; tests run both).
+// Chunk cache. The multi-pass scan of a chunk is a pure function of its bytes, and text repeats its chunks (Zipf):
+// the encoder keeps "chunk bytes (<= 31) -> ids" in an open-addressed table in HBM, 64-byte slots = key sector + value
+// sector (more than 7 ids: in an arena); nine chunks in ten are answered by the key sector alone (see CacheSlot). The tile kernel only READS it; chunks it had to scan go to a log, and
+// k_cache_insert adds the log to the table between launches -- no kernel both reads and writes the table, so there is no
+// publication protocol to get wrong. Results are bit-identical with or without the cache (MBPE_ENCODE_CACHE=0 disables
+// it; tests run both).
 // ---------------------------------------------------------------------------------------------------------
-struct SmallSlot { // 32 bytes
-    uint32_t k[4]; // bytes 0..14 little endian, zero padded; k[3] bits 24..27 = length (1..15), bits 28..30 = id count (7: stub);
-                   // k[3] == 0: empty
-    uint32_t v[4]; // the ids
-};
-static_assert(sizeof(SmallSlot) == 32, "one sector per entry");
-constexpr uint32_t SMALL_MAX_LEN = 15, SMALL_MAX_IDS = 4, SMALL_KEY_MASK = 0x0FFFFFFFu;
-constexpr uint32_t SMALL_STUB = 7; // id count of a stub: the chunk has more than 4 ids, they are in the BIG cache
-
-struct CacheSlot { // 64 bytes = two sectors: key, value
-    uint64_t k[4]; // chunk bytes, little endian, zero padded; top byte of k[3] = length (1..31); k[3] == 0: empty
+struct CacheSlot { // 64 bytes = two sectors
+    // Key sector. Chunk bytes little endian, zero padded; top byte of k[3] = length (1..31); k[3] == 0: empty slot.
+    // A SHORT key (<= 16 bytes) fills k[0], k[1] only, and the rest of its sector carries the answer, so that one 32-byte
+    // load resolves the chunk: k[3] bits 0..6 = id count, bit 7 = "ids not inline"; k[2] = up to three ids of 21 bits.
+    uint64_t k[4];
+    // Value sector (read when the ids are not inline: long keys, more than three ids, ids of more than 21 bits).
     uint32_t n;    // number of ids (1..31)
     uint32_t v[7]; // n <= 7: the ids; otherwise v[0] = offset of the ids in the arena
 };
 static_assert(sizeof(CacheSlot) == 64, "two sectors per entry");
 struct CacheLogEntry {
-    uint64_t k[4]; // BIG-table key layout
+    uint64_t k[4];
     uint32_t n;
     uint32_t ids[31];
 };
-constexpr uint32_t CACHE_MAX_LEN = 31, CACHE_INLINE_IDS = 7;
+constexpr uint32_t CACHE_MAX_LEN = 31, CACHE_SHORT_KEY = 16, CACHE_INLINE_IDS = 7, CACHE_KEY_IDS = 3, CACHE_ID_BITS = 21;
+constexpr uint64_t CACHE_NOT_INLINE = 0x80;
 // An entry lives at most this many slots from its home: inserts give up beyond it (the chunk is simply not cached), so
 // lookups may stop there too -- no probe loop depends on the table having a free slot.
 constexpr uint32_t CACHE_MAX_PROBES = 64;
 
 struct ChunkCache {
-    SmallSlot *small; // nullptr = caches disabled
-    uint32_t small_shift; // slot = hash >> small_shift
-    uint32_t small_mask;
-    CacheSlot *slots;
+    CacheSlot *slots;    // nullptr = cache disabled
+    uint32_t shift;      // home slot = hash >> shift (the top bits of a multiplicative hash are the good ones)
     uint32_t mask;       // slots - 1
     CacheLogEntry *log;  // chunks the current launch had to scan
     uint32_t *log_count;
     uint32_t log_cap;
-    uint32_t *used;      // [0] occupied BIG slots, [1] occupied SMALL slots (learning stops at half full)
-    uint32_t *arena;     // ids of BIG entries with more than CACHE_INLINE_IDS ids
+    uint32_t *used;      // occupied slots (learning stops at half full)
+    uint32_t *arena;     // ids of entries with more than CACHE_INLINE_IDS ids
     uint32_t *arena_used;
     uint32_t arena_cap;
 };
 
-__host__ __device__ __forceinline__ uint32_t small_hash(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
-    const uint64_t lo = ((uint64_t)w1 << 32) | w0, hi = ((uint64_t)w3 << 32) | w2;
-    const uint64_t m = hi * 0x9E3779B97F4A7C15ull;
-    const uint64_t x = lo ^ ((m >> 32) | (m << 32));
-    return (uint32_t)((x * 0xD6E8FEB86659FD93ull) >> 32); // callers use the TOP bits: they depend on every key bit
+// Two multiplies for the chunks of <= 16 bytes (k2 == 0, k3 == length only), two more for the longer ones. The length
+// is not hashed ("a" and "a\0" share a home slot; the key compare tells them apart).
+__host__ __device__ __forceinline__ uint64_t cache_hash_lo(uint64_t k0, uint64_t k1) {
+    const uint64_t m = k1 * 0x9E3779B97F4A7C15ull;
+    return k0 ^ ((m >> 32) | (m << 32));
 }
+__host__ __device__ __forceinline__ uint64_t cache_hash_hi(uint64_t k2, uint64_t k3_bytes) { // k3 without its length byte
+    const uint64_t m = k2 * 0xC2B2AE3D27D4EB4Full;
+    return ((m >> 32) | (m << 32)) + k3_bytes * 0x165667B19E3779F9ull;
+}
+__host__ __device__ __forceinline__ uint32_t cache_hash_fin(uint64_t x) { return (uint32_t)((x * 0xD6E8FEB86659FD93ull) >> 32); }
 __host__ __device__ __forceinline__ uint32_t cache_hash(uint64_t k0, uint64_t k1, uint64_t k2, uint64_t k3) {
-    uint64_t h = (k0 ^ (k1 * 0x9E3779B97F4A7C15ull)) * 0xff51afd7ed558ccdULL;
-    h ^= (k2 * 0xc2b2ae3d27d4eb4fULL) ^ (k3 * 0x165667b19e3779f9ULL);
-    h ^= h >> 32;
-    h *= 0xc4ceb9fe1a85ec53ULL;
-    return (uint32_t)(h >> 32);
+    uint64_t x = cache_hash_lo(k0, k1);
+    const uint64_t b3 = k3 & 0x00FFFFFFFFFFFFFFull;
+    if (k2 | b3) x ^= cache_hash_hi(k2, b3);
+    return cache_hash_fin(x);
 }
 
 __global__ void k_cache_insert(ChunkCache cc) {
     const uint32_t n = min(*cc.log_count, cc.log_cap);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const CacheLogEntry &e = cc.log[i];
-        const uint64_t k0 = e.k[0], k1 = e.k[1], k2 = e.k[2], k3 = e.k[3];
-        const uint32_t en = e.n, len = (uint32_t)(k3 >> 56);
-        // SMALL entry: the ids themselves (<= 4), or -- for a short chunk with more ids -- a stub (id count 7) that says
-        // "look in BIG": the tile kernel's fast path then knows the chunk is cached without probing BIG for every miss
-        if (len <= SMALL_MAX_LEN) {
-            const bool stub = en > SMALL_MAX_IDS;
-            if (*((volatile uint32_t *)(cc.used + 1)) * 2 <= cc.small_mask) { // (half full: stop learning)
-                const uint32_t w0 = (uint32_t)k0, w1 = (uint32_t)(k0 >> 32), w2 = (uint32_t)k1;
-                const uint32_t w3 = (uint32_t)(k1 >> 32) | (len << 24); // byte 15 is free: len <= 15
-                uint32_t h = small_hash(w0, w1, w2, w3) >> cc.small_shift;
-                for (uint32_t probes = 0; probes < CACHE_MAX_PROBES; probes++) {
-                    SmallSlot *s = &cc.small[h];
-                    uint32_t cur = *((volatile uint32_t *)&s->k[3]);
-                    if (cur == 0) {
-                        cur = atomicCAS(&s->k[3], 0u, w3 | ((stub ? SMALL_STUB : en) << 28));
-                        if (cur == 0) { // claimed: k[3] is the claim word, the rest is written by the winner only
-                            s->k[0] = w0;
-                            s->k[1] = w1;
-                            s->k[2] = w2;
-                            for (uint32_t q = 0; q < SMALL_MAX_IDS; q++) s->v[q] = (!stub && q < en) ? e.ids[q] : 0u;
-                            atomicAdd(cc.used + 1, 1u);
-                            break;
-                        }
-                    }
-                    // Same key: already there (the log holds duplicates of hot chunks). Words of a slot claimed in THIS launch
-                    // may not be visible yet; then the duplicate takes a second slot -- harmless, both slots hold the same ids
-                    // and a reader uses the first one it finds.
-                    if ((cur & SMALL_KEY_MASK) == w3 && *((volatile uint32_t *)&s->k[0]) == w0 &&
-                        *((volatile uint32_t *)&s->k[1]) == w1 && *((volatile uint32_t *)&s->k[2]) == w2)
-                        break;
-                    h = (h + 1) & cc.small_mask;
-                }
-            }
-            if (!stub) continue;
+        const uint64_t k0 = e.k[0], k1 = e.k[1];
+        uint64_t k2 = e.k[2], k3 = e.k[3];
+        const uint32_t en = e.n;
+        if (*((volatile uint32_t *)cc.used) * 2 > cc.mask) return; // half full: stop learning
+        uint32_t h = cache_hash(k0, k1, k2, k3) >> cc.shift;
+        const bool short_key = (k3 >> 56) <= CACHE_SHORT_KEY;
+        if (short_key) { // the answer rides in the key sector (a pure function of the key, like the key words themselves)
+            bool inline_ids = en <= CACHE_KEY_IDS;
+            for (uint32_t q = 0; q < en && inline_ids; q++) inline_ids = e.ids[q] < (1u << CACHE_ID_BITS);
+            k3 |= en | (inline_ids ? 0 : CACHE_NOT_INLINE);
+            if (inline_ids)
+                for (uint32_t q = 0; q < en; q++) k2 |= (uint64_t)e.ids[q] << (CACHE_ID_BITS * q);
         }
-        if (*((volatile uint32_t *)cc.used) * 2 > cc.mask) continue; // half full: stop learning
-        uint32_t h = cache_hash(k0, k1, k2, k3) & cc.mask;
         for (uint32_t probes = 0; probes < CACHE_MAX_PROBES; probes++) {
             unsigned long long *claim = reinterpret_cast<unsigned long long *>(&cc.slots[h].k[3]);
             unsigned long long cur = *((volatile unsigned long long *)claim);
@@ -195,7 +163,7 @@ __global__ void k_cache_insert(ChunkCache cc) {
                     if (aoff + en > cc.arena_cap) break;
                 }
                 cur = atomicCAS(claim, 0ull, (unsigned long long)k3);
-                if (cur == 0) {
+                if (cur == 0) { // claimed: k[3] is the claim word, the rest is written by the winner only
                     cc.slots[h].k[0] = k0;
                     cc.slots[h].k[1] = k1;
                     cc.slots[h].k[2] = k2;
@@ -210,6 +178,9 @@ __global__ void k_cache_insert(ChunkCache cc) {
                     break;
                 }
             }
+            // Same key: already there (the log holds duplicates of hot chunks). Words of a slot claimed in THIS launch
+            // may not be visible yet; then the duplicate takes a second slot -- harmless, both slots hold the same ids
+            // and a reader uses the first one it finds.
             if (cur == k3 && *((volatile uint64_t *)&cc.slots[h].k[0]) == k0 &&
                 *((volatile uint64_t *)&cc.slots[h].k[1]) == k1 && *((volatile uint64_t *)&cc.slots[h].k[2]) == k2)
                 break;
@@ -259,8 +230,8 @@ struct EncArgs {
     uint64_t out_cap;
     unsigned long long *d_n_out;
     unsigned long long *out_off; // optional per-chunk token offsets (n_chunks + 1)
-    uint32_t *tile_total;        // pass 1 out: ids of every tile of this launch
-    const unsigned long long *tile_base; // pass 2 in: place of every tile in the stream (k_tile_scan)
+    unsigned long long *status;  // look-back words, one per tile, zeroed
+    uint32_t *ticket;            // zeroed
     uint32_t n_tiles;
     const uint32_t *scratch_a;   // long-chunk tokens / counts; null = no long pre-pass was run (optimistic launch)
     const uint32_t *scratch_b;
@@ -273,41 +244,48 @@ struct EncArgs {
     uint32_t bulk;               // bytes / off are 16-byte aligned: stage with cp.async.bulk
     uint32_t out_aligned;        // out is 16-byte aligned: ids leave as 16-byte stores
     unsigned long long *prof;    // optional: SM cycles per phase summed over CTAs (thread 0's clock), see ENC_PROF_*
-    uint32_t ablate;             // MBPE_ENC_ABLATE (profiling only, WRONG results): 2 no cache probe (every short chunk
-                                 // "hits" with two fake ids), 4 no id stores, 8 open chunks are not resolved (one fake id)
+    uint32_t ablate;             // MBPE_ENC_ABLATE (profiling only, WRONG results): 1 no look-back wait, 2 no cache probe
+                                 // (every short chunk "hits" with two fake ids), 4 no id stores
 };
 
-// EncArgs::prof[pass * 8 + i]: cycles thread 0 spent ... 0 waiting for the tile's data, 1 cache probes + cached open chunks
-// (+ barrier), 2 scan list, 3 block sum / scan (+ barrier), 4 gather (+ barrier), 5 issuing the prefetch, 6 storing the
-// ids, 7 tiles processed
-constexpr int ENC_PROF_N = 16;
+// EncArgs::prof[i]: cycles thread 0 spent ... 0 waiting for the tile's data, 1 cache probes (+ barrier), 2 scan list,
+// 3 count scan (+ barrier), 4 look-back / gather (+ barrier), 5 fetching the next tile (ticket + two bulk copies),
+// 6 storing the ids, 7 tiles processed
+constexpr int ENC_PROF_N = 8;
 constexpr uint32_t TILE_NONE = 0xFFFFFFFFu;
 constexpr uint64_t ENC_MAX_SUBBATCH = 1ull << 26; // chunks per launch at most (tile ids and look-back words are 32-bit safe)
-// Parking area of a tile = ids of its open chunks until they are written: the first PARK words live in shared memory, the
-// rest in the CTA's spill block in HBM (one index space; every id covers at least one byte of text, so a tile of
-// ENC_SHORT_MAX-byte chunks at most needs TILE * ENC_SHORT_MAX words: it always fits, nothing is ever encoded twice).
 constexpr uint32_t ET_WARP_SCAN_MAX = 48;     // up to this many scans per tile run one warp per chunk
+// what the tile knows about a chunk after the probes (EncSmemT::rec)
+constexpr uint32_t CK_REGS = 0;   // ids (<= CACHE_KEY_IDS) in the record itself, or no ids at all
+constexpr uint32_t CK_SLOT = 1;   // cached with more ids: the value sector of its slot is fetched again when writing
+constexpr uint32_t CK_PARKED = 2; // scanned by the tile: ids in the parking area
+constexpr uint32_t CK_LONG = 3;   // longer than ENC_SHORT_MAX: ids in the long-chunk scratch stream
 
+// Parking area of a tile = ids of its scanned chunks until they are written: the first PARK words live in shared memory,
+// the rest in the CTA's spill block in HBM (one index space; every id covers at least one byte of text, so a tile of
+// ENC_SHORT_MAX-byte chunks at most needs TILE * ENC_SHORT_MAX words: it always fits, nothing is ever encoded twice).
 template <int THREADS, int CPT>
 struct EncSmemT {
     static constexpr int TILE = THREADS * CPT;
     static constexpr int TEXT_CAP = TILE * 10;  // staged text bytes per tile (average chunk ~5 bytes); wider tiles read HBM
     static constexpr int STAGE = TILE * 5 / 2;  // ids gathered per tile (average ~2.1 per chunk); more: direct stores
-    static constexpr int PARK = TILE;           // parking words in shared memory (warm caches park a few dozen ids per tile)
+    static constexpr int PARK = TILE / 2;       // parking words in shared memory (a warm cache parks a few dozen ids per tile)
     static constexpr int SPILL = TILE * 64;     // parking words per CTA in HBM (EncArgs::spill): the worst case
-    alignas(128) uint32_t off_buf[2][TILE + 8];          // double buffered: the next tile's data arrives during this tile
-    alignas(128) uint32_t text_buf[2][TEXT_CAP / 4 + 16]; // + halo: key assembly reads whole words past the chunk's end
+    alignas(128) uint32_t off[TILE + 8];
+    alignas(128) uint32_t text[TEXT_CAP / 4 + 16]; // + halo: key assembly reads whole words past the chunk's end
     alignas(16) uint32_t stage[STAGE + 4];
+    alignas(16) uint4 rec[TILE];   // per chunk: x = id count | CK_* kind << 30; CK_REGS: y, z = the ids (three times 21 bits); CK_SLOT:
+                                   // y = cache slot; CK_PARKED: y = start in the parking area; CK_LONG: y = text offset
+    alignas(16) uint32_t cnt[TILE]; // per chunk: id count, then (step 3, in place) its offset within its warp's segment of the tile
     uint32_t park[PARK];
-    uint32_t meta[TILE];       // per open chunk (index = its place on the open list): start in park (20 bits) | id count << 20
-    uint16_t open_k[TILE];     // open list (chunks nobody has seen before): chunk index within the tile
+    uint16_t open_k[TILE];     // scan list: chunk index within the tile
+    uint4 len_mask[17];        // len_mask[l] keeps the first l bytes of 16
     uint32_t warp_scratch[THREADS / 32][32];
     uint32_t warp_sum[THREADS / 32];
-    alignas(8) uint64_t bar_off[2], bar_txt[2]; // mbarriers per buffer: boundaries landed (thread 0 waits), text landed (all wait)
-    const uint32_t *off;       // the current tile's buffers (set by thread 0 before the tile's first barrier; helpers that run
-    const uint32_t *text;      // after a barrier read them)
-    uint32_t a0[2], staged[2], n_open, park_used;
-    unsigned long long prof[8];
+    alignas(8) uint64_t bar_off, bar_tile; // mbarriers: boundaries landed (thread 0 only waits), tile ready (all wait)
+    unsigned long long base;
+    uint32_t tile, a0, staged, n_open, park_used;
+    unsigned long long prof[ENC_PROF_N];
 };
 
 template <class SM>
@@ -346,7 +324,7 @@ __device__ __forceinline__ uint32_t scan_chunk_warp(const EncTable &tab, uint32_
     return len;
 }
 
-// BIG-table key of chunk [o, o + len), len <= 31: bytes little endian, zero padded, length in the top byte
+// cache key of chunk [o, o + len), len <= 31: bytes little endian, zero padded, length in the top byte
 template <class SM>
 __device__ __forceinline__ void big_key(const EncArgs &a, const SM &sm, bool staged, uint32_t a0, uint32_t o, uint32_t len,
                                         uint64_t *key) {
@@ -369,11 +347,11 @@ __device__ __forceinline__ void big_key(const EncArgs &a, const SM &sm, bool sta
     key[3] |= (uint64_t)len << 56;
 }
 
-// a chunk the scan had to encode goes to the log that k_cache_insert folds into the caches after the launch
+// a chunk the scan had to encode goes to the log that k_cache_insert folds into the cache after the launch
 template <class SM>
 __device__ __forceinline__ void log_scanned(const EncArgs &a, const SM &sm, bool staged, uint32_t a0, uint32_t o,
                                             uint32_t len, const uint32_t *ids, uint32_t n) {
-    if (!a.cache.small || len > CACHE_MAX_LEN) return;
+    if (!a.cache.slots || len > CACHE_MAX_LEN) return;
     const uint32_t li = atomicAdd(a.cache.log_count, 1u);
     if (li >= a.cache.log_cap) return;
     CacheLogEntry &e = a.cache.log[li];
@@ -398,12 +376,20 @@ template <class SM>
 __device__ __forceinline__ uint32_t park_load(const EncArgs &a, const SM &sm, uint32_t at) {
     return at < (uint32_t)SM::PARK ? sm.park[at] : __ldcg(a.spill + (size_t)blockIdx.x * SM::SPILL + (at - SM::PARK));
 }
-// result of an open chunk: its ids go to the parking area, meta = start | n << 20
+// result of a scanned chunk: its ids go to the parking area; returns start | n << 20
 template <class SM>
 __device__ __forceinline__ uint32_t park_ids(const EncArgs &a, SM &sm, const uint32_t *ids, uint32_t n) {
     const uint32_t at = atomicAdd(&sm.park_used, n);
     for (uint32_t i = 0; i < n; i++) park_store(a, sm, at + i, ids[i]);
     return at | (n << 20);
+}
+
+// a scanned chunk's record: id count and where its ids are parked (meta = start | n << 20, see park_ids)
+template <class SM>
+__device__ __forceinline__ void set_parked(SM &sm, uint32_t k, uint32_t meta) {
+    sm.rec[k].x = (meta >> 20) | (CK_PARKED << 30);
+    sm.rec[k].y = meta & 0xFFFFF;
+    sm.cnt[k] = meta >> 20;
 }
 
 // the multi-pass scan of one chunk (<= ENC_SHORT_MAX bytes) by ONE thread (special tokens first); returns meta
@@ -440,8 +426,8 @@ __device__ __forceinline__ void scan_by_warp(const EncArgs &a, SM &sm, uint32_t 
     if (lane == 0) start = atomicAdd(&sm.park_used, mn);
     start = __shfl_sync(0xffffffffu, start, 0);
     if (lane < mn) park_store(a, sm, start + lane, tok);
-    if (lane == 0) sm.meta[q] = start | (mn << 20);
-    if (log && a.cache.small && mlen <= CACHE_MAX_LEN && sid == ENC_NONE) { // teach the caches
+    if (lane == 0) set_parked(sm, k, start | (mn << 20));
+    if (log && a.cache.slots && mlen <= CACHE_MAX_LEN && sid == ENC_NONE) { // teach the cache
         uint32_t li = 0;
         if (lane == 0) li = atomicAdd(a.cache.log_count, 1u);
         li = __shfl_sync(0xffffffffu, li, 0);
@@ -469,74 +455,10 @@ __device__ __forceinline__ void scan_by_warp(const EncArgs &a, SM &sm, uint32_t 
 // fetched together). Out of line so that its registers are not charged to the fast path.
 // hint: 0 = whole SMALL probe sequence (home slot not seen), 1 = home slot taken by another chunk (continue behind it),
 //       2 = stub / long chunk: BIG only.
-// Returns the id count (0: in no cache -- the scan has to encode it); <= 4 ids come back in v, more are parked (v.x = start).
-template <class SM>
-__device__ __noinline__ uint32_t resolve_cached(const EncArgs &a, SM &sm, uint32_t a0, bool staged, uint32_t o, uint32_t len, uint32_t hint,
-                                                uint4 &v) {
-    if (a.sp.n) {
-        const uint32_t sid = special_match(a.sp, len, [&](uint32_t i) { return tile_byte(a, sm, staged, a0, o + i); });
-        if (sid != ENC_NONE) {
-            v.x = sid;
-            return 1;
-        }
-    }
-    if (!a.cache.small || len > CACHE_MAX_LEN) return 0;
-    uint64_t key[4];
-    big_key(a, sm, staged, a0, o, len, key);
-    if (len <= SMALL_MAX_LEN && hint != 2) {
-        const uint32_t w0 = (uint32_t)key[0], w1 = (uint32_t)(key[0] >> 32), w2 = (uint32_t)key[1];
-        const uint32_t w3 = (uint32_t)(key[1] >> 32) | (len << 24);
-        uint32_t h = ((small_hash(w0, w1, w2, w3) >> a.cache.small_shift) + (hint == 1 ? 1u : 0u)) & a.cache.small_mask;
-        bool stub = false;
-        for (uint32_t probes = hint == 1 ? 1u : 0u; probes < CACHE_MAX_PROBES; probes++) {
-            uint4 kq, vv;
-            ld_slot256(&a.cache.small[h], kq, vv);
-            if (kq.w == 0) return 0; // not cached at all
-            if ((kq.w & SMALL_KEY_MASK) == w3 && kq.x == w0 && kq.y == w1 && kq.z == w2) {
-                if ((kq.w >> 28) <= SMALL_MAX_IDS) {
-                    v = vv;
-                    return kq.w >> 28;
-                }
-                stub = true;
-                break;
-            }
-            h = (h + 1) & a.cache.small_mask;
-        }
-        if (!stub) return 0;
-    }
-    uint32_t h = cache_hash(key[0], key[1], key[2], key[3]) & a.cache.mask;
-    for (uint32_t probes = 0; probes < CACHE_MAX_PROBES; probes++) {
-        uint4 k0, k1, v0, v1; // the whole 64-byte slot: two 32-byte loads in flight together
-        ld_slot256(&a.cache.slots[h], k0, k1);
-        ld_slot256(reinterpret_cast<const uint8_t *>(&a.cache.slots[h]) + 32, v0, v1);
-        if ((k1.z | k1.w) == 0) return 0; // k[3] == 0: empty
-        if (k0.x == (uint32_t)key[0] && k0.y == (uint32_t)(key[0] >> 32) && k0.z == (uint32_t)key[1] &&
-            k0.w == (uint32_t)(key[1] >> 32) && k1.x == (uint32_t)key[2] && k1.y == (uint32_t)(key[2] >> 32) &&
-            k1.z == (uint32_t)key[3] && k1.w == (uint32_t)(key[3] >> 32)) {
-            const uint32_t n = v0.x;
-            if (n <= 4) {
-                v = make_uint4(v0.y, v0.z, v0.w, v1.x);
-                return n;
-            }
-            const uint32_t at = atomicAdd(&sm.park_used, n);
-            v.x = at;
-            if (n <= CACHE_INLINE_IDS) {
-                const uint32_t ids[CACHE_INLINE_IDS] = {v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-                for (uint32_t i = 0; i < n; i++) park_store(a, sm, at + i, ids[i]);
-            } else {
-                const uint32_t *src = a.cache.arena + v0.y;
-                for (uint32_t i = 0; i < n; i++) park_store(a, sm, at + i, __ldg(&src[i]));
-            }
-            return n;
-        }
-        h = (h + 1) & a.cache.mask;
-    }
-    return 0;
-}
 
-// The chunks nobody has seen before (the tile's scan list), by all threads of the CTA; the caller's barrier follows.
-// Few (warm caches): latency matters -- one WARP per chunk, lanes = positions, one lookup latency per pass. Many (cold
-// caches): throughput matters -- one THREAD per chunk; also for chunks of 33..64 bytes.
+// The chunks the cache does not hold (the tile's scan list), by all threads of the CTA; the caller's barrier follows.
+// Few (warm cache): latency matters -- one WARP per chunk, lanes = positions, one lookup latency per pass. Many (cold
+// cache): throughput matters -- one THREAD per chunk; also for chunks of 33..64 bytes.
 template <int THREADS, class SM>
 __device__ __noinline__ void scan_open_chunks(const EncArgs &a, SM &sm, uint32_t a0, bool staged, uint32_t n_scan, bool log) {
     constexpr int NW = THREADS / 32;
@@ -545,14 +467,14 @@ __device__ __noinline__ void scan_open_chunks(const EncArgs &a, SM &sm, uint32_t
     if (n_scan > ET_WARP_SCAN_MAX) {
         for (uint32_t s = tid; s < n_scan; s += THREADS) {
             const uint32_t q = s, k = sm.open_k[q], so = sm.off[k];
-            sm.meta[q] = scan_serial(a, sm, a0, staged, so, sm.off[k + 1] - so, log);
+            set_parked(sm, k, scan_serial(a, sm, a0, staged, so, sm.off[k + 1] - so, log));
         }
         return;
     }
     for (uint32_t s = warp; s < n_scan; s += NW) {
         const uint32_t q = s, k = sm.open_k[q];
         if (sm.off[k + 1] - sm.off[k] > 32) { // 33..64 bytes do not fit the lanes
-            if ((tid & 31) == 0) sm.meta[q] = scan_serial(a, sm, a0, staged, sm.off[k], sm.off[k + 1] - sm.off[k], log);
+            if ((tid & 31) == 0) set_parked(sm, k, scan_serial(a, sm, a0, staged, sm.off[k], sm.off[k + 1] - sm.off[k], log));
             __syncwarp();
             continue;
         }
@@ -560,86 +482,118 @@ __device__ __noinline__ void scan_open_chunks(const EncArgs &a, SM &sm, uint32_t
     }
 }
 
-// one chunk's ids -> dst[0 .. n) (shared-memory gather buffer, or the stream itself for oversized tiles).
-// openq: the chunk's place on the open list, or TILE_NONE: its ids are in v (<= 4) or parked at v.x (more)
+
+// one chunk's ids -> dst[0 .. n) (shared-memory gather buffer, or the stream itself for oversized tiles); r = its record
 template <class SM>
-__device__ __forceinline__ void emit_chunk(const EncArgs &a, SM &sm, uint32_t n, uint32_t openq, uint32_t o0, uint32_t o1, uint4 v,
-                                           uint32_t *dst, uint64_t room) {
-    if (n == 0) return;
+__device__ __forceinline__ void emit_chunk(const EncArgs &a, SM &sm, const uint4 r, uint32_t *dst, uint64_t room) {
+    const uint32_t n = r.x & 0x3FFFFFFFu, kind = r.x >> 30;
     if (n > room) {
         *a.overflow = 1;
         return;
     }
-    if (openq == TILE_NONE && o1 - o0 > ENC_SHORT_MAX) {
-        for (uint32_t i = 0; i < n; i++) dst[i] = a.scratch_a[o0 + i];
-    } else if (openq == TILE_NONE && n <= 4) {
-        dst[0] = v.x;
-        if (n > 1) dst[1] = v.y;
-        if (n > 2) dst[2] = v.z;
-        if (n > 3) dst[3] = v.w;
+    if (kind == CK_REGS) { // y, z = the key sector's id word: three ids of 21 bits
+        dst[0] = r.y & 0x1FFFFFu;
+        if (n > 1) dst[1] = __funnelshift_r(r.y, r.z, CACHE_ID_BITS) & 0x1FFFFFu;
+        if (n > 2) dst[2] = r.z >> (2 * CACHE_ID_BITS - 32);
+    } else if (kind == CK_SLOT) {
+        uint64_t q0, q1, q2, q3; // n, v[0 .. 6]
+        ld_sector256(reinterpret_cast<const uint8_t *>(&a.cache.slots[r.y]) + 32, q0, q1, q2, q3);
+        if (n <= CACHE_INLINE_IDS) {
+            dst[0] = (uint32_t)(q0 >> 32);
+            if (n > 1) dst[1] = (uint32_t)q1;
+            if (n > 2) dst[2] = (uint32_t)(q1 >> 32);
+            if (n > 3) dst[3] = (uint32_t)q2;
+            if (n > 4) dst[4] = (uint32_t)(q2 >> 32);
+            if (n > 5) dst[5] = (uint32_t)q3;
+            if (n > 6) dst[6] = (uint32_t)(q3 >> 32);
+        } else {
+            const uint32_t *src = a.cache.arena + (uint32_t)(q0 >> 32);
+#pragma unroll 1
+            for (uint32_t i = 0; i < n; i++) dst[i] = __ldg(&src[i]);
+        }
+    } else if (kind == CK_PARKED) {
+#pragma unroll 1
+        for (uint32_t i = 0; i < n; i++) dst[i] = park_load(a, sm, r.y + i);
     } else {
-        const uint32_t start = openq == TILE_NONE ? v.x : (sm.meta[openq] & 0xFFFFF);
-        for (uint32_t i = 0; i < n; i++) dst[i] = park_load(a, sm, start + i);
+#pragma unroll 1
+        for (uint32_t i = 0; i < n; i++) dst[i] = a.scratch_a[r.y + i];
     }
 }
 
-// thread 0, first half of a tile fetch: the tile's boundaries on their way into off_buf[buf]
+// thread 0: ticket, then the tile's boundaries and text window into shared memory by bulk copies.
+// Publishes sm.tile / sm.a0 / sm.staged and completes sm.bar_tile when everything has landed.
 template <class SM>
-__device__ __forceinline__ void fetch_off(const EncArgs &a, SM &sm, uint32_t tile, uint32_t buf, uint64_t policy) {
-    const uint64_t c0 = a.chunk0 + (uint64_t)tile * SM::TILE;
+__device__ __forceinline__ void fetch_tile_bulk(const EncArgs &a, SM &sm, uint32_t &off_parity, uint64_t policy) {
+    const uint32_t t = atomicAdd(a.ticket, 1u); // tiles start in order: look-back cannot deadlock
+    if (t >= a.n_tiles) {
+        sm.tile = TILE_NONE;
+        mbar_arrive(&sm.bar_tile);
+        return;
+    }
+    const uint64_t c0 = a.chunk0 + (uint64_t)t * SM::TILE;
     const uint32_t nc = (uint32_t)min((uint64_t)SM::TILE, a.chunk1 - c0);
     const uint32_t nw = nc + 1, nb = nw & ~3u; // whole 16-byte vectors by bulk copy, the last <= 3 words by hand
     if (nb) {
-        mbar_arrive_expect_tx(&sm.bar_off[buf], nb * 4);
-        bulk_g2s(sm.off_buf[buf], a.off + c0, nb * 4, &sm.bar_off[buf], policy);
+        mbar_arrive_expect_tx(&sm.bar_off, nb * 4);
+        bulk_g2s(sm.off, a.off + c0, nb * 4, &sm.bar_off, policy);
     } else {
-        mbar_arrive(&sm.bar_off[buf]);
+        mbar_arrive(&sm.bar_off);
     }
-    for (uint32_t i = nb; i < nw; i++) sm.off_buf[buf][i] = __ldg(&a.off[c0 + i]);
-}
-// second half, once the boundaries have landed: the text window into text_buf[buf]; completes bar_txt[buf]
-template <class SM>
-__device__ __forceinline__ void fetch_text(const EncArgs &a, SM &sm, uint32_t tile, uint32_t buf, uint32_t off_parity, uint64_t policy) {
-    mbar_wait(&sm.bar_off[buf], off_parity);
-    const uint64_t c0 = a.chunk0 + (uint64_t)tile * SM::TILE;
-    const uint32_t nc = (uint32_t)min((uint64_t)SM::TILE, a.chunk1 - c0);
-    const uint32_t b0 = sm.off_buf[buf][0], b1 = sm.off_buf[buf][nc];
+    for (uint32_t i = nb; i < nw; i++) sm.off[i] = __ldg(&a.off[c0 + i]);
+    mbar_wait(&sm.bar_off, off_parity);
+    off_parity ^= 1;
+    const uint32_t b0 = sm.off[0], b1 = sm.off[nc];
     const uint32_t a0 = b0 & ~15u; // 16-byte aligned window start
     const uint32_t span = b1 - a0;
     const bool staged = span <= (uint32_t)SM::TEXT_CAP;
-    sm.a0[buf] = a0;
-    sm.staged[buf] = staged;
+    sm.tile = t;
+    sm.a0 = a0;
+    sm.staged = staged;
     if (staged) {
         // whole vectors that lie inside the buffer by bulk copy, the last (< 16) bytes of the buffer by hand
         const uint64_t avail = (a.n_bytes_total - a0) & ~15ull;
         const uint32_t full = (uint32_t)min((uint64_t)((span + 15) & ~15u), avail);
-        for (uint32_t g = a0 + full; g < b1; g++) reinterpret_cast<uint8_t *>(sm.text_buf[buf])[g - a0] = __ldg(&a.bytes[g]);
+        for (uint32_t g = a0 + full; g < b1; g++) reinterpret_cast<uint8_t *>(sm.text)[g - a0] = __ldg(&a.bytes[g]);
         if (full) {
-            mbar_arrive_expect_tx(&sm.bar_txt[buf], full);
-            bulk_g2s(sm.text_buf[buf], a.bytes + a0, full, &sm.bar_txt[buf], policy);
+            mbar_arrive_expect_tx(&sm.bar_tile, full);
+            bulk_g2s(sm.text, a.bytes + a0, full, &sm.bar_tile, policy);
             return;
         }
     }
-    mbar_arrive(&sm.bar_txt[buf]);
+    mbar_arrive(&sm.bar_tile);
 }
 
-// PASS 1: count (tile_total). PASS 2: write (ids at tile_base).
-template <int THREADS, int CPT, int MIN_CTAS, int PASS>
-__global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArgs a) {
+// PIF = cache probes a thread keeps in flight together (its CPT chunks are probed in groups of PIF).
+// Chunk <-> thread: steps 1 and 3b (probe, gather) take chunk j * THREADS + tid for j < CPT -- neighbouring lanes work on
+// neighbouring chunks, so their shared-memory traffic is conflict free and their ids land side by side; step 3a (the count
+// scan) takes CPT consecutive chunks per thread. Nothing about a chunk is kept in registers between the steps: it is all
+// in the chunk's record in shared memory, which is what lets the probe loop run at 64 registers without spilling.
+template <int THREADS, int CPT, int MIN_CTAS, int PIF>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const __grid_constant__ EncArgs a) {
     using SM = EncSmemT<THREADS, CPT>;
     constexpr int TILE = SM::TILE, NW = THREADS / 32;
+    static_assert(CPT % PIF == 0 && NW % CPT == 0 && (CPT == 2 || CPT % 4 == 0), "see the chunk <-> thread mapping");
+    constexpr int SEG_PER_J = NW / CPT; // warp segments of the count scan covered by one round of THREADS chunks
     extern __shared__ __align__(128) unsigned char enc_smem_raw[];
     SM &sm = *reinterpret_cast<SM *>(enc_smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool bulk = a.bulk != 0;
-    if (tid == 0) {
-        for (int b = 0; b < 2; b++) {
-            mbar_init(&sm.bar_off[b], 1);
-            mbar_init(&sm.bar_txt[b], 1);
+    if (tid < 17) { // len_mask[l]: ones over the first l bytes
+        uint32_t m[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int nb = (int)tid - 4 * q;
+            m[q] = nb >= 4 ? 0xFFFFFFFFu : nb <= 0 ? 0u : ((1u << (8 * nb)) - 1);
         }
+        sm.len_mask[tid] = make_uint4(m[0], m[1], m[2], m[3]);
+    }
+    if (tid == 0) {
+        mbar_init(&sm.bar_off, 1);
+        mbar_init(&sm.bar_tile, 1);
         mbar_init_fence();
-        sm.n_open = sm.park_used = 0;
-        for (int i = 0; i < 8; i++) sm.prof[i] = 0;
+        sm.n_open = 0;
+        sm.park_used = 0;
+        for (int i = 0; i < ENC_PROF_N; i++) sm.prof[i] = 0;
     }
     __syncthreads();
     long long t_lap = clock64();
@@ -650,306 +604,279 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const EncArg
             t_lap = t;
         }
     };
-    const uint64_t policy = l2_evict_first_policy();
-    // tiles of this CTA: blockIdx.x, + gridDim.x, ... (no tile depends on another one)
-    if (bulk && tid == 0 && blockIdx.x < a.n_tiles) {
-        fetch_off(a, sm, blockIdx.x, 0, policy);
-        fetch_text(a, sm, blockIdx.x, 0, 0, policy);
-        if (blockIdx.x + gridDim.x < a.n_tiles) fetch_off(a, sm, blockIdx.x + gridDim.x, 1, policy);
+    uint32_t tile_parity = 0, off_parity = 0;
+    uint64_t policy = 0;
+    if (bulk && tid == 0) {
+        policy = l2_evict_first_policy();
+        fetch_tile_bulk(a, sm, off_parity, policy);
     }
-    uint32_t it = 0;
-    for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, it++) {
-        const uint32_t buf = it & 1, par = (it >> 1) & 1; // buffer of this tile, and how often it has been used before (parity)
-        const uint64_t c0 = a.chunk0 + (uint64_t)tile * TILE;
-        const uint32_t nc = (uint32_t)min((uint64_t)TILE, a.chunk1 - c0);
+    for (;;) {
         // ---- 0. the tile's boundaries and text in shared memory ----------------------------------------------------
         if (bulk) {
-            mbar_wait(&sm.bar_txt[buf], par);
-        } else { // unaligned caller buffers: cooperative loads, no prefetch
+            mbar_wait(&sm.bar_tile, tile_parity);
+            tile_parity ^= 1;
+        } else { // unaligned caller buffers: ticket and cooperative loads
             __syncthreads();
-            uint32_t *ob = sm.off_buf[buf];
-            for (uint32_t i = tid; i <= nc; i += THREADS) ob[i] = __ldg(&a.off[c0 + i]);
+            if (tid == 0) {
+                const uint32_t t = atomicAdd(a.ticket, 1u);
+                sm.tile = t < a.n_tiles ? t : TILE_NONE;
+                sm.n_open = 0;
+                sm.park_used = 0;
+            }
             __syncthreads();
-            const uint32_t b0 = ob[0], b1 = ob[nc], w0 = b0 & ~3u;
+        }
+        const uint32_t tile = sm.tile;
+        if (tile == TILE_NONE) break;
+        const uint64_t c0 = a.chunk0 + (uint64_t)tile * TILE;
+        const uint32_t nc = (uint32_t)min((uint64_t)TILE, a.chunk1 - c0);
+        if (!bulk) {
+            for (uint32_t i = tid; i <= nc; i += THREADS) sm.off[i] = __ldg(&a.off[c0 + i]);
+            __syncthreads();
+            const uint32_t b0 = sm.off[0], b1 = sm.off[nc], w0 = b0 & ~3u;
             const bool st = (b1 - w0) <= (uint32_t)SM::TEXT_CAP;
             if (st) // byte loads: nothing is known about the alignment of the buffer
-                for (uint32_t g = b0 + tid; g < b1; g += THREADS) reinterpret_cast<uint8_t *>(sm.text_buf[buf])[g - w0] = __ldg(&a.bytes[g]);
+                for (uint32_t g = b0 + tid; g < b1; g += THREADS) reinterpret_cast<uint8_t *>(sm.text)[g - w0] = __ldg(&a.bytes[g]);
             if (tid == 0) {
-                sm.a0[buf] = w0;
-                sm.staged[buf] = st;
+                sm.a0 = w0;
+                sm.staged = st;
             }
             __syncthreads();
         }
-        sm.off = sm.off_buf[buf]; // (every thread stores the same two pointers: a reader has written them itself or sees the
-        sm.text = sm.text_buf[buf]; //  identical value; every tile ends with a barrier, so nobody still reads the previous ones)
-        const uint32_t *const soff = sm.off_buf[buf];
-        const uint32_t *const stext = sm.text_buf[buf];
-        const uint32_t a0 = sm.a0[buf];
-        const bool staged = sm.staged[buf] != 0;
+        const uint32_t a0 = sm.a0;
+        const bool staged = sm.staged != 0;
         lap(0);
-        // ---- 1. fast path: the home slot of every chunk in the SMALL cache, all of a thread's probes in flight ------
-        uint32_t o[CPT + 1];
+        // ---- 1. cache probes: every chunk's home slot, PIF of them in flight per thread ----------------------------
+        const bool keyed = a.cache.slots != nullptr && staged && !(a.ablate & 2); // (an unstaged tile -- very long chunks -- is all scanned)
 #pragma unroll
-        for (int j = 0; j <= CPT; j++) o[j] = soff[min(tid * CPT + j, nc)];
-        uint32_t cnt[CPT];
-        uint32_t openq[CPT]; // place on the open list, or TILE_NONE: cnt / vq are final
-        uint4 vq[CPT];       // hit: the chunk's ids
-        uint32_t hints = 0;  // two bits per chunk: what its home slot in the SMALL cache showed (see resolve_cached)
-        const bool keyed = a.cache.small != nullptr && staged && !(a.ablate & 2); // (an unstaged tile -- very long chunks -- is all "open")
-        if (keyed) {
-            uint4 kw[CPT], kq[CPT];
+        for (int g = 0; g < CPT; g += PIF) {
+            uint64_t k0[PIF], k1[PIF], k2[PIF], k3[PIF], q0[PIF], q1[PIF], q2[PIF], q3[PIF];
+            uint32_t h[PIF], o0[PIF], len[PIF];
 #pragma unroll
-            for (int j = 0; j < CPT; j++) {
-                const uint32_t len = o[j + 1] - o[j];
-                // the 16 bytes at the chunk's start, bytes at and after `len` cleared, length in the top byte
-                const uint32_t r = o[j] - a0, wi = r >> 2, sh = (r & 3) * 8;
-                const uint32_t nb = len < 16 ? len : 0; // ones over the key's first `len` bytes, word by word
-                uint4 lm;
-                lm.x = (uint32_t)((1ull << (8 * min(nb, 4u))) - 1);
-                lm.y = (uint32_t)((1ull << (8 * (min(max(nb, 4u), 8u) - 4))) - 1);
-                lm.z = (uint32_t)((1ull << (8 * (min(max(nb, 8u), 12u) - 8))) - 1);
-                lm.w = (uint32_t)((1ull << (8 * (min(max(nb, 12u), 16u) - 12))) - 1);
-                const uint32_t t0 = stext[wi], t1 = stext[wi + 1], t2 = stext[wi + 2], t3 = stext[wi + 3], t4 = stext[wi + 4];
-                kw[j].x = __funnelshift_r(t0, t1, sh) & lm.x;
-                kw[j].y = __funnelshift_r(t1, t2, sh) & lm.y;
-                kw[j].z = __funnelshift_r(t2, t3, sh) & lm.z;
-                kw[j].w = (__funnelshift_r(t3, t4, sh) & lm.w) | (len << 24);
-                const uint32_t h = small_hash(kw[j].x, kw[j].y, kw[j].z, kw[j].w) >> a.cache.small_shift;
-                if (PASS == 1) // (counting needs the key half only; empty / long chunks probe too: the answer is ignored)
-                    kq[j] = __ldg(reinterpret_cast<const uint4 *>(&a.cache.small[h]));
-                else
-                    ld_slot256(&a.cache.small[h], kq[j], vq[j]);
-            }
-#pragma unroll
-            for (int j = 0; j < CPT; j++) {
-                const uint32_t len = o[j + 1] - o[j];
-                const bool small = len - 1u < SMALL_MAX_LEN;
-                const bool hit = small && (kq[j].w & SMALL_KEY_MASK) == kw[j].w && kq[j].x == kw[j].x && kq[j].y == kw[j].y && kq[j].z == kw[j].z;
-                const bool final = hit && (kq[j].w >> 28) <= SMALL_MAX_IDS; // (a stub is a hit that only says "BIG has it")
-                cnt[j] = final ? kq[j].w >> 28 : 0u;
-                openq[j] = final ? TILE_NONE : 0u; // 0: undecided, see below
-                // what the home slot showed, for resolve_cached: 1 = another chunk, 2 = this chunk's stub (or a long chunk)
-                hints |= (hit ? 2u : (small && kq[j].w != 0) ? 1u : (small ? 3u : 2u)) << (2 * j); // 3: empty home slot = not cached
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < CPT; j++) {
-                cnt[j] = 0;
-                openq[j] = 0;
-                vq[j] = make_uint4(0, 0, 0, 0);
-            }
-            hints = 0; // (no home slot was looked at: the whole probe sequence is open)
-        }
-        // the next tile's boundaries have had a whole fast path to land: start its text on its way, and the boundaries
-        // of the tile after it (their buffers belong to tiles that are completely done)
-        if (bulk && tid == 0) {
-            const uint32_t t1 = tile + gridDim.x;
-            if (t1 < a.n_tiles) fetch_text(a, sm, t1, buf ^ 1, ((it + 1) >> 1) & 1, policy);
-        }
-        // open chunks: bit j of `open`. First the ones that need no look-up at all ...
-        uint32_t open = 0;
-#pragma unroll
-        for (int j = 0; j < CPT; j++) {
-            if (openq[j] == TILE_NONE) continue; // hit
-            openq[j] = TILE_NONE;
-            const uint32_t k = tid * CPT + j, len = o[j + 1] - o[j];
-            if (k >= nc || len == 0) continue;
-            if (len > ENC_SHORT_MAX) {
-                if (a.scratch_b) {
-                    cnt[j] = a.scratch_b[o[j]]; // encoded by k_encode_long
-                } else if (PASS == 1) {         // optimistic launch: report it, the host runs the long path and repeats
-                    const uint32_t q = atomicAdd(a.n_long, 1u);
-                    if (q < a.long_cap) a.long_list[q] = (uint32_t)(c0 + k);
+            for (int p = 0; p < PIF; p++) {
+                const uint32_t k = (g + p) * THREADS + tid;
+                o0[p] = sm.off[min(k, nc)];
+                len[p] = sm.off[min(k + 1, nc)] - o0[p]; // (0 past the tile's end)
+                if (keyed) {
+                    // Chunks of 0 or more than 31 bytes build a key and probe like everybody else -- the text window has a
+                    // halo, the slot address is always valid -- and ignore the answer.
+                    const uint32_t r = o0[p] - a0, wi = r >> 2, sh = (r & 3) * 8;
+                    const uint4 lm = sm.len_mask[min(len[p], 16u)];
+                    const uint32_t t0 = sm.text[wi], t1 = sm.text[wi + 1], t2 = sm.text[wi + 2], t3 = sm.text[wi + 3], t4 = sm.text[wi + 4];
+                    const uint32_t w0 = __funnelshift_r(t0, t1, sh) & lm.x, w1 = __funnelshift_r(t1, t2, sh) & lm.y;
+                    const uint32_t w2 = __funnelshift_r(t2, t3, sh) & lm.z, w3 = __funnelshift_r(t3, t4, sh) & lm.w;
+                    k0[p] = ((uint64_t)w1 << 32) | w0;
+                    k1[p] = ((uint64_t)w3 << 32) | w2;
+                    k2[p] = 0;
+                    k3[p] = (uint64_t)len[p] << 56;
+                    uint64_t x = cache_hash_lo(k0[p], k1[p]);
+                    if (len[p] > CACHE_SHORT_KEY) { // one chunk in a hundred
+                        const uint4 hm = sm.len_mask[min(len[p], 32u) - 16];
+                        const uint32_t t5 = sm.text[wi + 5], t6 = sm.text[wi + 6], t7 = sm.text[wi + 7], t8 = sm.text[wi + 8];
+                        const uint32_t w4 = __funnelshift_r(t4, t5, sh) & hm.x, w5 = __funnelshift_r(t5, t6, sh) & hm.y;
+                        const uint32_t w6 = __funnelshift_r(t6, t7, sh) & hm.z, w7 = __funnelshift_r(t7, t8, sh) & hm.w & 0x00FFFFFFu;
+                        k2[p] = ((uint64_t)w5 << 32) | w4;
+                        const uint64_t b3 = ((uint64_t)w7 << 32) | w6;
+                        k3[p] |= b3;
+                        if (k2[p] | b3) x ^= cache_hash_hi(k2[p], b3);
+                    }
+                    h[p] = cache_hash_fin(x) >> a.cache.shift;
+                    ld_sector256(&a.cache.slots[h[p]], q0[p], q1[p], q2[p], q3[p]);
                 }
-                continue;
             }
-            if (a.ablate & 10) { // (profiling only: 2 = every chunk "hits", 8 = open chunks are not resolved)
-                cnt[j] = (a.ablate & 2) ? 2 : 1;
-                vq[j] = make_uint4(o[j], len, 0, 0);
-                continue;
+#pragma unroll
+            for (int p = 0; p < PIF; p++) {
+                const uint32_t k = (g + p) * THREADS + tid;
+                const bool short_key = len[p] <= CACHE_SHORT_KEY;
+                // a short key owns k[0], k[1] and the length byte of its sector (the rest is the answer), a long one all of it
+                auto same_key = [&]() {
+                    return q0[p] == k0[p] && q1[p] == k1[p] && (short_key ? (q3[p] >> 56) == len[p] : (q2[p] == k2[p] && q3[p] == k3[p]));
+                };
+                bool hit = false;
+                if (keyed && len[p] - 1u < CACHE_MAX_LEN) {
+                    hit = same_key();
+                    if (!hit && q3[p] != 0) { // the home slot holds another chunk: the probe sequence goes on
+#pragma unroll 1
+                        for (uint32_t probes = 1; probes < CACHE_MAX_PROBES; probes++) {
+                            h[p] = (h[p] + 1) & a.cache.mask;
+                            ld_sector256(&a.cache.slots[h[p]], q0[p], q1[p], q2[p], q3[p]);
+                            if (q3[p] == 0) break;
+                            if (same_key()) {
+                                hit = true;
+                                break;
+                            }
+                        }
+                    }
+                }
+                uint4 rec = make_uint4(0, 0, 0, 0); // (x = count | kind << 30)
+                if (hit) {
+                    if (short_key && !(q3[p] & CACHE_NOT_INLINE)) { // nine chunks in ten end here
+                        rec.x = (uint32_t)q3[p] & 0x7Fu;
+                        rec.y = (uint32_t)q2[p];
+                        rec.z = (uint32_t)(q2[p] >> 32);
+                    } else {
+                        rec.x = (short_key ? ((uint32_t)q3[p] & 0x7Fu) : __ldg(&a.cache.slots[h[p]].n)) | (CK_SLOT << 30);
+                        rec.y = h[p];
+                    }
+                } else if (len[p] != 0) {
+                    if (len[p] > ENC_SHORT_MAX) {
+                        rec.x = CK_LONG << 30;
+                        rec.y = o0[p];
+                        if (a.scratch_b) {
+                            rec.x |= a.scratch_b[o0[p]]; // encoded by k_encode_long
+                        } else {                         // optimistic launch: report it, the host runs the long path and repeats
+                            const uint32_t q = atomicAdd(a.n_long, 1u);
+                            if (q < a.long_cap) a.long_list[q] = (uint32_t)(c0 + k);
+                        }
+                    } else if (a.ablate & 2) {
+                        rec.x = 2;
+                        rec.y = o0[p] | (len[p] << CACHE_ID_BITS);
+                    } else {
+                        const uint32_t q = atomicAdd(&sm.n_open, 1u);
+                        sm.open_k[q] = (uint16_t)k;
+                        rec.x = CK_PARKED << 30; // (count and place: set_parked)
+                    }
+                }
+                sm.rec[k] = rec;
+                sm.cnt[k] = rec.x & 0x3FFFFFFFu;
             }
-            open |= 1u << j;
-        }
-        // ... then, one open chunk per lane and round (a lane rarely has two), the ones that may be cached elsewhere: a special
-        // token; a chunk of 16..31 bytes or a stub (BIG); a short one whose home slot holds somebody else. No barrier: the lanes
-        // that have one diverge into resolve_cached for about one memory round trip.
-        for (uint32_t todo = open; todo;) {
-            const int j = __ffs(todo) - 1;
-            todo &= todo - 1;
-            uint32_t oj = 0, ej = 0;
-#pragma unroll
-            for (int q = 0; q < CPT; q++)
-                if (q == j) {
-                    oj = o[q];
-                    ej = o[q + 1];
-                }
-            const uint32_t len = ej - oj, hint = (hints >> (2 * j)) & 3u;
-            const bool maybe_cached = a.cache.small != nullptr && len <= CACHE_MAX_LEN && hint != 3u;
-            if (!(maybe_cached || (a.sp.n && ((a.sp.len_mask >> (len < 63u ? len : 63u)) & 1ull)))) continue;
-            uint4 r = make_uint4(0, 0, 0, 0);
-            const uint32_t n = resolve_cached(a, sm, a0, staged, oj, len, hint == 3u ? 0u : hint, r);
-            if (n == 0) continue;
-            open &= ~(1u << j);
-#pragma unroll
-            for (int q = 0; q < CPT; q++)
-                if (q == j) {
-                    cnt[q] = n;
-                    vq[q] = r;
-                }
-        }
-        // ... and what nobody has seen before goes on the tile's scan list
-#pragma unroll
-        for (int j = 0; j < CPT; j++) {
-            if (!((open >> j) & 1u)) continue;
-            const uint32_t q = atomicAdd(&sm.n_open, 1u);
-            sm.open_k[q] = (uint16_t)(tid * CPT + j);
-            openq[j] = q;
         }
         __syncthreads();
         lap(1);
-        // ---- 2. chunks nobody has seen before ----------------------------------------------------------------------------
+        // ---- 2. chunks the cache does not hold ------------------------------------------------------------------------
         {
             const uint32_t n_scan = sm.n_open;
             if (n_scan) {
-                scan_open_chunks<THREADS>(a, sm, a0, staged, n_scan, PASS == 1);
+                scan_open_chunks<THREADS>(a, sm, a0, staged, n_scan, true);
                 __syncthreads();
             }
         }
         lap(2);
-        uint32_t sum = 0;
+        // ---- 3a. count scan: CPT consecutive chunks per thread; cnt[k] becomes the offset within the warp's segment ----
+        {
+            uint32_t c[CPT];
+            if constexpr (CPT == 2) {
+                const uint2 x = reinterpret_cast<const uint2 *>(sm.cnt)[tid];
+                c[0] = x.x;
+                c[1] = x.y;
+            } else {
 #pragma unroll
-        for (int j = 0; j < CPT; j++) {
-            if (openq[j] != TILE_NONE) cnt[j] = sm.meta[openq[j]] >> 20;
-            sum += cnt[j];
-        }
-        // ---- 3. the tile's id count (pass 1) / every thread's place in the tile (pass 2) -----------------------------
-        uint32_t incl = sum;
+                for (int q = 0; q < CPT / 4; q++) {
+                    const uint4 x = reinterpret_cast<const uint4 *>(sm.cnt)[tid * (CPT / 4) + q];
+                    c[4 * q] = x.x;
+                    c[4 * q + 1] = x.y;
+                    c[4 * q + 2] = x.z;
+                    c[4 * q + 3] = x.w;
+                }
+            }
+            uint32_t sum = 0;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += v;
+            for (int i = 0; i < CPT; i++) sum += c[i];
+            uint32_t incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            uint32_t run = incl - sum;
+#pragma unroll
+            for (int i = 0; i < CPT; i++) {
+                const uint32_t n = c[i];
+                c[i] = run;
+                run += n;
+            }
+            if constexpr (CPT == 2) {
+                reinterpret_cast<uint2 *>(sm.cnt)[tid] = make_uint2(c[0], c[1]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < CPT / 4; q++)
+                    reinterpret_cast<uint4 *>(sm.cnt)[tid * (CPT / 4) + q] = make_uint4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]);
+            }
+            if (lane == 31) sm.warp_sum[warp] = incl;
         }
-        if (lane == 31) sm.warp_sum[warp] = incl;
         __syncthreads();
-        uint32_t warp_base = 0, total = 0;
+        lap(3);
+        // ---- 3b. place in the stream: look-back by warp 0; the ids are gathered in shared memory meanwhile ------------
+        uint32_t total = 0, pre[CPT]; // pre[j]: ids of the tile before the segment of this thread's j-th chunk
+#pragma unroll
+        for (int j = 0; j < CPT; j++) pre[j] = 0;
 #pragma unroll
         for (int w = 0; w < NW; w++) {
             const uint32_t v = sm.warp_sum[w];
-            if (w < (int)warp) warp_base += v;
+#pragma unroll
+            for (int j = 0; j < CPT; j++)
+                if (w < j * SEG_PER_J + (int)(warp / CPT)) pre[j] += v;
             total += v;
         }
-        lap(3);
-        if (tid == 0) sm.n_open = sm.park_used = 0; // (everybody is past the open list; the next appends come after a barrier below)
-        if (PASS == 1) {
-            if (tid == 0) a.tile_total[tile] = total;
-            __syncthreads();
-        } else {
-            const uint64_t base = a.tile_base[tile];
-            const bool via_smem = total <= (uint32_t)SM::STAGE;
-            const uint32_t loc0 = warp_base + (incl - sum);
-            if (!(a.ablate & 4)) {
-                uint32_t loc = loc0;
-#pragma unroll
-                for (int j = 0; j < CPT; j++) {
-                    const uint64_t at = base + loc;
-                    if (via_smem)
-                        emit_chunk(a, sm, cnt[j], openq[j], o[j], o[j + 1], vq[j], sm.stage + loc, ~0ull);
-                    else // a tile with more ids than the gather buffer holds: every thread stores its own
-                        emit_chunk(a, sm, cnt[j], openq[j], o[j], o[j + 1], vq[j], a.out + at, at < a.out_cap ? a.out_cap - at : 0);
-                    loc += cnt[j];
-                }
-            }
-            if (a.out_off) {
-                uint32_t loc = loc0;
-#pragma unroll
-                for (int j = 0; j < CPT; j++) {
-                    const uint32_t k = tid * CPT + j;
-                    if (k < nc) a.out_off[c0 + k] = base + loc;
-                    loc += cnt[j];
-                }
-            }
-            __syncthreads();
-            lap(4);
-            if (via_smem && !(a.ablate & 4)) {
-                if (base + total <= a.out_cap && a.out_aligned) {
-                    // 16-byte stores: vector v = stream words [w0 + 4v, w0 + 4v + 4), w0 = base rounded down to 4 words
-                    const uint32_t pad = (uint32_t)(base & 3);
-                    uint32_t *const gout = a.out + (base - pad);
-                    const uint32_t n_vec = (pad + total + 3) >> 2;
-                    for (uint32_t v = tid; v < n_vec; v += THREADS) {
-                        const int lo = (int)(4 * v) - (int)pad; // index of the vector's first word in the gather buffer
-                        if (lo >= 0 && (uint32_t)lo + 4 <= total) {
-                            const uint4 q = make_uint4(sm.stage[lo], sm.stage[lo + 1], sm.stage[lo + 2], sm.stage[lo + 3]);
-                            __stcs(reinterpret_cast<uint4 *>(gout) + v, q);
-                        } else {
-                            for (int i = lo < 0 ? 0 : lo; i < lo + 4 && (uint32_t)i < total; i++) __stcs(&a.out[base + i], sm.stage[i]);
-                        }
-                    }
-                } else {
-                    for (uint32_t i = tid; i < total; i += THREADS)
-                        if (base + i < a.out_cap) a.out[base + i] = sm.stage[i];
-                    if (tid == 0 && base + total > a.out_cap) *a.overflow = 1;
-                }
-            }
-            if (tile == a.n_tiles - 1 && tid == 0 && a.out_off && a.chunk1 == a.n_chunks) a.out_off[a.n_chunks] = base + total;
+        if (warp == 0) {
+            const uint64_t b = (a.ablate & 1) ? (uint64_t)tile * (TILE * 9 / 4) : lookback_base<4>(a.status, tile, total, a.stream_base);
+            if (lane == 0) sm.base = b;
         }
-        if (PASS == 2) __syncthreads(); // every tile ends with a barrier: nothing of it is still read when the next one starts
-        // the boundaries of the tile after the next one go into this tile's buffer
+        const bool via_smem = total <= (uint32_t)SM::STAGE;
+#pragma unroll
+        for (int j = 0; j < CPT; j++) {
+            const uint32_t k = j * THREADS + tid;
+            pre[j] += sm.cnt[k]; // = the chunk's place in the tile
+            if (via_smem && !(a.ablate & 4)) {
+                const uint4 r = sm.rec[k];
+                if (r.x & 0x3FFFFFFFu) emit_chunk(a, sm, r, sm.stage + pre[j], ~0ull);
+            }
+        }
+        __syncthreads();
+        lap(4);
+        const uint64_t base = sm.base;
+        if (!via_smem && !(a.ablate & 4)) { // a tile with more ids than the gather buffer holds: every thread stores its own
+#pragma unroll
+            for (int j = 0; j < CPT; j++) {
+                const uint4 r = sm.rec[j * THREADS + tid];
+                const uint64_t at = base + pre[j];
+                if (r.x & 0x3FFFFFFFu) emit_chunk(a, sm, r, a.out + at, at < a.out_cap ? a.out_cap - at : 0);
+            }
+            __syncthreads(); // (emit reads the records and the parking area: they are replaced below)
+        }
+        // ---- 4. the next tile's loads start now; this tile's ids leave as whole lines --------------------------------
         if (bulk && tid == 0) {
-            const uint32_t t2 = tile + 2 * gridDim.x;
-            if (t2 < a.n_tiles) fetch_off(a, sm, t2, buf, policy);
+            sm.n_open = 0; // (everybody is past the scan list; the next tile's appends come after the next mbarrier wait)
+            sm.park_used = 0;
+            fetch_tile_bulk(a, sm, off_parity, policy);
+        }
+        lap(5);
+        if (a.out_off) {
+#pragma unroll
+            for (int j = 0; j < CPT; j++) {
+                const uint32_t k = j * THREADS + tid;
+                if (k < nc) a.out_off[c0 + k] = base + pre[j];
+            }
+        }
+        if (via_smem && !(a.ablate & 4)) {
+            if (base + total <= a.out_cap && a.out_aligned) {
+                // 16-byte stores: vector v = stream words [w0 + 4v, w0 + 4v + 4), w0 = base rounded down to 4 words
+                const uint32_t pad = (uint32_t)(base & 3);
+                uint32_t *const gout = a.out + (base - pad);
+                const uint32_t n_vec = (pad + total + 3) >> 2;
+                for (uint32_t v = tid; v < n_vec; v += THREADS) {
+                    const int lo = (int)(4 * v) - (int)pad; // index of the vector's first word in the gather buffer
+                    if (lo >= 0 && (uint32_t)lo + 4 <= total) {
+                        const uint4 q = make_uint4(sm.stage[lo], sm.stage[lo + 1], sm.stage[lo + 2], sm.stage[lo + 3]);
+                        __stcs(reinterpret_cast<uint4 *>(gout) + v, q);
+                    } else {
+                        for (int i = lo < 0 ? 0 : lo; i < lo + 4 && (uint32_t)i < total; i++) __stcs(&a.out[base + i], sm.stage[i]);
+                    }
+                }
+            } else {
+                for (uint32_t i = tid; i < total; i += THREADS)
+                    if (base + i < a.out_cap) a.out[base + i] = sm.stage[i];
+                if (tid == 0 && base + total > a.out_cap) *a.overflow = 1;
+            }
+        }
+        if (tile == a.n_tiles - 1 && tid == 0) {
+            *a.d_n_out = base + total;
+            if (a.out_off && a.chunk1 == a.n_chunks) a.out_off[a.n_chunks] = base + total;
         }
         lap(6);
         if (a.prof && tid == 0) sm.prof[7] += 1;
     }
     if (a.prof && tid == 0)
-        for (int i = 0; i < 8; i++) atomicAdd(&a.prof[(PASS - 1) * 8 + i], sm.prof[i]);
-}
-
-// tile_total[0 .. n) -> tile_base[0 .. n) (exclusive scan, starting at the ids of earlier launches); *d_n_out = the new total.
-// One CTA: a launch has at most 2^26 / 256 tiles.
-__global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t *tile_total, uint32_t n, unsigned long long *tile_base,
-                                                   unsigned long long *d_n_out) {
-    __shared__ unsigned long long warp_sum[32];
-    __shared__ unsigned long long carry;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) carry = *d_n_out;
-    __syncthreads();
-    for (uint32_t i0 = 0; i0 < n; i0 += 1024 * 4) {
-        uint32_t v[4];
-        unsigned long long mine = 0;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const uint32_t i = i0 + tid * 4 + q;
-            v[q] = i < n ? tile_total[i] : 0u;
-            mine += v[q];
-        }
-        unsigned long long incl = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned long long x = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += x;
-        }
-        if (lane == 31) warp_sum[warp] = incl;
-        __syncthreads();
-        unsigned long long wb = 0, all = 0;
-        for (int w = 0; w < 32; w++) {
-            const unsigned long long x = warp_sum[w];
-            if (w < (int)warp) wb += x;
-            all += x;
-        }
-        unsigned long long at = carry + wb + (incl - mine);
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const uint32_t i = i0 + tid * 4 + q;
-            if (i < n) tile_base[i] = at;
-            at += v[q];
-        }
-        __syncthreads();
-        if (tid == 0) carry += all;
-        __syncthreads();
-    }
-    if (tid == 0) *d_n_out = carry;
+        for (int i = 0; i < ENC_PROF_N; i++) atomicAdd(&a.prof[i], sm.prof[i]);
 }
 
 } // namespace mbpe
