@@ -356,10 +356,10 @@ struct EncConfig {
     void (*kernel)(const EncArgs);
     size_t smem;
 };
-#define ENC_CFG(T, C, M, P) EncConfig{T, C, M, k_encode_tiles<T, C, M, P>, sizeof(EncSmemT<T, C>)}
-// (threads, chunks per thread, CTAs per SM, probes in flight per thread); 0 = default, the others for A/B runs (MBPE_ENC_CFG)
-static const EncConfig enc_configs[] = {ENC_CFG(256, 4, 4, 1), ENC_CFG(256, 4, 3, 1), ENC_CFG(256, 4, 3, 2), ENC_CFG(256, 4, 4, 2),
-                                        ENC_CFG(256, 8, 2, 1), ENC_CFG(128, 4, 8, 1), ENC_CFG(512, 4, 2, 1), ENC_CFG(256, 8, 2, 2)};
+#define ENC_CFG(T, C, M, P, L) EncConfig{T, C, M, k_encode_tiles<T, C, M, P, L>, sizeof(EncSmemT<T, C>)}
+// (threads, chunks per thread, CTAs per SM, probes in flight per thread, L1 policy of the probe loads); 0 = default, the others for A/B runs (MBPE_ENC_CFG)
+static const EncConfig enc_configs[] = {ENC_CFG(256, 4, 4, 1, 0), ENC_CFG(256, 4, 4, 1, 3), ENC_CFG(256, 4, 3, 1, 0), ENC_CFG(512, 4, 2, 1, 0),
+                                        ENC_CFG(256, 8, 2, 1, 0), ENC_CFG(128, 4, 8, 1, 0), ENC_CFG(256, 4, 4, 2, 0), ENC_CFG(256, 4, 4, 1, 1)};
 constexpr int N_ENC_CONFIGS = sizeof(enc_configs) / sizeof(enc_configs[0]);
 
 static ChunkCache cache_view(const mbpe_encoder *e) {
@@ -481,6 +481,8 @@ static int encoder_create_impl(mbpe_encoder *e, const uint32_t *merges, uint32_t
     e->cfg = cfg_env && *cfg_env ? std::min(std::max(atoi(cfg_env), 0), N_ENC_CONFIGS - 1) : 0;
     for (int i = 0; i < N_ENC_CONFIGS; i++) {
         MB_CUDA(cudaFuncSetAttribute(enc_configs[i].kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_configs[i].smem));
+        if (const char *co = getenv("MBPE_ENC_CARVEOUT")) // percent of the L1/shared array given to shared memory (A/B runs)
+            MB_CUDA(cudaFuncSetAttribute(enc_configs[i].kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co)));
     }
     return MBPE_OK;
 }
@@ -805,6 +807,8 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
             fprintf(stderr, "[mbpe] encode tiles %llu, cycles per tile: wait data %.0f, probes %.0f, scan list %.0f, count scan %.0f, "
                             "look-back+gather %.0f, fetch next %.0f, store %.0f\n",
                     pr[7], pr[0] / t, pr[1] / t, pr[2] / t, pr[3] / t, pr[4] / t, pr[5] / t, pr[6] / t);
+            fprintf(stderr, "[mbpe]   thread 0: look-back %.0f, gather %.0f, barrier %.0f; thread 32: gather %.0f, barrier %.0f\n", pr[8] / t,
+                    pr[9] / t, pr[10] / t, pr[11] / t, pr[12] / t);
         }
     }
     return MBPE_OK;

@@ -6,20 +6,25 @@
 // One tile = THREADS x CPT consecutive chunks, one CTA, one pass over the data:
 //   0. thread 0 takes the next tile (ticket: tiles START in stream order, which is what makes the look-back of step 3
 //      deadlock free) and brings its boundaries and its text window into shared memory with two bulk asynchronous copies
-//      (cp.async.bulk -> the TMA engine, completion on mbarriers); the request for the next tile is issued while this
-//      tile's ids are still being stored.
-//   1. every thread, CPT chunks: the chunk's bytes (<= 31) are the key of the chunk cache, "chunk bytes -> ids" in
-//      64-byte slots (key sector, value sector). One 256-bit load (LDG.E.256) fetches the key sector, one 128-bit load
-//      the id count and the first three ids: nineteen chunks in twenty are done after that one round trip, and every lane
-//      runs the same instructions (the measured cost of this kernel is instruction issue and divergence, not bytes:
-//      see DESIGN.md "encode: what was tried").
-//   2. chunks the cache does not hold (cold cache, chunks of 32..64 bytes, a full table) go to the tile's scan list: the
+//      (cp.async.bulk -> the TMA engine, completion on mbarriers), while the other threads still store the previous
+//      tile's ids. The ticket is taken as late as possible: see fetch_tile_bulk.
+//   1. every thread, CPT chunks: the chunk's bytes (<= 30) are the key of the chunk cache, "chunk bytes -> ids" in
+//      64-byte slots. The key sector also carries the id count and, for keys of <= 16 bytes, up to three ids, so ONE
+//      256-bit load (LDG.E.256) answers nine chunks in ten, and every lane runs the same instructions. What a thread
+//      learns about a chunk goes into the chunk's 8-byte record in shared memory, not into registers: the probe loop
+//      needs 40 registers, neighbouring lanes work on neighbouring chunks (conflict-free shared memory traffic) and
+//      their ids land side by side in step 3.
+//   2. chunks the cache does not hold (cold cache, chunks of 31..64 bytes, a full table) go to the tile's scan list: the
 //      multi-pass scan itself, one warp per chunk when few, one thread per chunk when many; their ids wait in a parking
 //      area (shared memory, overflow in HBM), and a log hands them to k_cache_insert, which runs between launches.
-//   3. block scan of the id counts; warp 0 resolves the tile's place in the stream by decoupled look-back over the
-//      predecessors' counts (128 per round trip) WHILE the other warps gather the tile's ids in shared memory; the ids
-//      leave as 16-byte stores.
+//   3. block scan of the id counts; warp 0 announces the tile's count, everybody gathers the tile's ids in shared memory
+//      (ids that live in the value sector of a cache slot: all of a thread's loads in flight together), and only then
+//      warp 0 walks the predecessors' counts (decoupled look-back, 128 per round trip) -- by then most of them have
+//      announced themselves. The ids leave as 16-byte stores.
 // Results never depend on the cache: a miss is scanned, and special tokens are matched in the scan path itself.
+// What bounds it (profiles/README.md, round 2): not bytes -- DRAM traffic is the algorithmic 13 bytes per chunk -- but the
+// chain of latencies of one tile (ticket -> boundaries -> text -> four dependent probe rounds -> look-back) at the
+// occupancy 64 registers x 256 threads x 4 CTAs allow; DESIGN.md "encode: what was tried" lists the measured dead ends.
 #pragma once
 #include "lookback.cuh"
 
@@ -66,10 +71,16 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  : "memory");
 }
 
-// one 32-byte sector in ONE load (LDG.E.256, new with sm_100): one L1 wavefront instead of two
+// one 32-byte sector in ONE load (LDG.E.256, new with sm_100): one L1 wavefront instead of two.
+// LD = how the load treats L1: 0 read-only path, allocates (LDG.CONSTANT); 1 L2 only (ld.cg); 2 read-only path, no L1
+// allocation (LDG.NA); 3 read-only path, evict-last in L1 (LDG.EL)
+template <int LD = 0>
 __device__ __forceinline__ void ld_sector256(const void *p, uint64_t &q0, uint64_t &q1, uint64_t &q2, uint64_t &q3) {
     unsigned long long a0, a1, a2, a3;
-    asm("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a0), "=l"(a1), "=l"(a2), "=l"(a3) : "l"(p));
+    if (LD == 0) asm("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a0), "=l"(a1), "=l"(a2), "=l"(a3) : "l"(p));
+    if (LD == 1) asm("ld.global.cg.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a0), "=l"(a1), "=l"(a2), "=l"(a3) : "l"(p));
+    if (LD == 2) asm("ld.global.nc.L1::no_allocate.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a0), "=l"(a1), "=l"(a2), "=l"(a3) : "l"(p));
+    if (LD == 3) asm("ld.global.nc.L1::evict_last.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a0), "=l"(a1), "=l"(a2), "=l"(a3) : "l"(p));
     q0 = a0;
     q1 = a1;
     q2 = a2;
@@ -78,19 +89,21 @@ __device__ __forceinline__ void ld_sector256(const void *p, uint64_t &q0, uint64
 
 // ---------------------------------------------------------------------------------------------------------
 // Chunk cache. The multi-pass scan of a chunk is a pure function of its bytes, and text repeats its chunks (Zipf):
-// the encoder keeps "chunk bytes (<= 31) -> ids" in an open-addressed table in HBM, 64-byte slots = key sector + value
+// the encoder keeps "chunk bytes (<= 30) -> ids" in an open-addressed table in HBM, 64-byte slots = key sector + value
 // sector (more than 7 ids: in an arena); nine chunks in ten are answered by the key sector alone (see CacheSlot). The tile kernel only READS it; chunks it had to scan go to a log, and
 // k_cache_insert adds the log to the table between launches -- no kernel both reads and writes the table, so there is no
 // publication protocol to get wrong. Results are bit-identical with or without the cache (MBPE_ENCODE_CACHE=0 disables
 // it; tests run both).
 // ---------------------------------------------------------------------------------------------------------
 struct CacheSlot { // 64 bytes = two sectors
-    // Key sector. Chunk bytes little endian, zero padded; top byte of k[3] = length (1..31); k[3] == 0: empty slot.
-    // A SHORT key (<= 16 bytes) fills k[0], k[1] only, and the rest of its sector carries the answer, so that one 32-byte
-    // load resolves the chunk: k[3] bits 0..6 = id count, bit 7 = "ids not inline"; k[2] = up to three ids of 21 bits.
+    // Key sector. Chunk bytes little endian, zero padded; top byte of k[3] = length (1..30); k[3] == 0: empty slot.
+    // The id count rides in the key sector, so that a probe is ONE 32-byte load:
+    //   SHORT key (<= 16 bytes): k[0], k[1] = the bytes; k[3] bits 0..6 = id count, bit 7 = "ids not inline";
+    //                            k[2] = up to three ids of 21 bits (nine chunks in ten are answered by this sector alone);
+    //   LONG key (17..30 bytes): k[0..2] and k[3] bits 0..47 = the bytes; k[3] bits 48..55 = id count.
     uint64_t k[4];
     // Value sector (read when the ids are not inline: long keys, more than three ids, ids of more than 21 bits).
-    uint32_t n;    // number of ids (1..31)
+    uint32_t n;    // number of ids (1..30)
     uint32_t v[7]; // n <= 7: the ids; otherwise v[0] = offset of the ids in the arena
 };
 static_assert(sizeof(CacheSlot) == 64, "two sectors per entry");
@@ -99,8 +112,10 @@ struct CacheLogEntry {
     uint32_t n;
     uint32_t ids[31];
 };
-constexpr uint32_t CACHE_MAX_LEN = 31, CACHE_SHORT_KEY = 16, CACHE_INLINE_IDS = 7, CACHE_KEY_IDS = 3, CACHE_ID_BITS = 21;
+constexpr uint32_t CACHE_MAX_LEN = 30, CACHE_SHORT_KEY = 16, CACHE_INLINE_IDS = 7, CACHE_KEY_IDS = 3, CACHE_ID_BITS = 21;
 constexpr uint64_t CACHE_NOT_INLINE = 0x80;
+constexpr uint32_t CACHE_LONG_N_SHIFT = 48;
+constexpr uint64_t CACHE_LONG_N_MASK = 0xFFull << CACHE_LONG_N_SHIFT;
 // An entry lives at most this many slots from its home: inserts give up beyond it (the chunk is simply not cached), so
 // lookups may stop there too -- no probe loop depends on the table having a free slot.
 constexpr uint32_t CACHE_MAX_PROBES = 64;
@@ -152,6 +167,8 @@ __global__ void k_cache_insert(ChunkCache cc) {
             k3 |= en | (inline_ids ? 0 : CACHE_NOT_INLINE);
             if (inline_ids)
                 for (uint32_t q = 0; q < en; q++) k2 |= (uint64_t)e.ids[q] << (CACHE_ID_BITS * q);
+        } else {
+            k3 |= (uint64_t)en << CACHE_LONG_N_SHIFT;
         }
         for (uint32_t probes = 0; probes < CACHE_MAX_PROBES; probes++) {
             unsigned long long *claim = reinterpret_cast<unsigned long long *>(&cc.slots[h].k[3]);
@@ -249,9 +266,10 @@ struct EncArgs {
 };
 
 // EncArgs::prof[i]: cycles thread 0 spent ... 0 waiting for the tile's data, 1 cache probes (+ barrier), 2 scan list,
-// 3 count scan (+ barrier), 4 look-back / gather (+ barrier), 5 fetching the next tile (ticket + two bulk copies),
-// 6 storing the ids, 7 tiles processed
-constexpr int ENC_PROF_N = 8;
+// 3 count scan (+ barrier), 4 gather + look-back (+ barrier), 5 fetching the next tile (ticket + two bulk copies),
+// 6 storing the ids, 7 tiles processed; inside 4: 8 look-back walk, 9 gather, 10 barrier (thread 0), 11 gather, 12 barrier
+// (thread 32: what the other warps wait for warp 0)
+constexpr int ENC_PROF_N = 16;
 constexpr uint32_t TILE_NONE = 0xFFFFFFFFu;
 constexpr uint64_t ENC_MAX_SUBBATCH = 1ull << 26; // chunks per launch at most (tile ids and look-back words are 32-bit safe)
 constexpr uint32_t ET_WARP_SCAN_MAX = 48;     // up to this many scans per tile run one warp per chunk
@@ -260,6 +278,7 @@ constexpr uint32_t CK_REGS = 0;   // ids (<= CACHE_KEY_IDS) in the record itself
 constexpr uint32_t CK_SLOT = 1;   // cached with more ids: the value sector of its slot is fetched again when writing
 constexpr uint32_t CK_PARKED = 2; // scanned by the tile: ids in the parking area
 constexpr uint32_t CK_LONG = 3;   // longer than ENC_SHORT_MAX: ids in the long-chunk scratch stream
+constexpr uint32_t REC_REF = 0x80000000u; // EncSmemT::rec[].y: not CK_REGS
 
 // Parking area of a tile = ids of its scanned chunks until they are written: the first PARK words live in shared memory,
 // the rest in the CTA's spill block in HBM (one index space; every id covers at least one byte of text, so a tile of
@@ -267,16 +286,21 @@ constexpr uint32_t CK_LONG = 3;   // longer than ENC_SHORT_MAX: ids in the long-
 template <int THREADS, int CPT>
 struct EncSmemT {
     static constexpr int TILE = THREADS * CPT;
-    static constexpr int TEXT_CAP = TILE * 10;  // staged text bytes per tile (average chunk ~5 bytes); wider tiles read HBM
+    static constexpr int TEXT_CAP = TILE * 8;   // staged text bytes per tile (average chunk ~5 bytes); wider tiles read HBM
     static constexpr int STAGE = TILE * 5 / 2;  // ids gathered per tile (average ~2.1 per chunk); more: direct stores
-    static constexpr int PARK = TILE / 2;       // parking words in shared memory (a warm cache parks a few dozen ids per tile)
+    static constexpr int PARK = TILE / 4;       // parking words in shared memory (a warm cache parks a few dozen ids per tile)
     static constexpr int SPILL = TILE * 64;     // parking words per CTA in HBM (EncArgs::spill): the worst case
-    alignas(128) uint32_t off[TILE + 8];
+    union alignas(128) {
+        uint32_t off[TILE + 8]; // steps 0 .. 2: the tile's chunk boundaries
+        uint32_t loc[TILE];     // step 3: every chunk's offset within its warp's segment of the tile
+    };
     alignas(128) uint32_t text[TEXT_CAP / 4 + 16]; // + halo: key assembly reads whole words past the chunk's end
     alignas(16) uint32_t stage[STAGE + 4];
-    alignas(16) uint4 rec[TILE];   // per chunk: x = id count | CK_* kind << 30; CK_REGS: y, z = the ids (three times 21 bits); CK_SLOT:
-                                   // y = cache slot; CK_PARKED: y = start in the parking area; CK_LONG: y = text offset
-    alignas(16) uint32_t cnt[TILE]; // per chunk: id count, then (step 3, in place) its offset within its warp's segment of the tile
+    // per chunk: its id count, and where the ids are: rec.y bit 31 clear = CK_REGS, {x, y} = the key sector's id word (three
+    // ids of 21 bits); bit 31 set: y bits 29..30 = CK_* kind, x = cache slot (CK_SLOT) / start in the parking area
+    // (CK_PARKED) / text offset (CK_LONG)
+    alignas(16) uint2 rec[TILE];
+    alignas(16) uint32_t cnt[TILE];
     uint32_t park[PARK];
     uint16_t open_k[TILE];     // scan list: chunk index within the tile
     uint4 len_mask[17];        // len_mask[l] keeps the first l bytes of 16
@@ -387,8 +411,7 @@ __device__ __forceinline__ uint32_t park_ids(const EncArgs &a, SM &sm, const uin
 // a scanned chunk's record: id count and where its ids are parked (meta = start | n << 20, see park_ids)
 template <class SM>
 __device__ __forceinline__ void set_parked(SM &sm, uint32_t k, uint32_t meta) {
-    sm.rec[k].x = (meta >> 20) | (CK_PARKED << 30);
-    sm.rec[k].y = meta & 0xFFFFF;
+    sm.rec[k] = make_uint2(meta & 0xFFFFF, REC_REF | (CK_PARKED << 29));
     sm.cnt[k] = meta >> 20;
 }
 
@@ -483,21 +506,23 @@ __device__ __noinline__ void scan_open_chunks(const EncArgs &a, SM &sm, uint32_t
 }
 
 
-// one chunk's ids -> dst[0 .. n) (shared-memory gather buffer, or the stream itself for oversized tiles); r = its record
+__device__ __forceinline__ bool rec_is_slot(const uint2 r) { return (r.y >> 29) == (4u | CK_SLOT); }
+
+// one chunk's ids -> dst[0 .. n), n > 0 (shared-memory gather buffer, or the stream itself for oversized tiles); r = its
+// record, q0 .. q3 = the value sector of its cache slot if rec_is_slot(r) (the caller has all of a thread's in flight together)
 template <class SM>
-__device__ __forceinline__ void emit_chunk(const EncArgs &a, SM &sm, const uint4 r, uint32_t *dst, uint64_t room) {
-    const uint32_t n = r.x & 0x3FFFFFFFu, kind = r.x >> 30;
+__device__ __forceinline__ void emit_chunk(const EncArgs &a, SM &sm, const uint2 r, uint32_t n, uint64_t q0, uint64_t q1, uint64_t q2,
+                                           uint64_t q3, uint32_t *dst, uint64_t room) {
+    const uint32_t kind = (r.y & REC_REF) ? (r.y >> 29) & 3u : CK_REGS;
     if (n > room) {
         *a.overflow = 1;
         return;
     }
-    if (kind == CK_REGS) { // y, z = the key sector's id word: three ids of 21 bits
-        dst[0] = r.y & 0x1FFFFFu;
-        if (n > 1) dst[1] = __funnelshift_r(r.y, r.z, CACHE_ID_BITS) & 0x1FFFFFu;
-        if (n > 2) dst[2] = r.z >> (2 * CACHE_ID_BITS - 32);
-    } else if (kind == CK_SLOT) {
-        uint64_t q0, q1, q2, q3; // n, v[0 .. 6]
-        ld_sector256(reinterpret_cast<const uint8_t *>(&a.cache.slots[r.y]) + 32, q0, q1, q2, q3);
+    if (kind == CK_REGS) { // {x, y} = the key sector's id word: three ids of 21 bits
+        dst[0] = r.x & 0x1FFFFFu;
+        if (n > 1) dst[1] = __funnelshift_r(r.x, r.y, CACHE_ID_BITS) & 0x1FFFFFu;
+        if (n > 2) dst[2] = r.y >> (2 * CACHE_ID_BITS - 32);
+    } else if (kind == CK_SLOT) { // q = n, v[0 .. 6]
         if (n <= CACHE_INLINE_IDS) {
             dst[0] = (uint32_t)(q0 >> 32);
             if (n > 1) dst[1] = (uint32_t)q1;
@@ -513,23 +538,49 @@ __device__ __forceinline__ void emit_chunk(const EncArgs &a, SM &sm, const uint4
         }
     } else if (kind == CK_PARKED) {
 #pragma unroll 1
-        for (uint32_t i = 0; i < n; i++) dst[i] = park_load(a, sm, r.y + i);
+        for (uint32_t i = 0; i < n; i++) dst[i] = park_load(a, sm, r.x + i);
     } else {
 #pragma unroll 1
-        for (uint32_t i = 0; i < n; i++) dst[i] = a.scratch_a[r.y + i];
+        for (uint32_t i = 0; i < n; i++) dst[i] = a.scratch_a[r.x + i];
     }
 }
 
-// thread 0: ticket, then the tile's boundaries and text window into shared memory by bulk copies.
-// Publishes sm.tile / sm.a0 / sm.staged and completes sm.bar_tile when everything has landed.
+// The ids of this thread's CPT chunks (chunk j * THREADS + tid at place[j] of the tile) -> dst + place[j]. Chunks whose
+// ids sit in the value sector of their cache slot fetch it first, all of them before the first use: one round trip per
+// thread, not one per chunk.
+template <int THREADS, int CPT, class SM>
+__device__ __forceinline__ void gather_chunks(const EncArgs &a, SM &sm, const uint32_t *place, uint32_t *dst, uint64_t room) {
+    uint64_t q[CPT][4];
+#pragma unroll
+    for (int j = 0; j < CPT; j++) {
+        const uint32_t k = j * THREADS + threadIdx.x;
+        const uint2 r = sm.rec[k];
+        q[j][0] = q[j][1] = q[j][2] = q[j][3] = 0;
+        if (rec_is_slot(r) && sm.cnt[k])
+            ld_sector256(reinterpret_cast<const uint8_t *>(&a.cache.slots[r.x]) + 32, q[j][0], q[j][1], q[j][2], q[j][3]);
+    }
+#pragma unroll
+    for (int j = 0; j < CPT; j++) { // (record and count are read again: cheaper than keeping them across the loads)
+        const uint32_t k = j * THREADS + threadIdx.x, n = sm.cnt[k];
+        if (n) emit_chunk(a, sm, sm.rec[k], n, q[j][0], q[j][1], q[j][2], q[j][3], dst + place[j], room > place[j] ? room - place[j] : 0);
+    }
+}
+
+// thread 0: ticket, then the tile's boundaries and text window into shared memory by bulk copies. Publishes sm.tile /
+// sm.a0 / sm.staged and completes sm.bar_tile when everything has landed.
+// The ticket is taken as LATE as possible, when the CTA has nothing else left to do but store its ids. Taking it earlier
+// (to prefetch the next tile during the gather or the look-back) was measured twice and is a disaster: a CTA that holds
+// a ticket while it waits in a look-back blocks every later tile, whose CTAs then hold THEIR next tickets longer -- the
+// look-back went from 4.5 k to 45 k cycles per tile. Tiles must start in stream order, and a ticket must not be held idle.
 template <class SM>
-__device__ __forceinline__ void fetch_tile_bulk(const EncArgs &a, SM &sm, uint32_t &off_parity, uint64_t policy) {
-    const uint32_t t = atomicAdd(a.ticket, 1u); // tiles start in order: look-back cannot deadlock
+__device__ __forceinline__ void fetch_tile_bulk(const EncArgs &a, SM &sm, uint32_t &off_parity) {
+    const uint32_t t = atomicAdd(a.ticket, 1u);
     if (t >= a.n_tiles) {
         sm.tile = TILE_NONE;
         mbar_arrive(&sm.bar_tile);
         return;
     }
+    const uint64_t policy = l2_evict_first_policy();
     const uint64_t c0 = a.chunk0 + (uint64_t)t * SM::TILE;
     const uint32_t nc = (uint32_t)min((uint64_t)SM::TILE, a.chunk1 - c0);
     const uint32_t nw = nc + 1, nb = nw & ~3u; // whole 16-byte vectors by bulk copy, the last <= 3 words by hand
@@ -568,7 +619,7 @@ __device__ __forceinline__ void fetch_tile_bulk(const EncArgs &a, SM &sm, uint32
 // neighbouring chunks, so their shared-memory traffic is conflict free and their ids land side by side; step 3a (the count
 // scan) takes CPT consecutive chunks per thread. Nothing about a chunk is kept in registers between the steps: it is all
 // in the chunk's record in shared memory, which is what lets the probe loop run at 64 registers without spilling.
-template <int THREADS, int CPT, int MIN_CTAS, int PIF>
+template <int THREADS, int CPT, int MIN_CTAS, int PIF, int LD>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const __grid_constant__ EncArgs a) {
     using SM = EncSmemT<THREADS, CPT>;
     constexpr int TILE = SM::TILE, NW = THREADS / 32;
@@ -605,11 +656,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const __grid
         }
     };
     uint32_t tile_parity = 0, off_parity = 0;
-    uint64_t policy = 0;
-    if (bulk && tid == 0) {
-        policy = l2_evict_first_policy();
-        fetch_tile_bulk(a, sm, off_parity, policy);
-    }
+    if (bulk && tid == 0) fetch_tile_bulk(a, sm, off_parity);
     for (;;) {
         // ---- 0. the tile's boundaries and text in shared memory ----------------------------------------------------
         if (bulk) {
@@ -657,7 +704,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const __grid
                 o0[p] = sm.off[min(k, nc)];
                 len[p] = sm.off[min(k + 1, nc)] - o0[p]; // (0 past the tile's end)
                 if (keyed) {
-                    // Chunks of 0 or more than 31 bytes build a key and probe like everybody else -- the text window has a
+                    // Chunks of 0 or more than CACHE_MAX_LEN bytes build a key and probe like everybody else -- the text window has a
                     // halo, the slot address is always valid -- and ignore the answer.
                     const uint32_t r = o0[p] - a0, wi = r >> 2, sh = (r & 3) * 8;
                     const uint4 lm = sm.len_mask[min(len[p], 16u)];
@@ -680,16 +727,17 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const __grid
                         if (k2[p] | b3) x ^= cache_hash_hi(k2[p], b3);
                     }
                     h[p] = cache_hash_fin(x) >> a.cache.shift;
-                    ld_sector256(&a.cache.slots[h[p]], q0[p], q1[p], q2[p], q3[p]);
+                    ld_sector256<LD>(&a.cache.slots[h[p]], q0[p], q1[p], q2[p], q3[p]);
                 }
             }
 #pragma unroll
             for (int p = 0; p < PIF; p++) {
                 const uint32_t k = (g + p) * THREADS + tid;
                 const bool short_key = len[p] <= CACHE_SHORT_KEY;
-                // a short key owns k[0], k[1] and the length byte of its sector (the rest is the answer), a long one all of it
+                // a short key owns k[0], k[1] and the length byte of its sector (the rest is the answer), a long one all but the count byte
                 auto same_key = [&]() {
-                    return q0[p] == k0[p] && q1[p] == k1[p] && (short_key ? (q3[p] >> 56) == len[p] : (q2[p] == k2[p] && q3[p] == k3[p]));
+                    return q0[p] == k0[p] && q1[p] == k1[p] &&
+                           (short_key ? (q3[p] >> 56) == len[p] : (q2[p] == k2[p] && (q3[p] & ~CACHE_LONG_N_MASK) == k3[p]));
                 };
                 bool hit = false;
                 if (keyed && len[p] - 1u < CACHE_MAX_LEN) {
@@ -698,7 +746,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const __grid
 #pragma unroll 1
                         for (uint32_t probes = 1; probes < CACHE_MAX_PROBES; probes++) {
                             h[p] = (h[p] + 1) & a.cache.mask;
-                            ld_sector256(&a.cache.slots[h[p]], q0[p], q1[p], q2[p], q3[p]);
+                            ld_sector256<LD>(&a.cache.slots[h[p]], q0[p], q1[p], q2[p], q3[p]);
                             if (q3[p] == 0) break;
                             if (same_key()) {
                                 hit = true;
@@ -707,37 +755,37 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const __grid
                         }
                     }
                 }
-                uint4 rec = make_uint4(0, 0, 0, 0); // (x = count | kind << 30)
+                uint2 rec = make_uint2(0, 0);
+                uint32_t n = 0;
                 if (hit) {
                     if (short_key && !(q3[p] & CACHE_NOT_INLINE)) { // nine chunks in ten end here
-                        rec.x = (uint32_t)q3[p] & 0x7Fu;
-                        rec.y = (uint32_t)q2[p];
-                        rec.z = (uint32_t)(q2[p] >> 32);
+                        n = (uint32_t)q3[p] & 0x7Fu;
+                        rec = make_uint2((uint32_t)q2[p], (uint32_t)(q2[p] >> 32));
                     } else {
-                        rec.x = (short_key ? ((uint32_t)q3[p] & 0x7Fu) : __ldg(&a.cache.slots[h[p]].n)) | (CK_SLOT << 30);
-                        rec.y = h[p];
+                        n = short_key ? ((uint32_t)q3[p] & 0x7Fu) : (uint32_t)(q3[p] >> CACHE_LONG_N_SHIFT) & 0xFFu;
+                        rec = make_uint2(h[p], REC_REF | (CK_SLOT << 29));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(&a.cache.slots[h[p]].n)); // (the gather reads the value sector)
                     }
                 } else if (len[p] != 0) {
                     if (len[p] > ENC_SHORT_MAX) {
-                        rec.x = CK_LONG << 30;
-                        rec.y = o0[p];
+                        rec = make_uint2(o0[p], REC_REF | (CK_LONG << 29));
                         if (a.scratch_b) {
-                            rec.x |= a.scratch_b[o0[p]]; // encoded by k_encode_long
-                        } else {                         // optimistic launch: report it, the host runs the long path and repeats
+                            n = a.scratch_b[o0[p]]; // encoded by k_encode_long
+                        } else {                    // optimistic launch: report it, the host runs the long path and repeats
                             const uint32_t q = atomicAdd(a.n_long, 1u);
                             if (q < a.long_cap) a.long_list[q] = (uint32_t)(c0 + k);
                         }
                     } else if (a.ablate & 2) {
-                        rec.x = 2;
-                        rec.y = o0[p] | (len[p] << CACHE_ID_BITS);
+                        n = 2;
+                        rec = make_uint2(o0[p] | (len[p] << CACHE_ID_BITS), 0);
                     } else {
                         const uint32_t q = atomicAdd(&sm.n_open, 1u);
                         sm.open_k[q] = (uint16_t)k;
-                        rec.x = CK_PARKED << 30; // (count and place: set_parked)
+                        rec.y = REC_REF | (CK_PARKED << 29); // (count and place: set_parked)
                     }
                 }
                 sm.rec[k] = rec;
-                sm.cnt[k] = rec.x & 0x3FFFFFFFu;
+                sm.cnt[k] = n;
             }
         }
         __syncthreads();
@@ -751,7 +799,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const __grid
             }
         }
         lap(2);
-        // ---- 3a. count scan: CPT consecutive chunks per thread; cnt[k] becomes the offset within the warp's segment ----
+        // ---- 3a. count scan: CPT consecutive chunks per thread -> loc[k], the chunk's offset within the warp's segment -----
         {
             uint32_t c[CPT];
             if constexpr (CPT == 2) {
@@ -784,12 +832,13 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const __grid
                 c[i] = run;
                 run += n;
             }
+            // (loc lies over the boundaries: the scan list was their last reader, and a barrier has passed since)
             if constexpr (CPT == 2) {
-                reinterpret_cast<uint2 *>(sm.cnt)[tid] = make_uint2(c[0], c[1]);
+                reinterpret_cast<uint2 *>(sm.loc)[tid] = make_uint2(c[0], c[1]);
             } else {
 #pragma unroll
                 for (int q = 0; q < CPT / 4; q++)
-                    reinterpret_cast<uint4 *>(sm.cnt)[tid * (CPT / 4) + q] = make_uint4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]);
+                    reinterpret_cast<uint4 *>(sm.loc)[tid * (CPT / 4) + q] = make_uint4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]);
             }
             if (lane == 31) sm.warp_sum[warp] = incl;
         }
@@ -807,37 +856,34 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const __grid
                 if (w < j * SEG_PER_J + (int)(warp / CPT)) pre[j] += v;
             total += v;
         }
-        if (warp == 0) {
-            const uint64_t b = (a.ablate & 1) ? (uint64_t)tile * (TILE * 9 / 4) : lookback_base<4>(a.status, tile, total, a.stream_base);
-            if (lane == 0) sm.base = b;
-        }
+        long long t_dbg = a.prof ? clock64() : 0;
+        // warp 0 announces the tile's id count, gathers its share like everybody else, and only then walks the predecessors:
+        // most of them have announced themselves by then, so the walk rarely has to wait
+        uint64_t base0 = 0;
+        if (warp == 0 && !(a.ablate & 1)) base0 = lookback_announce(a.status, tile, total, a.stream_base);
         const bool via_smem = total <= (uint32_t)SM::STAGE;
 #pragma unroll
-        for (int j = 0; j < CPT; j++) {
-            const uint32_t k = j * THREADS + tid;
-            pre[j] += sm.cnt[k]; // = the chunk's place in the tile
-            if (via_smem && !(a.ablate & 4)) {
-                const uint4 r = sm.rec[k];
-                if (r.x & 0x3FFFFFFFu) emit_chunk(a, sm, r, sm.stage + pre[j], ~0ull);
-            }
+        for (int j = 0; j < CPT; j++) pre[j] += sm.loc[j * THREADS + tid]; // = the chunk's place in the tile
+        if (via_smem && !(a.ablate & 4)) gather_chunks<THREADS, CPT>(a, sm, pre, sm.stage, ~0ull);
+        if (a.prof && (tid == 0 || tid == 32)) { const long long t = clock64(); sm.prof[tid ? 11 : 9] += t - t_dbg; t_dbg = t; }
+        if (warp == 0) {
+            const uint64_t b = (a.ablate & 1) ? (uint64_t)tile * (TILE * 9 / 4) : lookback_resolve<4>(a.status, tile, total, base0);
+            if (lane == 0) sm.base = b;
         }
+        if (a.prof && tid == 0) { const long long t = clock64(); sm.prof[8] += t - t_dbg; t_dbg = t; }
         __syncthreads();
+        if (a.prof && (tid == 0 || tid == 32)) { const long long t = clock64(); sm.prof[tid ? 12 : 10] += t - t_dbg; t_dbg = t; }
         lap(4);
         const uint64_t base = sm.base;
         if (!via_smem && !(a.ablate & 4)) { // a tile with more ids than the gather buffer holds: every thread stores its own
-#pragma unroll
-            for (int j = 0; j < CPT; j++) {
-                const uint4 r = sm.rec[j * THREADS + tid];
-                const uint64_t at = base + pre[j];
-                if (r.x & 0x3FFFFFFFu) emit_chunk(a, sm, r, a.out + at, at < a.out_cap ? a.out_cap - at : 0);
-            }
-            __syncthreads(); // (emit reads the records and the parking area: they are replaced below)
+            gather_chunks<THREADS, CPT>(a, sm, pre, a.out + base, base < a.out_cap ? a.out_cap - base : 0);
+            __syncthreads(); // (the gather reads the records and the parking area: they are replaced below)
         }
         // ---- 4. the next tile's loads start now; this tile's ids leave as whole lines --------------------------------
         if (bulk && tid == 0) {
             sm.n_open = 0; // (everybody is past the scan list; the next tile's appends come after the next mbarrier wait)
             sm.park_used = 0;
-            fetch_tile_bulk(a, sm, off_parity, policy);
+            fetch_tile_bulk(a, sm, off_parity);
         }
         lap(5);
         if (a.out_off) {

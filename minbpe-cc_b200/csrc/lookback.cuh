@@ -14,16 +14,27 @@ constexpr uint64_t LB_AGG = 1ull << 62, LB_PREFIX = 2ull << 62, LB_VAL = (1ull <
 // one L2 round trip), so a tile that starts while several hundred older tiles are still in flight resolves its base
 // in a handful of rounds instead of hundreds of serial loads. W = 1 is the round-1 behaviour; the tile kernels of
 // encode and decode use W = 4 (128 predecessors per round trip: with ~900 tiles in flight the walk is <= 8 rounds).
-template <int W = 1>
-__device__ __forceinline__ uint64_t lookback_base(unsigned long long *status, uint32_t tile, uint64_t total,
-                                                  const unsigned long long *first_base = nullptr) {
-    const uint32_t lane = threadIdx.x & 31;
+// The two halves of a look-back, for callers that have work to do in between (the longer the gap, the more of the
+// predecessors have announced themselves by the time the walk starts). announce: this tile's total becomes visible.
+// Returns the base of tile 0 (ids of earlier launches; read ONCE, here: the stream's last tile may overwrite the word as
+// soon as tile 0 is announced), 0 for the other tiles.
+__device__ __forceinline__ uint64_t lookback_announce(unsigned long long *status, uint32_t tile, uint64_t total,
+                                                      const unsigned long long *first_base = nullptr) {
     if (tile == 0) {
-        const uint64_t b = first_base ? *first_base : 0;
-        if (lane == 0) atomicExch(&status[0], LB_PREFIX | (b + total));
+        const uint64_t b = first_base ? *((const volatile unsigned long long *)first_base) : 0;
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) atomicExch(&status[0], LB_PREFIX | (b + total));
         return b;
     }
-    if (lane == 0) atomicExch(&status[tile], LB_AGG | total);
+    if ((threadIdx.x & 31) == 0) atomicExch(&status[tile], LB_AGG | total);
+    return 0;
+}
+// resolve: the walk over the predecessors; returns the tile's base and publishes its inclusive prefix.
+// base0 = what lookback_announce returned.
+template <int W = 1>
+__device__ __forceinline__ uint64_t lookback_resolve(unsigned long long *status, uint32_t tile, uint64_t total, uint64_t base0) {
+    const uint32_t lane = threadIdx.x & 31;
+    if (tile == 0) return base0;
     uint64_t acc = 0;
     int64_t j = (int64_t)tile - 1; // lane l, word w looks at tile j - (w * 32 + l): nearest predecessors first
     for (;;) {
@@ -56,6 +67,13 @@ __device__ __forceinline__ uint64_t lookback_base(unsigned long long *status, ui
     }
     if (lane == 0) atomicExch(&status[tile], LB_PREFIX | (acc + total));
     return acc;
+}
+
+template <int W = 1>
+__device__ __forceinline__ uint64_t lookback_base(unsigned long long *status, uint32_t tile, uint64_t total,
+                                                  const unsigned long long *first_base = nullptr) {
+    const uint64_t b0 = lookback_announce(status, tile, total, first_base);
+    return lookback_resolve<W>(status, tile, total, b0);
 }
 
 } // namespace mbpe
