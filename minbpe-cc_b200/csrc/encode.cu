@@ -147,42 +147,74 @@ struct DecArgs {
     uint32_t n_tiles;
 };
 
-// A tile = DEC_THREADS x DEC_IPT consecutive ids. Each thread owns DEC_IPT consecutive ids: coalesced 16-byte id
-// loads; one 8-byte load per id from a packed table answers "how long, which bytes" for tokens of up to 7 bytes (nearly
-// all of them; the table is 8 B x vocab, L2 resident); block scan of the lengths; then warp 0 resolves the tile's place in
-// the byte stream by decoupled look-back (128 predecessors per round trip) and takes the NEXT tile's ticket WHILE the other
-// warps gather the tile's bytes in shared memory at tile-local offsets. The tile leaves as aligned 4-byte words (128 bytes
-// per warp store): the misalignment of the tile's base is absorbed by a funnel shift over the shared-memory image.
-// Tiles whose bytes do not fit the staging buffer store directly.
-constexpr int DEC_THREADS = 256, DEC_IPT = 8, DEC_IDS = DEC_THREADS * DEC_IPT;
-constexpr uint32_t DEC_STAGE = 24576; // bytes staged per tile (avg ~5 KB)
+// A tile = THREADS x DEC_IPT consecutive ids, one CTA. Each thread owns DEC_IPT consecutive ids: coalesced 16-byte id
+// loads; one 8-byte word per id from a packed table answers "how long, which bytes" for tokens of up to 7 bytes (nearly
+// all of them). The first TAB_IDS entries of that table live in SHARED memory (ids are handed out in merge order, so the
+// low ids are the frequent ones): a random 8-byte gather costs a few shared-memory wavefronts there, against one L1 tag
+// look-up per lane on the global path, which is what bounded the round-1 kernel. Block scan of the lengths; then warp 0
+// resolves the tile's place in the byte stream by decoupled look-back (128 predecessors per round trip) and takes the NEXT
+// tile's ticket WHILE the other warps assemble the tile's bytes in shared memory at tile-local offsets -- each thread
+// shifts its tokens into a 64-bit register and stores whole words (the first and the last word of its run, which it shares
+// with its neighbours, byte by byte). The tile leaves as aligned 4-byte words (128 bytes per warp store): the
+// misalignment of the tile's base is absorbed by a funnel shift over the shared-memory image. Tiles whose bytes do not
+// fit the staging buffer store directly.
+constexpr int DEC_IPT = 8;
 
-struct DecSmem {
-    alignas(16) uint32_t stage[DEC_STAGE / 4 + 4];
-    uint32_t s_warp[DEC_THREADS / 32];
+// The CTA's threads work in GROUPS of GROUP threads: every group runs its own stream of tiles (own ticket, own image, own
+// named barrier) and all of them share the one table. Measured (1 GiB of text, ms): groups of 1024: 4.05, 512: 3.95,
+// 256: 4.87, 128: 5.57 -- every tile pays a fixed price (look-back walk, ticket, two barriers), so small tiles lose.
+template <int GROUP>
+struct DecGroupSmemT {
+    static constexpr uint32_t STAGE = GROUP * DEC_IPT * 3; // bytes staged per tile (average ~2.4 bytes per id)
+    alignas(16) uint32_t stage[STAGE / 4 + 4];
+    uint32_t s_warp[32];
     uint32_t s_tile[2];
     unsigned long long s_base;
 };
+template <int THREADS, int TAB_IDS, int GROUP>
+struct DecSmemT {
+    alignas(16) unsigned long long tab[TAB_IDS ? TAB_IDS : 1];
+    DecGroupSmemT<GROUP> grp[THREADS / GROUP];
+};
+__device__ __forceinline__ void group_barrier(uint32_t id, uint32_t n_threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
+}
 
-__global__ void __launch_bounds__(DEC_THREADS) k_decode_tiles(const DecArgs a) {
-    __shared__ DecSmem sm;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+template <int THREADS, int TAB_IDS, int MIN_CTAS, int GROUP>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS) k_decode_tiles(const __grid_constant__ DecArgs a) {
+    static_assert(THREADS % GROUP == 0 && GROUP % 32 == 0 && THREADS / GROUP <= 15, "one named barrier per group");
+    constexpr int NW = GROUP / 32;
+    constexpr uint32_t DEC_IDS = GROUP * DEC_IPT, DEC_STAGE = DecGroupSmemT<GROUP>::STAGE;
+    extern __shared__ __align__(16) unsigned char dec_smem_raw[];
+    DecSmemT<THREADS, TAB_IDS, GROUP> &cta = *reinterpret_cast<DecSmemT<THREADS, TAB_IDS, GROUP> *>(dec_smem_raw);
+    DecGroupSmemT<GROUP> &sm = cta.grp[threadIdx.x / GROUP];
+    const uint32_t tid = threadIdx.x % GROUP, lane = tid & 31, warp = tid >> 5; // (within the group)
+    const uint32_t bar_id = 1 + threadIdx.x / GROUP;
     uint8_t *const stage8 = reinterpret_cast<uint8_t *>(sm.stage);
+    if (TAB_IDS && a.v_pack)
+        for (uint32_t i = threadIdx.x; i < (uint32_t)TAB_IDS; i += THREADS) cta.tab[i] = i < a.vocab_size ? __ldg(&a.v_pack[i]) : 0xFFull;
     if (tid == 0) sm.s_tile[0] = atomicAdd(a.ticket, 1u); // tiles start in order: look-back cannot deadlock
     __syncthreads();
+    uint32_t nxt[DEC_IPT];
+    auto load_ids = [&](uint32_t t, uint32_t *dst) { // this thread's ids of tile t (0xFFFFFFFF past the end)
+        const uint64_t k = (uint64_t)t * DEC_IDS + (uint64_t)tid * DEC_IPT;
+        if (t < a.n_tiles && k + DEC_IPT <= a.n_ids) { // ids is 16-byte aligned (device allocation), k a multiple of 8
+            const uint4 q0 = __ldcs(reinterpret_cast<const uint4 *>(a.ids + k));
+            const uint4 q1 = __ldcs(reinterpret_cast<const uint4 *>(a.ids + k + 4));
+            dst[0] = q0.x, dst[1] = q0.y, dst[2] = q0.z, dst[3] = q0.w, dst[4] = q1.x, dst[5] = q1.y, dst[6] = q1.z, dst[7] = q1.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < DEC_IPT; j++) dst[j] = (t < a.n_tiles && k + j < a.n_ids) ? __ldcs(a.ids + k + j) : 0xFFFFFFFFu;
+        }
+    };
     for (uint32_t it = 0;; it++) {
         const uint32_t tile = sm.s_tile[it & 1];
         if (tile >= a.n_tiles) return;
         const uint64_t k0 = (uint64_t)tile * DEC_IDS + (uint64_t)tid * DEC_IPT;
         uint32_t id[DEC_IPT];
-        if (k0 + DEC_IPT <= a.n_ids) { // ids is 16-byte aligned (device allocation), k0 a multiple of 8
-            const uint4 q0 = __ldcs(reinterpret_cast<const uint4 *>(a.ids + k0));
-            const uint4 q1 = __ldcs(reinterpret_cast<const uint4 *>(a.ids + k0 + 4));
-            id[0] = q0.x, id[1] = q0.y, id[2] = q0.z, id[3] = q0.w, id[4] = q1.x, id[5] = q1.y, id[6] = q1.z, id[7] = q1.w;
-        } else {
+        if (it == 0) load_ids(tile, nxt);
 #pragma unroll
-            for (int j = 0; j < DEC_IPT; j++) id[j] = k0 + j < a.n_ids ? __ldcs(a.ids + k0 + j) : 0xFFFFFFFFu;
-        }
+        for (int j = 0; j < DEC_IPT; j++) id[j] = nxt[j]; // (loaded while the previous tile was being stored)
         unsigned long long pk[DEC_IPT]; // low byte: length (0xFF: long / special -> resolved through the index), then the bytes
         uint32_t len[DEC_IPT], sum = 0;
         auto find_special = [&](uint32_t idv) -> int { // special tokens override the vocabulary (Tokenizer.h:733)
@@ -200,7 +232,11 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode_tiles(const DecArgs a) {
         };
         constexpr unsigned long long PK_SPECIAL = 1ull << 63; // with low byte 0xFF: bits 8..39 = index of the special token
 #pragma unroll
-        for (int j = 0; j < DEC_IPT; j++) pk[j] = (a.v_pack && k0 + j < a.n_ids && id[j] < a.vocab_size) ? __ldg(&a.v_pack[id[j]]) : 0xFFull;
+        for (int j = 0; j < DEC_IPT; j++) {
+            pk[j] = 0xFFull;
+            if (a.v_pack && k0 + j < a.n_ids && id[j] < a.vocab_size)
+                pk[j] = (TAB_IDS && id[j] < (uint32_t)TAB_IDS) ? cta.tab[id[j]] : __ldg(&a.v_pack[id[j]]);
+        }
 #pragma unroll
         for (int j = 0; j < DEC_IPT; j++) {
             len[j] = 0;
@@ -225,45 +261,80 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode_tiles(const DecArgs a) {
             if (lane >= d) incl += v;
         }
         if (lane == 31) sm.s_warp[warp] = incl;
-        __syncthreads();
-        uint32_t warp_base = 0, total = 0;
+        group_barrier(bar_id, GROUP);
+        uint32_t warp_base, total;
+        { // every warp scans the warp sums itself (lane w holds warp w's)
+            const uint32_t mine = lane < NW ? sm.s_warp[lane] : 0u;
+            uint32_t wi = mine;
 #pragma unroll
-        for (int w = 0; w < DEC_THREADS / 32; w++) {
-            const uint32_t v = sm.s_warp[w];
-            if (w < (int)warp) warp_base += v;
-            total += v;
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += v;
+            }
+            total = __shfl_sync(0xffffffffu, wi, 31);
+            warp_base = __shfl_sync(0xffffffffu, wi - mine, warp);
         }
-        if (warp == 0) { // the other warps gather their bytes meanwhile
-            const uint64_t b = lookback_base<4>(a.status, tile, total);
+        // warp 0 announces the tile's size, assembles its share like everybody else, and only then walks the predecessors
+        uint64_t base0 = 0;
+        if (warp == 0) base0 = lookback_announce(a.status, tile, total);
+        const bool via_smem = a.out != nullptr && total <= DEC_STAGE;
+        const uint32_t loc0 = warp_base + (incl - sum);
+        // the bytes of a token that is not in the packed word (longer than 7 bytes, or a special token)
+        auto long_src = [&](int j) -> const uint8_t * {
+            return (pk[j] & PK_SPECIAL) ? a.sp_bytes + __ldg(&a.sp_off[(uint32_t)(pk[j] >> 8)]) : a.v_bytes + __ldg(&a.v_off[id[j]]);
+        };
+        if (via_smem) {
+            // This thread's tokens -> stage8[loc0 ..): bytes are shifted into `acc` behind the `fill` (< 4) bytes that precede
+            // them in the current word; whole words are stored as words, except the first one of the run if it starts
+            // inside a word (`head`: those leading bytes belong to the neighbour), and the tail: byte by byte.
+            uint32_t wpos = loc0 & ~3u, fill = loc0 & 3u, head = fill;
+            unsigned long long acc = 0;
+            auto put_word = [&](uint32_t w, uint32_t upto) { // bytes [head, upto) of the word at wpos
+                if (head == 0 && upto == 4) {
+                    sm.stage[wpos >> 2] = w;
+                } else {
+                    for (uint32_t b = head; b < upto; b++) stage8[wpos + b] = (uint8_t)(w >> (8 * b));
+                }
+                head = 0;
+            };
+#pragma unroll
+            for (int j = 0; j < DEC_IPT; j++) {
+                if (len[j] == 0) continue;
+                if ((pk[j] & 0xFF) != 0xFF) { // <= 7 bytes, in the register (zero padded)
+                    const unsigned long long v = pk[j] >> 8;
+                    acc |= v << (8 * fill);
+                    uint32_t over = fill ? (uint32_t)(v >> (64 - 8 * fill)) : 0u; // (what the shift pushed out: fill + len <= 10 bytes)
+                    fill += len[j];
+                    while (fill >= 4) {
+                        put_word((uint32_t)acc, 4);
+                        acc = (acc >> 32) | ((unsigned long long)over << 32);
+                        over = 0;
+                        fill -= 4;
+                        wpos += 4;
+                    }
+                } else { // rare: pending bytes out, then the token byte by byte, then start over at its end
+                    put_word((uint32_t)acc, fill);
+                    const uint8_t *src = long_src(j);
+                    const uint32_t at = wpos + fill;
+                    for (uint32_t i = 0; i < len[j]; i++) stage8[at + i] = __ldg(src + i);
+                    const uint32_t end = at + len[j];
+                    wpos = end & ~3u;
+                    fill = head = end & 3u;
+                    acc = 0;
+                }
+            }
+            put_word((uint32_t)acc, fill);
+        }
+        if (warp == 0) {
+            const uint64_t b = lookback_resolve<4>(a.status, tile, total, base0);
             if (lane == 0) {
                 sm.s_base = b;
                 sm.s_tile[(it + 1) & 1] = atomicAdd(a.ticket, 1u); // (this tile's size is published: successors do not wait for us)
             }
         }
-        const bool via_smem = a.out != nullptr && total <= DEC_STAGE;
-        const uint32_t loc0 = warp_base + (incl - sum);
-        // the bytes of this thread's tokens -> dst[0 ..), dst = the shared-memory image or the stream itself
-        auto emit = [&](uint8_t *dst, uint64_t room) {
-            uint32_t loc = 0;
-#pragma unroll
-            for (int j = 0; j < DEC_IPT; j++) {
-                if (len[j] == 0) continue;
-                if (loc + len[j] <= room) {
-                    if ((pk[j] & 0xFF) != 0xFF) { // bytes are in the register
-                        unsigned long long v = pk[j] >> 8;
-                        for (uint32_t i = 0; i < len[j]; i++, v >>= 8) dst[loc + i] = (uint8_t)v;
-                    } else {
-                        const uint8_t *src = (pk[j] & PK_SPECIAL) ? a.sp_bytes + __ldg(&a.sp_off[(uint32_t)(pk[j] >> 8)])
-                                                                    : a.v_bytes + __ldg(&a.v_off[id[j]]);
-                        for (uint32_t i = 0; i < len[j]; i++) dst[loc + i] = __ldg(src + i);
-                    }
-                }
-                loc += len[j];
-            }
-        };
-        if (via_smem) emit(stage8 + loc0, ~0ull);
-        __syncthreads();
+        group_barrier(bar_id, GROUP);
         const uint64_t base = sm.s_base;
+        load_ids(sm.s_tile[(it + 1) & 1], nxt); // the next tile's ids arrive while this one is stored
         if (a.out) {
             if (via_smem && base + total <= a.out_cap) {
                 // global word k of the tile = bytes [4k - pad, 4k - pad + 4) of the image; whole words by funnel shift
@@ -271,7 +342,7 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode_tiles(const DecArgs a) {
                 const uint64_t w0 = base - pad; // 4-byte aligned (out is a device allocation)
                 const uint32_t n_words = (pad + total + 3) >> 2;
                 uint32_t *const gw = reinterpret_cast<uint32_t *>(a.out + w0);
-                for (uint32_t k = tid; k < n_words; k += DEC_THREADS) {
+                for (uint32_t k = tid; k < n_words; k += GROUP) {
                     const int lo = (int)(4 * k) - (int)pad; // tile-local offset of the word's first byte
                     if (lo >= 0 && (uint32_t)lo + 4 <= total) {
                         const uint32_t j = (uint32_t)lo >> 2;
@@ -282,17 +353,45 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode_tiles(const DecArgs a) {
                     }
                 }
             } else if (via_smem) { // the end of a buffer that is too small: what fits, byte by byte
-                for (uint32_t i = tid; i < total; i += DEC_THREADS)
+                for (uint32_t i = tid; i < total; i += GROUP)
                     if (base + i < a.out_cap) a.out[base + i] = stage8[i];
-            } else {
+            } else { // a tile with more bytes than the image holds: every thread stores its own, byte by byte
                 const uint64_t at = base + loc0;
-                emit(a.out + at, at < a.out_cap ? a.out_cap - at : 0);
+                const uint64_t room = at < a.out_cap ? a.out_cap - at : 0;
+                uint8_t *const dst = a.out + at;
+                uint32_t loc = 0;
+#pragma unroll
+                for (int j = 0; j < DEC_IPT; j++) {
+                    if (len[j] == 0) continue;
+                    if (loc + len[j] <= room) {
+                        if ((pk[j] & 0xFF) != 0xFF) {
+                            unsigned long long v = pk[j] >> 8;
+                            for (uint32_t i = 0; i < len[j]; i++, v >>= 8) dst[loc + i] = (uint8_t)v;
+                        } else {
+                            const uint8_t *src = long_src(j);
+                            for (uint32_t i = 0; i < len[j]; i++) dst[loc + i] = __ldg(src + i);
+                        }
+                    }
+                    loc += len[j];
+                }
             }
         }
         if (tile == a.n_tiles - 1 && tid == 0) *a.d_n_out = base + total;
         // (the image is rewritten only after the next tile's first barrier, which every thread reaches after its stores)
     }
 }
+
+struct DecConfig {
+    int threads, group, ctas;
+    void (*kernel)(const DecArgs);
+    size_t smem;
+};
+#define DEC_CFG(T, I, M, G) DecConfig{T, G, M, k_decode_tiles<T, I, M, G>, sizeof(DecSmemT<T, I, G>)}
+// (threads, packed-vocabulary entries in shared memory, CTAs per SM, threads per tile group); 0 = default, the others for
+// A/B runs (MBPE_DEC_CFG)
+static const DecConfig dec_configs[] = {DEC_CFG(1024, 24576, 1, 512), DEC_CFG(1024, 24576, 1, 1024), DEC_CFG(1024, 24576, 1, 256),
+                                        DEC_CFG(256, 0, 4, 256),       DEC_CFG(512, 12288, 2, 256)};
+constexpr int N_DEC_CONFIGS = sizeof(dec_configs) / sizeof(dec_configs[0]);
 } // namespace mbpe
 
 using namespace mbpe;
@@ -339,6 +438,7 @@ struct mbpe_encoder {
     uint64_t sub_batch_chunks = 0; // fixed sub-batch size (MBPE_ENCODE_SUBBATCH), 0 = geometric schedule
     uint64_t chunks_seen = 0;      // chunks encoded so far with this handle: how warm the caches are
     int cfg = 0; // kernel shape, see enc_configs
+    int dec_cfg = 0; // see dec_configs
     size_t l2_window_max = 0, l2_persist_bytes = 0;
     // mbpe_encode (host buffers): pinned staging + device buffers of the segment pipeline, two of each
     struct HostPipe {
@@ -479,6 +579,10 @@ static int encoder_create_impl(mbpe_encoder *e, const uint32_t *merges, uint32_t
     }
     const char *cfg_env = getenv("MBPE_ENC_CFG");
     e->cfg = cfg_env && *cfg_env ? std::min(std::max(atoi(cfg_env), 0), N_ENC_CONFIGS - 1) : 0;
+    const char *dcfg_env = getenv("MBPE_DEC_CFG");
+    e->dec_cfg = dcfg_env && *dcfg_env ? std::min(std::max(atoi(dcfg_env), 0), N_DEC_CONFIGS - 1) : 0;
+    for (int i = 0; i < N_DEC_CONFIGS; i++)
+        MB_CUDA(cudaFuncSetAttribute(dec_configs[i].kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_configs[i].smem));
     for (int i = 0; i < N_ENC_CONFIGS; i++) {
         MB_CUDA(cudaFuncSetAttribute(enc_configs[i].kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_configs[i].smem));
         if (const char *co = getenv("MBPE_ENC_CARVEOUT")) // percent of the L1/shared array given to shared memory (A/B runs)
@@ -981,7 +1085,9 @@ extern "C" int mbpe_encode(mbpe_encoder *e, const uint8_t *bytes, uint64_t n_byt
 
 static int decode_launch(mbpe_encoder *e, const uint32_t *d_ids, uint64_t n_ids, uint8_t *d_out, uint64_t out_cap,
                          unsigned long long *d_n_out, cudaStream_t st) {
-    const uint64_t n_tiles = (n_ids + DEC_IDS - 1) / DEC_IDS;
+    const DecConfig &dc = dec_configs[e->dec_cfg];
+    const uint64_t tile_ids = (uint64_t)dc.group * DEC_IPT;
+    const uint64_t n_tiles = (n_ids + tile_ids - 1) / tile_ids;
     if (n_tiles >= 0xFFFFFFFFull) return set_error(MBPE_E_INVALID, "too many ids in one call");
     int rc = ensure_status(e, n_tiles);
     if (rc) return rc;
@@ -1004,8 +1110,9 @@ static int decode_launch(mbpe_encoder *e, const uint32_t *d_ids, uint64_t n_ids,
     a.out_cap = d_out ? out_cap : 0;
     MB_CUDA(cudaMemsetAsync(e->d_small, 0, 16, st));
     MB_CUDA(cudaMemsetAsync(e->d_status, 0, n_tiles * 8, st));
-    const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)e->sms * 6);
-    k_decode_tiles<<<grid, DEC_THREADS, 0, st>>>(a);
+    const uint64_t groups_per_cta = dc.threads / dc.group;
+    const unsigned grid = (unsigned)std::min<uint64_t>((n_tiles + groups_per_cta - 1) / groups_per_cta, (uint64_t)e->sms * dc.ctas);
+    dc.kernel<<<grid, dc.threads, dc.smem, st>>>(a);
     e->launches++;
     MB_CUDA(cudaGetLastError());
     return MBPE_OK;
