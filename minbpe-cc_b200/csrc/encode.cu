@@ -456,10 +456,10 @@ struct EncConfig {
     void (*kernel)(const EncArgs);
     size_t smem;
 };
-#define ENC_CFG(T, C, M, P, L) EncConfig{T, C, M, k_encode_tiles<T, C, M, P, L>, sizeof(EncSmemT<T, C>)}
-// (threads, chunks per thread, CTAs per SM, probes in flight per thread, L1 policy of the probe loads); 0 = default, the others for A/B runs (MBPE_ENC_CFG)
-static const EncConfig enc_configs[] = {ENC_CFG(256, 4, 4, 1, 0), ENC_CFG(256, 4, 4, 1, 3), ENC_CFG(256, 4, 3, 1, 0), ENC_CFG(512, 4, 2, 1, 0),
-                                        ENC_CFG(256, 8, 2, 1, 0), ENC_CFG(128, 4, 8, 1, 0), ENC_CFG(256, 4, 4, 2, 0), ENC_CFG(256, 4, 4, 1, 1)};
+#define ENC_CFG(T, C, M, P, L, R) EncConfig{T, C, M, k_encode_tiles<T, C, M, P, L, R>, sizeof(EncSmemT<T, C>)}
+// (threads, chunks per thread, CTAs per SM, probes in flight per thread, L1 policy of the probe loads, L2 prefetch pass); 0 = default, the others for A/B runs (MBPE_ENC_CFG)
+static const EncConfig enc_configs[] = {ENC_CFG(256, 4, 4, 1, 0, 0), ENC_CFG(256, 4, 4, 1, 0, 1), ENC_CFG(256, 4, 3, 1, 0, 0), ENC_CFG(512, 4, 2, 1, 0, 0),
+                                        ENC_CFG(256, 8, 2, 1, 0, 0), ENC_CFG(128, 4, 8, 1, 0, 0), ENC_CFG(512, 4, 2, 1, 0, 1), ENC_CFG(256, 8, 2, 1, 0, 1)};
 constexpr int N_ENC_CONFIGS = sizeof(enc_configs) / sizeof(enc_configs[0]);
 
 static ChunkCache cache_view(const mbpe_encoder *e) {

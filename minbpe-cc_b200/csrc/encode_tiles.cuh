@@ -26,6 +26,7 @@
 // chain of latencies of one tile (ticket -> boundaries -> text -> four dependent probe rounds -> look-back) at the
 // occupancy 64 registers x 256 threads x 4 CTAs allow; DESIGN.md "encode: what was tried" lists the measured dead ends.
 #pragma once
+#include <type_traits>
 #include "lookback.cuh"
 
 namespace mbpe {
@@ -619,7 +620,7 @@ __device__ __forceinline__ void fetch_tile_bulk(const EncArgs &a, SM &sm, uint32
 // neighbouring chunks, so their shared-memory traffic is conflict free and their ids land side by side; step 3a (the count
 // scan) takes CPT consecutive chunks per thread. Nothing about a chunk is kept in registers between the steps: it is all
 // in the chunk's record in shared memory, which is what lets the probe loop run at 64 registers without spilling.
-template <int THREADS, int CPT, int MIN_CTAS, int PIF, int LD>
+template <int THREADS, int CPT, int MIN_CTAS, int PIF, int LD, int PRE>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const __grid_constant__ EncArgs a) {
     using SM = EncSmemT<THREADS, CPT>;
     constexpr int TILE = SM::TILE, NW = THREADS / 32;
@@ -694,6 +695,44 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const __grid
         lap(0);
         // ---- 1. cache probes: every chunk's home slot, PIF of them in flight per thread ----------------------------
         const bool keyed = a.cache.slots != nullptr && staged && !(a.ablate & 2); // (an unstaged tile -- very long chunks -- is all scanned)
+        // key of chunk [o0, o0 + len) and, if WITH_HASH, its home slot. Chunks of 0 or more than CACHE_MAX_LEN bytes build a key
+        // and probe like everybody else -- the text window has a halo, the slot address is always valid -- and ignore the answer.
+        auto make_key = [&](auto with_hash, uint32_t o0, uint32_t len, uint64_t &k0, uint64_t &k1, uint64_t &k2, uint64_t &k3) -> uint32_t {
+            const uint32_t r = o0 - a0, wi = r >> 2, sh = (r & 3) * 8;
+            const uint4 lm = sm.len_mask[min(len, 16u)];
+            const uint32_t t0 = sm.text[wi], t1 = sm.text[wi + 1], t2 = sm.text[wi + 2], t3 = sm.text[wi + 3], t4 = sm.text[wi + 4];
+            const uint32_t w0 = __funnelshift_r(t0, t1, sh) & lm.x, w1 = __funnelshift_r(t1, t2, sh) & lm.y;
+            const uint32_t w2 = __funnelshift_r(t2, t3, sh) & lm.z, w3 = __funnelshift_r(t3, t4, sh) & lm.w;
+            k0 = ((uint64_t)w1 << 32) | w0;
+            k1 = ((uint64_t)w3 << 32) | w2;
+            k2 = 0;
+            k3 = (uint64_t)len << 56;
+            uint64_t x = 0;
+            if (decltype(with_hash)::value) x = cache_hash_lo(k0, k1);
+            if (len > CACHE_SHORT_KEY) { // one chunk in a hundred
+                const uint4 hm = sm.len_mask[min(len, 32u) - 16];
+                const uint32_t t5 = sm.text[wi + 5], t6 = sm.text[wi + 6], t7 = sm.text[wi + 7], t8 = sm.text[wi + 8];
+                const uint32_t w4 = __funnelshift_r(t4, t5, sh) & hm.x, w5 = __funnelshift_r(t5, t6, sh) & hm.y;
+                const uint32_t w6 = __funnelshift_r(t6, t7, sh) & hm.z, w7 = __funnelshift_r(t7, t8, sh) & hm.w & 0x00FFFFFFu;
+                k2 = ((uint64_t)w5 << 32) | w4;
+                const uint64_t b3 = ((uint64_t)w7 << 32) | w6;
+                k3 |= b3;
+                if (decltype(with_hash)::value && (k2 | b3)) x ^= cache_hash_hi(k2, b3);
+            }
+            return decltype(with_hash)::value ? cache_hash_fin(x) >> a.cache.shift : 0u;
+        };
+        // PRE: a first pass over the thread's chunks only computes the home slots and asks L2 for them, so that the probes
+        // below -- one round trip after the other -- find them there instead of each waiting for DRAM in its turn
+        uint32_t hpre[PRE ? CPT : 1];
+        if (PRE && keyed) {
+#pragma unroll
+            for (int j = 0; j < CPT; j++) {
+                const uint32_t k = j * THREADS + tid, o0 = sm.off[min(k, nc)], len = sm.off[min(k + 1, nc)] - o0;
+                uint64_t k0, k1, k2, k3;
+                hpre[j] = make_key(std::true_type{}, o0, len, k0, k1, k2, k3);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(&a.cache.slots[hpre[j]]) : "memory");
+            }
+        }
 #pragma unroll
         for (int g = 0; g < CPT; g += PIF) {
             uint64_t k0[PIF], k1[PIF], k2[PIF], k3[PIF], q0[PIF], q1[PIF], q2[PIF], q3[PIF];
@@ -704,29 +743,12 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const __grid
                 o0[p] = sm.off[min(k, nc)];
                 len[p] = sm.off[min(k + 1, nc)] - o0[p]; // (0 past the tile's end)
                 if (keyed) {
-                    // Chunks of 0 or more than CACHE_MAX_LEN bytes build a key and probe like everybody else -- the text window has a
-                    // halo, the slot address is always valid -- and ignore the answer.
-                    const uint32_t r = o0[p] - a0, wi = r >> 2, sh = (r & 3) * 8;
-                    const uint4 lm = sm.len_mask[min(len[p], 16u)];
-                    const uint32_t t0 = sm.text[wi], t1 = sm.text[wi + 1], t2 = sm.text[wi + 2], t3 = sm.text[wi + 3], t4 = sm.text[wi + 4];
-                    const uint32_t w0 = __funnelshift_r(t0, t1, sh) & lm.x, w1 = __funnelshift_r(t1, t2, sh) & lm.y;
-                    const uint32_t w2 = __funnelshift_r(t2, t3, sh) & lm.z, w3 = __funnelshift_r(t3, t4, sh) & lm.w;
-                    k0[p] = ((uint64_t)w1 << 32) | w0;
-                    k1[p] = ((uint64_t)w3 << 32) | w2;
-                    k2[p] = 0;
-                    k3[p] = (uint64_t)len[p] << 56;
-                    uint64_t x = cache_hash_lo(k0[p], k1[p]);
-                    if (len[p] > CACHE_SHORT_KEY) { // one chunk in a hundred
-                        const uint4 hm = sm.len_mask[min(len[p], 32u) - 16];
-                        const uint32_t t5 = sm.text[wi + 5], t6 = sm.text[wi + 6], t7 = sm.text[wi + 7], t8 = sm.text[wi + 8];
-                        const uint32_t w4 = __funnelshift_r(t4, t5, sh) & hm.x, w5 = __funnelshift_r(t5, t6, sh) & hm.y;
-                        const uint32_t w6 = __funnelshift_r(t6, t7, sh) & hm.z, w7 = __funnelshift_r(t7, t8, sh) & hm.w & 0x00FFFFFFu;
-                        k2[p] = ((uint64_t)w5 << 32) | w4;
-                        const uint64_t b3 = ((uint64_t)w7 << 32) | w6;
-                        k3[p] |= b3;
-                        if (k2[p] | b3) x ^= cache_hash_hi(k2[p], b3);
+                    if (PRE) {
+                        make_key(std::false_type{}, o0[p], len[p], k0[p], k1[p], k2[p], k3[p]);
+                        h[p] = hpre[g + p];
+                    } else {
+                        h[p] = make_key(std::true_type{}, o0[p], len[p], k0[p], k1[p], k2[p], k3[p]);
                     }
-                    h[p] = cache_hash_fin(x) >> a.cache.shift;
                     ld_sector256<LD>(&a.cache.slots[h[p]], q0[p], q1[p], q2[p], q3[p]);
                 }
             }

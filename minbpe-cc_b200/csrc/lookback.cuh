@@ -10,6 +10,13 @@ namespace mbpe {
 // ---------------------------------------------------------------------------------------------------------
 constexpr uint64_t LB_AGG = 1ull << 62, LB_PREFIX = 2ull << 62, LB_VAL = (1ull << 62) - 1;
 
+// status words are polled with GPU-scope relaxed loads (a `volatile` access compiles to a SYSTEM-scope one)
+__device__ __forceinline__ unsigned long long lb_load(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // Called by all 32 lanes of one warp. Each round inspects 32 * W predecessors at once (W independent loads per lane,
 // one L2 round trip), so a tile that starts while several hundred older tiles are still in flight resolves its base
 // in a handful of rounds instead of hundreds of serial loads. W = 1 is the round-1 behaviour; the tile kernels of
@@ -43,14 +50,14 @@ __device__ __forceinline__ uint64_t lookback_resolve(unsigned long long *status,
         for (int w = 0; w < W; w++) {
             const int64_t idx = j - (w * 32 + (int)lane);
             // tiles before 0 do not exist: tile 0 always ends the walk itself
-            v[w] = idx >= 0 ? *((volatile unsigned long long *)&status[idx]) : LB_PREFIX;
+            v[w] = idx >= 0 ? lb_load(&status[idx]) : LB_PREFIX;
         }
         bool done = false;
 #pragma unroll
         for (int w = 0; w < W; w++) {
             const int64_t idx = j - (w * 32 + (int)lane);
             if (idx >= 0)
-                while ((v[w] >> 62) == 0) v[w] = *((volatile unsigned long long *)&status[idx]); // not published yet
+                while ((v[w] >> 62) == 0) v[w] = lb_load(&status[idx]); // not published yet
             const unsigned pm = __ballot_sync(0xffffffffu, (v[w] & LB_PREFIX) != 0);
             uint64_t val = v[w] & LB_VAL;
             if (pm) {
