@@ -90,6 +90,7 @@ __device__ __forceinline__ uint32_t enc_pass(const EncTable &tab, uint32_t *t, u
 } // namespace mbpe
 
 #include "encode_tiles.cuh"
+#include "encode_hot.cuh"
 
 namespace mbpe {
 // ---------------------------------------------------------------------------------------------------------
@@ -438,6 +439,12 @@ struct mbpe_encoder {
     uint64_t sub_batch_chunks = 0; // fixed sub-batch size (MBPE_ENCODE_SUBBATCH), 0 = geometric schedule
     uint64_t chunks_seen = 0;      // chunks encoded so far with this handle: how warm the caches are
     int cfg = 0; // kernel shape, see enc_configs
+    // k_encode_hot: image of the shared-memory table of the hottest chunks, and the scratch its rebuild needs
+    uint4 *d_hot_img = nullptr;
+    uint32_t *d_hot_count = nullptr;
+    unsigned long long *d_hot_best = nullptr;
+    bool hot_valid = false;
+    uint64_t hot_built_at = 0; // chunks_seen when the image was last rebuilt
     int dec_cfg = 0; // see dec_configs
     size_t l2_window_max = 0, l2_persist_bytes = 0;
     // mbpe_encode (host buffers): pinned staging + device buffers of the segment pipeline, two of each
@@ -455,11 +462,14 @@ struct EncConfig {
     int threads, cpt, ctas;
     void (*kernel)(const EncArgs);
     size_t smem;
+    bool hot; // k_encode_hot (falls back to configuration 0 for the launches it does not take, see encode_device_impl)
 };
-#define ENC_CFG(T, C, M, P, L, R) EncConfig{T, C, M, k_encode_tiles<T, C, M, P, L, R>, sizeof(EncSmemT<T, C>)}
+#define ENC_CFG(T, C, M, P, L, R) EncConfig{T, C, M, k_encode_tiles<T, C, M, P, L, R>, sizeof(EncSmemT<T, C>), false}
+#define ENC_HOT(T, C, P) EncConfig{T, C, 1, k_encode_hot<T, C, P>, sizeof(HotSmemT<T, C>), true}
 // (threads, chunks per thread, CTAs per SM, probes in flight per thread, L1 policy of the probe loads, L2 prefetch pass); 0 = default, the others for A/B runs (MBPE_ENC_CFG)
 static const EncConfig enc_configs[] = {ENC_CFG(256, 4, 4, 1, 0, 0), ENC_CFG(256, 4, 4, 1, 0, 1), ENC_CFG(256, 4, 3, 1, 0, 0), ENC_CFG(512, 4, 2, 1, 0, 0),
-                                        ENC_CFG(256, 8, 2, 1, 0, 0), ENC_CFG(128, 4, 8, 1, 0, 0), ENC_CFG(512, 4, 2, 1, 0, 1), ENC_CFG(256, 8, 2, 1, 0, 1)};
+                                        ENC_CFG(256, 8, 2, 1, 0, 0), ENC_CFG(128, 4, 8, 1, 0, 0), ENC_CFG(512, 4, 2, 1, 0, 1), ENC_CFG(256, 8, 2, 1, 0, 1),
+                                        ENC_HOT(1024, 4, 2), ENC_HOT(512, 8, 4)}; // 8, 9: k_encode_hot (experimental, measured slower: DESIGN.md section 3)
 constexpr int N_ENC_CONFIGS = sizeof(enc_configs) / sizeof(enc_configs[0]);
 
 static ChunkCache cache_view(const mbpe_encoder *e) {
@@ -562,6 +572,10 @@ static int encoder_create_impl(mbpe_encoder *e, const uint32_t *merges, uint32_t
         MB_CUDA(cudaMalloc(&e->d_cache_arena, (uint64_t)e->cache_arena_cap * 4));
         MB_CUDA(cudaMalloc(&e->d_cache_ctr, 16));
         MB_CUDA(cudaMemset(e->d_cache_ctr, 0, 16));
+        MB_CUDA(cudaMalloc(&e->d_hot_img, (size_t)HOT_N * sizeof(uint4)));
+        MB_CUDA(cudaMemset(e->d_hot_img, 0, (size_t)HOT_N * sizeof(uint4)));
+        MB_CUDA(cudaMalloc(&e->d_hot_count, (size_t)4 << HOT_COUNT_LOG2));
+        MB_CUDA(cudaMalloc(&e->d_hot_best, (size_t)HOT_N * 8));
     }
     const char *sb_env = getenv("MBPE_ENCODE_SUBBATCH");
     if (sb_env && *sb_env) e->sub_batch_chunks = std::max<uint64_t>(4096, strtoull(sb_env, nullptr, 10)) / 4096 * 4096;
@@ -625,7 +639,8 @@ extern "C" void mbpe_encoder_destroy(mbpe_encoder *e) {
     cudaSetDevice(e->device);
     void *ps[] = {e->d_slots, e->d_voff, e->d_vbytes, e->d_vpack, e->d_sp_ids, e->d_sp_off, e->d_sp_bytes, e->d_status, e->d_small,
                   e->d_n_out, e->d_long_list, e->d_scratch_a, e->d_scratch_b, e->d_cache, e->d_cache_log,
-                  e->d_cache_ctr, e->d_cache_arena, e->d_esp_ids, e->d_esp_off, e->d_esp_bytes, e->d_prof, e->d_spill};
+                  e->d_cache_ctr, e->d_cache_arena, e->d_esp_ids, e->d_esp_off, e->d_esp_bytes, e->d_prof, e->d_spill,
+                  e->d_hot_img, e->d_hot_count, e->d_hot_best};
     for (void *p : ps) cudaFree(p);
     free_host_pipe(e);
     if (e->pipe_stream) cudaStreamDestroy(e->pipe_stream);
@@ -719,6 +734,9 @@ extern "C" int mbpe_encoder_seed_special_chunks(mbpe_encoder *e, const uint32_t 
     }
     MB_CUDA(cudaMemset(e->d_cache, 0, (uint64_t)e->cache_slots * sizeof(CacheSlot)));
     MB_CUDA(cudaMemset(e->d_cache_ctr, 0, 16));
+    MB_CUDA(cudaMemset(e->d_hot_img, 0, (size_t)HOT_N * sizeof(uint4))); // (its entries come from the cache)
+    e->hot_valid = false;
+    e->hot_built_at = 0;
     e->chunks_seen = 0;
     if (!log.empty()) {
         MB_CUDA(cudaMemcpy(e->d_cache_log, log.data(), log.size() * sizeof(CacheLogEntry), cudaMemcpyHostToDevice));
@@ -750,7 +768,11 @@ extern "C" int mbpe_encode_reserve(mbpe_encoder *e, uint64_t n_bytes, uint64_t n
     (void)n_bytes;
     int rc = use_device(e->device);
     if (rc) return rc;
-    const uint64_t tile_chunks = (uint64_t)enc_configs[e->cfg].threads * enc_configs[e->cfg].cpt;
+    uint64_t tile_chunks = ~0ull, sm_chunks = 0; // smallest tile of the configurations a launch may use; most chunks in flight per SM
+    for (int c : {e->cfg, 0}) {
+        tile_chunks = std::min<uint64_t>(tile_chunks, (uint64_t)enc_configs[c].threads * enc_configs[c].cpt);
+        sm_chunks = std::max<uint64_t>(sm_chunks, (uint64_t)enc_configs[c].threads * enc_configs[c].cpt * enc_configs[c].ctas);
+    }
     const uint64_t max_sb = e->sub_batch_chunks ? e->sub_batch_chunks : ENC_MAX_SUBBATCH;
     if ((rc = ensure_status(e, (std::min(n_chunks, max_sb) + tile_chunks - 1) / tile_chunks + 1))) return rc;
     if (e->long_cap == 0) {
@@ -759,7 +781,7 @@ extern "C" int mbpe_encode_reserve(mbpe_encoder *e, uint64_t n_bytes, uint64_t n
     }
     // parking overflow of the tile kernel: one block of TILE * ENC_SHORT_MAX words per CTA (the worst case; untouched pages
     // cost nothing but address space)
-    const uint64_t need = (uint64_t)e->sms * enc_configs[e->cfg].ctas * tile_chunks * ENC_SHORT_MAX;
+    const uint64_t need = (uint64_t)e->sms * sm_chunks * ENC_SHORT_MAX;
     if (need > e->spill_words) {
         cudaFree(e->d_spill);
         e->d_spill = nullptr;
@@ -808,13 +830,17 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
     a.bulk = ((((uintptr_t)d_bytes) | ((uintptr_t)d_off)) & 15) == 0 && !getenv("MBPE_ENC_NO_BULK");
     a.out_aligned = (((uintptr_t)d_out) & 15) == 0;
     if (const char *ab = getenv("MBPE_ENC_ABLATE")) a.ablate = (uint32_t)atoi(ab);
-    const EncConfig &kc = enc_configs[e->cfg];
-    const uint64_t ET_CHUNKS = (uint64_t)kc.threads * kc.cpt;
+    a.hot_img = e->d_hot_img;
     uint32_t small[4] = {0, 0, 0, 0};
     // First launch sequence is optimistic: no chunk is longer than ENC_SHORT_MAX bytes (true for the regex patterns on
     // ordinary text), so the boundaries are read exactly once. The tile kernel reports the long chunks it meets
     // instead of encoding them; if there are any, they go through k_encode_long and the sequence runs again.
     for (int attempt = 0; attempt < 2; attempt++) {
+        // k_encode_hot takes the common case: aligned buffers, chunk cache on, no per-chunk offsets wanted, no long chunks
+        // known (it reports them like k_encode_tiles does; the repeat run with the splice enabled is k_encode_tiles')
+        const bool use_hot = enc_configs[e->cfg].hot && a.bulk && a.cache.slots && !a.out_off && !a.scratch_a && !a.ablate;
+        const EncConfig &kc = enc_configs[use_hot || !enc_configs[e->cfg].hot ? e->cfg : 0];
+        const uint64_t ET_CHUNKS = (uint64_t)kc.threads * kc.cpt;
         MB_CUDA(cudaMemsetAsync(e->d_small, 0, 16, st));
         MB_CUDA(cudaMemsetAsync(d_n_out, 0, 8, st));
         // Launches of whole tiles: the cache learns from one launch before the next one starts (a cold encoder starts
@@ -836,6 +862,32 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
             if (a.cache.slots) {
                 k_cache_reset_log<<<1, 1, 0, st>>>(a.cache);
                 e->launches++;
+            }
+            // the hot table follows the text: rebuilt from a sample of this launch's chunks at the start of a call and
+            // whenever the encoder has seen twice as many chunks as at the last rebuild (the chunk cache it draws the ids
+            // from is still filling up then)
+            const uint64_t seen_before = e->chunks_seen - (a.chunk1 - a.chunk0);
+            if (use_hot && (!e->hot_valid || (a.chunk0 == 0 && a.chunk1 >= (1u << 16)) || seen_before >= 2 * e->hot_built_at)) {
+                HotBuild hb{};
+                hb.bytes = d_bytes;
+                hb.off = d_off;
+                hb.chunk0 = a.chunk0;
+                hb.n_sample = (uint32_t)std::min<uint64_t>(a.chunk1 - a.chunk0, 1u << 18);
+                hb.stride = (a.chunk1 - a.chunk0) / hb.n_sample;
+                hb.count = e->d_hot_count;
+                hb.best = e->d_hot_best;
+                hb.img = e->d_hot_img;
+                MB_CUDA(cudaMemsetAsync(e->d_hot_count, 0, (size_t)4 << HOT_COUNT_LOG2, st));
+                MB_CUDA(cudaMemsetAsync(e->d_hot_best, 0, (size_t)HOT_N * 8, st));
+                MB_CUDA(cudaMemsetAsync(e->d_hot_img, 0, (size_t)HOT_N * sizeof(uint4), st));
+                const unsigned gb = (hb.n_sample + 255) / 256;
+                k_hot_count<<<gb, 256, 0, st>>>(hb);
+                k_hot_elect<<<gb, 256, 0, st>>>(hb);
+                k_hot_fill<<<gb, 256, 0, st>>>(hb);
+                k_hot_resolve<<<HOT_N / 256, 256, 0, st>>>(hb, a.cache);
+                e->launches += 4;
+                e->hot_valid = true;
+                e->hot_built_at = seen_before;
             }
             unsigned g2 = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)e->sms * kc.ctas);
             cudaLaunchConfig_t lc{};
@@ -907,6 +959,14 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
             unsigned long long pr[ENC_PROF_N];
             MB_CUDA(cudaMemcpy(pr, e->d_prof, sizeof pr, cudaMemcpyDeviceToHost));
             MB_CUDA(cudaMemset(e->d_prof, 0, sizeof pr));
+            if (enc_configs[e->cfg].hot) {
+                const double w = pr[11] ? (double)pr[11] : 1.0;
+                fprintf(stderr, "[mbpe] k_encode_hot: hot table %llu, home slot %llu, rest of the probe sequence %llu, slow path %llu chunks; warp tiles %llu, "
+                                "cycles per warp tile: keys+hot %.0f, chunk cache %.0f, scan+place %.0f, gather %.0f, wait for previous base %.0f, "
+                                "store previous %.0f, all %.0f\n",
+                        pr[0], pr[1], pr[3], pr[2], pr[11], pr[4] / w, pr[5] / w, pr[6] / w, pr[7] / w, pr[8] / w, pr[9] / w, pr[10] / w);
+                return MBPE_OK;
+            }
             const double t = pr[7] ? (double)pr[7] : 1.0;
             fprintf(stderr, "[mbpe] encode tiles %llu, cycles per tile: wait data %.0f, probes %.0f, scan list %.0f, count scan %.0f, "
                             "look-back+gather %.0f, fetch next %.0f, store %.0f\n",

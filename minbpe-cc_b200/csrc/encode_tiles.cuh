@@ -262,6 +262,7 @@ struct EncArgs {
     uint32_t bulk;               // bytes / off are 16-byte aligned: stage with cp.async.bulk
     uint32_t out_aligned;        // out is 16-byte aligned: ids leave as 16-byte stores
     unsigned long long *prof;    // optional: SM cycles per phase summed over CTAs (thread 0's clock), see ENC_PROF_*
+    const uint4 *hot_img;        // k_encode_hot: image of the shared-memory table of the hottest chunks (encode_hot.cuh)
     uint32_t ablate;             // MBPE_ENC_ABLATE (profiling only, WRONG results): 1 no look-back wait, 2 no cache probe
                                  // (every short chunk "hits" with two fake ids), 4 no id stores
 };

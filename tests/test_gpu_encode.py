@@ -265,7 +265,7 @@ def test_unaligned_device_buffers_take_the_cooperative_path(pkg, oracle):
 
 
 def test_encode_is_the_same_for_every_kernel_shape_and_without_caches(pkg, oracle, monkeypatch):
-    """every k_encode_tiles configuration, bulk and cooperative staging, caches on / off / tiny: identical ids, cold and warm"""
+    """every k_encode_tiles configuration and both k_encode_hot shapes (8, 9), bulk and cooperative staging, caches on / off / tiny: identical ids, cold and warm"""
     text = pkg.synth_corpus(0x5EED0013, 6 << 20).tobytes() + golden_data("sample.txt") * 20
     tok, off, w, _ = pkg.split_dedup(pkg.patterns()["gpt4"], text[: 4 << 20])
     merges, _, _ = pkg.train(tok, off, w, 256 + 3000, "lexical")
@@ -275,7 +275,7 @@ def test_encode_is_the_same_for_every_kernel_shape_and_without_caches(pkg, oracl
     so, eo = oracle.split(text[:cut], oracle.GPT4_SPLIT_PATTERN)
     oids, _ = oracle.encode_chunks(merges, text[:cut], so, eo)
     ref = None
-    envs = [{"MBPE_ENC_CFG": str(c)} for c in range(8)] + [{"MBPE_ENC_NO_BULK": "1"}, {"MBPE_ENCODE_CACHE": "0"},
+    envs = [{"MBPE_ENC_CFG": str(c)} for c in range(10)] + [{"MBPE_ENC_NO_BULK": "1"}, {"MBPE_ENCODE_CACHE": "0"},
                                                             {"MBPE_ENCODE_CACHE": "12"}, {"MBPE_ENCODE_SUBBATCH": "8192"}]
     for env in envs:
         for k, v in env.items():
