@@ -181,7 +181,11 @@ __device__ __forceinline__ void group_barrier(uint32_t id, uint32_t n_threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
 }
 
-template <int THREADS, int TAB_IDS, int MIN_CTAS, int GROUP>
+// LANES: the ids of a tile are dealt to the lanes round-robin (warp w, round j, lane l: id w * 256 + j * 32 + l) instead of 8
+// consecutive ids per thread: every lane places ONE token per round with predicated byte stores -- no per-thread
+// accumulator, no data-dependent loops, all 32 lanes busy (the consecutive layout ran at 6 warp instructions per id with
+// 20 of 32 lanes active: ncu in profiles/r2).
+template <int THREADS, int TAB_IDS, int MIN_CTAS, int GROUP, bool LANES = false>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_decode_tiles(const __grid_constant__ DecArgs a) {
     static_assert(THREADS % GROUP == 0 && GROUP % 32 == 0 && THREADS / GROUP <= 15, "one named barrier per group");
     constexpr int NW = GROUP / 32;
@@ -198,6 +202,12 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_decode_tiles(const __grid
     __syncthreads();
     uint32_t nxt[DEC_IPT];
     auto load_ids = [&](uint32_t t, uint32_t *dst) { // this thread's ids of tile t (0xFFFFFFFF past the end)
+        if (LANES) {
+            const uint64_t k = (uint64_t)t * DEC_IDS + (uint64_t)warp * (32 * DEC_IPT) + lane;
+#pragma unroll
+            for (int j = 0; j < DEC_IPT; j++) dst[j] = (t < a.n_tiles && k + j * 32 < a.n_ids) ? __ldcs(a.ids + k + j * 32) : 0xFFFFFFFFu;
+            return;
+        }
         const uint64_t k = (uint64_t)t * DEC_IDS + (uint64_t)tid * DEC_IPT;
         if (t < a.n_tiles && k + DEC_IPT <= a.n_ids) { // ids is 16-byte aligned (device allocation), k a multiple of 8
             const uint4 q0 = __ldcs(reinterpret_cast<const uint4 *>(a.ids + k));
@@ -211,7 +221,9 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_decode_tiles(const __grid
     for (uint32_t it = 0;; it++) {
         const uint32_t tile = sm.s_tile[it & 1];
         if (tile >= a.n_tiles) return;
-        const uint64_t k0 = (uint64_t)tile * DEC_IDS + (uint64_t)tid * DEC_IPT;
+        // index of this thread's j-th id: k0 + j * KS
+        const uint64_t k0 = (uint64_t)tile * DEC_IDS + (LANES ? (uint64_t)warp * (32 * DEC_IPT) + lane : (uint64_t)tid * DEC_IPT);
+        constexpr uint32_t KS = LANES ? 32 : 1;
         uint32_t id[DEC_IPT];
         if (it == 0) load_ids(tile, nxt);
 #pragma unroll
@@ -235,13 +247,13 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_decode_tiles(const __grid
 #pragma unroll
         for (int j = 0; j < DEC_IPT; j++) {
             pk[j] = 0xFFull;
-            if (a.v_pack && k0 + j < a.n_ids && id[j] < a.vocab_size)
+            if (a.v_pack && k0 + j * KS < a.n_ids && id[j] < a.vocab_size)
                 pk[j] = (TAB_IDS && id[j] < (uint32_t)TAB_IDS) ? cta.tab[id[j]] : __ldg(&a.v_pack[id[j]]);
         }
 #pragma unroll
         for (int j = 0; j < DEC_IPT; j++) {
             len[j] = 0;
-            if (k0 + j >= a.n_ids) continue;
+            if (k0 + j * KS >= a.n_ids) continue;
             const int sp = a.n_sp ? find_special(id[j]) : -1;
             if (sp >= 0) {
                 len[j] = __ldg(&a.sp_off[sp + 1]) - __ldg(&a.sp_off[sp]);
@@ -256,10 +268,47 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_decode_tiles(const __grid
             sum += len[j];
         }
         uint32_t incl = sum;
+        uint32_t loc[DEC_IPT]; // LANES: offset of token j within the warp's part of the tile (id order = round major)
+        if (LANES) {
+            // two rounds per scan, 16 bits each (a warp's round total stays below 65536 while every token is shorter than
+            // 2048 bytes; a longer special token takes the unpacked scans)
+            const bool wide = __any_sync(0xffffffffu, sum >= 2048u);
+            uint32_t run = 0;
+            if (!wide) {
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += v;
+                for (int j = 0; j < DEC_IPT; j += 2) {
+                    uint32_t pi = len[j] | (len[j + 1] << 16);
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t v = __shfl_up_sync(0xffffffffu, pi, d);
+                        if (lane >= d) pi += v;
+                    }
+                    const uint32_t tot = __shfl_sync(0xffffffffu, pi, 31);
+                    loc[j] = run + (pi & 0xFFFFu) - len[j];
+                    run += tot & 0xFFFFu;
+                    loc[j + 1] = run + (pi >> 16) - len[j + 1];
+                    run += tot >> 16;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < DEC_IPT; j++) {
+                    uint32_t pi = len[j];
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t v = __shfl_up_sync(0xffffffffu, pi, d);
+                        if (lane >= d) pi += v;
+                    }
+                    loc[j] = run + pi - len[j];
+                    run += __shfl_sync(0xffffffffu, pi, 31);
+                }
+            }
+            incl = run; // (every lane holds the warp's total)
+        } else {
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
         }
         if (lane == 31) sm.s_warp[warp] = incl;
         group_barrier(bar_id, GROUP);
@@ -284,7 +333,30 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_decode_tiles(const __grid
         auto long_src = [&](int j) -> const uint8_t * {
             return (pk[j] & PK_SPECIAL) ? a.sp_bytes + __ldg(&a.sp_off[(uint32_t)(pk[j] >> 8)]) : a.v_bytes + __ldg(&a.v_off[id[j]]);
         };
-        if (via_smem) {
+        if (LANES && via_smem) {
+#pragma unroll
+            for (int j = 0; j < DEC_IPT; j++) {
+                uint8_t *const d = stage8 + warp_base + loc[j];
+                const bool packed = (pk[j] & 0xFF) != 0xFF;
+                const bool any_hi = __any_sync(0xffffffffu, packed && len[j] > 3); // (asked by all lanes, before they diverge)
+                if (packed) { // <= 7 bytes, in the register: predicated byte stores, the same code in every lane
+                    const unsigned long long v = pk[j] >> 8;
+                    const uint32_t l = len[j];
+                    if (l > 0) d[0] = (uint8_t)v;
+                    if (l > 1) d[1] = (uint8_t)(v >> 8);
+                    if (l > 2) d[2] = (uint8_t)(v >> 16);
+                    if (any_hi) {
+                        if (l > 3) d[3] = (uint8_t)(v >> 24);
+                        if (l > 4) d[4] = (uint8_t)(v >> 32);
+                        if (l > 5) d[5] = (uint8_t)(v >> 40);
+                        if (l > 6) d[6] = (uint8_t)(v >> 48);
+                    }
+                } else if (len[j]) { // rare: longer than 7 bytes, or a special token
+                    const uint8_t *src = long_src(j);
+                    for (uint32_t i = 0; i < len[j]; i++) d[i] = __ldg(src + i);
+                }
+            }
+        } else if (via_smem) {
             // This thread's tokens -> stage8[loc0 ..): bytes are shifted into `acc` behind the `fill` (< 4) bytes that precede
             // them in the current word; whole words are stored as words, except the first one of the run if it starts
             // inside a word (`head`: those leading bytes belong to the neighbour), and the tail: byte by byte.
@@ -356,6 +428,19 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_decode_tiles(const __grid
             } else if (via_smem) { // the end of a buffer that is too small: what fits, byte by byte
                 for (uint32_t i = tid; i < total; i += GROUP)
                     if (base + i < a.out_cap) a.out[base + i] = stage8[i];
+            } else if (LANES) { // a tile with more bytes than the image holds: every lane stores its tokens, byte by byte
+#pragma unroll
+                for (int j = 0; j < DEC_IPT; j++) {
+                    const uint64_t at = base + warp_base + loc[j];
+                    if (len[j] == 0 || at + len[j] > a.out_cap) continue;
+                    if ((pk[j] & 0xFF) != 0xFF) {
+                        unsigned long long v = pk[j] >> 8;
+                        for (uint32_t i = 0; i < len[j]; i++, v >>= 8) a.out[at + i] = (uint8_t)v;
+                    } else {
+                        const uint8_t *src = long_src(j);
+                        for (uint32_t i = 0; i < len[j]; i++) a.out[at + i] = __ldg(src + i);
+                    }
+                }
             } else { // a tile with more bytes than the image holds: every thread stores its own, byte by byte
                 const uint64_t at = base + loc0;
                 const uint64_t room = at < a.out_cap ? a.out_cap - at : 0;
@@ -388,10 +473,12 @@ struct DecConfig {
     size_t smem;
 };
 #define DEC_CFG(T, I, M, G) DecConfig{T, G, M, k_decode_tiles<T, I, M, G>, sizeof(DecSmemT<T, I, G>)}
+#define DEC_LANES(T, I, M, G) DecConfig{T, G, M, k_decode_tiles<T, I, M, G, true>, sizeof(DecSmemT<T, I, G>)}
 // (threads, packed-vocabulary entries in shared memory, CTAs per SM, threads per tile group); 0 = default, the others for
 // A/B runs (MBPE_DEC_CFG)
 static const DecConfig dec_configs[] = {DEC_CFG(1024, 24576, 1, 512), DEC_CFG(1024, 24576, 1, 1024), DEC_CFG(1024, 24576, 1, 256),
-                                        DEC_CFG(256, 0, 4, 256),       DEC_CFG(512, 12288, 2, 256)};
+                                        DEC_CFG(256, 0, 4, 256),       DEC_CFG(512, 12288, 2, 256),
+                                        DEC_LANES(1024, 24576, 1, 512), DEC_LANES(1024, 24576, 1, 1024), DEC_LANES(1024, 24576, 1, 256)};
 constexpr int N_DEC_CONFIGS = sizeof(dec_configs) / sizeof(dec_configs[0]);
 } // namespace mbpe
 

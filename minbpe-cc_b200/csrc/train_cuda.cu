@@ -1045,7 +1045,7 @@ extern "C" int mbpe_trainer_run(mbpe_trainer *t, uint32_t vocab_size, int mode, 
         }
     }
     TrainConfig cfg{vocab_size, mode, engine, env_u32("MBPE_BIG_LIMIT", 16384), env_u32("MBPE_CAND_WANT", 1024),
-                    env_u32("MBPE_CAND_LIMIT", PS_SEL * PERSISTENT_THREADS), env_u32("MBPE_INIT_SLOTS", 0)};
+                    env_u32("MBPE_CAND_LIMIT", PS_SEL * PERSISTENT_THREADS), env_u32("MBPE_INIT_SLOTS", 0), env_u32("MBPE_TRAIN_PF", 0)};
     TrainOutcome o;
     *n_merges_out = 0;
     MB_CUDA(cudaEventRecord(t->ev[0], be.stream));
@@ -1337,7 +1337,7 @@ extern "C" int mbpe_sharded_trainer_run(mbpe_sharded_trainer *t, uint32_t vocab_
         be.links = &comm->links;
         be.xstep_ptr = &comm->xstep;
     }
-    TrainConfig cfg{vocab_size, mode, engine, ~0u, env_u32("MBPE_CAND_WANT", 512), env_u32("MBPE_CAND_LIMIT", PS_SEL * PERSISTENT_THREADS), 0};
+    TrainConfig cfg{vocab_size, mode, engine, ~0u, env_u32("MBPE_CAND_WANT", 512), env_u32("MBPE_CAND_LIMIT", PS_SEL * PERSISTENT_THREADS), 0, env_u32("MBPE_TRAIN_PF", 0)};
     TrainOutcome o;
     *n_merges_out = 0;
     MB_CUDA(cudaEventRecord(t->e0, st));

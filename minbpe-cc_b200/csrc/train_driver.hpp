@@ -29,6 +29,7 @@ struct TrainConfig {
     uint32_t cand_want;  // candidate list target size at a rebuild
     uint32_t cand_limit; // rebuild when the candidate list grows past this (0 = 4096)
     uint32_t init_slots; // initial pair-table capacity (power of two), 0 = sized for 65536 byte pairs
+    uint32_t pf_mode;    // occurrence walk: sectors on either side of an occurrence asked into L2 ahead of the walk (0 = off)
 };
 
 struct TrainOutcome {
@@ -85,6 +86,7 @@ class TrainLoop {
         h.best_cand = NIL;
         h.theta = 1;
         h.big_limit = cfg.big_limit;
+        h.pf_mode = cfg.pf_mode;
         h.cand_limit = cfg.cand_limit ? cfg.cand_limit : 4096;
         h.min_key_ever = ~0ull;
         h.live_tokens = n_tokens;
@@ -284,6 +286,7 @@ class TrainLoopSharded {
         h.best_cand = NIL;
         h.theta = 1;
         h.big_limit = ~0u;
+        h.pf_mode = cfg.pf_mode;
         const uint32_t resident_limit = cfg.engine == 1 ? be_.resident_limit() : 0;
         resident_limit_ = resident_limit;
         h.big_count = resident_limit;

@@ -140,7 +140,8 @@ struct Ctl {
     uint64_t dbg[4];
     uint64_t hh_steps[6], hh_cycles[6], hh_occ[6]; // hits phase by segment length class (debug)
     uint32_t pt_max[6];      // MBPE_PROFILE_HITS: slowest thread of the current step at checkpoints A..F
-    uint32_t pt_pad[2];
+    uint32_t pf_mode;        // occurrence walk: ask L2 for the sectors around an occurrence while its own node is fetched (0 = off)
+    uint32_t pt_pad1;
     uint64_t pt_sum[6][6];   // summed per segment length class
 };
 
@@ -623,8 +624,19 @@ MB_HD void phase_hits(const Ctx &c, uint32_t tid, uint32_t nth) {
 #endif
     const uint32_t a = MB_G(a), b = MB_G(b), id = MB_G(new_id), seg = MB_G(seg), len = MB_G(seg_len);
     const int32_t mode = MB_G(mode);
+    const uint32_t pf = MB_G(pf_mode);
     for (uint32_t k = tid; k < len; k += nth) {
         uint32_t pos = ld_l2(&c.occ[seg + k]);
+#if MB_ON_DEVICE
+        // The walk reads the occurrence's node, then -- one dependent round trip after the other -- its right neighbour, the
+        // neighbours of both, and theirs. They are the next live nodes of the same chunk, a few nodes away: ask L2 for the
+        // sectors (2 nodes each) around the occurrence NOW, so that only the first of those round trips goes to HBM.
+        if (pf & 255u) {
+            const uint32_t pfn = pf & 255u;
+            const uint32_t s0 = (pos >> 1) > pfn ? (pos >> 1) - pfn : 0u, s1 = min((pos >> 1) + pfn, (c.n_pos - 1) >> 1);
+            for (uint32_t sct = s0; sct <= s1; sct++) asm volatile("prefetch.global.L2 [%0];" ::"l"(&c.node[2 * sct]));
+        }
+#endif
         Node p = ld_node<S>(&c.node[pos]);
         if (p.tok != a || p.nxt == NIL) continue; // stale record
         uint32_t j = p.nxt;
@@ -670,6 +682,16 @@ MB_HD void phase_hits(const Ctx &c, uint32_t tid, uint32_t nth) {
                 fi2 = ld_l2(&c.slot[hi2].key);
                 if (c.m_cnt) pd2 = ld_l2(&c.slot[hd2].pad);
             }
+#if MB_ON_DEVICE
+            // A home slot that holds another pair means one more round trip for that lookup (the next four slots), and the
+            // four lookups are resolved one after the other: ask L2 for all the continuations now (pf_mode bit 8).
+            if (pf & 256u) {
+                if (do_l && fd1 != kd1 && fd1 != EMPTY_KEY) asm volatile("prefetch.global.L2 [%0];" ::"l"(&c.slot[(hd1 + 1) & c.cap_mask]));
+                if (do_l && fi1 != ki1 && fi1 != EMPTY_KEY) asm volatile("prefetch.global.L2 [%0];" ::"l"(&c.slot[(hi1 + 1) & c.cap_mask]));
+                if (has_r && fd2 != kd2 && fd2 != EMPTY_KEY) asm volatile("prefetch.global.L2 [%0];" ::"l"(&c.slot[(hd2 + 1) & c.cap_mask]));
+                if (has_r && fi2 != ki2 && fi2 != EMPTY_KEY) asm volatile("prefetch.global.L2 [%0];" ::"l"(&c.slot[(hi2 + 1) & c.cap_mask]));
+            }
+#endif
             MB_PT(2);
             // both claims of empty home slots go out before either answer is needed
             uint64_t o1 = 0, o2 = 0;
