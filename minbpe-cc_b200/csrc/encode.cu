@@ -135,6 +135,10 @@ struct DecArgs {
     const uint32_t *v_off; // vocab_size + 1
     const uint8_t *v_bytes;
     const unsigned long long *v_pack; // per id: length in the low byte (0xFF = longer than 7 bytes), then the bytes
+    // k_decode_lean: per id, byte 0 = length if <= 7; 0x80 | length if 8..126; 0xFF = look it up (127 bytes or more, or a
+    // special token: then bit 63 is set and bits 8..39 hold the index of the special token); bytes 1..7 = the token's first
+    // 7 bytes. v_pack2: the token's bytes 7..14.
+    const unsigned long long *v_lean, *v_pack2;
     uint32_t vocab_size;
     const uint32_t *sp_ids; // sorted
     const uint32_t *sp_off; // n_sp + 1 into sp_bytes
@@ -467,6 +471,239 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_decode_tiles(const __grid
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// k_decode_lean: the same tile scheme as k_decode_tiles (ticket, block scan, announce / walk, staged image, aligned word
+// stores), with the per-id work cut to what ncu shows is needed -- k_decode_tiles runs 6 warp instructions per id at 20 of
+// 32 lanes. One id per lane and round (ids dealt round-robin within a warp: 32 consecutive ids per round, coalesced 4-byte
+// loads); ONE table word answers length and first 7 bytes for every id below the vocabulary size (special tokens inside
+// that range are patched into the table by mbpe_encoder_set_specials, so nobody searches for them; ids beyond the
+// vocabulary take the out-of-line path); no per-id index checks (ids past the end of the stream are loaded as 0xFFFFFFFF =
+// unknown = nothing); tokens of 8..15 bytes take their second word from a second table instead of a byte loop; bytes leave
+// as predicated byte stores, the same instructions in every lane.
+// ---------------------------------------------------------------------------------------------------------
+constexpr unsigned long long PKL_SPECIAL = 1ull << 63;
+
+// ids beyond the vocabulary: a special token (Tokenizer.h:733-736) or unknown (nothing, :739-742); -> table word
+__device__ __noinline__ unsigned long long dec_lean_outside(const DecArgs &a, uint32_t idv) {
+    int lo = 0, hi = (int)a.n_sp - 1;
+    while (lo <= hi) {
+        const int mid = (lo + hi) >> 1;
+        const uint32_t v = __ldg(&a.sp_ids[mid]);
+        if (v == idv) return PKL_SPECIAL | ((unsigned long long)(uint32_t)mid << 8) | 0xFFull;
+        if (v < idv)
+            lo = mid + 1;
+        else
+            hi = mid - 1;
+    }
+    return 0ull;
+}
+// a token the table does not hold whole: its length and where its bytes are
+__device__ __forceinline__ const uint8_t *dec_lean_src(const DecArgs &a, unsigned long long pk, uint32_t idv, uint32_t &len) {
+    if (pk & PKL_SPECIAL) {
+        const uint32_t sp = (uint32_t)(pk >> 8);
+        const uint32_t o = __ldg(&a.sp_off[sp]);
+        len = __ldg(&a.sp_off[sp + 1]) - o;
+        return a.sp_bytes + o;
+    }
+    const uint32_t o = __ldg(&a.v_off[idv]);
+    len = __ldg(&a.v_off[idv + 1]) - o;
+    return a.v_bytes + o;
+}
+
+template <int THREADS, int TAB_IDS, int GROUP>
+__global__ void __launch_bounds__(THREADS, 1) k_decode_lean(const __grid_constant__ DecArgs a) {
+    static_assert(THREADS % GROUP == 0 && GROUP % 32 == 0 && THREADS / GROUP <= 15 && TAB_IDS > 0, "one named barrier per group");
+    constexpr int NW = GROUP / 32;
+    constexpr uint32_t DEC_IDS = GROUP * DEC_IPT, DEC_STAGE = DecGroupSmemT<GROUP>::STAGE;
+    extern __shared__ __align__(16) unsigned char dec_smem_raw[];
+    DecSmemT<THREADS, TAB_IDS, GROUP> &cta = *reinterpret_cast<DecSmemT<THREADS, TAB_IDS, GROUP> *>(dec_smem_raw);
+    DecGroupSmemT<GROUP> &sm = cta.grp[threadIdx.x / GROUP];
+    const uint32_t tid = threadIdx.x % GROUP, lane = tid & 31, warp = tid >> 5; // (within the group)
+    const uint32_t bar_id = 1 + threadIdx.x / GROUP;
+    uint8_t *const stage8 = reinterpret_cast<uint8_t *>(sm.stage);
+    for (uint32_t i = threadIdx.x; i < (uint32_t)TAB_IDS; i += THREADS) cta.tab[i] = i < a.vocab_size ? __ldg(&a.v_lean[i]) : 0ull;
+    if (tid == 0) sm.s_tile[0] = atomicAdd(a.ticket, 1u); // tiles start in order: look-back cannot deadlock
+    __syncthreads();
+    const uint32_t vocab = a.vocab_size;
+    uint32_t nxt[DEC_IPT];
+    auto load_ids = [&](uint32_t t, uint32_t *dst) { // round j, lane l: id (warp * 8 + j) * 32 + l of tile t (0xFFFFFFFF past the end)
+        const uint64_t k = (uint64_t)t * DEC_IDS + (uint64_t)warp * (32 * DEC_IPT) + lane;
+        if (t < a.n_tiles && (uint64_t)(t + 1) * DEC_IDS <= a.n_ids) {
+#pragma unroll
+            for (int j = 0; j < DEC_IPT; j++) dst[j] = __ldcs(a.ids + k + j * 32);
+        } else {
+#pragma unroll
+            for (int j = 0; j < DEC_IPT; j++) dst[j] = (t < a.n_tiles && k + j * 32 < a.n_ids) ? __ldcs(a.ids + k + j * 32) : 0xFFFFFFFFu;
+        }
+    };
+    for (uint32_t it = 0;; it++) {
+        const uint32_t tile = sm.s_tile[it & 1];
+        if (tile >= a.n_tiles) return;
+        if (it == 0) load_ids(tile, nxt);
+        uint32_t id[DEC_IPT];
+        unsigned long long pk[DEC_IPT];
+        uint32_t len[DEC_IPT];
+        bool odd = false; // some token of this lane is not answered by the table word alone
+#pragma unroll
+        for (int j = 0; j < DEC_IPT; j++) {
+            id[j] = nxt[j]; // (loaded while the previous tile was being stored)
+            pk[j] = cta.tab[min(id[j], (uint32_t)TAB_IDS - 1)];
+            if (id[j] >= (uint32_t)TAB_IDS) pk[j] = id[j] < vocab ? __ldg(&a.v_lean[id[j]]) : dec_lean_outside(a, id[j]);
+            const uint32_t b0 = (uint32_t)pk[j] & 0xFFu;
+            len[j] = b0 & 0x7Fu;
+            odd = odd || b0 == 0xFFu;
+        }
+        if (__any_sync(0xffffffffu, odd)) { // 127 bytes or more, or a special token: the length comes from the index
+#pragma unroll
+            for (int j = 0; j < DEC_IPT; j++)
+                if (((uint32_t)pk[j] & 0xFFu) == 0xFFu) dec_lean_src(a, pk[j], id[j], len[j]);
+        }
+        // ---- place of every token within the warp's part of the tile (id order = round major) ---------------------------
+        uint32_t loc[DEC_IPT], run = 0;
+        {
+            uint32_t mx = 0;
+#pragma unroll
+            for (int j = 0; j < DEC_IPT; j++) mx = max(mx, len[j]);
+            if (!__any_sync(0xffffffffu, mx >= 2048u)) { // two rounds per scan, 16 bits each
+#pragma unroll
+                for (int j = 0; j < DEC_IPT; j += 2) {
+                    uint32_t pi = len[j] | (len[j + 1] << 16);
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t v = __shfl_up_sync(0xffffffffu, pi, d);
+                        if (lane >= d) pi += v;
+                    }
+                    const uint32_t tot = __shfl_sync(0xffffffffu, pi, 31);
+                    loc[j] = run + (pi & 0xFFFFu) - len[j];
+                    run += tot & 0xFFFFu;
+                    loc[j + 1] = run + (pi >> 16) - len[j + 1];
+                    run += tot >> 16;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < DEC_IPT; j++) {
+                    uint32_t pi = len[j];
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t v = __shfl_up_sync(0xffffffffu, pi, d);
+                        if (lane >= d) pi += v;
+                    }
+                    loc[j] = run + pi - len[j];
+                    run += __shfl_sync(0xffffffffu, pi, 31);
+                }
+            }
+        }
+        if (lane == 31) sm.s_warp[warp] = run;
+        group_barrier(bar_id, GROUP);
+        uint32_t warp_base, total;
+        { // every warp scans the warp sums itself (lane w holds warp w's)
+            const uint32_t mine = lane < NW ? sm.s_warp[lane] : 0u;
+            uint32_t wi = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += v;
+            }
+            total = __shfl_sync(0xffffffffu, wi, 31);
+            warp_base = __shfl_sync(0xffffffffu, wi - mine, warp);
+        }
+        uint64_t base0 = 0;
+        if (warp == 0) base0 = lookback_announce(a.status, tile, total);
+        const bool via_smem = a.out != nullptr && total <= DEC_STAGE;
+        if (via_smem) {
+#pragma unroll
+            for (int j = 0; j < DEC_IPT; j++) {
+                uint8_t *const d = stage8 + warp_base + loc[j];
+                const uint32_t lo = (uint32_t)(pk[j] >> 8), hi = (uint32_t)(pk[j] >> 40), l = len[j];
+                const uint32_t b0 = (uint32_t)pk[j] & 0xFFu;
+                const bool plain = b0 != 0xFFu;          // the first min(l, 7) bytes are in the table word
+                const bool tail = plain && l > 7;          // bytes 7.. come from the second table (8..15) / the index (more)
+                const bool any4 = __any_sync(0xffffffffu, plain && l > 3), any_tail = __any_sync(0xffffffffu, tail || !plain);
+                if (plain) {
+                    if (l > 0) d[0] = (uint8_t)lo;
+                    if (l > 1) d[1] = (uint8_t)(lo >> 8);
+                    if (l > 2) d[2] = (uint8_t)(lo >> 16);
+                    if (any4) {
+                        if (l > 3) d[3] = (uint8_t)(lo >> 24);
+                        if (l > 4) d[4] = (uint8_t)hi;
+                        if (l > 5) d[5] = (uint8_t)(hi >> 8);
+                        if (l > 6) d[6] = (uint8_t)(hi >> 16);
+                    }
+                }
+                if (any_tail) {
+                    if (tail) {
+                        const unsigned long long w2 = __ldg(&a.v_pack2[id[j]]);
+                        const uint32_t lo2 = (uint32_t)w2, hi2 = (uint32_t)(w2 >> 32);
+                        d[7] = (uint8_t)lo2;
+                        if (l > 8) d[8] = (uint8_t)(lo2 >> 8);
+                        if (l > 9) d[9] = (uint8_t)(lo2 >> 16);
+                        if (l > 10) d[10] = (uint8_t)(lo2 >> 24);
+                        if (l > 11) {
+                            d[11] = (uint8_t)hi2;
+                            if (l > 12) d[12] = (uint8_t)(hi2 >> 8);
+                            if (l > 13) d[13] = (uint8_t)(hi2 >> 16);
+                            if (l > 14) d[14] = (uint8_t)(hi2 >> 24);
+                            if (l > 15) {
+                                const uint8_t *src = a.v_bytes + __ldg(&a.v_off[id[j]]);
+#pragma unroll 1
+                                for (uint32_t i = 15; i < l; i++) d[i] = __ldg(src + i);
+                            }
+                        }
+                    } else if (!plain && l) {
+                        uint32_t ll;
+                        const uint8_t *src = dec_lean_src(a, pk[j], id[j], ll);
+#pragma unroll 1
+                        for (uint32_t i = 0; i < l; i++) d[i] = __ldg(src + i);
+                    }
+                }
+            }
+        }
+        if (warp == 0) {
+            const uint64_t b = lookback_resolve<4>(a.status, tile, total, base0);
+            if (lane == 0) {
+                sm.s_base = b;
+                sm.s_tile[(it + 1) & 1] = atomicAdd(a.ticket, 1u); // (this tile's size is published: successors do not wait for us)
+            }
+        }
+        group_barrier(bar_id, GROUP);
+        const uint64_t base = sm.s_base;
+        load_ids(sm.s_tile[(it + 1) & 1], nxt); // the next tile's ids arrive while this one is stored
+        if (a.out) {
+            if (via_smem && base + total <= a.out_cap) {
+                // global word k of the tile = bytes [4k - pad, 4k - pad + 4) of the image; whole words by funnel shift
+                const uint32_t pad = (uint32_t)(base & 3), sh = ((4 - pad) & 3) * 8;
+                const uint64_t w0 = base - pad; // 4-byte aligned (out is a device allocation)
+                const uint32_t n_words = (pad + total + 3) >> 2;
+                uint32_t *const gw = reinterpret_cast<uint32_t *>(a.out + w0);
+                for (uint32_t k = tid; k < n_words; k += GROUP) {
+                    const int lo = (int)(4 * k) - (int)pad; // tile-local offset of the word's first byte
+                    if (lo >= 0 && (uint32_t)lo + 4 <= total) {
+                        const uint32_t j = (uint32_t)lo >> 2;
+                        const uint32_t v = pad ? __funnelshift_r(sm.stage[j], sm.stage[j + 1], sh) : sm.stage[j];
+                        __stcs(gw + k, v);
+                    } else { // first / last word of the tile: shared with the neighbouring tiles, byte stores
+                        for (int i = lo < 0 ? 0 : lo; i < lo + 4 && (uint32_t)i < total; i++) a.out[base + i] = stage8[i];
+                    }
+                }
+            } else if (via_smem) { // the end of a buffer that is too small: what fits, byte by byte
+                for (uint32_t i = tid; i < total; i += GROUP)
+                    if (base + i < a.out_cap) a.out[base + i] = stage8[i];
+            } else { // a tile with more bytes than the image holds: every lane stores its tokens, byte by byte
+#pragma unroll
+                for (int j = 0; j < DEC_IPT; j++) {
+                    const uint64_t at = base + warp_base + loc[j];
+                    if (len[j] == 0 || at + len[j] > a.out_cap) continue;
+                    uint32_t ll;
+                    const uint8_t *src = dec_lean_src(a, (pk[j] & PKL_SPECIAL) ? pk[j] : 0ull, id[j], ll);
+                    for (uint32_t i = 0; i < len[j]; i++) a.out[at + i] = __ldg(src + i);
+                }
+            }
+        }
+        if (tile == a.n_tiles - 1 && tid == 0) *a.d_n_out = base + total;
+        // (the image is rewritten only after the next tile's first barrier, which every thread reaches after its stores)
+    }
+}
+
 struct DecConfig {
     int threads, group, ctas;
     void (*kernel)(const DecArgs);
@@ -474,11 +711,13 @@ struct DecConfig {
 };
 #define DEC_CFG(T, I, M, G) DecConfig{T, G, M, k_decode_tiles<T, I, M, G>, sizeof(DecSmemT<T, I, G>)}
 #define DEC_LANES(T, I, M, G) DecConfig{T, G, M, k_decode_tiles<T, I, M, G, true>, sizeof(DecSmemT<T, I, G>)}
+#define DEC_LEAN(T, I, G) DecConfig{T, G, 1, k_decode_lean<T, I, G>, sizeof(DecSmemT<T, I, G>)}
 // (threads, packed-vocabulary entries in shared memory, CTAs per SM, threads per tile group); 0 = default, the others for
 // A/B runs (MBPE_DEC_CFG)
 static const DecConfig dec_configs[] = {DEC_CFG(1024, 24576, 1, 512), DEC_CFG(1024, 24576, 1, 1024), DEC_CFG(1024, 24576, 1, 256),
                                         DEC_CFG(256, 0, 4, 256),       DEC_CFG(512, 12288, 2, 256),
-                                        DEC_LANES(1024, 24576, 1, 512), DEC_LANES(1024, 24576, 1, 1024), DEC_LANES(1024, 24576, 1, 256)};
+                                        DEC_LANES(1024, 24576, 1, 512), DEC_LANES(1024, 24576, 1, 1024), DEC_LANES(1024, 24576, 1, 256),
+                                        DEC_LEAN(1024, 24576, 512),     DEC_LEAN(1024, 24576, 1024),      DEC_LEAN(1024, 24576, 256)};
 constexpr int N_DEC_CONFIGS = sizeof(dec_configs) / sizeof(dec_configs[0]);
 } // namespace mbpe
 
@@ -496,6 +735,8 @@ struct mbpe_encoder {
     uint32_t *d_voff = nullptr;
     uint8_t *d_vbytes = nullptr;
     unsigned long long *d_vpack = nullptr; // decode: length + up to 7 bytes per id in one word
+    unsigned long long *d_vlean = nullptr, *d_vpack2 = nullptr; // k_decode_lean: see DecArgs::v_lean
+    std::vector<unsigned long long> h_vlean;                    // without special tokens (they are patched in on the device copy)
     uint32_t *d_sp_ids = nullptr, *d_sp_off = nullptr;
     uint8_t *d_sp_bytes = nullptr;
     uint32_t n_sp = 0;
@@ -635,6 +876,19 @@ static int encoder_create_impl(mbpe_encoder *e, const uint32_t *merges, uint32_t
         }
         MB_CUDA(cudaMalloc(&e->d_vpack, vpack.size() * 8));
         MB_CUDA(cudaMemcpy(e->d_vpack, vpack.data(), vpack.size() * 8, cudaMemcpyHostToDevice));
+        std::vector<unsigned long long> vpack2(vpack.size(), 0ull);
+        e->h_vlean.assign(vpack.size(), 0ull);
+        for (size_t i = 0; i < vpack.size(); i++) {
+            const uint32_t l = voff[i + 1] - voff[i];
+            unsigned long long v = l <= 7 ? l : l <= 126 ? (0x80u | l) : 0xFFu;
+            for (uint32_t q = 0; q < std::min(l, 7u); q++) v |= (unsigned long long)vbytes[voff[i] + q] << (8 * (q + 1));
+            e->h_vlean[i] = v;
+            for (uint32_t q = 7; q < std::min(l, 15u); q++) vpack2[i] |= (unsigned long long)vbytes[voff[i] + q] << (8 * (q - 7));
+        }
+        MB_CUDA(cudaMalloc(&e->d_vlean, vpack.size() * 8));
+        MB_CUDA(cudaMemcpy(e->d_vlean, e->h_vlean.data(), vpack.size() * 8, cudaMemcpyHostToDevice));
+        MB_CUDA(cudaMalloc(&e->d_vpack2, vpack.size() * 8));
+        MB_CUDA(cudaMemcpy(e->d_vpack2, vpack2.data(), vpack.size() * 8, cudaMemcpyHostToDevice));
     }
     MB_CUDA(cudaMalloc(&e->d_small, 16));
     MB_CUDA(cudaMalloc(&e->d_n_out, 8));
@@ -727,7 +981,7 @@ extern "C" void mbpe_encoder_destroy(mbpe_encoder *e) {
     void *ps[] = {e->d_slots, e->d_voff, e->d_vbytes, e->d_vpack, e->d_sp_ids, e->d_sp_off, e->d_sp_bytes, e->d_status, e->d_small,
                   e->d_n_out, e->d_long_list, e->d_scratch_a, e->d_scratch_b, e->d_cache, e->d_cache_log,
                   e->d_cache_ctr, e->d_cache_arena, e->d_esp_ids, e->d_esp_off, e->d_esp_bytes, e->d_prof, e->d_spill,
-                  e->d_hot_img, e->d_hot_count, e->d_hot_best};
+                  e->d_hot_img, e->d_hot_count, e->d_hot_best, e->d_vlean, e->d_vpack2};
     for (void *p : ps) cudaFree(p);
     free_host_pipe(e);
     if (e->pipe_stream) cudaStreamDestroy(e->pipe_stream);
@@ -766,6 +1020,13 @@ extern "C" int mbpe_encoder_set_specials(mbpe_encoder *e, const uint32_t *ids, c
     MB_CUDA(cudaMemcpy(e->d_sp_off, soff.data(), soff.size() * 4, cudaMemcpyHostToDevice));
     MB_CUDA(cudaMemcpy(e->d_sp_bytes, sb.data(), sb.size(), cudaMemcpyHostToDevice));
     e->n_sp = (uint32_t)sid.size();
+    // k_decode_lean finds a special token that overrides a vocabulary id (Tokenizer.h:733-736) in the table word itself
+    if (e->d_vlean) {
+        std::vector<unsigned long long> vl = e->h_vlean;
+        for (size_t k = 0; k < sid.size(); k++)
+            if (sid[k] < vl.size()) vl[sid[k]] = PKL_SPECIAL | ((unsigned long long)k << 8) | 0xFFull;
+        MB_CUDA(cudaMemcpy(e->d_vlean, vl.data(), vl.size() * 8, cudaMemcpyHostToDevice));
+    }
     return MBPE_OK;
 }
 
@@ -1153,7 +1414,7 @@ extern "C" int mbpe_encode(mbpe_encoder *e, const uint8_t *bytes, uint64_t n_byt
     if (n_seg == 0) return MBPE_OK;
     if ((rc = ensure_host_pipe(e, max_b, max_c, out_off != nullptr))) return rc;
     cudaStream_t st = e->pipe_stream;
-    const unsigned n_thr = (unsigned)std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    const unsigned n_thr = (unsigned)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     std::atomic<int> bad_order{0};
     auto stage_in = [&](size_t k) {
         auto &p = e->pipe[k & 1];
@@ -1232,7 +1493,8 @@ extern "C" int mbpe_encode(mbpe_encoder *e, const uint8_t *bytes, uint64_t n_byt
 
 static int decode_launch(mbpe_encoder *e, const uint32_t *d_ids, uint64_t n_ids, uint8_t *d_out, uint64_t out_cap,
                          unsigned long long *d_n_out, cudaStream_t st) {
-    const DecConfig &dc = dec_configs[e->dec_cfg];
+    const bool nopack = getenv("MBPE_DEC_NOPACK") != nullptr;
+    const DecConfig &dc = dec_configs[nopack ? 3 : e->dec_cfg]; // (configuration 3 keeps no table in shared memory)
     const uint64_t tile_ids = (uint64_t)dc.group * DEC_IPT;
     const uint64_t n_tiles = (n_ids + tile_ids - 1) / tile_ids;
     if (n_tiles >= 0xFFFFFFFFull) return set_error(MBPE_E_INVALID, "too many ids in one call");
@@ -1243,7 +1505,9 @@ static int decode_launch(mbpe_encoder *e, const uint32_t *d_ids, uint64_t n_ids,
     a.n_ids = n_ids;
     a.v_off = e->d_voff;
     a.v_bytes = e->d_vbytes;
-    a.v_pack = getenv("MBPE_DEC_NOPACK") ? nullptr : e->d_vpack;
+    a.v_pack = nopack ? nullptr : e->d_vpack;
+    a.v_lean = e->d_vlean;
+    a.v_pack2 = e->d_vpack2;
     a.vocab_size = e->vocab_size;
     a.sp_ids = e->d_sp_ids;
     a.sp_off = e->d_sp_off;
