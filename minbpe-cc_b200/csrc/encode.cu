@@ -510,6 +510,9 @@ __device__ __forceinline__ const uint8_t *dec_lean_src(const DecArgs &a, unsigne
     return a.v_bytes + o;
 }
 
+// (Tried: warp 0 of a group as a control warp that carries no ids and walks the predecessors while the others place their
+// tokens -- 3.4 / 3.6 ms against 2.9 / 3.0: the walk starts before the predecessors have announced themselves and the next
+// ticket is taken earlier, i.e. held idle longer.)
 template <int THREADS, int TAB_IDS, int GROUP>
 __global__ void __launch_bounds__(THREADS, 1) k_decode_lean(const __grid_constant__ DecArgs a) {
     static_assert(THREADS % GROUP == 0 && GROUP % 32 == 0 && THREADS / GROUP <= 15 && TAB_IDS > 0, "one named barrier per group");
@@ -524,22 +527,32 @@ __global__ void __launch_bounds__(THREADS, 1) k_decode_lean(const __grid_constan
     for (uint32_t i = threadIdx.x; i < (uint32_t)TAB_IDS; i += THREADS) cta.tab[i] = i < a.vocab_size ? __ldg(&a.v_lean[i]) : 0ull;
     if (tid == 0) sm.s_tile[0] = atomicAdd(a.ticket, 1u); // tiles start in order: look-back cannot deadlock
     __syncthreads();
-    const uint32_t vocab = a.vocab_size;
+    const uint32_t vocab = a.vocab_size, tab_n = min((uint32_t)TAB_IDS, vocab); // ids the shared-memory table answers (vocab >= 256)
     uint32_t nxt[DEC_IPT];
-    auto load_ids = [&](uint32_t t, uint32_t *dst) { // round j, lane l: id (warp * 8 + j) * 32 + l of tile t (0xFFFFFFFF past the end)
+    // round j, lane l: id (warp * 8 + j) * 32 + l of tile t; returns the mask of the rounds that hold an id at all (any u32 may
+    // be the id of a special token, so "no id here" cannot be a value)
+    auto load_ids = [&](uint32_t t, uint32_t *dst) -> uint32_t {
         const uint64_t k = (uint64_t)t * DEC_IDS + (uint64_t)warp * (32 * DEC_IPT) + lane;
         if (t < a.n_tiles && (uint64_t)(t + 1) * DEC_IDS <= a.n_ids) {
 #pragma unroll
             for (int j = 0; j < DEC_IPT; j++) dst[j] = __ldcs(a.ids + k + j * 32);
-        } else {
-#pragma unroll
-            for (int j = 0; j < DEC_IPT; j++) dst[j] = (t < a.n_tiles && k + j * 32 < a.n_ids) ? __ldcs(a.ids + k + j * 32) : 0xFFFFFFFFu;
+            return 0xFFu;
         }
+        uint32_t m = 0;
+#pragma unroll
+        for (int j = 0; j < DEC_IPT; j++) {
+            const bool ok = t < a.n_tiles && k + j * 32 < a.n_ids;
+            dst[j] = ok ? __ldcs(a.ids + k + j * 32) : 0u;
+            m |= ok ? 1u << j : 0u;
+        }
+        return m;
     };
+    uint32_t nxt_mask = 0;
     for (uint32_t it = 0;; it++) {
         const uint32_t tile = sm.s_tile[it & 1];
         if (tile >= a.n_tiles) return;
-        if (it == 0) load_ids(tile, nxt);
+        if (it == 0) nxt_mask = load_ids(tile, nxt);
+        const uint32_t have = nxt_mask;
         uint32_t id[DEC_IPT];
         unsigned long long pk[DEC_IPT];
         uint32_t len[DEC_IPT];
@@ -547,11 +560,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_decode_lean(const __grid_constan
 #pragma unroll
         for (int j = 0; j < DEC_IPT; j++) {
             id[j] = nxt[j]; // (loaded while the previous tile was being stored)
-            pk[j] = cta.tab[min(id[j], (uint32_t)TAB_IDS - 1)];
-            if (id[j] >= (uint32_t)TAB_IDS) pk[j] = id[j] < vocab ? __ldg(&a.v_lean[id[j]]) : dec_lean_outside(a, id[j]);
+            pk[j] = cta.tab[min(id[j], tab_n - 1)];
+            if (id[j] >= tab_n) pk[j] = id[j] < vocab ? __ldg(&a.v_lean[id[j]]) : dec_lean_outside(a, id[j]);
+            if (have != 0xFFu && !((have >> j) & 1u)) pk[j] = 0ull;
             const uint32_t b0 = (uint32_t)pk[j] & 0xFFu;
             len[j] = b0 & 0x7Fu;
             odd = odd || b0 == 0xFFu;
+            // (bytes 7..14 of a longer token are fetched when it is placed, one round after the other: ask L1 for them now)
+            if (b0 > 0x87u && b0 != 0xFFu) asm volatile("prefetch.global.L1 [%0];" ::"l"(&a.v_pack2[id[j]]));
         }
         if (__any_sync(0xffffffffu, odd)) { // 127 bytes or more, or a special token: the length comes from the index
 #pragma unroll
@@ -667,9 +683,26 @@ __global__ void __launch_bounds__(THREADS, 1) k_decode_lean(const __grid_constan
         }
         group_barrier(bar_id, GROUP);
         const uint64_t base = sm.s_base;
-        load_ids(sm.s_tile[(it + 1) & 1], nxt); // the next tile's ids arrive while this one is stored
+        nxt_mask = load_ids(sm.s_tile[(it + 1) & 1], nxt); // the next tile's ids arrive while this one is stored
         if (a.out) {
-            if (via_smem && base + total <= a.out_cap) {
+            if (via_smem && base + total <= a.out_cap && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0) {
+                // global 16-byte vector v of the tile = bytes [16v - pad, 16v - pad + 16) of the image: five image words, four
+                // funnel shifts (the misalignment of the tile's base is the same for every vector), one 16-byte store
+                const uint32_t pad = (uint32_t)(base & 15), sh = ((16 - pad) & 3) * 8;
+                const uint32_t n_vec = (pad + total + 15) >> 4;
+                uint4 *const gv = reinterpret_cast<uint4 *>(a.out + (base - pad));
+                for (uint32_t v = tid; v < n_vec; v += GROUP) {
+                    const int lo = (int)(16 * v) - (int)pad; // tile-local offset of the vector's first byte
+                    if (lo >= 0 && (uint32_t)lo + 16 <= total) {
+                        const uint32_t j = (uint32_t)lo >> 2;
+                        const uint32_t w0 = sm.stage[j], w1 = sm.stage[j + 1], w2 = sm.stage[j + 2], w3 = sm.stage[j + 3], w4 = sm.stage[j + 4];
+                        __stcs(gv + v, make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                                                  __funnelshift_r(w3, w4, sh)));
+                    } else { // first / last vector of the tile: shared with the neighbouring tiles, byte stores
+                        for (int i = lo < 0 ? 0 : lo; i < lo + 16 && (uint32_t)i < total; i++) a.out[base + i] = stage8[i];
+                    }
+                }
+            } else if (via_smem && base + total <= a.out_cap) {
                 // global word k of the tile = bytes [4k - pad, 4k - pad + 4) of the image; whole words by funnel shift
                 const uint32_t pad = (uint32_t)(base & 3), sh = ((4 - pad) & 3) * 8;
                 const uint64_t w0 = base - pad; // 4-byte aligned (out is a device allocation)
@@ -705,19 +738,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_decode_lean(const __grid_constan
 }
 
 struct DecConfig {
-    int threads, group, ctas;
+    int threads, group, ctas, tile_ids; // tile_ids: ids of one tile of one group
     void (*kernel)(const DecArgs);
     size_t smem;
 };
-#define DEC_CFG(T, I, M, G) DecConfig{T, G, M, k_decode_tiles<T, I, M, G>, sizeof(DecSmemT<T, I, G>)}
-#define DEC_LANES(T, I, M, G) DecConfig{T, G, M, k_decode_tiles<T, I, M, G, true>, sizeof(DecSmemT<T, I, G>)}
-#define DEC_LEAN(T, I, G) DecConfig{T, G, 1, k_decode_lean<T, I, G>, sizeof(DecSmemT<T, I, G>)}
+#define DEC_CFG(T, I, M, G) DecConfig{T, G, M, G * DEC_IPT, k_decode_tiles<T, I, M, G>, sizeof(DecSmemT<T, I, G>)}
+#define DEC_LANES(T, I, M, G) DecConfig{T, G, M, G * DEC_IPT, k_decode_tiles<T, I, M, G, true>, sizeof(DecSmemT<T, I, G>)}
+#define DEC_LEAN(T, I, G) DecConfig{T, G, 1, G * DEC_IPT, k_decode_lean<T, I, G>, sizeof(DecSmemT<T, I, G>)}
 // (threads, packed-vocabulary entries in shared memory, CTAs per SM, threads per tile group); 0 = default, the others for
 // A/B runs (MBPE_DEC_CFG)
 static const DecConfig dec_configs[] = {DEC_CFG(1024, 24576, 1, 512), DEC_CFG(1024, 24576, 1, 1024), DEC_CFG(1024, 24576, 1, 256),
                                         DEC_CFG(256, 0, 4, 256),       DEC_CFG(512, 12288, 2, 256),
                                         DEC_LANES(1024, 24576, 1, 512), DEC_LANES(1024, 24576, 1, 1024), DEC_LANES(1024, 24576, 1, 256),
                                         DEC_LEAN(1024, 24576, 512),     DEC_LEAN(1024, 24576, 1024),      DEC_LEAN(1024, 24576, 256)};
+constexpr int DEC_DEFAULT_CFG = 8; // k_decode_lean, two groups of 512 threads
 constexpr int N_DEC_CONFIGS = sizeof(dec_configs) / sizeof(dec_configs[0]);
 } // namespace mbpe
 
@@ -935,7 +969,7 @@ static int encoder_create_impl(mbpe_encoder *e, const uint32_t *merges, uint32_t
     const char *cfg_env = getenv("MBPE_ENC_CFG");
     e->cfg = cfg_env && *cfg_env ? std::min(std::max(atoi(cfg_env), 0), N_ENC_CONFIGS - 1) : 0;
     const char *dcfg_env = getenv("MBPE_DEC_CFG");
-    e->dec_cfg = dcfg_env && *dcfg_env ? std::min(std::max(atoi(dcfg_env), 0), N_DEC_CONFIGS - 1) : 0;
+    e->dec_cfg = dcfg_env && *dcfg_env ? std::min(std::max(atoi(dcfg_env), 0), N_DEC_CONFIGS - 1) : DEC_DEFAULT_CFG;
     for (int i = 0; i < N_DEC_CONFIGS; i++)
         MB_CUDA(cudaFuncSetAttribute(dec_configs[i].kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_configs[i].smem));
     for (int i = 0; i < N_ENC_CONFIGS; i++) {
@@ -1495,7 +1529,7 @@ static int decode_launch(mbpe_encoder *e, const uint32_t *d_ids, uint64_t n_ids,
                          unsigned long long *d_n_out, cudaStream_t st) {
     const bool nopack = getenv("MBPE_DEC_NOPACK") != nullptr;
     const DecConfig &dc = dec_configs[nopack ? 3 : e->dec_cfg]; // (configuration 3 keeps no table in shared memory)
-    const uint64_t tile_ids = (uint64_t)dc.group * DEC_IPT;
+    const uint64_t tile_ids = (uint64_t)dc.tile_ids;
     const uint64_t n_tiles = (n_ids + tile_ids - 1) / tile_ids;
     if (n_tiles >= 0xFFFFFFFFull) return set_error(MBPE_E_INVALID, "too many ids in one call");
     int rc = ensure_status(e, n_tiles);

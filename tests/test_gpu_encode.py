@@ -290,3 +290,43 @@ def test_encode_is_the_same_for_every_kernel_shape_and_without_caches(pkg, oracl
         enc.close()
         for k in env:
             monkeypatch.delenv(k)
+
+
+def test_decode_is_the_same_for_every_kernel_shape(pkg, oracle, monkeypatch):
+    """every decode configuration (thread-per-8-ids, lane-per-token, k_decode_lean, no packed table): identical bytes for a
+    stream with tokens of 1..40 bytes, special tokens inside and outside the vocabulary (one of them 3000 bytes long, one
+    with the id 0xFFFFFFFF), unknown ids, and a last tile that is not full"""
+    # a vocabulary with long tokens: chain merges build "abcdefgh..." of up to 40 bytes
+    merges = [[97 + i, 98 + i] for i in range(0, 20, 2)]          # 10 two-byte tokens 256..265
+    merges += [[256 + i, 257 + i] for i in range(0, 10, 2)]      # 5 four-byte tokens 266..270
+    merges += [[266, 267], [268, 269], [271, 272], [273, 270], [274, 274]]  # 8, 8, 16, 20, 40 bytes: 271..275
+    merges = np.asarray(merges, np.uint32)
+    sp = {7: b"SEVEN", 260: b"<two-sixty>", 100257: b"<|endoftext|>", 0xFFFFFFFF: b"<max>", 5000: b"L" * 3000}
+    rng = np.random.default_rng(5)
+    ids = rng.integers(0, 256 + len(merges), 300001).astype(np.uint32)
+    ids[rng.integers(0, len(ids), 3000)] = 100257
+    ids[rng.integers(0, len(ids), 3000)] = 7
+    ids[rng.integers(0, len(ids), 3000)] = 260
+    ids[rng.integers(0, len(ids), 300)] = 0xFFFFFFFF
+    ids[rng.integers(0, len(ids), 30)] = 5000
+    ids[rng.integers(0, len(ids), 3000)] = 4000000   # unknown
+    ids[rng.integers(0, len(ids), 3000)] = 300       # unknown, just past the vocabulary
+    want = oracle.decode(merges, ids[:5000].tolist(), sp)
+    ref = None
+    envs = [{"MBPE_DEC_CFG": str(c)} for c in range(11)] + [{"MBPE_DEC_NOPACK": "1"}]
+    for env in envs:
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        enc = pkg.Encoder(merges)
+        assert enc.decode(ids[:5000]) == oracle.decode(merges, ids[:5000].tolist(), {}), env  # before any special token is set
+        enc.set_specials(sp)
+        assert enc.decode(ids[:5000]) == want, env
+        got = enc.decode(ids)
+        if ref is None:
+            ref = got
+        assert got == ref, env
+        enc.set_specials({})  # and the table forgets them again
+        assert enc.decode(ids[:5000]) == oracle.decode(merges, ids[:5000].tolist(), {}), env
+        enc.close()
+        for k in env:
+            monkeypatch.delenv(k)
