@@ -569,13 +569,13 @@ def main():
         roundtrip = all_true(n_txt == bt0["n_bytes"] and bool(torch.equal(d_txt[:n_txt], bt0["d_bytes"])))
         b_dec = int(sum_over_ranks(4 * bt0["n_ids"] + n_txt))
         dec_bytes = int(sum_over_ranks(n_txt))
-        trd = ncu_traffic("k_decode_tiles")
+        trd = ncu_traffic("k_decode_lean")
         line["decode"] = {
             "metric": "bpe_decode_mb_per_sec", "value": dec_bytes / 1e6 / (dec_ms / 1e3), "unit": "MB/s", "ms_per_step": dec_ms,
             "n_ids": int(sum_over_ranks(bt0["n_ids"])), "bytes_out": dec_bytes, "equals_input_text": roundtrip,
             "roofline": {"bound": "hbm", "achieved": b_dec / 1e9 / (dec_ms / 1e3), "peak": peak * world, "unit": "GB/s",
                          "frac": b_dec / 1e9 / (dec_ms / 1e3) / (peak * world), "traffic": trd["dram_bytes_per_launch"] if trd else None,
-                         "traffic_detail": trd, "peak_source": peak_src, "kernel": "k_decode_tiles",
+                         "traffic_detail": trd, "peak_source": peak_src, "kernel": "k_decode_lean",
                          "algorithmic_bytes_per_step": b_dec},
         }
         first_ids_host = d_out[:bt0["n_ids"]].cpu().numpy().view(np.uint32) if rank == 0 else None

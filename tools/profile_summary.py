@@ -81,7 +81,7 @@ launches()
 traffic = {}
 for rep, kernel, note in (("prof_persistent", "k_persistent", "launch 300 of `bench.py` (1 GiB corpus, vocab 32768, lexical): the resident merge loop between two grid-wide steps"),
                           ("prof_encode", "k_encode_tiles", "tools/enc_ab.py 512 0: first launch of a warm pass over 512 MiB of text = 2^26 chunks (about 306 MiB of text, 141 M ids)"),
-                          ("prof_decode", "k_decode_tiles", "tools/dec_ab.py 1024: one launch = 1 GiB of text, 442 M ids")):
+                          ("prof_decode", "k_decode_lean", "tools/dec_ab.py 1024 (default configuration): one launch = 1 GiB of text, 442 M ids")):
     t = full(rep, kernel, note)
     if t:
         traffic[kernel] = t
