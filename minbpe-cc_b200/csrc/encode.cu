@@ -756,8 +756,13 @@ struct DecConfig {
 static const DecConfig dec_configs[] = {DEC_CFG(1024, 24576, 1, 512), DEC_CFG(1024, 24576, 1, 1024), DEC_CFG(1024, 24576, 1, 256),
                                         DEC_CFG(256, 0, 4, 256),       DEC_CFG(512, 12288, 2, 256),
                                         DEC_LANES(1024, 24576, 1, 512), DEC_LANES(1024, 24576, 1, 1024), DEC_LANES(1024, 24576, 1, 256),
-                                        DEC_LEAN(1024, 24576, 512),     DEC_LEAN(1024, 24576, 1024),      DEC_LEAN(1024, 24576, 256)};
-constexpr int DEC_DEFAULT_CFG = 8; // k_decode_lean, two groups of 512 threads
+                                        DEC_LEAN(1024, 24576, 512),     DEC_LEAN(1024, 24576, 1024),      DEC_LEAN(1024, 24576, 256),
+                                        DEC_LEAN(1024, 20480, 512),     DEC_LEAN(1024, 16384, 512),       DEC_LEAN(1024, 12288, 512),
+                                        DEC_LEAN(1024, 8192, 512),      DEC_LEAN(1024, 16384, 256)};
+// 0-4 k_decode_tiles, 5-7 its lane-per-token variant, 8-15 k_decode_lean. Default: 16384 table words in shared memory and four
+// groups of 256 threads -- a smaller table leaves L1 to the ids and to the global half of the table (2.79 -> 2.70 ms per GiB
+// from 24576 to 20480 words, flat down to 8192), and with it four groups beat two (2.67).
+constexpr int DEC_DEFAULT_CFG = 15;
 constexpr int N_DEC_CONFIGS = sizeof(dec_configs) / sizeof(dec_configs[0]);
 } // namespace mbpe
 

@@ -313,7 +313,7 @@ def test_decode_is_the_same_for_every_kernel_shape(pkg, oracle, monkeypatch):
     ids[rng.integers(0, len(ids), 3000)] = 300       # unknown, just past the vocabulary
     want = oracle.decode(merges, ids[:5000].tolist(), sp)
     ref = None
-    envs = [{"MBPE_DEC_CFG": str(c)} for c in range(11)] + [{"MBPE_DEC_NOPACK": "1"}]
+    envs = [{"MBPE_DEC_CFG": str(c)} for c in range(16)] + [{"MBPE_DEC_NOPACK": "1"}]
     for env in envs:
         for k, v in env.items():
             monkeypatch.setenv(k, v)
