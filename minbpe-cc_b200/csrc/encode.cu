@@ -1223,6 +1223,8 @@ static int encode_device_impl(mbpe_encoder *e, const uint8_t *d_bytes, uint64_t 
     a.bulk = ((((uintptr_t)d_bytes) | ((uintptr_t)d_off)) & 15) == 0 && !getenv("MBPE_ENC_NO_BULK");
     a.out_aligned = (((uintptr_t)d_out) & 15) == 0;
     if (const char *ab = getenv("MBPE_ENC_ABLATE")) a.ablate = (uint32_t)atoi(ab);
+    if (const char *pf = getenv("MBPE_ENC_PF")) a.pf_ahead = (uint32_t)atoi(pf);
+    if (a.pf_ahead == 1) a.pf_ahead = (uint32_t)(e->sms * enc_configs[e->cfg].ctas); // one round of tickets
     a.hot_img = e->d_hot_img;
     uint32_t small[4] = {0, 0, 0, 0};
     // First launch sequence is optimistic: no chunk is longer than ENC_SHORT_MAX bytes (true for the regex patterns on

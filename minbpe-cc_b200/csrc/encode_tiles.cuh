@@ -263,6 +263,7 @@ struct EncArgs {
     uint32_t out_aligned;        // out is 16-byte aligned: ids leave as 16-byte stores
     unsigned long long *prof;    // optional: SM cycles per phase summed over CTAs (thread 0's clock), see ENC_PROF_*
     const uint4 *hot_img;        // k_encode_hot: image of the shared-memory table of the hottest chunks (encode_hot.cuh)
+    uint32_t pf_ahead;           // MBPE_ENC_PF: the boundaries (exact) and the text (estimated) of the tile this many tickets ahead are asked into L2
     uint32_t ablate;             // MBPE_ENC_ABLATE (profiling only, WRONG results): 1 no look-back wait, 2 no cache probe
                                  // (every short chunk "hits" with two fake ids), 4 no id stores
 };
@@ -310,7 +311,7 @@ struct EncSmemT {
     uint32_t warp_sum[THREADS / 32];
     alignas(8) uint64_t bar_off, bar_tile; // mbarriers: boundaries landed (thread 0 only waits), tile ready (all wait)
     unsigned long long base;
-    uint32_t tile, a0, staged, n_open, park_used;
+    uint32_t tile, a0, staged, n_open, park_used, off_span;
     unsigned long long prof[ENC_PROF_N];
 };
 
@@ -602,6 +603,7 @@ __device__ __forceinline__ void fetch_tile_bulk(const EncArgs &a, SM &sm, uint32
     sm.tile = t;
     sm.a0 = a0;
     sm.staged = staged;
+    sm.off_span = span;
     if (staged) {
         // whole vectors that lie inside the buffer by bulk copy, the last (< 16) bytes of the buffer by hand
         const uint64_t avail = (a.n_bytes_total - a0) & ~15ull;
@@ -909,6 +911,20 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_encode_tiles(const __grid
             fetch_tile_bulk(a, sm, off_parity);
         }
         lap(5);
+        if (a.pf_ahead && bulk) {
+            // One round of tickets from now some CTA fetches tile `tile + pf_ahead`: its boundaries are at a known place, its
+            // text about pf_ahead tiles of this tile's size further on (a window of 16 KiB around the estimate). Asking L2 for
+            // them now turns the two dependent HBM round trips of fetch_tile_bulk into L2 round trips.
+            const uint64_t ca = a.chunk0 + ((uint64_t)tile + a.pf_ahead) * TILE;
+            if (ca < a.chunk1) {
+                if (tid < TILE / 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.off + min(ca + tid * 32, a.chunk1)));
+                if (tid >= 64 && tid < 64 + 128) {
+                    const uint64_t span = (uint64_t)sm.off_span, est = (uint64_t)a0 + span * a.pf_ahead + span / 2;
+                    const uint64_t g = (est > 8192 ? est - 8192 : 0) + (uint64_t)(tid - 64) * 128;
+                    if (g < a.n_bytes_total) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.bytes + g));
+                }
+            }
+        }
         if (a.out_off) {
 #pragma unroll
             for (int j = 0; j < CPT; j++) {
