@@ -74,8 +74,8 @@ __device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
 
 // get_top_pair_count for the resident CTA: same result as sel_max .. sel_commit, but each candidate's slot is
 // fetched once (one 16-byte load: key, cnt, len) and kept in registers across the three reductions.
-struct PersistSmem;
-__device__ __forceinline__ void fused_select(const Ctx &c, PersistSmem *red) {
+template <class SMEM> // PersistSmem / ShardSmem: only red_max, red_live, red_tie are touched (mirror path)
+__device__ __forceinline__ void fused_select(const Ctx &c, SMEM *red) {
     Ctl *g = c.ctl; // shared memory
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t n = g->n_cand;
@@ -450,6 +450,16 @@ struct ShardSmem {
     uint32_t rec_pos[PS_REC];
     uint32_t cand[PS_SEL * PERSISTENT_THREADS];
     uint32_t counts[XCH_MAX_WORLD];
+    // LEXICAL mode: the candidate mirror of k_persistent (see PersistSmem); the other ranks' records update it in
+    // phase_apply_foreign through Slot::pad, like this rank's own decrements do
+    int32_t ccnt[PS_SEL * PERSISTENT_THREADS];
+    uint32_t cfirst[PS_SEL * PERSISTENT_THREADS];
+    uint32_t clen[PS_SEL * PERSISTENT_THREADS];
+    uint32_t cseg[PS_SEL * PERSISTENT_THREADS];
+    uint64_t ckey[PS_SEL * PERSISTENT_THREADS];
+    int32_t red_max[PERSISTENT_THREADS / 32];
+    uint32_t red_live[PERSISTENT_THREADS / 32];
+    uint64_t red_tie[PERSISTENT_THREADS / 32];
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
@@ -517,7 +527,7 @@ __global__ void __launch_bounds__(PERSISTENT_THREADS, 1) k_persistent_sharded(co
     __syncthreads();
     Ctx c = cg;
     c.ctl = &sm->ctl;
-    c.m_cnt = nullptr; // no candidate mirror: counts also change through the other ranks' records
+    c.m_cnt = nullptr;
     c.m_cap = 0;
     Ctl *g = &sm->ctl;
     const uint32_t n_cand_in = g->n_cand;
@@ -527,13 +537,33 @@ __global__ void __launch_bounds__(PERSISTENT_THREADS, 1) k_persistent_sharded(co
         c.cand = sm->cand;
         c.cand_cap = PS_SEL * PERSISTENT_THREADS; // appends past it are dropped and phase_fin asks for a rebuild
         __syncthreads();
+        if (g->mode == 1 && cg.m_cap) { // LEXICAL (m_cap != 0: the host allows it): mirror the candidates' slots, as k_persistent does
+            for (uint32_t i = tid; i < n_cand_in; i += PERSISTENT_THREADS) {
+                const uint32_t s = sm->cand[i];
+                const uint4 *sp = reinterpret_cast<const uint4 *>(&cg.slot[s]);
+                const uint4 head = __ldcg(sp), tail = __ldcg(sp + 1); // {key.lo, key.hi, cnt, len} {first, seg, fill, pad}
+                sm->ccnt[i] = (int32_t)head.z;
+                sm->cfirst[i] = tail.x;
+                sm->ckey[i] = ((uint64_t)head.y << 32) | head.x;
+                sm->clen[i] = head.w;
+                sm->cseg[i] = tail.y;
+                if (tail.w != i + 1) cg.slot[s].pad = i + 1;
+            }
+            c.m_cnt = sm->ccnt;
+            c.m_first = sm->cfirst;
+            c.m_key = sm->ckey;
+            c.m_len = sm->clen;
+            c.m_seg = sm->cseg;
+            c.m_cap = PS_SEL * PERSISTENT_THREADS;
+            __syncthreads();
+        }
     }
     const long long t_enter = clock64();
     for (;;) {
         if (g->status != ST_RUN) break;
         if (g->selected == 0) {
             if (g->mode == 1) {
-                fused_select(c, nullptr); // LEXICAL: a function of the replicated table only
+                fused_select(c, sm); // LEXICAL: a function of the replicated table only
             } else { // FIRST: a tied pair that lost its first occurrence needs the minimum over ALL ranks' occurrences
                 phase_sel_max<true>(c, tid, PERSISTENT_THREADS);
                 __syncthreads();
@@ -735,7 +765,10 @@ struct CudaBE {
         if (err != cudaSuccess) return;
         note(cudaFuncSetAttribute(k_persistent_sharded, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ShardSmem)),
              "smem attr");
-        k_persistent_sharded<<<1, PERSISTENT_THREADS, sizeof(ShardSmem), stream>>>(c, *links);
+        Ctx cl = c;
+        static const bool no_mirror = getenv("MBPE_NO_CAND_MIRROR") != nullptr || getenv("MBPE_NO_SHARD_MIRROR") != nullptr;
+        cl.m_cap = no_mirror ? 0 : 1; // request the shared-memory candidate mirror (lexical mode; the kernel sets the real capacity)
+        k_persistent_sharded<<<1, PERSISTENT_THREADS, sizeof(ShardSmem), stream>>>(cl, *links);
         n_launch++;
         note(cudaGetLastError(), "k_persistent_sharded launch");
     }

@@ -1106,7 +1106,14 @@ MB_HD void phase_apply_foreign(const Ctx &c, const XRec *all, const uint32_t *co
                 c.newp[a_add(&g->n_newp, 1u)] = s; // gets an (empty) segment and a candidate check like local births
                 a_min(&g->min_key_ever, x.key);
             }
-            if (x.delta) a_add(&c.slot[s].cnt, x.delta);
+            if (x.delta) {
+                a_add(&c.slot[s].cnt, x.delta);
+                if (c.m_cnt) { // resident CTA with the candidate mirror: the count it selects from follows (Slot::pad = place + 1)
+                    uint32_t ci = ld_l2(&c.slot[s].pad);
+                    if (ci > c.m_cap) ci = 0;
+                    if (ci) a_add(&c.m_cnt[ci - 1], x.delta);
+                }
+            }
             if (mode == 0) {
                 if (x.delta >= 0) // birth, or (delta == 0) a rank's recomputed first live occurrence
                     a_min(&c.slot[s].first, x.pos);
