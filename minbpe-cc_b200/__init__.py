@@ -409,6 +409,10 @@ class Encoder:
         view of it -- no allocation, no first-touch page faults and no copy inside the call"""
         off = np.ascontiguousarray(chunk_off, np.uint64)
         if out is not None:
+            if want_off:
+                raise ValueError("out= and want_off=True are mutually exclusive")
+            if out.dtype != np.uint32 or not out.flags["C_CONTIGUOUS"]:
+                raise ValueError("out must be a C-contiguous uint32 array")
             n = C.c_uint64()
             _ck(lib().mbpe_encode(self.h, _p(_u8(data), C.c_uint8), C.c_uint64(len(data)), _p(off, C.c_uint64),
                                   C.c_uint64(len(off) - 1), _p(out, C.c_uint32), C.c_uint64(len(out)), C.byref(n), None))
