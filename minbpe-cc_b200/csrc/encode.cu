@@ -563,7 +563,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_decode_lean(const __grid_constan
             id[j] = nxt[j]; // (loaded while the previous tile was being stored)
             pk[j] = cta.tab[min(id[j], tab_n - 1)];
             if (id[j] >= tab_n) pk[j] = id[j] < vocab ? __ldg(&a.v_lean[id[j]]) : dec_lean_outside(a, id[j]);
-            if (have != 0xFFu && !((have >> j) & 1u)) pk[j] = 0ull;
+        }
+        if (have != 0xFFu) { // the stream's last tile only
+#pragma unroll
+            for (int j = 0; j < DEC_IPT; j++)
+                if (!((have >> j) & 1u)) pk[j] = 0ull;
+        }
+#pragma unroll
+        for (int j = 0; j < DEC_IPT; j++) {
             const uint32_t b0 = (uint32_t)pk[j] & 0xFFu;
             len[j] = b0 & 0x7Fu;
             odd = odd || b0 == 0xFFu;
@@ -635,17 +642,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_decode_lean(const __grid_constan
                 const uint32_t b0 = (uint32_t)pk[j] & 0xFFu;
                 const bool plain = b0 != 0xFFu;          // the first min(l, 7) bytes are in the table word
                 const bool tail = plain && l > 7;          // bytes 7.. come from the second table (8..15) / the index (more)
-                const bool any4 = __any_sync(0xffffffffu, plain && l > 3), any_tail = __any_sync(0xffffffffu, tail || !plain);
-                if (plain) {
+                const bool any_tail = __any_sync(0xffffffffu, tail || !plain);
+                if (plain) { // (some lane of 32 nearly always has more than 3 bytes: no vote to skip bytes 3..6)
                     if (l > 0) d[0] = (uint8_t)lo;
                     if (l > 1) d[1] = (uint8_t)(lo >> 8);
                     if (l > 2) d[2] = (uint8_t)(lo >> 16);
-                    if (any4) {
-                        if (l > 3) d[3] = (uint8_t)(lo >> 24);
-                        if (l > 4) d[4] = (uint8_t)hi;
-                        if (l > 5) d[5] = (uint8_t)(hi >> 8);
-                        if (l > 6) d[6] = (uint8_t)(hi >> 16);
-                    }
+                    if (l > 3) d[3] = (uint8_t)(lo >> 24);
+                    if (l > 4) d[4] = (uint8_t)hi;
+                    if (l > 5) d[5] = (uint8_t)(hi >> 8);
+                    if (l > 6) d[6] = (uint8_t)(hi >> 16);
                 }
                 if (any_tail) {
                     if (tail) {
