@@ -662,19 +662,28 @@ def main():
         pin5 = torch.empty(len(text5), dtype=torch.uint8, pin_memory=True)
         pin5.numpy()[:] = text5
         del text5
-        times5 = []
+        times5, err5 = [], None
         for i in range(2):  # first call sizes the resident buffers
             barrier()
             t0 = time.time()
-            if world == 1:
-                tk.train(pin5.numpy(), a.config5_vocab, a.mode)
-                m5 = tk.merges()
-                st5 = tk.last_train_stats()
-            else:
-                m5, c5, st5 = comm.train_text(pin5.numpy(), a.config5_vocab, a.mode)
+            try:
+                if world == 1:
+                    tk.train(pin5.numpy(), a.config5_vocab, a.mode)
+                    m5 = tk.merges()
+                    st5 = tk.last_train_stats()
+                else:
+                    m5, c5, st5 = comm.train_text(pin5.numpy(), a.config5_vocab, a.mode)
+            except Exception as ex:  # (the headline legs above must not be lost to this one)
+                err5 = f"{type(ex).__name__}: {ex}"
             torch.cuda.synchronize()
+            if not all_true(err5 is None):
+                err5 = err5 or "failed on another rank"
+                break
             barrier()
             times5.append(time.time() - t0)
+        if err5 is not None:
+            line["config5"] = {"error": err5}
+            m5, st5, times5 = np.zeros((0, 2), np.uint32), {}, [float("nan")]
         s5 = max_over_ranks(times5[-1])
         leg5 = {"workload": f"BASELINE config 5: train {a.config5_gib} GiB synthetic corpus (seed 0x{SEED_CONFIG5:X}), --vocab-size "
                             f"{a.config5_vocab} gpt4 -c {a.mode}, text sharded over {world} GPU(s) in pinned host memory",
@@ -689,7 +698,8 @@ def main():
             h0 = h.clone()
             dist.broadcast(h0, 0)
             leg5["same_merges_on_every_rank"] = all_true(bool((h == h0).all()))
-        line["config5"] = leg5
+        if err5 is None:
+            line["config5"] = leg5
         del pin5
 
     # ---------------- CPU baseline (rank 0, N == 1 only): the compiled reference on bounded samples --------------------
